@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Headline benchmark: heatmaps/sec of the SBP hot path (render + loss + grad + decode) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port), host cores
+
+One "step" = one pass of the hot path over one synthetic batch (BASELINE.json configs[1]: B=4096 per GPU,
+K=17, 64x48 fp32 heat maps, sigma 2, 256x192 input): fused render+loss+grad+decode kernel, back-projection /
+COCO-row kernel and, for N>1, the loss all-reduce and prediction all-gather (NCCL).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, H, W, SIGMA, IN_H, IN_W, THR = 17, 64, 48, 2, 256, 192, 0.25
+BYTES_FUSED = 24596          # algorithmic bytes per heat map, full pipeline with logits read once (SURVEY.md 8 d, row C)
+METRIC, UNIT = "heatmaps_per_sec", "heatmaps/s"
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("sbp_fused_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                     "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._once()
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        if self.nv:
+            self._once()
+            self._stop.set()
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_reference_pass(sample):
+    """The reference's CPU algorithm on `sample` images: per-sample render loop -> SBPLoss fwd+bwd -> per-sample
+    decode loop -> back-projection + COCO rows (utils/sbp_utils.py:33-53, :103-118, :131-164; models/loss/sbp_loss.py)."""
+    import numpy as np
+    import torch
+    from oracle import sbp_oracle as so
+    kp, logits, bbox, iid, cid = sample
+    n = logits.size(0)
+    target = torch.from_numpy(np.stack([so.sbp_render_loop(kp[b], H, W, SIGMA) for b in range(n)]))
+    x = logits.detach().clone().requires_grad_(True)
+    loss = so.sbp_loss(x, target)
+    loss.backward()
+    joints = torch.stack([so.sbp_decode_loop(logits[b:b + 1], IN_W, THR, True) for b in range(n)])
+    rows = so.sbp_result_rows(so.sbp_backproject(joints, bbox, (IN_H, IN_W)), iid, cid)
+    return float(loss.detach()), len(rows)
+
+
+def make_cpu_sample(n):
+    from oracle import sbp_oracle as so
+    return so.make_config1_inputs(n, K, H, W)
+
+
+def run_reference(args):
+    """--impl reference: rank 0 times the oracle port (the reference is pure Python and cannot travel to the GPU box;
+    its CPU algorithm is restated in oracle/, pinned to it by tests/golden)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = args.ref_sample
+    sample = make_cpu_sample(n)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_reference_pass(sample)
+    t0 = time.perf_counter()
+    steps = max(1, min(args.steps, 20))
+    for _ in range(steps):
+        cpu_reference_pass(sample)
+    dt = (time.perf_counter() - t0) / steps
+    value = n * K / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SBP 256x192: {K}x{H}x{W} heat maps, sigma {SIGMA}: render + JointsMSE fwd/bwd + decode + "
+                               f"back-projection; bounded sample of {n} images per step (of the B=4096 workload)",
+                   "batch_per_step": n, "threads": torch.get_num_threads()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} images x {steps} steps, oracle port of the reference's per-sample Python loops, "
+                                   f"torch {torch.get_num_threads()} threads for the loss"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- CUDA arm
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    import pose_b200 as pb
+    from pose_b200 import dist as pd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: pose_b200 has no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pb.lib()
+
+    B = args.batch
+    global_batch = B * world
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    logits = torch.randn(B, K, H, W, device=dev, generator=gen) * 3.0
+    kp = torch.stack([torch.rand(B, K, device=dev, generator=gen, dtype=torch.float64) * W,
+                      torch.rand(B, K, device=dev, generator=gen, dtype=torch.float64) * H], dim=-1)
+    kp[torch.rand(B, K, device=dev, generator=gen) >= 0.85] = -1.0
+    bbox = torch.stack([torch.rand(B, device=dev, generator=gen, dtype=torch.float64) * 400,
+                        torch.rand(B, device=dev, generator=gen, dtype=torch.float64) * 400,
+                        torch.rand(B, device=dev, generator=gen, dtype=torch.float64) * 260 + 40,
+                        torch.rand(B, device=dev, generator=gen, dtype=torch.float64) * 340 + 60], dim=-1)
+    image_id = torch.arange(B, device=dev, dtype=torch.int64) + rank * B
+    category_id = torch.ones(B, device=dev, dtype=torch.int64)
+
+    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def step(i=None):
+        if i is not None:
+            ev_k0[i].record()
+        r = pb.sbp_fused(logits, keypoints=kp, sigma=SIGMA, want_grad=True, decode=True, conf_threshold=THR,
+                         coord_scale=IN_W / W, global_batch=global_batch)
+        if i is not None:
+            ev_k1[i].record()
+        rows, score = pb.backproject_rows(r["joints"], bbox, (IN_H, IN_W))
+        loss = pd.global_sbp_loss(r["loss_num"], K, global_batch)
+        rows, score, ids, cats = pd.gather_rows(rows, score, image_id, category_id)
+        return loss, rows, score
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    fence()
+    launches0 = pb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        fence()
+        e0.record()
+        for i in range(args.steps):
+            out = step(i)
+        e1.record()
+        fence()
+    launches = pb.launch_count() - launches0
+    ms = e0.elapsed_time(e1) / args.steps
+    kern_ms = sum(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = global_batch * K / (ms * 1e-3)
+
+    # ---- e2e: the same step through the public API from pinned HOST buffers, result back on the host
+    h_logits = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True).copy_(logits)
+    h_kp = torch.empty(kp.shape, dtype=kp.dtype, pin_memory=True).copy_(kp)
+    h_bbox = torch.empty(bbox.shape, dtype=bbox.dtype, pin_memory=True).copy_(bbox)
+    h_rows = torch.empty((global_batch, K, 3), dtype=torch.float32, pin_memory=True)
+    h_score = torch.empty((global_batch,), dtype=torch.float32, pin_memory=True)
+    h_loss = torch.empty((), dtype=torch.float32, pin_memory=True)
+    d_logits, d_kp, d_bbox = torch.empty_like(logits), torch.empty_like(kp), torch.empty_like(bbox)
+
+    def e2e_step():
+        d_logits.copy_(h_logits, non_blocking=True)
+        d_kp.copy_(h_kp, non_blocking=True)
+        d_bbox.copy_(h_bbox, non_blocking=True)
+        r = pb.sbp_fused(d_logits, keypoints=d_kp, sigma=SIGMA, want_grad=True, decode=True, conf_threshold=THR,
+                         coord_scale=IN_W / W, global_batch=global_batch)
+        rows, score = pb.backproject_rows(r["joints"], d_bbox, (IN_H, IN_W))
+        loss = pd.global_sbp_loss(r["loss_num"], K, global_batch)
+        rows, score, ids, cats = pd.gather_rows(rows, score, image_id, category_id)
+        h_rows.copy_(rows, non_blocking=True)
+        h_score.copy_(score, non_blocking=True)
+        h_loss.copy_(loss, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        e2e_step()
+    fence()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record()
+    fence()
+    e2e_ms = f0.elapsed_time(f1) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = h_logits.numel() * 4 + h_kp.numel() * 8 + h_bbox.numel() * 8
+    d2h = h_rows.numel() * 4 + h_score.numel() * 4 + 4
+    loss_host = float(h_loss)
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        achieved = BYTES_FUSED * B * K / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"SBP 256x192 (configs[1]): B={B} per GPU x {K} joints x {H}x{W} fp32 heat maps, sigma {SIGMA}; "
+                                   "fused render+loss+grad+decode + back-projection"
+                                   + ("; NCCL loss all-reduce + prediction all-gather" if world > 1 else ""),
+                       "batch_per_gpu": B, "global_batch": global_batch, "partition": f"images x{world}",
+                       "l2": "inputs (856 MB logits per GPU) larger than the 126 MB L2; no explicit flush",
+                       "kp_dtype": "f64", "loss": loss_host},
+            "roofline": {"bound": "hbm", "kernel": "sbp_fused_kernel<4,RENDER,GRAD,DECODE> (+ 1-CTA finalize)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(), "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": BYTES_FUSED * B * K},
+            "e2e": {"value": global_batch * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clk.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sample = make_cpu_sample(args.ref_sample)
+            cpu_reference_pass(sample)
+            best = None
+            t_start = time.perf_counter()
+            passes = 0
+            while passes < 3 or (time.perf_counter() - t_start < 10.0 and passes < 40):
+                t0 = time.perf_counter()
+                cpu_reference_pass(sample)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+                passes += 1
+            line["cpu_baseline"] = {"value": args.ref_sample * K / best, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.ref_sample} images of the same workload, best of {passes} passes; oracle port of "
+                                              f"the reference's per-sample loops (render, decode single-threaded Python; loss on "
+                                              f"{torch.get_num_threads()} torch threads)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="images per GPU")
+    ap.add_argument("--ref-sample", type=int, default=64, help="images per CPU-baseline pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

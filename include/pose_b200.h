@@ -1,0 +1,146 @@
+/*
+ * pose_b200.h -- C ABI of the B200-native heatmap hot path (render -> loss -> decode).
+ *
+ * Drop-in boundary for the hot path of myungsanglee/PyTorch-Pose-Estimation.  The reference has
+ * no FFI of its own (it is pure Python); each entry point below names the reference function it
+ * replaces (file:line in the reference tree).  The Python side (pose_b200/_cabi.py) binds these
+ * with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions for every compute entry point:
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*); no allocation, no host
+ *     synchronisation, no global mutable state (thread-safe; one library shared by all ranks);
+ *   - the caller owns all memory, including workspaces (sizes from the *_workspace_bytes calls);
+ *   - returns 0 on success, <0 for a bad argument (POSE_E*), >0 a cudaError_t from a launch;
+ *     pose_b200_last_error() gives a thread-local message for the last non-zero return;
+ *   - tensors are dense, C-contiguous, fp32 unless stated; maps are [N][K][H][W].
+ */
+#ifndef POSE_B200_H
+#define POSE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POSE_OK 0
+#define POSE_EINVAL (-1)      /* bad shape / null pointer / unsupported parameter */
+#define POSE_EALIGN (-2)      /* pointer not aligned as required                   */
+#define POSE_EWORKSPACE (-3)  /* workspace too small                               */
+
+/* kp_dtype values */
+#define POSE_KP_F32 0
+#define POSE_KP_F64 1
+
+/* flags for pose_sbp_fused */
+#define POSE_F_GRAD 1u          /* write dlogits                                   */
+#define POSE_F_TARGET_OUT 2u    /* also materialise the rendered target (render mode only) */
+#define POSE_F_DECODE 4u        /* also decode joints from sigmoid(logits) in the same pass */
+
+/* decode modes */
+#define POSE_DECODE_DIRECT 0    /* activation on every element, argmax on activated values */
+#define POSE_DECODE_INTERVAL 1  /* max logit first, then first index inside the activation's pre-image of the max */
+
+typedef void* pose_stream_t;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int pose_b200_version(void);
+const char* pose_b200_last_error(void);
+/* kernels launched by this library since load (statistics only; relaxed atomic) */
+unsigned long long pose_b200_launch_count(void);
+
+/* ---- Gaussian template (host) -- SBPHeatmapGenerator.__init__ utils/sbp_utils.py:21-31,
+ *      SPMHeatmapGenerator.__init__ utils/spm_utils.py:17-27.
+ * Writes n*n fp32 values (n = number of samples of arange(0, 6*sigma+3)) row-major to out_host,
+ * computed in double and rounded once to fp32.  Returns n, or POSE_EINVAL if capacity < n*n. */
+int pose_gauss_template_host(double sigma, float* out_host, int capacity);
+
+/* ---- SBP render -- SBPHeatmapGenerator.__call__ utils/sbp_utils.py:33-53, batched.
+ * kp [N][K][2] (x, y) in heat-map pixels, fp32 or fp64 (kp_dtype); x<0 or y<0 = invisible.
+ * lut: device copy of the n*n template.  target [N][K][H][W] is fully overwritten. */
+int pose_sbp_render(const void* kp, int kp_dtype, float* target, int N, int K, int H, int W,
+                    double sigma, const float* lut, int lut_n, pose_stream_t stream);
+
+/* ---- SBP loss (+grad, +render, +decode) in one pass --
+ *      SBPLoss.forward/encode_target models/loss/sbp_loss.py:20-66 (+ autograd backward),
+ *      SBPHeatmapGenerator.__call__ utils/sbp_utils.py:33-53 when kp != NULL,
+ *      DecodeSBP.forward/nms_sbp utils/sbp_utils.py:56-118 when POSE_F_DECODE.
+ * Exactly one of `target_in` (dense target, [N][K][H][W]) or `kp` (keypoints, rendered in
+ * registers) must be non-NULL.
+ *   loss      = (lambda_pos * S_pos + lambda_neg * S_neg) * inv_norm,    inv_norm = 1/(2*K*B_global)
+ *   dlogits   = dloss/dlogits (scaled by inv_norm; written iff POSE_F_GRAD)
+ *   loss_out  [1] fp32; loss_num_out [2] fp64 = (S_pos, S_neg) un-normalised (may be NULL)
+ *   joints    [N][K][3] fp32 (x*scale, y*scale, conf) / (-scale,-scale,-1)   iff POSE_F_DECODE
+ * workspace: pose_sbp_fused_workspace_bytes(); contents need no initialisation. */
+unsigned long long pose_sbp_fused_workspace_bytes(void);
+int pose_sbp_fused(const float* logits, const float* target_in,
+                   const void* kp, int kp_dtype, double sigma, const float* lut, int lut_n,
+                   float* dlogits, float* target_out,
+                   float* loss_out, double* loss_num_out,
+                   float* joints, float conf_threshold, float coord_scale,
+                   int N, int K, int H, int W,
+                   float lambda_pos, float lambda_neg, double inv_norm,
+                   unsigned flags, void* workspace, unsigned long long workspace_bytes,
+                   pose_stream_t stream);
+
+/* ---- in-place dlogits *= *grad_output (device scalar), skipped in-kernel when it is 1.0f --
+ *      autograd backward of the 0-dim loss (module/sbp_detector.py:24-28 -> loss.backward()). */
+int pose_scale_grad(float* dlogits, const float* grad_output, unsigned long long n, pose_stream_t stream);
+
+/* ---- SBP decode -- nms_sbp utils/sbp_utils.py:56-82 + DecodeSBP.forward :103-118, batched.
+ * x [N][K][H][W]; joints [N][K][3].  apply_sigmoid = DecodeSBP.pred.  Both coordinates are
+ * multiplied by coord_scale (= input_w / W, :116), undetected rows are (-1,-1,-1)*scale on x,y.
+ * refine != 0 adds the quarter-pixel shift (NOT in the reference; off by default). */
+int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W,
+                    float conf_threshold, int apply_sigmoid, float coord_scale,
+                    int refine, int mode, pose_stream_t stream);
+
+/* ---- back-projection + COCO row fields -- SBPmAPCOCO.update_state utils/sbp_utils.py:141-163,
+ *      SBPmAPPIS.update_state utils/sbp_pis_utils.py:23-45.
+ * joints [N][K][3] (input-size scale, from decode); bbox [N][4] fp64 (x, y, w, h).
+ * rows_out [N][K][3]: (x_img, y_img, 1) for detected joints, (0,0,0) otherwise;
+ * score_out [N]: left-to-right fp32 sum of detected confidences / K. */
+int pose_sbp_backproject(const float* joints, const double* bbox, float* rows_out, float* score_out,
+                         int N, int K, int input_h, int input_w, pose_stream_t stream);
+
+/* ---- SPM render -- SPMHeatmapGenerator/MaskGenerator/DisplacementGenerator
+ *      utils/spm_utils.py:16-95 + concat dataset/spm_coco_dataset.py:77-86, batched.
+ * centers [N][Pmax][2] int64, joints [N][Pmax][K][2] int64, counts [N] int32 (persons per image).
+ * target [N][1+2K][R][R] fully overwritten. */
+int pose_spm_render(const long long* centers, const long long* joints, const int* counts,
+                    float* target, int N, int Pmax, int K, int R, double sigma,
+                    const float* lut, int lut_n, pose_stream_t stream);
+
+/* ---- SPM loss fwd(+bwd) -- SPMLoss.forward models/loss/spm_loss.py:23-105.
+ * logits/target/dlogits [N][1+2K][R][R]; loss = (lambda_root*S_root + lambda_disp*S_disp)*inv_norm,
+ * inv_norm = 1/B_global.  loss_num_out [2] fp64 = (S_root, S_disp). */
+unsigned long long pose_spm_loss_workspace_bytes(void);
+int pose_spm_loss(const float* logits, const float* target, float* dlogits,
+                  float* loss_out, double* loss_num_out, int N, int K, int R,
+                  float lambda_root, float lambda_disp, double inv_norm, int write_grad,
+                  void* workspace, unsigned long long workspace_bytes, pose_stream_t stream);
+
+/* ---- SPM decode -- nms_spm :98-161, get_spm_keypoints :164-200, DecodeSPM.forward :225-250.
+ * x [N][1+2K][R][R]; roots [N][Pmax][3], kps [N][Pmax][K][3], counts [N] (roots found, capped at
+ * Pmax; total found incl. overflow in counts_total if non-NULL).  Ties between equal root
+ * confidences break row-major (the reference's order is undefined there).
+ * workspace: pose_spm_decode_workspace_bytes(N, R). */
+unsigned long long pose_spm_decode_workspace_bytes(int N, int R);
+int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* counts_total,
+                    int N, int Pmax, int K, int R, float conf_threshold, double dist_threshold,
+                    int apply_act, float input_size, void* workspace, unsigned long long workspace_bytes,
+                    pose_stream_t stream);
+
+/* ---- SPM joint gather -- get_spm_keypoints utils/spm_utils.py:164-200 (no rescale).
+ * roots [n][3] (x, y, conf) in map pixels, disp [2K][R][R] (already activated) -> kps [n][K][3]. */
+int pose_spm_gather(const float* roots, const float* disp, float* kps, int n_roots, int K, int R,
+                    double dist_threshold, pose_stream_t stream);
+
+/* ---- diagnostics -- exhaustive check that the device sigmoid used by decode is monotone
+ * non-decreasing over all finite fp32 inputs (the INTERVAL decode mode relies on it).
+ * violations_out [1] uint64 on device, zeroed by the call. */
+int pose_sigmoid_monotone_check(unsigned long long* violations_out, pose_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSE_B200_H */

@@ -1,0 +1,110 @@
+"""ctypes binding of libpose_b200.so (include/pose_b200.h).  No CPU fallback: a missing library or a
+non-CUDA tensor is an error."""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpose_b200.so")
+
+KP_F32, KP_F64 = 0, 1
+F_GRAD, F_TARGET_OUT, F_DECODE = 1, 2, 4
+DECODE_DIRECT, DECODE_INTERVAL = 0, 1
+
+_c = ctypes
+_vp, _i, _u, _f, _d, _ull = _c.c_void_p, _c.c_int, _c.c_uint, _c.c_float, _c.c_double, _c.c_ulonglong
+
+# name -> (restype, argtypes); mirrors include/pose_b200.h one to one
+SIGNATURES = {
+    "pose_b200_version": (_i, []),
+    "pose_b200_last_error": (_c.c_char_p, []),
+    "pose_b200_launch_count": (_ull, []),
+    "pose_gauss_template_host": (_i, [_d, _vp, _i]),
+    "pose_sbp_render": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp]),
+    "pose_sbp_fused_workspace_bytes": (_ull, []),
+    "pose_sbp_fused": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f,
+                            _i, _i, _i, _i, _f, _f, _d, _u, _vp, _ull, _vp]),
+    "pose_scale_grad": (_i, [_vp, _vp, _ull, _vp]),
+    "pose_sbp_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _f, _i, _i, _vp]),
+    "pose_sbp_backproject": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pose_spm_render": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp]),
+    "pose_spm_loss_workspace_bytes": (_ull, []),
+    "pose_spm_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _d, _i, _vp, _ull, _vp]),
+    "pose_spm_decode_workspace_bytes": (_ull, [_i, _i]),
+    "pose_spm_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _d, _i, _f, _vp, _ull, _vp]),
+    "pose_spm_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp]),
+    "pose_sigmoid_monotone_check": (_i, [_vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class PoseB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded C-ABI library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise PoseB200Error(
+                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a).  pose_b200 has no CPU or PyTorch fallback.")
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype, fn.argtypes = res, args
+                _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().pose_b200_last_error().decode(errors="replace")
+        raise PoseB200Error(f"{what or 'pose_b200'} failed (rc={rc}): {msg}")
+
+
+def launch_count():
+    return int(lib().pose_b200_launch_count())
+
+
+def require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise PoseB200Error(f"{name} must be a CUDA tensor: pose_b200 runs only its sm_100a kernels (no CPU fallback)")
+    return t
+
+
+def dense(t, name, dtype=torch.float32):
+    """CUDA, contiguous, expected dtype -- converts layout/dtype on device if needed, never moves to the CPU."""
+    require_cuda(t, name)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_ws = {}
+
+
+def workspace(device, nbytes):
+    """Per-(device, stream) scratch for the loss partials; allocated once, reused (stream-ordered use only)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf

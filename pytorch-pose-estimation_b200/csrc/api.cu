@@ -1,0 +1,323 @@
+// extern "C" boundary of libpose_b200.so (see include/pose_b200.h for the contract).
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/pose_b200.h"
+#include "sbp_kernels.cuh"
+#include "spm_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return POSE_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+pose::FastDiv make_div(int d) {
+    pose::FastDiv f;
+    f.d = (uint32_t)d;
+    f.m = d > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d) : 0u;
+    return f;
+}
+
+int sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
+// persistent grid: resident CTAs per SM (occupancy API) x SM count, capped by the amount of work
+template <typename Kern>
+int persistent_grid(Kern kern, int threads, size_t smem, long long work_ctas) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    long long g = (long long)per_sm * sm_count();
+    if (g > pose::kMaxPartialBlocks) g = pose::kMaxPartialBlocks;
+    if (g > work_ctas) g = work_ctas;
+    return (int)(g < 1 ? 1 : g);
+}
+
+int check_map_shape(int N, int K, int H, int W) {
+    if (N < 0 || K <= 0 || H <= 0 || W <= 0) return fail(POSE_EINVAL, "bad shape N=%d K=%d H=%d W=%d", N, K, H, W);
+    if ((long long)H * W >= (1ll << 20) || W >= (1 << 11)) return fail(POSE_EINVAL, "map too large: H=%d W=%d", H, W);
+    return POSE_OK;
+}
+
+}  // namespace
+
+namespace {
+template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
+int launch_fused(const pose::SbpFusedParams& P0, size_t smem, cudaStream_t st, int* grid_out) {
+    pose::SbpFusedParams P = P0;
+    const long long ctas = (P.n_maps + pose::kSbpWarps - 1) / pose::kSbpWarps;
+    const int grid = persistent_grid(pose::sbp_fused_kernel<V, TGT, GRAD, WTGT, DEC>, pose::kSbpThreads, smem, ctas);
+    pose::sbp_fused_kernel<V, TGT, GRAD, WTGT, DEC><<<grid, pose::kSbpThreads, smem, st>>>(P);
+    *grid_out = grid;
+    return check_launch("sbp_fused");
+}
+template <int V, int TGT>
+int dispatch_fused(const pose::SbpFusedParams& P, unsigned flags, size_t smem, cudaStream_t st, int* grid) {
+    const bool g = flags & POSE_F_GRAD, t = (flags & POSE_F_TARGET_OUT) && TGT == pose::TGT_RENDER, d = flags & POSE_F_DECODE;
+#define POSE_CASE(G, T, D) \
+    if (g == G && t == T && d == D) return launch_fused<V, TGT, G, T, D>(P, smem, st, grid);
+    POSE_CASE(false, false, false) POSE_CASE(true, false, false) POSE_CASE(false, false, true) POSE_CASE(true, false, true)
+    if (TGT == pose::TGT_RENDER) {
+        POSE_CASE(false, true, false) POSE_CASE(true, true, false) POSE_CASE(false, true, true) POSE_CASE(true, true, true)
+    }
+#undef POSE_CASE
+    return fail(POSE_EINVAL, "sbp_fused: unsupported flag combination 0x%x", flags);
+}
+}  // namespace
+
+extern "C" {
+
+int pose_b200_version(void) { return 100; }
+const char* pose_b200_last_error(void) { return g_err; }
+unsigned long long pose_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int pose_gauss_template_host(double sigma, float* out_host, int capacity) {
+    if (!(sigma > 0.0) || !out_host) return fail(POSE_EINVAL, "gauss template: sigma must be > 0");
+    const double size = 6.0 * sigma + 3.0;
+    const int n = (int)std::ceil(size);          // len(np.arange(0, size, 1.0))
+    if (n * n > capacity) return fail(POSE_EINVAL, "gauss template: capacity %d < %d", capacity, n * n);
+    const double c = 3.0 * sigma + 1.0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            const double dx = (double)j - c, dy = (double)i - c;
+            out_host[i * n + j] = (float)std::exp(-(dx * dx + dy * dy) / (2.0 * (sigma * sigma)));
+        }
+    return n;
+}
+
+int pose_sbp_render(const void* kp, int kp_dtype, float* target, int N, int K, int H, int W, double sigma,
+                    const float* lut, int lut_n, pose_stream_t stream) {
+    if (int rc = check_map_shape(N, K, H, W)) return rc;
+    if (!kp || !target || !lut || lut_n <= 0 || lut_n > 64 || !(sigma > 0.0)) return fail(POSE_EINVAL, "sbp_render: bad argument");
+    if (N == 0) return POSE_OK;
+    pose::SbpRenderParams P;
+    P.kp = kp; P.kp_f64 = kp_dtype == POSE_KP_F64; P.target = target; P.lut = lut; P.lut_n = lut_n;
+    P.three_sigma = 3 * sigma;
+    P.n_maps = (long long)N * K; P.H = H; P.W = W; P.HW = H * W; P.divW = make_div(W);
+    const size_t smem = (size_t)lut_n * lut_n * sizeof(float);
+    const bool vec = (P.HW % 4 == 0) && W >= 4 && aligned16(target);
+    const long long ctas = (P.n_maps + pose::kSbpWarps - 1) / pose::kSbpWarps;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec) {
+        const int grid = persistent_grid(pose::sbp_render_kernel<4>, pose::kSbpThreads, smem, ctas);
+        pose::sbp_render_kernel<4><<<grid, pose::kSbpThreads, smem, st>>>(P);
+    } else {
+        const int grid = persistent_grid(pose::sbp_render_kernel<1>, pose::kSbpThreads, smem, ctas);
+        pose::sbp_render_kernel<1><<<grid, pose::kSbpThreads, smem, st>>>(P);
+    }
+    return check_launch("sbp_render");
+}
+
+unsigned long long pose_sbp_fused_workspace_bytes(void) { return (unsigned long long)pose::kMaxPartialBlocks * 2 * sizeof(double); }
+
+
+int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, int kp_dtype, double sigma,
+                   const float* lut, int lut_n, float* dlogits, float* target_out, float* loss_out,
+                   double* loss_num_out, float* joints, float conf_threshold, float coord_scale, int N, int K,
+                   int H, int W, float lambda_pos, float lambda_neg, double inv_norm, unsigned flags,
+                   void* workspace, unsigned long long workspace_bytes, pose_stream_t stream) {
+    if (int rc = check_map_shape(N, K, H, W)) return rc;
+    if (!logits) return fail(POSE_EINVAL, "sbp_fused: logits is NULL");
+    if ((target_in != nullptr) == (kp != nullptr)) return fail(POSE_EINVAL, "sbp_fused: pass exactly one of target_in / kp");
+    if (kp && (!lut || lut_n <= 0 || lut_n > 64 || !(sigma > 0.0))) return fail(POSE_EINVAL, "sbp_fused: render mode needs sigma>0 and a template");
+    if ((flags & POSE_F_GRAD) && !dlogits) return fail(POSE_EINVAL, "sbp_fused: POSE_F_GRAD without dlogits");
+    if ((flags & POSE_F_TARGET_OUT) && (!target_out || !kp)) return fail(POSE_EINVAL, "sbp_fused: POSE_F_TARGET_OUT needs target_out and kp");
+    if ((flags & POSE_F_DECODE) && !joints) return fail(POSE_EINVAL, "sbp_fused: POSE_F_DECODE without joints");
+    if (!loss_out && !loss_num_out) return fail(POSE_EINVAL, "sbp_fused: no loss output");
+    if (!workspace || workspace_bytes < pose_sbp_fused_workspace_bytes()) return fail(POSE_EWORKSPACE, "sbp_fused: workspace too small");
+    if (!aligned16(workspace)) return fail(POSE_EALIGN, "sbp_fused: workspace must be 16-byte aligned");
+    if (dlogits == logits || (target_out && target_out == logits)) return fail(POSE_EINVAL, "sbp_fused: outputs must not alias logits");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    pose::SbpFusedParams P;
+    memset(&P, 0, sizeof(P));
+    P.logits = logits; P.target_in = target_in; P.kp = kp; P.kp_f64 = kp_dtype == POSE_KP_F64;
+    P.lut = lut; P.lut_n = lut_n; P.three_sigma = 3 * sigma;
+    P.dlogits = dlogits; P.target_out = target_out; P.joints = joints;
+    P.partials = reinterpret_cast<double*>(workspace);
+    P.thr = conf_threshold; P.scale = coord_scale;
+    P.gpos = (float)(2.0 * (double)lambda_pos * inv_norm);
+    P.gneg = (float)(2.0 * (double)lambda_neg * inv_norm);
+    P.n_maps = (long long)N * K; P.H = H; P.W = W; P.HW = H * W; P.divW = make_div(W);
+
+    int grid = 0;
+    if (N > 0) {
+        const bool vec = (P.HW % 4 == 0) && W >= 4 && aligned16(logits) && (!target_in || aligned16(target_in)) &&
+                         (!(flags & POSE_F_GRAD) || aligned16(dlogits)) && (!(flags & POSE_F_TARGET_OUT) || aligned16(target_out));
+        const size_t smem = kp ? (size_t)lut_n * lut_n * sizeof(float) : 0;
+        int rc;
+        if (kp) rc = vec ? dispatch_fused<4, pose::TGT_RENDER>(P, flags, smem, st, &grid) : dispatch_fused<1, pose::TGT_RENDER>(P, flags, smem, st, &grid);
+        else rc = vec ? dispatch_fused<4, pose::TGT_DENSE>(P, flags, smem, st, &grid) : dispatch_fused<1, pose::TGT_DENSE>(P, flags, smem, st, &grid);
+        if (rc) return rc;
+    }
+    pose::loss_finalize_kernel<<<1, 256, 0, st>>>(P.partials, grid, (double)lambda_pos, (double)lambda_neg, inv_norm, loss_out, loss_num_out);
+    return check_launch("loss_finalize");
+}
+
+int pose_scale_grad(float* dlogits, const float* grad_output, unsigned long long n, pose_stream_t stream) {
+    if (!dlogits || !grad_output) return fail(POSE_EINVAL, "scale_grad: NULL pointer");
+    if (n == 0) return POSE_OK;
+    unsigned long long blocks = (n / 4 + 255) / 256;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    pose::scale_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dlogits, grad_output, n);
+    return check_launch("scale_grad");
+}
+
+int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W, float conf_threshold, int apply_sigmoid,
+                    float coord_scale, int refine, int mode, pose_stream_t stream) {
+    if (int rc = check_map_shape(N, K, H, W)) return rc;
+    if (!x || !joints) return fail(POSE_EINVAL, "sbp_decode: NULL pointer");
+    if (mode != POSE_DECODE_DIRECT && mode != POSE_DECODE_INTERVAL) return fail(POSE_EINVAL, "sbp_decode: bad mode %d", mode);
+    if (N == 0) return POSE_OK;
+    pose::SbpDecodeParams P;
+    P.x = x; P.joints = joints; P.thr = conf_threshold; P.scale = coord_scale;
+    P.n_maps = (long long)N * K; P.H = H; P.W = W; P.HW = H * W; P.divW = make_div(W); P.refine = refine;
+    const bool vec = (P.HW % 4 == 0) && aligned16(x);
+    const long long ctas = (P.n_maps + pose::kSbpWarps - 1) / pose::kSbpWarps;
+    cudaStream_t st = (cudaStream_t)stream;
+#define POSE_DEC(V, S, I)                                                                             \
+    {                                                                                                 \
+        const int grid = persistent_grid(pose::sbp_decode_kernel<V, S, I>, pose::kSbpThreads, 0, ctas); \
+        pose::sbp_decode_kernel<V, S, I><<<grid, pose::kSbpThreads, 0, st>>>(P);                      \
+    }
+    const bool sig = apply_sigmoid != 0, itv = mode == POSE_DECODE_INTERVAL;
+    if (vec) {
+        if (sig && itv) POSE_DEC(4, true, true) else if (sig) POSE_DEC(4, true, false) else if (itv) POSE_DEC(4, false, true) else POSE_DEC(4, false, false)
+    } else {
+        if (sig && itv) POSE_DEC(1, true, true) else if (sig) POSE_DEC(1, true, false) else if (itv) POSE_DEC(1, false, true) else POSE_DEC(1, false, false)
+    }
+#undef POSE_DEC
+    return check_launch("sbp_decode");
+}
+
+int pose_sbp_backproject(const float* joints, const double* bbox, float* rows_out, float* score_out, int N, int K,
+                         int input_h, int input_w, pose_stream_t stream) {
+    if (N < 0 || K <= 0 || input_h <= 0 || input_w <= 0 || !joints || !bbox || !rows_out || !score_out)
+        return fail(POSE_EINVAL, "sbp_backproject: bad argument");
+    if (N == 0) return POSE_OK;
+    pose::sbp_backproject_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(joints, bbox, rows_out, score_out, N, K,
+                                                                                    (double)input_h, (double)input_w);
+    return check_launch("sbp_backproject");
+}
+
+int pose_spm_render(const long long* centers, const long long* joints, const int* counts, float* target, int N, int Pmax,
+                    int K, int R, double sigma, const float* lut, int lut_n, pose_stream_t stream) {
+    if (N < 0 || Pmax < 0 || K <= 0 || R <= 0 || R % 4 != 0 || R > 2048) return fail(POSE_EINVAL, "spm_render: bad shape (R must be a multiple of 4)");
+    if (!counts || !target || !lut || lut_n <= 0 || lut_n > 64 || !(sigma > 0.0) || (Pmax > 0 && (!centers || !joints)))
+        return fail(POSE_EINVAL, "spm_render: bad argument");
+    if (!aligned16(target)) return fail(POSE_EALIGN, "spm_render: target must be 16-byte aligned");
+    if (N == 0) return POSE_OK;
+    pose::SpmRenderParams P;
+    P.centers = centers; P.joints = joints; P.counts = counts; P.target = target; P.lut = lut; P.lut_n = lut_n;
+    P.three_sigma = 3 * sigma; P.half = (int)((6 * sigma + 2) / 2);
+    P.z = std::sqrt((double)((long long)R * R + (long long)R * R));
+    P.N = N; P.Pmax = Pmax; P.K = K; P.R = R;
+    const int quads = R * R / 4;
+    const long long grid = (long long)N * ((quads + pose::kSpmThreads - 1) / pose::kSpmThreads);
+    if (grid > 0x7fffffffll) return fail(POSE_EINVAL, "spm_render: grid too large");
+    pose::spm_render_kernel<<<(unsigned)grid, pose::kSpmThreads, (size_t)lut_n * lut_n * sizeof(float), (cudaStream_t)stream>>>(P);
+    return check_launch("spm_render");
+}
+
+unsigned long long pose_spm_loss_workspace_bytes(void) { return (unsigned long long)pose::kMaxPartialBlocks * 2 * sizeof(double); }
+
+int pose_spm_loss(const float* logits, const float* target, float* dlogits, float* loss_out, double* loss_num_out, int N,
+                  int K, int R, float lambda_root, float lambda_disp, double inv_norm, int write_grad, void* workspace,
+                  unsigned long long workspace_bytes, pose_stream_t stream) {
+    if (N < 0 || K <= 0 || R <= 0 || R % 4 != 0) return fail(POSE_EINVAL, "spm_loss: bad shape (R must be a multiple of 4)");
+    if (!logits || !target || (write_grad && !dlogits) || (!loss_out && !loss_num_out)) return fail(POSE_EINVAL, "spm_loss: NULL pointer");
+    if (!aligned16(logits) || !aligned16(target) || (write_grad && !aligned16(dlogits))) return fail(POSE_EALIGN, "spm_loss: tensors must be 16-byte aligned");
+    if (!workspace || workspace_bytes < pose_spm_loss_workspace_bytes() || !aligned16(workspace)) return fail(POSE_EWORKSPACE, "spm_loss: workspace too small / unaligned");
+    if (write_grad && dlogits == logits) return fail(POSE_EINVAL, "spm_loss: dlogits must not alias logits");
+    cudaStream_t st = (cudaStream_t)stream;
+    pose::SpmLossParams P;
+    P.logits = logits; P.target = target; P.dlogits = dlogits; P.partials = reinterpret_cast<double*>(workspace);
+    P.quads = R * R / 4; P.units = (long long)N * P.quads; P.C = 1 + 2 * K;
+    P.groot = (float)(2.0 * (double)lambda_root * inv_norm);
+    P.gdisp = (float)((double)lambda_disp * inv_norm);
+    int grid = 0;
+    if (N > 0) {
+        const long long ctas = (P.units + pose::kSpmThreads - 1) / pose::kSpmThreads;
+        if (write_grad) {
+            grid = persistent_grid(pose::spm_loss_kernel<true>, pose::kSpmThreads, 0, ctas);
+            pose::spm_loss_kernel<true><<<grid, pose::kSpmThreads, 0, st>>>(P);
+        } else {
+            grid = persistent_grid(pose::spm_loss_kernel<false>, pose::kSpmThreads, 0, ctas);
+            pose::spm_loss_kernel<false><<<grid, pose::kSpmThreads, 0, st>>>(P);
+        }
+        if (int rc = check_launch("spm_loss")) return rc;
+    }
+    pose::loss_finalize_kernel<<<1, 256, 0, st>>>(P.partials, grid, (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out);
+    return check_launch("loss_finalize");
+}
+
+unsigned long long pose_spm_decode_workspace_bytes(int N, int R) { (void)N; (void)R; return 0ull; }
+
+int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* counts_total, int N, int Pmax, int K, int R,
+                    float conf_threshold, double dist_threshold, int apply_act, float input_size, void* workspace,
+                    unsigned long long workspace_bytes, pose_stream_t stream) {
+    (void)workspace; (void)workspace_bytes;
+    if (N < 0 || Pmax <= 0 || K <= 0 || R <= 0) return fail(POSE_EINVAL, "spm_decode: bad shape");
+    if (!x || !roots || !kps || !counts) return fail(POSE_EINVAL, "spm_decode: NULL pointer");
+    if (!(dist_threshold >= 0.0) || dist_threshold > 1024.0) return fail(POSE_EINVAL, "spm_decode: bad dist_threshold");
+    const size_t smem = (size_t)R * R * sizeof(float);
+    if (smem > 200 * 1024) return fail(POSE_EINVAL, "spm_decode: R=%d root map does not fit in shared memory", R);
+    if (N == 0) return POSE_OK;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pose::spm_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "spm_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    pose::SpmDecodeParams P;
+    P.x = x; P.roots = roots; P.kps = kps; P.counts = counts; P.counts_total = counts_total;
+    P.N = N; P.Pmax = Pmax; P.K = K; P.R = R; P.C = 1 + 2 * K;
+    P.thr = conf_threshold; P.dist_thr = dist_threshold; P.apply_act = apply_act;
+    P.zf = (float)std::sqrt((double)((long long)R * R + (long long)R * R));
+    P.input_size = input_size;
+    pose::spm_decode_kernel<<<N, pose::kSpmThreads, smem, (cudaStream_t)stream>>>(P);
+    return check_launch("spm_decode");
+}
+
+int pose_spm_gather(const float* roots, const float* disp, float* kps, int n_roots, int K, int R, double dist_threshold,
+                    pose_stream_t stream) {
+    if (n_roots < 0 || K <= 0 || R <= 0 || !disp || (n_roots > 0 && (!roots || !kps))) return fail(POSE_EINVAL, "spm_gather: bad argument");
+    if (n_roots == 0) return POSE_OK;
+    const float zf = (float)std::sqrt((double)((long long)R * R + (long long)R * R));
+    const int total = n_roots * K;
+    pose::spm_gather_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(roots, disp, kps, n_roots, K, R, zf, dist_threshold);
+    return check_launch("spm_gather");
+}
+
+int pose_sigmoid_monotone_check(unsigned long long* violations_out, pose_stream_t stream) {
+    if (!violations_out) return fail(POSE_EINVAL, "monotone_check: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(violations_out, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return fail((int)e, "monotone_check: %s", cudaGetErrorString(e));
+    pose::sigmoid_monotone_kernel<<<sm_count() * 8, 256, 0, st>>>(violations_out);
+    return check_launch("sigmoid_monotone");
+}
+
+}  // extern "C"

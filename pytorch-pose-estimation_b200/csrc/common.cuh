@@ -1,0 +1,99 @@
+// Shared device helpers for the heatmap hot-path kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define POSE_WARP 32
+#define FULL_MASK 0xffffffffu
+
+namespace pose {
+
+// ---------------------------------------------------------------- memory: 128-bit streaming accesses
+// Every byte of logits / target / dlogits is touched exactly once per pass, so loads bypass L1
+// allocation and stores are streaming: nothing here is worth keeping in L1.
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// second look at data the same warp has just streamed: keep it cacheable (L1/L2 hit expected)
+__device__ __forceinline__ float4 ldg_cached(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float ldg_cached(const float* p) { return __ldg(p); }
+
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream(float* p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// ---------------------------------------------------------------- activations
+// sigmoid(x) = 1 / (1 + 2^(-x*log2 e)) on the SFU: one MUFU.EX2 + one MUFU.RCP.
+// Max error a few ulp (inside the 1e-5 parity tolerance); saturates cleanly: x -> +inf gives 1,
+// x -> -inf gives +0 (ex2 -> +inf, rcp(+inf) = 0).  The .ftz forms drop the denormal fix-up code
+// (6 extra instructions per element): results below 2^-126 (x < -87.3) flush to +0.  The same function is used by loss and decode so
+// that "argmax of sigmoid" means the same thing in every kernel.  Monotonicity over all fp32
+// inputs is verified exhaustively on the device (pose_sigmoid_monotone_check).
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    float e, r;
+    float t = x * -1.4426950408889634f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+
+// ---------------------------------------------------------------- warp reductions
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+// argmax with first-index tie-break: larger value wins, equal values -> smaller index wins.
+__device__ __forceinline__ void warp_argmax_first(float& v, int& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(FULL_MASK, v, o);
+        int oi = __shfl_xor_sync(FULL_MASK, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+// ---------------------------------------------------------------- order-preserving float <-> uint key
+__device__ __forceinline__ uint32_t float_key(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(b);
+}
+
+// exact integer division by a runtime constant for small operands (n < 2^16 * d is plenty here):
+// q = (n * m) >> 32 with m = ceil(2^32 / d); valid for n*d < 2^32 -- checked on the host.
+struct FastDiv {
+    uint32_t d, m;
+};
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return f.d == 1 ? n : __umulhi(n, f.m); }
+
+}  // namespace pose

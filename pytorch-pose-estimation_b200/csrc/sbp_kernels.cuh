@@ -1,0 +1,500 @@
+// Simple-Baselines hot path kernels: render, fused render+loss+grad(+decode), decode, back-projection.
+//
+// Work unit = one heat map (H*W fp32, 12 288 B at 64x48).  One warp owns one map at a time and a
+// persistent grid (SM count x resident CTAs) strides over all N*K maps, so every global access is
+// a fully coalesced 128-bit load/store of 512 contiguous bytes per warp instruction, the per-map
+// reductions (argmax, loss partials) are warp shuffles only, and no __syncthreads() appears in
+// the streaming loop.  All stages are HBM-bound; nothing here is a contraction (no tensor cores).
+#pragma once
+#include "common.cuh"
+
+namespace pose {
+
+constexpr int kSbpThreads = 256;               // 8 warps per CTA
+constexpr int kSbpWarps = kSbpThreads / 32;
+constexpr int kMaxPartialBlocks = 148 * 16;    // upper bound on the persistent grid (workspace sizing)
+
+// ---------------------------------------------------------------- vector helpers
+template <int V> struct Vec;
+template <> struct Vec<4> {
+    using T = float4;
+    static __device__ __forceinline__ void load(const float* base, int vi, float (&o)[4]) {
+        float4 v = ldg_stream(reinterpret_cast<const float4*>(base) + vi);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    static __device__ __forceinline__ void load_cached(const float* base, int vi, float (&o)[4]) {
+        float4 v = ldg_cached(reinterpret_cast<const float4*>(base) + vi);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    static __device__ __forceinline__ void store(float* base, int vi, const float (&o)[4]) {
+        __stcs(reinterpret_cast<float4*>(base) + vi, make_float4(o[0], o[1], o[2], o[3]));
+    }
+};
+template <> struct Vec<1> {
+    using T = float;
+    static __device__ __forceinline__ void load(const float* base, int vi, float (&o)[1]) { o[0] = ldg_stream(base + vi); }
+    static __device__ __forceinline__ void load_cached(const float* base, int vi, float (&o)[1]) { o[0] = ldg_cached(base + vi); }
+    static __device__ __forceinline__ void store(float* base, int vi, const float (&o)[1]) { __stcs(base + vi, o[0]); }
+};
+
+// ---------------------------------------------------------------- Gaussian patch geometry of one map
+// SBPHeatmapGenerator.__call__ (utils/sbp_utils.py:36-51): skip if x<0 or y<0; centre = clip(int(x));
+// corners = round-half-even(c - 3s - 1), round-half-even(c + 3s + 2) evaluated in double exactly as
+// numpy does ((c - 3s) - 1); destination window = corners clipped to the map.
+struct Patch {
+    int ulx, uly;            // template origin in map coordinates (may be negative)
+    int px0, px1, py0, py1;  // clipped destination window, empty when the joint is invisible
+};
+
+__device__ __forceinline__ Patch make_patch(double x, double y, int H, int W, double three_sigma, int lut_n) {
+    Patch p;
+    const bool visible = (x >= 0.0) && (y >= 0.0);   // == not (x<0 or y<0) for non-NaN input; -0.0 is visible
+    // x >= 0 here, so clip(int(x), 0, W-1) == int(min(x, W-1)) -- also safe for huge / inf inputs
+    const int cx = (int)fmin(x, (double)(W - 1));
+    const int cy = (int)fmin(y, (double)(H - 1));
+    p.ulx = (int)rint(((double)cx - three_sigma) - 1.0);
+    p.uly = (int)rint(((double)cy - three_sigma) - 1.0);
+    const int brx = (int)rint(((double)cx + three_sigma) + 2.0);
+    const int bry = (int)rint(((double)cy + three_sigma) + 2.0);
+    p.px0 = max(0, p.ulx);
+    p.py0 = max(0, p.uly);
+    p.px1 = min(min(brx, W), p.ulx + lut_n);
+    p.py1 = min(min(bry, H), p.uly + lut_n);
+    if (!visible) { p.px0 = p.px1 = p.py0 = p.py1 = 0; p.ulx = p.uly = 0; }
+    return p;
+}
+
+__device__ __forceinline__ void load_kp(const void* kp, int kp_f64, long long map, double& x, double& y) {
+    if (kp_f64) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(kp) + map);
+        x = v.x; y = v.y;
+    } else {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(kp) + map);
+        x = (double)v.x; y = (double)v.y;
+    }
+}
+
+// target values of V consecutive elements starting at flat index e0 of a map
+template <int V>
+__device__ __forceinline__ bool patch_values(const Patch& p, const float* __restrict__ lut_s, int lut_n, int e0,
+                                             int W, FastDiv divW, float (&t)[V]) {
+    int row = (int)fdiv((uint32_t)e0, divW);
+    int col = e0 - row * W;
+#pragma unroll
+    for (int j = 0; j < V; ++j) t[j] = 0.0f;
+    // whole vector outside the patch rows: the overwhelmingly common case (zero target)
+    const int row_last = row + ((col + V - 1) >= W ? 1 : 0);   // V <= 4 <= W on the vector path: at most one wrap
+    if (row_last < p.py0 || row >= p.py1) return false;
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        if (row >= p.py0 && row < p.py1 && col >= p.px0 && col < p.px1) {
+            t[j] = lut_s[(row - p.uly) * lut_n + (col - p.ulx)];
+            any = true;
+        }
+        if (++col >= W) { col = 0; ++row; }
+    }
+    return any;
+}
+
+// ---------------------------------------------------------------- render only
+struct SbpRenderParams {
+    const void* kp; int kp_f64;
+    float* target;
+    const float* lut; int lut_n;
+    double three_sigma;
+    long long n_maps; int H, W, HW; FastDiv divW;
+};
+
+template <int V>
+__global__ void __launch_bounds__(kSbpThreads) sbp_render_kernel(SbpRenderParams P) {
+    extern __shared__ float lut_s[];
+    for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * kSbpWarps + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kSbpWarps;
+    const int nvec = P.HW / V;
+    for (long long map = warp0; map < P.n_maps; map += nwarps) {
+        double x, y;
+        load_kp(P.kp, P.kp_f64, map, x, y);
+        const Patch pt = make_patch(x, y, P.H, P.W, P.three_sigma, P.lut_n);
+        float* out = P.target + map * P.HW;
+#pragma unroll 4
+        for (int vi = lane; vi < nvec; vi += 32) {
+            float t[V];
+            patch_values<V>(pt, lut_s, P.lut_n, vi * V, P.W, P.divW, t);
+            Vec<V>::store(out, vi, t);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- fused loss (+render, +grad, +decode)
+struct SbpFusedParams {
+    const float* logits;
+    const float* target_in;      // TGT == 1
+    const void* kp; int kp_f64;  // TGT == 2
+    const float* lut; int lut_n; double three_sigma;
+    float* dlogits;              // GRAD
+    float* target_out;           // WTGT
+    float* joints;               // DEC
+    double* partials;            // [gridDim.x][2]  (S_pos, S_neg)
+    float thr, scale;
+    float gpos, gneg;            // 2*lambda*inv_norm
+    long long n_maps; int H, W, HW; FastDiv divW;
+};
+
+constexpr int TGT_DENSE = 1;
+constexpr int TGT_RENDER = 2;
+
+// One element of the joints-MSE loss in closed form (models/loss/sbp_loss.py:44-47):
+//   t > 0 : S_pos += (s-t)^2                      dL/dp = gpos (s-t) s (1-s)
+//   t <= 0: S_pos += t^2, S_neg += (s-t)^2        dL/dp = gneg (s-t) s (1-s)
+template <bool GRAD>
+__device__ __forceinline__ float loss_elem(float s, float t, float gpos, float gneg, float& apos, float& aneg) {
+    const float d = s - t;
+    const bool pos = t > 0.0f;
+    apos = fmaf(pos ? d : t, pos ? d : t, apos);
+    aneg = pos ? aneg : fmaf(d, d, aneg);
+    if (!GRAD) return 0.0f;
+    return (pos ? gpos : gneg) * d * ((1.0f - s) * s);
+}
+
+template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
+__global__ void __launch_bounds__(kSbpThreads) sbp_fused_kernel(SbpFusedParams P) {
+    extern __shared__ float lut_s[];
+    __shared__ double red[kSbpWarps][2];
+    if (TGT == TGT_RENDER) {
+        for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * kSbpWarps + wid;
+    const long long nwarps = (long long)gridDim.x * kSbpWarps;
+    const int nvec = P.HW / V;
+    constexpr int U = (V == 4) ? 4 : 8;     // independent 128-bit loads in flight per lane
+    double dpos = 0.0, dneg = 0.0;
+
+    for (long long map = warp0; map < P.n_maps; map += nwarps) {
+        const float* lg = P.logits + map * P.HW;
+        const float* tg = (TGT == TGT_DENSE) ? P.target_in + map * P.HW : nullptr;
+        float* dl = GRAD ? P.dlogits + map * P.HW : nullptr;
+        float* to = WTGT ? P.target_out + map * P.HW : nullptr;
+        Patch pt;
+        if (TGT == TGT_RENDER) {
+            double x, y;
+            load_kp(P.kp, P.kp_f64, map, x, y);
+            pt = make_patch(x, y, P.H, P.W, P.three_sigma, P.lut_n);
+        }
+        float apos = 0.0f, aneg = 0.0f;
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+
+        for (int base = lane; base < nvec; base += 32 * U) {
+            float xv[U][V], tv[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int vi = base + 32 * u;
+                if (vi < nvec) {
+                    Vec<V>::load(lg, vi, xv[u]);
+                    if (TGT == TGT_DENSE) Vec<V>::load(tg, vi, tv[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int vi = base + 32 * u;
+                if (vi >= nvec) break;
+                float g[V];
+                bool nonzero = true;
+                if (TGT == TGT_RENDER) nonzero = patch_values<V>(pt, lut_s, P.lut_n, vi * V, P.W, P.divW, tv[u]);
+                if (TGT == TGT_RENDER && !nonzero) {
+                    // zero target: S_neg += s^2, grad = gneg s^2 (1-s)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const float s = sigmoid_fast(xv[u][j]);
+                        const float s2 = s * s;
+                        aneg += s2;
+                        if (GRAD) g[j] = P.gneg * s2 * (1.0f - s);
+                        if (DEC && s > best) { best = s; besti = vi * V + j; }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const float s = sigmoid_fast(xv[u][j]);
+                        g[j] = loss_elem<GRAD>(s, tv[u][j], P.gpos, P.gneg, apos, aneg);
+                        if (DEC && s > best) { best = s; besti = vi * V + j; }
+                    }
+                }
+                if (GRAD) Vec<V>::store(dl, vi, g);
+                if (WTGT) Vec<V>::store(to, vi, tv[u]);
+            }
+        }
+        // per-map flush of the fp32 partials into fp64 (keeps the 2e8-term sum accurate and deterministic)
+        dpos += (double)apos;
+        dneg += (double)aneg;
+
+        if (DEC) {
+            warp_argmax_first(best, besti);
+            if (lane == 0) {
+                float jx = -1.0f, jy = -1.0f, jc = -1.0f;
+                if (best > P.thr) {
+                    const int row = (int)fdiv((uint32_t)besti, P.divW);
+                    jx = (float)(besti - row * P.W);
+                    jy = (float)row;
+                    jc = best;
+                }
+                float* jo = P.joints + map * 3;
+                jo[0] = __fmul_rn(jx, P.scale);
+                jo[1] = __fmul_rn(jy, P.scale);
+                jo[2] = jc;
+            }
+        }
+    }
+
+    dpos = warp_sum(dpos);
+    dneg = warp_sum(dneg);
+    if (lane == 0) { red[wid][0] = dpos; red[wid][1] = dneg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < kSbpWarps; ++w) { a += red[w][0]; b += red[w][1]; }
+        P.partials[2 * blockIdx.x] = a;
+        P.partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// deterministic second stage: one CTA sums the per-CTA partials in a fixed order
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const double* __restrict__ partials, int nblocks,
+                                                            double w0, double w1, double inv_norm,
+                                                            float* __restrict__ loss_out, double* __restrict__ num_out) {
+    __shared__ double sa[256], sb[256];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 256) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+    sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (num_out) { num_out[0] = sa[0]; num_out[1] = sb[0]; }
+        if (loss_out) loss_out[0] = (float)((w0 * sa[0] + w1 * sb[0]) * inv_norm);
+    }
+}
+
+// dlogits *= *g, whole launch is a no-op when *g == 1 (the usual loss.backward())
+__global__ void __launch_bounds__(256) scale_grad_kernel(float* __restrict__ d, const float* __restrict__ g, unsigned long long n) {
+    const float s = __ldg(g);
+    if (s == 1.0f) return;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        const unsigned long long n4 = n >> 2;
+        float4* d4 = reinterpret_cast<float4*>(d);
+        for (unsigned long long k = i; k < n4; k += stride) {
+            float4 v = d4[k];
+            v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+            d4[k] = v;
+        }
+        for (unsigned long long k = (n4 << 2) + i; k < n; k += stride) d[k] *= s;
+    } else {
+        for (unsigned long long k = i; k < n; k += stride) d[k] *= s;
+    }
+}
+
+// ---------------------------------------------------------------- decode only
+struct SbpDecodeParams {
+    const float* x;
+    float* joints;
+    float thr, scale;
+    long long n_maps; int H, W, HW; FastDiv divW;
+    int refine;
+};
+
+template <bool SIG>
+__device__ __forceinline__ float act(float v) { return SIG ? sigmoid_fast(v) : v; }
+
+// Smallest float lo with act(lo) == s, given act(m) == s and act monotone non-decreasing: all elements
+// whose activation equals the maximum are exactly those with value >= lo.  Warp-cooperative: an
+// exponential probe below m (lane j tests key(m) - 2^j) followed by 32-ary search rounds.
+template <bool SIG>
+__device__ __forceinline__ float preimage_floor(float m, float s, int lane) {
+    if (!SIG) return m;
+    const uint32_t hi = float_key(m);
+    const uint32_t step = 1u << lane;
+    const uint32_t probe = hi >= step ? hi - step : 0u;
+    const bool same = act<SIG>(key_float(probe)) == s;
+    const unsigned bal = __ballot_sync(FULL_MASK, same);
+    if (!(bal & 1u)) return m;                       // even m's predecessor maps lower: lo == m
+    // first lane j whose probe is already below the pre-image: answer in (hi-2^j, hi-2^(j-1)]
+    const unsigned notsame = ~bal;
+    uint32_t L, R;
+    if (notsame == 0u) {                             // pre-image reaches below hi-2^31: search from key 0
+        L = 0u;
+        R = hi >= 0x80000000u ? hi - 0x80000000u : 0u;
+    } else {
+        const int j = __ffs(notsame) - 1;            // j >= 1: probe j is below the pre-image, probe j-1 inside
+        L = (hi >= (1u << j) ? hi - (1u << j) : 0u) + 1u;
+        R = hi - (1u << (j - 1));
+    }
+    // invariant: act(R) == s, answer in [L, R]
+    while (L < R) {
+        const uint64_t width = (uint64_t)(R - L);
+        const uint32_t p = L + (uint32_t)((width * (uint64_t)(lane + 1)) / 33u);
+        const bool ok = act<SIG>(key_float(p)) == s;
+        const unsigned b = __ballot_sync(FULL_MASK, ok);
+        if (b == 0u) {
+            L = __shfl_sync(FULL_MASK, p, 31) + 1u;
+        } else {
+            const int j = __ffs(b) - 1;
+            const uint32_t pj = __shfl_sync(FULL_MASK, p, j);
+            const uint32_t pjm = __shfl_sync(FULL_MASK, p, j > 0 ? j - 1 : 0);
+            R = pj;
+            if (j > 0) L = pjm + 1u;
+        }
+    }
+    return key_float(R);
+}
+
+template <int V, bool SIG, bool INTERVAL>
+__global__ void __launch_bounds__(kSbpThreads) sbp_decode_kernel(SbpDecodeParams P) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * kSbpWarps + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kSbpWarps;
+    const int nvec = P.HW / V;
+    constexpr int U = (V == 4) ? 8 : 8;
+
+    for (long long map = warp0; map < P.n_maps; map += nwarps) {
+        const float* src = P.x + map * P.HW;
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+
+        if (INTERVAL) {
+            // pass 1: raw maximum (1 FMNMX per element, no SFU work); NaNs are ignored by fmaxf
+            float m = -INFINITY;
+            for (int base = lane; base < nvec; base += 32 * U) {
+                float xv[U][V];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int vi = base + 32 * u;
+                    if (vi < nvec) Vec<V>::load_cached(src, vi, xv[u]);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) xv[u][j] = -INFINITY;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) m = fmaxf(m, xv[u][j]);
+            }
+            m = warp_max(m);
+            best = act<SIG>(m);
+            if (best > P.thr) {
+                const float lo = preimage_floor<SIG>(m, best, lane);
+                // pass 2: first row-major element >= lo; the map was just read by this warp (L1/L2 hit)
+                for (int base = 0; base < nvec; base += 32) {
+                    const int vi = base + lane;
+                    int hit = 0x7fffffff;
+                    if (vi < nvec) {
+                        float xv[V];
+                        Vec<V>::load_cached(src, vi, xv);
+#pragma unroll
+                        for (int j = V - 1; j >= 0; --j)
+                            if (xv[j] >= lo) hit = vi * V + j;
+                    }
+                    const unsigned b = __ballot_sync(FULL_MASK, hit != 0x7fffffff);
+                    if (b) { besti = __shfl_sync(FULL_MASK, hit, __ffs(b) - 1); break; }
+                }
+            }
+        } else {
+            for (int base = lane; base < nvec; base += 32 * U) {
+                float xv[U][V];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int vi = base + 32 * u;
+                    if (vi < nvec) Vec<V>::load(src, vi, xv[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int vi = base + 32 * u;
+                    if (vi >= nvec) break;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const float s = act<SIG>(xv[u][j]);
+                        if (s > best) { best = s; besti = vi * V + j; }
+                    }
+                }
+            }
+            warp_argmax_first(best, besti);
+        }
+
+        if (lane == 0) {
+            float jx = -1.0f, jy = -1.0f, jc = -1.0f;
+            if (best > P.thr && besti != 0x7fffffff) {
+                const int row = (int)fdiv((uint32_t)besti, P.divW);
+                const int col = besti - row * P.W;
+                jx = (float)col; jy = (float)row; jc = best;
+                if (P.refine && col > 1 && col < P.W - 1 && row > 1 && row < P.H - 1) {
+                    // quarter-pixel shift toward the higher neighbour (NOT in the reference; opt-in)
+                    const float dx = act<SIG>(__ldg(src + besti + 1)) - act<SIG>(__ldg(src + besti - 1));
+                    const float dy = act<SIG>(__ldg(src + besti + P.W)) - act<SIG>(__ldg(src + besti - P.W));
+                    jx += dx > 0.0f ? 0.25f : (dx < 0.0f ? -0.25f : 0.0f);
+                    jy += dy > 0.0f ? 0.25f : (dy < 0.0f ? -0.25f : 0.0f);
+                }
+            }
+            float* jo = P.joints + map * 3;
+            jo[0] = __fmul_rn(jx, P.scale);
+            jo[1] = __fmul_rn(jy, P.scale);
+            jo[2] = jc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- back-projection + COCO row fields
+// SBPmAPCOCO.update_state (utils/sbp_utils.py:141-163): ratio in fp64 -> fp32, fp32 multiply, fp32 add of
+// fp32(bbox origin) (two roundings, no FMA); conf<0 -> (0,0,0); score = sequential fp32 sum / K.
+__global__ void __launch_bounds__(128) sbp_backproject_kernel(const float* __restrict__ joints, const double* __restrict__ bbox,
+                                                              float* __restrict__ rows, float* __restrict__ score,
+                                                              int N, int K, double in_h, double in_w) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const double bx = bbox[4 * n], by = bbox[4 * n + 1], bw = bbox[4 * n + 2], bh = bbox[4 * n + 3];
+    const float rx = (float)(bw / in_w), ry = (float)(bh / in_h);
+    const float ox = (float)bx, oy = (float)by;
+    float sum = 0.0f;
+    for (int k = 0; k < K; ++k) {
+        const float* j = joints + ((long long)n * K + k) * 3;
+        float* o = rows + ((long long)n * K + k) * 3;
+        const float c = j[2];
+        if (c < 0.0f) {
+            o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f;
+        } else {
+            o[0] = __fadd_rn(__fmul_rn(j[0], rx), ox);
+            o[1] = __fadd_rn(__fmul_rn(j[1], ry), oy);
+            o[2] = 1.0f;
+            sum = __fadd_rn(sum, c);
+        }
+    }
+    score[n] = __fdiv_rn(sum, (float)K);
+}
+
+// ---------------------------------------------------------------- sigmoid monotonicity (diagnostic)
+__global__ void sigmoid_monotone_kernel(unsigned long long* violations) {
+    // keys of all non-NaN floats: [key(-inf), key(+inf)]
+    const uint32_t k0 = float_key(-INFINITY), k1 = float_key(INFINITY);
+    const uint64_t total = (uint64_t)(k1 - k0);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const float a = key_float(k0 + (uint32_t)i), b = key_float(k0 + (uint32_t)i + 1u);
+        const float fa = sigmoid_fast(a), fb = sigmoid_fast(b);
+        if (!(fb >= fa)) ++bad;
+    }
+    bad = __reduce_add_sync(FULL_MASK, (unsigned)bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(violations, bad);
+}
+
+}  // namespace pose

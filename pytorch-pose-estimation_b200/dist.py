@@ -1,0 +1,76 @@
+"""Image-sharded multi-GPU glue: one process per GPU, torch.distributed (NCCL on GPUs, gloo in CPU tests).
+
+The hot path shards by image with no exchange inside render / loss / decode.  Two collectives remain
+(SURVEY.md 8 e), both latency-bound and both enqueued stream-ordered with no host synchronisation:
+
+* loss: all-reduce(SUM) of the two fp64 un-normalised numerators each rank's fused kernel produced;
+  every rank then holds the global-batch loss.  dlogits need no exchange -- each rank's kernel already
+  scales them by 1/(2*K*B_global).
+* predictions: all-gather of the fixed-size [B_local, K, 3] rows (+ scores, image ids) so that OKS/AP is
+  evaluated over the whole validation set on every rank.  The reference never gathers (each rank writes
+  its own results.json, utils/sbp_utils.py:167-169); this fixes that race.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous image shard [lo, hi) of rank `rank`; sizes differ by at most one, earlier ranks get the extras."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad world_size / rank")
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _active(group):
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def global_sbp_loss(loss_num, num_keypoints, global_batch, lambda_pos=5.0, lambda_neg=1.0, group=None):
+    """loss_num: fp64[2] local (S_pos, S_neg) -> 0-dim fp32 global loss (same on every rank).  In place on loss_num."""
+    if _active(group):
+        dist.all_reduce(loss_num, op=dist.ReduceOp.SUM, group=group)
+    return ((lambda_pos * loss_num[0] + lambda_neg * loss_num[1]) / (2.0 * num_keypoints * global_batch)).to(torch.float32)
+
+
+def global_spm_loss(loss_num, global_batch, lambda_root=1.0, lambda_disp=0.1, group=None):
+    if _active(group):
+        dist.all_reduce(loss_num, op=dist.ReduceOp.SUM, group=group)
+    return ((lambda_root * loss_num[0] + lambda_disp * loss_num[1]) / float(global_batch)).to(torch.float32)
+
+
+def gather_rows(rows, score, image_ids, category_ids, group=None):
+    """All-gather equal-sized shards: rows [B,K,3], score [B], ids [B] -> the same tensors for the global batch,
+    ordered by rank (= by image for contiguous shards).  One packed fp32 gather + one int64 gather."""
+    packed = torch.cat([rows.reshape(rows.size(0), -1), score[:, None]], dim=1).contiguous()
+    ids = torch.stack([image_ids.to(packed.device, torch.int64), category_ids.to(packed.device, torch.int64)], dim=1).contiguous()
+    if not _active(group):
+        return rows, score, ids[:, 0], ids[:, 1]
+    world = dist.get_world_size(group)
+    out_p = torch.empty((world * packed.size(0), packed.size(1)), dtype=packed.dtype, device=packed.device)
+    out_i = torch.empty((world * ids.size(0), 2), dtype=torch.int64, device=ids.device)
+    dist.all_gather_into_tensor(out_p, packed, group=group)
+    dist.all_gather_into_tensor(out_i, ids, group=group)
+    k = rows.size(1)
+    return out_p[:, :-1].reshape(-1, k, 3), out_p[:, -1], out_i[:, 0], out_i[:, 1]
+
+
+def gather_rows_ragged(rows, score, image_ids, category_ids, group=None):
+    """Same for shards whose sizes differ by at most one (shard_bounds): pad to the max, gather, strip."""
+    if not _active(group):
+        return rows, score, image_ids, category_ids
+    n = torch.tensor([rows.size(0)], dtype=torch.int64, device=rows.device)
+    sizes = [torch.zeros_like(n) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s) for s in sizes]
+    m = max(sizes)
+    pad = m - rows.size(0)
+    if pad:
+        rows = torch.cat([rows, rows.new_zeros((pad,) + tuple(rows.shape[1:]))])
+        score = torch.cat([score, score.new_zeros(pad)])
+        image_ids = torch.cat([image_ids, image_ids.new_full((pad,), -1)])
+        category_ids = torch.cat([category_ids, category_ids.new_full((pad,), -1)])
+    r, s, i, c = gather_rows(rows, score, image_ids, category_ids, group)
+    keep = torch.cat([torch.arange(m, device=r.device) < sz for sz in sizes])
+    return r[keep], s[keep], i[keep], c[keep]

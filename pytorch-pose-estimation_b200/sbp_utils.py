@@ -1,0 +1,214 @@
+"""Simple-Baselines utilities with the reference's names and call signatures (utils/sbp_utils.py).
+
+Every numeric operation runs in the sm_100a kernels behind libpose_b200.so.  Differences from the
+reference are additive only: batched entry points (`render_batch`, `decode_batch`) next to the
+per-sample drop-ins, and one device-to-host copy per batch in `update_state` instead of ~6*K
+synchronisations per sample.
+"""
+import json
+import os
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _cabi
+from ._cabi import check, dense, lib, ptr, stream_ptr
+
+
+def _gauss_template(sigma):
+    """float64 template of utils/sbp_utils.py:27-31 (size 6s+3, centre 3s+1)."""
+    ax = np.arange(0, 6 * sigma + 3, 1, float)
+    c = 3 * sigma + 1
+    return np.exp(-((ax[None, :] - c) ** 2 + (ax[:, None] - c) ** 2) / (2 * sigma ** 2))
+
+
+class _TemplateCache:
+    """fp32 device copies of Gaussian templates, one per (sigma, device)."""
+
+    def __init__(self):
+        self._dev = {}
+
+    def get(self, g64, sigma, device):
+        key = (float(sigma), device.type, device.index)
+        t = self._dev.get(key)
+        if t is None:
+            t = torch.from_numpy(np.ascontiguousarray(g64.astype(np.float32))).to(device)
+            self._dev[key] = t
+        return t
+
+
+_templates = _TemplateCache()
+
+
+def template_on(device, sigma):
+    g = _gauss_template(sigma)
+    return _templates.get(g, sigma, device), g.shape[0]
+
+
+def _kp_tensor(kp, device):
+    """Keypoints as a dense CUDA tensor [.., 2], fp64 preserved (truncation happens in fp64 in the reference)."""
+    if isinstance(kp, np.ndarray):
+        kp = torch.from_numpy(np.ascontiguousarray(kp))
+    if not isinstance(kp, torch.Tensor):
+        kp = torch.as_tensor(np.asarray(kp, dtype=np.float64))
+    if kp.dtype not in (torch.float32, torch.float64):
+        kp = kp.to(torch.float64)
+    return kp.to(device, non_blocking=True).contiguous()
+
+
+################################################################################################################
+# Simple Baselines Pose Estimation Utils
+################################################################################################################
+class SBPHeatmapGenerator:
+    """Drop-in for utils/sbp_utils.py:20-53.  `__call__` keeps the per-sample NumPy contract;
+    `render_batch` is the batched device entry point the training loop should use."""
+
+    def __init__(self, output_res, num_joints, sigma=-1, device=None):
+        self.output_res_h, self.output_res_w = output_res
+        self.num_joints = num_joints
+        if sigma < 0:
+            sigma = self.output_res_h / 64
+        self.sigma = sigma
+        self.g = _gauss_template(sigma)
+        self.device = torch.device(device) if device is not None else None
+
+    def _dev(self):
+        if self.device is None:
+            if not torch.cuda.is_available():
+                raise _cabi.PoseB200Error("SBPHeatmapGenerator needs a CUDA device: pose_b200 has no CPU path")
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        return self.device
+
+    def render_batch(self, joints, out=None):
+        """joints [B,K,2] (numpy / tensor, fp32 or fp64) -> CUDA fp32 [B,K,H,W]."""
+        dev = joints.device if isinstance(joints, torch.Tensor) and joints.is_cuda else self._dev()
+        kp = _kp_tensor(joints, dev)
+        assert kp.dim() == 3 and kp.size(-1) == 2, "joints must be [B,K,2]"
+        b, k = kp.size(0), kp.size(1)
+        if out is None:
+            out = torch.empty((b, k, self.output_res_h, self.output_res_w), dtype=torch.float32, device=dev)
+        lut = _templates.get(self.g, self.sigma, dev)
+        with torch.cuda.device(dev):
+            check(lib().pose_sbp_render(ptr(kp), _cabi.KP_F64 if kp.dtype == torch.float64 else _cabi.KP_F32, ptr(out),
+                                        b, k, self.output_res_h, self.output_res_w, float(self.sigma), ptr(lut),
+                                        self.g.shape[0], stream_ptr(dev)), "pose_sbp_render")
+        return out
+
+    def __call__(self, joints):
+        """joints [K,2] -> np.float32 [K,H,W] (reference contract; runs the same kernel with B=1)."""
+        kp = np.asarray(joints, dtype=np.float64).reshape(1, -1, 2)
+        return self.render_batch(kp)[0].cpu().numpy()
+
+
+def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False, refine=False, mode="interval"):
+    """[B,K,H,W] CUDA fp32 -> [B,K,3] (x*scale, y*scale, conf); undetected rows are (-scale,-scale,-1)."""
+    x = dense(heatmaps, "heatmaps")
+    assert x.dim() == 4
+    b, k, h, w = x.shape
+    out = torch.empty((b, k, 3), dtype=torch.float32, device=x.device)
+    m = _cabi.DECODE_INTERVAL if mode == "interval" else _cabi.DECODE_DIRECT
+    with torch.cuda.device(x.device):
+        check(lib().pose_sbp_decode(ptr(x), ptr(out), b, k, h, w, float(conf_threshold), int(bool(apply_sigmoid)),
+                                    float(coord_scale), int(bool(refine)), m, stream_ptr(x.device)), "pose_sbp_decode")
+    return out
+
+
+def nms_sbp(heatmaps, conf_threshold=0.8):
+    """Drop-in for utils/sbp_utils.py:56-82: heatmaps [K,H,W] -> joints [K,3] = [x, y, confidence]."""
+    return decode_batch(heatmaps[None], conf_threshold, 1.0, False)[0]
+
+
+class DecodeSBP(nn.Module):
+    """Drop-in for utils/sbp_utils.py:85-118 (same ctor / forward), plus `decode_batch` for B > 1."""
+
+    def __init__(self, input_size, conf_threshold, pred=True, refine=False, mode="interval"):
+        super().__init__()
+        self.input_size = input_size[-1]
+        self.conf_threshold = conf_threshold
+        self.pred = pred
+        self.refine = refine          # quarter-pixel refinement: NOT in the reference, default off
+        self.mode = mode
+
+    def decode_batch(self, x):
+        return decode_batch(x, self.conf_threshold, self.input_size / x.size(-1), self.pred, self.refine, self.mode)
+
+    def forward(self, x):
+        assert x.size(0) == 1
+        return self.decode_batch(x)[0]
+
+
+def backproject_rows(joints, bbox, input_size):
+    """joints [B,K,3] (input scale), bbox [B,4] fp64 -> (rows [B,K,3] = (x_img, y_img, 1|0), score [B])."""
+    j = dense(joints, "joints")
+    bb = dense(bbox.to(j.device) if isinstance(bbox, torch.Tensor) else torch.as_tensor(np.asarray(bbox)).to(j.device),
+               "bbox", torch.float64)
+    b, k = j.size(0), j.size(1)
+    rows = torch.empty_like(j)
+    score = torch.empty((b,), dtype=torch.float32, device=j.device)
+    with torch.cuda.device(j.device):
+        check(lib().pose_sbp_backproject(ptr(j), ptr(bb), ptr(rows), ptr(score), b, k, int(input_size[0]), int(input_size[1]),
+                                         stream_ptr(j.device)), "pose_sbp_backproject")
+    return rows, score
+
+
+def _ids(v):
+    return v.tolist() if isinstance(v, torch.Tensor) else [int(i) for i in v]
+
+
+def rows_to_results(rows, score, image_ids, category_ids, pad=0):
+    """One D2H copy, then plain-Python COCO result dicts (utils/sbp_utils.py:148-164)."""
+    packed = torch.cat([rows.reshape(rows.size(0), -1), score[:, None]], dim=1).cpu()
+    kps, sc = packed[:, :-1], packed[:, -1]
+    out = []
+    tail = [0] * pad
+    for i, (iid, cid) in enumerate(zip(_ids(image_ids), _ids(category_ids))):
+        flat = []
+        for x, y, v in kps[i].reshape(-1, 3).tolist():
+            flat.extend([x, y, 1] if v != 0 else [0, 0, 0])     # same literals as the reference emits
+        out.append({"image_id": int(iid), "category_id": int(cid), "keypoints": flat + tail, "score": float(sc[i])})
+    return out
+
+
+class SBPmAPCOCO:
+    """Drop-in for utils/sbp_utils.py:121-189.  `update_state` is batched on the device;
+    `result()` needs pycocotools exactly as the reference does (COCOeval is out of scope here)."""
+
+    _pad = 0
+
+    def __init__(self, json_path, input_size, conf_threshold):
+        self.coco = _load_coco(json_path)
+        self.input_size = input_size
+        self.decoder = DecodeSBP(input_size, conf_threshold, True)
+        self.result_list = []
+
+    def reset_states(self):
+        self.result_list = []
+
+    def update_state(self, target, y_pred):
+        joints = self.decoder.decode_batch(y_pred)                       # [B,K,3] at input scale
+        rows, score = backproject_rows(joints, target['bbox'], self.input_size)
+        self.result_list.extend(rows_to_results(rows, score, target['image_id'], target['category_id'], self._pad))
+
+    def result(self):
+        if self.coco is None:
+            raise ImportError("SBPmAPCOCO.result() needs pycocotools (COCOeval); result_list holds the COCO rows")
+        from pycocotools.cocoeval import COCOeval
+        path = os.path.join(os.getcwd(), 'results.json')
+        with open(path, "w") as f:
+            json.dump(self.result_list, f, indent=4)
+        ev = COCOeval(self.coco, self.coco.loadRes(path), "keypoints")
+        ev.params.imgIds = sorted(self.coco.getImgIds())
+        ev.params.catIds = sorted(self.coco.getCatIds())
+        ev.evaluate()
+        ev.accumulate()
+        ev.summarize()
+        return ev.stats[1]
+
+
+def _load_coco(json_path):
+    try:
+        from pycocotools.coco import COCO
+    except ImportError:
+        return None
+    return COCO(json_path)

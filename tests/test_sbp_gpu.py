@@ -1,0 +1,316 @@
+"""GPU parity tests, Simple Baselines path: CUDA kernels (through the C ABI / drop-in classes) vs the golden vectors
+produced by the unmodified reference and vs the oracle.
+
+Tolerances (BASELINE.json north_star): argmax indices bit-exact incl. first-index tie-breaking; rendered targets
+bit-exact; loss, gradients, confidences within REL = 1e-5 relative (fp32).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_rows, load_golden
+from helpers import allclose, assert_joints, assert_rows, close
+from oracle import cases
+from oracle import sbp_oracle as so
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import pose_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device (no CPU fallback exists)"
+    pose_b200.lib()
+    return pose_b200
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def test_device_sigmoid_is_monotone(pb, dev):
+    """The INTERVAL decode mode is exact iff the device sigmoid is monotone: check every adjacent fp32 pair."""
+    v = torch.ones(1, dtype=torch.int64, device=dev)
+    pb._cabi.check(pb.lib().pose_sigmoid_monotone_check(pb._cabi.ptr(v), pb._cabi.stream_ptr(dev)))
+    assert int(v.item()) == 0
+
+
+def test_device_sigmoid_accuracy(pb, dev):
+    """conf = sigmoid(logit) within 1e-5 of torch's sigmoid over the useful range; saturates to exactly 1 / 0."""
+    x = torch.linspace(-30, 30, 3072 * 8, device=dev).reshape(1, 8, 64, 48)
+    # one non-minimal element per map so the max is that element: decode returns its sigmoid as conf
+    probe = torch.tensor([-20.0, -8.0, -2.5, -0.3, 0.0, 0.7, 3.0, 9.0], device=dev)
+    maps = torch.full((1, 8, 64, 48), -50.0, device=dev)
+    maps[0, torch.arange(8), 5, 7] = probe
+    j = pb.decode_batch(maps, -1.0, 1.0, True, mode="direct")[0, :, 2].cpu()
+    want = torch.sigmoid(probe.cpu())
+    assert torch.all((j - want).abs() <= REL * want)
+    sat = torch.tensor([17.0, 30.0, 88.0, 1e4], device=dev).reshape(1, 4, 1, 1).expand(1, 4, 4, 4).contiguous()
+    assert torch.all(pb.decode_batch(sat, 0.5, 1.0, True)[0, :, 2] == 1.0)
+
+
+@pytest.mark.parametrize("name", list(cases.SBP_SHAPES))
+def test_render_bit_exact(pb, dev, name):
+    g = load_golden("sbp_" + name)
+    kp, logits, bbox, iid, cid, meta = cases.sbp_case(name)
+    gen = pb.SBPHeatmapGenerator([meta["h"], meta["w"]], meta["k"], meta["sigma"])
+    assert np.array_equal(gen.g, g["template"])
+    got = gen.render_batch(kp).cpu().numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, g["target"])
+    # per-sample drop-in contract (numpy in, numpy out)
+    one = gen(kp[1])
+    assert isinstance(one, np.ndarray) and np.array_equal(one, g["target"][1])
+    # fp32 keypoints: same kernel, truncation happens on the fp32 value
+    kp32 = kp.astype(np.float32)
+    want32 = so.sbp_render(kp32.astype(np.float64), meta["h"], meta["w"], meta["sigma"])
+    assert np.array_equal(gen.render_batch(torch.from_numpy(kp32).to(dev)).cpu().numpy(), want32)
+
+
+@pytest.mark.parametrize("name", list(cases.SBP_SHAPES))
+def test_loss_and_grad_dense_and_fused(pb, dev, name):
+    g = load_golden("sbp_" + name)
+    kp, logits, bbox, iid, cid, meta = cases.sbp_case(name)
+    target = torch.from_numpy(g["target"]).to(dev)
+    want_loss, want_grad = float(g["loss"]), g["dlogits"]
+    l64, g64 = so.sbp_loss_closed_form_f64(logits, torch.from_numpy(g["target"]))
+
+    for tgt, kw in ((target, {}), (torch.from_numpy(kp).to(dev), {"sigma": meta["sigma"]})):
+        x = logits.to(dev).requires_grad_(True)
+        loss = pb.SBPLoss(**kw)(x, tgt)
+        assert loss.dim() == 0 and loss.dtype == torch.float32 and loss.device == x.device and loss.requires_grad
+        loss.backward()
+        assert close(loss.item(), want_loss, REL), (loss.item(), want_loss)
+        assert close(loss.item(), float(l64), REL)
+        assert allclose(x.grad, want_grad, REL)
+        assert allclose(x.grad, g64, REL)
+
+    # arbitrary upstream gradient (e.g. loss / accumulate_grad_batches) is applied without a host sync
+    x = logits.to(dev).requires_grad_(True)
+    (pb.SBPLoss()(x, target) * 0.37).backward()
+    assert allclose(x.grad, 0.37 * g64, REL)
+    # no-grad (validation) path returns the same value
+    with torch.no_grad():
+        assert close(pb.SBPLoss()(logits.to(dev), target).item(), want_loss, REL)
+
+
+@pytest.mark.parametrize("name", list(cases.SBP_SHAPES))
+def test_decode_matches_reference(pb, dev, name):
+    g = load_golden("sbp_" + name)
+    kp, logits, bbox, iid, cid, meta = cases.sbp_case(name)
+    in_size = meta["input_size"]
+    x = logits.to(dev)
+    for mode in ("interval", "direct"):
+        for thr in (0.25, 0.99):
+            dec = pb.DecodeSBP(list(in_size), thr, True, mode=mode)
+            assert_joints(dec.decode_batch(x), g[f"joints_pred_thr{thr}"], REL)
+        dec = pb.DecodeSBP(list(in_size), 0.99, False, mode=mode)
+        got = dec.decode_batch(torch.from_numpy(g["target"]).to(dev)).cpu().numpy()
+        assert np.array_equal(got, g["joints_target_thr0.99"])        # pred=False: no activation -> bit exact
+    # reference call shape: batch of one -> [K,3]
+    one = pb.DecodeSBP(list(in_size), 0.25, True)(x[2:3])
+    assert tuple(one.shape) == (meta["k"], 3)
+    assert_joints(one, g["joints_pred_thr0.25"][2], REL)
+    with pytest.raises(AssertionError):
+        pb.DecodeSBP(list(in_size), 0.25, True)(x[:2])
+    # nms_sbp drop-in on an activated map
+    h = torch.sigmoid(logits[0]).to(dev)
+    want = so.sbp_decode(torch.sigmoid(logits[0:1]), h.size(-1), 0.8, False)[0]
+    assert_joints(pb.nms_sbp(h, 0.8), want, REL)
+
+
+def test_decode_adversarial_ties_plateaus_borders(pb, dev):
+    g = load_golden("sbp_adversarial")
+    maps = cases.sbp_adversarial_maps().to(dev)
+    for mode in ("interval", "direct"):
+        for thr in (0.25, 0.5):
+            assert_joints(pb.decode_batch(maps, thr, 4.0, True, mode=mode), g[f"joints_pred_thr{thr}"], REL)
+        got = pb.decode_batch(maps, 0.99, 4.0, False, mode=mode).cpu().numpy()
+        assert np.array_equal(got, g["joints_raw_thr0.99"])
+
+
+def test_decode_fp32_threshold_and_modes_agree(pb, dev):
+    x = torch.zeros(1, 2, 8, 8, device=dev)
+    x[0, 0, 3, 4] = float(np.float32(0.99))
+    x[0, 1, 3, 4] = float(np.nextafter(np.float32(0.99), np.float32(2)))
+    j = pb.decode_batch(x, 0.99, 4.0, False).cpu().numpy()
+    assert np.array_equal(j[0, 0], np.array([-4, -4, -1], dtype=np.float32))
+    assert np.array_equal(j[0, 1, :2], np.array([16, 12], dtype=np.float32))
+    # both decode modes are bit-identical on random and on heavily tied data
+    gen = torch.Generator(device=dev).manual_seed(3)
+    a = torch.randn(64, 17, 64, 48, device=dev, generator=gen) * 4
+    b = torch.randint(-3, 4, (64, 17, 64, 48), device=dev, generator=gen).float() * 6.0
+    for t in (a, b):
+        for pred in (True, False):
+            d = pb.decode_batch(t, 0.25, 4.0, pred, mode="direct")
+            i = pb.decode_batch(t, 0.25, 4.0, pred, mode="interval")
+            assert torch.equal(d, i)
+
+
+@pytest.mark.parametrize("name", ["coco", "hires"])
+def test_fused_render_loss_grad_decode_single_pass(pb, dev, name):
+    """One launch: keypoints + logits -> loss, dlogits, rendered target, joints -- all equal to the staged results."""
+    g = load_golden("sbp_" + name)
+    kp, logits, bbox, iid, cid, meta = cases.sbp_case(name)
+    x = logits.to(dev)
+    scale = meta["input_size"][1] / meta["w"]
+    before = pb.launch_count()
+    r = pb.sbp_fused(x, keypoints=kp, sigma=meta["sigma"], want_grad=True, decode=True, conf_threshold=0.25,
+                     coord_scale=scale, want_target=True)
+    assert pb.launch_count() - before == 2           # fused kernel + the deterministic partial-sum finalize
+    assert np.array_equal(r["target"].cpu().numpy(), g["target"])
+    assert close(r["loss"].item(), float(g["loss"]), REL)
+    assert allclose(r["dlogits"], g["dlogits"], REL)
+    assert_joints(r["joints"], g["joints_pred_thr0.25"], REL)
+    assert torch.equal(r["joints"], pb.decode_batch(x, 0.25, scale, True, mode="direct"))
+    # un-normalised numerators reproduce the loss: (5 S_pos + S_neg) / (2 K B)
+    num = r["loss_num"].cpu().numpy()
+    assert close((5 * num[0] + num[1]) / (2 * meta["k"] * x.size(0)), float(g["loss"]), REL)
+    # run-to-run determinism (fixed reduction order, no float atomics)
+    r2 = pb.sbp_fused(x, keypoints=kp, sigma=meta["sigma"], want_grad=True, decode=True, conf_threshold=0.25, coord_scale=scale)
+    assert torch.equal(r["loss"], r2["loss"]) and torch.equal(r["dlogits"], r2["dlogits"])
+
+
+@pytest.mark.parametrize("name", list(cases.SBP_SHAPES))
+def test_update_state_rows(pb, dev, name):
+    g = load_golden("sbp_" + name)
+    kp, logits, bbox, iid, cid, meta = cases.sbp_case(name)
+    tgt = {"bbox": bbox, "image_id": iid, "category_id": cid}
+    m = pb.SBPmAPCOCO(None, list(meta["input_size"]), 0.25)
+    m.update_state(tgt, logits.to(dev))
+    assert_rows(m.result_list, golden_rows(g, "rows_coco"), REL)
+    m.reset_states()
+    assert m.result_list == []
+    p = pb.SBPmAPPIS(None, list(meta["input_size"]), 0.25)
+    p.update_state({k: (v.to(dev) if k == "bbox" else v) for k, v in tgt.items()}, logits.to(dev))
+    assert_rows(p.result_list, golden_rows(g, "rows_pis"), REL)
+
+
+def test_config1_batch32_matches_reference(pb, dev):
+    """BASELINE.json configs[0]: B=32 synthetic batch, every stage against what the reference produced."""
+    g = load_golden("sbp_config1")
+    kp, logits, bbox, iid, cid = so.make_config1_inputs(32)
+    assert cases.digest(kp, logits, bbox) == str(g["inputs_sha"])
+    t = pb.SBPHeatmapGenerator([64, 48], 17, 2).render_batch(kp)
+    assert float(t.double().sum().item()) == float(g["target_sum"]) and int((t > 0).sum()) == int(g["target_nnz"])
+    x = logits.to(dev).requires_grad_(True)
+    loss = pb.SBPLoss(sigma=2)(x, torch.from_numpy(kp).to(dev))
+    loss.backward()
+    assert close(loss.item(), float(g["loss"]), REL)
+    assert allclose(x.grad[:2], g["grad_slice"], REL)
+    assert close(x.grad.double().abs().sum().item(), float(g["grad_abs_sum"]), REL)
+    assert_joints(pb.DecodeSBP([256, 192], 0.25, True).decode_batch(x.detach()), g["joints"], REL)
+
+
+def test_odd_shapes_scalar_path_and_empty_batch(pb, dev):
+    """H*W not a multiple of 4 -> scalar kernels; unaligned views; N == 0."""
+    k, h, w, sigma = 3, 7, 9, 1
+    kp, logits, *_ = so.make_config1_inputs(5, k, h, w, seed=9, torch_seed=9)
+    logits = logits * 3
+    want_t = so.sbp_render(kp, h, w, sigma)
+    assert np.array_equal(pb.SBPHeatmapGenerator([h, w], k, sigma).render_batch(kp).cpu().numpy(), want_t)
+    wl, wg = so.sbp_loss_closed_form_f64(logits, torch.from_numpy(want_t))
+    x = logits.to(dev).requires_grad_(True)
+    loss = pb.SBPLoss(sigma=sigma)(x, torch.from_numpy(kp).to(dev))
+    loss.backward()
+    assert close(loss.item(), float(wl), REL) and allclose(x.grad, wg, REL)
+    for mode in ("interval", "direct"):
+        assert_joints(pb.decode_batch(logits.to(dev), 0.25, 4.0, True, mode=mode), so.sbp_decode(logits, 4 * w, 0.25, True), REL)
+    # a 4-byte-offset view is not 16-byte aligned: dense() keeps it on the device and the kernels still agree
+    big = torch.randn(2 * 17 * 64 * 48 + 1, device=dev)
+    view = big[1:].view(2, 17, 64, 48)
+    assert torch.equal(pb.decode_batch(view, 0.25, 4.0, True), pb.decode_batch(view.clone(), 0.25, 4.0, True))
+    empty = torch.zeros(0, 17, 64, 48, device=dev)
+    assert tuple(pb.decode_batch(empty, 0.25, 4.0, True).shape) == (0, 17, 3)
+
+
+def test_quarter_pixel_refinement_unpinned(pb, dev):
+    """PARITY UNPINNED: the reference has no refinement; checked against our restatement of the published rule."""
+    kp, logits, *_ = so.make_config1_inputs(8, 17, 64, 48, seed=21, torch_seed=21)
+    x = so.realistic_logits(kp, 64, 48).to(dev)
+    base = pb.decode_batch(x, 0.25, 1.0, True)
+    ref = so.sbp_refine_quarter(base.cpu(), torch.sigmoid(x.cpu()))
+    got = pb.decode_batch(x, 0.25, 1.0, True, refine=True).cpu()
+    assert torch.equal(got[..., 2], base.cpu()[..., 2])
+    # sign decisions agree wherever the neighbours differ by more than sigmoid rounding noise
+    assert (got[..., :2] - ref[..., :2]).abs().max() <= 0.5
+    assert ((got[..., :2] - ref[..., :2]).abs() > 0).float().mean() < 0.02
+
+
+def test_no_cpu_fallback(pb):
+    with pytest.raises(pb.PoseB200Error):
+        pb.decode_batch(torch.zeros(1, 1, 8, 8), 0.5)
+    with pytest.raises(pb.PoseB200Error):
+        pb.SBPLoss()(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+
+
+def test_cabi_argument_errors(pb, dev):
+    L, C = pb.lib(), pb._cabi
+    x = torch.zeros(1, 1, 8, 8, device=dev)
+    j = torch.zeros(1, 1, 3, device=dev)
+    assert L.pose_sbp_decode(None, C.ptr(j), 1, 1, 8, 8, 0.5, 1, 1.0, 0, 1, C.stream_ptr(dev)) == -1
+    assert b"NULL" in L.pose_b200_last_error()
+    assert L.pose_sbp_decode(C.ptr(x), C.ptr(j), 1, 0, 8, 8, 0.5, 1, 1.0, 0, 1, C.stream_ptr(dev)) == -1
+    assert L.pose_sbp_decode(C.ptr(x), C.ptr(j), 1, 1, 8, 8, 0.5, 1, 1.0, 0, 7, C.stream_ptr(dev)) == -1
+    loss = torch.zeros((), device=dev)
+    ws = torch.zeros(16, dtype=torch.uint8, device=dev)
+    rc = L.pose_sbp_fused(C.ptr(x), C.ptr(x), None, 0, 1.0, None, 0, None, None, C.ptr(loss), None, None, 0.0, 1.0,
+                          1, 1, 8, 8, 5.0, 1.0, 0.5, 0, C.ptr(ws), ws.numel(), C.stream_ptr(dev))
+    assert rc == -3      # workspace too small
+
+
+# ----------------------------------------------------------------------------------------------- full size (config 2)
+
+@pytest.fixture(scope="module")
+def big(dev):
+    """BASELINE.json configs[1] shapes: B=4096, K=17, 64x48, generated on the device."""
+    b, k, h, w = 4096, 17, 64, 48
+    gen = torch.Generator(device=dev).manual_seed(0)
+    logits = torch.randn(b, k, h, w, device=dev, generator=gen) * 3
+    kp = torch.stack([torch.rand(b, k, device=dev, generator=gen, dtype=torch.float64) * w,
+                      torch.rand(b, k, device=dev, generator=gen, dtype=torch.float64) * h], dim=-1)
+    vis = torch.rand(b, k, device=dev, generator=gen) < 0.85
+    kp[~vis] = -1.0
+    return logits, kp, vis
+
+
+def test_full_size_render_decode_roundtrip(pb, dev, big):
+    """decode(render(kp), thr .99, pred=False) == (4*int(x), 4*int(y), 1) for visible, (-4,-4,-1) for invisible joints."""
+    logits, kp, vis = big
+    t = pb.SBPHeatmapGenerator([64, 48], 17, 2).render_batch(kp)
+    for mode in ("interval", "direct"):
+        j = pb.decode_batch(t, 0.99, 4.0, False, mode=mode)
+        want = torch.where(vis[..., None], torch.stack([4 * kp[..., 0].floor(), 4 * kp[..., 1].floor(), torch.ones_like(kp[..., 0])], -1),
+                           torch.tensor([-4.0, -4.0, -1.0], device=dev, dtype=torch.float64)).float()
+        assert torch.equal(j, want)
+    # linearity-style checksum: every visible interior joint contributes the same template mass
+    interior = vis & (kp[..., 0] >= 8) & (kp[..., 0] < 40) & (kp[..., 1] >= 8) & (kp[..., 1] < 56)
+    mass = t.double().sum(dim=(2, 3))
+    g = so.gauss_template(2).astype(np.float32).astype(np.float64).sum()
+    assert torch.all((mass[interior] - g).abs() < 1e-9) and torch.all(mass[~vis] == 0)
+
+
+def test_full_size_fused_equals_staged_and_oracle_subset(pb, dev, big):
+    logits, kp, vis = big
+    b = logits.size(0)
+    fused = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0)
+    t = pb.SBPHeatmapGenerator([64, 48], 17, 2).render_batch(kp)
+    dense_ = pb.sbp_fused(logits, target=t, want_grad=True)
+    assert close(fused["loss"].item(), dense_["loss"].item(), 1e-6)
+    assert allclose(fused["dlogits"][:64], dense_["dlogits"][:64], 1e-6)
+    assert torch.equal(fused["joints"], pb.decode_batch(logits, 0.25, 4.0, True, mode="interval"))
+    # oracle on a 128-sample subset: loss numerators are additive over samples
+    sub = slice(1000, 1128)
+    ls, gs = so.sbp_loss_closed_form_f64(logits[sub].cpu(), torch.from_numpy(so.sbp_render(kp[sub].cpu().numpy(), 64, 48, 2)))
+    r = pb.sbp_fused(logits[sub], keypoints=kp[sub], sigma=2, want_grad=True, global_batch=b)
+    assert close(r["loss"].item() * b / 128, float(ls), REL)
+    assert allclose(r["dlogits"] * (b / 128), gs, REL)
+    assert allclose(fused["dlogits"][sub] * (b / 128), gs, REL)
+    assert_joints(fused["joints"][sub], so.sbp_decode(logits[sub].cpu(), 192, 0.25, True), REL)
+    # additivity of the un-normalised numerators over shards (what the multi-GPU all-reduce relies on)
+    parts = [pb.sbp_fused(logits[i:i + 1024], keypoints=kp[i:i + 1024], sigma=2, want_grad=False)["loss_num"] for i in range(0, b, 1024)]
+    tot = torch.stack(parts).sum(0)
+    assert allclose(tot, fused["loss_num"], 1e-12)

@@ -1,0 +1,164 @@
+"""GPU parity tests, SPM path (config 4): render, loss fwd/bwd, root NMS + displacement decode, COCO rows.
+
+Peak picks (root x, y, count, order) are bit-exact; rendered targets are bit-exact; loss, gradients, confidences and
+joint coordinates within REL = 1e-5 relative (fp32).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_rows, load_golden
+from helpers import allclose, assert_rows, assert_spm_people, close
+from oracle import cases
+from oracle import spm_oracle as po
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import pose_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device (no CPU fallback exists)"
+    pose_b200.lib()
+    return pose_b200
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("name,n", [("small", 6), ("coco", 4)])
+def test_render_bit_exact(pb, dev, name, n):
+    g = load_golden("spm_" + name)
+    people, target, logits, meta = cases.spm_case(name, n)
+    c, j, cnt = cases.pack_people(people)
+    got = pb.spm_render_batch(c, j, cnt, meta["res"], meta["sigma"]).cpu().numpy()
+    assert got.dtype == np.float32 and got.shape == g["target"].shape
+    assert np.array_equal(got, g["target"])
+    # padding beyond counts[i] must be ignored whatever it holds
+    c2, j2, _ = cases.pack_people(people, pmax=c.shape[1] + 3)
+    c2[:, c.shape[1]:] = 50
+    j2[:, c.shape[1]:] = 60
+    assert np.array_equal(pb.spm_render_batch(c2, j2, cnt, meta["res"], meta["sigma"]).cpu().numpy(), g["target"])
+
+
+def test_generator_dropins(pb, dev):
+    """The reference's three-object protocol (dataset/spm_coco_dataset.py:77-86), per image, numpy in / numpy out."""
+    g = load_golden("spm_small")
+    people, target, logits, meta = cases.spm_case("small", 6)
+    k, res, sigma = meta["k"], meta["res"], meta["sigma"]
+    hg, mg, dg = pb.SPMHeatmapGenerator(res, 1, sigma), pb.SPMMaskGenerator(res, sigma), pb.SPMDisplacementGenerator(res, k)
+    for i, (c, j) in enumerate(people[:3]):
+        hm = hg(c)
+        masks = mg(c)
+        disp = dg(j, masks)
+        assert hm.shape == (1, res, res) and disp.shape == (2 * k, res, res)
+        assert np.array_equal(np.asarray(masks), po.spm_masks(c, res, sigma))
+        assert np.array_equal(np.concatenate([hm, disp], axis=0), g["target"][i])
+
+
+@pytest.mark.parametrize("name,n", [("small", 6), ("coco", 4)])
+def test_loss_and_grad(pb, dev, name, n):
+    g = load_golden("spm_" + name)
+    people, target, logits, meta = cases.spm_case(name, n)
+    tt = torch.from_numpy(g["target"])
+    l64, g64 = po.spm_loss_closed_form_f64(logits, tt)
+    x = logits.to(dev).requires_grad_(True)
+    loss = pb.SPMLoss()(x, tt.to(dev))
+    assert loss.dim() == 0 and loss.requires_grad
+    loss.backward()
+    assert close(loss.item(), float(g["loss"]), REL), (loss.item(), float(g["loss"]))
+    assert close(loss.item(), float(l64), REL)
+    assert allclose(x.grad, g64, REL)
+    if "dlogits" in g:
+        assert allclose(x.grad, g["dlogits"], REL)
+    else:
+        assert allclose(x.grad[:1, :, 40:88, 40:88], g["grad_slice"], REL)
+        assert close(x.grad.double().abs().sum().item(), float(g["grad_abs_sum"]), REL)
+    x2 = logits.to(dev).requires_grad_(True)
+    (pb.SPMLoss()(x2, tt.to(dev)) * 2.5).backward()
+    assert allclose(x2.grad, 2.5 * g64, REL)
+    with torch.no_grad():
+        assert close(pb.SPMLoss()(logits.to(dev), tt.to(dev)).item(), float(g["loss"]), REL)
+    # random logits against a target (exercises |d| >= 1 SmoothL1 branch and saturated activations)
+    gen = torch.Generator().manual_seed(5)
+    xr = torch.randn(logits.shape, generator=gen) * 4
+    lr, gr = po.spm_loss_closed_form_f64(xr, tt)
+    x3 = xr.to(dev).requires_grad_(True)
+    l3 = pb.SPMLoss()(x3, tt.to(dev))
+    l3.backward()
+    assert close(l3.item(), float(lr), REL) and allclose(x3.grad, gr, REL)
+
+
+@pytest.mark.parametrize("name,n", [("small", 6), ("coco", 4)])
+def test_decode_matches_reference(pb, dev, name, n):
+    g = load_golden("spm_" + name)
+    people, target, logits, meta = cases.spm_case(name, n)
+    in_size, sigma = meta["input_size"], meta["sigma"]
+    tt = torch.from_numpy(g["target"])
+    for tag, src, pred, thr in (("pred", logits, True, 0.5), ("target", tt, False, 0.99)):
+        dec = pb.DecodeSPM(in_size, sigma, thr, pred)
+        for b in range(n):
+            r, kj = dec(src[b:b + 1].to(dev))
+            assert_spm_people(r, kj, g[f"roots_{tag}_{b}"], g[f"kps_{tag}_{b}"], REL)
+        # batched form agrees with the per-image drop-in
+        roots, kps, counts, total = dec.decode_batch(src.to(dev))
+        for b in range(n):
+            c = int(counts[b])
+            assert c == g[f"roots_{tag}_{b}"].shape[0] and int(total[b]) == c
+            assert_spm_people(roots[b, :c], kps[b, :c], g[f"roots_{tag}_{b}"], g[f"kps_{tag}_{b}"], REL)
+    m = pb.SPMmAPCOCO(None, in_size, sigma, 0.5)
+    m.update_state({"image_size": [torch.from_numpy(g["image_w"]), torch.from_numpy(g["image_h"])],
+                    "image_id": torch.arange(n) + 7, "category_id": torch.ones(n, dtype=torch.int64)}, logits.to(dev))
+    assert_rows(m.result_list, golden_rows(g, "rows"), REL)
+
+
+def test_nms_rules_empty_overflow_and_gather(pb, dev):
+    # empty decode returns two shape-[0] tensors (utils/spm_utils.py:120-121, :180-181)
+    x = torch.full((1, 3, 16, 16), -9.0, device=dev)
+    r, k = pb.DecodeSPM(64, 1, 0.5, True)(x)
+    assert tuple(r.shape) == (0,) and tuple(k.shape) == (0,)
+    assert pb.SPMmAPCOCO(None, 64, 1, 0.5).result() == 0
+    # radius rule: distance exactly == threshold is suppressed (strict >), sqrt(17) survives; ties -> row-major
+    h = torch.zeros(1, 16, 16)
+    h[0, 5, 5], h[0, 5, 9], h[0, 9, 6] = 0.9, 0.8, 0.7
+    got = pb.nms_spm(h.to(dev), 0.5, 4.0).cpu()
+    assert torch.equal(got, po.spm_nms(h, 0.5, 4.0)) and got.shape[0] == 2
+    h2 = torch.zeros(1, 16, 16)
+    h2[0, 2, 12] = h2[0, 2, 3] = h2[0, 10, 3] = 0.75
+    assert torch.equal(pb.nms_spm(h2.to(dev), 0.5, 4.0).cpu(), po.spm_nms(h2, 0.5, 4.0))
+    # more roots than the fixed buffer: counts are capped, totals reported, the drop-in retries with the exact size
+    dense_map = torch.full((1, 3, 32, 32), 0.0)
+    gen = torch.Generator().manual_seed(1)
+    dense_map[0, 0] = torch.rand(32, 32, generator=gen) * 0.5 + 0.5
+    roots, kps, counts, total = pb.spm_decode_batch(dense_map.to(dev), 32, 1, 0.5, pred=False, max_people=4)
+    want = po.spm_nms(dense_map[0, 0:1], 0.5, 4.0)
+    assert int(counts[0]) == 4 and int(total[0]) == want.shape[0] > 4
+    assert torch.equal(roots[0, :4, :2].cpu(), want[:4, :2])
+    r, _ = pb.DecodeSPM(32, 1, 0.5, False, max_people=4)(dense_map.to(dev))
+    assert torch.equal(r.cpu(), want)
+    # get_spm_keypoints drop-in
+    people, target, logits, meta = cases.spm_case("small", 2)
+    tt = torch.from_numpy(target)
+    roots = po.spm_nms(tt[0, 0:1], 0.99, 4.0)
+    want_k = po.spm_keypoints(roots, tt[0, 1:], 4.0)
+    got_k = pb.get_spm_keypoints(roots.to(dev), tt[0, 1:].to(dev), 4.0)
+    assert allclose(got_k, want_k, REL) and torch.equal(got_k.cpu() == 0, want_k == 0)
+
+
+def test_config4_batch_decode_against_oracle(pb, dev):
+    """Config 4 at a larger batch: 64 multi-person images, every image's picks against the oracle."""
+    people, target, logits, meta = cases.spm_case("coco", 64, seed=777)
+    c, j, cnt = cases.pack_people(people)
+    t = pb.spm_render_batch(c, j, cnt, 128, 1)
+    assert np.array_equal(t.cpu().numpy(), target)
+    roots, kps, counts, total = pb.spm_decode_batch(logits.to(dev), 512, 1, 0.5, True, max_people=32)
+    for b in range(0, 64, 4):
+        wr, wk = po.spm_decode(logits[b:b + 1], 512, 1, 0.5, True)
+        n = int(counts[b])
+        assert_spm_people(roots[b, :n], kps[b, :n], wr, wk, REL)
+    l64, _ = po.spm_loss_closed_form_f64(logits[:8], torch.from_numpy(target[:8]))
+    assert close(pb.spm_loss_fused(logits[:8].to(dev), torch.from_numpy(target[:8]).to(dev), want_grad=False)["loss"].item(),
+                 float(l64), REL)
