@@ -186,6 +186,7 @@ def run_cuda(args):
                         torch.rand(B, device=dev, generator=gen, dtype=torch.float64) * 340 + 60], dim=-1)
     image_id = torch.arange(B, device=dev, dtype=torch.int64) + rank * B
     category_id = torch.ones(B, device=dev, dtype=torch.int64)
+    ids_local = torch.stack([image_id, category_id], dim=1).contiguous()
 
     ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -197,10 +198,10 @@ def run_cuda(args):
                          coord_scale=IN_W / W, global_batch=global_batch)
         if i is not None:
             ev_k1[i].record()
-        rows, score = pb.backproject_rows(r["joints"], bbox, (IN_H, IN_W))
-        loss = pd.global_sbp_loss(r["loss_num"], K, global_batch)
-        rows, score, ids, cats = pd.gather_rows(rows, score, image_id, category_id)
-        return loss, rows, score
+        packed = pb.backproject_packed(r["joints"], bbox, (IN_H, IN_W))
+        loss = pd.global_sbp_loss(r["loss_num"], K, global_batch, local_loss=r["loss"])
+        packed, ids = pd.gather_packed(packed, ids_local)
+        return loss, packed, ids
 
     def fence():
         if world > 1:
@@ -232,8 +233,7 @@ def run_cuda(args):
     h_logits = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True).copy_(logits)
     h_kp = torch.empty(kp.shape, dtype=kp.dtype, pin_memory=True).copy_(kp)
     h_bbox = torch.empty(bbox.shape, dtype=bbox.dtype, pin_memory=True).copy_(bbox)
-    h_rows = torch.empty((global_batch, K, 3), dtype=torch.float32, pin_memory=True)
-    h_score = torch.empty((global_batch,), dtype=torch.float32, pin_memory=True)
+    h_packed = torch.empty((global_batch, 3 * K + 1), dtype=torch.float32, pin_memory=True)
     h_loss = torch.empty((), dtype=torch.float32, pin_memory=True)
     d_logits, d_kp, d_bbox = torch.empty_like(logits), torch.empty_like(kp), torch.empty_like(bbox)
 
@@ -243,11 +243,10 @@ def run_cuda(args):
         d_bbox.copy_(h_bbox, non_blocking=True)
         r = pb.sbp_fused(d_logits, keypoints=d_kp, sigma=SIGMA, want_grad=True, decode=True, conf_threshold=THR,
                          coord_scale=IN_W / W, global_batch=global_batch)
-        rows, score = pb.backproject_rows(r["joints"], d_bbox, (IN_H, IN_W))
-        loss = pd.global_sbp_loss(r["loss_num"], K, global_batch)
-        rows, score, ids, cats = pd.gather_rows(rows, score, image_id, category_id)
-        h_rows.copy_(rows, non_blocking=True)
-        h_score.copy_(score, non_blocking=True)
+        packed = pb.backproject_packed(r["joints"], d_bbox, (IN_H, IN_W))
+        loss = pd.global_sbp_loss(r["loss_num"], K, global_batch, local_loss=r["loss"])
+        packed, ids = pd.gather_packed(packed, ids_local)
+        h_packed.copy_(packed, non_blocking=True)
         h_loss.copy_(loss, non_blocking=True)
 
     e2e_steps = max(3, min(args.steps, 20))
@@ -266,7 +265,7 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     h2d = h_logits.numel() * 4 + h_kp.numel() * 8 + h_bbox.numel() * 8
-    d2h = h_rows.numel() * 4 + h_score.numel() * 4 + 4
+    d2h = h_packed.numel() * 4 + 4
     loss_host = float(h_loss)
 
     if rank == 0:

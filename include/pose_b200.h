@@ -97,9 +97,9 @@ int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W,
 /* ---- back-projection + COCO row fields -- SBPmAPCOCO.update_state utils/sbp_utils.py:141-163,
  *      SBPmAPPIS.update_state utils/sbp_pis_utils.py:23-45.
  * joints [N][K][3] (input-size scale, from decode); bbox [N][4] fp64 (x, y, w, h).
- * rows_out [N][K][3]: (x_img, y_img, 1) for detected joints, (0,0,0) otherwise;
- * score_out [N]: left-to-right fp32 sum of detected confidences / K. */
-int pose_sbp_backproject(const float* joints, const double* bbox, float* rows_out, float* score_out,
+ * packed_out [N][3K+1]: K rows of (x_img, y_img, 1) for detected joints / (0,0,0) otherwise, followed by
+ * the score = left-to-right fp32 sum of detected confidences / K. */
+int pose_sbp_backproject(const float* joints, const double* bbox, float* packed_out,
                          int N, int K, int input_h, int input_w, pose_stream_t stream);
 
 /* ---- SPM render -- SPMHeatmapGenerator/MaskGenerator/DisplacementGenerator

@@ -110,8 +110,8 @@ int pose_gauss_template_host(double sigma, float* out_host, int capacity) {
 int pose_sbp_render(const void* kp, int kp_dtype, float* target, int N, int K, int H, int W, double sigma,
                     const float* lut, int lut_n, pose_stream_t stream) {
     if (int rc = check_map_shape(N, K, H, W)) return rc;
-    if (!kp || !target || !lut || lut_n <= 0 || lut_n > 64 || !(sigma > 0.0)) return fail(POSE_EINVAL, "sbp_render: bad argument");
     if (N == 0) return POSE_OK;
+    if (!kp || !target || !lut || lut_n <= 0 || lut_n > 64 || !(sigma > 0.0)) return fail(POSE_EINVAL, "sbp_render: bad argument");
     pose::SbpRenderParams P;
     P.kp = kp; P.kp_f64 = kp_dtype == POSE_KP_F64; P.target = target; P.lut = lut; P.lut_n = lut_n;
     P.three_sigma = 3 * sigma;
@@ -190,9 +190,9 @@ int pose_scale_grad(float* dlogits, const float* grad_output, unsigned long long
 int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W, float conf_threshold, int apply_sigmoid,
                     float coord_scale, int refine, int mode, pose_stream_t stream) {
     if (int rc = check_map_shape(N, K, H, W)) return rc;
-    if (!x || !joints) return fail(POSE_EINVAL, "sbp_decode: NULL pointer");
     if (mode != POSE_DECODE_DIRECT && mode != POSE_DECODE_INTERVAL) return fail(POSE_EINVAL, "sbp_decode: bad mode %d", mode);
     if (N == 0) return POSE_OK;
+    if (!x || !joints) return fail(POSE_EINVAL, "sbp_decode: NULL pointer");
     pose::SbpDecodeParams P;
     P.x = x; P.joints = joints; P.thr = conf_threshold; P.scale = coord_scale;
     P.n_maps = (long long)N * K; P.H = H; P.W = W; P.HW = H * W; P.divW = make_div(W); P.refine = refine;
@@ -214,13 +214,14 @@ int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W, f
     return check_launch("sbp_decode");
 }
 
-int pose_sbp_backproject(const float* joints, const double* bbox, float* rows_out, float* score_out, int N, int K,
+int pose_sbp_backproject(const float* joints, const double* bbox, float* packed_out, int N, int K,
                          int input_h, int input_w, pose_stream_t stream) {
-    if (N < 0 || K <= 0 || input_h <= 0 || input_w <= 0 || !joints || !bbox || !rows_out || !score_out)
-        return fail(POSE_EINVAL, "sbp_backproject: bad argument");
+    if (N < 0 || K <= 0 || input_h <= 0 || input_w <= 0) return fail(POSE_EINVAL, "sbp_backproject: bad shape");
     if (N == 0) return POSE_OK;
-    pose::sbp_backproject_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(joints, bbox, rows_out, score_out, N, K,
-                                                                                    (double)input_h, (double)input_w);
+    if (!joints || !bbox || !packed_out) return fail(POSE_EINVAL, "sbp_backproject: NULL pointer");
+    const long long threads = (long long)N * 32;
+    pose::sbp_backproject_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(joints, bbox, packed_out, N, K,
+                                                                                                   (double)input_h, (double)input_w);
     return check_launch("sbp_backproject");
 }
 

@@ -10,6 +10,12 @@
 
 namespace pose {
 
+#ifndef POSE_FUSED_U
+#define POSE_FUSED_U 6          // independent 128-bit loads in flight per lane in the fused kernel (tuned: tools/tune_fused.py)
+#endif
+#ifndef POSE_FUSED_MINB
+#define POSE_FUSED_MINB 3       // resident CTAs per SM the fused kernel is compiled for (register cap 80)
+#endif
 constexpr int kSbpThreads = 256;               // 8 warps per CTA
 constexpr int kSbpWarps = kSbpThreads / 32;
 constexpr int kMaxPartialBlocks = 148 * 16;    // upper bound on the persistent grid (workspace sizing)
@@ -161,7 +167,7 @@ __device__ __forceinline__ float loss_elem(float s, float t, float gpos, float g
 }
 
 template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
-__global__ void __launch_bounds__(kSbpThreads) sbp_fused_kernel(SbpFusedParams P) {
+__global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel(SbpFusedParams P) {
     extern __shared__ float lut_s[];
     __shared__ double red[kSbpWarps][2];
     if (TGT == TGT_RENDER) {
@@ -173,7 +179,8 @@ __global__ void __launch_bounds__(kSbpThreads) sbp_fused_kernel(SbpFusedParams P
     const long long warp0 = (long long)blockIdx.x * kSbpWarps + wid;
     const long long nwarps = (long long)gridDim.x * kSbpWarps;
     const int nvec = P.HW / V;
-    constexpr int U = (V == 4) ? 4 : 8;     // independent 128-bit loads in flight per lane
+    constexpr int U = (V == 4) ? POSE_FUSED_U : 8;
+    const int rstep = (32 * V) / P.W, cstep = (32 * V) - rstep * P.W;   // 32 vectors further = rstep rows + cstep columns
     double dpos = 0.0, dneg = 0.0;
 
     for (long long map = warp0; map < P.n_maps; map += nwarps) {
@@ -190,6 +197,9 @@ __global__ void __launch_bounds__(kSbpThreads) sbp_fused_kernel(SbpFusedParams P
         float apos = 0.0f, aneg = 0.0f;
         float best = -INFINITY;
         int besti = 0x7fffffff;
+        // (row, col) of this lane's current vector, advanced by 32 vectors per step (no per-vector division)
+        int row = (int)fdiv((uint32_t)(lane * V), P.divW);
+        int col = lane * V - row * P.W;
 
         for (int base = lane; base < nvec; base += 32 * U) {
             float xv[U][V], tv[U][V];
@@ -206,24 +216,50 @@ __global__ void __launch_bounds__(kSbpThreads) sbp_fused_kernel(SbpFusedParams P
                 const int vi = base + 32 * u;
                 if (vi >= nvec) break;
                 float g[V];
-                bool nonzero = true;
-                if (TGT == TGT_RENDER) nonzero = patch_values<V>(pt, lut_s, P.lut_n, vi * V, P.W, P.divW, tv[u]);
-                if (TGT == TGT_RENDER && !nonzero) {
-                    // zero target: S_neg += s^2, grad = gneg s^2 (1-s)
+                if (TGT == TGT_RENDER) {
+                    // Every lane first takes the zero-target result (the target is zero on ~93% of a map):
+                    //   S_neg += s^2,  dL/dp = gneg s^2 (1-s);
+                    // lanes whose vector touches the joint's Gaussian patch then overwrite their elements.
+                    float sg[V], c[V];
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
-                        const float s = sigmoid_fast(xv[u][j]);
-                        const float s2 = s * s;
-                        aneg += s2;
-                        if (GRAD) g[j] = P.gneg * s2 * (1.0f - s);
-                        if (DEC && s > best) { best = s; besti = vi * V + j; }
+                        const float sj = sigmoid_fast(xv[u][j]);
+                        sg[j] = sj;
+                        c[j] = sj * sj;
+                        if (GRAD) g[j] = P.gneg * fmaf(-c[j], sj, c[j]);
+                        if (DEC && sj > best) { best = sj; besti = vi * V + j; }
+                        if (WTGT) tv[u][j] = 0.0f;
                     }
+                    const int row_last = row + ((col + V - 1) >= P.W ? 1 : 0);
+                    if (row_last >= pt.py0 && row < pt.py1) {
+                        int r = row, cc = col;
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            if (r >= pt.py0 && r < pt.py1 && cc >= pt.px0 && cc < pt.px1) {
+                                const float t = lut_s[(r - pt.uly) * P.lut_n + (cc - pt.ulx)];
+                                if (WTGT) tv[u][j] = t;
+                                if (t > 0.0f) {      // t == 0 (underflowed template tail): the zero-target result stands
+                                    const float d = sg[j] - t;
+                                    c[j] = 0.0f;
+                                    apos = fmaf(d, d, apos);
+                                    if (GRAD) g[j] = P.gpos * d * ((1.0f - sg[j]) * sg[j]);
+                                }
+                            }
+                            if (++cc >= P.W) { cc = 0; ++r; }
+                        }
+                    }
+                    float q = c[0];
+#pragma unroll
+                    for (int j = 1; j < V; ++j) q += c[j];
+                    aneg += q;
+                    col += cstep; row += rstep;
+                    if (col >= P.W) { col -= P.W; ++row; }
                 } else {
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
-                        const float s = sigmoid_fast(xv[u][j]);
-                        g[j] = loss_elem<GRAD>(s, tv[u][j], P.gpos, P.gneg, apos, aneg);
-                        if (DEC && s > best) { best = s; besti = vi * V + j; }
+                        const float sj = sigmoid_fast(xv[u][j]);
+                        g[j] = loss_elem<GRAD>(sj, tv[u][j], P.gpos, P.gneg, apos, aneg);
+                        if (DEC && sj > best) { best = sj; besti = vi * V + j; }
                     }
                 }
                 if (GRAD) Vec<V>::store(dl, vi, g);
@@ -455,30 +491,42 @@ __global__ void __launch_bounds__(kSbpThreads) sbp_decode_kernel(SbpDecodeParams
 
 // ---------------------------------------------------------------- back-projection + COCO row fields
 // SBPmAPCOCO.update_state (utils/sbp_utils.py:141-163): ratio in fp64 -> fp32, fp32 multiply, fp32 add of
-// fp32(bbox origin) (two roundings, no FMA); conf<0 -> (0,0,0); score = sequential fp32 sum / K.
-__global__ void __launch_bounds__(128) sbp_backproject_kernel(const float* __restrict__ joints, const double* __restrict__ bbox,
-                                                              float* __restrict__ rows, float* __restrict__ score,
-                                                              int N, int K, double in_h, double in_w) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+// fp32(bbox origin) (two roundings, no FMA); conf<0 -> (0,0,0); score = left-to-right fp32 sum / K.
+// One warp per sample: lane k handles joint k (coalesced 12-byte rows), lane 0 then folds the K confidences
+// in index order through shuffles so the sum is bit-identical to the reference's python sum().
+// Output is packed [N][3K+1] = K rows of (x_img, y_img, flag) followed by the score -- ready for one all-gather / D2H.
+__global__ void __launch_bounds__(256) sbp_backproject_kernel(const float* __restrict__ joints, const double* __restrict__ bbox,
+                                                              float* __restrict__ packed, int N, int K, double in_h, double in_w) {
+    const int lane = threadIdx.x & 31;
+    const int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (n >= N) return;
-    const double bx = bbox[4 * n], by = bbox[4 * n + 1], bw = bbox[4 * n + 2], bh = bbox[4 * n + 3];
+    const double bx = __ldg(bbox + 4 * n), by = __ldg(bbox + 4 * n + 1), bw = __ldg(bbox + 4 * n + 2), bh = __ldg(bbox + 4 * n + 3);
     const float rx = (float)(bw / in_w), ry = (float)(bh / in_h);
     const float ox = (float)bx, oy = (float)by;
+    const int stride = 3 * K + 1;
     float sum = 0.0f;
-    for (int k = 0; k < K; ++k) {
-        const float* j = joints + ((long long)n * K + k) * 3;
-        float* o = rows + ((long long)n * K + k) * 3;
-        const float c = j[2];
-        if (c < 0.0f) {
-            o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f;
-        } else {
-            o[0] = __fadd_rn(__fmul_rn(j[0], rx), ox);
-            o[1] = __fadd_rn(__fmul_rn(j[1], ry), oy);
-            o[2] = 1.0f;
-            sum = __fadd_rn(sum, c);
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        float c = -1.0f;
+        if (k < K) {
+            const float* j = joints + ((long long)n * K + k) * 3;
+            float* o = packed + (long long)n * stride + 3 * k;
+            c = j[2];
+            if (c < 0.0f) {
+                o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f;
+            } else {
+                o[0] = __fadd_rn(__fmul_rn(j[0], rx), ox);
+                o[1] = __fadd_rn(__fmul_rn(j[1], ry), oy);
+                o[2] = 1.0f;
+            }
+        }
+        const int cnt = min(32, K - k0);
+        for (int i = 0; i < cnt; ++i) {
+            const float ci = __shfl_sync(FULL_MASK, c, i);
+            if (!(ci < 0.0f)) sum = __fadd_rn(sum, ci);
         }
     }
-    score[n] = __fdiv_rn(sum, (float)K);
+    if (lane == 0) packed[(long long)n * stride + 3 * K] = __fdiv_rn(sum, (float)K);
 }
 
 // ---------------------------------------------------------------- sigmoid monotonicity (diagnostic)

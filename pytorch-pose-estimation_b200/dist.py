@@ -27,9 +27,13 @@ def _active(group):
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
-def global_sbp_loss(loss_num, num_keypoints, global_batch, lambda_pos=5.0, lambda_neg=1.0, group=None):
-    """loss_num: fp64[2] local (S_pos, S_neg) -> 0-dim fp32 global loss (same on every rank).  In place on loss_num."""
-    if _active(group):
+def global_sbp_loss(loss_num, num_keypoints, global_batch, lambda_pos=5.0, lambda_neg=1.0, group=None, local_loss=None):
+    """loss_num: fp64[2] local (S_pos, S_neg) -> 0-dim fp32 global loss (same on every rank).  In place on loss_num.
+    With a single rank the kernel's own `local_loss` (already normalised by the global batch) is returned untouched."""
+    if not _active(group):
+        if local_loss is not None:
+            return local_loss
+    else:
         dist.all_reduce(loss_num, op=dist.ReduceOp.SUM, group=group)
     return ((lambda_pos * loss_num[0] + lambda_neg * loss_num[1]) / (2.0 * num_keypoints * global_batch)).to(torch.float32)
 
@@ -40,19 +44,27 @@ def global_spm_loss(loss_num, global_batch, lambda_root=1.0, lambda_disp=0.1, gr
     return ((lambda_root * loss_num[0] + lambda_disp * loss_num[1]) / float(global_batch)).to(torch.float32)
 
 
-def gather_rows(rows, score, image_ids, category_ids, group=None):
-    """All-gather equal-sized shards: rows [B,K,3], score [B], ids [B] -> the same tensors for the global batch,
-    ordered by rank (= by image for contiguous shards).  One packed fp32 gather + one int64 gather."""
-    packed = torch.cat([rows.reshape(rows.size(0), -1), score[:, None]], dim=1).contiguous()
-    ids = torch.stack([image_ids.to(packed.device, torch.int64), category_ids.to(packed.device, torch.int64)], dim=1).contiguous()
+def gather_packed(packed, ids, group=None):
+    """All-gather equal-sized shards of the packed prediction rows [B, 3K+1] (fp32) and ids [B, 2] (int64), ordered by
+    rank (= by image for contiguous shards).  Two collectives, no packing kernels, no host synchronisation."""
     if not _active(group):
-        return rows, score, ids[:, 0], ids[:, 1]
+        return packed, ids
     world = dist.get_world_size(group)
     out_p = torch.empty((world * packed.size(0), packed.size(1)), dtype=packed.dtype, device=packed.device)
-    out_i = torch.empty((world * ids.size(0), 2), dtype=torch.int64, device=ids.device)
+    out_i = torch.empty((world * ids.size(0), ids.size(1)), dtype=ids.dtype, device=ids.device)
     dist.all_gather_into_tensor(out_p, packed, group=group)
     dist.all_gather_into_tensor(out_i, ids, group=group)
+    return out_p, out_i
+
+
+def gather_rows(rows, score, image_ids, category_ids, group=None):
+    """rows [B,K,3], score [B], ids [B] -> the same tensors for the global batch (equal-sized shards)."""
+    if not _active(group):
+        return rows, score, image_ids, category_ids
     k = rows.size(1)
+    packed = torch.cat([rows.reshape(rows.size(0), -1), score[:, None]], dim=1).contiguous()
+    ids = torch.stack([image_ids.to(packed.device, torch.int64), category_ids.to(packed.device, torch.int64)], dim=1).contiguous()
+    out_p, out_i = gather_packed(packed, ids, group)
     return out_p[:, :-1].reshape(-1, k, 3), out_p[:, -1], out_i[:, 0], out_i[:, 1]
 
 

@@ -74,7 +74,7 @@ def scale_grad_(dlogits, grad_output):
 class _SBPLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, target, is_kp, sigma, lp, ln, global_batch):
-        need = logits.requires_grad and torch.is_grad_enabled()
+        need = bool(ctx.needs_input_grad[0])     # grad mode is off inside Function.forward; this is the caller's view
         r = sbp_fused(logits, None if is_kp else target, target if is_kp else None, sigma, want_grad=need,
                       lambda_positive=lp, lambda_negative=ln, global_batch=global_batch)
         ctx.dlogits = r["dlogits"]

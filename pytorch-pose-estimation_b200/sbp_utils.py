@@ -101,12 +101,14 @@ class SBPHeatmapGenerator:
         return self.render_batch(kp)[0].cpu().numpy()
 
 
-def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False, refine=False, mode="interval"):
+def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False, refine=False, mode="direct"):
     """[B,K,H,W] CUDA fp32 -> [B,K,3] (x*scale, y*scale, conf); undetected rows are (-scale,-scale,-1)."""
     x = dense(heatmaps, "heatmaps")
     assert x.dim() == 4
     b, k, h, w = x.shape
     out = torch.empty((b, k, 3), dtype=torch.float32, device=x.device)
+    if b == 0:
+        return out
     m = _cabi.DECODE_INTERVAL if mode == "interval" else _cabi.DECODE_DIRECT
     with torch.cuda.device(x.device):
         check(lib().pose_sbp_decode(ptr(x), ptr(out), b, k, h, w, float(conf_threshold), int(bool(apply_sigmoid)),
@@ -122,7 +124,7 @@ def nms_sbp(heatmaps, conf_threshold=0.8):
 class DecodeSBP(nn.Module):
     """Drop-in for utils/sbp_utils.py:85-118 (same ctor / forward), plus `decode_batch` for B > 1."""
 
-    def __init__(self, input_size, conf_threshold, pred=True, refine=False, mode="interval"):
+    def __init__(self, input_size, conf_threshold, pred=True, refine=False, mode="direct"):
         super().__init__()
         self.input_size = input_size[-1]
         self.conf_threshold = conf_threshold
@@ -138,28 +140,34 @@ class DecodeSBP(nn.Module):
         return self.decode_batch(x)[0]
 
 
-def backproject_rows(joints, bbox, input_size):
-    """joints [B,K,3] (input scale), bbox [B,4] fp64 -> (rows [B,K,3] = (x_img, y_img, 1|0), score [B])."""
+def backproject_packed(joints, bbox, input_size):
+    """joints [B,K,3] (input scale), bbox [B,4] fp64 -> packed [B, 3K+1]: K rows (x_img, y_img, 1|0) then the score."""
     j = dense(joints, "joints")
     bb = dense(bbox.to(j.device) if isinstance(bbox, torch.Tensor) else torch.as_tensor(np.asarray(bbox)).to(j.device),
                "bbox", torch.float64)
     b, k = j.size(0), j.size(1)
-    rows = torch.empty_like(j)
-    score = torch.empty((b,), dtype=torch.float32, device=j.device)
+    packed = torch.empty((b, 3 * k + 1), dtype=torch.float32, device=j.device)
     with torch.cuda.device(j.device):
-        check(lib().pose_sbp_backproject(ptr(j), ptr(bb), ptr(rows), ptr(score), b, k, int(input_size[0]), int(input_size[1]),
+        check(lib().pose_sbp_backproject(ptr(j), ptr(bb), ptr(packed), b, k, int(input_size[0]), int(input_size[1]),
                                          stream_ptr(j.device)), "pose_sbp_backproject")
-    return rows, score
+    return packed
+
+
+def backproject_rows(joints, bbox, input_size):
+    """-> (rows [B,K,3] = (x_img, y_img, 1|0), score [B]) as views of the packed buffer."""
+    p = backproject_packed(joints, bbox, input_size)
+    k = joints.size(1)
+    return p[:, :3 * k].unflatten(1, (k, 3)), p[:, 3 * k]
 
 
 def _ids(v):
     return v.tolist() if isinstance(v, torch.Tensor) else [int(i) for i in v]
 
 
-def rows_to_results(rows, score, image_ids, category_ids, pad=0):
+def packed_to_results(packed, image_ids, category_ids, pad=0):
     """One D2H copy, then plain-Python COCO result dicts (utils/sbp_utils.py:148-164)."""
-    packed = torch.cat([rows.reshape(rows.size(0), -1), score[:, None]], dim=1).cpu()
-    kps, sc = packed[:, :-1], packed[:, -1]
+    host = packed.cpu()
+    kps, sc = host[:, :-1], host[:, -1]
     out = []
     tail = [0] * pad
     for i, (iid, cid) in enumerate(zip(_ids(image_ids), _ids(category_ids))):
@@ -187,8 +195,8 @@ class SBPmAPCOCO:
 
     def update_state(self, target, y_pred):
         joints = self.decoder.decode_batch(y_pred)                       # [B,K,3] at input scale
-        rows, score = backproject_rows(joints, target['bbox'], self.input_size)
-        self.result_list.extend(rows_to_results(rows, score, target['image_id'], target['category_id'], self._pad))
+        packed = backproject_packed(joints, target['bbox'], self.input_size)
+        self.result_list.extend(packed_to_results(packed, target['image_id'], target['category_id'], self._pad))
 
     def result(self):
         if self.coco is None:

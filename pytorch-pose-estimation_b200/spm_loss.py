@@ -30,7 +30,7 @@ def spm_loss_fused(logits, target, want_grad=True, lambda_root=1.0, lambda_disp=
 class _SPMLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, target, lr, ld, global_batch):
-        need = logits.requires_grad and torch.is_grad_enabled()
+        need = bool(ctx.needs_input_grad[0])     # grad mode is off inside Function.forward; this is the caller's view
         r = spm_loss_fused(logits, target, need, lr, ld, global_batch)
         ctx.dlogits = r["dlogits"]
         ctx.in_dtype, ctx.in_shape = logits.dtype, logits.shape

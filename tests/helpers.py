@@ -51,7 +51,8 @@ def assert_rows(got, want, rel):
         a, b = np.array(r["keypoints"], dtype=np.float64), np.array(w["keypoints"], dtype=np.float64)
         assert a.shape == b.shape
         assert np.array_equal(a == 0, b == 0), (r, w)
-        assert np.all(np.abs(a - b) <= rel * np.abs(b) + 1e-12), (r, w)
+        # coordinates: relative to the value, plus 0.1*rel of the row's coordinate range (kx = disp*z + x cancels near 0)
+        assert np.all(np.abs(a - b) <= rel * np.abs(b) + 0.1 * rel * np.abs(b).max() + 1e-12), (r, w)
         assert abs(r["score"] - w["score"]) <= rel * abs(w["score"]) + 1e-12, (r["score"], w["score"])
 
 

@@ -302,6 +302,7 @@ def test_full_size_fused_equals_staged_and_oracle_subset(pb, dev, big):
     assert close(fused["loss"].item(), dense_["loss"].item(), 1e-6)
     assert allclose(fused["dlogits"][:64], dense_["dlogits"][:64], 1e-6)
     assert torch.equal(fused["joints"], pb.decode_batch(logits, 0.25, 4.0, True, mode="interval"))
+    assert torch.equal(fused["joints"], pb.decode_batch(logits, 0.25, 4.0, True, mode="direct"))
     # oracle on a 128-sample subset: loss numerators are additive over samples
     sub = slice(1000, 1128)
     ls, gs = so.sbp_loss_closed_form_f64(logits[sub].cpu(), torch.from_numpy(so.sbp_render(kp[sub].cpu().numpy(), 64, 48, 2)))
@@ -311,6 +312,10 @@ def test_full_size_fused_equals_staged_and_oracle_subset(pb, dev, big):
     assert allclose(fused["dlogits"][sub] * (b / 128), gs, REL)
     assert_joints(fused["joints"][sub], so.sbp_decode(logits[sub].cpu(), 192, 0.25, True), REL)
     # additivity of the un-normalised numerators over shards (what the multi-GPU all-reduce relies on)
-    parts = [pb.sbp_fused(logits[i:i + 1024], keypoints=kp[i:i + 1024], sigma=2, want_grad=False)["loss_num"] for i in range(0, b, 1024)]
+    # (same kernel variant as `fused`: the per-map fp32 partial sums are then bit-identical, only the fp64 grouping differs)
+    parts = [pb.sbp_fused(logits[i:i + 1024], keypoints=kp[i:i + 1024], sigma=2, want_grad=True, decode=True, conf_threshold=0.25,
+                          coord_scale=4.0)["loss_num"] for i in range(0, b, 1024)]
     tot = torch.stack(parts).sum(0)
     assert allclose(tot, fused["loss_num"], 1e-12)
+    other = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=False)["loss_num"]      # another variant: fp32 rounding differs
+    assert allclose(other, fused["loss_num"], 1e-7)

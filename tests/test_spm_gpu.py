@@ -71,15 +71,17 @@ def test_loss_and_grad(pb, dev, name, n):
     loss.backward()
     assert close(loss.item(), float(g["loss"]), REL), (loss.item(), float(g["loss"]))
     assert close(loss.item(), float(l64), REL)
-    assert allclose(x.grad, g64, REL)
+    # displacement gradients carry (1 - tanh^2): with |tanh| ~ 0.999 the fp32 subtraction cancels three digits, in the
+    # reference as much as here, so the absolute floor is 1e-5 of the gradient scale (atol_frac=1), not 1e-6
+    assert allclose(x.grad, g64, REL, atol_frac=1.0)
     if "dlogits" in g:
-        assert allclose(x.grad, g["dlogits"], REL)
+        assert allclose(x.grad, g["dlogits"], REL, atol_frac=1.0)
     else:
-        assert allclose(x.grad[:1, :, 40:88, 40:88], g["grad_slice"], REL)
+        assert allclose(x.grad[:1, :, 40:88, 40:88], g["grad_slice"], REL, atol_frac=1.0)
         assert close(x.grad.double().abs().sum().item(), float(g["grad_abs_sum"]), REL)
     x2 = logits.to(dev).requires_grad_(True)
     (pb.SPMLoss()(x2, tt.to(dev)) * 2.5).backward()
-    assert allclose(x2.grad, 2.5 * g64, REL)
+    assert allclose(x2.grad, 2.5 * g64, REL, atol_frac=1.0)
     with torch.no_grad():
         assert close(pb.SPMLoss()(logits.to(dev), tt.to(dev)).item(), float(g["loss"]), REL)
     # random logits against a target (exercises |d| >= 1 SmoothL1 branch and saturated activations)
@@ -89,7 +91,7 @@ def test_loss_and_grad(pb, dev, name, n):
     x3 = xr.to(dev).requires_grad_(True)
     l3 = pb.SPMLoss()(x3, tt.to(dev))
     l3.backward()
-    assert close(l3.item(), float(lr), REL) and allclose(x3.grad, gr, REL)
+    assert close(l3.item(), float(lr), REL) and allclose(x3.grad, gr, REL, atol_frac=1.0)
 
 
 @pytest.mark.parametrize("name,n", [("small", 6), ("coco", 4)])

@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""Per-kernel device timings (CUDA events) at the BASELINE.json shapes, as a fraction of the HBM roofline.
+
+    python tools/kbench.py [--batch 4096] [--reps 30] [--out gpurun_out/kbench.json] [--only NAME]
+
+Every stage is timed alone, inputs resident in HBM and larger than L2, 5 warm-up + `reps` timed launches, median and best.
+Algorithmic bytes per heat map are the SURVEY.md 8(d) figures.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pose_b200 as pb  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def timeit(fn, reps, warm=5):
+    """Queue-saturated timing: `reps` back-to-back launches between one event pair (host launch overhead hidden behind
+    the previous kernel), repeated 3 times; returns (median, best) per-launch ms."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) / reps)
+    ts.sort()
+    return ts[1], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--reps", type=int, default=30)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kbench.json"))
+    ap.add_argument("--only", default="")
+    ap.add_argument("--hw", default="64x48")
+    ap.add_argument("--k", type=int, default=17)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    B, K = args.batch, args.k
+    H, W = map(int, args.hw.split("x"))
+    sigma = 2 if H == 64 else -1
+    gen = torch.Generator(device=dev).manual_seed(0)
+    logits = torch.randn(B, K, H, W, device=dev, generator=gen) * 3
+    kp = torch.stack([torch.rand(B, K, device=dev, generator=gen, dtype=torch.float64) * W,
+                      torch.rand(B, K, device=dev, generator=gen, dtype=torch.float64) * H], -1)
+    kp[torch.rand(B, K, device=dev, generator=gen) >= 0.85] = -1
+    bbox = torch.rand(B, 4, device=dev, generator=gen, dtype=torch.float64) * 300 + 40
+    gen_t = pb.SBPHeatmapGenerator([H, W], K, sigma)
+    target = gen_t.render_batch(kp)
+    realistic = torch.logit((target + 0.05 * torch.rand(target.shape, device=dev, generator=gen)).clamp(1e-4, 1 - 1e-4))
+    joints = pb.decode_batch(logits, 0.25, 4.0, True)
+    maps = B * K
+    map_bytes = H * W * 4
+    pk = peak()
+    res = {}
+
+    def run(name, fn, bytes_per_map):
+        if args.only and args.only not in name:
+            return
+        med, best = timeit(fn, args.reps)
+        gbs = bytes_per_map * maps / (med * 1e-3) / 1e9
+        res[name] = {"ms_median": med, "ms_best": best, "heatmaps_per_s": maps / (med * 1e-3), "GBps": gbs, "frac_of_measured_peak": gbs / pk,
+                     "bytes_per_map": bytes_per_map}
+        print(f"{name:44s} {med*1e3:9.1f} us (best {best*1e3:8.1f})  {gbs:8.1f} GB/s  {gbs/pk*100:5.1f}%  {maps/(med*1e-3)/1e6:8.1f} M maps/s", flush=True)
+
+    out = torch.empty_like(logits)
+    run("render_only", lambda: gen_t.render_batch(kp, out=out), map_bytes + 8)
+    run("fused_render_loss_grad", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma), 2 * map_bytes + 8)
+    run("fused_render_loss_grad_decode", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, decode=True, coord_scale=4.0), 2 * map_bytes + 20)
+    run("fused_render_loss_only(no grad)", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, want_grad=False), map_bytes + 8)
+    run("fused_render_loss_decode(no grad)", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, want_grad=False, decode=True), map_bytes + 20)
+    run("dense_loss_grad", lambda: pb.sbp_fused(logits, target=target), 3 * map_bytes)
+    run("dense_loss_only(no grad)", lambda: pb.sbp_fused(logits, target=target, want_grad=False), 2 * map_bytes)
+    for pred in (True, False):
+        for mode in ("interval", "direct"):
+            for src, tag in ((logits, "randn"), (realistic, "realistic")):
+                run(f"decode_{mode}_pred{int(pred)}_{tag}", lambda: pb.decode_batch(src, 0.25, 4.0, pred, mode=mode), map_bytes + 12)
+    run("decode_interval_pred0_target_thr.99", lambda: pb.decode_batch(target, 0.99, 4.0, False), map_bytes + 12)
+    run("backproject_rows", lambda: pb.backproject_rows(joints, bbox, (256, 192)), 24)
+
+    if not args.only or "spm" in args.only:
+        from oracle import cases        # input generator only (tools/ is not the product)
+        n = 256
+        people, tgt_np, lg, meta = cases.spm_case("coco", 16, seed=99)
+        c, j, cnt = cases.pack_people(people)
+        reps_ = n // 16
+        c = torch.from_numpy(c).repeat(reps_, 1, 1).to(dev)
+        j = torch.from_numpy(j).repeat(reps_, 1, 1, 1).to(dev)
+        cnt = torch.from_numpy(cnt).repeat(reps_).to(dev)
+        t = pb.spm_render_batch(c, j, cnt, 128, 1)
+        x = lg.repeat(reps_, 1, 1, 1).to(dev)
+        img_bytes = 35 * 128 * 128 * 4
+
+        def run_spm(name, fn, bytes_per_img):
+            med, best = timeit(fn, args.reps)
+            gbs = bytes_per_img * n / (med * 1e-3) / 1e9
+            res[name] = {"ms_median": med, "ms_best": best, "images_per_s": n / (med * 1e-3), "GBps": gbs, "frac_of_measured_peak": gbs / pk}
+            print(f"{name:44s} {med*1e3:9.1f} us (best {best*1e3:8.1f})  {gbs:8.1f} GB/s  {gbs/pk*100:5.1f}%  {n/(med*1e-3)/1e3:8.1f} K img/s", flush=True)
+
+        run_spm("spm_render(N=256)", lambda: pb.spm_render_batch(c, j, cnt, 128, 1), img_bytes)
+        run_spm("spm_loss_grad(N=256)", lambda: pb.spm_loss_fused(x, t), 3 * img_bytes)
+        run_spm("spm_loss_only(N=256)", lambda: pb.spm_loss_fused(x, t, want_grad=False), 2 * img_bytes)
+        run_spm("spm_decode(N=256,thr=.5)", lambda: pb.spm_decode_batch(x, 512, 1, 0.5, True, 32), 128 * 128 * 4)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    json.dump({"batch": B, "K": K, "H": H, "W": W, "peak_GBps": pk, "results": res}, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

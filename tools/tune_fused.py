@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""A/B the fused kernel's compile-time knobs (loads in flight per lane, resident CTAs per SM).
+
+    python tools/tune_fused.py --build          # here (no GPU): nvcc one .so per variant into build/tune/
+    python tools/tune_fused.py --run            # on the B200: time every variant, JSON to gpurun_out/tune_fused.json
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "build", "tune")
+SRC = os.path.join(ROOT, "pytorch-pose-estimation_b200", "csrc", "api.cu")
+VARIANTS = [(u, m) for u in (2, 4, 6, 8) for m in (2, 3, 4, 5)]
+
+
+def build():
+    os.makedirs(OUT, exist_ok=True)
+    procs = []
+    for u, m in VARIANTS:
+        lib = os.path.join(OUT, f"libpose_u{u}_m{m}.so")
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+               f"-DPOSE_FUSED_U={u}", f"-DPOSE_FUSED_MINB={m}", "-o", lib, SRC]
+        procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for lib, p in procs:
+        out, _ = p.communicate()
+        print(os.path.basename(lib), "ok" if p.returncode == 0 else "FAILED\n" + out)
+
+
+def run(reps):
+    import torch
+    from pose_b200 import _cabi
+    from pose_b200.sbp_utils import _gauss_template
+    dev = torch.device("cuda", 0)
+    B, K, H, W = 4096, 17, 64, 48
+    gen = torch.Generator(device=dev).manual_seed(0)
+    logits = torch.randn(B, K, H, W, device=dev, generator=gen) * 3
+    kp = torch.stack([torch.rand(B, K, device=dev, generator=gen, dtype=torch.float64) * W,
+                      torch.rand(B, K, device=dev, generator=gen, dtype=torch.float64) * H], -1)
+    kp[torch.rand(B, K, device=dev, generator=gen) >= 0.85] = -1
+    lut = torch.from_numpy(_gauss_template(2).astype("float32")).to(dev)
+    dl = torch.empty_like(logits)
+    joints = torch.empty(B, K, 3, device=dev)
+    loss = torch.empty((), device=dev)
+    num = torch.empty(2, dtype=torch.float64, device=dev)
+    ws = torch.empty(1 << 17, dtype=torch.uint8, device=dev)
+    st = _cabi.stream_ptr(dev)
+    res = {}
+    ref = None
+    for u, m in VARIANTS:
+        path = os.path.join(OUT, f"libpose_u{u}_m{m}.so")
+        if not os.path.exists(path):
+            continue
+        L = ctypes.CDLL(path)
+        fn = L.pose_sbp_fused
+        fn.restype, fn.argtypes = _cabi.SIGNATURES["pose_sbp_fused"]
+
+        def call():
+            rc = fn(_cabi.ptr(logits), None, _cabi.ptr(kp), 1, 2.0, _cabi.ptr(lut), 15, _cabi.ptr(dl), None, _cabi.ptr(loss), _cabi.ptr(num),
+                    _cabi.ptr(joints), 0.25, 4.0, B, K, H, W, 5.0, 1.0, 1.0 / (2 * K * B), 1 | 4, _cabi.ptr(ws), ws.numel(), st)
+            assert rc == 0, rc
+        for _ in range(5):
+            call()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                call()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b) / reps)
+        sig = (float(loss), float(dl.double().abs().sum()), float(joints.double().sum()))
+        ref = ref or sig
+        res[f"U{u}_M{m}"] = {"ms": min(ts), "GBps": 24596 * B * K / (min(ts) * 1e-3) / 1e9, "same_result": sig == ref}
+        print(f"U={u} MINB={m}: {min(ts)*1e3:7.1f} us  {res[f'U{u}_M{m}']['GBps']:7.1f} GB/s  same={sig == ref}", flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "tune_fused.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--build", action="store_true")
+    ap.add_argument("--run", action="store_true")
+    ap.add_argument("--reps", type=int, default=40)
+    a = ap.parse_args()
+    if a.build:
+        build()
+    if a.run:
+        run(a.reps)
