@@ -70,6 +70,10 @@ int pose_sbp_render(const void* kp, int kp_dtype, float* target, int N, int K, i
  *   dlogits   = dloss/dlogits (scaled by inv_norm; written iff POSE_F_GRAD)
  *   loss_out  [1] fp32; loss_num_out [2] fp64 = (S_pos, S_neg) un-normalised (may be NULL)
  *   joints    [N][K][3] fp32 (x*scale, y*scale, conf) / (-scale,-scale,-1)   iff POSE_F_DECODE
+ *   bbox [N][4] fp64 + packed_out [N][3K+1] (both or neither; needs POSE_F_DECODE): the epilogue launch also
+ *             back-projects the joints exactly like pose_sbp_backproject (SBPmAPCOCO.update_state :141-163)
+ * Two launches: the fused streaming kernel, then one epilogue grid (fixed-order loss reduction + back-projection)
+ * issued with programmatic dependent launch.
  * workspace: pose_sbp_fused_workspace_bytes(); contents need no initialisation. */
 unsigned long long pose_sbp_fused_workspace_bytes(void);
 int pose_sbp_fused(const float* logits, const float* target_in,
@@ -79,8 +83,15 @@ int pose_sbp_fused(const float* logits, const float* target_in,
                    float* joints, float conf_threshold, float coord_scale,
                    int N, int K, int H, int W,
                    float lambda_pos, float lambda_neg, double inv_norm,
-                   unsigned flags, void* workspace, unsigned long long workspace_bytes,
+                   unsigned flags,
+                   const double* bbox, float* packed_out, int input_h, int input_w,
+                   void* workspace, unsigned long long workspace_bytes,
                    pose_stream_t stream);
+
+/* ---- fixed-order reduction of n (a, b) fp64 pairs, `stride` doubles apart: loss = (w0*A + w1*B)*inv_norm.
+ *      Used on the all-gathered per-rank numerators (multi-GPU global loss); one CTA, deterministic. */
+int pose_loss_reduce(const double* pairs, int n, long long stride, double w0, double w1, double inv_norm,
+                     float* loss_out, double* num_out, pose_stream_t stream);
 
 /* ---- in-place dlogits *= *grad_output (device scalar), skipped in-kernel when it is 1.0f --
  *      autograd backward of the 0-dim loss (module/sbp_detector.py:24-28 -> loss.backward()). */

@@ -25,7 +25,8 @@ SIGNATURES = {
     "pose_sbp_render": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp]),
     "pose_sbp_fused_workspace_bytes": (_ull, []),
     "pose_sbp_fused": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f,
-                            _i, _i, _i, _i, _f, _f, _d, _u, _vp, _ull, _vp]),
+                            _i, _i, _i, _i, _f, _f, _d, _u, _vp, _vp, _i, _i, _vp, _ull, _vp]),
+    "pose_loss_reduce": (_i, [_vp, _i, _c.c_longlong, _d, _d, _d, _vp, _vp, _vp]),
     "pose_scale_grad": (_i, [_vp, _vp, _ull, _vp]),
     "pose_sbp_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _f, _i, _i, _vp]),
     "pose_sbp_backproject": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -55,6 +55,23 @@ int persistent_grid(Kern kern, int threads, size_t smem, long long work_ctas) {
     return (int)(g < 1 ? 1 : g);
 }
 
+// launch with programmatic stream serialisation: the grid may be scheduled while its predecessor drains; the kernel
+// itself calls griddepcontrol.wait before touching the predecessor's results
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 int check_map_shape(int N, int K, int H, int W) {
     if (N < 0 || K <= 0 || H <= 0 || W <= 0) return fail(POSE_EINVAL, "bad shape N=%d K=%d H=%d W=%d", N, K, H, W);
     if ((long long)H * W >= (1ll << 20) || W >= (1 << 11)) return fail(POSE_EINVAL, "map too large: H=%d W=%d", H, W);
@@ -137,6 +154,7 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
                    const float* lut, int lut_n, float* dlogits, float* target_out, float* loss_out,
                    double* loss_num_out, float* joints, float conf_threshold, float coord_scale, int N, int K,
                    int H, int W, float lambda_pos, float lambda_neg, double inv_norm, unsigned flags,
+                   const double* bbox, float* packed_out, int input_h, int input_w,
                    void* workspace, unsigned long long workspace_bytes, pose_stream_t stream) {
     if (int rc = check_map_shape(N, K, H, W)) return rc;
     if (!logits) return fail(POSE_EINVAL, "sbp_fused: logits is NULL");
@@ -146,6 +164,8 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
     if ((flags & POSE_F_TARGET_OUT) && (!target_out || !kp)) return fail(POSE_EINVAL, "sbp_fused: POSE_F_TARGET_OUT needs target_out and kp");
     if ((flags & POSE_F_DECODE) && !joints) return fail(POSE_EINVAL, "sbp_fused: POSE_F_DECODE without joints");
     if (!loss_out && !loss_num_out) return fail(POSE_EINVAL, "sbp_fused: no loss output");
+    if ((bbox != nullptr) != (packed_out != nullptr)) return fail(POSE_EINVAL, "sbp_fused: bbox and packed_out go together");
+    if (bbox && (!(flags & POSE_F_DECODE) || input_h <= 0 || input_w <= 0)) return fail(POSE_EINVAL, "sbp_fused: back-projection needs POSE_F_DECODE and the input size");
     if (!workspace || workspace_bytes < pose_sbp_fused_workspace_bytes()) return fail(POSE_EWORKSPACE, "sbp_fused: workspace too small");
     if (!aligned16(workspace)) return fail(POSE_EALIGN, "sbp_fused: workspace must be 16-byte aligned");
     if (dlogits == logits || (target_out && target_out == logits)) return fail(POSE_EINVAL, "sbp_fused: outputs must not alias logits");
@@ -172,8 +192,20 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
         else rc = vec ? dispatch_fused<4, pose::TGT_DENSE>(P, flags, smem, st, &grid) : dispatch_fused<1, pose::TGT_DENSE>(P, flags, smem, st, &grid);
         if (rc) return rc;
     }
-    pose::loss_finalize_kernel<<<1, 256, 0, st>>>(P.partials, grid, (double)lambda_pos, (double)lambda_neg, inv_norm, loss_out, loss_num_out);
-    return check_launch("loss_finalize");
+    pose::SbpEpilogueParams E;
+    E.partials = P.partials; E.nblocks = grid; E.w0 = (double)lambda_pos; E.w1 = (double)lambda_neg; E.inv_norm = inv_norm;
+    E.loss_out = loss_out; E.num_out = loss_num_out;
+    E.joints = joints; E.bbox = bbox; E.packed = packed_out; E.N = bbox ? N : 0; E.K = K; E.in_h = (double)input_h; E.in_w = (double)input_w;
+    const unsigned bp_ctas = bbox ? (unsigned)(((long long)N * 32 + 255) / 256) : 0u;
+    launch_pdl(pose::sbp_epilogue_kernel, bp_ctas + 1u, 256u, st, E);
+    return check_launch("sbp_epilogue");
+}
+
+int pose_loss_reduce(const double* pairs, int n, long long stride, double w0, double w1, double inv_norm, float* loss_out,
+                     double* num_out, pose_stream_t stream) {
+    if (!pairs || n <= 0 || stride < 2 || (!loss_out && !num_out)) return fail(POSE_EINVAL, "loss_reduce: bad argument");
+    launch_pdl(pose::loss_reduce_kernel, 1u, 256u, (cudaStream_t)stream, pairs, n, stride, w0, w1, inv_norm, loss_out, num_out);
+    return check_launch("loss_reduce");
 }
 
 int pose_scale_grad(float* dlogits, const float* grad_output, unsigned long long n, pose_stream_t stream) {
@@ -272,8 +304,9 @@ int pose_spm_loss(const float* logits, const float* target, float* dlogits, floa
         }
         if (int rc = check_launch("spm_loss")) return rc;
     }
-    pose::loss_finalize_kernel<<<1, 256, 0, st>>>(P.partials, grid, (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out);
-    return check_launch("loss_finalize");
+    launch_pdl(pose::loss_reduce_kernel, 1u, 256u, st, (const double*)P.partials, grid, 2ll, (double)lambda_root, (double)lambda_disp,
+               inv_norm, loss_out, loss_num_out);
+    return check_launch("loss_reduce");
 }
 
 unsigned long long pose_spm_decode_workspace_bytes(int N, int R) { (void)N; (void)R; return 0ull; }

@@ -33,6 +33,12 @@ __device__ __forceinline__ void stg_stream(float* p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (sm_90+)
+// Primary grid: allow the next grid in the stream to be scheduled early.  Secondary grid: block until every
+// prerequisite grid has completed and flushed its memory.  Both are no-ops for launches without the PDL attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- activations
 // sigmoid(x) = 1 / (1 + 2^(-x*log2 e)) on the SFU: one MUFU.EX2 + one MUFU.RCP.
 // Max error a few ulp (inside the 1e-5 parity tolerance); saturates cleanly: x -> +inf gives 1,

@@ -170,6 +170,7 @@ template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
 __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel(SbpFusedParams P) {
     extern __shared__ float lut_s[];
     __shared__ double red[kSbpWarps][2];
+    pdl_launch_dependents();      // the epilogue grid may be scheduled as our CTAs retire; it waits for our completion itself
     if (TGT == TGT_RENDER) {
         for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
         __syncthreads();
@@ -301,13 +302,13 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel
     }
 }
 
-// deterministic second stage: one CTA sums the per-CTA partials in a fixed order
-__global__ void __launch_bounds__(256) loss_finalize_kernel(const double* __restrict__ partials, int nblocks,
-                                                            double w0, double w1, double inv_norm,
-                                                            float* __restrict__ loss_out, double* __restrict__ num_out) {
+// Deterministic second stage of the loss: sum `n` (a, b) fp64 pairs, `stride` doubles apart, in a fixed order (no float
+// atomics), then loss = (w0*A + w1*B) * inv_norm.  Runs in one CTA.
+__device__ __forceinline__ void reduce_pairs_cta(const double* __restrict__ pairs, int n, long long stride, double w0, double w1,
+                                                 double inv_norm, float* __restrict__ loss_out, double* __restrict__ num_out) {
     __shared__ double sa[256], sb[256];
     double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += 256) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+    for (int i = threadIdx.x; i < n; i += 256) { a += pairs[i * stride]; b += pairs[i * stride + 1]; }
     sa[threadIdx.x] = a; sb[threadIdx.x] = b;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
@@ -318,6 +319,67 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const double* __rest
         if (num_out) { num_out[0] = sa[0]; num_out[1] = sb[0]; }
         if (loss_out) loss_out[0] = (float)((w0 * sa[0] + w1 * sb[0]) * inv_norm);
     }
+}
+
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const double* __restrict__ pairs, int n, long long stride, double w0, double w1,
+                                                          double inv_norm, float* __restrict__ loss_out, double* __restrict__ num_out) {
+    pdl_wait();
+    reduce_pairs_cta(pairs, n, stride, w0, w1, inv_norm, loss_out, num_out);
+}
+
+// back-projection + COCO row fields of one sample by one warp.
+// SBPmAPCOCO.update_state (utils/sbp_utils.py:141-163): ratio in fp64 -> fp32, fp32 multiply, fp32 add of
+// fp32(bbox origin) (two roundings, no FMA); conf<0 -> (0,0,0); score = left-to-right fp32 sum / K.
+// Lane k handles joint k, lane 0 then folds the K confidences in index order through shuffles so the sum is
+// bit-identical to the reference's python sum().  Output is packed [N][3K+1] = K rows of (x_img, y_img, flag) followed
+// by the score -- ready for one all-gather / D2H.
+__device__ __forceinline__ void backproject_sample(const float* __restrict__ joints, const double* __restrict__ bbox,
+                                                   float* __restrict__ packed, int n, int K, double in_h, double in_w, int lane) {
+    const double bx = __ldg(bbox + 4 * n), by = __ldg(bbox + 4 * n + 1), bw = __ldg(bbox + 4 * n + 2), bh = __ldg(bbox + 4 * n + 3);
+    const float rx = (float)(bw / in_w), ry = (float)(bh / in_h);
+    const float ox = (float)bx, oy = (float)by;
+    const int stride = 3 * K + 1;
+    float sum = 0.0f;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        float c = -1.0f;
+        if (k < K) {
+            const float* j = joints + ((long long)n * K + k) * 3;
+            float* o = packed + (long long)n * stride + 3 * k;
+            c = j[2];
+            if (c < 0.0f) {
+                o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f;
+            } else {
+                o[0] = __fadd_rn(__fmul_rn(j[0], rx), ox);
+                o[1] = __fadd_rn(__fmul_rn(j[1], ry), oy);
+                o[2] = 1.0f;
+            }
+        }
+        const int cnt = min(32, K - k0);
+        for (int i = 0; i < cnt; ++i) {
+            const float ci = __shfl_sync(FULL_MASK, c, i);
+            if (!(ci < 0.0f)) sum = __fadd_rn(sum, ci);
+        }
+    }
+    if (lane == 0) packed[(long long)n * stride + 3 * K] = __fdiv_rn(sum, (float)K);
+}
+
+// Epilogue of the fused step, one launch: the LAST CTA reduces the loss partials, the others back-project the decoded
+// joints (8 samples per CTA).  Launched with programmatic stream serialisation: it is scheduled while the fused kernel
+// drains and blocks in griddepcontrol.wait until that grid has completed and its writes are visible.
+struct SbpEpilogueParams {
+    const double* partials; int nblocks; double w0, w1, inv_norm; float* loss_out; double* num_out;
+    const float* joints; const double* bbox; float* packed; int N, K; double in_h, in_w;
+};
+
+__global__ void __launch_bounds__(256) sbp_epilogue_kernel(SbpEpilogueParams P) {
+    pdl_wait();
+    if (blockIdx.x == gridDim.x - 1) {
+        reduce_pairs_cta(P.partials, P.nblocks, 2, P.w0, P.w1, P.inv_norm, P.loss_out, P.num_out);
+        return;
+    }
+    const int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (n < P.N) backproject_sample(P.joints, P.bbox, P.packed, n, P.K, P.in_h, P.in_w, threadIdx.x & 31);
 }
 
 // dlogits *= *g, whole launch is a no-op when *g == 1 (the usual loss.backward())
@@ -489,44 +551,11 @@ __global__ void __launch_bounds__(kSbpThreads) sbp_decode_kernel(SbpDecodeParams
     }
 }
 
-// ---------------------------------------------------------------- back-projection + COCO row fields
-// SBPmAPCOCO.update_state (utils/sbp_utils.py:141-163): ratio in fp64 -> fp32, fp32 multiply, fp32 add of
-// fp32(bbox origin) (two roundings, no FMA); conf<0 -> (0,0,0); score = left-to-right fp32 sum / K.
-// One warp per sample: lane k handles joint k (coalesced 12-byte rows), lane 0 then folds the K confidences
-// in index order through shuffles so the sum is bit-identical to the reference's python sum().
-// Output is packed [N][3K+1] = K rows of (x_img, y_img, flag) followed by the score -- ready for one all-gather / D2H.
+// ---------------------------------------------------------------- stand-alone back-projection (one warp per sample)
 __global__ void __launch_bounds__(256) sbp_backproject_kernel(const float* __restrict__ joints, const double* __restrict__ bbox,
                                                               float* __restrict__ packed, int N, int K, double in_h, double in_w) {
-    const int lane = threadIdx.x & 31;
     const int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (n >= N) return;
-    const double bx = __ldg(bbox + 4 * n), by = __ldg(bbox + 4 * n + 1), bw = __ldg(bbox + 4 * n + 2), bh = __ldg(bbox + 4 * n + 3);
-    const float rx = (float)(bw / in_w), ry = (float)(bh / in_h);
-    const float ox = (float)bx, oy = (float)by;
-    const int stride = 3 * K + 1;
-    float sum = 0.0f;
-    for (int k0 = 0; k0 < K; k0 += 32) {
-        const int k = k0 + lane;
-        float c = -1.0f;
-        if (k < K) {
-            const float* j = joints + ((long long)n * K + k) * 3;
-            float* o = packed + (long long)n * stride + 3 * k;
-            c = j[2];
-            if (c < 0.0f) {
-                o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f;
-            } else {
-                o[0] = __fadd_rn(__fmul_rn(j[0], rx), ox);
-                o[1] = __fadd_rn(__fmul_rn(j[1], ry), oy);
-                o[2] = 1.0f;
-            }
-        }
-        const int cnt = min(32, K - k0);
-        for (int i = 0; i < cnt; ++i) {
-            const float ci = __shfl_sync(FULL_MASK, c, i);
-            if (!(ci < 0.0f)) sum = __fadd_rn(sum, ci);
-        }
-    }
-    if (lane == 0) packed[(long long)n * stride + 3 * K] = __fdiv_rn(sum, (float)K);
+    if (n < N) backproject_sample(joints, bbox, packed, n, K, in_h, in_w, threadIdx.x & 31);
 }
 
 // ---------------------------------------------------------------- sigmoid monotonicity (diagnostic)

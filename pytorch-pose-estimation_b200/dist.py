@@ -57,6 +57,64 @@ def gather_packed(packed, ids, group=None):
     return out_p, out_i
 
 
+class ShardExchange:
+    """ONE all-gather per step for everything the ranks exchange.
+
+    Per-rank send buffer = [ packed prediction rows [B,3K+1] fp32 | loss numerators [2] fp64 | ids [B,2] int64 ].
+    The fused kernel's epilogue writes rows and numerators straight into it (`out_views()`), so no packing kernel runs;
+    after `exchange()` every rank holds all shards in rank (= image) order and `global_loss()` reduces the gathered
+    numerators in a fixed order on the device (bit-identical on every rank, no second collective).
+    """
+
+    def __init__(self, batch_local, num_keypoints, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if _active(group) else 1
+        self.b, self.k = batch_local, num_keypoints
+        row_bytes = batch_local * (3 * num_keypoints + 1) * 4
+        self.off_num = (row_bytes + 15) // 16 * 16
+        self.off_ids = self.off_num + 16
+        self.nbytes = self.off_ids + batch_local * 16
+        self.send = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.recv = torch.zeros((self.world, self.nbytes), dtype=torch.uint8, device=device) if self.world > 1 else self.send.view(1, -1)
+        self.packed = self.send[:row_bytes].view(torch.float32).view(batch_local, 3 * num_keypoints + 1)
+        self.loss_num = self.send[self.off_num:self.off_num + 16].view(torch.float64)
+        self.ids = self.send[self.off_ids:].view(torch.int64).view(batch_local, 2)
+        self._row_bytes = row_bytes
+        self.loss = torch.zeros((), dtype=torch.float32, device=device)
+
+    def out_views(self):
+        """kwargs for sbp_fused(out=...): write rows and numerators directly into the send buffer."""
+        return {"packed": self.packed, "loss_num": self.loss_num}
+
+    def exchange(self):
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.recv.view(-1), self.send, group=self.group)
+        return self
+
+    def gathered_packed(self):
+        """[world*B, 3K+1] fp32 rows in image order (a copy for world > 1: the per-rank blocks are strided in `recv`)."""
+        if self.world == 1:
+            return self.packed
+        return self.recv[:, :self._row_bytes].contiguous().view(torch.float32).view(self.world * self.b, 3 * self.k + 1)
+
+    def gathered_ids(self):
+        if self.world == 1:
+            return self.ids
+        return self.recv[:, self.off_ids:].contiguous().view(torch.int64).view(self.world * self.b, 2)
+
+    def global_loss(self, global_batch, lambda_pos=5.0, lambda_neg=1.0, local_loss=None):
+        """0-dim fp32 loss of the global batch from the gathered numerators (call after exchange())."""
+        if self.world == 1 and local_loss is not None:
+            return local_loss
+        from ._cabi import check, lib, ptr, stream_ptr
+        nums = self.recv.view(-1)[self.off_num:]
+        with torch.cuda.device(self.send.device):
+            check(lib().pose_loss_reduce(ptr(nums), self.world, self.nbytes // 8, float(lambda_pos), float(lambda_neg),
+                                         1.0 / (2.0 * self.k * global_batch), ptr(self.loss), None, stream_ptr(self.send.device)),
+                  "pose_loss_reduce")
+        return self.loss
+
+
 def gather_rows(rows, score, image_ids, category_ids, group=None):
     """rows [B,K,3], score [B], ids [B] -> the same tensors for the global batch (equal-sized shards)."""
     if not _active(group):

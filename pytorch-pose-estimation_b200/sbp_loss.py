@@ -14,12 +14,16 @@ from .sbp_utils import _gauss_template, _kp_tensor, _templates
 
 
 def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, decode=False, conf_threshold=0.25,
-              coord_scale=1.0, want_target=False, lambda_positive=5.0, lambda_negative=1.0, global_batch=None):
+              coord_scale=1.0, want_target=False, lambda_positive=5.0, lambda_negative=1.0, global_batch=None,
+              bbox=None, input_size=None, out=None):
     """One pass over the logits: loss (+dlogits) (+rendered target) (+decoded joints).
 
-    Returns dict(loss 0-dim fp32, loss_num fp64[2] = un-normalised (S_pos, S_neg), dlogits, target, joints);
+    Returns dict(loss 0-dim fp32, loss_num fp64[2] = un-normalised (S_pos, S_neg), dlogits, target, joints, packed);
     entries not requested are None.  `global_batch` (default: local B) sets the 1/(2*K*B) normalisation so
-    image shards on several GPUs produce gradients of the global-batch loss.
+    image shards on several GPUs produce gradients of the global-batch loss.  With `bbox` [B,4] fp64 and
+    `input_size` (H_in, W_in) the same call also back-projects the decoded joints into `packed` [B,3K+1]
+    (SBPmAPCOCO.update_state arithmetic).  `out` may carry preallocated `dlogits`, `joints`, `packed`, `loss`,
+    `loss_num` tensors (e.g. views into a communication buffer).
     """
     x = dense(logits, "input")
     assert x.dim() == 4, "input must be [B,K,H,W]"
@@ -40,18 +44,34 @@ def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, dec
         g = _gauss_template(sig)
         lut, lut_n = _templates.get(g, sig, dev), g.shape[0]
         kp_dtype = _cabi.KP_F64 if kp.dtype == torch.float64 else _cabi.KP_F32
-    dlogits = t_out = joints = None
+    out = out or {}
+    dlogits = t_out = joints = packed = bb = None
     if want_grad:
         flags |= _cabi.F_GRAD
-        dlogits = torch.empty_like(x)
+        dlogits = out.get("dlogits")
+        if dlogits is None:
+            dlogits = torch.empty_like(x)
     if want_target and kp is not None:
         flags |= _cabi.F_TARGET_OUT
         t_out = torch.empty_like(x)
-    if decode:
+    if decode or bbox is not None:
         flags |= _cabi.F_DECODE
-        joints = torch.empty((b, k, 3), dtype=torch.float32, device=dev)
-    loss = torch.empty((), dtype=torch.float32, device=dev)
-    num = torch.empty((2,), dtype=torch.float64, device=dev)
+        joints = out.get("joints")
+        if joints is None:
+            joints = torch.empty((b, k, 3), dtype=torch.float32, device=dev)
+    in_h = in_w = 0
+    if bbox is not None:
+        bb = dense(bbox.to(dev) if isinstance(bbox, torch.Tensor) else torch.as_tensor(bbox).to(dev), "bbox", torch.float64)
+        in_h, in_w = int(input_size[0]), int(input_size[1])
+        packed = out.get("packed")
+        if packed is None:
+            packed = torch.empty((b, 3 * k + 1), dtype=torch.float32, device=dev)
+    loss = out.get("loss")
+    if loss is None:
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+    num = out.get("loss_num")
+    if num is None:
+        num = torch.empty((2,), dtype=torch.float64, device=dev)
     nbytes = int(lib().pose_sbp_fused_workspace_bytes())
     ws = _cabi.workspace(dev, nbytes)
     inv_norm = 1.0 / (2.0 * k * (global_batch if global_batch is not None else b)) if b > 0 else 0.0
@@ -59,8 +79,9 @@ def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, dec
         check(lib().pose_sbp_fused(ptr(x), ptr(t_in), ptr(kp), kp_dtype, sig, ptr(lut), lut_n, ptr(dlogits), ptr(t_out),
                                    ptr(loss), ptr(num), ptr(joints), float(conf_threshold), float(coord_scale),
                                    b, k, h, w, float(lambda_positive), float(lambda_negative), inv_norm, flags,
+                                   ptr(bb), ptr(packed), in_h, in_w,
                                    ptr(ws), ws.numel(), stream_ptr(dev)), "pose_sbp_fused")
-    return dict(loss=loss, loss_num=num, dlogits=dlogits, target=t_out, joints=joints)
+    return dict(loss=loss, loss_num=num, dlogits=dlogits, target=t_out, joints=joints, packed=packed)
 
 
 def scale_grad_(dlogits, grad_output):

@@ -169,6 +169,11 @@ def test_fused_render_loss_grad_decode_single_pass(pb, dev, name):
     # un-normalised numerators reproduce the loss: (5 S_pos + S_neg) / (2 K B)
     num = r["loss_num"].cpu().numpy()
     assert close((5 * num[0] + num[1]) / (2 * meta["k"] * x.size(0)), float(g["loss"]), REL)
+    # the same call can also back-project (bbox given): the epilogue launch writes the packed COCO rows
+    rb = pb.sbp_fused(x, keypoints=kp, sigma=meta["sigma"], want_grad=True, decode=True, conf_threshold=0.25, coord_scale=scale,
+                      bbox=bbox, input_size=meta["input_size"])
+    assert torch.equal(rb["packed"], pb.backproject_packed(r["joints"], bbox, meta["input_size"]))
+    assert_rows(pb.packed_to_results(rb["packed"], iid, cid), golden_rows(g, "rows_coco"), REL)
     # run-to-run determinism (fixed reduction order, no float atomics)
     r2 = pb.sbp_fused(x, keypoints=kp, sigma=meta["sigma"], want_grad=True, decode=True, conf_threshold=0.25, coord_scale=scale)
     assert torch.equal(r["loss"], r2["loss"]) and torch.equal(r["dlogits"], r2["dlogits"])

@@ -61,7 +61,7 @@ def run(reps):
 
         def call():
             rc = fn(_cabi.ptr(logits), None, _cabi.ptr(kp), 1, 2.0, _cabi.ptr(lut), 15, _cabi.ptr(dl), None, _cabi.ptr(loss), _cabi.ptr(num),
-                    _cabi.ptr(joints), 0.25, 4.0, B, K, H, W, 5.0, 1.0, 1.0 / (2 * K * B), 1 | 4, _cabi.ptr(ws), ws.numel(), st)
+                    _cabi.ptr(joints), 0.25, 4.0, B, K, H, W, 5.0, 1.0, 1.0 / (2 * K * B), 1 | 4, None, None, 0, 0, _cabi.ptr(ws), ws.numel(), st)
             assert rc == 0, rc
         for _ in range(5):
             call()
