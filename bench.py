@@ -345,7 +345,12 @@ def run_cuda(args):
                                               f"{torch.get_num_threads()} torch threads)"}
         _emit(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: destroying a communicator whose collectives were captured in a CUDA graph
+        # can block; every rank has finished its work and rank 0 has printed, so a barrier and a plain exit are enough
+        fence()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -263,8 +263,13 @@ def test_cabi_argument_errors(pb, dev):
     loss = torch.zeros((), device=dev)
     ws = torch.zeros(16, dtype=torch.uint8, device=dev)
     rc = L.pose_sbp_fused(C.ptr(x), C.ptr(x), None, 0, 1.0, None, 0, None, None, C.ptr(loss), None, None, 0.0, 1.0,
-                          1, 1, 8, 8, 5.0, 1.0, 0.5, 0, C.ptr(ws), ws.numel(), C.stream_ptr(dev))
+                          1, 1, 8, 8, 5.0, 1.0, 0.5, 0, None, None, 0, 0, C.ptr(ws), ws.numel(), C.stream_ptr(dev))
     assert rc == -3      # workspace too small
+    big_ws = torch.zeros(int(L.pose_sbp_fused_workspace_bytes()), dtype=torch.uint8, device=dev)
+    bb = torch.zeros(1, 4, dtype=torch.float64, device=dev)
+    rc = L.pose_sbp_fused(C.ptr(x), C.ptr(x), None, 0, 1.0, None, 0, None, None, C.ptr(loss), None, None, 0.0, 1.0,
+                          1, 1, 8, 8, 5.0, 1.0, 0.5, 0, C.ptr(bb), None, 256, 192, C.ptr(big_ws), big_ws.numel(), C.stream_ptr(dev))
+    assert rc == -1 and b"bbox and packed_out" in L.pose_b200_last_error()
 
 
 # ----------------------------------------------------------------------------------------------- full size (config 2)
