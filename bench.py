@@ -189,15 +189,23 @@ def run_cuda(args):
                         torch.rand(B, device=dev, generator=gen, dtype=torch.float64) * 340 + 60], dim=-1)
     image_id = torch.arange(B, device=dev, dtype=torch.int64) + rank * B
     category_id = torch.ones(B, device=dev, dtype=torch.int64)
-    ex = pd.ShardExchange(B, K, dev)
-    ex.ids.copy_(torch.stack([image_id, category_id], dim=1))
+    ex, ex_kind = pd.make_exchange(B, K, dev, image_id, category_id, prefer_p2p=not args.nccl)
     dlogits = torch.empty_like(logits)
     joints = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
     loss_local = torch.empty((), dtype=torch.float32, device=dev)
-    outs = dict(ex.out_views(), dlogits=dlogits, joints=joints, loss=loss_local)
+    outs = dict(dlogits=dlogits, joints=joints, loss=loss_local)
+    if ex_kind != "p2p":
+        outs.update(ex.out_views())
 
     def step(src_logits=logits, src_kp=kp, src_bbox=bbox):
-        """One pass of the hot path over the batch: 2 launches of ours (+ 1 NCCL all-gather and 1 reduce launch for N>1)."""
+        """One pass of the hot path over the batch.  N=1: 2 launches (fused kernel + epilogue).  N>1: + 1 launch that
+        waits for the peers' rows (stored over NVLink by every rank's epilogue) and reduces the global loss -- or, on
+        the NCCL fallback, 1 all-gather + 1 reduce launch."""
+        if ex_kind == "p2p":
+            pb.sbp_fused(src_logits, keypoints=src_kp, sigma=SIGMA, want_grad=True, decode=True, conf_threshold=THR,
+                         coord_scale=IN_W / W, global_batch=global_batch, bbox=src_bbox, input_size=(IN_H, IN_W), out=outs,
+                         exchange=ex)
+            return ex.finish(global_batch)
         r = pb.sbp_fused(src_logits, keypoints=src_kp, sigma=SIGMA, want_grad=True, decode=True, conf_threshold=THR,
                          coord_scale=IN_W / W, global_batch=global_batch, bbox=src_bbox, input_size=(IN_H, IN_W), out=outs)
         ex.exchange()
@@ -221,10 +229,15 @@ def run_cuda(args):
             step()
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
+        host_steps = getattr(ex, "steps", 0)
         with torch.cuda.graph(graph):
             loss_graph = step()
+        if ex_kind == "p2p":
+            ex.steps = host_steps          # capturing ran no device work: keep the host mirror of the step counter in sync
         for _ in range(3):
             graph.replay()
+        if ex_kind == "p2p":
+            ex.advance(3)
         fence()
     run_step = graph.replay if graph is not None else step
 
@@ -238,6 +251,8 @@ def run_cuda(args):
             run_step()
         e1.record()
         fence()
+    if graph is not None and ex_kind == "p2p":
+        ex.advance(args.steps)
     if graph is None:
         launches = pb.launch_count() - launches0
     else:            # graph replays do not pass through the library: count the launches of one eager step and scale
@@ -312,8 +327,9 @@ def run_cuda(args):
             "data": "synthetic",
             "config": {"workload": f"SBP 256x192 (configs[1]): B={B} per GPU x {K} joints x {H}x{W} fp32 heat maps, sigma {SIGMA}; "
                                    "fused render+loss+grad+decode + back-projection"
-                                   + ("; NCCL loss all-reduce + prediction all-gather" if world > 1 else ""),
-                       "batch_per_gpu": B, "global_batch": global_batch, "partition": f"images x{world}",
+                                   + ({"p2p": "; rows + loss numerators exchanged by the epilogue kernel over NVLink peer memory (no NCCL call)",
+                                       "nccl": "; one NCCL all-gather (rows + loss numerators + ids) per step"}.get(ex_kind, "")),
+                       "batch_per_gpu": B, "global_batch": global_batch, "partition": f"images x{world}", "exchange": ex_kind,
                        "l2": "inputs (856 MB logits per GPU) larger than the 126 MB L2; no explicit flush",
                        "kp_dtype": "f64", "loss": loss_host, "cuda_graph": graph is not None},
             "roofline": {"bound": "hbm", "kernel": "sbp_fused_kernel<4,RENDER,GRAD,DECODE> (+ its 1-CTA loss-reduce epilogue launch)",
@@ -362,6 +378,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="images per GPU")
     ap.add_argument("--ref-sample", type=int, default=64, help="images per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N>1: use the NCCL all-gather exchange instead of the peer-memory epilogue")
     ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything libraries print (e.g. NCCL's version banner) is sent to stderr

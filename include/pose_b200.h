@@ -35,12 +35,14 @@ extern "C" {
 #define POSE_F_GRAD 1u          /* write dlogits                                   */
 #define POSE_F_TARGET_OUT 2u    /* also materialise the rendered target (render mode only) */
 #define POSE_F_DECODE 4u        /* also decode joints from sigmoid(logits) in the same pass */
+#define POSE_F_TMA 8u           /* stage the maps through shared memory with bulk async copies (render mode, 16-byte aligned) */
 
 /* decode modes */
 #define POSE_DECODE_DIRECT 0    /* activation on every element, argmax on activated values */
 #define POSE_DECODE_INTERVAL 1  /* max logit first, then first index inside the activation's pre-image of the max */
 
 typedef void* pose_stream_t;
+struct pose_exchange;
 
 /* ---- library ------------------------------------------------------------------------------- */
 int pose_b200_version(void);
@@ -72,6 +74,7 @@ int pose_sbp_render(const void* kp, int kp_dtype, float* target, int N, int K, i
  *   joints    [N][K][3] fp32 (x*scale, y*scale, conf) / (-scale,-scale,-1)   iff POSE_F_DECODE
  *   bbox [N][4] fp64 + packed_out [N][3K+1] (both or neither; needs POSE_F_DECODE): the epilogue launch also
  *             back-projects the joints exactly like pose_sbp_backproject (SBPmAPCOCO.update_state :141-163)
+ *   exchange (may be NULL; needs bbox): multi-GPU -- see pose_exchange_t below; packed_out may then be NULL
  * Two launches: the fused streaming kernel, then one epilogue grid (fixed-order loss reduction + back-projection)
  * issued with programmatic dependent launch.
  * workspace: pose_sbp_fused_workspace_bytes(); contents need no initialisation. */
@@ -85,8 +88,29 @@ int pose_sbp_fused(const float* logits, const float* target_in,
                    float lambda_pos, float lambda_neg, double inv_norm,
                    unsigned flags,
                    const double* bbox, float* packed_out, int input_h, int input_w,
+                   const struct pose_exchange* exchange,
                    void* workspace, unsigned long long workspace_bytes,
                    pose_stream_t stream);
+
+/* ---- multi-GPU exchange over peer-mapped (symmetric) memory -- replaces NCCL for the per-step all-gather.
+ * Every rank owns one exchange buffer of pose_exchange_layout() bytes, zero-initialised, mapped into every other
+ * rank's address space (e.g. torch.distributed._symmetric_memory); peer_base[r] is rank r's buffer as seen from THIS
+ * process.  Passing the descriptor to pose_sbp_fused makes the epilogue store rows / loss numerators / ids into every
+ * rank's receive region and raise a per-rank flag; pose_exchange_finish waits for all flags of the step and reduces
+ * the gathered numerators (rank order) into the global-batch loss.  Receive regions are double-buffered by step
+ * parity; rows_offset/ids_offset of the just-finished step are pose_exchange_t.off_rows/off_ids[step & 1]. */
+#define POSE_MAX_PEERS 16
+typedef struct pose_exchange {
+    int world, rank;
+    int batch_local, num_keypoints;
+    void* peer_base[POSE_MAX_PEERS];
+    unsigned long long off_ctrl, off_flags, off_rows[2], off_nums[2], off_ids[2];
+    const long long* ids_local;               /* device [batch_local][2] (image_id, category_id) of this rank */
+} pose_exchange_t;
+/* fills the off_* fields of *x from world / batch_local / num_keypoints and returns the buffer size in bytes */
+unsigned long long pose_exchange_layout(pose_exchange_t* x);
+int pose_exchange_finish(const pose_exchange_t* x, double w0, double w1, double inv_norm, float* loss_out,
+                         pose_stream_t stream);
 
 /* ---- fixed-order reduction of n (a, b) fp64 pairs, `stride` doubles apart: loss = (w0*A + w1*B)*inv_norm.
  *      Used on the all-gathered per-rank numerators (multi-GPU global loss); one CTA, deterministic. */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpose_b200.so")
 
 KP_F32, KP_F64 = 0, 1
-F_GRAD, F_TARGET_OUT, F_DECODE = 1, 2, 4
+F_GRAD, F_TARGET_OUT, F_DECODE, F_TMA = 1, 2, 4, 8
 DECODE_DIRECT, DECODE_INTERVAL = 0, 1
 
 _c = ctypes
@@ -25,7 +25,9 @@ SIGNATURES = {
     "pose_sbp_render": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp]),
     "pose_sbp_fused_workspace_bytes": (_ull, []),
     "pose_sbp_fused": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f,
-                            _i, _i, _i, _i, _f, _f, _d, _u, _vp, _vp, _i, _i, _vp, _ull, _vp]),
+                            _i, _i, _i, _i, _f, _f, _d, _u, _vp, _vp, _i, _i, _vp, _vp, _ull, _vp]),
+    "pose_exchange_layout": (_ull, [_vp]),
+    "pose_exchange_finish": (_i, [_vp, _d, _d, _d, _vp, _vp]),
     "pose_loss_reduce": (_i, [_vp, _i, _c.c_longlong, _d, _d, _d, _vp, _vp, _vp]),
     "pose_scale_grad": (_i, [_vp, _vp, _ull, _vp]),
     "pose_sbp_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _f, _i, _i, _vp]),
@@ -38,6 +40,17 @@ SIGNATURES = {
     "pose_spm_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp]),
     "pose_sigmoid_monotone_check": (_i, [_vp, _vp]),
 }
+
+MAX_PEERS = 16
+
+
+class ExchangeDesc(ctypes.Structure):
+    """pose_exchange_t (include/pose_b200.h)."""
+    _fields_ = [("world", _i), ("rank", _i), ("batch_local", _i), ("num_keypoints", _i),
+                ("peer_base", _vp * MAX_PEERS),
+                ("off_ctrl", _ull), ("off_flags", _ull), ("off_rows", _ull * 2), ("off_nums", _ull * 2), ("off_ids", _ull * 2),
+                ("ids_local", _vp)]
+
 
 _lib = None
 _lock = threading.Lock()

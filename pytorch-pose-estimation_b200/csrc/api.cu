@@ -7,6 +7,8 @@
 
 #include "../../include/pose_b200.h"
 #include "sbp_kernels.cuh"
+#include "sbp_tma_kernels.cuh"
+#include "exchange_kernels.cuh"
 #include "spm_kernels.cuh"
 
 namespace {
@@ -72,6 +74,17 @@ void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStrea
     cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+pose::ExchangeDev to_dev(const pose_exchange_t& x) {
+    pose::ExchangeDev d;
+    memset(&d, 0, sizeof(d));
+    d.world = x.world; d.rank = x.rank; d.B = x.batch_local; d.K = x.num_keypoints;
+    for (int r = 0; r < x.world && r < pose::kMaxPeers; ++r) d.peer[r] = reinterpret_cast<unsigned char*>(x.peer_base[r]);
+    d.off_ctrl = x.off_ctrl; d.off_flags = x.off_flags;
+    for (int p = 0; p < 2; ++p) { d.off_rows[p] = x.off_rows[p]; d.off_nums[p] = x.off_nums[p]; d.off_ids[p] = x.off_ids[p]; }
+    d.ids_local = x.ids_local;
+    return d;
+}
+
 int check_map_shape(int N, int K, int H, int W) {
     if (N < 0 || K <= 0 || H <= 0 || W <= 0) return fail(POSE_EINVAL, "bad shape N=%d K=%d H=%d W=%d", N, K, H, W);
     if ((long long)H * W >= (1ll << 20) || W >= (1 << 11)) return fail(POSE_EINVAL, "map too large: H=%d W=%d", H, W);
@@ -90,6 +103,19 @@ int launch_fused(const pose::SbpFusedParams& P0, size_t smem, cudaStream_t st, i
     *grid_out = grid;
     return check_launch("sbp_fused");
 }
+template <bool GRAD, bool DEC>
+int launch_fused_tma(const pose::SbpFusedParams& P0, cudaStream_t st, int* grid_out) {
+    pose::SbpFusedParams P = P0;
+    const size_t smem = pose::sbp_tma_smem_bytes(P.lut_n);
+    cudaError_t e = cudaFuncSetAttribute(pose::sbp_fused_tma_kernel<GRAD, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "sbp_fused(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const long long ctas = (P.n_maps + pose::kTmaWarps - 1) / pose::kTmaWarps;
+    const int grid = persistent_grid(pose::sbp_fused_tma_kernel<GRAD, DEC>, pose::kTmaThreads, smem, ctas);
+    pose::sbp_fused_tma_kernel<GRAD, DEC><<<grid, pose::kTmaThreads, smem, st>>>(P);
+    *grid_out = grid;
+    return check_launch("sbp_fused_tma");
+}
+
 template <int V, int TGT>
 int dispatch_fused(const pose::SbpFusedParams& P, unsigned flags, size_t smem, cudaStream_t st, int* grid) {
     const bool g = flags & POSE_F_GRAD, t = (flags & POSE_F_TARGET_OUT) && TGT == pose::TGT_RENDER, d = flags & POSE_F_DECODE;
@@ -155,6 +181,7 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
                    double* loss_num_out, float* joints, float conf_threshold, float coord_scale, int N, int K,
                    int H, int W, float lambda_pos, float lambda_neg, double inv_norm, unsigned flags,
                    const double* bbox, float* packed_out, int input_h, int input_w,
+                   const struct pose_exchange* exchange,
                    void* workspace, unsigned long long workspace_bytes, pose_stream_t stream) {
     if (int rc = check_map_shape(N, K, H, W)) return rc;
     if (!logits) return fail(POSE_EINVAL, "sbp_fused: logits is NULL");
@@ -164,7 +191,14 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
     if ((flags & POSE_F_TARGET_OUT) && (!target_out || !kp)) return fail(POSE_EINVAL, "sbp_fused: POSE_F_TARGET_OUT needs target_out and kp");
     if ((flags & POSE_F_DECODE) && !joints) return fail(POSE_EINVAL, "sbp_fused: POSE_F_DECODE without joints");
     if (!loss_out && !loss_num_out) return fail(POSE_EINVAL, "sbp_fused: no loss output");
-    if ((bbox != nullptr) != (packed_out != nullptr)) return fail(POSE_EINVAL, "sbp_fused: bbox and packed_out go together");
+    if (packed_out && !bbox) return fail(POSE_EINVAL, "sbp_fused: bbox and packed_out go together");
+    if (bbox && !packed_out && !exchange) return fail(POSE_EINVAL, "sbp_fused: bbox and packed_out go together");
+    if (exchange) {
+        if (!bbox) return fail(POSE_EINVAL, "sbp_fused: the exchange needs bbox (back-projected rows are what is exchanged)");
+        if (exchange->world < 1 || exchange->world > POSE_MAX_PEERS || exchange->rank < 0 || exchange->rank >= exchange->world ||
+            exchange->batch_local != N || exchange->num_keypoints != K || !exchange->ids_local)
+            return fail(POSE_EINVAL, "sbp_fused: bad exchange descriptor");
+    }
     if (bbox && (!(flags & POSE_F_DECODE) || input_h <= 0 || input_w <= 0)) return fail(POSE_EINVAL, "sbp_fused: back-projection needs POSE_F_DECODE and the input size");
     if (!workspace || workspace_bytes < pose_sbp_fused_workspace_bytes()) return fail(POSE_EWORKSPACE, "sbp_fused: workspace too small");
     if (!aligned16(workspace)) return fail(POSE_EALIGN, "sbp_fused: workspace must be 16-byte aligned");
@@ -188,7 +222,12 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
                          (!(flags & POSE_F_GRAD) || aligned16(dlogits)) && (!(flags & POSE_F_TARGET_OUT) || aligned16(target_out));
         const size_t smem = kp ? (size_t)lut_n * lut_n * sizeof(float) : 0;
         int rc;
-        if (kp) rc = vec ? dispatch_fused<4, pose::TGT_RENDER>(P, flags, smem, st, &grid) : dispatch_fused<1, pose::TGT_RENDER>(P, flags, smem, st, &grid);
+        const bool tma = (flags & POSE_F_TMA) && kp && vec && !(flags & POSE_F_TARGET_OUT) && lut_n <= 31;
+        if (tma) {
+            const bool g = flags & POSE_F_GRAD, d = flags & POSE_F_DECODE;
+            rc = g ? (d ? launch_fused_tma<true, true>(P, st, &grid) : launch_fused_tma<true, false>(P, st, &grid))
+                   : (d ? launch_fused_tma<false, true>(P, st, &grid) : launch_fused_tma<false, false>(P, st, &grid));
+        } else if (kp) rc = vec ? dispatch_fused<4, pose::TGT_RENDER>(P, flags, smem, st, &grid) : dispatch_fused<1, pose::TGT_RENDER>(P, flags, smem, st, &grid);
         else rc = vec ? dispatch_fused<4, pose::TGT_DENSE>(P, flags, smem, st, &grid) : dispatch_fused<1, pose::TGT_DENSE>(P, flags, smem, st, &grid);
         if (rc) return rc;
     }
@@ -197,8 +236,37 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
     E.loss_out = loss_out; E.num_out = loss_num_out;
     E.joints = joints; E.bbox = bbox; E.packed = packed_out; E.N = bbox ? N : 0; E.K = K; E.in_h = (double)input_h; E.in_w = (double)input_w;
     const unsigned bp_ctas = bbox ? (unsigned)(((long long)N * 32 + 255) / 256) : 0u;
+    if (exchange) {
+        launch_pdl(pose::sbp_epilogue_p2p_kernel, bp_ctas + 1u, 256u, st, E, to_dev(*exchange));
+        return check_launch("sbp_epilogue_p2p");
+    }
     launch_pdl(pose::sbp_epilogue_kernel, bp_ctas + 1u, 256u, st, E);
     return check_launch("sbp_epilogue");
+}
+
+unsigned long long pose_exchange_layout(pose_exchange_t* x) {
+    if (!x || x->world < 1 || x->world > POSE_MAX_PEERS || x->batch_local < 0 || x->num_keypoints <= 0) return 0ull;
+    auto up = [](unsigned long long v) { return (v + 255ull) / 256ull * 256ull; };
+    const unsigned long long rows = up((unsigned long long)x->world * x->batch_local * (3ull * x->num_keypoints + 1ull) * 4ull);
+    const unsigned long long nums = up((unsigned long long)x->world * 16ull);
+    const unsigned long long ids = up((unsigned long long)x->world * x->batch_local * 16ull);
+    unsigned long long off = 0;
+    x->off_ctrl = off; off += 256;
+    x->off_flags = off; off += up((unsigned long long)POSE_MAX_PEERS * 8ull);
+    for (int p = 0; p < 2; ++p) {
+        x->off_rows[p] = off; off += rows;
+        x->off_nums[p] = off; off += nums;
+        x->off_ids[p] = off; off += ids;
+    }
+    return off;
+}
+
+int pose_exchange_finish(const pose_exchange_t* x, double w0, double w1, double inv_norm, float* loss_out, pose_stream_t stream) {
+    if (!x || !loss_out || x->world < 1 || x->world > POSE_MAX_PEERS || x->rank < 0 || x->rank >= x->world)
+        return fail(POSE_EINVAL, "exchange_finish: bad argument");
+    // ~2 s at 2 GHz: a peer that never signals must not hang this GPU
+    launch_pdl(pose::exchange_wait_reduce_kernel, 1u, 256u, (cudaStream_t)stream, to_dev(*x), w0, w1, inv_norm, loss_out, 4000000000ll);
+    return check_launch("exchange_wait_reduce");
 }
 
 int pose_loss_reduce(const double* pairs, int n, long long stride, double w0, double w1, double inv_norm, float* loss_out,

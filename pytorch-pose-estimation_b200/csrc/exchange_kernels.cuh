@@ -1,0 +1,137 @@
+// Multi-GPU exchange fused into the step's epilogue: the kernel that back-projects the decoded joints stores each row
+// straight into EVERY rank's receive buffer over NVLink (peer-mapped symmetric memory), the CTA that reduces the loss
+// partials stores the two fp64 numerators the same way, and the last CTA to finish publishes "step s of rank r has
+// landed" with a system-scope release store on every peer.  A one-CTA kernel on each rank then waits (acquire) for all
+// ranks' flags and reduces the gathered numerators in rank order -> the global-batch loss, bit-identical on all ranks.
+// No NCCL call, no staging copy, no host synchronisation; receive regions are double-buffered by step parity, which is
+// safe because a rank can only be one step ahead of the slowest peer (it needs that peer's flag to finish its own step).
+#pragma once
+#include "sbp_kernels.cuh"
+
+namespace pose {
+
+constexpr int kMaxPeers = 16;
+
+struct ExchangeDev {
+    int world, rank, B, K;
+    unsigned char* peer[kMaxPeers];                 // base of every rank's exchange buffer as mapped into THIS process
+    unsigned long long off_ctrl, off_flags, off_rows[2], off_nums[2], off_ids[2];
+    const long long* ids_local;                     // [B][2]
+};
+
+struct ExchangeCtrl {
+    unsigned long long step;                        // last completed step (advanced by the wait kernel)
+    unsigned int ticket;                            // CTAs of the running epilogue that have finished their peer stores
+    unsigned int error;                             // set when a wait timed out (a peer never signalled)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams P, ExchangeDev X) {
+    pdl_wait();
+    ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
+    const unsigned long long step = ctrl->step + 1;            // constant while this grid runs
+    const int par = (int)(step & 1);
+    const int stride = 3 * P.K + 1;
+
+    if (blockIdx.x == gridDim.x - 1) {
+        // loss partials -> local loss / numerators, then the numerators to every rank's slot [rank]
+        __shared__ double nums[2];
+        reduce_pairs_cta(P.partials, P.nblocks, 2, P.w0, P.w1, P.inv_norm, P.loss_out, nums);
+        __syncthreads();
+        if (P.num_out && threadIdx.x == 0) { P.num_out[0] = nums[0]; P.num_out[1] = nums[1]; }
+        if ((int)threadIdx.x < X.world) {
+            double* dst = reinterpret_cast<double*>(X.peer[threadIdx.x] + X.off_nums[par]) + 2 * X.rank;
+            dst[0] = nums[0];
+            dst[1] = nums[1];
+        }
+    } else {
+        const int lane = threadIdx.x & 31;
+        const int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+        if (n < P.N) {
+            // same arithmetic as backproject_sample (SBPmAPCOCO.update_state utils/sbp_utils.py:141-163)
+            const double bx = __ldg(P.bbox + 4 * n), by = __ldg(P.bbox + 4 * n + 1), bw = __ldg(P.bbox + 4 * n + 2), bh = __ldg(P.bbox + 4 * n + 3);
+            const float rx = (float)(bw / P.in_w), ry = (float)(bh / P.in_h);
+            const float ox = (float)bx, oy = (float)by;
+            const long long grow = (long long)X.rank * X.B + n;       // row in the gathered (global, image-ordered) arrays
+            float sum = 0.0f;
+            for (int k0 = 0; k0 < P.K; k0 += 32) {
+                const int k = k0 + lane;
+                float c = -1.0f;
+                if (k < P.K) {
+                    const float* j = P.joints + ((long long)n * P.K + k) * 3;
+                    c = j[2];
+                    float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+                    if (!(c < 0.0f)) {
+                        o0 = __fadd_rn(__fmul_rn(j[0], rx), ox);
+                        o1 = __fadd_rn(__fmul_rn(j[1], ry), oy);
+                        o2 = 1.0f;
+                    }
+                    if (P.packed) { float* o = P.packed + (long long)n * stride + 3 * k; o[0] = o0; o[1] = o1; o[2] = o2; }
+                    for (int r = 0; r < X.world; ++r) {
+                        float* o = reinterpret_cast<float*>(X.peer[r] + X.off_rows[par]) + grow * stride + 3 * k;
+                        o[0] = o0; o[1] = o1; o[2] = o2;
+                    }
+                }
+                const int cnt = min(32, P.K - k0);
+                for (int i = 0; i < cnt; ++i) {
+                    const float ci = __shfl_sync(FULL_MASK, c, i);
+                    if (!(ci < 0.0f)) sum = __fadd_rn(sum, ci);
+                }
+            }
+            if (lane == 0) {
+                const float score = __fdiv_rn(sum, (float)P.K);
+                if (P.packed) P.packed[(long long)n * stride + 3 * P.K] = score;
+                for (int r = 0; r < X.world; ++r)
+                    (reinterpret_cast<float*>(X.peer[r] + X.off_rows[par]) + grow * stride)[3 * P.K] = score;
+            }
+            if (lane < 2) {
+                const long long id = X.ids_local[2 * n + lane];
+                for (int r = 0; r < X.world; ++r) (reinterpret_cast<long long*>(X.peer[r] + X.off_ids[par]) + 2 * grow)[lane] = id;
+            }
+        }
+    }
+    // publish: every thread's peer stores are ordered before its CTA's ticket; the last CTA raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&ctrl->ticket, 1u);
+        if (t == gridDim.x - 1) {
+            ctrl->ticket = 0u;
+            __threadfence_system();
+            for (int r = 0; r < X.world; ++r)
+                st_release_sys(reinterpret_cast<unsigned long long*>(X.peer[r] + X.off_flags) + X.rank, step);
+        }
+    }
+}
+
+// wait for every rank's flag of this step, reduce the gathered numerators in rank order, advance the step counter
+__global__ void __launch_bounds__(256) exchange_wait_reduce_kernel(ExchangeDev X, double w0, double w1, double inv_norm,
+                                                                   float* __restrict__ loss_out, long long timeout_cycles) {
+    pdl_wait();
+    ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
+    const unsigned long long step = ctrl->step + 1;
+    const int par = (int)(step & 1);
+    if ((int)threadIdx.x < X.world) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.off_flags) + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) < step) {
+            if (clock64() - t0 > timeout_cycles) { atomicExch(&ctrl->error, 1u + threadIdx.x); break; }   // never hang the GPU
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const double* nums = reinterpret_cast<const double*>(X.peer[X.rank] + X.off_nums[par]);
+    reduce_pairs_cta(nums, X.world, 2, w0, w1, inv_norm, loss_out, nullptr);
+    __syncthreads();
+    if (threadIdx.x == 0) ctrl->step = step;
+}
+
+}  // namespace pose

@@ -166,6 +166,52 @@ __device__ __forceinline__ float loss_elem(float s, float t, float gpos, float g
     return (pos ? gpos : gneg) * d * ((1.0f - s) * s);
 }
 
+// One vector (V consecutive elements) of the fused render+loss(+grad)(+argmax) pass.
+// Every lane first takes the zero-target result (the target is zero on ~93% of a map):
+//   S_neg += s^2,  dL/dp = gneg s^2 (1-s);
+// lanes whose vector touches the joint's Gaussian patch then overwrite their elements from the template.
+// (row, col) is the position of element vi*V and is advanced by 32 vectors on return.
+template <int V, bool GRAD, bool WTGT, bool DEC>
+__device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[V], float (&tout)[V], int vi, const Patch& pt,
+                                                const float* __restrict__ lut_s, int lut_n, int W, float gpos, float gneg,
+                                                int rstep, int cstep, int& row, int& col, float& apos, float& aneg,
+                                                float& best, int& besti) {
+    float sg[V], c[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const float sj = sigmoid_fast(x[j]);
+        sg[j] = sj;
+        c[j] = sj * sj;
+        if (GRAD) g[j] = gneg * fmaf(-c[j], sj, c[j]);
+        if (DEC && sj > best) { best = sj; besti = vi * V + j; }
+        if (WTGT) tout[j] = 0.0f;
+    }
+    const int row_last = row + ((col + V - 1) >= W ? 1 : 0);
+    if (row_last >= pt.py0 && row < pt.py1) {
+        int r = row, cc = col;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (r >= pt.py0 && r < pt.py1 && cc >= pt.px0 && cc < pt.px1) {
+                const float t = lut_s[(r - pt.uly) * lut_n + (cc - pt.ulx)];
+                if (WTGT) tout[j] = t;
+                if (t > 0.0f) {      // t == 0 (underflowed template tail): the zero-target result stands
+                    const float d = sg[j] - t;
+                    c[j] = 0.0f;
+                    apos = fmaf(d, d, apos);
+                    if (GRAD) g[j] = gpos * d * ((1.0f - sg[j]) * sg[j]);
+                }
+            }
+            if (++cc >= W) { cc = 0; ++r; }
+        }
+    }
+    float q = c[0];
+#pragma unroll
+    for (int j = 1; j < V; ++j) q += c[j];
+    aneg += q;
+    col += cstep; row += rstep;
+    if (col >= W) { col -= W; ++row; }
+}
+
 template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
 __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel(SbpFusedParams P) {
     extern __shared__ float lut_s[];
@@ -218,43 +264,8 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel
                 if (vi >= nvec) break;
                 float g[V];
                 if (TGT == TGT_RENDER) {
-                    // Every lane first takes the zero-target result (the target is zero on ~93% of a map):
-                    //   S_neg += s^2,  dL/dp = gneg s^2 (1-s);
-                    // lanes whose vector touches the joint's Gaussian patch then overwrite their elements.
-                    float sg[V], c[V];
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        const float sj = sigmoid_fast(xv[u][j]);
-                        sg[j] = sj;
-                        c[j] = sj * sj;
-                        if (GRAD) g[j] = P.gneg * fmaf(-c[j], sj, c[j]);
-                        if (DEC && sj > best) { best = sj; besti = vi * V + j; }
-                        if (WTGT) tv[u][j] = 0.0f;
-                    }
-                    const int row_last = row + ((col + V - 1) >= P.W ? 1 : 0);
-                    if (row_last >= pt.py0 && row < pt.py1) {
-                        int r = row, cc = col;
-#pragma unroll
-                        for (int j = 0; j < V; ++j) {
-                            if (r >= pt.py0 && r < pt.py1 && cc >= pt.px0 && cc < pt.px1) {
-                                const float t = lut_s[(r - pt.uly) * P.lut_n + (cc - pt.ulx)];
-                                if (WTGT) tv[u][j] = t;
-                                if (t > 0.0f) {      // t == 0 (underflowed template tail): the zero-target result stands
-                                    const float d = sg[j] - t;
-                                    c[j] = 0.0f;
-                                    apos = fmaf(d, d, apos);
-                                    if (GRAD) g[j] = P.gpos * d * ((1.0f - sg[j]) * sg[j]);
-                                }
-                            }
-                            if (++cc >= P.W) { cc = 0; ++r; }
-                        }
-                    }
-                    float q = c[0];
-#pragma unroll
-                    for (int j = 1; j < V; ++j) q += c[j];
-                    aneg += q;
-                    col += cstep; row += rstep;
-                    if (col >= P.W) { col -= P.W; ++row; }
+                    render_loss_vec<V, GRAD, WTGT, DEC>(xv[u], g, tv[u], vi, pt, lut_s, P.lut_n, P.W, P.gpos, P.gneg, rstep, cstep,
+                                                        row, col, apos, aneg, best, besti);
                 } else {
 #pragma unroll
                     for (int j = 0; j < V; ++j) {

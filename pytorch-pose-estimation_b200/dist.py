@@ -115,6 +115,102 @@ class ShardExchange:
         return self.loss
 
 
+class PeerExchange:
+    """The per-step exchange WITHOUT a collective call: peer-mapped symmetric memory + the fused epilogue kernel.
+
+    Every rank allocates one exchange buffer with torch's symmetric-memory allocator and maps all peers' buffers.
+    `sbp_fused(..., exchange=self)` makes the back-projection epilogue store its rows, the loss numerators and the ids
+    directly into every rank's receive region (NVLink peer stores) and raise a per-rank flag; `finish()` launches the
+    one-CTA kernel that waits for all flags and reduces the numerators in rank order.  Receive regions are
+    double-buffered by step parity; `self.steps` (host) mirrors the device step counter so the views of the finished
+    step can be handed out without a synchronisation -- call `advance(n)` after replaying a captured step n times.
+    """
+
+    def __init__(self, batch_local, num_keypoints, device, image_ids, category_ids, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from ._cabi import ExchangeDesc, lib
+        group = group if group is not None else dist.group.WORLD
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.b, self.k, self.device = batch_local, num_keypoints, device
+        d = ExchangeDesc()
+        d.world, d.rank, d.batch_local, d.num_keypoints = self.world, self.rank, batch_local, num_keypoints
+        nbytes = int(lib().pose_exchange_layout(ctypes.byref(d)))
+        if nbytes == 0:
+            raise ValueError("bad exchange shape")
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.buf.zero_()
+        for r, p in enumerate(self.handle.buffer_ptrs):
+            d.peer_base[r] = int(p)
+        self.ids = torch.stack([image_ids.to(device, torch.int64), category_ids.to(device, torch.int64)], dim=1).contiguous()
+        d.ids_local = self.ids.data_ptr()
+        self.desc = d
+        self.steps = 0
+        self.loss = torch.zeros((), dtype=torch.float32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)            # every rank's buffer is zeroed before anyone's first peer store
+
+    def _view(self, off, dtype, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        return self.buf[off:off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+
+    def finish(self, global_batch, lambda_pos=5.0, lambda_neg=1.0):
+        """Wait for every rank's rows of this step and reduce the global loss (stream-ordered, no host sync)."""
+        import ctypes
+
+        from ._cabi import check, lib, ptr, stream_ptr
+        with torch.cuda.device(self.device):
+            check(lib().pose_exchange_finish(ctypes.byref(self.desc), float(lambda_pos), float(lambda_neg),
+                                             1.0 / (2.0 * self.k * global_batch), ptr(self.loss), stream_ptr(self.device)),
+                  "pose_exchange_finish")
+        self.steps += 1
+        return self.loss
+
+    def advance(self, n=1):
+        """Tell the host mirror that a captured step was replayed n more times."""
+        self.steps += n
+
+    def gathered_packed(self):
+        """[world*B, 3K+1] fp32 rows of the last finished step, image order (a view of the receive region)."""
+        return self._view(int(self.desc.off_rows[self.steps & 1]), torch.float32, (self.world * self.b, 3 * self.k + 1))
+
+    def gathered_ids(self):
+        return self._view(int(self.desc.off_ids[self.steps & 1]), torch.int64, (self.world * self.b, 2))
+
+    def error(self):
+        """Non-zero if a wait timed out (costs a host sync; for tests / diagnostics)."""
+        return int(self._view(int(self.desc.off_ctrl) + 12, torch.int32, (1,)).item())
+
+
+def make_exchange(batch_local, num_keypoints, device, image_ids, category_ids, group=None, prefer_p2p=True):
+    """PeerExchange when symmetric memory can be set up across the group, else the NCCL ShardExchange.  Returns (exchange, kind)."""
+    if not _active(group):
+        ex = ShardExchange(batch_local, num_keypoints, device, group)
+        ex.ids.copy_(torch.stack([image_ids.to(device, torch.int64), category_ids.to(device, torch.int64)], dim=1))
+        return ex, "single"
+    ok = torch.zeros(1, device=device)
+    ex = None
+    if prefer_p2p:
+        try:
+            ex = PeerExchange(batch_local, num_keypoints, device, image_ids, category_ids, group)
+            ok.fill_(1)
+        except Exception as e:          # noqa: BLE001 -- any set-up failure (no P2P, no VMM, old driver) means: use NCCL
+            import sys
+            print(f"[pose_b200] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if ex is not None and float(ok.item()) == 1.0:
+        return ex, "p2p"
+    ex = ShardExchange(batch_local, num_keypoints, device, group)
+    ex.ids.copy_(torch.stack([image_ids.to(device, torch.int64), category_ids.to(device, torch.int64)], dim=1))
+    return ex, "nccl"
+
+
 def gather_rows(rows, score, image_ids, category_ids, group=None):
     """rows [B,K,3], score [B], ids [B] -> the same tensors for the global batch (equal-sized shards)."""
     if not _active(group):

@@ -5,6 +5,9 @@ the keypoints [B,K,2] themselves, in which case the Gaussian target is rendered 
 never exists in HBM.  The gradient w.r.t. the logits is produced by the same pass that computes the
 loss; backward() only applies grad_output (a no-op launch when it is 1).
 """
+import ctypes
+import os
+
 import torch
 from torch import nn
 
@@ -13,9 +16,13 @@ from ._cabi import check, dense, lib, ptr, stream_ptr
 from .sbp_utils import _gauss_template, _kp_tensor, _templates
 
 
+# stage heat maps through shared memory with the TMA engine (cp.async.bulk) instead of per-lane LDG/STG
+DEFAULT_TMA = os.environ.get("POSE_B200_TMA", "0") == "1"
+
+
 def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, decode=False, conf_threshold=0.25,
               coord_scale=1.0, want_target=False, lambda_positive=5.0, lambda_negative=1.0, global_batch=None,
-              bbox=None, input_size=None, out=None):
+              bbox=None, input_size=None, out=None, tma=None, exchange=None):
     """One pass over the logits: loss (+dlogits) (+rendered target) (+decoded joints).
 
     Returns dict(loss 0-dim fp32, loss_num fp64[2] = un-normalised (S_pos, S_neg), dlogits, target, joints, packed);
@@ -23,7 +30,8 @@ def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, dec
     image shards on several GPUs produce gradients of the global-batch loss.  With `bbox` [B,4] fp64 and
     `input_size` (H_in, W_in) the same call also back-projects the decoded joints into `packed` [B,3K+1]
     (SBPmAPCOCO.update_state arithmetic).  `out` may carry preallocated `dlogits`, `joints`, `packed`, `loss`,
-    `loss_num` tensors (e.g. views into a communication buffer).
+    `loss_num` tensors (e.g. views into a communication buffer).  `exchange` (a `dist.PeerExchange`) makes the
+    epilogue store the rows / loss numerators / ids into every rank's receive buffer over NVLink.
     """
     x = dense(logits, "input")
     assert x.dim() == 4, "input must be [B,K,H,W]"
@@ -64,8 +72,10 @@ def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, dec
         bb = dense(bbox.to(dev) if isinstance(bbox, torch.Tensor) else torch.as_tensor(bbox).to(dev), "bbox", torch.float64)
         in_h, in_w = int(input_size[0]), int(input_size[1])
         packed = out.get("packed")
-        if packed is None:
+        if packed is None and exchange is None:
             packed = torch.empty((b, 3 * k + 1), dtype=torch.float32, device=dev)
+    if tma if tma is not None else DEFAULT_TMA:
+        flags |= _cabi.F_TMA           # honoured by the library only where it applies (render mode, aligned, no target out)
     loss = out.get("loss")
     if loss is None:
         loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -80,6 +90,7 @@ def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, dec
                                    ptr(loss), ptr(num), ptr(joints), float(conf_threshold), float(coord_scale),
                                    b, k, h, w, float(lambda_positive), float(lambda_negative), inv_norm, flags,
                                    ptr(bb), ptr(packed), in_h, in_w,
+                                   ctypes.byref(exchange.desc) if exchange is not None else None,
                                    ptr(ws), ws.numel(), stream_ptr(dev)), "pose_sbp_fused")
     return dict(loss=loss, loss_num=num, dlogits=dlogits, target=t_out, joints=joints, packed=packed)
 

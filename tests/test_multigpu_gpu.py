@@ -51,7 +51,26 @@ def _worker(rank, world, port, q):
         torch.cuda.synchronize()
         assert torch.equal(gp3, ex.gathered_packed()) and torch.equal(gi3, ex.gathered_ids())
         assert abs(float(loss3) - float(loss)) <= 1e-6 * abs(float(loss))
-        q.put((rank, float(loss), r["dlogits"].cpu(), ex.gathered_packed().cpu(), ex.gathered_ids().cpu(), (lo, hi)))
+        out = [rank, float(loss), r["dlogits"].cpu(), ex.gathered_packed().cpu(), ex.gathered_ids().cpu(), (lo, hi)]
+        # the same exchange fused into the epilogue over NVLink peer memory (no collective call), three steps (parity flips)
+        p2p = None
+        try:
+            px = pd.PeerExchange(hi - lo, 17, dev, torch.arange(lo, hi, device=dev), torch.ones(hi - lo, dtype=torch.int64, device=dev))
+        except Exception as e:      # noqa: BLE001
+            px, p2p = None, f"unavailable: {type(e).__name__}: {e}"
+        if px is not None:
+            p2p = []
+            for it in range(3):
+                x_it = logits[lo:hi] * (1.0 + 0.25 * it)
+                pb.sbp_fused(x_it, keypoints=kp[lo:hi], sigma=2, want_grad=False, decode=True, conf_threshold=0.25, coord_scale=4.0,
+                             global_batch=b, bbox=bbox[lo:hi], input_size=(256, 192), exchange=px)
+                l_it = px.finish(b)
+                torch.cuda.synchronize()
+                p2p.append((float(l_it), px.gathered_packed().cpu().clone(), px.gathered_ids().cpu().clone()))
+            assert px.error() == 0
+            dist.barrier()
+        out.append(p2p)
+        q.put(tuple(out))
     finally:
         dist.destroy_process_group()
 
@@ -74,8 +93,20 @@ def test_two_gpu_shards_match_single_gpu():
     logits, kp, bbox = _inputs(dev)
     one = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0)
     packed = pb.backproject_packed(one["joints"], bbox, (256, 192)).cpu()
-    for rank, loss, dl, gp, gi, (lo, hi) in got:
+    for rank, loss, dl, gp, gi, (lo, hi), p2p in got:
         assert abs(loss - one["loss"].item()) <= 1e-6 * abs(one["loss"].item())
         assert torch.equal(dl, one["dlogits"][lo:hi].cpu())          # same kernel, same normalisation -> bit identical
         assert torch.equal(gp, packed)                               # gathered in image order on every rank
         assert torch.equal(gi[:, 0], torch.arange(logits.size(0)))
+    p2p0, p2p1 = got[0][6], got[1][6]
+    if isinstance(p2p0, str):
+        pytest.skip("symmetric memory " + p2p0)
+    for it in range(3):
+        ref = pb.sbp_fused(logits * (1.0 + 0.25 * it), keypoints=kp, sigma=2, want_grad=False, decode=True, conf_threshold=0.25,
+                           coord_scale=4.0, bbox=bbox, input_size=(256, 192))
+        for p in (p2p0, p2p1):
+            l_it, rows_it, ids_it = p[it]
+            assert abs(l_it - ref["loss"].item()) <= 1e-6 * abs(ref["loss"].item())
+            assert torch.equal(rows_it, ref["packed"].cpu())
+            assert torch.equal(ids_it[:, 0], torch.arange(logits.size(0)))
+        assert p2p0[it][0] == p2p1[it][0]                            # bit-identical global loss on every rank

@@ -179,6 +179,25 @@ def test_fused_render_loss_grad_decode_single_pass(pb, dev, name):
     assert torch.equal(r["loss"], r2["loss"]) and torch.equal(r["dlogits"], r2["dlogits"])
 
 
+@pytest.mark.parametrize("name", ["coco", "hires", "sigma3", "sigma1"])
+def test_tma_staged_kernel_matches_ldg_kernel(pb, dev, name):
+    """The bulk-async (TMA) staged variant is the same arithmetic in the same per-lane order: bit-identical outputs."""
+    g = load_golden("sbp_" + name)
+    kp, logits, bbox, iid, cid, meta = cases.sbp_case(name)
+    x = logits.to(dev)
+    scale = meta["input_size"][1] / meta["w"]
+    for grad in (True, False):
+        for dec in (True, False):
+            a = pb.sbp_fused(x, keypoints=kp, sigma=meta["sigma"], want_grad=grad, decode=dec, conf_threshold=0.25, coord_scale=scale, tma=False)
+            b = pb.sbp_fused(x, keypoints=kp, sigma=meta["sigma"], want_grad=grad, decode=dec, conf_threshold=0.25, coord_scale=scale, tma=True)
+            assert close(b["loss"].item(), a["loss"].item(), 1e-7) and allclose(b["loss_num"], a["loss_num"], 1e-12)
+            if grad:
+                assert torch.equal(a["dlogits"], b["dlogits"])
+            if dec:
+                assert torch.equal(a["joints"], b["joints"])
+    assert close(b["loss"].item(), float(g["loss"]), REL)
+
+
 @pytest.mark.parametrize("name", list(cases.SBP_SHAPES))
 def test_update_state_rows(pb, dev, name):
     g = load_golden("sbp_" + name)
@@ -263,12 +282,12 @@ def test_cabi_argument_errors(pb, dev):
     loss = torch.zeros((), device=dev)
     ws = torch.zeros(16, dtype=torch.uint8, device=dev)
     rc = L.pose_sbp_fused(C.ptr(x), C.ptr(x), None, 0, 1.0, None, 0, None, None, C.ptr(loss), None, None, 0.0, 1.0,
-                          1, 1, 8, 8, 5.0, 1.0, 0.5, 0, None, None, 0, 0, C.ptr(ws), ws.numel(), C.stream_ptr(dev))
+                          1, 1, 8, 8, 5.0, 1.0, 0.5, 0, None, None, 0, 0, None, C.ptr(ws), ws.numel(), C.stream_ptr(dev))
     assert rc == -3      # workspace too small
     big_ws = torch.zeros(int(L.pose_sbp_fused_workspace_bytes()), dtype=torch.uint8, device=dev)
     bb = torch.zeros(1, 4, dtype=torch.float64, device=dev)
-    rc = L.pose_sbp_fused(C.ptr(x), C.ptr(x), None, 0, 1.0, None, 0, None, None, C.ptr(loss), None, None, 0.0, 1.0,
-                          1, 1, 8, 8, 5.0, 1.0, 0.5, 0, C.ptr(bb), None, 256, 192, C.ptr(big_ws), big_ws.numel(), C.stream_ptr(dev))
+    rc = L.pose_sbp_fused(C.ptr(x), C.ptr(x), None, 0, 1.0, None, 0, None, None, C.ptr(loss), None, C.ptr(j), 0.0, 1.0,
+                          1, 1, 8, 8, 5.0, 1.0, 0.5, 4, C.ptr(bb), None, 256, 192, None, C.ptr(big_ws), big_ws.numel(), C.stream_ptr(dev))
     assert rc == -1 and b"bbox and packed_out" in L.pose_b200_last_error()
 
 
@@ -327,5 +346,8 @@ def test_full_size_fused_equals_staged_and_oracle_subset(pb, dev, big):
                           coord_scale=4.0)["loss_num"] for i in range(0, b, 1024)]
     tot = torch.stack(parts).sum(0)
     assert allclose(tot, fused["loss_num"], 1e-12)
+    tma = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0, tma=True)
+    assert torch.equal(tma["dlogits"], fused["dlogits"]) and torch.equal(tma["joints"], fused["joints"])
+    assert allclose(tma["loss_num"], fused["loss_num"], 1e-12)
     other = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=False)["loss_num"]      # another variant: fp32 rounding differs
     assert allclose(other, fused["loss_num"], 1e-7)

@@ -15,7 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "tune")
 SRC = os.path.join(ROOT, "pytorch-pose-estimation_b200", "csrc", "api.cu")
-VARIANTS = [(u, m) for u in (2, 4, 6, 8) for m in (2, 3, 4, 5)]
+VARIANTS = [(u, m) for u in (4, 6, 8) for m in (2, 3, 4)]
+# TMA-staged kernel: (stages, warps per CTA, float4 per tile)
+TMA_VARIANTS = [(2, 8, 256), (3, 8, 256), (4, 8, 256), (3, 4, 256), (3, 16, 256), (2, 16, 256), (3, 8, 128), (4, 8, 128), (6, 8, 128),
+                (2, 8, 768), (2, 4, 768), (3, 4, 768)]
 
 
 def build():
@@ -25,6 +28,11 @@ def build():
         lib = os.path.join(OUT, f"libpose_u{u}_m{m}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                f"-DPOSE_FUSED_U={u}", f"-DPOSE_FUSED_MINB={m}", "-o", lib, SRC]
+        procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for st, w, tv in TMA_VARIANTS:
+        lib = os.path.join(OUT, f"libpose_tma_s{st}_w{w}_t{tv}.so")
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+               f"-DPOSE_TMA_STAGES={st}", f"-DPOSE_TMA_WARPS={w}", f"-DPOSE_TMA_TILE_VEC={tv}", "-o", lib, SRC]
         procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for lib, p in procs:
         out, _ = p.communicate()
@@ -51,8 +59,9 @@ def run(reps):
     st = _cabi.stream_ptr(dev)
     res = {}
     ref = None
-    for u, m in VARIANTS:
-        path = os.path.join(OUT, f"libpose_u{u}_m{m}.so")
+    jobs = [(f"U{u}_M{m}", os.path.join(OUT, f"libpose_u{u}_m{m}.so"), 1 | 4) for u, m in VARIANTS]
+    jobs += [(f"TMA_S{st}_W{w}_T{tv}", os.path.join(OUT, f"libpose_tma_s{st}_w{w}_t{tv}.so"), 1 | 4 | 8) for st, w, tv in TMA_VARIANTS]
+    for name, path, flags in jobs:
         if not os.path.exists(path):
             continue
         L = ctypes.CDLL(path)
@@ -61,7 +70,7 @@ def run(reps):
 
         def call():
             rc = fn(_cabi.ptr(logits), None, _cabi.ptr(kp), 1, 2.0, _cabi.ptr(lut), 15, _cabi.ptr(dl), None, _cabi.ptr(loss), _cabi.ptr(num),
-                    _cabi.ptr(joints), 0.25, 4.0, B, K, H, W, 5.0, 1.0, 1.0 / (2 * K * B), 1 | 4, None, None, 0, 0, _cabi.ptr(ws), ws.numel(), st)
+                    _cabi.ptr(joints), 0.25, 4.0, B, K, H, W, 5.0, 1.0, 1.0 / (2 * K * B), flags, None, None, 0, 0, None, _cabi.ptr(ws), ws.numel(), st)
             assert rc == 0, rc
         for _ in range(5):
             call()
@@ -77,8 +86,8 @@ def run(reps):
             ts.append(a.elapsed_time(b) / reps)
         sig = (float(loss), float(dl.double().abs().sum()), float(joints.double().sum()))
         ref = ref or sig
-        res[f"U{u}_M{m}"] = {"ms": min(ts), "GBps": 24596 * B * K / (min(ts) * 1e-3) / 1e9, "same_result": sig == ref}
-        print(f"U={u} MINB={m}: {min(ts)*1e3:7.1f} us  {res[f'U{u}_M{m}']['GBps']:7.1f} GB/s  same={sig == ref}", flush=True)
+        res[name] = {"ms": min(ts), "GBps": 24596 * B * K / (min(ts) * 1e-3) / 1e9, "same_result": sig == ref}
+        print(f"{name:18s}: {min(ts)*1e3:7.1f} us  {res[name]['GBps']:7.1f} GB/s  same={sig == ref} {sig}", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "tune_fused.json"), "w"), indent=1)
 
