@@ -98,14 +98,18 @@ int pose_sbp_fused(const float* logits, const float* target_in,
  * process.  Passing the descriptor to pose_sbp_fused makes the epilogue store rows / loss numerators / ids into every
  * rank's receive region and raise a per-rank flag; pose_exchange_finish waits for all flags of the step and reduces
  * the gathered numerators (rank order) into the global-batch loss.  Receive regions are double-buffered by step
- * parity; rows_offset/ids_offset of the just-finished step are pose_exchange_t.off_rows/off_ids[step & 1]. */
+ * parity; the rows ([world*batch_local][row_stride] fp32, the first 3K+1 of each valid) and ids of the just-finished
+ * step are at pose_exchange_t.off_rows/off_ids[step & 1]. */
 #define POSE_MAX_PEERS 16
 typedef struct pose_exchange {
     int world, rank;
     int batch_local, num_keypoints;
+    int row_stride;                           /* floats per exchanged row: 3K+1 rounded up to a multiple of 4 (set by _layout) */
+    int reserved;
     void* peer_base[POSE_MAX_PEERS];
     unsigned long long off_ctrl, off_flags, off_rows[2], off_nums[2], off_ids[2];
     const long long* ids_local;               /* device [batch_local][2] (image_id, category_id) of this rank */
+    void* multicast_base;                     /* NVLS multicast alias of the buffer on all ranks (multimem.st), or NULL */
 } pose_exchange_t;
 /* fills the off_* fields of *x from world / batch_local / num_keypoints and returns the buffer size in bytes */
 unsigned long long pose_exchange_layout(pose_exchange_t* x);

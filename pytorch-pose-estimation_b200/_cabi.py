@@ -46,10 +46,10 @@ MAX_PEERS = 16
 
 class ExchangeDesc(ctypes.Structure):
     """pose_exchange_t (include/pose_b200.h)."""
-    _fields_ = [("world", _i), ("rank", _i), ("batch_local", _i), ("num_keypoints", _i),
+    _fields_ = [("world", _i), ("rank", _i), ("batch_local", _i), ("num_keypoints", _i), ("row_stride", _i), ("reserved", _i),
                 ("peer_base", _vp * MAX_PEERS),
                 ("off_ctrl", _ull), ("off_flags", _ull), ("off_rows", _ull * 2), ("off_nums", _ull * 2), ("off_ids", _ull * 2),
-                ("ids_local", _vp)]
+                ("ids_local", _vp), ("multicast_base", _vp)]
 
 
 _lib = None

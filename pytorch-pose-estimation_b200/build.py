@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "api.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "common.cuh", "sbp_kernels.cuh", "spm_kernels.cuh")] + [
+DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith((".cu", ".cuh", ".h"))) + [
     os.path.join(ROOT, "include", "pose_b200.h")]
 LIB = os.path.join(HERE, "libpose_b200.so")
 

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/pose_b200.h"
@@ -77,11 +78,12 @@ void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStrea
 pose::ExchangeDev to_dev(const pose_exchange_t& x) {
     pose::ExchangeDev d;
     memset(&d, 0, sizeof(d));
-    d.world = x.world; d.rank = x.rank; d.B = x.batch_local; d.K = x.num_keypoints;
+    d.world = x.world; d.rank = x.rank; d.B = x.batch_local; d.K = x.num_keypoints; d.row_stride = x.row_stride;
     for (int r = 0; r < x.world && r < pose::kMaxPeers; ++r) d.peer[r] = reinterpret_cast<unsigned char*>(x.peer_base[r]);
     d.off_ctrl = x.off_ctrl; d.off_flags = x.off_flags;
     for (int p = 0; p < 2; ++p) { d.off_rows[p] = x.off_rows[p]; d.off_nums[p] = x.off_nums[p]; d.off_ids[p] = x.off_ids[p]; }
     d.ids_local = x.ids_local;
+    d.mc = reinterpret_cast<unsigned char*>(x.multicast_base);
     return d;
 }
 
@@ -196,7 +198,8 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
     if (exchange) {
         if (!bbox) return fail(POSE_EINVAL, "sbp_fused: the exchange needs bbox (back-projected rows are what is exchanged)");
         if (exchange->world < 1 || exchange->world > POSE_MAX_PEERS || exchange->rank < 0 || exchange->rank >= exchange->world ||
-            exchange->batch_local != N || exchange->num_keypoints != K || !exchange->ids_local)
+            exchange->batch_local != N || exchange->num_keypoints != K || !exchange->ids_local ||
+            exchange->row_stride != (3 * K + 1 + 3) / 4 * 4 || exchange->row_stride > pose::kMaxRowStride)
             return fail(POSE_EINVAL, "sbp_fused: bad exchange descriptor");
     }
     if (bbox && (!(flags & POSE_F_DECODE) || input_h <= 0 || input_w <= 0)) return fail(POSE_EINVAL, "sbp_fused: back-projection needs POSE_F_DECODE and the input size");
@@ -247,7 +250,9 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
 unsigned long long pose_exchange_layout(pose_exchange_t* x) {
     if (!x || x->world < 1 || x->world > POSE_MAX_PEERS || x->batch_local < 0 || x->num_keypoints <= 0) return 0ull;
     auto up = [](unsigned long long v) { return (v + 255ull) / 256ull * 256ull; };
-    const unsigned long long rows = up((unsigned long long)x->world * x->batch_local * (3ull * x->num_keypoints + 1ull) * 4ull);
+    x->row_stride = (3 * x->num_keypoints + 1 + 3) / 4 * 4;
+    if (x->row_stride > pose::kMaxRowStride) return 0ull;
+    const unsigned long long rows = up((unsigned long long)x->world * x->batch_local * (unsigned long long)x->row_stride * 4ull);
     const unsigned long long nums = up((unsigned long long)x->world * 16ull);
     const unsigned long long ids = up((unsigned long long)x->world * x->batch_local * 16ull);
     unsigned long long off = 0;
@@ -264,8 +269,10 @@ unsigned long long pose_exchange_layout(pose_exchange_t* x) {
 int pose_exchange_finish(const pose_exchange_t* x, double w0, double w1, double inv_norm, float* loss_out, pose_stream_t stream) {
     if (!x || !loss_out || x->world < 1 || x->world > POSE_MAX_PEERS || x->rank < 0 || x->rank >= x->world)
         return fail(POSE_EINVAL, "exchange_finish: bad argument");
-    // ~2 s at 2 GHz: a peer that never signals must not hang this GPU
-    launch_pdl(pose::exchange_wait_reduce_kernel, 1u, 256u, (cudaStream_t)stream, to_dev(*x), w0, w1, inv_norm, loss_out, 4000000000ll);
+    // ~2 s at 2 GHz: a peer that never signals must not hang this GPU (POSE_B200_EXCHANGE_TIMEOUT_CYCLES overrides; diagnostics)
+    long long timeout = 4000000000ll;
+    if (const char* e = getenv("POSE_B200_EXCHANGE_TIMEOUT_CYCLES")) timeout = atoll(e);
+    launch_pdl(pose::exchange_wait_reduce_kernel, 1u, 256u, (cudaStream_t)stream, to_dev(*x), w0, w1, inv_norm, loss_out, timeout);
     return check_launch("exchange_wait_reduce");
 }
 

@@ -1,8 +1,8 @@
 // Multi-GPU exchange fused into the step's epilogue: the kernel that back-projects the decoded joints stores each row
-// straight into EVERY rank's receive buffer over NVLink (peer-mapped symmetric memory), the CTA that reduces the loss
-// partials stores the two fp64 numerators the same way, and the last CTA to finish publishes "step s of rank r has
-// landed" with a system-scope release store on every peer.  A one-CTA kernel on each rank then waits (acquire) for all
-// ranks' flags and reduces the gathered numerators in rank order -> the global-batch loss, bit-identical on all ranks.
+// straight into EVERY rank's receive buffer over NVLink (peer-mapped symmetric memory) and the CTA that reduces the loss
+// partials stores the two fp64 numerators the same way.  A one-CTA kernel on each rank then publishes "step s of rank r
+// has landed" with a system-scope release store on every peer, waits (acquire) for all ranks' flags and reduces the
+// gathered numerators in rank order -> the global-batch loss, bit-identical on all ranks.
 // No NCCL call, no staging copy, no host synchronisation; receive regions are double-buffered by step parity, which is
 // safe because a rank can only be one step ahead of the slowest peer (it needs that peer's flag to finish its own step).
 #pragma once
@@ -12,11 +12,15 @@ namespace pose {
 
 constexpr int kMaxPeers = 16;
 
+constexpr int kMaxRowStride = 256;                 // floats per exchanged row (3K+1 padded to a multiple of 4): K <= 85
+
 struct ExchangeDev {
     int world, rank, B, K;
+    int row_stride;                                 // floats per row in the receive regions (16-byte aligned rows)
     unsigned char* peer[kMaxPeers];                 // base of every rank's exchange buffer as mapped into THIS process
     unsigned long long off_ctrl, off_flags, off_rows[2], off_nums[2], off_ids[2];
     const long long* ids_local;                     // [B][2]
+    unsigned char* mc;                              // multicast (NVLS) alias of the same buffer on ALL ranks, or nullptr
 };
 
 struct ExchangeCtrl {
@@ -34,6 +38,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// one 16-byte store replicated by the NVSwitch into every rank's copy of the buffer (multimem = NVLS multicast object)
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// store 16 bytes at byte offset `off` of every rank's exchange buffer: one multicast store, or one store per peer
+__device__ __forceinline__ void store_all(const ExchangeDev& X, unsigned long long off, float4 v) {
+    if (X.mc) {
+        multimem_st_v4(X.mc + off, v);
+    } else {
+        for (int r = 0; r < X.world; ++r) *reinterpret_cast<float4*>(X.peer[r] + off) = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams P, ExchangeDev X) {
     pdl_wait();
     ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
@@ -47,13 +64,18 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
         reduce_pairs_cta(P.partials, P.nblocks, 2, P.w0, P.w1, P.inv_norm, P.loss_out, nums);
         __syncthreads();
         if (P.num_out && threadIdx.x == 0) { P.num_out[0] = nums[0]; P.num_out[1] = nums[1]; }
-        if ((int)threadIdx.x < X.world) {
-            double* dst = reinterpret_cast<double*>(X.peer[threadIdx.x] + X.off_nums[par]) + 2 * X.rank;
-            dst[0] = nums[0];
-            dst[1] = nums[1];
+        if (threadIdx.x == 0) {
+            float4 v;
+            reinterpret_cast<double*>(&v)[0] = nums[0];
+            reinterpret_cast<double*>(&v)[1] = nums[1];
+            store_all(X, X.off_nums[par] + 16ull * X.rank, v);
         }
     } else {
-        const int lane = threadIdx.x & 31;
+        // One warp per sample.  The sample's row (K x (x_img, y_img, flag) + score, zero-padded to a 16-byte multiple) is
+        // assembled in shared memory and then sent to every rank as 128-bit stores: NVLink carries a few wide, aligned
+        // writes per sample instead of ~3K scalar ones.
+        __shared__ __align__(16) float stage[8][kMaxRowStride];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
         const int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
         if (n < P.N) {
             // same arithmetic as backproject_sample (SBPmAPCOCO.update_state utils/sbp_utils.py:141-163)
@@ -61,6 +83,7 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
             const float rx = (float)(bw / P.in_w), ry = (float)(bh / P.in_h);
             const float ox = (float)bx, oy = (float)by;
             const long long grow = (long long)X.rank * X.B + n;       // row in the gathered (global, image-ordered) arrays
+            float* row = stage[w];
             float sum = 0.0f;
             for (int k0 = 0; k0 < P.K; k0 += 32) {
                 const int k = k0 + lane;
@@ -74,11 +97,8 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
                         o1 = __fadd_rn(__fmul_rn(j[1], ry), oy);
                         o2 = 1.0f;
                     }
+                    row[3 * k] = o0; row[3 * k + 1] = o1; row[3 * k + 2] = o2;
                     if (P.packed) { float* o = P.packed + (long long)n * stride + 3 * k; o[0] = o0; o[1] = o1; o[2] = o2; }
-                    for (int r = 0; r < X.world; ++r) {
-                        float* o = reinterpret_cast<float*>(X.peer[r] + X.off_rows[par]) + grow * stride + 3 * k;
-                        o[0] = o0; o[1] = o1; o[2] = o2;
-                    }
                 }
                 const int cnt = min(32, P.K - k0);
                 for (int i = 0; i < cnt; ++i) {
@@ -88,28 +108,21 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
             }
             if (lane == 0) {
                 const float score = __fdiv_rn(sum, (float)P.K);
+                row[3 * P.K] = score;
                 if (P.packed) P.packed[(long long)n * stride + 3 * P.K] = score;
-                for (int r = 0; r < X.world; ++r)
-                    (reinterpret_cast<float*>(X.peer[r] + X.off_rows[par]) + grow * stride)[3 * P.K] = score;
             }
-            if (lane < 2) {
-                const long long id = X.ids_local[2 * n + lane];
-                for (int r = 0; r < X.world; ++r) (reinterpret_cast<long long*>(X.peer[r] + X.off_ids[par]) + 2 * grow)[lane] = id;
+            if (lane >= 1 && lane < 4 && 3 * P.K + lane < X.row_stride) row[3 * P.K + lane] = 0.0f;     // padding
+            __syncwarp();
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            for (int v = lane; v < X.row_stride / 4; v += 32) {
+                store_all(X, X.off_rows[par] + 16ull * (unsigned long long)(grow * (X.row_stride / 4) + v), row4[v]);
             }
+            if (lane == 0)
+                store_all(X, X.off_ids[par] + 16ull * (unsigned long long)grow, *reinterpret_cast<const float4*>(X.ids_local + 2 * n));
         }
     }
-    // publish: every thread's peer stores are ordered before its CTA's ticket; the last CTA raises the flags
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(&ctrl->ticket, 1u);
-        if (t == gridDim.x - 1) {
-            ctrl->ticket = 0u;
-            __threadfence_system();
-            for (int r = 0; r < X.world; ++r)
-                st_release_sys(reinterpret_cast<unsigned long long*>(X.peer[r] + X.off_flags) + X.rank, step);
-        }
-    }
+    // No fence, no flag here: the grid boundary orders these stores (remote ones included) before the next grid in the
+    // stream, and that grid -- exchange_wait_reduce_kernel -- publishes this rank's flag before it waits for the others.
 }
 
 // wait for every rank's flag of this step, reduce the gathered numerators in rank order, advance the step counter
@@ -119,6 +132,10 @@ __global__ void __launch_bounds__(256) exchange_wait_reduce_kernel(ExchangeDev X
     ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
     const unsigned long long step = ctrl->step + 1;
     const int par = (int)(step & 1);
+    // publish "step `step` of rank X.rank has landed everywhere": the epilogue grid has completed (griddepcontrol.wait
+    // above returns only after its memory operations, peer stores included, are performed), so a release store suffices
+    if ((int)threadIdx.x < X.world)
+        st_release_sys(reinterpret_cast<unsigned long long*>(X.peer[threadIdx.x] + X.off_flags) + X.rank, step);
     if ((int)threadIdx.x < X.world) {
         const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.off_flags) + threadIdx.x;
         const long long t0 = clock64();

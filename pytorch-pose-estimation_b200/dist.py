@@ -126,8 +126,9 @@ class PeerExchange:
     step can be handed out without a synchronisation -- call `advance(n)` after replaying a captured step n times.
     """
 
-    def __init__(self, batch_local, num_keypoints, device, image_ids, category_ids, group=None):
+    def __init__(self, batch_local, num_keypoints, device, image_ids, category_ids, group=None, multicast=None):
         import ctypes
+        import os
 
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -148,6 +149,12 @@ class PeerExchange:
             d.peer_base[r] = int(p)
         self.ids = torch.stack([image_ids.to(device, torch.int64), category_ids.to(device, torch.int64)], dim=1).contiguous()
         d.ids_local = self.ids.data_ptr()
+        # NVLS: one multimem.st reaches every rank's copy through the switch (egress independent of the world size)
+        if multicast is None:
+            multicast = os.environ.get("POSE_B200_MULTICAST", "1") == "1"
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.multicast = bool(multicast and mc)
+        d.multicast_base = mc if self.multicast else None
         self.desc = d
         self.steps = 0
         self.loss = torch.zeros((), dtype=torch.float32, device=device)
@@ -176,9 +183,13 @@ class PeerExchange:
         """Tell the host mirror that a captured step was replayed n more times."""
         self.steps += n
 
+    def gathered_padded(self):
+        """[world*B, row_stride] fp32: the receive region of the last finished step as it lies in memory (contiguous)."""
+        return self._view(int(self.desc.off_rows[self.steps & 1]), torch.float32, (self.world * self.b, int(self.desc.row_stride)))
+
     def gathered_packed(self):
-        """[world*B, 3K+1] fp32 rows of the last finished step, image order (a view of the receive region)."""
-        return self._view(int(self.desc.off_rows[self.steps & 1]), torch.float32, (self.world * self.b, 3 * self.k + 1))
+        """[world*B, 3K+1] fp32 rows of the last finished step, image order (a strided view: rows are 16-byte padded)."""
+        return self.gathered_padded()[:, :3 * self.k + 1]
 
     def gathered_ids(self):
         return self._view(int(self.desc.off_ids[self.steps & 1]), torch.int64, (self.world * self.b, 2))

@@ -69,6 +69,7 @@ def _worker(rank, world, port, q):
                 p2p.append((float(l_it), px.gathered_packed().cpu().clone(), px.gathered_ids().cpu().clone()))
             assert px.error() == 0
             dist.barrier()
+            p2p.append(px.multicast)
         out.append(p2p)
         q.put(tuple(out))
     finally:
@@ -101,6 +102,7 @@ def test_two_gpu_shards_match_single_gpu():
     p2p0, p2p1 = got[0][6], got[1][6]
     if isinstance(p2p0, str):
         pytest.skip("symmetric memory " + p2p0)
+    print("multicast (NVLS) stores used:", p2p0[3])
     for it in range(3):
         ref = pb.sbp_fused(logits * (1.0 + 0.25 * it), keypoints=kp, sigma=2, want_grad=False, decode=True, conf_threshold=0.25,
                            coord_scale=4.0, bbox=bbox, input_size=(256, 192))
