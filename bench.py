@@ -189,7 +189,7 @@ def run_cuda(args):
                         torch.rand(B, device=dev, generator=gen, dtype=torch.float64) * 340 + 60], dim=-1)
     image_id = torch.arange(B, device=dev, dtype=torch.int64) + rank * B
     category_id = torch.ones(B, device=dev, dtype=torch.int64)
-    ex, ex_kind = pd.make_exchange(B, K, dev, image_id, category_id, prefer_p2p=not args.nccl)
+    ex, ex_kind = pd.make_exchange(B, K, dev, image_id, category_id, prefer_p2p=not args.nccl, defer=args.defer)
     dlogits = torch.empty_like(logits)
     joints = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
     loss_local = torch.empty((), dtype=torch.float32, device=dev)
@@ -249,10 +249,12 @@ def run_cuda(args):
         e0.record()
         for i in range(args.steps):
             run_step()
+        if graph is not None and ex_kind == "p2p":
+            ex.advance(args.steps)
+        if ex_kind == "p2p":
+            ex.flush(global_batch)         # defer=1: the last step's exchange completes inside the timed region too
         e1.record()
         fence()
-    if graph is not None and ex_kind == "p2p":
-        ex.advance(args.steps)
     if graph is None:
         launches = pb.launch_count() - launches0
     else:            # graph replays do not pass through the library: count the launches of one eager step and scale
@@ -296,6 +298,8 @@ def run_cuda(args):
         d_kp.copy_(h_kp, non_blocking=True)
         d_bbox.copy_(h_bbox, non_blocking=True)
         loss = step(d_logits, d_kp, d_bbox)
+        if ex_kind == "p2p":
+            loss = ex.flush(global_batch)     # the host wants THIS step's rows: complete it now (no-op for defer=0)
         h_packed.copy_(ex.gathered_packed(), non_blocking=True)
         h_loss.copy_(loss, non_blocking=True)
 
@@ -329,7 +333,7 @@ def run_cuda(args):
                                    "fused render+loss+grad+decode + back-projection"
                                    + ({"p2p": "; rows + loss numerators exchanged by the epilogue kernel over NVLink peer memory (no NCCL call)",
                                        "nccl": "; one NCCL all-gather (rows + loss numerators + ids) per step"}.get(ex_kind, "")),
-                       "batch_per_gpu": B, "global_batch": global_batch, "partition": f"images x{world}", "exchange": ex_kind,
+                       "batch_per_gpu": B, "global_batch": global_batch, "partition": f"images x{world}", "exchange": ex_kind, "exchange_defer": getattr(ex, "defer", 0),
                        "l2": "inputs (856 MB logits per GPU) larger than the 126 MB L2; no explicit flush",
                        "kp_dtype": "f64", "loss": loss_host, "cuda_graph": graph is not None},
             "roofline": {"bound": "hbm", "kernel": "sbp_fused_kernel<4,RENDER,GRAD,DECODE> (+ its 1-CTA loss-reduce epilogue launch)",
@@ -378,6 +382,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="images per GPU")
     ap.add_argument("--ref-sample", type=int, default=64, help="images per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--defer", type=int, default=int(os.environ.get("POSE_B200_EXCHANGE_DEFER", "1")),
+                    help="N>1, peer exchange: 1 = a step's wait kernel completes the PREVIOUS step's exchange (ranks may drift), 0 = lock-step")
     ap.add_argument("--nccl", action="store_true", help="N>1: use the NCCL all-gather exchange instead of the peer-memory epilogue")
     ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

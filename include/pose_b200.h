@@ -97,17 +97,20 @@ int pose_sbp_fused(const float* logits, const float* target_in,
  * rank's address space (e.g. torch.distributed._symmetric_memory); peer_base[r] is rank r's buffer as seen from THIS
  * process.  Passing the descriptor to pose_sbp_fused makes the epilogue store rows / loss numerators / ids into every
  * rank's receive region and raise a per-rank flag; pose_exchange_finish waits for all flags of the step and reduces
- * the gathered numerators (rank order) into the global-batch loss.  Receive regions are double-buffered by step
- * parity; the rows ([world*batch_local][row_stride] fp32, the first 3K+1 of each valid) and ids of the just-finished
- * step are at pose_exchange_t.off_rows/off_ids[step & 1]. */
+ * the gathered numerators (rank order) into the global-batch loss.  Receive regions form a ring of
+ * POSE_EXCHANGE_SLOTS steps; the rows ([world*batch_local][row_stride] fp32, the first 3K+1 of each valid) and ids
+ * of completed step c are at pose_exchange_t.off_rows/off_ids[c % POSE_EXCHANGE_SLOTS].  With defer = 1,
+ * pose_exchange_finish of step s completes step s-1 (ranks may drift instead of running in lock-step) and
+ * pose_exchange_flush completes the last one. */
 #define POSE_MAX_PEERS 16
+#define POSE_EXCHANGE_SLOTS 4
 typedef struct pose_exchange {
     int world, rank;
     int batch_local, num_keypoints;
     int row_stride;                           /* floats per exchanged row: 3K+1 rounded up to a multiple of 4 (set by _layout) */
-    int reserved;
+    int defer;                                /* 0: finish(s) completes step s (lock-step); 1: it completes step s-1 */
     void* peer_base[POSE_MAX_PEERS];
-    unsigned long long off_ctrl, off_flags, off_rows[2], off_nums[2], off_ids[2];
+    unsigned long long off_ctrl, off_flags, off_rows[POSE_EXCHANGE_SLOTS], off_nums[POSE_EXCHANGE_SLOTS], off_ids[POSE_EXCHANGE_SLOTS];
     const long long* ids_local;               /* device [batch_local][2] (image_id, category_id) of this rank */
     void* multicast_base;                     /* NVLS multicast alias of the buffer on all ranks (multimem.st), or NULL */
 } pose_exchange_t;
@@ -115,6 +118,8 @@ typedef struct pose_exchange {
 unsigned long long pose_exchange_layout(pose_exchange_t* x);
 int pose_exchange_finish(const pose_exchange_t* x, double w0, double w1, double inv_norm, float* loss_out,
                          pose_stream_t stream);
+int pose_exchange_flush(const pose_exchange_t* x, double w0, double w1, double inv_norm, float* loss_out,
+                        pose_stream_t stream);
 
 /* ---- fixed-order reduction of n (a, b) fp64 pairs, `stride` doubles apart: loss = (w0*A + w1*B)*inv_norm.
  *      Used on the all-gathered per-rank numerators (multi-GPU global loss); one CTA, deterministic. */

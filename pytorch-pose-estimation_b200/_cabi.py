@@ -28,6 +28,7 @@ SIGNATURES = {
                             _i, _i, _i, _i, _f, _f, _d, _u, _vp, _vp, _i, _i, _vp, _vp, _ull, _vp]),
     "pose_exchange_layout": (_ull, [_vp]),
     "pose_exchange_finish": (_i, [_vp, _d, _d, _d, _vp, _vp]),
+    "pose_exchange_flush": (_i, [_vp, _d, _d, _d, _vp, _vp]),
     "pose_loss_reduce": (_i, [_vp, _i, _c.c_longlong, _d, _d, _d, _vp, _vp, _vp]),
     "pose_scale_grad": (_i, [_vp, _vp, _ull, _vp]),
     "pose_sbp_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _f, _i, _i, _vp]),
@@ -42,13 +43,15 @@ SIGNATURES = {
 }
 
 MAX_PEERS = 16
+EXCHANGE_SLOTS = 4
 
 
 class ExchangeDesc(ctypes.Structure):
     """pose_exchange_t (include/pose_b200.h)."""
-    _fields_ = [("world", _i), ("rank", _i), ("batch_local", _i), ("num_keypoints", _i), ("row_stride", _i), ("reserved", _i),
+    _fields_ = [("world", _i), ("rank", _i), ("batch_local", _i), ("num_keypoints", _i), ("row_stride", _i), ("defer", _i),
                 ("peer_base", _vp * MAX_PEERS),
-                ("off_ctrl", _ull), ("off_flags", _ull), ("off_rows", _ull * 2), ("off_nums", _ull * 2), ("off_ids", _ull * 2),
+                ("off_ctrl", _ull), ("off_flags", _ull), ("off_rows", _ull * EXCHANGE_SLOTS), ("off_nums", _ull * EXCHANGE_SLOTS),
+                ("off_ids", _ull * EXCHANGE_SLOTS),
                 ("ids_local", _vp), ("multicast_base", _vp)]
 
 

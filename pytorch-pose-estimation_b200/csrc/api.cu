@@ -81,7 +81,7 @@ pose::ExchangeDev to_dev(const pose_exchange_t& x) {
     d.world = x.world; d.rank = x.rank; d.B = x.batch_local; d.K = x.num_keypoints; d.row_stride = x.row_stride;
     for (int r = 0; r < x.world && r < pose::kMaxPeers; ++r) d.peer[r] = reinterpret_cast<unsigned char*>(x.peer_base[r]);
     d.off_ctrl = x.off_ctrl; d.off_flags = x.off_flags;
-    for (int p = 0; p < 2; ++p) { d.off_rows[p] = x.off_rows[p]; d.off_nums[p] = x.off_nums[p]; d.off_ids[p] = x.off_ids[p]; }
+    for (int p = 0; p < POSE_EXCHANGE_SLOTS; ++p) { d.off_rows[p] = x.off_rows[p]; d.off_nums[p] = x.off_nums[p]; d.off_ids[p] = x.off_ids[p]; }
     d.ids_local = x.ids_local;
     d.mc = reinterpret_cast<unsigned char*>(x.multicast_base);
     return d;
@@ -258,7 +258,7 @@ unsigned long long pose_exchange_layout(pose_exchange_t* x) {
     unsigned long long off = 0;
     x->off_ctrl = off; off += 256;
     x->off_flags = off; off += up((unsigned long long)POSE_MAX_PEERS * 8ull);
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < POSE_EXCHANGE_SLOTS; ++p) {
         x->off_rows[p] = off; off += rows;
         x->off_nums[p] = off; off += nums;
         x->off_ids[p] = off; off += ids;
@@ -266,14 +266,24 @@ unsigned long long pose_exchange_layout(pose_exchange_t* x) {
     return off;
 }
 
-int pose_exchange_finish(const pose_exchange_t* x, double w0, double w1, double inv_norm, float* loss_out, pose_stream_t stream) {
-    if (!x || !loss_out || x->world < 1 || x->world > POSE_MAX_PEERS || x->rank < 0 || x->rank >= x->world)
+namespace {
+int exchange_wait(const pose_exchange_t* x, int mode, double w0, double w1, double inv_norm, float* loss_out, pose_stream_t stream) {
+    if (!x || !loss_out || x->world < 1 || x->world > POSE_MAX_PEERS || x->rank < 0 || x->rank >= x->world || x->defer < 0 || x->defer > 1)
         return fail(POSE_EINVAL, "exchange_finish: bad argument");
     // ~2 s at 2 GHz: a peer that never signals must not hang this GPU (POSE_B200_EXCHANGE_TIMEOUT_CYCLES overrides; diagnostics)
     long long timeout = 4000000000ll;
     if (const char* e = getenv("POSE_B200_EXCHANGE_TIMEOUT_CYCLES")) timeout = atoll(e);
-    launch_pdl(pose::exchange_wait_reduce_kernel, 1u, 256u, (cudaStream_t)stream, to_dev(*x), w0, w1, inv_norm, loss_out, timeout);
+    launch_pdl(pose::exchange_wait_reduce_kernel, 1u, 256u, (cudaStream_t)stream, to_dev(*x), x->defer, mode, w0, w1, inv_norm, loss_out, timeout);
     return check_launch("exchange_wait_reduce");
+}
+}  // namespace
+
+int pose_exchange_finish(const pose_exchange_t* x, double w0, double w1, double inv_norm, float* loss_out, pose_stream_t stream) {
+    return exchange_wait(x, 0, w0, w1, inv_norm, loss_out, stream);
+}
+
+int pose_exchange_flush(const pose_exchange_t* x, double w0, double w1, double inv_norm, float* loss_out, pose_stream_t stream) {
+    return exchange_wait(x, 1, w0, w1, inv_norm, loss_out, stream);
 }
 
 int pose_loss_reduce(const double* pairs, int n, long long stride, double w0, double w1, double inv_norm, float* loss_out,

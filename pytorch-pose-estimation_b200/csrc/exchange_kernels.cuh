@@ -3,14 +3,18 @@
 // partials stores the two fp64 numerators the same way.  A one-CTA kernel on each rank then publishes "step s of rank r
 // has landed" with a system-scope release store on every peer, waits (acquire) for all ranks' flags and reduces the
 // gathered numerators in rank order -> the global-batch loss, bit-identical on all ranks.
-// No NCCL call, no staging copy, no host synchronisation; receive regions are double-buffered by step parity, which is
-// safe because a rank can only be one step ahead of the slowest peer (it needs that peer's flag to finish its own step).
+// No NCCL call, no staging copy, no host synchronisation.  Receive regions form a ring of kExchangeSlots steps.  With
+// defer = 0 a rank finishes step s only after every peer's step s has landed (lock-step).  With defer = 1 the wait
+// kernel of step s publishes this rank's flag s but waits only for the peers' step s-1, so ranks may drift up to two
+// steps apart and per-step jitter no longer adds up across GPUs; four slots make that safe: a rank can store step s
+// only after its wait kernel s-1 saw every peer's flag s-2, i.e. every peer's stream is past the consumers of step s-4.
 #pragma once
 #include "sbp_kernels.cuh"
 
 namespace pose {
 
 constexpr int kMaxPeers = 16;
+constexpr int kExchangeSlots = 4;
 
 constexpr int kMaxRowStride = 256;                 // floats per exchanged row (3K+1 padded to a multiple of 4): K <= 85
 
@@ -18,7 +22,7 @@ struct ExchangeDev {
     int world, rank, B, K;
     int row_stride;                                 // floats per row in the receive regions (16-byte aligned rows)
     unsigned char* peer[kMaxPeers];                 // base of every rank's exchange buffer as mapped into THIS process
-    unsigned long long off_ctrl, off_flags, off_rows[2], off_nums[2], off_ids[2];
+    unsigned long long off_ctrl, off_flags, off_rows[kExchangeSlots], off_nums[kExchangeSlots], off_ids[kExchangeSlots];
     const long long* ids_local;                     // [B][2]
     unsigned char* mc;                              // multicast (NVLS) alias of the same buffer on ALL ranks, or nullptr
 };
@@ -55,7 +59,7 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
     pdl_wait();
     ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
     const unsigned long long step = ctrl->step + 1;            // constant while this grid runs
-    const int par = (int)(step & 1);
+    const int par = (int)(step % kExchangeSlots);
     const int stride = 3 * P.K + 1;
 
     if (blockIdx.x == gridDim.x - 1) {
@@ -125,30 +129,33 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
     // stream, and that grid -- exchange_wait_reduce_kernel -- publishes this rank's flag before it waits for the others.
 }
 
-// wait for every rank's flag of this step, reduce the gathered numerators in rank order, advance the step counter
-__global__ void __launch_bounds__(256) exchange_wait_reduce_kernel(ExchangeDev X, double w0, double w1, double inv_norm,
-                                                                   float* __restrict__ loss_out, long long timeout_cycles) {
+// One CTA per rank and step.  mode 0 (finish): publish this rank's flag for step s = ctrl.step+1 (the epilogue grid
+// has completed -- griddepcontrol.wait returns only after its memory operations, peer stores included, are performed --
+// so a system-scope release store suffices), wait for every rank's flag >= s - defer, reduce the numerators of step
+// s - defer in rank order, advance the step counter.  mode 1 (flush, defer > 0 only): wait for and reduce step ctrl.step.
+__global__ void __launch_bounds__(256) exchange_wait_reduce_kernel(ExchangeDev X, int defer, int mode, double w0, double w1,
+                                                                   double inv_norm, float* __restrict__ loss_out, long long timeout_cycles) {
     pdl_wait();
     ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
-    const unsigned long long step = ctrl->step + 1;
-    const int par = (int)(step & 1);
-    // publish "step `step` of rank X.rank has landed everywhere": the epilogue grid has completed (griddepcontrol.wait
-    // above returns only after its memory operations, peer stores included, are performed), so a release store suffices
-    if ((int)threadIdx.x < X.world)
+    const unsigned long long step = ctrl->step + (mode == 0 ? 1 : 0);
+    const unsigned long long need = mode == 0 ? step - (unsigned long long)min((unsigned long long)defer, step) : step;
+    if (mode == 0 && (int)threadIdx.x < X.world)
         st_release_sys(reinterpret_cast<unsigned long long*>(X.peer[threadIdx.x] + X.off_flags) + X.rank, step);
-    if ((int)threadIdx.x < X.world) {
+    if (need > 0 && (int)threadIdx.x < X.world) {
         const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.off_flags) + threadIdx.x;
         const long long t0 = clock64();
-        while (ld_acquire_sys(flag) < step) {
+        while (ld_acquire_sys(flag) < need) {
             if (clock64() - t0 > timeout_cycles) { atomicExch(&ctrl->error, 1u + threadIdx.x); break; }   // never hang the GPU
             __nanosleep(64);
         }
     }
     __syncthreads();
-    const double* nums = reinterpret_cast<const double*>(X.peer[X.rank] + X.off_nums[par]);
-    reduce_pairs_cta(nums, X.world, 2, w0, w1, inv_norm, loss_out, nullptr);
-    __syncthreads();
-    if (threadIdx.x == 0) ctrl->step = step;
+    if (need > 0) {
+        const double* nums = reinterpret_cast<const double*>(X.peer[X.rank] + X.off_nums[need % kExchangeSlots]);
+        reduce_pairs_cta(nums, X.world, 2, w0, w1, inv_norm, loss_out, nullptr);
+        __syncthreads();
+    }
+    if (mode == 0 && threadIdx.x == 0) ctrl->step = step;
 }
 
 }  // namespace pose

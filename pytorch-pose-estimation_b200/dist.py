@@ -121,12 +121,16 @@ class PeerExchange:
     Every rank allocates one exchange buffer with torch's symmetric-memory allocator and maps all peers' buffers.
     `sbp_fused(..., exchange=self)` makes the back-projection epilogue store its rows, the loss numerators and the ids
     directly into every rank's receive region (NVLink peer stores) and raise a per-rank flag; `finish()` launches the
-    one-CTA kernel that waits for all flags and reduces the numerators in rank order.  Receive regions are
-    double-buffered by step parity; `self.steps` (host) mirrors the device step counter so the views of the finished
-    step can be handed out without a synchronisation -- call `advance(n)` after replaying a captured step n times.
+    one-CTA kernel that waits for all flags and reduces the numerators in rank order.  Receive regions form a ring of
+    4 steps; `self.steps` (host) mirrors the device step counter so the views of the completed step can be handed out
+    without a synchronisation -- call `advance(n)` after replaying a captured step n times.
+
+    `defer=1`: `finish()` of step s completes step s-1 (its loss / rows), so ranks need not run in lock-step and
+    per-step jitter does not add up across GPUs; `flush()` completes the last step.  `defer=0`: `finish()` completes
+    the step it belongs to.
     """
 
-    def __init__(self, batch_local, num_keypoints, device, image_ids, category_ids, group=None, multicast=None):
+    def __init__(self, batch_local, num_keypoints, device, image_ids, category_ids, group=None, multicast=None, defer=0):
         import ctypes
         import os
 
@@ -139,6 +143,7 @@ class PeerExchange:
         self.b, self.k, self.device = batch_local, num_keypoints, device
         d = ExchangeDesc()
         d.world, d.rank, d.batch_local, d.num_keypoints = self.world, self.rank, batch_local, num_keypoints
+        d.defer = self.defer = int(defer)
         nbytes = int(lib().pose_exchange_layout(ctypes.byref(d)))
         if nbytes == 0:
             raise ValueError("bad exchange shape")
@@ -167,17 +172,35 @@ class PeerExchange:
             n *= s
         return self.buf[off:off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
 
-    def finish(self, global_batch, lambda_pos=5.0, lambda_neg=1.0):
-        """Wait for every rank's rows of this step and reduce the global loss (stream-ordered, no host sync)."""
+    def _wait(self, fn, global_batch, lambda_pos, lambda_neg):
         import ctypes
 
         from ._cabi import check, lib, ptr, stream_ptr
         with torch.cuda.device(self.device):
-            check(lib().pose_exchange_finish(ctypes.byref(self.desc), float(lambda_pos), float(lambda_neg),
-                                             1.0 / (2.0 * self.k * global_batch), ptr(self.loss), stream_ptr(self.device)),
-                  "pose_exchange_finish")
-        self.steps += 1
+            check(getattr(lib(), fn)(ctypes.byref(self.desc), float(lambda_pos), float(lambda_neg),
+                                     1.0 / (2.0 * self.k * global_batch), ptr(self.loss), stream_ptr(self.device)), fn)
         return self.loss
+
+    def finish(self, global_batch, lambda_pos=5.0, lambda_neg=1.0):
+        """Publish this rank's step, wait for every rank's rows of step (current - defer) and reduce its global loss
+        (stream-ordered, no host sync)."""
+        loss = self._wait("pose_exchange_finish", global_batch, lambda_pos, lambda_neg)
+        self.steps += 1
+        return loss
+
+    def flush(self, global_batch, lambda_pos=5.0, lambda_neg=1.0):
+        """defer=1 only: complete the last published step (its rows / loss are what gathered_*() / the result refer to)."""
+        if self.defer == 0:
+            return self.loss
+        loss = self._wait("pose_exchange_flush", global_batch, lambda_pos, lambda_neg)
+        self._flushed = self.steps
+        return loss
+
+    def _completed(self):
+        """Index of the newest step whose rows are complete on this rank (host mirror)."""
+        if self.defer and getattr(self, "_flushed", -1) == self.steps:
+            return self.steps
+        return self.steps - self.defer
 
     def advance(self, n=1):
         """Tell the host mirror that a captured step was replayed n more times."""
@@ -185,21 +208,21 @@ class PeerExchange:
 
     def gathered_padded(self):
         """[world*B, row_stride] fp32: the receive region of the last finished step as it lies in memory (contiguous)."""
-        return self._view(int(self.desc.off_rows[self.steps & 1]), torch.float32, (self.world * self.b, int(self.desc.row_stride)))
+        return self._view(int(self.desc.off_rows[self._completed() % 4]), torch.float32, (self.world * self.b, int(self.desc.row_stride)))
 
     def gathered_packed(self):
         """[world*B, 3K+1] fp32 rows of the last finished step, image order (a strided view: rows are 16-byte padded)."""
         return self.gathered_padded()[:, :3 * self.k + 1]
 
     def gathered_ids(self):
-        return self._view(int(self.desc.off_ids[self.steps & 1]), torch.int64, (self.world * self.b, 2))
+        return self._view(int(self.desc.off_ids[self._completed() % 4]), torch.int64, (self.world * self.b, 2))
 
     def error(self):
         """Non-zero if a wait timed out (costs a host sync; for tests / diagnostics)."""
         return int(self._view(int(self.desc.off_ctrl) + 12, torch.int32, (1,)).item())
 
 
-def make_exchange(batch_local, num_keypoints, device, image_ids, category_ids, group=None, prefer_p2p=True):
+def make_exchange(batch_local, num_keypoints, device, image_ids, category_ids, group=None, prefer_p2p=True, defer=0):
     """PeerExchange when symmetric memory can be set up across the group, else the NCCL ShardExchange.  Returns (exchange, kind)."""
     if not _active(group):
         ex = ShardExchange(batch_local, num_keypoints, device, group)
@@ -209,7 +232,7 @@ def make_exchange(batch_local, num_keypoints, device, image_ids, category_ids, g
     ex = None
     if prefer_p2p:
         try:
-            ex = PeerExchange(batch_local, num_keypoints, device, image_ids, category_ids, group)
+            ex = PeerExchange(batch_local, num_keypoints, device, image_ids, category_ids, group, defer=defer)
             ok.fill_(1)
         except Exception as e:          # noqa: BLE001 -- any set-up failure (no P2P, no VMM, old driver) means: use NCCL
             import sys

@@ -70,6 +70,23 @@ def _worker(rank, world, port, q):
             assert px.error() == 0
             dist.barrier()
             p2p.append(px.multicast)
+            # deferred completion: finish() of step s completes step s-1, flush() the last one
+            pd_ = pd.PeerExchange(hi - lo, 17, dev, torch.arange(lo, hi, device=dev), torch.ones(hi - lo, dtype=torch.int64, device=dev), defer=1)
+            deferred = []
+            for it in range(4):
+                x_it = logits[lo:hi] * (1.0 + 0.25 * it)
+                pb.sbp_fused(x_it, keypoints=kp[lo:hi], sigma=2, want_grad=False, decode=True, conf_threshold=0.25, coord_scale=4.0,
+                             global_batch=b, bbox=bbox[lo:hi], input_size=(256, 192), exchange=pd_)
+                l_it = pd_.finish(b)
+                torch.cuda.synchronize()
+                if it >= 1:
+                    deferred.append((float(l_it), pd_.gathered_packed().cpu().clone()))
+            l_last = pd_.flush(b)
+            torch.cuda.synchronize()
+            deferred.append((float(l_last), pd_.gathered_packed().cpu().clone()))
+            assert pd_.error() == 0
+            dist.barrier()
+            p2p.append(deferred)
         out.append(p2p)
         q.put(tuple(out))
     finally:
@@ -112,3 +129,10 @@ def test_two_gpu_shards_match_single_gpu():
             assert torch.equal(rows_it, ref["packed"].cpu())
             assert torch.equal(ids_it[:, 0], torch.arange(logits.size(0)))
         assert p2p0[it][0] == p2p1[it][0]                            # bit-identical global loss on every rank
+    for it in range(4):                                              # deferred ring: entry `it` is the completed step `it`
+        ref = pb.sbp_fused(logits * (1.0 + 0.25 * it), keypoints=kp, sigma=2, want_grad=False, decode=True, conf_threshold=0.25,
+                           coord_scale=4.0, bbox=bbox, input_size=(256, 192))
+        for p in (p2p0, p2p1):
+            l_it, rows_it = p[4][it]
+            assert abs(l_it - ref["loss"].item()) <= 1e-6 * abs(ref["loss"].item())
+            assert torch.equal(rows_it, ref["packed"].cpu())
