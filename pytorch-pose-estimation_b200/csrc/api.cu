@@ -355,9 +355,27 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
     P.z = std::sqrt((double)((long long)R * R + (long long)R * R));
     P.N = N; P.Pmax = Pmax; P.K = K; P.R = R;
     const int quads = R * R / 4;
-    const long long grid = (long long)N * ((quads + pose::kSpmThreads - 1) / pose::kSpmThreads);
-    if (grid > 0x7fffffffll) return fail(POSE_EINVAL, "spm_render: grid too large");
-    pose::spm_render_kernel<<<(unsigned)grid, pose::kSpmThreads, (size_t)lut_n * lut_n * sizeof(float), (cudaStream_t)stream>>>(P);
+    const size_t smem = (size_t)lut_n * lut_n * sizeof(float);
+    const long long units = (long long)N * (1 + 2 * K) * ((quads + pose::kSpmRenderChunk - 1) / pose::kSpmRenderChunk);
+    const int grid = persistent_grid(pose::spm_fill_kernel, pose::kSpmThreads, smem, units);
+    pose::spm_fill_kernel<<<grid, pose::kSpmThreads, smem, (cudaStream_t)stream>>>(P);
+    if (int rc = check_launch("spm_fill")) return rc;
+    if (Pmax > 0) {
+        if ((long long)N * Pmax > 0x7fffffffll) return fail(POSE_EINVAL, "spm_render: N*Pmax too large");
+        // quotient table in dynamic shared memory ((2R+1) doubles): needs an explicit launch config for PDL + smem
+        const int div_n = R <= 1024 ? 2 * R + 1 : 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((long long)N * Pmax));
+        cfg.blockDim = dim3((unsigned)pose::kSpmThreads);
+        cfg.dynamicSmemBytes = (size_t)div_n * sizeof(double);
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, pose::spm_patch_kernel, P, div_n);
+    }
     return check_launch("spm_render");
 }
 
@@ -374,12 +392,12 @@ int pose_spm_loss(const float* logits, const float* target, float* dlogits, floa
     cudaStream_t st = (cudaStream_t)stream;
     pose::SpmLossParams P;
     P.logits = logits; P.target = target; P.dlogits = dlogits; P.partials = reinterpret_cast<double*>(workspace);
-    P.quads = R * R / 4; P.units = (long long)N * P.quads; P.C = 1 + 2 * K;
+    P.quads = R * R / 4; P.C = 1 + 2 * K; P.planes = (long long)N * P.C;
     P.groot = (float)(2.0 * (double)lambda_root * inv_norm);
     P.gdisp = (float)((double)lambda_disp * inv_norm);
     int grid = 0;
     if (N > 0) {
-        const long long ctas = (P.units + pose::kSpmThreads - 1) / pose::kSpmThreads;
+        const long long ctas = P.planes * ((P.quads + pose::kSpmLossChunk - 1) / pose::kSpmLossChunk);
         if (write_grad) {
             grid = persistent_grid(pose::spm_loss_kernel<true>, pose::kSpmThreads, 0, ctas);
             pose::spm_loss_kernel<true><<<grid, pose::kSpmThreads, 0, st>>>(P);

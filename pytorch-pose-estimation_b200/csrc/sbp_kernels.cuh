@@ -50,6 +50,8 @@ template <> struct Vec<1> {
 struct Patch {
     int ulx, uly;            // template origin in map coordinates (may be negative)
     int px0, px1, py0, py1;  // clipped destination window, empty when the joint is invisible
+    // flat element range [e0, e0 + ecnt) of the rows the window touches (ecnt == 0: nothing): the cheap per-vector test
+    int e0, ecnt;
 };
 
 __device__ __forceinline__ Patch make_patch(double x, double y, int H, int W, double three_sigma, int lut_n) {
@@ -67,6 +69,8 @@ __device__ __forceinline__ Patch make_patch(double x, double y, int H, int W, do
     p.px1 = min(min(brx, W), p.ulx + lut_n);
     p.py1 = min(min(bry, H), p.uly + lut_n);
     if (!visible) { p.px0 = p.px1 = p.py0 = p.py1 = 0; p.ulx = p.uly = 0; }
+    p.e0 = p.py0 * W;
+    p.ecnt = (p.py1 > p.py0 && p.px1 > p.px0) ? (p.py1 - p.py0) * W : 0;
     return p;
 }
 
@@ -166,29 +170,35 @@ __device__ __forceinline__ float loss_elem(float s, float t, float gpos, float g
     return (pos ? gpos : gneg) * d * ((1.0f - s) * s);
 }
 
-// One vector (V consecutive elements) of the fused render+loss(+grad)(+argmax) pass.
+// One vector (V consecutive elements, flat index e = vi*V) of the fused render+loss(+grad)(+argmax) pass.
 // Every lane first takes the zero-target result (the target is zero on ~93% of a map):
 //   S_neg += s^2,  dL/dp = gneg s^2 (1-s);
-// lanes whose vector touches the joint's Gaussian patch then overwrite their elements from the template.
-// (row, col) is the position of element vi*V and is advanced by 32 vectors on return.
+// then one unsigned compare decides whether the vector can touch the rows of the joint's Gaussian patch; only those
+// lanes compute (row, col), look the template up and replace their elements' results (`arem` collects the s^2 terms
+// that have to be taken out of S_neg again, so the common path stays a single FFMA per element).
 template <int V, bool GRAD, bool WTGT, bool DEC>
 __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[V], float (&tout)[V], int vi, const Patch& pt,
-                                                const float* __restrict__ lut_s, int lut_n, int W, float gpos, float gneg,
-                                                int rstep, int cstep, int& row, int& col, float& apos, float& aneg,
-                                                float& best, int& besti) {
-    float sg[V], c[V];
+                                                const float* __restrict__ lut_s, int lut_n, int W, FastDiv divW, float gpos, float gneg,
+                                                float& apos, float& aneg, float& arem, float& best, int& besti) {
+    float sg[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const float sj = sigmoid_fast(x[j]);
         sg[j] = sj;
-        c[j] = sj * sj;
-        if (GRAD) g[j] = gneg * fmaf(-c[j], sj, c[j]);
+        if (GRAD) {
+            const float c = sj * sj;
+            aneg += c;
+            g[j] = gneg * fmaf(-c, sj, c);
+        } else {
+            aneg = fmaf(sj, sj, aneg);
+        }
         if (DEC && sj > best) { best = sj; besti = vi * V + j; }
         if (WTGT) tout[j] = 0.0f;
     }
-    const int row_last = row + ((col + V - 1) >= W ? 1 : 0);
-    if (row_last >= pt.py0 && row < pt.py1) {
-        int r = row, cc = col;
+    const int e = vi * V;
+    if ((unsigned)(e + (V - 1) - pt.e0) < (unsigned)(pt.ecnt + (V - 1))) {
+        int r = (int)fdiv((uint32_t)e, divW);
+        int cc = e - r * W;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             if (r >= pt.py0 && r < pt.py1 && cc >= pt.px0 && cc < pt.px1) {
@@ -196,7 +206,7 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
                 if (WTGT) tout[j] = t;
                 if (t > 0.0f) {      // t == 0 (underflowed template tail): the zero-target result stands
                     const float d = sg[j] - t;
-                    c[j] = 0.0f;
+                    arem = fmaf(sg[j], sg[j], arem);
                     apos = fmaf(d, d, apos);
                     if (GRAD) g[j] = gpos * d * ((1.0f - sg[j]) * sg[j]);
                 }
@@ -204,12 +214,6 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
             if (++cc >= W) { cc = 0; ++r; }
         }
     }
-    float q = c[0];
-#pragma unroll
-    for (int j = 1; j < V; ++j) q += c[j];
-    aneg += q;
-    col += cstep; row += rstep;
-    if (col >= W) { col -= W; ++row; }
 }
 
 template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
@@ -227,7 +231,6 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel
     const long long nwarps = (long long)gridDim.x * kSbpWarps;
     const int nvec = P.HW / V;
     constexpr int U = (V == 4) ? POSE_FUSED_U : 8;
-    const int rstep = (32 * V) / P.W, cstep = (32 * V) - rstep * P.W;   // 32 vectors further = rstep rows + cstep columns
     double dpos = 0.0, dneg = 0.0;
 
     for (long long map = warp0; map < P.n_maps; map += nwarps) {
@@ -241,12 +244,9 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel
             load_kp(P.kp, P.kp_f64, map, x, y);
             pt = make_patch(x, y, P.H, P.W, P.three_sigma, P.lut_n);
         }
-        float apos = 0.0f, aneg = 0.0f;
+        float apos = 0.0f, aneg = 0.0f, arem = 0.0f;
         float best = -INFINITY;
         int besti = 0x7fffffff;
-        // (row, col) of this lane's current vector, advanced by 32 vectors per step (no per-vector division)
-        int row = (int)fdiv((uint32_t)(lane * V), P.divW);
-        int col = lane * V - row * P.W;
 
         for (int base = lane; base < nvec; base += 32 * U) {
             float xv[U][V], tv[U][V];
@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel
                 if (vi >= nvec) break;
                 float g[V];
                 if (TGT == TGT_RENDER) {
-                    render_loss_vec<V, GRAD, WTGT, DEC>(xv[u], g, tv[u], vi, pt, lut_s, P.lut_n, P.W, P.gpos, P.gneg, rstep, cstep,
-                                                        row, col, apos, aneg, best, besti);
+                    render_loss_vec<V, GRAD, WTGT, DEC>(xv[u], g, tv[u], vi, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg,
+                                                        apos, aneg, arem, best, besti);
                 } else {
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel
         }
         // per-map flush of the fp32 partials into fp64 (keeps the 2e8-term sum accurate and deterministic)
         dpos += (double)apos;
-        dneg += (double)aneg;
+        dneg += (double)aneg - (double)arem;
 
         if (DEC) {
             warp_argmax_first(best, besti);

@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
     const int tiles_per_map = (nvec + kTmaTileVec - 1) / kTmaTileVec;
     const long long my_maps = P.n_maps > warp0 ? (P.n_maps - warp0 + nwarps - 1) / nwarps : 0;
     const long long total = my_maps * tiles_per_map;
-    const int rstep = 128 / P.W, cstep = 128 - rstep * P.W;   // 32 vectors of 4 elements further
     constexpr int D = kTmaStages - 1;                 // tile loads kept in flight
 
     // lane 0 only: start the load of this warp's t-th tile
@@ -81,8 +80,8 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
         for (long long t = 0; t < D && t < total; ++t) issue_load(t);
 
     double dpos = 0.0, dneg = 0.0;
-    float apos = 0.0f, aneg = 0.0f, best = -INFINITY;
-    int besti = 0x7fffffff, row = 0, col = 0;
+    float apos = 0.0f, aneg = 0.0f, arem = 0.0f, best = -INFINITY;
+    int besti = 0x7fffffff;
     Patch pt;
     long long map = warp0;
     int c = 0;                                        // tile index inside the current map
@@ -92,11 +91,9 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
             double x, y;
             load_kp(P.kp, P.kp_f64, map, x, y);
             pt = make_patch(x, y, P.H, P.W, P.three_sigma, P.lut_n);
-            apos = aneg = 0.0f;
+            apos = aneg = arem = 0.0f;
             best = -INFINITY;
             besti = 0x7fffffff;
-            row = (int)fdiv((uint32_t)(lane * 4), P.divW);
-            col = lane * 4 - row * P.W;
         }
         mbar_wait(smem_u32(bars + b), (uint32_t)((t / kTmaStages) & 1));
         float4* tile = reinterpret_cast<float4*>(tiles + b * kTmaTileBytes);
@@ -109,8 +106,8 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
                 const float4 xv4 = tile[li];
                 const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
                 float g[4], unused[4];
-                render_loss_vec<4, GRAD, false, DEC>(xv, g, unused, v0 + li, pt, lut_s, P.lut_n, P.W, P.gpos, P.gneg, rstep, cstep,
-                                                     row, col, apos, aneg, best, besti);
+                render_loss_vec<4, GRAD, false, DEC>(xv, g, unused, v0 + li, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg,
+                                                     apos, aneg, arem, best, besti);
                 if (GRAD) tile[li] = make_float4(g[0], g[1], g[2], g[3]);
             }
         }
@@ -131,7 +128,7 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
         }
         if (++c == tiles_per_map) {                   // last tile of the map: per-map results
             dpos += (double)apos;
-            dneg += (double)aneg;
+            dneg += (double)aneg - (double)arem;
             if (DEC) {
                 warp_argmax_first(best, besti);
                 if (lane == 0) {

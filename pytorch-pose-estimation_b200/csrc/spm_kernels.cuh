@@ -14,8 +14,7 @@ constexpr int kSpmMaxPersonsSmem = 64;   // persons of one image staged in share
 // SPMDisplacementGenerator (:84-95): per person p (in order), per joint j not (x<=0 and y<=0):
 //   disp[2j]   = fp32( fp64(disp[2j])   + mask_p * (xj - col) / z )
 //   disp[2j+1] = fp32( fp64(disp[2j+1]) + mask_p * (yj - row) / z ),   z = sqrt(2 R^2)
-// One thread owns 4 consecutive pixels of the plane and walks all 1+2K channels; stores are coalesced
-// float4 streams (the tensor is ~97% zeros, the kernel is a write stream).
+// The tensor is ~97% zeros: the kernel is a write stream (see spm_render_kernel).
 struct SpmRenderParams {
     const long long* centers;   // [N][Pmax][2]
     const long long* joints;    // [N][Pmax][K][2]
@@ -27,81 +26,164 @@ struct SpmRenderParams {
     int N, Pmax, K, R;
 };
 
-__global__ void __launch_bounds__(kSpmThreads) spm_render_kernel(SpmRenderParams P) {
+struct SpmPerson {
+    int cx, cy;                 // centre
+    int ulx, uly, brx, bry;     // Gaussian patch corners (fp64 half-to-even rounding done once per person and work unit)
+};
+
+constexpr int kSpmRenderU = 4;
+constexpr int kSpmRenderChunk = kSpmThreads * kSpmRenderU;    // float4 per work unit (16 KB of one plane)
+
+// Render = two launches.
+//  (1) spm_fill_kernel: ONE linear write stream over the whole target, plane by plane (unit = 16 KB of a plane).
+//      Displacement planes are written as zeros with no other work; root planes stage the image's persons (integer
+//      patch geometry + a per-row bitmask of the persons touching each row) and take the max of the template patches.
+//  (2) spm_patch_kernel: the ~3% of displacement pixels inside some person's box, one thread per (joint, pixel):
+//      full lane efficiency where v1-v3 ran a 32-lane warp for 3 covered lanes (profiles/: that path, not the 587 MB of
+//      stores, set the run time).
+__global__ void __launch_bounds__(kSpmThreads) spm_fill_kernel(SpmRenderParams P) {
     extern __shared__ float lut_s[];
-    __shared__ int s_cx[kSpmMaxPersonsSmem], s_cy[kSpmMaxPersonsSmem];
-    const int quads = P.R * P.R / 4;
-    const int ctas_per_img = (quads + kSpmThreads - 1) / kSpmThreads;
-    const int img = blockIdx.x / ctas_per_img;
-    const int q = (blockIdx.x - img * ctas_per_img) * kSpmThreads + threadIdx.x;
+    __shared__ SpmPerson s_p[kSpmMaxPersonsSmem];
+    __shared__ unsigned long long s_rootmask[72];                       // per row of the unit: persons whose patch touches it
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
+    const int C = 1 + 2 * P.K;
+    const int quads = P.R * P.R / 4;
+    const int qpr = P.R / 4;                                            // quads per row
+    const int upp = (quads + kSpmRenderChunk - 1) / kSpmRenderChunk;
+    const long long units = (long long)P.N * C * upp;
+    float4* out4 = reinterpret_cast<float4*>(P.target);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const long long plane = unit / upp;
+        const int chunk = (int)(unit - plane * upp);
+        const int img = (int)(plane / C), c = (int)(plane - (long long)img * C);
+        const int q_lo = chunk * kSpmRenderChunk, q_hi = min(quads, q_lo + kSpmRenderChunk);   // [q_lo, q_hi)
+        float4* dst = out4 + plane * quads;
+        if (c != 0) {                                                   // CTA-uniform: 34 of 35 planes
+#pragma unroll
+            for (int u = 0; u < kSpmRenderU; ++u) {
+                const int q = q_lo + u * kSpmThreads + threadIdx.x;
+                if (q < q_hi) __stcs(dst + q, z4);
+            }
+            continue;
+        }
+        // root plane: SPMHeatmapGenerator -- max with each person's template patch, clipped to the map (no clamp of the centre)
+        const int np = min(max(P.counts[img], 0), P.Pmax);
+        const int row_lo = q_lo / qpr, nrows = (q_hi - 1) / qpr - row_lo + 1;                    // <= 66 rows
+        float a[kSpmRenderU][4];
+#pragma unroll
+        for (int u = 0; u < kSpmRenderU; ++u) a[u][0] = a[u][1] = a[u][2] = a[u][3] = 0.0f;
+        for (int p0 = 0; p0 < np; p0 += kSpmMaxPersonsSmem) {
+            const int pc = min(kSpmMaxPersonsSmem, np - p0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < pc; i += blockDim.x) {
+                const long long pi = (long long)img * P.Pmax + p0 + i;
+                SpmPerson sp;
+                sp.cx = (int)P.centers[pi * 2];
+                sp.cy = (int)P.centers[pi * 2 + 1];
+                sp.ulx = (int)rint(((double)sp.cx - P.three_sigma) - 1.0);
+                sp.uly = (int)rint(((double)sp.cy - P.three_sigma) - 1.0);
+                sp.brx = (int)rint(((double)sp.cx + P.three_sigma) + 2.0);
+                sp.bry = (int)rint(((double)sp.cy + P.three_sigma) + 2.0);
+                s_p[i] = sp;
+            }
+            __syncthreads();
+            for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+                const int row = row_lo + r;
+                unsigned long long m = 0ull;
+                for (int p = 0; p < pc; ++p) {
+                    const SpmPerson sp = s_p[p];
+                    if (sp.cx <= 0 && sp.cy <= 0) continue;
+                    if (row >= max(0, sp.uly) && row < min(sp.bry, P.R) && row - sp.uly < P.lut_n) m |= 1ull << p;
+                }
+                s_rootmask[r] = m;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < kSpmRenderU; ++u) {
+                const int q = q_lo + u * kSpmThreads + threadIdx.x;
+                if (q >= q_hi) continue;
+                const int row = q / qpr, col0 = (q - row * qpr) * 4;
+                unsigned long long m = s_rootmask[row - row_lo];
+                while (m) {
+                    const int p = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const SpmPerson sp = s_p[p];
+                    const int gy = row - sp.uly;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int cc = col0 + e, gx = cc - sp.ulx;
+                        if (cc >= max(0, sp.ulx) && cc < min(sp.brx, P.R) && gx < P.lut_n)
+                            a[u][e] = fmaxf(a[u][e], lut_s[gy * P.lut_n + gx]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kSpmRenderU; ++u) {
+            const int q = q_lo + u * kSpmThreads + threadIdx.x;
+            if (q < q_hi) __stcs(dst + q, make_float4(a[u][0], a[u][1], a[u][2], a[u][3]));
+        }
+    }
+}
+
+// SPMMaskGenerator + SPMDisplacementGenerator on the covered pixels.  One CTA per (image, person p); its threads walk
+// (joint j, pixel of p's box).  A pixel is handled by the LOWEST-index person whose box covers it (so every covered pixel
+// is written exactly once) and that thread replays ALL covering persons in order:
+//   disp[2j]   = fp32(fp64(disp[2j])   + (xj - col) / z),   disp[2j+1] = fp32(fp64(disp[2j+1]) + (yj - row) / z)
+// skipping persons whose centre or whose joint j is (<=0, <=0) -- the reference's accumulation order and rounding.
+constexpr int kSpmPatchPersons = 256;       // centres of one image kept in shared memory (more: read through L1)
+
+__global__ void __launch_bounds__(kSpmThreads) spm_patch_kernel(SpmRenderParams P, int div_n) {
+    // dynamic shared memory: quotient table (joint - coord) / z for every integer difference in [-R, R] -- exactly the fp64
+    // values the reference computes, so a covered pixel costs a shared-memory load instead of a software fp64 division
+    extern __shared__ __align__(16) double div_s[];
+    __shared__ int s_cx[kSpmPatchPersons], s_cy[kSpmPatchPersons];
+    const int img = blockIdx.x / P.Pmax, p = blockIdx.x - img * P.Pmax;
     const int np = min(max(P.counts[img], 0), P.Pmax);
-    const int row = (q * 4) / P.R, col0 = (q * 4) - row * P.R;
-    const bool active = q < quads;
+    const long long* cen = P.centers + (long long)img * P.Pmax * 2;
+    if (p >= np) return;                                                // CTA-uniform
+    const int cx = (int)__ldg(cen + 2 * p), cy = (int)__ldg(cen + 2 * p + 1);
+    if (cx <= 0 && cy <= 0) return;
+    for (int i = threadIdx.x; i < div_n; i += blockDim.x) div_s[i] = (double)(i - P.R) / P.z;
+    for (int i = threadIdx.x; i < min(np, kSpmPatchPersons); i += blockDim.x) {
+        s_cx[i] = (int)__ldg(cen + 2 * i);
+        s_cy[i] = (int)__ldg(cen + 2 * i + 1);
+    }
+    __syncthreads();
+    pdl_wait();                                                         // the zero fill of the same planes comes first
+    const int side = 2 * P.half + 1;
+    const int items = P.K * side * side;
     const long long plane = (long long)P.R * P.R;
-    float* out = P.target + (long long)img * (1 + 2 * P.K) * plane + (long long)q * 4;
-
-    float root[4] = {0.f, 0.f, 0.f, 0.f};
-    // displacement accumulators are kept per channel pair inside the channel loop; persons are staged
-    // through shared memory in chunks so Pmax is unbounded
-    bool any_cover = false;
-    for (int p0 = 0; p0 < np; p0 += kSpmMaxPersonsSmem) {
-        const int pc = min(kSpmMaxPersonsSmem, np - p0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < pc; i += blockDim.x) {
-            s_cx[i] = (int)P.centers[((long long)img * P.Pmax + p0 + i) * 2];
-            s_cy[i] = (int)P.centers[((long long)img * P.Pmax + p0 + i) * 2 + 1];
-        }
-        __syncthreads();
-        if (!active) continue;
-        for (int p = 0; p < pc; ++p) {
-            const int cx = s_cx[p], cy = s_cy[p];
-            if (cx <= 0 && cy <= 0) continue;
-            // root Gaussian
-            const int ulx = (int)rint(((double)cx - P.three_sigma) - 1.0), uly = (int)rint(((double)cy - P.three_sigma) - 1.0);
-            const int brx = (int)rint(((double)cx + P.three_sigma) + 2.0), bry = (int)rint(((double)cy + P.three_sigma) + 2.0);
-            const int gy = row - uly;
-            if (row >= max(0, uly) && row < min(bry, P.R) && gy < P.lut_n) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = col0 + j, gx = c - ulx;
-                    if (c >= max(0, ulx) && c < min(brx, P.R) && gx < P.lut_n) root[j] = fmaxf(root[j], lut_s[gy * P.lut_n + gx]);
-                }
-            }
-            if (row >= cy - P.half && row < cy + P.half + 1 && col0 + 3 >= cx - P.half && col0 < cx + P.half + 1) any_cover = true;
-        }
-    }
-    if (!active) return;
-    __stcs(reinterpret_cast<float4*>(out), make_float4(root[0], root[1], root[2], root[3]));
-
-    if (!any_cover) {
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = 1; c <= 2 * P.K; ++c) __stcs(reinterpret_cast<float4*>(out + c * plane), z4);
-        return;
-    }
-    // covered pixels (a few percent of the plane): walk persons in order for every joint
-    for (int j = 0; j < P.K; ++j) {
-        float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int p = 0; p < np; ++p) {
-            const long long* cp = P.centers + ((long long)img * P.Pmax + p) * 2;
-            const int cx = (int)cp[0], cy = (int)cp[1];
-            if (cx <= 0 && cy <= 0) continue;
-            if (!(row >= max(0, cy - P.half) && row < min(P.R, cy + P.half + 1))) continue;
-            const long long* jp = P.joints + (((long long)img * P.Pmax + p) * P.K + j) * 2;
-            const long long jx = jp[0], jy = jp[1];
+    float* out = P.target + (long long)img * (1 + 2 * P.K) * plane;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int j = it / (side * side), pi = it - j * side * side;
+        const int dy = pi / side, dx = pi - dy * side;
+        const int row = cy - P.half + dy, col = cx - P.half + dx;
+        if (row < 0 || row >= P.R || col < 0 || col >= P.R) continue;
+        float ax = 0.0f, ay = 0.0f;
+        bool mine = true;
+        for (int q = 0; q < np; ++q) {
+            int qx, qy;
+            if (q < kSpmPatchPersons) { qx = s_cx[q]; qy = s_cy[q]; }
+            else { qx = (int)__ldg(cen + 2 * q); qy = (int)__ldg(cen + 2 * q + 1); }
+            if (qx <= 0 && qy <= 0) continue;
+            if (row < qy - P.half || row > qy + P.half || col < qx - P.half || col > qx + P.half) continue;
+            if (q < p) { mine = false; break; }                         // an earlier person's CTA owns this pixel
+            const long long* jp = P.joints + (((long long)img * P.Pmax + q) * P.K + j) * 2;
+            const long long jx = __ldg(jp), jy = __ldg(jp + 1);
             if (jx <= 0 && jy <= 0) continue;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = col0 + e;
-                if (c >= max(0, cx - P.half) && c < min(P.R, cx + P.half + 1)) {
-                    ax[e] = (float)((double)ax[e] + (double)(jx - (long long)c) / P.z);
-                    ay[e] = (float)((double)ay[e] + (double)(jy - (long long)row) / P.z);
-                }
-            }
+            const long long ddx = jx - (long long)col, ddy = jy - (long long)row;
+            const double qx_ = (div_n && ddx >= -P.R && ddx <= P.R) ? div_s[(int)ddx + P.R] : (double)ddx / P.z;
+            const double qy_ = (div_n && ddy >= -P.R && ddy <= P.R) ? div_s[(int)ddy + P.R] : (double)ddy / P.z;
+            ax = (float)((double)ax + qx_);
+            ay = (float)((double)ay + qy_);
         }
-        __stcs(reinterpret_cast<float4*>(out + (1 + 2 * j) * plane), make_float4(ax[0], ax[1], ax[2], ax[3]));
-        __stcs(reinterpret_cast<float4*>(out + (2 + 2 * j) * plane), make_float4(ay[0], ay[1], ay[2], ay[3]));
+        if (!mine) continue;
+        out[(1 + 2 * j) * plane + (long long)row * P.R + col] = ax;
+        out[(2 + 2 * j) * plane + (long long)row * P.R + col] = ay;
     }
 }
 
@@ -112,66 +194,75 @@ __global__ void __launch_bounds__(kSpmThreads) spm_render_kernel(SpmRenderParams
 struct SpmLossParams {
     const float* logits; const float* target; float* dlogits;
     double* partials;            // [grid][2]  (S_root, S_disp)
-    long long units;             // N * R*R/4
-    int quads;                   // R*R/4
+    long long planes;            // N * C channel planes
+    int quads;                   // R*R/4 float4 per plane
     int C;                       // 1 + 2K
     float groot, gdisp;          // 2*lambda_root*inv_norm, lambda_disp*inv_norm
 };
 
+constexpr int kSpmLossU = 4;                                  // float4 per thread and tensor in flight
+constexpr int kSpmLossChunk = kSpmThreads * kSpmLossU;        // float4 per work unit (1024 -> 16 KB per tensor)
+
+// The tensors are streamed linearly, plane by plane (unit = 16 KB of one channel plane), exactly like the SBP kernels;
+// the root mask of a displacement plane comes from channel 0 of the same image, re-read through L2 (64 KB per image).
 template <bool GRAD>
 __global__ void __launch_bounds__(kSpmThreads) spm_loss_kernel(SpmLossParams P) {
     __shared__ double red[kSpmThreads / 32][2];
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long plane4 = P.quads;    // float4 per channel plane
+    pdl_launch_dependents();
+    const int upp = (P.quads + kSpmLossChunk - 1) / kSpmLossChunk;          // units per plane
+    const long long units = P.planes * upp;
+    const float4* L4 = reinterpret_cast<const float4*>(P.logits);
+    const float4* T4 = reinterpret_cast<const float4*>(P.target);
+    float4* G4 = reinterpret_cast<float4*>(P.dlogits);
     double droot = 0.0, ddisp = 0.0;
-    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < P.units; u += stride) {
-        const long long img = u / P.quads;
-        const int q = (int)(u - img * P.quads);
-        const float4* lp = reinterpret_cast<const float4*>(P.logits) + img * P.C * plane4 + q;
-        const float4* tp = reinterpret_cast<const float4*>(P.target) + img * P.C * plane4 + q;
-        float4* gp = GRAD ? reinterpret_cast<float4*>(P.dlogits) + img * P.C * plane4 + q : nullptr;
-        const float4 p0 = ldg_stream(lp), t0 = ldg_stream(tp);
-        const float pv[4] = {p0.x, p0.y, p0.z, p0.w}, tv[4] = {t0.x, t0.y, t0.z, t0.w};
-        bool m[4];
-        float g0[4];
-        float aroot = 0.f, adisp = 0.f;
-        bool anym = false;
+    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const long long plane = unit / upp;
+        const int chunk = (int)(unit - plane * upp);
+        const int c = (int)(plane % P.C);
+        const long long off = plane * P.quads, off0 = (plane - c) * P.quads;  // this plane / the image's root plane
+        float4 pv[kSpmLossU], tv[kSpmLossU], t0[kSpmLossU];
+        int q[kSpmLossU];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            m[e] = tv[e] > 0.0f;
-            anym |= m[e];
-            const float s = sigmoid_fast(pv[e]);
-            const float d = (m[e] ? s : s * 0.0f) - tv[e];
-            aroot = fmaf(d, d, aroot);
-            g0[e] = m[e] ? P.groot * d * ((1.0f - s) * s) : 0.0f;
+        for (int u = 0; u < kSpmLossU; ++u) {
+            q[u] = chunk * kSpmLossChunk + u * kSpmThreads + threadIdx.x;
+            if (q[u] < P.quads) {
+                pv[u] = ldg_stream(L4 + off + q[u]);
+                tv[u] = ldg_stream(T4 + off + q[u]);
+                if (c != 0) t0[u] = __ldg(T4 + off0 + q[u]);
+            }
         }
-        if (GRAD) __stcs(gp, make_float4(g0[0], g0[1], g0[2], g0[3]));
-        constexpr int CU = 4;
-        for (int c = 1; c < P.C; c += CU) {
-            float4 pc[CU], tc[CU];
+        float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < CU; ++k)
-                if (c + k < P.C) { pc[k] = ldg_stream(lp + (c + k) * plane4); tc[k] = ldg_stream(tp + (c + k) * plane4); }
+        for (int u = 0; u < kSpmLossU; ++u) {
+            if (q[u] >= P.quads) break;
+            const float pe[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w}, te[4] = {tv[u].x, tv[u].y, tv[u].z, tv[u].w};
+            float ge[4];
+            if (c == 0) {
 #pragma unroll
-            for (int k = 0; k < CU; ++k) {
-                if (c + k >= P.C) break;
-                const float pe[4] = {pc[k].x, pc[k].y, pc[k].z, pc[k].w}, te[4] = {tc[k].x, tc[k].y, tc[k].z, tc[k].w};
-                float ge[4];
+                for (int e = 0; e < 4; ++e) {
+                    const bool m = te[e] > 0.0f;
+                    const float s = sigmoid_fast(pe[e]);
+                    const float d = (m ? s : s * 0.0f) - te[e];
+                    acc = fmaf(d, d, acc);
+                    ge[e] = m ? P.groot * d * ((1.0f - s) * s) : 0.0f;
+                }
+            } else {
+                const float me[4] = {t0[u].x, t0[u].y, t0[u].z, t0[u].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
+                    const bool m = me[e] > 0.0f;
                     float th = 0.0f, pm = pe[e] != pe[e] ? pe[e] : 0.0f;    // NaN logits propagate as in the reference
-                    if (m[e]) { th = tanhf(pe[e]); pm = th; }
+                    if (m) { th = tanhf(pe[e]); pm = th; }
                     const float d = pm - te[e];
                     const float ad = fabsf(d);
-                    adisp += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-                    ge[e] = m[e] ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
+                    acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+                    ge[e] = m ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
                 }
-                if (GRAD) __stcs(gp + (c + k) * plane4, make_float4(ge[0], ge[1], ge[2], ge[3]));
             }
+            if (GRAD) __stcs(G4 + off + q[u], make_float4(ge[0], ge[1], ge[2], ge[3]));
         }
-        droot += (double)aroot;
-        ddisp += (double)adisp;
+        if (c == 0) droot += (double)acc; else ddisp += (double)acc;
     }
     droot = warp_sum(droot);
     ddisp = warp_sum(ddisp);

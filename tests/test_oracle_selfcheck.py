@@ -1,0 +1,65 @@
+"""Property tests of the oracle against itself (CPU): loop forms vs vectorised forms, closed forms vs op-order forms,
+render -> decode round trips, on hypothesis-generated shapes and keypoints (edge coordinates included)."""
+import numpy as np
+import torch
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import sbp_oracle as so
+from oracle import spm_oracle as po
+
+shapes = st.sampled_from([(3, 16, 12, 1), (2, 20, 28, 1.5), (4, 32, 24, 2), (1, 9, 7, 1), (2, 64, 48, 3)])
+coords = st.one_of(st.floats(-3, 80, allow_nan=False), st.sampled_from([-1.0, -0.0, 0.0, 0.999999999, 11.5, 47.9, 63.9, 1e6]))
+
+
+@settings(max_examples=40, deadline=None)
+@given(shape=shapes, data=st.data())
+def test_sbp_render_loop_equals_vectorised_and_roundtrips(shape, data):
+    k, h, w, sigma = shape
+    kp = np.array(data.draw(st.lists(st.tuples(coords, coords), min_size=2 * k, max_size=2 * k))).reshape(2, k, 2)
+    vec = so.sbp_render(kp, h, w, sigma)
+    loop = np.stack([so.sbp_render_loop(kp[b], h, w, sigma) for b in range(2)])
+    assert vec.dtype == np.float32 and np.array_equal(vec, loop)
+    if sigma != int(sigma):
+        return          # half-integer template centre: no pixel reaches 1.0, the known-answer round trip does not apply
+    j = so.sbp_decode(torch.from_numpy(vec), 4 * w, 0.99, False).numpy()
+    vis = ~((kp[..., 0] < 0) | (kp[..., 1] < 0))
+    cx = np.clip(np.trunc(np.where(vis, kp[..., 0], 0)), 0, w - 1)
+    cy = np.clip(np.trunc(np.where(vis, kp[..., 1], 0)), 0, h - 1)
+    assert np.array_equal(j[vis][:, 0], 4.0 * cx[vis]) and np.array_equal(j[vis][:, 1], 4.0 * cy[vis])
+    assert np.all(j[~vis] == np.array([-4.0, -4.0, -1.0], dtype=np.float32))
+
+
+@settings(max_examples=15, deadline=None)
+@given(shape=shapes, seed=st.integers(0, 10_000), scale=st.sampled_from([0.5, 3.0, 8.0]))
+def test_sbp_loss_closed_form_and_decode_forms_agree(shape, seed, scale):
+    k, h, w, sigma = shape
+    kp, logits, *_ = so.make_config1_inputs(3, k, h, w, seed=seed, torch_seed=seed)
+    logits = logits * scale
+    t = torch.from_numpy(so.sbp_render(kp, h, w, sigma))
+    loss, grad = so.sbp_loss_and_grad(logits, t)
+    l64, g64 = so.sbp_loss_closed_form_f64(logits, t)
+    assert abs(float(loss) - float(l64)) <= 2e-6 * abs(float(l64))
+    assert float((grad.double() - g64).abs().max()) <= 2e-6 * float(g64.abs().max()) + 1e-12
+    for thr, pred in ((0.25, True), (0.9, True), (0.5, False)):
+        a = so.sbp_decode(logits, 4 * w, thr, pred)
+        b = torch.stack([so.sbp_decode_loop(logits[i:i + 1], 4 * w, thr, pred) for i in range(3)])
+        assert torch.equal(a, b)
+
+
+@settings(max_examples=10, deadline=None)
+@given(seed=st.integers(0, 10_000), res=st.sampled_from([24, 32, 48]), k=st.integers(1, 4))
+def test_spm_forms_agree(seed, res, k):
+    people = po.make_config4_people(2, k=k, res=res, max_people=4, seed=seed)
+    target = np.stack([po.spm_render(c, j, res, 1) for c, j in people])
+    logits = po.spm_logits_from_target(target, seed=seed)
+    tt = torch.from_numpy(target)
+    loss, grad = po.spm_loss_and_grad(logits, tt)
+    l64, g64 = po.spm_loss_closed_form_f64(logits, tt)
+    assert abs(float(loss) - float(l64)) <= 2e-6 * abs(float(l64)) + 1e-12
+    assert float((grad.double() - g64).abs().max()) <= 1e-5 * float(g64.abs().max()) + 1e-12
+    # decoding the target itself finds every non-overlapping centre exactly
+    for b, (c, j) in enumerate(people):
+        roots, kps = po.spm_decode(tt[b:b + 1], res, 1, 0.99, False)
+        found = {(int(r[0]), int(r[1])) for r in roots} if roots.dim() == 2 else set()
+        assert found <= {(int(x), int(y)) for x, y in c[:, 0]}

@@ -44,6 +44,31 @@ def test_render_bit_exact(pb, dev, name, n):
     assert np.array_equal(pb.spm_render_batch(c2, j2, cnt, meta["res"], meta["sigma"]).cpu().numpy(), g["target"])
 
 
+def test_render_many_persons_and_empty_images(pb, dev):
+    """More persons than one shared-memory pass (64), overlapping boxes (displacements add up in person order),
+    images without persons, and persons whose centre is (0, 0) (skipped)."""
+    rng = np.random.default_rng(3)
+    k, res, sigma = 3, 64, 1
+    people = []
+    for p in (70, 0, 130, 1):
+        c = rng.integers(2, res - 2, size=(p, 1, 2), dtype=np.int64)
+        j = np.clip(c + rng.integers(-20, 21, size=(p, k, 2), dtype=np.int64), 0, res - 1)
+        if p:
+            c[0] = 0                              # centre (0,0): skipped by all three generators
+            j[p // 2, 1] = 0                      # joint (0,0): skipped
+        people.append((c, j))
+    want = np.stack([po.spm_render(c, j, res, sigma) for c, j in people])
+    pmax = 130
+    cc = np.zeros((4, pmax, 2), dtype=np.int64)
+    jj = np.zeros((4, pmax, k, 2), dtype=np.int64)
+    cnt = np.array([70, 0, 130, 1], dtype=np.int32)
+    for i, (c, j) in enumerate(people):
+        cc[i, :c.shape[0]] = c[:, 0]
+        jj[i, :c.shape[0]] = j
+    got = pb.spm_render_batch(cc, jj, cnt, res, sigma).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
 def test_generator_dropins(pb, dev):
     """The reference's three-object protocol (dataset/spm_coco_dataset.py:77-86), per image, numpy in / numpy out."""
     g = load_golden("spm_small")

@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--hw", default="64x48")
     ap.add_argument("--k", type=int, default=17)
+    ap.add_argument("--tma", action="store_true", help="fused render variants through the TMA-staged kernel")
+    ap.add_argument("--no-spm", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     B, K = args.batch, args.k
@@ -81,10 +83,15 @@ def main():
 
     out = torch.empty_like(logits)
     run("render_only", lambda: gen_t.render_batch(kp, out=out), map_bytes + 8)
-    run("fused_render_loss_grad", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma), 2 * map_bytes + 8)
-    run("fused_render_loss_grad_decode", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, decode=True, coord_scale=4.0), 2 * map_bytes + 20)
-    run("fused_render_loss_only(no grad)", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, want_grad=False), map_bytes + 8)
-    run("fused_render_loss_decode(no grad)", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, want_grad=False, decode=True), map_bytes + 20)
+    tma = args.tma
+    dl = torch.empty_like(logits)
+    fo = dict(dlogits=dl, joints=torch.empty(B, K, 3, device=dev), loss=torch.empty((), device=dev), loss_num=torch.empty(2, dtype=torch.float64, device=dev))
+    run("fused_render_loss_grad", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, tma=tma, out=fo), 2 * map_bytes + 8)
+    run("fused_render_loss_grad_decode", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, decode=True, coord_scale=4.0, tma=tma, out=fo), 2 * map_bytes + 20)
+    run("fused_render_loss_only(no grad)", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, want_grad=False, tma=tma, out=fo), map_bytes + 8)
+    run("fused_render_loss_decode(no grad)", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, want_grad=False, decode=True, tma=tma, out=fo), map_bytes + 20)
+    run("fused_full_step(+backproject epilogue)", lambda: pb.sbp_fused(logits, keypoints=kp, sigma=sigma, decode=True, coord_scale=4.0, tma=tma, out=fo,
+                                                                         bbox=bbox, input_size=(4 * H, 4 * W)), 2 * map_bytes + 20 + 24)
     run("dense_loss_grad", lambda: pb.sbp_fused(logits, target=target), 3 * map_bytes)
     run("dense_loss_only(no grad)", lambda: pb.sbp_fused(logits, target=target, want_grad=False), 2 * map_bytes)
     for pred in (True, False):
@@ -94,7 +101,7 @@ def main():
     run("decode_interval_pred0_target_thr.99", lambda: pb.decode_batch(target, 0.99, 4.0, False), map_bytes + 12)
     run("backproject_rows", lambda: pb.backproject_rows(joints, bbox, (256, 192)), 24)
 
-    if not args.only or "spm" in args.only:
+    if (not args.only or "spm" in args.only) and not args.no_spm:
         from oracle import cases        # input generator only (tools/ is not the product)
         n = 256
         people, tgt_np, lg, meta = cases.spm_case("coco", 16, seed=99)
@@ -118,7 +125,7 @@ def main():
         run_spm("spm_loss_only(N=256)", lambda: pb.spm_loss_fused(x, t, want_grad=False), 2 * img_bytes)
         run_spm("spm_decode(N=256,thr=.5)", lambda: pb.spm_decode_batch(x, 512, 1, 0.5, True, 32), 128 * 128 * 4)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    json.dump({"batch": B, "K": K, "H": H, "W": W, "peak_GBps": pk, "results": res}, open(args.out, "w"), indent=1)
+    json.dump({"batch": B, "K": K, "H": H, "W": W, "tma": args.tma, "peak_GBps": pk, "results": res}, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":
