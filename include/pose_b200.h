@@ -99,20 +99,23 @@ int pose_sbp_fused(const float* logits, const float* target_in,
  * rank's receive region and raise a per-rank flag; pose_exchange_finish waits for all flags of the step and reduces
  * the gathered numerators (rank order) into the global-batch loss.  Receive regions form a ring of
  * POSE_EXCHANGE_SLOTS steps; the rows ([world*batch_local][row_stride] fp32, the first 3K+1 of each valid) and ids
- * of completed step c are at pose_exchange_t.off_rows/off_ids[c % POSE_EXCHANGE_SLOTS].  With defer = 1,
- * pose_exchange_finish of step s completes step s-1 (ranks may drift instead of running in lock-step) and
- * pose_exchange_flush completes the last one. */
+ * of completed step c are at pose_exchange_t.off_rows/off_ids[c % POSE_EXCHANGE_SLOTS].  With defer = 1 there is
+ * no per-step finish launch at all: a step is published by the next step's fused kernel and completed inside the next
+ * step's epilogue (ranks may drift up to two steps apart); pose_exchange_flush completes the last one. */
 #define POSE_MAX_PEERS 16
 #define POSE_EXCHANGE_SLOTS 4
 typedef struct pose_exchange {
     int world, rank;
     int batch_local, num_keypoints;
     int row_stride;                           /* floats per exchanged row: 3K+1 rounded up to a multiple of 4 (set by _layout) */
-    int defer;                                /* 0: finish(s) completes step s (lock-step); 1: it completes step s-1 */
+    int defer;                                /* 0: lock-step, pose_exchange_finish(s) completes step s;
+                                                 1: in-band -- the fused kernel of step s+1 publishes step s, the epilogue of
+                                                    step s+1 completes it (writes its loss to loss_prev); no finish launch */
     void* peer_base[POSE_MAX_PEERS];
     unsigned long long off_ctrl, off_flags, off_rows[POSE_EXCHANGE_SLOTS], off_nums[POSE_EXCHANGE_SLOTS], off_ids[POSE_EXCHANGE_SLOTS];
     const long long* ids_local;               /* device [batch_local][2] (image_id, category_id) of this rank */
     void* multicast_base;                     /* NVLS multicast alias of the buffer on all ranks (multimem.st), or NULL */
+    float* loss_prev;                         /* defer = 1: device scalar receiving the global loss of the previous step */
 } pose_exchange_t;
 /* fills the off_* fields of *x from world / batch_local / num_keypoints and returns the buffer size in bytes */
 unsigned long long pose_exchange_layout(pose_exchange_t* x);

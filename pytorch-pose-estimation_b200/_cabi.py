@@ -52,7 +52,7 @@ class ExchangeDesc(ctypes.Structure):
                 ("peer_base", _vp * MAX_PEERS),
                 ("off_ctrl", _ull), ("off_flags", _ull), ("off_rows", _ull * EXCHANGE_SLOTS), ("off_nums", _ull * EXCHANGE_SLOTS),
                 ("off_ids", _ull * EXCHANGE_SLOTS),
-                ("ids_local", _vp), ("multicast_base", _vp)]
+                ("ids_local", _vp), ("multicast_base", _vp), ("loss_prev", _vp)]
 
 
 _lib = None

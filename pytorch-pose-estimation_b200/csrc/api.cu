@@ -75,7 +75,13 @@ void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStrea
     cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-pose::ExchangeDev to_dev(const pose_exchange_t& x) {
+long long exchange_timeout_cycles() {
+    // ~2 s at 2 GHz: a peer that never signals must not hang this GPU (POSE_B200_EXCHANGE_TIMEOUT_CYCLES overrides; diagnostics)
+    if (const char* e = getenv("POSE_B200_EXCHANGE_TIMEOUT_CYCLES")) return atoll(e);
+    return 4000000000ll;
+}
+
+pose::ExchangeDev to_dev(const pose_exchange_t& x, double w0 = 0.0, double w1 = 0.0, double inv_norm = 0.0) {
     pose::ExchangeDev d;
     memset(&d, 0, sizeof(d));
     d.world = x.world; d.rank = x.rank; d.B = x.batch_local; d.K = x.num_keypoints; d.row_stride = x.row_stride;
@@ -84,6 +90,8 @@ pose::ExchangeDev to_dev(const pose_exchange_t& x) {
     for (int p = 0; p < POSE_EXCHANGE_SLOTS; ++p) { d.off_rows[p] = x.off_rows[p]; d.off_nums[p] = x.off_nums[p]; d.off_ids[p] = x.off_ids[p]; }
     d.ids_local = x.ids_local;
     d.mc = reinterpret_cast<unsigned char*>(x.multicast_base);
+    d.defer = x.defer; d.loss_prev = x.loss_prev; d.w0 = w0; d.w1 = w1; d.inv_norm_global = inv_norm;
+    d.timeout_cycles = exchange_timeout_cycles();
     return d;
 }
 
@@ -199,7 +207,8 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
         if (!bbox) return fail(POSE_EINVAL, "sbp_fused: the exchange needs bbox (back-projected rows are what is exchanged)");
         if (exchange->world < 1 || exchange->world > POSE_MAX_PEERS || exchange->rank < 0 || exchange->rank >= exchange->world ||
             exchange->batch_local != N || exchange->num_keypoints != K || !exchange->ids_local ||
-            exchange->row_stride != (3 * K + 1 + 3) / 4 * 4 || exchange->row_stride > pose::kMaxRowStride)
+            exchange->row_stride != (3 * K + 1 + 3) / 4 * 4 || exchange->row_stride > pose::kMaxRowStride ||
+            exchange->defer < 0 || exchange->defer > 1 || (exchange->defer && !exchange->loss_prev))
             return fail(POSE_EINVAL, "sbp_fused: bad exchange descriptor");
     }
     if (bbox && (!(flags & POSE_F_DECODE) || input_h <= 0 || input_w <= 0)) return fail(POSE_EINVAL, "sbp_fused: back-projection needs POSE_F_DECODE and the input size");
@@ -218,6 +227,12 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
     P.gpos = (float)(2.0 * (double)lambda_pos * inv_norm);
     P.gneg = (float)(2.0 * (double)lambda_neg * inv_norm);
     P.n_maps = (long long)N * K; P.H = H; P.W = W; P.HW = H * W; P.divW = make_div(W);
+    if (exchange && exchange->defer) {           // in-band mode: the fused kernel publishes the previous step and opens this one
+        if (N == 0) return fail(POSE_EINVAL, "sbp_fused: the in-band exchange needs a non-empty shard");
+        P.xpub.world = exchange->world; P.xpub.rank = exchange->rank;
+        P.xpub.off_ctrl = exchange->off_ctrl; P.xpub.off_flags = exchange->off_flags;
+        for (int r = 0; r < exchange->world; ++r) P.xpub.peer[r] = reinterpret_cast<unsigned char*>(exchange->peer_base[r]);
+    }
 
     int grid = 0;
     if (N > 0) {
@@ -240,7 +255,7 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
     E.joints = joints; E.bbox = bbox; E.packed = packed_out; E.N = bbox ? N : 0; E.K = K; E.in_h = (double)input_h; E.in_w = (double)input_w;
     const unsigned bp_ctas = bbox ? (unsigned)(((long long)N * 32 + 255) / 256) : 0u;
     if (exchange) {
-        launch_pdl(pose::sbp_epilogue_p2p_kernel, bp_ctas + 1u, 256u, st, E, to_dev(*exchange));
+        launch_pdl(pose::sbp_epilogue_p2p_kernel, bp_ctas + 1u, 256u, st, E, to_dev(*exchange, (double)lambda_pos, (double)lambda_neg, inv_norm));
         return check_launch("sbp_epilogue_p2p");
     }
     launch_pdl(pose::sbp_epilogue_kernel, bp_ctas + 1u, 256u, st, E);
@@ -270,10 +285,9 @@ namespace {
 int exchange_wait(const pose_exchange_t* x, int mode, double w0, double w1, double inv_norm, float* loss_out, pose_stream_t stream) {
     if (!x || !loss_out || x->world < 1 || x->world > POSE_MAX_PEERS || x->rank < 0 || x->rank >= x->world || x->defer < 0 || x->defer > 1)
         return fail(POSE_EINVAL, "exchange_finish: bad argument");
-    // ~2 s at 2 GHz: a peer that never signals must not hang this GPU (POSE_B200_EXCHANGE_TIMEOUT_CYCLES overrides; diagnostics)
-    long long timeout = 4000000000ll;
-    if (const char* e = getenv("POSE_B200_EXCHANGE_TIMEOUT_CYCLES")) timeout = atoll(e);
-    launch_pdl(pose::exchange_wait_reduce_kernel, 1u, 256u, (cudaStream_t)stream, to_dev(*x), x->defer, mode, w0, w1, inv_norm, loss_out, timeout);
+    if ((mode == 0) == (x->defer == 1)) return POSE_OK;      // in-band mode has no per-step finish; lock-step mode has nothing to flush
+    launch_pdl(pose::exchange_wait_reduce_kernel, 1u, 256u, (cudaStream_t)stream, to_dev(*x), mode, w0, w1, inv_norm, loss_out,
+               exchange_timeout_cycles());
     return check_launch("exchange_wait_reduce");
 }
 }  // namespace

@@ -142,4 +142,46 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- multi-GPU exchange: control block and flags
+constexpr int kMaxPeers = 16;
+constexpr int kExchangeSlots = 4;
+
+struct ExchangeCtrl {
+    unsigned long long step;       // newest step whose flag this rank has published (= completed epilogues made visible)
+    unsigned int ticket;           // (unused, kept for layout stability)
+    unsigned int error;            // set when a wait timed out (a peer never signalled)
+    unsigned long long launched;   // in-band mode: fused kernels started so far (= index of the step being produced)
+};
+
+// what a producer kernel needs to publish "all my stores of step n have landed on every rank"
+struct ExchangePub {
+    int world, rank;               // world == 0: no exchange
+    unsigned long long off_ctrl, off_flags;
+    unsigned char* peer[kMaxPeers];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// In-band (deferred) mode, executed by ONE thread at the start of the fused kernel of step n+1: the epilogue grid of
+// step n finished before this grid started (stream order), so all of its peer stores are performed -- publish flag n on
+// every rank with a system-scope release store, then open step n+1.
+__device__ __forceinline__ void exchange_open_step(const ExchangePub& X) {
+    ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
+    const unsigned long long n = ctrl->launched;
+    if (n > 0 && ctrl->step < n) {
+        for (int r = 0; r < X.world; ++r)
+            st_release_sys(reinterpret_cast<unsigned long long*>(X.peer[r] + X.off_flags) + X.rank, n);
+        ctrl->step = n;
+    }
+    ctrl->launched = n + 1;
+}
+
 }  // namespace pose

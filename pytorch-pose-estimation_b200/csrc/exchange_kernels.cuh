@@ -13,8 +13,6 @@
 
 namespace pose {
 
-constexpr int kMaxPeers = 16;
-constexpr int kExchangeSlots = 4;
 
 constexpr int kMaxRowStride = 256;                 // floats per exchanged row (3K+1 padded to a multiple of 4): K <= 85
 
@@ -25,22 +23,11 @@ struct ExchangeDev {
     unsigned long long off_ctrl, off_flags, off_rows[kExchangeSlots], off_nums[kExchangeSlots], off_ids[kExchangeSlots];
     const long long* ids_local;                     // [B][2]
     unsigned char* mc;                              // multicast (NVLS) alias of the same buffer on ALL ranks, or nullptr
+    int defer;                                      // 1: in-band mode (flags published by the next fused kernel, waits in the epilogue)
+    float* loss_prev;                               // in-band mode: global loss of the previous step, written by the epilogue
+    double w0, w1, inv_norm_global;                 // loss weights / normalisation for that reduction
+    long long timeout_cycles;
 };
-
-struct ExchangeCtrl {
-    unsigned long long step;                        // last completed step (advanced by the wait kernel)
-    unsigned int ticket;                            // CTAs of the running epilogue that have finished their peer stores
-    unsigned int error;                             // set when a wait timed out (a peer never signalled)
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // one 16-byte store replicated by the NVSwitch into every rank's copy of the buffer (multimem = NVLS multicast object)
 __device__ __forceinline__ void multimem_st_v4(void* mc_addr, float4 v) {
@@ -58,7 +45,9 @@ __device__ __forceinline__ void store_all(const ExchangeDev& X, unsigned long lo
 __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams P, ExchangeDev X) {
     pdl_wait();
     ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
-    const unsigned long long step = ctrl->step + 1;            // constant while this grid runs
+    // constant while this grid runs: lock-step mode counts completed steps, in-band mode reads the step the fused
+    // kernel of this call opened
+    const unsigned long long step = X.defer ? ctrl->launched : ctrl->step + 1;
     const int par = (int)(step % kExchangeSlots);
     const int stride = 3 * P.K + 1;
 
@@ -73,6 +62,22 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
             reinterpret_cast<double*>(&v)[0] = nums[0];
             reinterpret_cast<double*>(&v)[1] = nums[1];
             store_all(X, X.off_nums[par] + 16ull * X.rank, v);
+        }
+        if (X.defer && step >= 2) {
+            // in-band completion of the PREVIOUS step: every rank published flag step-1 when its fused kernel of this
+            // step started (~one kernel duration ago), so this wait normally falls straight through
+            const unsigned long long need = step - 1;
+            if ((int)threadIdx.x < X.world) {
+                const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.off_flags) + threadIdx.x;
+                const long long t0 = clock64();
+                while (ld_acquire_sys(flag) < need) {
+                    if (clock64() - t0 > X.timeout_cycles) { atomicExch(&ctrl->error, 1u + threadIdx.x); break; }
+                    __nanosleep(64);
+                }
+            }
+            __syncthreads();
+            const double* prev = reinterpret_cast<const double*>(X.peer[X.rank] + X.off_nums[need % kExchangeSlots]);
+            reduce_pairs_cta(prev, X.world, 2, X.w0, X.w1, X.inv_norm_global, X.loss_prev, nullptr);
         }
     } else {
         // One warp per sample.  The sample's row (K x (x_img, y_img, flag) + score, zero-padded to a 16-byte multiple) is
@@ -129,17 +134,20 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
     // stream, and that grid -- exchange_wait_reduce_kernel -- publishes this rank's flag before it waits for the others.
 }
 
-// One CTA per rank and step.  mode 0 (finish): publish this rank's flag for step s = ctrl.step+1 (the epilogue grid
-// has completed -- griddepcontrol.wait returns only after its memory operations, peer stores included, are performed --
-// so a system-scope release store suffices), wait for every rank's flag >= s - defer, reduce the numerators of step
-// s - defer in rank order, advance the step counter.  mode 1 (flush, defer > 0 only): wait for and reduce step ctrl.step.
-__global__ void __launch_bounds__(256) exchange_wait_reduce_kernel(ExchangeDev X, int defer, int mode, double w0, double w1,
+// One CTA per rank.  mode 0 = finish of the lock-step mode: publish this rank's flag for step s = ctrl.step+1 (the
+// epilogue grid has completed -- griddepcontrol.wait returns only after its memory operations, peer stores included,
+// are performed -- so a system-scope release store suffices), wait for every rank's flag >= s, reduce the numerators
+// of step s in rank order, advance the step counter.  mode 1 = flush of the in-band mode: same for the newest produced
+// step (ctrl.launched), whose flag would otherwise only be published by the next fused kernel.
+__global__ void __launch_bounds__(256) exchange_wait_reduce_kernel(ExchangeDev X, int mode, double w0, double w1,
                                                                    double inv_norm, float* __restrict__ loss_out, long long timeout_cycles) {
     pdl_wait();
     ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
-    const unsigned long long step = ctrl->step + (mode == 0 ? 1 : 0);
-    const unsigned long long need = mode == 0 ? step - (unsigned long long)min((unsigned long long)defer, step) : step;
-    if (mode == 0 && (int)threadIdx.x < X.world)
+    // mode 0: lock-step finish of step ctrl.step+1.  mode 1: flush of the in-band mode -- the newest produced step is
+    // ctrl.launched; publish its flag (its epilogue grid has completed), wait for everybody's, reduce it.
+    const unsigned long long step = mode == 0 ? ctrl->step + 1 : ctrl->launched;
+    const unsigned long long need = step;
+    if ((int)threadIdx.x < X.world && (mode == 0 || ctrl->step < step))
         st_release_sys(reinterpret_cast<unsigned long long*>(X.peer[threadIdx.x] + X.off_flags) + X.rank, step);
     if (need > 0 && (int)threadIdx.x < X.world) {
         const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.off_flags) + threadIdx.x;
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(256) exchange_wait_reduce_kernel(ExchangeDev X
         reduce_pairs_cta(nums, X.world, 2, w0, w1, inv_norm, loss_out, nullptr);
         __syncthreads();
     }
-    if (mode == 0 && threadIdx.x == 0) ctrl->step = step;
+    if (threadIdx.x == 0) ctrl->step = step;
 }
 
 }  // namespace pose

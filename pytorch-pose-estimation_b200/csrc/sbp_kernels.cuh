@@ -152,6 +152,7 @@ struct SbpFusedParams {
     float thr, scale;
     float gpos, gneg;            // 2*lambda*inv_norm
     long long n_maps; int H, W, HW; FastDiv divW;
+    ExchangePub xpub;            // multi-GPU in-band exchange: block 0 publishes the previous step's flag (world == 0: off)
 };
 
 constexpr int TGT_DENSE = 1;
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel
     extern __shared__ float lut_s[];
     __shared__ double red[kSbpWarps][2];
     pdl_launch_dependents();      // the epilogue grid may be scheduled as our CTAs retire; it waits for our completion itself
+    if (P.xpub.world > 0 && blockIdx.x == 0 && threadIdx.x == 0) exchange_open_step(P.xpub);
     if (TGT == TGT_RENDER) {
         for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
         __syncthreads();

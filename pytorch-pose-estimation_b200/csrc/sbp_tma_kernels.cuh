@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red[kTmaWarps][2];
     pdl_launch_dependents();
+    if (P.xpub.world > 0 && blockIdx.x == 0 && threadIdx.x == 0) exchange_open_step(P.xpub);
 
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;

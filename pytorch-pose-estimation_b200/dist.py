@@ -125,9 +125,10 @@ class PeerExchange:
     4 steps; `self.steps` (host) mirrors the device step counter so the views of the completed step can be handed out
     without a synchronisation -- call `advance(n)` after replaying a captured step n times.
 
-    `defer=1`: `finish()` of step s completes step s-1 (its loss / rows), so ranks need not run in lock-step and
-    per-step jitter does not add up across GPUs; `flush()` completes the last step.  `defer=0`: `finish()` completes
-    the step it belongs to.
+    `defer=0` (lock-step): `finish()` launches a one-CTA kernel that publishes this rank's step, waits for everybody's
+    and reduces the global loss of that step.  `defer=1` (in-band): no extra launch per step -- the NEXT step's fused
+    kernel publishes a step and the next step's epilogue waits for / reduces it, so `finish()` of step s returns the loss
+    of step s-1 (written by that epilogue), ranks may drift up to two steps apart, and `flush()` completes the last step.
     """
 
     def __init__(self, batch_local, num_keypoints, device, image_ids, category_ids, group=None, multicast=None, defer=0):
@@ -160,9 +161,10 @@ class PeerExchange:
         mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
         self.multicast = bool(multicast and mc)
         d.multicast_base = mc if self.multicast else None
-        self.desc = d
         self.steps = 0
         self.loss = torch.zeros((), dtype=torch.float32, device=device)
+        d.loss_prev = self.loss.data_ptr()
+        self.desc = d
         torch.cuda.synchronize(device)
         dist.barrier(group)            # every rank's buffer is zeroed before anyone's first peer store
 
@@ -184,7 +186,7 @@ class PeerExchange:
     def finish(self, global_batch, lambda_pos=5.0, lambda_neg=1.0):
         """Publish this rank's step, wait for every rank's rows of step (current - defer) and reduce its global loss
         (stream-ordered, no host sync)."""
-        loss = self._wait("pose_exchange_finish", global_batch, lambda_pos, lambda_neg)
+        loss = self._wait("pose_exchange_finish", global_batch, lambda_pos, lambda_neg) if self.defer == 0 else self.loss
         self.steps += 1
         return loss
 
