@@ -155,15 +155,20 @@ __global__ void __launch_bounds__(kSpmThreads) spm_patch_kernel(SpmRenderParams 
     __syncthreads();
     pdl_wait();                                                         // the zero fill of the same planes comes first
     const int side = 2 * P.half + 1;
-    const int items = P.K * side * side;
     const long long plane = (long long)P.R * P.R;
     float* out = P.target + (long long)img * (1 + 2 * P.K) * plane;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int j = it / (side * side), pi = it - j * side * side;
+    constexpr int kCov = 8;                                             // covering persons kept in registers per pixel
+    // one thread per pixel of this person's box; the set of persons covering a pixel is the same for every joint, so it
+    // is found once and the joints are then walked with a handful of instructions each
+    const int npix = side * side;
+    const int groups = max(1, (int)blockDim.x / npix);                  // joints are split over `groups` threads per pixel
+    for (int t = threadIdx.x; t < npix * groups; t += blockDim.x) {
+        const int g = t / npix, pi = t - g * npix;
         const int dy = pi / side, dx = pi - dy * side;
         const int row = cy - P.half + dy, col = cx - P.half + dx;
         if (row < 0 || row >= P.R || col < 0 || col >= P.R) continue;
-        float ax = 0.0f, ay = 0.0f;
+        int cov[kCov];
+        int ncov = 0;
         bool mine = true;
         for (int q = 0; q < np; ++q) {
             int qx, qy;
@@ -172,18 +177,38 @@ __global__ void __launch_bounds__(kSpmThreads) spm_patch_kernel(SpmRenderParams 
             if (qx <= 0 && qy <= 0) continue;
             if (row < qy - P.half || row > qy + P.half || col < qx - P.half || col > qx + P.half) continue;
             if (q < p) { mine = false; break; }                         // an earlier person's CTA owns this pixel
-            const long long* jp = P.joints + (((long long)img * P.Pmax + q) * P.K + j) * 2;
-            const long long jx = __ldg(jp), jy = __ldg(jp + 1);
-            if (jx <= 0 && jy <= 0) continue;
-            const long long ddx = jx - (long long)col, ddy = jy - (long long)row;
-            const double qx_ = (div_n && ddx >= -P.R && ddx <= P.R) ? div_s[(int)ddx + P.R] : (double)ddx / P.z;
-            const double qy_ = (div_n && ddy >= -P.R && ddy <= P.R) ? div_s[(int)ddy + P.R] : (double)ddy / P.z;
-            ax = (float)((double)ax + qx_);
-            ay = (float)((double)ay + qy_);
+            if (ncov < kCov) cov[ncov] = q;
+            ++ncov;
         }
         if (!mine) continue;
-        out[(1 + 2 * j) * plane + (long long)row * P.R + col] = ax;
-        out[(2 + 2 * j) * plane + (long long)row * P.R + col] = ay;
+        const long long* jbase = P.joints + (long long)img * P.Pmax * P.K * 2;
+        float* o = out + (long long)row * P.R + col;
+        for (int j = g; j < P.K; j += groups) {
+            float ax = 0.0f, ay = 0.0f;
+            auto add = [&](int q) {
+                const longlong2 jv = __ldg(reinterpret_cast<const longlong2*>(jbase + ((long long)q * P.K + j) * 2));
+                if (jv.x <= 0 && jv.y <= 0) return;
+                const long long ddx = jv.x - (long long)col, ddy = jv.y - (long long)row;
+                const double qx_ = (div_n && ddx >= -P.R && ddx <= P.R) ? div_s[(int)ddx + P.R] : (double)ddx / P.z;
+                const double qy_ = (div_n && ddy >= -P.R && ddy <= P.R) ? div_s[(int)ddy + P.R] : (double)ddy / P.z;
+                ax = (float)((double)ax + qx_);
+                ay = (float)((double)ay + qy_);
+            };
+            if (ncov <= kCov) {
+#pragma unroll
+                for (int c = 0; c < kCov; ++c)
+                    if (c < ncov) add(cov[c]);
+            } else {                                                    // crowded pixel: re-scan the persons in order
+                for (int q = p; q < np; ++q) {
+                    const int qx = (int)__ldg(cen + 2 * q), qy = (int)__ldg(cen + 2 * q + 1);
+                    if (qx <= 0 && qy <= 0) continue;
+                    if (row < qy - P.half || row > qy + P.half || col < qx - P.half || col > qx + P.half) continue;
+                    add(q);
+                }
+            }
+            o[(1 + 2 * j) * plane] = ax;
+            o[(2 + 2 * j) * plane] = ay;
+        }
     }
 }
 

@@ -8,17 +8,12 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import pose_b200 as pb  # noqa: E402
-from oracle import cases  # noqa: E402  (input generator only)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _inputs import spm_inputs  # noqa: E402
 
 dev = torch.device("cuda", 0)
-n = 128
-people, tgt, lg, meta = cases.spm_case("coco", 16, seed=99)
-c, j, cnt = cases.pack_people(people)
-rep = n // 16
-c = torch.from_numpy(c).repeat(rep, 1, 1).to(dev)
-j = torch.from_numpy(j).repeat(rep, 1, 1, 1).to(dev)
-cnt = torch.from_numpy(cnt).repeat(rep).to(dev)
-x = lg.repeat(rep, 1, 1, 1).to(dev)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+c, j, cnt, _t, x = spm_inputs(n, dev)
 for _ in range(3):
     t = pb.spm_render_batch(c, j, cnt, 128, 1)
     pb.spm_loss_fused(x, t)
