@@ -31,7 +31,7 @@ extern "C" {
 #define POSE_KP_F32 0
 #define POSE_KP_F64 1
 
-/* flags for pose_sbp_fused */
+/* flags for pose_sbp_fused / pose_spm_fused */
 #define POSE_F_GRAD 1u          /* write dlogits                                   */
 #define POSE_F_TARGET_OUT 2u    /* also materialise the rendered target (render mode only) */
 #define POSE_F_DECODE 4u        /* also decode joints from sigmoid(logits) in the same pass */
@@ -165,6 +165,19 @@ int pose_spm_loss(const float* logits, const float* target, float* dlogits,
                   float* loss_out, double* loss_num_out, int N, int K, int R,
                   float lambda_root, float lambda_disp, double inv_norm, int write_grad,
                   void* workspace, unsigned long long workspace_bytes, pose_stream_t stream);
+
+/* ---- SPM render + loss (+grad) in one pass -- SPMHeatmapGenerator/MaskGenerator/DisplacementGenerator
+ *      utils/spm_utils.py:16-95 evaluated in registers and fed into SPMLoss.forward models/loss/spm_loss.py:23-105
+ *      (+ autograd backward): the target never touches HBM.  Persons as for pose_spm_render (Pmax <= 64);
+ *      logits/dlogits/target_out [N][1+2K][R][R].  flags: POSE_F_GRAD (write dlogits), POSE_F_TARGET_OUT (also
+ *      materialise the rendered target, bit-identical to pose_spm_render).  loss = (lambda_root*S_root +
+ *      lambda_disp*S_disp)*inv_norm, inv_norm = 1/B_global; loss_num_out [2] fp64 = (S_root, S_disp). */
+unsigned long long pose_spm_fused_workspace_bytes(void);
+int pose_spm_fused(const float* logits, const long long* centers, const long long* joints, const int* counts,
+                   float* dlogits, float* target_out, float* loss_out, double* loss_num_out,
+                   int N, int Pmax, int K, int R, double sigma, const float* lut, int lut_n,
+                   float lambda_root, float lambda_disp, double inv_norm, unsigned flags,
+                   void* workspace, unsigned long long workspace_bytes, pose_stream_t stream);
 
 /* ---- SPM decode -- nms_spm :98-161, get_spm_keypoints :164-200, DecodeSPM.forward :225-250.
  * x [N][1+2K][R][R]; roots [N][Pmax][3], kps [N][Pmax][K][3], counts [N] (roots found, capped at

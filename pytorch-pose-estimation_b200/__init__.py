@@ -18,7 +18,7 @@ from .sbp_loss import SBPLoss, sbp_fused  # noqa: F401
 from .sbp_pis_utils import SBPmAPPIS  # noqa: F401
 from .sbp_utils import (DecodeSBP, SBPHeatmapGenerator, SBPmAPCOCO, backproject_packed, backproject_rows, decode_batch,  # noqa: F401
                         nms_sbp, packed_to_results)
-from .spm_loss import SPMLoss, spm_loss_fused  # noqa: F401
+from .spm_loss import SPMLoss, spm_fused, spm_loss_fused  # noqa: F401
 from .spm_utils import (DecodeSPM, SPMDisplacementGenerator, SPMHeatmapGenerator, SPMMaskGenerator, SPMmAPCOCO,  # noqa: F401
                         get_spm_keypoints, nms_spm, spm_decode_batch, spm_render_batch)
 

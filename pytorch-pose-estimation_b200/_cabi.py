@@ -7,7 +7,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpose_b200.so")
+# POSE_B200_LIB points at another build of the SAME library (tools/tune_*.py compile variants with different -D knobs)
+LIB_PATH = os.environ.get("POSE_B200_LIB") or os.path.join(_HERE, "libpose_b200.so")
 
 KP_F32, KP_F64 = 0, 1
 F_GRAD, F_TARGET_OUT, F_DECODE, F_TMA = 1, 2, 4, 8
@@ -36,6 +37,8 @@ SIGNATURES = {
     "pose_spm_render": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp]),
     "pose_spm_loss_workspace_bytes": (_ull, []),
     "pose_spm_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _d, _i, _vp, _ull, _vp]),
+    "pose_spm_fused_workspace_bytes": (_ull, []),
+    "pose_spm_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _f, _f, _d, _u, _vp, _ull, _vp]),
     "pose_spm_decode_workspace_bytes": (_ull, [_i, _i]),
     "pose_spm_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _d, _i, _f, _vp, _ull, _vp]),
     "pose_spm_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp]),

@@ -369,6 +369,29 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
     P.z = std::sqrt((double)((long long)R * R + (long long)R * R));
     P.N = N; P.Pmax = Pmax; P.K = K; P.R = R;
     const int quads = R * R / 4;
+    if (Pmax <= pose::kSpmFusedMaxPersons && !getenv("POSE_B200_SPM_RENDER_TWO_PASS")) {
+        // single pass: the render-only form of the fused kernel (linear write stream, covered pixels filled in by the same pass)
+        pose::SpmFusedParams F;
+        memset(&F, 0, sizeof(F));
+        F.target_out = target; F.centers = centers; F.joints = joints; F.counts = counts; F.lut = lut; F.lut_n = lut_n;
+        F.three_sigma = P.three_sigma; F.half = P.half; F.z = P.z;
+        F.N = N; F.Pmax = Pmax; F.K = K; F.R = R; F.quads = quads; F.div_qpr = make_div(R / 4);
+        F.wpr = (R / 4 + 31) / 32;
+        F.div_n = R <= 1024 ? 2 * R + 1 : 0;
+        const size_t fsmem = pose::spm_fused_smem_bytes(F.div_n, R, K, F.wpr, lut_n);
+        if (fsmem <= 200 * 1024) {
+            const long long funits = (long long)N * (1 + 2 * K) * ((quads + pose::kSpmFusedChunk - 1) / pose::kSpmFusedChunk);
+#define POSE_SPMR(RG)                                                                                                          \
+    {                                                                                                                          \
+        if (fsmem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<false, false, true, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem); \
+        const int fgrid = persistent_grid(pose::spm_fused_kernel<false, false, true, RG>, pose::kSpmThreads, fsmem, funits);   \
+        pose::spm_fused_kernel<false, false, true, RG><<<fgrid, pose::kSpmThreads, fsmem, (cudaStream_t)stream>>>(F);          \
+    }
+            if (R % 128 == 0) POSE_SPMR(true) else POSE_SPMR(false)
+#undef POSE_SPMR
+            return check_launch("spm_render(single pass)");
+        }
+    }
     const size_t smem = (size_t)lut_n * lut_n * sizeof(float);
     const long long units = (long long)N * (1 + 2 * K) * ((quads + pose::kSpmRenderChunk - 1) / pose::kSpmRenderChunk);
     const int grid = persistent_grid(pose::spm_fill_kernel, pose::kSpmThreads, smem, units);
@@ -426,6 +449,61 @@ int pose_spm_loss(const float* logits, const float* target, float* dlogits, floa
     return check_launch("loss_reduce");
 }
 
+unsigned long long pose_spm_fused_workspace_bytes(void) { return (unsigned long long)pose::kMaxPartialBlocks * 2 * sizeof(double); }
+
+int pose_spm_fused(const float* logits, const long long* centers, const long long* joints, const int* counts, float* dlogits,
+                   float* target_out, float* loss_out, double* loss_num_out, int N, int Pmax, int K, int R, double sigma,
+                   const float* lut, int lut_n, float lambda_root, float lambda_disp, double inv_norm, unsigned flags,
+                   void* workspace, unsigned long long workspace_bytes, pose_stream_t stream) {
+    if (N < 0 || Pmax < 0 || K <= 0 || R <= 0 || R % 4 != 0 || R > 2048) return fail(POSE_EINVAL, "spm_fused: bad shape (R must be a multiple of 4, <= 2048)");
+    if (Pmax > pose::kSpmFusedMaxPersons) return fail(POSE_EINVAL, "spm_fused: Pmax=%d > %d persons per image (use pose_spm_render + pose_spm_loss)", Pmax, pose::kSpmFusedMaxPersons);
+    if (flags & ~(POSE_F_GRAD | POSE_F_TARGET_OUT)) return fail(POSE_EINVAL, "spm_fused: unsupported flags 0x%x", flags);
+    const bool grad = flags & POSE_F_GRAD, wtgt = flags & POSE_F_TARGET_OUT;
+    if (!loss_out && !loss_num_out) return fail(POSE_EINVAL, "spm_fused: no loss output");
+    if (!workspace || workspace_bytes < pose_spm_fused_workspace_bytes() || !aligned16(workspace)) return fail(POSE_EWORKSPACE, "spm_fused: workspace too small / unaligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = 0;
+    if (N > 0) {
+        if (!logits || !counts || !lut || lut_n <= 0 || lut_n > 64 || !(sigma > 0.0) || (Pmax > 0 && (!centers || !joints)) ||
+            (grad && !dlogits) || (wtgt && !target_out))
+            return fail(POSE_EINVAL, "spm_fused: bad argument");
+        if (!aligned16(logits) || (grad && !aligned16(dlogits)) || (wtgt && !aligned16(target_out))) return fail(POSE_EALIGN, "spm_fused: tensors must be 16-byte aligned");
+        if ((grad && dlogits == logits) || (wtgt && target_out == logits)) return fail(POSE_EINVAL, "spm_fused: outputs must not alias logits");
+        pose::SpmFusedParams P;
+        memset(&P, 0, sizeof(P));
+        P.logits = logits; P.dlogits = dlogits; P.target_out = target_out;
+        P.centers = centers; P.joints = joints; P.counts = counts; P.lut = lut; P.lut_n = lut_n;
+        P.three_sigma = 3 * sigma; P.half = (int)((6 * sigma + 2) / 2);
+        P.z = std::sqrt((double)((long long)R * R + (long long)R * R));
+        P.partials = reinterpret_cast<double*>(workspace);
+        P.N = N; P.Pmax = Pmax; P.K = K; P.R = R; P.quads = R * R / 4; P.div_qpr = make_div(R / 4);
+        P.wpr = (R / 4 + 31) / 32;
+        P.div_n = R <= 1024 ? 2 * R + 1 : 0;
+        P.groot = (float)(2.0 * (double)lambda_root * inv_norm);
+        P.gdisp = (float)((double)lambda_disp * inv_norm);
+        const size_t smem = pose::spm_fused_smem_bytes(P.div_n, R, K, P.wpr, lut_n);
+        if (smem > 200 * 1024) return fail(POSE_EINVAL, "spm_fused: R=%d K=%d needs %zu bytes of shared memory (use pose_spm_render + pose_spm_loss)", R, K, smem);
+        const long long units = (long long)N * (1 + 2 * K) * ((P.quads + pose::kSpmFusedChunk - 1) / pose::kSpmFusedChunk);
+#define POSE_SPMF2(G, T, RG)                                                                                                  \
+    {                                                                                                                          \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<true, G, T, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        grid = persistent_grid(pose::spm_fused_kernel<true, G, T, RG>, pose::kSpmThreads, smem, units);                        \
+        pose::spm_fused_kernel<true, G, T, RG><<<grid, pose::kSpmThreads, smem, st>>>(P);                                      \
+    }
+#define POSE_SPMF(G, T)                                                                                                        \
+    {                                                                                                                          \
+        if (R % 128 == 0) POSE_SPMF2(G, T, true) else POSE_SPMF2(G, T, false)                                                  \
+    }
+        if (grad && wtgt) POSE_SPMF(true, true) else if (grad) POSE_SPMF(true, false) else if (wtgt) POSE_SPMF(false, true) else POSE_SPMF(false, false)
+#undef POSE_SPMF2
+#undef POSE_SPMF
+        if (int rc = check_launch("spm_fused")) return rc;
+    }
+    launch_pdl(pose::loss_reduce_kernel, 1u, 256u, st, (const double*)workspace, grid, 2ll, (double)lambda_root, (double)lambda_disp,
+               inv_norm, loss_out, loss_num_out);
+    return check_launch("loss_reduce");
+}
+
 unsigned long long pose_spm_decode_workspace_bytes(int N, int R) { (void)N; (void)R; return 0ull; }
 
 int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* counts_total, int N, int Pmax, int K, int R,
@@ -448,6 +526,12 @@ int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* 
     P.thr = conf_threshold; P.dist_thr = dist_threshold; P.apply_act = apply_act;
     P.zf = (float)std::sqrt((double)((long long)R * R + (long long)R * R));
     P.input_size = input_size;
+    {   // nms_spm keeps candidates with sqrt(dx^2+dy^2) > dist_thr (fp64 sqrt of an integer): the same predicate as an integer bound
+        long long s = (long long)std::floor(dist_threshold * dist_threshold);
+        while (s > 0 && std::sqrt((double)(s - 1)) > dist_threshold) --s;
+        while (!(std::sqrt((double)s) > dist_threshold)) ++s;
+        P.s_min = s;
+    }
     pose::spm_decode_kernel<<<N, pose::kSpmThreads, smem, (cudaStream_t)stream>>>(P);
     return check_launch("spm_decode");
 }

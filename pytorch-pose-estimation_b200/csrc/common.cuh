@@ -33,6 +33,10 @@ __device__ __forceinline__ void stg_stream(float* p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// pull the line holding p into L2 ahead of use (no register, no scoreboard): turns a DRAM miss into an L2 hit for
+// kernels whose per-unit compute phase is long enough to expose the load latency
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---------------------------------------------------------------- programmatic dependent launch (sm_90+)
 // Primary grid: allow the next grid in the stream to be scheduled early.  Secondary grid: block until every
 // prerequisite grid has completed and flushed its memory.  Both are no-ops for launches without the PDL attribute.

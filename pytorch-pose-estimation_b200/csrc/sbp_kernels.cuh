@@ -16,6 +16,14 @@ namespace pose {
 #ifndef POSE_FUSED_MINB
 #define POSE_FUSED_MINB 3       // resident CTAs per SM the fused kernel is compiled for (register cap 80)
 #endif
+// The read-only render variants (validation: loss and/or decode from keypoints, no dlogits) have no store stream to carry half of the traffic:
+// they need more loads in flight per SM to hide the same latency, so they get their own knobs.
+#ifndef POSE_FUSED_U_NG
+#define POSE_FUSED_U_NG 8
+#endif
+#ifndef POSE_FUSED_MINB_NG
+#define POSE_FUSED_MINB_NG 4    // register cap 64
+#endif
 constexpr int kSbpThreads = 256;               // 8 warps per CTA
 constexpr int kSbpWarps = kSbpThreads / 32;
 constexpr int kMaxPartialBlocks = 148 * 16;    // upper bound on the persistent grid (workspace sizing)
@@ -218,7 +226,7 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
 }
 
 template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
-__global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel(SbpFusedParams P) {
+__global__ void __launch_bounds__(kSbpThreads, (GRAD || WTGT || TGT != 2) ? POSE_FUSED_MINB : POSE_FUSED_MINB_NG) sbp_fused_kernel(SbpFusedParams P) {
     extern __shared__ float lut_s[];
     __shared__ double red[kSbpWarps][2];
     pdl_launch_dependents();      // the epilogue grid may be scheduled as our CTAs retire; it waits for our completion itself
@@ -232,8 +240,13 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel
     const long long warp0 = (long long)blockIdx.x * kSbpWarps + wid;
     const long long nwarps = (long long)gridDim.x * kSbpWarps;
     const int nvec = P.HW / V;
-    constexpr int U = (V == 4) ? POSE_FUSED_U : 8;
+    constexpr int U = (V == 4) ? ((GRAD || WTGT || TGT != TGT_RENDER) ? POSE_FUSED_U : POSE_FUSED_U_NG) : 8;
     double dpos = 0.0, dneg = 0.0;
+
+    // the keypoint of the NEXT map is fetched while the current map streams, so its latency is off the per-map
+    // dependency chain (kp -> patch geometry -> first batch of loads)
+    double kx = -1.0, ky = -1.0;
+    if (TGT == TGT_RENDER && warp0 < P.n_maps) load_kp(P.kp, P.kp_f64, warp0, kx, ky);
 
     for (long long map = warp0; map < P.n_maps; map += nwarps) {
         const float* lg = P.logits + map * P.HW;
@@ -242,9 +255,8 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_FUSED_MINB) sbp_fused_kernel
         float* to = WTGT ? P.target_out + map * P.HW : nullptr;
         Patch pt;
         if (TGT == TGT_RENDER) {
-            double x, y;
-            load_kp(P.kp, P.kp_f64, map, x, y);
-            pt = make_patch(x, y, P.H, P.W, P.three_sigma, P.lut_n);
+            pt = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
+            if (map + nwarps < P.n_maps) load_kp(P.kp, P.kp_f64, map + nwarps, kx, ky);
         }
         float apos = 0.0f, aneg = 0.0f, arem = 0.0f;
         float best = -INFINITY;

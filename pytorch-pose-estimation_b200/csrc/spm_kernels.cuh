@@ -303,6 +303,288 @@ __global__ void __launch_bounds__(kSpmThreads) spm_loss_kernel(SpmLossParams P) 
     }
 }
 
+// ---------------------------------------------------------------- fused render + loss (+ grad)
+// SPMHeatmapGenerator + SPMMaskGenerator + SPMDisplacementGenerator (utils/spm_utils.py:16-95) evaluated in registers and fed
+// straight into SPMLoss.forward (models/loss/spm_loss.py:23-105): the [N,1+2K,R,R] target is never written to or read from
+// HBM, so a training step moves 2 tensor passes (read logits, write dlogits) instead of 1 (render) + 3 (dense loss).
+//
+// Work unit = 16 KB of one channel plane, streamed linearly exactly like spm_loss_kernel; every CTA owns a CONTIGUOUS range
+// of units, so an image's persons are staged in shared memory once per image, not once per unit: centres + patch corners,
+// all body joints, a per-row bitmask of the persons touching the row and a per-row bitmask of the COVERED float4 quads
+// (quads that intersect some person's box or Gaussian patch: ~3% of an image).
+//   phase A (every lane, per quad): not covered -> target 0, mask 0: the loss term is 0 unless the logit is NaN and
+//     dlogits = 0: a handful of instructions per element, no person data touched.
+//   phase B (per warp, only if some lane's quad is covered): the covered quads' elements are re-distributed over the lanes,
+//     one PIXEL per lane (logit fetched from the owning lane by shuffle), so the expensive part -- replaying the covering
+//     persons in order, template look-ups, tanhf -- runs once per warp at up to 32 useful lanes.  (v1 ran it inside the
+//     per-quad loop, 4 elements per lane at ~3 useful lanes per warp: 436 us per 256 images, slower than render + dense loss.)
+struct SpmFusedParams {
+    const float* logits; float* dlogits; float* target_out;
+    const long long* centers;   // [N][Pmax][2]
+    const long long* joints;    // [N][Pmax][K][2]
+    const int* counts;          // [N]
+    const float* lut; int lut_n;
+    double three_sigma; int half; double z;
+    double* partials;           // [grid][2]  (S_root, S_disp)
+    int N, Pmax, K, R;
+    int quads; FastDiv div_qpr; // float4 per plane; quads per row (R/4)
+    int wpr;                    // 32-bit words of covered-quad bits per row: ceil(R/4/32)
+    int div_n;                  // 2R+1 entries of the quotient table in shared memory, or 0 (R too large: divide directly)
+    float groot, gdisp;         // 2*lambda_root*inv_norm, lambda_disp*inv_norm
+};
+
+struct __align__(16) SpmFusedPerson {
+    int cx, cy;                 // centre (box = [cx-half, cx+half] x [cy-half, cy+half])
+    int ulx, uly;               // template origin in map coordinates
+    int px0, px1, py0, py1;     // Gaussian patch window clipped to the map and to the template, [x0,x1) x [y0,y1); empty: all 0
+};
+
+#ifndef POSE_SPM_FUSED_MINB
+#define POSE_SPM_FUSED_MINB 4   // resident CTAs per SM the kernel is compiled for (register cap 64)
+#endif
+constexpr int kSpmFusedU = 4;
+constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;      // float4 per work unit (16 KB)
+constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
+
+__host__ __device__ inline size_t spm_fused_smem_bytes(int div_n, int R, int K, int wpr, int lut_n) {
+    return (size_t)div_n * 8 + (size_t)R * 8 + (size_t)kSpmFusedMaxPersons * K * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4;
+}
+
+// target of one pixel: (root value t0 = max of the covering Gaussian patches, displacement te of plane (jn, axis))
+__device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const SpmFusedPerson* __restrict__ s_p, const int2* __restrict__ s_j,
+                                                 const double* __restrict__ div_s, const float* __restrict__ lut_s, unsigned long long m,
+                                                 int row, int col, bool disp, int jn, int axis, float& t0, float& te) {
+    t0 = 0.0f;
+    te = 0.0f;
+    while (m) {
+        const int p = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const SpmFusedPerson sp = s_p[p];
+        if (row >= sp.py0 && row < sp.py1 && col >= sp.px0 && col < sp.px1)
+            t0 = fmaxf(t0, lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)]);
+        if (disp && row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
+            const int2 jv = s_j[p * P.K + jn];
+            if (!(jv.x <= 0 && jv.y <= 0)) {
+                const int dd = axis ? jv.y - row : jv.x - col;
+                const double qd = (P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z;
+                te = (float)((double)te + qd);                       // fp32(fp64(acc) + q): numpy's mixed-precision +=
+            }
+        }
+    }
+}
+
+// LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read, the target is
+// written as one linear stream with the covered pixels filled in by the same pass.
+// ROWG: R % 128 == 0, the 32 quads of a warp instruction lie in one row and are exactly one word of its covered-quad bits.
+template <bool LOSS, bool GRAD, bool WTGT, bool ROWG>
+__global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
+    // dynamic shared memory: [div_n] double quotients | [R] u64 row masks | [64*K] int2 joints | [R*wpr] u32 covered quads | template
+    extern __shared__ __align__(16) unsigned char spm_fused_smem[];
+    double* div_s = reinterpret_cast<double*>(spm_fused_smem);
+    unsigned long long* rowmask_s = reinterpret_cast<unsigned long long*>(div_s + P.div_n);
+    int2* s_j = reinterpret_cast<int2*>(rowmask_s + P.R);
+    unsigned int* covq_s = reinterpret_cast<unsigned int*>(s_j + kSpmFusedMaxPersons * P.K);
+    float* lut_s = reinterpret_cast<float*>(covq_s + P.R * P.wpr);
+    __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
+    __shared__ double red[kSpmThreads / 32][2];
+    __shared__ unsigned char s_src[kSpmThreads / 32][32];
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
+    for (int i = threadIdx.x; i < P.div_n; i += blockDim.x) div_s[i] = (double)(i - P.R) / P.z;
+
+    const int C = 1 + 2 * P.K;
+    const int upp = (P.quads + kSpmFusedChunk - 1) / kSpmFusedChunk;
+    const long long units = (long long)P.N * C * upp;
+    const long long u_begin = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
+    const float4* L4 = reinterpret_cast<const float4*>(P.logits);
+    float4* G4 = reinterpret_cast<float4*>(P.dlogits);
+    float4* T4 = reinterpret_cast<float4*>(P.target_out);
+    const int qpr = (int)P.div_qpr.d;
+    const long long total_quads = (long long)P.N * C * P.quads;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    double droot = 0.0, ddisp = 0.0;
+    int staged_img = -1;
+
+    // (image, channel, chunk) of the first unit; advanced incrementally (no 64-bit divisions in the loop)
+    long long plane = u_begin / upp;
+    int chunk = (int)(u_begin - plane * upp);
+    int img = (int)(plane / C), c = (int)(plane - (long long)img * C);
+
+    for (long long unit = u_begin; unit < u_end; ++unit) {
+        if (img != staged_img) {                                       // CTA-uniform
+            const int np = min(max(P.counts[img], 0), min(P.Pmax, kSpmFusedMaxPersons));
+            __syncthreads();
+            for (int i = threadIdx.x; i < np; i += blockDim.x) {
+                SpmFusedPerson sp;
+                const long long pi = (long long)img * P.Pmax + i;
+                sp.cx = (int)max(min(P.centers[pi * 2], 1ll << 30), -(1ll << 30));
+                sp.cy = (int)max(min(P.centers[pi * 2 + 1], 1ll << 30), -(1ll << 30));
+                sp.ulx = (int)rint(((double)sp.cx - P.three_sigma) - 1.0);
+                sp.uly = (int)rint(((double)sp.cy - P.three_sigma) - 1.0);
+                const int brx = (int)rint(((double)sp.cx + P.three_sigma) + 2.0);
+                const int bry = (int)rint(((double)sp.cy + P.three_sigma) + 2.0);
+                sp.px0 = max(0, sp.ulx); sp.px1 = min(min(brx, P.R), sp.ulx + P.lut_n);
+                sp.py0 = max(0, sp.uly); sp.py1 = min(min(bry, P.R), sp.uly + P.lut_n);
+                if (sp.px1 <= sp.px0 || sp.py1 <= sp.py0) sp.px0 = sp.px1 = sp.py0 = sp.py1 = 0;
+                s_p[i] = sp;
+            }
+            const long long* jimg = P.joints + (long long)img * P.Pmax * P.K * 2;
+            for (int i = threadIdx.x; i < np * P.K; i += blockDim.x) {
+                const longlong2 jv = __ldg(reinterpret_cast<const longlong2*>(jimg) + i);
+                s_j[i] = make_int2((int)max(min(jv.x, 1ll << 30), -(1ll << 30)), (int)max(min(jv.y, 1ll << 30), -(1ll << 30)));
+            }
+            for (int i = threadIdx.x; i < P.R; i += blockDim.x) rowmask_s[i] = 0ull;
+            for (int i = threadIdx.x; i < P.R * P.wpr; i += blockDim.x) covq_s[i] = 0u;
+            __syncthreads();
+            // one thread per (person, row of the union of its box and patch): row mask bit + covered-quad bits
+            const int span = 2 * P.half + 1 + P.lut_n;                 // upper bound on the rows of the union
+            for (int t = threadIdx.x; t < np * span; t += blockDim.x) {
+                const int p = t / span;
+                const SpmFusedPerson sp = s_p[p];
+                if (sp.cx <= 0 && sp.cy <= 0) continue;                 // skipped by all three generators
+                const bool patch = sp.px1 > sp.px0;
+                const int ylo = patch ? min(sp.cy - P.half, sp.py0) : sp.cy - P.half;
+                const int yhi = patch ? max(sp.cy + P.half, sp.py1 - 1) : sp.cy + P.half;
+                const int row = ylo + (t - p * span);
+                if (row < 0 || row >= P.R || row > yhi) continue;
+                const int xlo = max(0, patch ? min(sp.cx - P.half, sp.px0) : sp.cx - P.half);
+                const int xhi = min(P.R - 1, patch ? max(sp.cx + P.half, sp.px1 - 1) : sp.cx + P.half);
+                if (xhi < xlo) continue;
+                atomicOr(&rowmask_s[row], 1ull << p);
+                const int q0 = xlo >> 2, q1 = xhi >> 2;
+                for (int w = q0 >> 5; w <= (q1 >> 5); ++w) {
+                    const int lo = max(q0 - 32 * w, 0), hi = min(q1 - 32 * w, 31);
+                    const unsigned int bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                    atomicOr(&covq_s[row * P.wpr + w], bits);
+                }
+            }
+            __syncthreads();
+            staged_img = img;
+        }
+        const long long off = plane * P.quads;
+        const int q_lo = chunk * kSpmFusedChunk;
+        float4 pv[kSpmFusedU];
+        const float4* lsrc = L4 + off + q_lo + threadIdx.x;
+        // ROWG: quads is a multiple of the chunk, so every quad of every unit is valid (no predicates on the stream)
+#pragma unroll
+        for (int u = 0; u < kSpmFusedU; ++u)
+            if (LOSS && (ROWG || q_lo + u * kSpmThreads + (int)threadIdx.x < P.quads)) pv[u] = ldg_stream(lsrc + u * kSpmThreads);
+        if (LOSS && unit + 1 < u_end) {
+            // the next unit of this CTA is the next 16 KB in memory (planes are contiguous): pull it into L2 while this unit
+            // computes.  (Measured: 342 -> 267 us per 256 images together with the leaner phase B; holding the next unit in
+            // registers instead -- a software pipeline at 3 CTAs/SM -- was slower, 285-291 us: the kernel is bound by issue
+            // slots, not by load latency.)
+            const float4* nsrc = L4 + off + min(q_lo + kSpmFusedChunk, P.quads) + threadIdx.x;
+            const float4* lend = L4 + total_quads;
+#pragma unroll
+            for (int u = 0; u < kSpmFusedU; ++u)
+                if (nsrc + u * kSpmThreads < lend) prefetch_l2(nsrc + u * kSpmThreads);
+        }
+        const bool disp = c != 0;
+        const int jn = (c - 1) >> 1, axis = (c - 1) & 1;                 // displacement plane: joint and axis (0 = x, 1 = y)
+        float acc = 0.f;
+        unsigned cmask[kSpmFusedU];
+        float4* gdst = GRAD ? G4 + off + q_lo + threadIdx.x : nullptr;
+        float4* tdst = WTGT ? T4 + off + q_lo + threadIdx.x : nullptr;
+        // phase A.  ROWG: the warp's 32 quads are exactly one word of the covered-quad bits, and with wpr = qpr/32 the word
+        // index is simply the warp's group index inside the plane: one broadcast LDS per warp instruction, no ballot.
+        const int g0 = (q_lo >> 5) + wid;
+#pragma unroll
+        for (int u = 0; u < kSpmFusedU; ++u) {
+            bool valid = true, covered = false;
+            if (ROWG) {
+                cmask[u] = covq_s[g0 + u * (kSpmThreads / 32)];
+                covered = (cmask[u] >> lane) & 1u;
+            } else {
+                const int qu = q_lo + u * kSpmThreads + (int)threadIdx.x;
+                valid = qu < P.quads;
+                if (valid) {
+                    const int row = (int)fdiv((uint32_t)qu, P.div_qpr), cq = qu - row * qpr;
+                    covered = (covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u;
+                }
+                cmask[u] = __ballot_sync(FULL_MASK, covered);
+            }
+            if (valid && !covered) {
+                // zero target, zero mask.  sigmoid(p)*0 and tanh(p)*0 are 0 for every non-NaN p; a NaN propagates
+                if (LOSS) {
+                    const float4 v = pv[u];
+                    const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+                    if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
+                }
+                if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
+                if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
+            }
+        }
+        // phase B: one pixel of a covered quad per lane.  Deliberately NOT unrolled over u (the body is large: an unrolled copy
+        // per u made the kernel 113 KB of SASS and `no_instruction` the second largest stall).  The pixel's logit is re-read
+        // from L2 (the warp streamed it a moment ago) rather than shuffled out of pv[]: pv dies after phase A, which keeps
+        // the kernel inside 64 registers without spills.
+#pragma unroll 1
+        for (int u = 0; u < kSpmFusedU; ++u) {
+            const unsigned cm = u == 0 ? cmask[0] : (u == 1 ? cmask[1] : (u == 2 ? cmask[2] : cmask[3]));
+            if (cm == 0u) continue;                                      // warp-uniform
+            // slot k of the warp's scratch row = lane that owns the k-th covered quad
+            if ((cm >> lane) & 1u) s_src[wid][__popc(cm & ((1u << lane) - 1u))] = (unsigned char)lane;
+            __syncwarp();
+            const int total = __popc(cm) * 4;
+            const int qbase = q_lo + u * kSpmThreads + wid * 32;         // quad of lane 0
+            for (int b = 0; b < total; b += 32) {
+                const int l = b + lane;
+                if (l >= total) continue;
+                const int qs = qbase + (int)s_src[wid][l >> 2];
+                const int e = l & 3;
+                const long long ei = (off + qs) * 4 + e;
+                float pe = 0.0f;
+                if (LOSS) pe = __ldg(P.logits + ei);
+                const int row = (int)fdiv((uint32_t)qs, P.div_qpr), col = (qs - row * qpr) * 4 + e;
+                float t0, te;
+                spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
+                const bool mk = t0 > 0.0f;
+                float ge = 0.0f;
+                if (!LOSS) {
+                    if (!disp) te = t0;
+                } else if (!disp) {
+                    const float sg = sigmoid_fast(pe);
+                    const float d = (mk ? sg : sg * 0.0f) - t0;
+                    acc = fmaf(d, d, acc);
+                    ge = mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
+                    te = t0;
+                } else {
+                    // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
+                    float th = 0.0f, pm = pe != pe ? pe : 0.0f;          // NaN logits propagate as in the reference
+                    if (mk) { th = tanhf(pe); pm = th; }
+                    const float d = pm - te;
+                    const float ad = fabsf(d);
+                    acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+                    ge = mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
+                }
+                if (GRAD) __stcs(P.dlogits + ei, ge);
+                if (WTGT) __stcs(P.target_out + ei, te);
+            }
+            __syncwarp();                                                // scratch row is rewritten by the next covered group
+        }
+        if (c == 0) droot += (double)acc; else ddisp += (double)acc;
+        if (++chunk == upp) {
+            chunk = 0;
+            ++plane;
+            if (++c == C) { c = 0; ++img; }
+        }
+    }
+    if (!LOSS) return;                                                   // render-only: no loss partials (P.partials is NULL)
+    droot = warp_sum(droot);
+    ddisp = warp_sum(ddisp);
+    if (lane == 0) { red[wid][0] = droot; red[wid][1] = ddisp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < kSpmThreads / 32; ++w) { a += red[w][0]; b += red[w][1]; }
+        P.partials[2 * blockIdx.x] = a;
+        P.partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
 // ---------------------------------------------------------------- decode
 // nms_spm (utils/spm_utils.py:112-161): candidates conf > thr, repeatedly take the best remaining candidate
 // (ties: lowest row-major index) and drop everything within dist_threshold of it (strict: d > thr survives).
@@ -315,6 +597,7 @@ struct SpmDecodeParams {
     float thr; double dist_thr; int apply_act;
     float zf;                    // fp32(sqrt(2 R^2))
     float input_size;            // DecodeSPM.input_size
+    long long s_min;             // smallest integer s with sqrt((double)s) > dist_thr: the radius test on integer offsets
 };
 
 // One body joint of one root (get_spm_keypoints utils/spm_utils.py:187-197 + the rescale at :247-248):
@@ -359,8 +642,29 @@ __global__ void __launch_bounds__(128) spm_gather_kernel(const float* __restrict
     else { o[0] = kx; o[1] = ky; o[2] = c; }
 }
 
+// Root NMS of one image.  The activated root map lives in shared memory (-inf = not a candidate / suppressed) together
+// with a compact list of the candidate pixels (conf > thr).  Real maps have a few dozen candidates, so the greedy loop
+// scans the LIST, not the 16 384-pixel map, and for <= kSpmWarpList candidates a single warp runs the whole loop with
+// shuffles and no block barrier (the earlier version scanned the full map with the whole CTA and 3 barriers per root:
+// 58 us per 256 images, all of it latency).  Dense maps (> kSpmCandCap candidates) fall back to the full scan.
+constexpr int kSpmCandCap = 2048;
+constexpr int kSpmWarpList = 256;
+
+template <typename Scan>
+__device__ __forceinline__ void spm_pick_best(Scan scan, int n, int t0, int stride, float& best, int& besti) {
+    best = -INFINITY;
+    besti = 0x7fffffff;
+    for (int e = t0; e < n; e += stride) {
+        float v; int idx;
+        scan(e, v, idx);
+        if (v > best || (v == best && idx < besti)) { best = v; besti = idx; }
+    }
+}
+
 __global__ void __launch_bounds__(kSpmThreads) spm_decode_kernel(SpmDecodeParams P) {
-    extern __shared__ float hmap[];                 // R*R
+    extern __shared__ __align__(16) float hmap[];   // R*R
+    __shared__ int s_cand[kSpmCandCap];
+    __shared__ int s_ncand;
     __shared__ float s_v[kSpmThreads / 32];
     __shared__ int s_i[kSpmThreads / 32];
     __shared__ float s_best;
@@ -370,60 +674,126 @@ __global__ void __launch_bounds__(kSpmThreads) spm_decode_kernel(SpmDecodeParams
     const long long plane = RR;
     const float* base = P.x + (long long)img * P.C * plane;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_ncand = 0;
+    __syncthreads();
 
-    for (int i = threadIdx.x; i < RR; i += blockDim.x) {
-        const float v = ldg_stream(base + i);
-        const float h = P.apply_act ? sigmoid_fast(v) : v;
-        hmap[i] = h > P.thr ? h : -INFINITY;
+    // load + activate + threshold; every thread then appends its own candidates to the list (one shared atomic per thread)
+    int mine = 0;
+    if ((RR & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        const float4* b4 = reinterpret_cast<const float4*>(base);
+        float4* h4 = reinterpret_cast<float4*>(hmap);
+        const int nq = RR >> 2;
+        constexpr int U = 8;
+        for (int q0 = threadIdx.x; q0 < nq; q0 += kSpmThreads * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * kSpmThreads;
+                if (q < nq) v[u] = ldg_stream(b4 + q);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * kSpmThreads;
+                if (q >= nq) break;
+                float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float h = P.apply_act ? sigmoid_fast(e[k]) : e[k];
+                    const bool cand = h > P.thr;
+                    e[k] = cand ? h : -INFINITY;
+                    mine += cand;
+                }
+                h4[q] = make_float4(e[0], e[1], e[2], e[3]);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < RR; i += blockDim.x) {
+            const float v = ldg_stream(base + i);
+            const float h = P.apply_act ? sigmoid_fast(v) : v;
+            const bool cand = h > P.thr;
+            hmap[i] = cand ? h : -INFINITY;
+            mine += cand;
+        }
+    }
+    if (mine) {
+        int pos = atomicAdd(&s_ncand, mine);
+        // re-walk this thread's own elements (same index pattern as above; its own shared-memory writes are visible to it)
+        if ((RR & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+            for (int q = threadIdx.x; q < (RR >> 2) && mine; q += kSpmThreads)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (hmap[4 * q + k] > -INFINITY) { if (pos < kSpmCandCap) s_cand[pos] = 4 * q + k; ++pos; --mine; }
+        } else {
+            for (int i = threadIdx.x; i < RR && mine; i += blockDim.x)
+                if (hmap[i] > -INFINITY) { if (pos < kSpmCandCap) s_cand[pos] = i; ++pos; --mine; }
+        }
     }
     __syncthreads();
+    const int ncand = s_ncand;
 
     const int rad = (int)floor(P.dist_thr);
     const int side = 2 * rad + 1;
     int found = 0;
     float* roots = P.roots + (long long)img * P.Pmax * 3;
     float* kps = P.kps + (long long)img * P.Pmax * P.K * 3;
-    while (true) {
-        float best = -INFINITY;
-        int besti = 0x7fffffff;
-        for (int i = threadIdx.x; i < RR; i += blockDim.x) {
-            const float v = hmap[i];
-            if (v > best) { best = v; besti = i; }
-        }
-        warp_argmax_first(best, besti);
-        if (lane == 0) { s_v[wid] = best; s_i[wid] = besti; }
-        __syncthreads();
-        if (wid == 0) {
-            best = lane < kSpmThreads / 32 ? s_v[lane] : -INFINITY;
-            besti = lane < kSpmThreads / 32 ? s_i[lane] : 0x7fffffff;
-            warp_argmax_first(best, besti);
-            if (lane == 0) { s_best = best; s_besti = besti; }
-        }
-        __syncthreads();
-        best = s_best; besti = s_besti;
-        if (!(best > -INFINITY)) break;
+
+    // emit root `found` and its joints with threads [t0, t0+stride, ...) of the calling group; then suppress the disc
+    auto emit_and_suppress = [&](float best, int besti, int t0, int stride) {
         const int ry = besti / P.R, rx = besti - ry * P.R;
         if (found < P.Pmax) {
-            // root row + its K joints: one thread per joint
-            if (threadIdx.x == 0) {
+            if (t0 == 0) {
                 roots[found * 3 + 0] = __fdiv_rn(__fmul_rn((float)rx, P.input_size), (float)P.R);
                 roots[found * 3 + 1] = __fdiv_rn(__fmul_rn((float)ry, P.input_size), (float)P.R);
                 roots[found * 3 + 2] = best;
             }
-            for (int k = threadIdx.x; k < P.K; k += blockDim.x) {
+            for (int k = t0; k < P.K; k += stride)
                 spm_joint(base + plane, plane, besti, rx, ry, best, k, P.apply_act, P.zf, P.dist_thr, P.input_size, (float)P.R,
                           kps + ((long long)found * P.K + k) * 3);
-            }
         }
-        ++found;
-        // suppress the disc (survivors satisfy sqrt(dx^2+dy^2) > dist_thr)
-        for (int t = threadIdx.x; t < side * side; t += blockDim.x) {
+        // survivors satisfy sqrt(dx^2+dy^2) > dist_thr  <=>  dx^2+dy^2 >= s_min (s_min found on the host with the same sqrt)
+        for (int t = t0; t < side * side; t += stride) {
             const int oy = t / side - rad, ox = t - (t / side) * side - rad;
             const int y = ry + oy, x = rx + ox;
             if (y < 0 || y >= P.R || x < 0 || x >= P.R) continue;
-            if (!(sqrt((double)(ox * ox + oy * oy)) > P.dist_thr)) hmap[y * P.R + x] = -INFINITY;
+            if ((long long)(ox * ox + oy * oy) < P.s_min) hmap[y * P.R + x] = -INFINITY;
         }
-        __syncthreads();
+    };
+
+    if (ncand <= kSpmWarpList) {
+        // one warp, no block barriers
+        if (wid == 0) {
+            while (true) {
+                float best; int besti;
+                spm_pick_best([&](int e, float& v, int& idx) { idx = s_cand[e]; v = hmap[idx]; }, ncand, lane, 32, best, besti);
+                warp_argmax_first(best, besti);
+                if (!(best > -INFINITY)) break;
+                emit_and_suppress(best, besti, lane, 32);
+                ++found;
+                __syncwarp();
+            }
+        }
+    } else {
+        const bool list = ncand <= kSpmCandCap;
+        while (true) {
+            float best; int besti;
+            if (list) spm_pick_best([&](int e, float& v, int& idx) { idx = s_cand[e]; v = hmap[idx]; }, ncand, (int)threadIdx.x, kSpmThreads, best, besti);
+            else spm_pick_best([&](int e, float& v, int& idx) { idx = e; v = hmap[e]; }, RR, (int)threadIdx.x, kSpmThreads, best, besti);
+            warp_argmax_first(best, besti);
+            if (lane == 0) { s_v[wid] = best; s_i[wid] = besti; }
+            __syncthreads();
+            if (wid == 0) {
+                best = lane < kSpmThreads / 32 ? s_v[lane] : -INFINITY;
+                besti = lane < kSpmThreads / 32 ? s_i[lane] : 0x7fffffff;
+                warp_argmax_first(best, besti);
+                if (lane == 0) { s_best = best; s_besti = besti; }
+            }
+            __syncthreads();
+            best = s_best; besti = s_besti;
+            if (!(best > -INFINITY)) break;
+            emit_and_suppress(best, besti, (int)threadIdx.x, kSpmThreads);
+            ++found;
+            __syncthreads();
+        }
     }
     if (threadIdx.x == 0) {
         P.counts[img] = min(found, P.Pmax);

@@ -31,6 +31,20 @@ def _i64(a, device):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int64))).to(device)
 
 
+def _render_args(centers, joints, counts, output_res, sigma, dev):
+    """Device-side person arrays + Gaussian template shared by `spm_render_batch` and `spm_loss.spm_fused`."""
+    c = _i64(centers, dev)
+    j = _i64(joints, dev)
+    n, pmax = j.size(0), j.size(1)
+    assert tuple(c.shape) == (n, pmax, 2) and j.dim() == 4 and j.size(3) == 2
+    cnt = (counts.to(device=dev, dtype=torch.int32) if isinstance(counts, torch.Tensor)
+           else torch.from_numpy(np.asarray(counts, dtype=np.int32)).to(dev)).contiguous()
+    assert cnt.numel() == n
+    sig = float(output_res / 64 if sigma < 0 else sigma)
+    g = _gauss_template(sig)
+    return c, j, cnt, sig, _templates.get(g, sig, dev), g.shape[0]
+
+
 def spm_render_batch(centers, joints, counts, output_res, sigma=-1, device=None):
     """centers [N,Pmax,2] i64, joints [N,Pmax,K,2] i64, counts [N] i32 -> CUDA fp32 [N,1+2K,R,R].
 
@@ -38,18 +52,11 @@ def spm_render_batch(centers, joints, counts, output_res, sigma=-1, device=None)
     (SPMMaskGenerator + SPMDisplacementGenerator), as concatenated at dataset/spm_coco_dataset.py:86.
     """
     dev = _device(device if device is not None else (centers.device if isinstance(centers, torch.Tensor) and centers.is_cuda else None))
-    c = _i64(centers, dev)
-    j = _i64(joints, dev)
+    c, j, cnt, sig, lut, lut_n = _render_args(centers, joints, counts, output_res, sigma, dev)
     n, pmax, k = j.size(0), j.size(1), j.size(2)
-    assert tuple(c.shape) == (n, pmax, 2) and j.size(3) == 2
-    cnt = (counts.to(device=dev, dtype=torch.int32) if isinstance(counts, torch.Tensor)
-           else torch.from_numpy(np.asarray(counts, dtype=np.int32)).to(dev)).contiguous()
-    sig = float(output_res / 64 if sigma < 0 else sigma)
-    g = _gauss_template(sig)
-    lut = _templates.get(g, sig, dev)
     out = torch.empty((n, 1 + 2 * k, output_res, output_res), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(lib().pose_spm_render(ptr(c), ptr(j), ptr(cnt), ptr(out), n, pmax, k, output_res, sig, ptr(lut), g.shape[0],
+        check(lib().pose_spm_render(ptr(c), ptr(j), ptr(cnt), ptr(out), n, pmax, k, output_res, sig, ptr(lut), lut_n,
                                     stream_ptr(dev)), "pose_spm_render")
     return out
 

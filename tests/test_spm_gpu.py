@@ -189,3 +189,91 @@ def test_config4_batch_decode_against_oracle(pb, dev):
     l64, _ = po.spm_loss_closed_form_f64(logits[:8], torch.from_numpy(target[:8]))
     assert close(pb.spm_loss_fused(logits[:8].to(dev), torch.from_numpy(target[:8]).to(dev), want_grad=False)["loss"].item(),
                  float(l64), REL)
+
+
+# --------------------------------------------------------------------------- fused render + loss (+grad): persons in, no dense target
+@pytest.mark.parametrize("name,n", [("small", 6), ("coco", 4)])
+def test_fused_render_loss_grad(pb, dev, name, n):
+    """pose_spm_fused: the target it renders in registers is bit-identical to the golden (reference-generated) target,
+    loss / gradients match the golden reference values and the dense-target kernel."""
+    g = load_golden("spm_" + name)
+    people, target, logits, meta = cases.spm_case(name, n)
+    c, j, cnt = cases.pack_people(people)
+    x = logits.to(dev)
+    r = pb.spm_fused(x, c, j, cnt, meta["sigma"], want_grad=True, want_target=True)
+    assert np.array_equal(r["target"].cpu().numpy(), g["target"])
+    assert close(r["loss"].item(), float(g["loss"]), REL)
+    l64, g64 = po.spm_loss_closed_form_f64(logits, torch.from_numpy(g["target"]))
+    assert close(r["loss"].item(), float(l64), REL) and allclose(r["dlogits"], g64, REL, atol_frac=1.0)
+    # same arithmetic per element as the dense-target kernel: gradients bit-identical, loss equal up to summation order
+    d = pb.spm_loss_fused(x, torch.from_numpy(g["target"]).to(dev))
+    assert torch.equal(r["dlogits"], d["dlogits"])
+    assert close(r["loss"].item(), d["loss"].item(), 1e-6)
+    # without grad / target outputs, and padding beyond counts[i] ignored
+    c2, j2, _ = cases.pack_people(people, pmax=c.shape[1] + 3)
+    c2[:, c.shape[1]:] = 9
+    j2[:, c.shape[1]:] = 11
+    r2 = pb.spm_fused(x, c2, j2, cnt, meta["sigma"], want_grad=False)
+    assert r2["dlogits"] is None and r2["target"] is None and r2["loss"].item() == r["loss"].item()
+    # SPMLoss drop-in with the persons hand-off (SURVEY 8 f-1), autograd with a scaled upstream gradient
+    x3 = logits.to(dev).requires_grad_(True)
+    loss = pb.SPMLoss(sigma=meta["sigma"])(x3, {"centers": torch.from_numpy(c), "joints": torch.from_numpy(j), "counts": torch.from_numpy(cnt)})
+    assert loss.dim() == 0 and loss.requires_grad
+    (loss * 2.5).backward()
+    assert close(loss.item(), float(g["loss"]), REL) and allclose(x3.grad, 2.5 * g64, REL, atol_frac=1.0)
+
+
+def test_fused_crowded_edges_and_nan(pb, dev):
+    """64 persons per image (the fused kernel's limit) with overlapping boxes, centres on the border / off the map / (0,0),
+    dropped joints, an empty image, random logits (saturated activations, |d| >= 1 SmoothL1 branch); non-integer sigma
+    (box and Gaussian support differ); more than 64 persons falls back to render + dense loss; NaN logits propagate."""
+    rng = np.random.default_rng(17)
+    for k, res, sigma, ps in ((3, 64, 1, (64, 0, 37, 1)), (2, 32, 1.5, (5, 9, 0, 2)), (2, 36, 0.5, (3, 1, 4, 2))):
+        people = []
+        for p in ps:
+            c = rng.integers(-3, res + 3, size=(p, 1, 2), dtype=np.int64)
+            j = np.clip(c + rng.integers(-20, 21, size=(p, k, 2), dtype=np.int64), 0, res - 1)
+            if p > 1:
+                c[0] = 0
+                j[p // 2, 1] = 0
+            people.append((c, j))
+        want_t = np.stack([po.spm_render(c, j, res, sigma) for c, j in people])
+        c, j, cnt = cases.pack_people(people)
+        xr = torch.randn((len(ps), 1 + 2 * k, res, res), generator=torch.Generator().manual_seed(3)) * 4
+        r = pb.spm_fused(xr.to(dev), c, j, cnt, sigma, want_grad=True, want_target=True)
+        assert np.array_equal(r["target"].cpu().numpy(), want_t), (k, res, sigma)
+        assert np.array_equal(pb.spm_render_batch(c, j, cnt, res, sigma).cpu().numpy(), want_t)
+        l64, g64 = po.spm_loss_closed_form_f64(xr, torch.from_numpy(want_t))
+        assert close(r["loss"].item(), float(l64), REL) and allclose(r["dlogits"], g64, REL, atol_frac=1.0)
+    # > 64 persons: SPMLoss renders and uses the dense kernel; the raw entry point refuses
+    k, res = 2, 64
+    c = rng.integers(2, res - 2, size=(1, 70, 2), dtype=np.int64)
+    j = np.clip(c[:, :, None, :] + rng.integers(-9, 10, size=(1, 70, k, 2), dtype=np.int64), 1, res - 2)
+    cnt = np.array([70], dtype=np.int32)
+    xr = torch.randn((1, 1 + 2 * k, res, res), generator=torch.Generator().manual_seed(4))
+    want_t = po.spm_render(c[0][:, None], j[0], res, 1)[None]
+    l64, _ = po.spm_loss_closed_form_f64(xr, torch.from_numpy(want_t))
+    assert close(pb.SPMLoss(sigma=1)(xr.to(dev), (c, j, cnt)).item(), float(l64), REL)
+    with pytest.raises(pb.PoseB200Error):
+        pb.spm_fused(xr.to(dev), c, j, cnt, 1)
+    # a NaN logit anywhere (even under a zero mask) makes the loss NaN, as tanh(nan)*0 does in the reference
+    xn = xr.clone()
+    xn[0, 3, 1, 1] = float("nan")
+    assert torch.isnan(pb.spm_fused(xn.to(dev), c[:, :8], j[:, :8], np.array([8], dtype=np.int32), 1, want_grad=False)["loss"])
+    # empty batch
+    e = pb.spm_fused(torch.zeros((0, 5, 32, 32), device=dev), np.zeros((0, 1, 2), np.int64), np.zeros((0, 1, 2, 2), np.int64),
+                     np.zeros((0,), np.int32), 1)
+    assert e["loss"].item() == 0.0 and e["dlogits"].shape[0] == 0
+
+
+def test_fused_config4_batch(pb, dev):
+    """Config 4 at N=64: fused kernel against the dense path on the same rendered target (every image, every plane)."""
+    people, target, logits, meta = cases.spm_case("coco", 64, seed=777)
+    c, j, cnt = cases.pack_people(people)
+    x = logits.to(dev)
+    r = pb.spm_fused(x, c, j, cnt, 1, want_grad=True, want_target=True)
+    assert np.array_equal(r["target"].cpu().numpy(), target)
+    d = pb.spm_loss_fused(x, torch.from_numpy(target).to(dev))
+    assert torch.equal(r["dlogits"], d["dlogits"]) and close(r["loss"].item(), d["loss"].item(), 1e-6)
+    l64, _ = po.spm_loss_closed_form_f64(logits, torch.from_numpy(target))
+    assert close(r["loss"].item(), float(l64), REL)

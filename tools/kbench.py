@@ -70,6 +70,7 @@ def main():
     ap.add_argument("--k", type=int, default=17)
     ap.add_argument("--tma", action="store_true", help="fused render variants through the TMA-staged kernel")
     ap.add_argument("--no-spm", action="store_true")
+    ap.add_argument("--spm-n", type=int, default=1024, help="second SPM batch size (config 4: 1024 images)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     B, K = args.batch, args.k
@@ -134,7 +135,17 @@ def main():
         run_spm("spm_render(N=256)", lambda: pb.spm_render_batch(c, j, cnt, 128, 1), img_bytes)
         run_spm("spm_loss_grad(N=256)", lambda: pb.spm_loss_fused(x, t), 3 * img_bytes)
         run_spm("spm_loss_only(N=256)", lambda: pb.spm_loss_fused(x, t, want_grad=False), 2 * img_bytes)
+        run_spm("spm_fused_render_loss_grad(N=256)", lambda: pb.spm_fused(x, c, j, cnt, 1), 2 * img_bytes)
+        run_spm("spm_fused_render_loss_only(N=256)", lambda: pb.spm_fused(x, c, j, cnt, 1, want_grad=False), img_bytes)
+        run_spm("spm_fused_render_loss_grad_target(N=256)", lambda: pb.spm_fused(x, c, j, cnt, 1, want_target=True), 3 * img_bytes)
         run_spm("spm_decode(N=256,thr=.5)", lambda: pb.spm_decode_batch(x, 512, 1, 0.5, True, 32), 128 * 128 * 4)
+        n = args.spm_n
+        if n != 256:
+            c, j, cnt, t, x = spm_inputs(n, dev)
+            run_spm(f"spm_fused_render_loss_grad(N={n})", lambda: pb.spm_fused(x, c, j, cnt, 1), 2 * img_bytes)
+            run_spm(f"spm_loss_grad(N={n})", lambda: pb.spm_loss_fused(x, t), 3 * img_bytes)
+            run_spm(f"spm_render(N={n})", lambda: pb.spm_render_batch(c, j, cnt, 128, 1), img_bytes)
+            run_spm(f"spm_decode(N={n},thr=.5)", lambda: pb.spm_decode_batch(x, 512, 1, 0.5, True, 32), 128 * 128 * 4)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump({"batch": B, "K": K, "H": H, "W": W, "tma": args.tma, "peak_GBps": pk, "results": res}, open(args.out, "w"), indent=1)
 

@@ -16,20 +16,27 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "tune")
 SRC = os.path.join(ROOT, "pytorch-pose-estimation_b200", "csrc", "api.cu")
 VARIANTS = [(u, m) for u in (4, 6, 8) for m in (2, 3, 4)]
+# read-only (validation) render variants: loads in flight per lane, resident CTAs per SM
+NG_VARIANTS = [(6, 3), (6, 4), (8, 3), (8, 4), (12, 2), (12, 3)]
 # TMA-staged kernel: (stages, warps per CTA, float4 per tile)
 TMA_VARIANTS = [(2, 8, 256), (3, 8, 256), (4, 8, 256), (3, 4, 256), (3, 16, 256), (2, 16, 256), (3, 8, 128), (4, 8, 128), (6, 8, 128),
                 (2, 8, 768), (2, 4, 768), (3, 4, 768)]
 
 
-def build():
+def build(which="all"):
     os.makedirs(OUT, exist_ok=True)
     procs = []
-    for u, m in VARIANTS:
+    for u, m in (VARIANTS if which != "ng" else []):
         lib = os.path.join(OUT, f"libpose_u{u}_m{m}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                f"-DPOSE_FUSED_U={u}", f"-DPOSE_FUSED_MINB={m}", "-o", lib, SRC]
         procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for st, w, tv in TMA_VARIANTS:
+    for u, m in NG_VARIANTS:
+        lib = os.path.join(OUT, f"libpose_ng_u{u}_m{m}.so")
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+               f"-DPOSE_FUSED_U_NG={u}", f"-DPOSE_FUSED_MINB_NG={m}", "-o", lib, SRC]
+        procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for st, w, tv in (TMA_VARIANTS if which != "ng" else []):
         lib = os.path.join(OUT, f"libpose_tma_s{st}_w{w}_t{tv}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                f"-DPOSE_TMA_STAGES={st}", f"-DPOSE_TMA_WARPS={w}", f"-DPOSE_TMA_TILE_VEC={tv}", "-o", lib, SRC]
@@ -39,7 +46,7 @@ def build():
         print(os.path.basename(lib), "ok" if p.returncode == 0 else "FAILED\n" + out)
 
 
-def run(reps):
+def run(reps, which="all"):
     import torch
     from pose_b200 import _cabi
     from pose_b200.sbp_utils import _gauss_template
@@ -59,8 +66,13 @@ def run(reps):
     st = _cabi.stream_ptr(dev)
     res = {}
     ref = None
-    jobs = [(f"U{u}_M{m}", os.path.join(OUT, f"libpose_u{u}_m{m}.so"), 1 | 4) for u, m in VARIANTS]
-    jobs += [(f"TMA_S{st}_W{w}_T{tv}", os.path.join(OUT, f"libpose_tma_s{st}_w{w}_t{tv}.so"), 1 | 4 | 8) for st, w, tv in TMA_VARIANTS]
+    jobs = []
+    if which != "ng":
+        jobs += [(f"U{u}_M{m}", os.path.join(OUT, f"libpose_u{u}_m{m}.so"), 1 | 4) for u, m in VARIANTS]
+        jobs += [(f"TMA_S{st}_W{w}_T{tv}", os.path.join(OUT, f"libpose_tma_s{st}_w{w}_t{tv}.so"), 1 | 4 | 8) for st, w, tv in TMA_VARIANTS]
+    for fl, tag in ((0, "loss"), (4, "loss+decode")):
+        jobs += [(f"NG[{tag}]_U{u}_M{m}", os.path.join(OUT, f"libpose_ng_u{u}_m{m}.so"), fl) for u, m in NG_VARIANTS]
+    refs = {}
     for name, path, flags in jobs:
         if not os.path.exists(path):
             continue
@@ -84,9 +96,10 @@ def run(reps):
             b.record()
             b.synchronize()
             ts.append(a.elapsed_time(b) / reps)
-        sig = (float(loss), float(dl.double().abs().sum()), float(joints.double().sum()))
-        ref = ref or sig
-        res[name] = {"ms": min(ts), "GBps": 24596 * B * K / (min(ts) * 1e-3) / 1e9, "same_result": sig == ref}
+        sig = (float(loss), float(dl.double().abs().sum()) if flags & 1 else 0.0, float(joints.double().sum()) if flags & 4 else 0.0)
+        ref = refs.setdefault(flags & 5, sig)
+        nbytes = (24576 if flags & 1 else 12288) + 8 + (12 if flags & 4 else 0)
+        res[name] = {"ms": min(ts), "GBps": nbytes * B * K / (min(ts) * 1e-3) / 1e9, "same_result": sig == ref}
         print(f"{name:18s}: {min(ts)*1e3:7.1f} us  {res[name]['GBps']:7.1f} GB/s  same={sig == ref} {sig}", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "tune_fused.json"), "w"), indent=1)
@@ -97,8 +110,9 @@ if __name__ == "__main__":
     ap.add_argument("--build", action="store_true")
     ap.add_argument("--run", action="store_true")
     ap.add_argument("--reps", type=int, default=40)
+    ap.add_argument("--which", default="all", choices=["all", "ng"], help="ng: only the read-only (no-grad) variants")
     a = ap.parse_args()
     if a.build:
-        build()
+        build(a.which)
     if a.run:
-        run(a.reps)
+        run(a.reps, a.which)
