@@ -18,8 +18,10 @@ namespace pose {
 #endif
 // The read-only render variants (validation: loss and/or decode from keypoints, no dlogits) have no store stream to carry half of the traffic:
 // they need more loads in flight per SM to hide the same latency, so they get their own knobs.
+// (tools/tune_fused.py --which ng, B=4096: U6/M4 158.6 us loss, 173.9 us loss+decode; U6/M3 171.9 / 185.4; U8/M4 160.3 / 199.0
+//  -- the decode variant spills at U8 under the 64-register cap.)
 #ifndef POSE_FUSED_U_NG
-#define POSE_FUSED_U_NG 8
+#define POSE_FUSED_U_NG 6
 #endif
 #ifndef POSE_FUSED_MINB_NG
 #define POSE_FUSED_MINB_NG 4    // register cap 64

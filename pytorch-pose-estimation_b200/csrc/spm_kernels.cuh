@@ -375,7 +375,12 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
 
 // LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read, the target is
 // written as one linear stream with the covered pixels filled in by the same pass.
-// ROWG: R % 128 == 0, the 32 quads of a warp instruction lie in one row and are exactly one word of its covered-quad bits.
+// ROWG (R % 128 == 0): the 32 quads of a warp instruction lie in one row and are exactly one word of that row's
+// covered-quad bits, and every unit is full: one broadcast LDS gives the warp's coverage mask (no per-lane look-up, no
+// ballot, no validity predicates on the stream).
+// (Tried and dropped: a 4-row x 8-quad tile per warp instruction, so that a 9x9 box touches ~3.75 tiles instead of 9 rows and
+// phase B is entered 2.4x less often -- the four separate 128-byte lines per access cost more than that saved: 253 -> 318 us
+// fused, 144 -> 177 us render-only per 256 images.)
 template <bool LOSS, bool GRAD, bool WTGT, bool ROWG>
 __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
     // dynamic shared memory: [div_n] double quotients | [R] u64 row masks | [64*K] int2 joints | [R*wpr] u32 covered quads | template
@@ -453,7 +458,7 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 if (xhi < xlo) continue;
                 atomicOr(&rowmask_s[row], 1ull << p);
                 const int q0 = xlo >> 2, q1 = xhi >> 2;
-                for (int w = q0 >> 5; w <= (q1 >> 5); ++w) {
+                    for (int w = q0 >> 5; w <= (q1 >> 5); ++w) {
                     const int lo = max(q0 - 32 * w, 0), hi = min(q1 - 32 * w, 31);
                     const unsigned int bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
                     atomicOr(&covq_s[row * P.wpr + w], bits);
@@ -475,11 +480,9 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
             // computes.  (Measured: 342 -> 267 us per 256 images together with the leaner phase B; holding the next unit in
             // registers instead -- a software pipeline at 3 CTAs/SM -- was slower, 285-291 us: the kernel is bound by issue
             // slots, not by load latency.)
-            const float4* nsrc = L4 + off + min(q_lo + kSpmFusedChunk, P.quads) + threadIdx.x;
-            const float4* lend = L4 + total_quads;
-#pragma unroll
-            for (int u = 0; u < kSpmFusedU; ++u)
-                if (nsrc + u * kSpmThreads < lend) prefetch_l2(nsrc + u * kSpmThreads);
+            const char* nsrc = reinterpret_cast<const char*>(L4 + off + min(q_lo + kSpmFusedChunk, P.quads));
+            const char* lend = reinterpret_cast<const char*>(L4 + total_quads);
+            if (threadIdx.x < kSpmFusedChunk * 16 / 128 && nsrc + threadIdx.x * 128 < lend) prefetch_l2(nsrc + threadIdx.x * 128);
         }
         const bool disp = c != 0;
         const int jn = (c - 1) >> 1, axis = (c - 1) & 1;                 // displacement plane: joint and axis (0 = x, 1 = y)
@@ -487,14 +490,13 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
         unsigned cmask[kSpmFusedU];
         float4* gdst = GRAD ? G4 + off + q_lo + threadIdx.x : nullptr;
         float4* tdst = WTGT ? T4 + off + q_lo + threadIdx.x : nullptr;
-        // phase A.  ROWG: the warp's 32 quads are exactly one word of the covered-quad bits, and with wpr = qpr/32 the word
-        // index is simply the warp's group index inside the plane: one broadcast LDS per warp instruction, no ballot.
-        const int g0 = (q_lo >> 5) + wid;
+        // phase A.  ROWG: with wpr = qpr/32 the word index is simply the warp's group index inside the plane
+        unsigned anyc = 0u;
 #pragma unroll
         for (int u = 0; u < kSpmFusedU; ++u) {
             bool valid = true, covered = false;
             if (ROWG) {
-                cmask[u] = covq_s[g0 + u * (kSpmThreads / 32)];
+                cmask[u] = covq_s[(q_lo >> 5) + u * (kSpmThreads / 32) + wid];
                 covered = (cmask[u] >> lane) & 1u;
             } else {
                 const int qu = q_lo + u * kSpmThreads + (int)threadIdx.x;
@@ -505,6 +507,7 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 }
                 cmask[u] = __ballot_sync(FULL_MASK, covered);
             }
+            if (cmask[u]) anyc |= 1u << u;
             if (valid && !covered) {
                 // zero target, zero mask.  sigmoid(p)*0 and tanh(p)*0 are 0 for every non-NaN p; a NaN propagates
                 if (LOSS) {
@@ -516,14 +519,14 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
             }
         }
-        // phase B: one pixel of a covered quad per lane.  Deliberately NOT unrolled over u (the body is large: an unrolled copy
-        // per u made the kernel 113 KB of SASS and `no_instruction` the second largest stall).  The pixel's logit is re-read
-        // from L2 (the warp streamed it a moment ago) rather than shuffled out of pv[]: pv dies after phase A, which keeps
-        // the kernel inside 64 registers without spills.
-#pragma unroll 1
-        for (int u = 0; u < kSpmFusedU; ++u) {
+        // phase B: one pixel of a covered quad per lane, only for the warp instructions that have covered quads.  Deliberately
+        // NOT unrolled (the body is large: an unrolled copy per u made the kernel 113 KB of SASS and `no_instruction` the second
+        // largest stall).  The pixel's logit is re-read from L2 (the warp streamed it a moment ago) rather than shuffled out
+        // of pv[]: pv dies after phase A, which keeps the kernel inside 64 registers without spills.
+        while (anyc) {                                                   // warp-uniform
+            const int u = __ffs((int)anyc) - 1;
+            anyc &= anyc - 1u;
             const unsigned cm = u == 0 ? cmask[0] : (u == 1 ? cmask[1] : (u == 2 ? cmask[2] : cmask[3]));
-            if (cm == 0u) continue;                                      // warp-uniform
             // slot k of the warp's scratch row = lane that owns the k-th covered quad
             if ((cm >> lane) & 1u) s_src[wid][__popc(cm & ((1u << lane) - 1u))] = (unsigned char)lane;
             __syncwarp();

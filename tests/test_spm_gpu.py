@@ -228,14 +228,16 @@ def test_fused_crowded_edges_and_nan(pb, dev):
     dropped joints, an empty image, random logits (saturated activations, |d| >= 1 SmoothL1 branch); non-integer sigma
     (box and Gaussian support differ); more than 64 persons falls back to render + dense loss; NaN logits propagate."""
     rng = np.random.default_rng(17)
-    for k, res, sigma, ps in ((3, 64, 1, (64, 0, 37, 1)), (2, 32, 1.5, (5, 9, 0, 2)), (2, 36, 0.5, (3, 1, 4, 2))):
+    # res 64 / 32 / 36: linear warp mapping; 256 (8 tile columns) and 384 (12: not a power of two): the tiled mapping
+    for k, res, sigma, ps in ((3, 64, 1, (64, 0, 37, 1)), (2, 32, 1.5, (5, 9, 0, 2)), (2, 36, 0.5, (3, 1, 4, 2)),
+                              (2, 256, 2.5, (9, 0, 3)), (1, 384, 1, (6, 2))):
         people = []
         for p in ps:
             c = rng.integers(-3, res + 3, size=(p, 1, 2), dtype=np.int64)
             j = np.clip(c + rng.integers(-20, 21, size=(p, k, 2), dtype=np.int64), 0, res - 1)
             if p > 1:
                 c[0] = 0
-                j[p // 2, 1] = 0
+                j[p // 2, k - 1] = 0
             people.append((c, j))
         want_t = np.stack([po.spm_render(c, j, res, sigma) for c, j in people])
         c, j, cnt = cases.pack_people(people)

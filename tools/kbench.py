@@ -19,6 +19,9 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import pose_b200 as pb  # noqa: E402
 
 
+EAGER = False      # --eager: time back-to-back eager launches instead of CUDA-graph replays
+
+
 def peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
@@ -33,6 +36,8 @@ def timeit(fn, reps, warm=5):
     torch.cuda.synchronize()
     run = None
     try:
+        if EAGER:
+            raise RuntimeError("eager timing requested")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -71,7 +76,10 @@ def main():
     ap.add_argument("--tma", action="store_true", help="fused render variants through the TMA-staged kernel")
     ap.add_argument("--no-spm", action="store_true")
     ap.add_argument("--spm-n", type=int, default=1024, help="second SPM batch size (config 4: 1024 images)")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph: queue-saturated eager launches")
     args = ap.parse_args()
+    global EAGER
+    EAGER = args.eager
     dev = torch.device("cuda", 0)
     B, K = args.batch, args.k
     H, W = map(int, args.hw.split("x"))
