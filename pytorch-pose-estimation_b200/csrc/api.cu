@@ -381,13 +381,14 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
         const size_t fsmem = pose::spm_fused_smem_bytes(F.div_n, R, K, F.wpr, lut_n);
         if (fsmem <= 200 * 1024) {
             const long long funits = (long long)N * (1 + 2 * K) * ((quads + pose::kSpmFusedChunk - 1) / pose::kSpmFusedChunk);
-#define POSE_SPMR(RG)                                                                                                          \
+#define POSE_SPMR(RG, MP)                                                                                                      \
     {                                                                                                                          \
-        if (fsmem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<false, false, true, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem); \
-        const int fgrid = persistent_grid(pose::spm_fused_kernel<false, false, true, RG>, pose::kSpmThreads, fsmem, funits);   \
-        pose::spm_fused_kernel<false, false, true, RG><<<fgrid, pose::kSpmThreads, fsmem, (cudaStream_t)stream>>>(F);          \
+        if (fsmem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<false, false, true, RG, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem); \
+        const int fgrid = persistent_grid(pose::spm_fused_kernel<false, false, true, RG, MP>, pose::kSpmThreads, fsmem, funits); \
+        pose::spm_fused_kernel<false, false, true, RG, MP><<<fgrid, pose::kSpmThreads, fsmem, (cudaStream_t)stream>>>(F);      \
     }
-            if (R % 128 == 0) POSE_SPMR(true) else POSE_SPMR(false)
+            if (pose::spm_fused_use_map(R)) { if (R % 128 == 0) POSE_SPMR(true, true) else POSE_SPMR(false, true) }
+            else { if (R % 128 == 0) POSE_SPMR(true, false) else POSE_SPMR(false, false) }
 #undef POSE_SPMR
             return check_launch("spm_render(single pass)");
         }
@@ -484,18 +485,19 @@ int pose_spm_fused(const float* logits, const long long* centers, const long lon
         const size_t smem = pose::spm_fused_smem_bytes(P.div_n, R, K, P.wpr, lut_n);
         if (smem > 200 * 1024) return fail(POSE_EINVAL, "spm_fused: R=%d K=%d needs %zu bytes of shared memory (use pose_spm_render + pose_spm_loss)", R, K, smem);
         const long long units = (long long)N * (1 + 2 * K) * ((P.quads + pose::kSpmFusedChunk - 1) / pose::kSpmFusedChunk);
-#define POSE_SPMF2(G, T, RG)                                                                                                  \
+#define POSE_SPMF3(G, T, RG, MP)                                                                                              \
     {                                                                                                                          \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<true, G, T, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        grid = persistent_grid(pose::spm_fused_kernel<true, G, T, RG>, pose::kSpmThreads, smem, units);                        \
-        pose::spm_fused_kernel<true, G, T, RG><<<grid, pose::kSpmThreads, smem, st>>>(P);                                      \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<true, G, T, RG, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        grid = persistent_grid(pose::spm_fused_kernel<true, G, T, RG, MP>, pose::kSpmThreads, smem, units);                    \
+        pose::spm_fused_kernel<true, G, T, RG, MP><<<grid, pose::kSpmThreads, smem, st>>>(P);                                  \
     }
 #define POSE_SPMF(G, T)                                                                                                        \
     {                                                                                                                          \
-        if (R % 128 == 0) POSE_SPMF2(G, T, true) else POSE_SPMF2(G, T, false)                                                  \
+        if (pose::spm_fused_use_map(R)) { if (R % 128 == 0) POSE_SPMF3(G, T, true, true) else POSE_SPMF3(G, T, false, true) }  \
+        else { if (R % 128 == 0) POSE_SPMF3(G, T, true, false) else POSE_SPMF3(G, T, false, false) }                           \
     }
         if (grad && wtgt) POSE_SPMF(true, true) else if (grad) POSE_SPMF(true, false) else if (wtgt) POSE_SPMF(false, true) else POSE_SPMF(false, false)
-#undef POSE_SPMF2
+#undef POSE_SPMF3
 #undef POSE_SPMF
         if (int rc = check_launch("spm_fused")) return rc;
     }

@@ -346,8 +346,12 @@ constexpr int kSpmFusedU = 4;
 constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;      // float4 per work unit (16 KB)
 constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
 
+constexpr int kSpmMapMaxBytes = 16384;                        // per-image pixel map (one byte per pixel): R <= 128
+
+__host__ __device__ inline bool spm_fused_use_map(int R) { return R * R <= kSpmMapMaxBytes; }
 __host__ __device__ inline size_t spm_fused_smem_bytes(int div_n, int R, int K, int wpr, int lut_n) {
-    return (size_t)div_n * 8 + (size_t)R * 8 + (size_t)kSpmFusedMaxPersons * K * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4;
+    return (size_t)div_n * 8 + (size_t)R * 8 + (size_t)kSpmFusedMaxPersons * K * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4 +
+           (spm_fused_use_map(R) ? (size_t)R * R : 0);
 }
 
 // target of one pixel: (root value t0 = max of the covering Gaussian patches, displacement te of plane (jn, axis))
@@ -375,21 +379,28 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
 
 // LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read, the target is
 // written as one linear stream with the covered pixels filled in by the same pass.
+// MAP (R*R <= 16 KB, i.e. R <= 128 -- configs/spm_coco.yaml): the geometry of a pixel is the same for all 2K displacement
+// planes of an image, so it is evaluated ONCE per image into a byte map in shared memory -- bit 7: root mask (t0 > 0), bits
+// 0-6: 0 = in no person's box, p+1 = in the box of person p only, 127 = in several boxes (replay them in order) -- and phase B
+// of a displacement plane is one byte load + one joint + one quotient look-up instead of a loop over the row's persons with
+// eight range compares each.  Larger maps keep the generic per-pixel evaluation.
 // ROWG (R % 128 == 0): the 32 quads of a warp instruction lie in one row and are exactly one word of that row's
 // covered-quad bits, and every unit is full: one broadcast LDS gives the warp's coverage mask (no per-lane look-up, no
 // ballot, no validity predicates on the stream).
 // (Tried and dropped: a 4-row x 8-quad tile per warp instruction, so that a 9x9 box touches ~3.75 tiles instead of 9 rows and
 // phase B is entered 2.4x less often -- the four separate 128-byte lines per access cost more than that saved: 253 -> 318 us
 // fused, 144 -> 177 us render-only per 256 images.)
-template <bool LOSS, bool GRAD, bool WTGT, bool ROWG>
+template <bool LOSS, bool GRAD, bool WTGT, bool ROWG, bool MAP>
 __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
     // dynamic shared memory: [div_n] double quotients | [R] u64 row masks | [64*K] int2 joints | [R*wpr] u32 covered quads | template
+    //                        | MAP: [R*R] u8 pixel map
     extern __shared__ __align__(16) unsigned char spm_fused_smem[];
     double* div_s = reinterpret_cast<double*>(spm_fused_smem);
     unsigned long long* rowmask_s = reinterpret_cast<unsigned long long*>(div_s + P.div_n);
     int2* s_j = reinterpret_cast<int2*>(rowmask_s + P.R);
     unsigned int* covq_s = reinterpret_cast<unsigned int*>(s_j + kSpmFusedMaxPersons * P.K);
     float* lut_s = reinterpret_cast<float*>(covq_s + P.R * P.wpr);
+    unsigned char* map_s = reinterpret_cast<unsigned char*>(lut_s + P.lut_n * P.lut_n);      // MAP only
     __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
     __shared__ double red[kSpmThreads / 32][2];
     __shared__ unsigned char s_src[kSpmThreads / 32][32];
@@ -465,6 +476,32 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 }
             }
             __syncthreads();
+            if (MAP) {
+                // one warp per row; only rows that some person touches are ever looked up, the others are not even written
+                for (int row = wid; row < P.R; row += kSpmThreads / 32) {
+                    const unsigned long long rm = rowmask_s[row];
+                    if (rm == 0ull) continue;                           // warp-uniform
+                  for (int col = lane; col < P.R; col += 32) {
+                    const int idx = row * P.R + col;
+                    unsigned long long m = rm;
+                    unsigned int code = 0u, nbox = 0u;
+                    bool mk = false;
+                    while (m) {
+                        const int p = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const SpmFusedPerson sp = s_p[p];
+                        if (row >= sp.py0 && row < sp.py1 && col >= sp.px0 && col < sp.px1 &&
+                            lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)] > 0.0f) mk = true;
+                        if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
+                            if (nbox++ == 0u) code = (unsigned)p + 1u;
+                        }
+                    }
+                    if (nbox > 1u) code = 127u;
+                    map_s[idx] = (unsigned char)(code | (mk ? 128u : 0u));
+                  }
+                }
+                __syncthreads();
+            }
             staged_img = img;
         }
         const long long off = plane * P.quads;
@@ -477,9 +514,9 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
             if (LOSS && (ROWG || q_lo + u * kSpmThreads + (int)threadIdx.x < P.quads)) pv[u] = ldg_stream(lsrc + u * kSpmThreads);
         if (LOSS && unit + 1 < u_end) {
             // the next unit of this CTA is the next 16 KB in memory (planes are contiguous): pull it into L2 while this unit
-            // computes.  (Measured: 342 -> 267 us per 256 images together with the leaner phase B; holding the next unit in
-            // registers instead -- a software pipeline at 3 CTAs/SM -- was slower, 285-291 us: the kernel is bound by issue
-            // slots, not by load latency.)
+            // computes.  Measured alternatives, both SLOWER than this prefetch (252 us per 256 images): holding the next unit in
+            // a second register set (285-291 us at 3 CTAs/SM), and re-using pv for the next unit's loads right after phase A so
+            // that they fly during phase B (278 us: pv then lives across phase B and spills under the 64-register cap).
             const char* nsrc = reinterpret_cast<const char*>(L4 + off + min(q_lo + kSpmFusedChunk, P.quads));
             const char* lend = reinterpret_cast<const char*>(L4 + total_quads);
             if (threadIdx.x < kSpmFusedChunk * 16 / 128 && nsrc + threadIdx.x * 128 < lend) prefetch_l2(nsrc + threadIdx.x * 128);
@@ -490,26 +527,15 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
         unsigned cmask[kSpmFusedU];
         float4* gdst = GRAD ? G4 + off + q_lo + threadIdx.x : nullptr;
         float4* tdst = WTGT ? T4 + off + q_lo + threadIdx.x : nullptr;
-        // phase A.  ROWG: with wpr = qpr/32 the word index is simply the warp's group index inside the plane
         unsigned anyc = 0u;
+        if (ROWG) {
+            // phase A, uniform: EVERY quad is treated as uncovered (zero target, zero mask: the loss term is 0 unless the logit
+            // is NaN -- sigmoid(p)*0 and tanh(p)*0 are 0 for every other p -- and dlogits = 0); phase B then overwrites the
+            // pixels of the covered quads (ordered after these stores by its __syncwarp; a NaN counted twice is still a NaN).
+            // The warp's coverage mask is one broadcast LDS: with wpr = qpr/32 the word index is the warp's group index in the
+            // plane.  No per-lane look-up, no ballot, no branch on the stream.
 #pragma unroll
-        for (int u = 0; u < kSpmFusedU; ++u) {
-            bool valid = true, covered = false;
-            if (ROWG) {
-                cmask[u] = covq_s[(q_lo >> 5) + u * (kSpmThreads / 32) + wid];
-                covered = (cmask[u] >> lane) & 1u;
-            } else {
-                const int qu = q_lo + u * kSpmThreads + (int)threadIdx.x;
-                valid = qu < P.quads;
-                if (valid) {
-                    const int row = (int)fdiv((uint32_t)qu, P.div_qpr), cq = qu - row * qpr;
-                    covered = (covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u;
-                }
-                cmask[u] = __ballot_sync(FULL_MASK, covered);
-            }
-            if (cmask[u]) anyc |= 1u << u;
-            if (valid && !covered) {
-                // zero target, zero mask.  sigmoid(p)*0 and tanh(p)*0 are 0 for every non-NaN p; a NaN propagates
+            for (int u = 0; u < kSpmFusedU; ++u) {
                 if (LOSS) {
                     const float4 v = pv[u];
                     const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
@@ -517,6 +543,30 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 }
                 if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
                 if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
+                cmask[u] = covq_s[(q_lo >> 5) + u * (kSpmThreads / 32) + wid];
+            }
+            anyc = (cmask[0] ? 1u : 0u) | (cmask[1] ? 2u : 0u) | (cmask[2] ? 4u : 0u) | (cmask[3] ? 8u : 0u);
+        } else {
+#pragma unroll
+            for (int u = 0; u < kSpmFusedU; ++u) {
+                const int qu = q_lo + u * kSpmThreads + (int)threadIdx.x;
+                const bool valid = qu < P.quads;
+                bool covered = false;
+                if (valid) {
+                    const int row = (int)fdiv((uint32_t)qu, P.div_qpr), cq = qu - row * qpr;
+                    covered = (covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u;
+                }
+                cmask[u] = __ballot_sync(FULL_MASK, covered);
+                if (cmask[u]) anyc |= 1u << u;
+                if (valid && !covered) {
+                    if (LOSS) {
+                        const float4 v = pv[u];
+                        const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+                        if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
+                    }
+                    if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
+                    if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
+                }
             }
         }
         // phase B: one pixel of a covered quad per lane, only for the warp instructions that have covered quads.  Deliberately
@@ -541,9 +591,24 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 float pe = 0.0f;
                 if (LOSS) pe = __ldg(P.logits + ei);
                 const int row = (int)fdiv((uint32_t)qs, P.div_qpr), col = (qs - row * qpr) * 4 + e;
-                float t0, te;
-                spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
-                const bool mk = t0 > 0.0f;
+                float t0 = 0.0f, te = 0.0f;
+                bool mk;
+                unsigned int code = 127u;
+                if (MAP && disp) code = map_s[row * P.R + col];
+                if (ROWG && MAP && disp && code == 0u) continue;      // slack pixel of a covered quad: phase A's zeros stand
+                if (MAP && disp && (code & 127u) != 127u) {
+                    mk = code >> 7;
+                    if (code & 127u) {
+                        const int2 jv = s_j[((int)(code & 127u) - 1) * P.K + jn];
+                        if (!(jv.x <= 0 && jv.y <= 0)) {
+                            const int dd = axis ? jv.y - row : jv.x - col;
+                            te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
+                        }
+                    }
+                } else {
+                    spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
+                    mk = t0 > 0.0f;
+                }
                 float ge = 0.0f;
                 if (!LOSS) {
                     if (!disp) te = t0;
