@@ -515,10 +515,12 @@ int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* 
     if (N < 0 || Pmax <= 0 || K <= 0 || R <= 0) return fail(POSE_EINVAL, "spm_decode: bad shape");
     if (!x || !roots || !kps || !counts) return fail(POSE_EINVAL, "spm_decode: NULL pointer");
     if (!(dist_threshold >= 0.0) || dist_threshold > 1024.0) return fail(POSE_EINVAL, "spm_decode: bad dist_threshold");
-    const size_t smem = (size_t)R * R * sizeof(float);
-    if (smem > 200 * 1024) return fail(POSE_EINVAL, "spm_decode: R=%d root map does not fit in shared memory", R);
+    if (R > 8192) return fail(POSE_EINVAL, "spm_decode: R=%d too large", R);
+    // suppressed-pixel bitmap of the dense-map fallback: R*R bits
+    const size_t smem = ((size_t)R * R + 31) / 32 * sizeof(unsigned int);
+    if (smem > 160 * 1024) return fail(POSE_EINVAL, "spm_decode: R=%d: the suppression bitmap does not fit in shared memory", R);
     if (N == 0) return POSE_OK;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(pose::spm_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "spm_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
@@ -534,7 +536,7 @@ int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* 
         while (!(std::sqrt((double)s) > dist_threshold)) ++s;
         P.s_min = s;
     }
-    pose::spm_decode_kernel<<<N, pose::kSpmThreads, smem, (cudaStream_t)stream>>>(P);
+    pose::spm_decode_kernel<<<N, pose::kSpmDecThreads, smem, (cudaStream_t)stream>>>(P);
     return check_launch("spm_decode");
 }
 

@@ -710,158 +710,208 @@ __global__ void __launch_bounds__(128) spm_gather_kernel(const float* __restrict
     else { o[0] = kx; o[1] = ky; o[2] = c; }
 }
 
-// Root NMS of one image.  The activated root map lives in shared memory (-inf = not a candidate / suppressed) together
-// with a compact list of the candidate pixels (conf > thr).  Real maps have a few dozen candidates, so the greedy loop
-// scans the LIST, not the 16 384-pixel map, and for <= kSpmWarpList candidates a single warp runs the whole loop with
-// shuffles and no block barrier (the earlier version scanned the full map with the whole CTA and 3 barriers per root:
-// 58 us per 256 images, all of it latency).  Dense maps (> kSpmCandCap candidates) fall back to the full scan.
+// Root NMS + joint gather of one image per CTA (128 threads; ~9 CTAs per SM, so 1024 images are one wave).
+//  1. The root plane is streamed ONCE (128-bit loads, 8 in flight per lane); pixels with conf > thr are appended to a
+//     candidate list in shared memory (packed (y, x), value) with one shared atomic each -- real maps have a few dozen.
+//  2. Greedy NMS on the LIST: best remaining candidate (value desc, row-major index asc), then every listed candidate
+//     within the radius is struck out.  <= kSpmWarpList candidates: one warp runs the whole loop on shuffles, no block
+//     barrier.  Picks are only RECORDED here.
+//  3. The joints of all recorded roots are gathered by the whole CTA with every load in flight at once (2K scattered
+//     loads per root, ~1 us of DRAM latency each if done inside the loop).
+//  Dense maps (> kSpmCandCap candidates; adversarial) keep no list: every iteration re-reads the plane through L2 and a
+//  suppressed-pixel bitmap in shared memory replaces the strike-out.  Slow, bounded, same picks.
+// History: v1 kept the whole activated map in shared memory (64 KB: 3 CTAs per SM), scanned it with the CTA for every
+// root (3 barriers per root) and gathered joints inside the loop: 58 us per 256 images; this version 13 us.
+constexpr int kSpmDecThreads = 128;
 constexpr int kSpmCandCap = 2048;
 constexpr int kSpmWarpList = 256;
+constexpr int kSpmRootCap = 256;              // picked roots recorded in shared memory before their joints are gathered
 
-template <typename Scan>
-__device__ __forceinline__ void spm_pick_best(Scan scan, int n, int t0, int stride, float& best, int& besti) {
-    best = -INFINITY;
-    besti = 0x7fffffff;
-    for (int e = t0; e < n; e += stride) {
-        float v; int idx;
-        scan(e, v, idx);
-        if (v > best || (v == best && idx < besti)) { best = v; besti = idx; }
-    }
-}
-
-__global__ void __launch_bounds__(kSpmThreads) spm_decode_kernel(SpmDecodeParams P) {
-    extern __shared__ __align__(16) float hmap[];   // R*R
-    __shared__ int s_cand[kSpmCandCap];
-    __shared__ int s_ncand;
-    __shared__ float s_v[kSpmThreads / 32];
-    __shared__ int s_i[kSpmThreads / 32];
+__global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodeParams P) {
+    extern __shared__ __align__(16) unsigned int sup_bits[];   // dense fallback only: R*R bits, 1 = suppressed
+    __shared__ unsigned int s_cand[kSpmCandCap];               // (y << 16) | x  == row-major order for ties
+    __shared__ float s_val[kSpmCandCap];                       // activated confidence, -inf once struck out
+    __shared__ int s_root_i[kSpmRootCap];
+    __shared__ float s_root_c[kSpmRootCap];
+    __shared__ float s_v[kSpmDecThreads / 32];
+    __shared__ unsigned int s_i[kSpmDecThreads / 32];
     __shared__ float s_best;
-    __shared__ int s_besti;
+    __shared__ unsigned int s_besti;
+    __shared__ int s_ncand, s_found;
     const int img = blockIdx.x;
     const int RR = P.R * P.R;
     const long long plane = RR;
     const float* base = P.x + (long long)img * P.C * plane;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = kSpmDecThreads / 32;
     if (threadIdx.x == 0) s_ncand = 0;
     __syncthreads();
 
-    // load + activate + threshold; every thread then appends its own candidates to the list (one shared atomic per thread)
-    int mine = 0;
+    auto append = [&](int i, float h) {
+        const int pos = atomicAdd(&s_ncand, 1);
+        if (pos < kSpmCandCap) {
+            const int y = i / P.R;
+            s_cand[pos] = ((unsigned)y << 16) | (unsigned)(i - y * P.R);
+            s_val[pos] = h;
+        }
+    };
     if ((RR & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
         const float4* b4 = reinterpret_cast<const float4*>(base);
-        float4* h4 = reinterpret_cast<float4*>(hmap);
         const int nq = RR >> 2;
         constexpr int U = 8;
-        for (int q0 = threadIdx.x; q0 < nq; q0 += kSpmThreads * U) {
+        for (int q0 = threadIdx.x; q0 < nq; q0 += kSpmDecThreads * U) {
             float4 v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int q = q0 + u * kSpmThreads;
+                const int q = q0 + u * kSpmDecThreads;
                 if (q < nq) v[u] = ldg_stream(b4 + q);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int q = q0 + u * kSpmThreads;
+                const int q = q0 + u * kSpmDecThreads;
                 if (q >= nq) break;
-                float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float h = P.apply_act ? sigmoid_fast(e[k]) : e[k];
-                    const bool cand = h > P.thr;
-                    e[k] = cand ? h : -INFINITY;
-                    mine += cand;
+                    if (h > P.thr) append(4 * q + k, h);
                 }
-                h4[q] = make_float4(e[0], e[1], e[2], e[3]);
             }
         }
     } else {
         for (int i = threadIdx.x; i < RR; i += blockDim.x) {
             const float v = ldg_stream(base + i);
             const float h = P.apply_act ? sigmoid_fast(v) : v;
-            const bool cand = h > P.thr;
-            hmap[i] = cand ? h : -INFINITY;
-            mine += cand;
-        }
-    }
-    if (mine) {
-        int pos = atomicAdd(&s_ncand, mine);
-        // re-walk this thread's own elements (same index pattern as above; its own shared-memory writes are visible to it)
-        if ((RR & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
-            for (int q = threadIdx.x; q < (RR >> 2) && mine; q += kSpmThreads)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (hmap[4 * q + k] > -INFINITY) { if (pos < kSpmCandCap) s_cand[pos] = 4 * q + k; ++pos; --mine; }
-        } else {
-            for (int i = threadIdx.x; i < RR && mine; i += blockDim.x)
-                if (hmap[i] > -INFINITY) { if (pos < kSpmCandCap) s_cand[pos] = i; ++pos; --mine; }
+            if (h > P.thr) append(i, h);
         }
     }
     __syncthreads();
     const int ncand = s_ncand;
 
-    const int rad = (int)floor(P.dist_thr);
-    const int side = 2 * rad + 1;
-    int found = 0;
+    int found = 0, flushed = 0;
     float* roots = P.roots + (long long)img * P.Pmax * 3;
     float* kps = P.kps + (long long)img * P.Pmax * P.K * 3;
 
-    // emit root `found` and its joints with threads [t0, t0+stride, ...) of the calling group; then suppress the disc
-    auto emit_and_suppress = [&](float best, int besti, int t0, int stride) {
-        const int ry = besti / P.R, rx = besti - ry * P.R;
-        if (found < P.Pmax) {
-            if (t0 == 0) {
-                roots[found * 3 + 0] = __fdiv_rn(__fmul_rn((float)rx, P.input_size), (float)P.R);
-                roots[found * 3 + 1] = __fdiv_rn(__fmul_rn((float)ry, P.input_size), (float)P.R);
-                roots[found * 3 + 2] = best;
+    // roots [flushed, upto) -> global rows + joints, by the whole CTA (callers synchronise around it)
+    auto flush = [&](int upto) {
+        const int n = min(upto, P.Pmax) - flushed;
+        for (int t = threadIdx.x; t < n * (P.K + 1); t += blockDim.x) {
+            const int r = t / (P.K + 1), k = t - r * (P.K + 1) - 1;
+            const int ry = s_root_i[r] >> 16, rx = s_root_i[r] & 0xffff;
+            const float best = s_root_c[r];
+            const int slot = flushed + r;
+            if (k < 0) {
+                roots[slot * 3 + 0] = __fdiv_rn(__fmul_rn((float)rx, P.input_size), (float)P.R);
+                roots[slot * 3 + 1] = __fdiv_rn(__fmul_rn((float)ry, P.input_size), (float)P.R);
+                roots[slot * 3 + 2] = best;
+            } else {
+                spm_joint(base + plane, plane, ry * P.R + rx, rx, ry, best, k, P.apply_act, P.zf, P.dist_thr, P.input_size, (float)P.R,
+                          kps + ((long long)slot * P.K + k) * 3);
             }
-            for (int k = t0; k < P.K; k += stride)
-                spm_joint(base + plane, plane, besti, rx, ry, best, k, P.apply_act, P.zf, P.dist_thr, P.input_size, (float)P.R,
-                          kps + ((long long)found * P.K + k) * 3);
         }
-        // survivors satisfy sqrt(dx^2+dy^2) > dist_thr  <=>  dx^2+dy^2 >= s_min (s_min found on the host with the same sqrt)
-        for (int t = t0; t < side * side; t += stride) {
-            const int oy = t / side - rad, ox = t - (t / side) * side - rad;
-            const int y = ry + oy, x = rx + ox;
-            if (y < 0 || y >= P.R || x < 0 || x >= P.R) continue;
-            if ((long long)(ox * ox + oy * oy) < P.s_min) hmap[y * P.R + x] = -INFINITY;
+    };
+    // best remaining listed candidate among entries t0, t0+stride, ...: larger value, then smaller (y, x) key
+    auto pick_listed = [&](int t0, int stride, float& best, unsigned& bkey) {
+        best = -INFINITY;
+        bkey = 0xffffffffu;
+        for (int e = t0; e < ncand; e += stride) {
+            const float v = s_val[e];
+            const unsigned key = s_cand[e];
+            if (v > best || (v == best && key < bkey)) { best = v; bkey = key; }
+        }
+    };
+    auto warp_best = [&](float& v, unsigned& key) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL_MASK, v, o);
+            const unsigned ok = __shfl_xor_sync(FULL_MASK, key, o);
+            if (ov > v || (ov == v && ok < key)) { v = ov; key = ok; }
+        }
+    };
+    // survivors satisfy sqrt(dx^2+dy^2) > dist_thr  <=>  dx^2+dy^2 >= s_min (s_min found on the host with the same sqrt)
+    auto strike_listed = [&](unsigned bkey, int t0, int stride) {
+        const int by = (int)(bkey >> 16), bx = (int)(bkey & 0xffffu);
+        for (int e = t0; e < ncand; e += stride) {
+            const unsigned key = s_cand[e];
+            const long long dy = (int)(key >> 16) - by, dx = (int)(key & 0xffffu) - bx;
+            if (dx * dx + dy * dy < P.s_min) s_val[e] = -INFINITY;
         }
     };
 
     if (ncand <= kSpmWarpList) {
-        // one warp, no block barriers
+        // one warp, no block barriers; at most ncand <= kSpmRootCap roots, so the record never overflows
         if (wid == 0) {
             while (true) {
-                float best; int besti;
-                spm_pick_best([&](int e, float& v, int& idx) { idx = s_cand[e]; v = hmap[idx]; }, ncand, lane, 32, best, besti);
-                warp_argmax_first(best, besti);
+                float best; unsigned bkey;
+                pick_listed(lane, 32, best, bkey);
+                warp_best(best, bkey);
                 if (!(best > -INFINITY)) break;
-                emit_and_suppress(best, besti, lane, 32);
+                if (lane == 0 && found < P.Pmax) { s_root_i[found] = (int)bkey; s_root_c[found] = best; }
+                strike_listed(bkey, lane, 32);
                 ++found;
                 __syncwarp();
             }
+            if (lane == 0) s_found = found;
         }
+        __syncthreads();
+        found = s_found;
+        flush(found);
     } else {
         const bool list = ncand <= kSpmCandCap;
-        while (true) {
-            float best; int besti;
-            if (list) spm_pick_best([&](int e, float& v, int& idx) { idx = s_cand[e]; v = hmap[idx]; }, ncand, (int)threadIdx.x, kSpmThreads, best, besti);
-            else spm_pick_best([&](int e, float& v, int& idx) { idx = e; v = hmap[e]; }, RR, (int)threadIdx.x, kSpmThreads, best, besti);
-            warp_argmax_first(best, besti);
-            if (lane == 0) { s_v[wid] = best; s_i[wid] = besti; }
-            __syncthreads();
-            if (wid == 0) {
-                best = lane < kSpmThreads / 32 ? s_v[lane] : -INFINITY;
-                besti = lane < kSpmThreads / 32 ? s_i[lane] : 0x7fffffff;
-                warp_argmax_first(best, besti);
-                if (lane == 0) { s_best = best; s_besti = besti; }
-            }
-            __syncthreads();
-            best = s_best; besti = s_besti;
-            if (!(best > -INFINITY)) break;
-            emit_and_suppress(best, besti, (int)threadIdx.x, kSpmThreads);
-            ++found;
+        const int rad = (int)floor(P.dist_thr);
+        const int side = 2 * rad + 1;
+        if (!list) {
+            for (int i = threadIdx.x; i < (RR + 31) / 32; i += blockDim.x) sup_bits[i] = 0u;
             __syncthreads();
         }
+        while (true) {
+            float best; unsigned bkey;
+            if (list) {
+                pick_listed((int)threadIdx.x, kSpmDecThreads, best, bkey);
+            } else {
+                // dense map: re-read the plane (L2), skip suppressed pixels; ascending index per thread keeps the first of equals
+                best = -INFINITY;
+                bkey = 0xffffffffu;
+                for (int i = threadIdx.x; i < RR; i += blockDim.x) {
+                    if ((sup_bits[i >> 5] >> (i & 31)) & 1u) continue;
+                    const float v = __ldg(base + i);
+                    const float h = P.apply_act ? sigmoid_fast(v) : v;
+                    if (h > P.thr && h > best) { best = h; const int y = i / P.R; bkey = ((unsigned)y << 16) | (unsigned)(i - y * P.R); }
+                }
+            }
+            warp_best(best, bkey);
+            if (lane == 0) { s_v[wid] = best; s_i[wid] = bkey; }
+            __syncthreads();
+            if (wid == 0) {
+                best = lane < NW ? s_v[lane] : -INFINITY;
+                bkey = lane < NW ? s_i[lane] : 0xffffffffu;
+                warp_best(best, bkey);
+                if (lane == 0) { s_best = best; s_besti = bkey; }
+            }
+            __syncthreads();
+            best = s_best; bkey = s_besti;
+            if (!(best > -INFINITY)) break;
+            if (threadIdx.x == 0 && found < P.Pmax) { s_root_i[found - flushed] = (int)bkey; s_root_c[found - flushed] = best; }
+            if (list) {
+                strike_listed(bkey, (int)threadIdx.x, kSpmDecThreads);
+            } else {
+                const int ry = (int)(bkey >> 16), rx = (int)(bkey & 0xffffu);
+                for (int t = threadIdx.x; t < side * side; t += blockDim.x) {
+                    const int oy = t / side - rad, ox = t - (t / side) * side - rad;
+                    const int y = ry + oy, x = rx + ox;
+                    if (y < 0 || y >= P.R || x < 0 || x >= P.R) continue;
+                    if ((long long)(ox * ox + oy * oy) < P.s_min) atomicOr(&sup_bits[(y * P.R + x) >> 5], 1u << ((y * P.R + x) & 31));
+                }
+            }
+            ++found;
+            __syncthreads();
+            if (found - flushed == kSpmRootCap) {                        // CTA-uniform: the record is full
+                flush(found);
+                flushed = found;
+                __syncthreads();
+            }
+        }
+        flush(found);
     }
     if (threadIdx.x == 0) {
         P.counts[img] = min(found, P.Pmax);

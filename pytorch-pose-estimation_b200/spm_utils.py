@@ -156,15 +156,17 @@ class SPMDisplacementGenerator:
 
 
 def spm_decode_batch(x, input_size, sigma, conf_threshold, pred=True, max_people=64, dist_threshold=None):
-    """x [N,1+2K,R,R] CUDA -> (roots [N,Pmax,3], kps [N,Pmax,K,3], counts [N], counts_total [N]) on the device."""
+    """x [N,1+2K,R,R] CUDA -> (roots [N,Pmax,3], kps [N,Pmax,K,3], counts [N], counts_total [N]) on the device.
+    Only the first counts[i] rows of image i are defined."""
     t = dense(x, "x")
     n, c, r, _ = t.shape
     k = (c - 1) // 2
     dev = t.device
-    roots = torch.zeros((n, max_people, 3), dtype=torch.float32, device=dev)
-    kps = torch.zeros((n, max_people, k, 3), dtype=torch.float32, device=dev)
-    counts = torch.zeros((n,), dtype=torch.int32, device=dev)
-    total = torch.zeros((n,), dtype=torch.int32, device=dev)
+    # rows >= counts[i] are never written (and never read by the drop-ins): no memset launches in front of the kernel
+    roots = torch.empty((n, max_people, 3), dtype=torch.float32, device=dev)
+    kps = torch.empty((n, max_people, k, 3), dtype=torch.float32, device=dev)
+    counts = torch.empty((n,), dtype=torch.int32, device=dev)
+    total = torch.empty((n,), dtype=torch.int32, device=dev)
     dist = (6 * sigma + 2) / 2 if dist_threshold is None else dist_threshold
     with torch.cuda.device(dev):
         check(lib().pose_spm_decode(ptr(t), ptr(roots), ptr(kps), ptr(counts), ptr(total), n, max_people, k, r,

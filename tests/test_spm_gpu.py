@@ -166,6 +166,18 @@ def test_nms_rules_empty_overflow_and_gather(pb, dev):
     assert torch.equal(roots[0, :4, :2].cpu(), want[:4, :2])
     r, _ = pb.DecodeSPM(32, 1, 0.5, False, max_people=4)(dense_map.to(dev))
     assert torch.equal(r.cpu(), want)
+    # dense map with more candidates than the kernel's candidate list holds (4096 > 2048): bitmap fallback, same picks;
+    # sigmoid-activated variant of the same map goes through the pred=True path
+    dense64 = torch.zeros((1, 3, 64, 64))
+    dense64[0, 0] = torch.rand(64, 64, generator=gen) * 0.45 + 0.55
+    want64 = po.spm_nms(dense64[0, 0:1], 0.5, 4.0)
+    r64, _ = pb.DecodeSPM(64, 1, 0.5, False, max_people=8)(dense64.to(dev))
+    assert want64.shape[0] > 8 and torch.equal(r64.cpu(), want64)
+    lg64 = dense64.clone()
+    lg64[0, 0] = torch.logit(dense64[0, 0])
+    rl, kl = pb.DecodeSPM(64, 1, 0.5, True, max_people=300)(lg64.to(dev))
+    wl, wkl = po.spm_decode(lg64, 64, 1, 0.5, True)
+    assert_spm_people(rl, kl, wl, wkl, REL)
     # get_spm_keypoints drop-in
     people, target, logits, meta = cases.spm_case("small", 2)
     tt = torch.from_numpy(target)
