@@ -276,3 +276,36 @@ def gather_rows_ragged(rows, score, image_ids, category_ids, group=None):
     r, s, i, c = gather_rows(rows, score, image_ids, category_ids, group)
     keep = torch.cat([torch.arange(m, device=r.device) < sz for sz in sizes])
     return r[keep], s[keep], i[keep], c[keep]
+
+
+def gather_spm_people(kps, counts, image_ids, category_ids, image_w, image_h, group=None):
+    """SPM predictions of the global batch: kps [B_local,Pmax,K,3] fp32 (first counts[i] rows of image i valid) + counts
+    [B_local] i32 + per-image ids / sizes [B_local] -> the same tensors with leading dimension B_global, in image order.
+
+    The number of persons per image is data dependent, so the fixed-size decode buffers are what travels (SURVEY.md 8 e):
+    ONE all-gather of [kps | counts, ids, sizes] per rank; every rank must use the same Pmax.  Shards may differ in size
+    by at most one image (shard_bounds): they are padded to the longest shard with count 0 and the padding is stripped.
+    """
+    if not _active(group):
+        return kps, counts, image_ids, category_ids, image_w, image_h
+    dev = kps.device
+    world = dist.get_world_size(group)
+    n = torch.tensor([kps.size(0)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s) for s in sizes]
+    m = max(sizes)
+    row = kps[0].numel() if kps.size(0) else int(kps.shape[1] * kps.shape[2] * kps.shape[3])
+    meta = torch.stack([counts.to(dev, torch.int64), image_ids.to(dev, torch.int64), category_ids.to(dev, torch.int64),
+                        image_w.to(dev, torch.int64), image_h.to(dev, torch.int64)], dim=1)          # [B,5]
+    send_k = kps.new_zeros((m, row))
+    send_k[:kps.size(0)] = kps.reshape(kps.size(0), -1)
+    send_m = meta.new_zeros((m, 5))
+    send_m[:meta.size(0)] = meta
+    out_k = kps.new_empty((world * m, row))
+    out_m = meta.new_empty((world * m, 5))
+    dist.all_gather_into_tensor(out_k, send_k, group=group)
+    dist.all_gather_into_tensor(out_m, send_m, group=group)
+    keep = torch.cat([torch.arange(m, device=dev) < sz for sz in sizes])
+    out_k, out_m = out_k[keep], out_m[keep]
+    return (out_k.view(-1, *kps.shape[1:]), out_m[:, 0].to(torch.int32), out_m[:, 1], out_m[:, 2], out_m[:, 3], out_m[:, 4])

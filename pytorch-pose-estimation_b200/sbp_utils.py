@@ -184,11 +184,15 @@ class SBPmAPCOCO:
 
     _pad = 0
 
-    def __init__(self, json_path, input_size, conf_threshold):
+    def __init__(self, json_path, input_size, conf_threshold, gather=False):
+        """`gather=True` (not in the reference): under torch.distributed every rank's rows are all-gathered in
+        `update_state`, so each rank's `result_list` covers the whole validation set -- the reference lets every rank
+        write its own shard to the same ./results.json (utils/sbp_utils.py:167-169)."""
         self.coco = _load_coco(json_path)
         self.input_size = input_size
         self.decoder = DecodeSBP(input_size, conf_threshold, True)
         self.result_list = []
+        self.gather = gather
 
     def reset_states(self):
         self.result_list = []
@@ -196,7 +200,15 @@ class SBPmAPCOCO:
     def update_state(self, target, y_pred):
         joints = self.decoder.decode_batch(y_pred)                       # [B,K,3] at input scale
         packed = backproject_packed(joints, target['bbox'], self.input_size)
-        self.result_list.extend(packed_to_results(packed, target['image_id'], target['category_id'], self._pad))
+        iid, cid = target['image_id'], target['category_id']
+        if self.gather:
+            from . import dist as pd
+            k = joints.size(1)
+            dev = packed.device
+            rows, score, iid, cid = pd.gather_rows_ragged(packed[:, :3 * k].unflatten(1, (k, 3)), packed[:, 3 * k],
+                                                          torch.as_tensor(iid).to(dev), torch.as_tensor(cid).to(dev))
+            packed = torch.cat([rows.flatten(1), score[:, None]], dim=1)
+        self.result_list.extend(packed_to_results(packed, iid, cid, self._pad))
 
     def result(self):
         if self.coco is None:

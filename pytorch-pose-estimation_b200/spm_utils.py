@@ -265,23 +265,37 @@ def spm_rows_to_results(kps, counts, image_sizes, image_ids, category_ids, input
 class SPMmAPCOCO:
     """Drop-in for utils/spm_utils.py:282-351 (batched `update_state`; `result()` needs pycocotools)."""
 
-    def __init__(self, json_path, input_size, sigma, conf_threshold, max_people=64):
+    def __init__(self, json_path, input_size, sigma, conf_threshold, max_people=64, gather=False):
+        """`gather=True` (not in the reference): under torch.distributed every rank's people are all-gathered in
+        `update_state` (fixed-size [B,Pmax,K,3] rows + counts), so each rank's `result_list` covers the whole set."""
         self.coco = _load_coco(json_path)
         self.input_size = input_size
         self.conf_threshold = conf_threshold
         self.decoder = DecodeSPM(input_size, sigma, conf_threshold, True, max_people)
         self.result_list = []
+        self.gather = gather
 
     def reset_states(self):
         self.result_list = []
 
     def update_state(self, target, y_pred):
         _, kps, counts, total = self.decoder.decode_batch(y_pred)
-        if int(total.max()) > self.decoder.max_people:
-            self.decoder.max_people = int(total.max())
+        need = total.max() if total.numel() else total.new_zeros(())
+        if self.gather:
+            from . import dist as pd
+            if pd._active(None):                          # every rank must gather with the same Pmax
+                need = need.clone()
+                pd.dist.all_reduce(need, op=pd.dist.ReduceOp.MAX)
+        if int(need) > self.decoder.max_people:
+            self.decoder.max_people = int(need)
             _, kps, counts, total = self.decoder.decode_batch(y_pred)
-        self.result_list.extend(spm_rows_to_results(kps, counts, target['image_size'], target['image_id'],
-                                                    target['category_id'], self.input_size))
+        sizes, iid, cid = target['image_size'], target['image_id'], target['category_id']
+        if self.gather:
+            dev = kps.device
+            kps, counts, iid, cid, w, h = pd.gather_spm_people(kps, counts, torch.as_tensor(iid).to(dev), torch.as_tensor(cid).to(dev),
+                                                               torch.as_tensor(sizes[0]).to(dev), torch.as_tensor(sizes[1]).to(dev))
+            sizes = [w, h]
+        self.result_list.extend(spm_rows_to_results(kps, counts, sizes, iid, cid, self.input_size))
 
     def result(self):
         if not self.result_list:

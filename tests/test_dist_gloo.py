@@ -75,3 +75,49 @@ def test_shard_bounds_cover_and_balance():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_bounds(4, 2, 2)
+
+
+def _spm_worker(rank, world, port, batch, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pose_b200 import dist as pd
+        g = torch.Generator().manual_seed(11)
+        pmax, k = 4, 3
+        kps = torch.rand((batch, pmax, k, 3), generator=g)
+        counts = torch.randint(0, pmax + 1, (batch,), generator=g, dtype=torch.int32)
+        iid, cid = torch.arange(batch) + 100, torch.ones(batch, dtype=torch.int64)
+        w, h = torch.arange(batch) + 640, torch.arange(batch) + 480
+        nums = torch.rand((batch, 2), generator=g, dtype=torch.float64)
+        lo, hi = pd.shard_bounds(batch, world, rank)
+        out = pd.gather_spm_people(kps[lo:hi], counts[lo:hi], iid[lo:hi], cid[lo:hi], w[lo:hi], h[lo:hi])
+        loss = pd.global_spm_loss(nums[lo:hi].sum(0), batch)
+        q.put((rank, [t.numpy() for t in out], float(loss)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [6, 5])
+def test_two_rank_spm_people_gather_and_loss(batch):
+    """SPM (SURVEY.md 8 e): fixed-size [B,Pmax,K,3] rows + counts travel in one all-gather, even and ragged shards."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_spm_worker, args=(r, world, port, batch, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(11)
+    kps = torch.rand((batch, 4, 3, 3), generator=g)
+    counts = torch.randint(0, 5, (batch,), generator=g, dtype=torch.int32)
+    nums = torch.rand((batch, 2), generator=g, dtype=torch.float64)
+    want_loss = float((nums[:, 0].sum() + 0.1 * nums[:, 1].sum()) / batch)
+    for rank, out, loss in got:
+        assert np.array_equal(out[0], kps.numpy()) and np.array_equal(out[1], counts.numpy())
+        assert np.array_equal(out[2], np.arange(batch) + 100) and np.array_equal(out[4], np.arange(batch) + 640)
+        assert np.array_equal(out[5], np.arange(batch) + 480) and out[1].dtype == np.int32
+        assert abs(loss - want_loss) <= 1e-6 * want_loss

@@ -136,3 +136,70 @@ def test_two_gpu_shards_match_single_gpu():
             l_it, rows_it = p[4][it]
             assert abs(l_it - ref["loss"].item()) <= 1e-6 * abs(ref["loss"].item())
             assert torch.equal(rows_it, ref["packed"].cpu())
+
+
+def _metric_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import pose_b200 as pb
+        from pose_b200 import dist as pd
+        logits, kp, bbox = _inputs(dev, b=13)                       # ragged shards: 7 + 6 images
+        b = logits.size(0)
+        lo, hi = pd.shard_bounds(b, world, rank)
+        m = pb.SBPmAPCOCO(None, (256, 192), 0.25, gather=True)
+        m.update_state({"bbox": bbox[lo:hi], "image_id": torch.arange(lo, hi) + 5, "category_id": torch.ones(hi - lo, dtype=torch.int64)},
+                       logits[lo:hi])
+        x, sizes = _spm_inputs(dev)
+        n = x.size(0)
+        lo2, hi2 = pd.shard_bounds(n, world, rank)
+        # max_people=2 on purpose: rank-local overflow must make EVERY rank redo the decode with the same Pmax
+        s = pb.SPMmAPCOCO(None, 512, 1, 0.5, max_people=2, gather=True)
+        s.update_state({"image_size": [sizes[0][lo2:hi2], sizes[1][lo2:hi2]], "image_id": torch.arange(lo2, hi2) + 9,
+                        "category_id": torch.ones(hi2 - lo2, dtype=torch.int64)}, x[lo2:hi2])
+        torch.cuda.synchronize()
+        q.put((rank, m.result_list, s.result_list))
+    finally:
+        dist.destroy_process_group()
+
+
+def _spm_inputs(dev, n=5):
+    """n images with 1..5 well separated root peaks each (logits), K=2 body joints."""
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.full((n, 5, 64, 64), -6.0)
+    x[:, 1:] = torch.randn(n, 4, 64, 64, generator=gen) * 0.5
+    for i in range(n):
+        for p in range(1 + i % 5):
+            x[i, 0, 8 + 11 * p, 10 + 9 * ((p + i) % 5)] = 2.0 + 0.1 * p + 0.01 * i
+    sizes = [torch.arange(n) * 10 + 600, torch.arange(n) * 7 + 400]
+    return x.to(dev), sizes
+
+
+def test_two_gpu_metric_gather_matches_single_gpu():
+    """SBPmAPCOCO / SPMmAPCOCO with gather=True: every rank ends up with the rows of the whole (ragged-sharded) set."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import pose_b200 as pb
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_metric_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    dev = torch.device("cuda", 0)
+    logits, kp, bbox = _inputs(dev, b=13)
+    m = pb.SBPmAPCOCO(None, (256, 192), 0.25)
+    m.update_state({"bbox": bbox, "image_id": torch.arange(13) + 5, "category_id": torch.ones(13, dtype=torch.int64)}, logits)
+    x, sizes = _spm_inputs(dev)
+    s = pb.SPMmAPCOCO(None, 512, 1, 0.5)
+    s.update_state({"image_size": sizes, "image_id": torch.arange(x.size(0)) + 9, "category_id": torch.ones(x.size(0), dtype=torch.int64)}, x)
+    assert len(m.result_list) == 13 and len(s.result_list) == sum(1 + i % 5 for i in range(5))
+    for rank, sbp_rows, spm_rows in got:
+        assert sbp_rows == m.result_list
+        assert spm_rows == s.result_list
