@@ -380,7 +380,8 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
         F.div_n = R <= 1024 ? 2 * R + 1 : 0;
         const size_t fsmem = pose::spm_fused_smem_bytes(F.div_n, R, K, F.wpr, lut_n);
         if (fsmem <= 200 * 1024) {
-            const long long funits = (long long)N * (1 + 2 * K) * ((quads + pose::kSpmFusedChunk - 1) / pose::kSpmFusedChunk);
+            const int fchunk = pose::kSpmThreads * pose::spm_fused_u(false, true);
+            const long long funits = (long long)N * (1 + 2 * K) * ((quads + fchunk - 1) / fchunk);
 #define POSE_SPMR(RG, MP)                                                                                                      \
     {                                                                                                                          \
         if (fsmem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<false, false, true, RG, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem); \
@@ -484,7 +485,8 @@ int pose_spm_fused(const float* logits, const long long* centers, const long lon
         P.gdisp = (float)((double)lambda_disp * inv_norm);
         const size_t smem = pose::spm_fused_smem_bytes(P.div_n, R, K, P.wpr, lut_n);
         if (smem > 200 * 1024) return fail(POSE_EINVAL, "spm_fused: R=%d K=%d needs %zu bytes of shared memory (use pose_spm_render + pose_spm_loss)", R, K, smem);
-        const long long units = (long long)N * (1 + 2 * K) * ((P.quads + pose::kSpmFusedChunk - 1) / pose::kSpmFusedChunk);
+        const int uchunk = pose::kSpmThreads * pose::spm_fused_u(grad, wtgt);
+        const long long units = (long long)N * (1 + 2 * K) * ((P.quads + uchunk - 1) / uchunk);
 #define POSE_SPMF3(G, T, RG, MP)                                                                                              \
     {                                                                                                                          \
         if (smem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<true, G, T, RG, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

@@ -342,8 +342,17 @@ struct __align__(16) SpmFusedPerson {
 #ifndef POSE_SPM_FUSED_MINB
 #define POSE_SPM_FUSED_MINB 4   // resident CTAs per SM the kernel is compiled for (register cap 64)
 #endif
-constexpr int kSpmFusedU = 4;
-constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;      // float4 per work unit (16 KB)
+// float4 per thread and unit (1, 2, 4 or 8: the unit must divide a 128x128 plane).  Variants that write a full-size stream
+// (dlogits or the target) run best with 16 KB units; the read-only loss variant with 32 KB units (more covered quads pooled
+// per phase B, twice the loads in flight): 139.6 -> 123.1 us per 256 images, while U = 8 costs the grad variant 234 -> 245 us.
+#ifndef POSE_SPM_FUSED_U
+#define POSE_SPM_FUSED_U 4
+#endif
+#ifndef POSE_SPM_FUSED_U_RO
+#define POSE_SPM_FUSED_U_RO 8
+#endif
+__host__ __device__ constexpr int spm_fused_u(bool grad, bool wtgt) { return (grad || wtgt) ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO; }
+constexpr int kSpmFusedUMax = POSE_SPM_FUSED_U > POSE_SPM_FUSED_U_RO ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
 constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
 
 constexpr int kSpmMapMaxBytes = 16384;                        // per-image pixel map (one byte per pixel): R <= 128
@@ -403,7 +412,9 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
     unsigned char* map_s = reinterpret_cast<unsigned char*>(lut_s + P.lut_n * P.lut_n);      // MAP only
     __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
     __shared__ double red[kSpmThreads / 32][2];
-    __shared__ unsigned char s_src[kSpmThreads / 32][32];
+    constexpr int kSpmFusedU = spm_fused_u(GRAD, WTGT);
+    constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;          // float4 per work unit
+    __shared__ unsigned char s_src[kSpmThreads / 32][32 * kSpmFusedU];
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
     for (int i = threadIdx.x; i < P.div_n; i += blockDim.x) div_s[i] = (double)(i - P.R) / P.z;
@@ -545,7 +556,8 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
                 cmask[u] = covq_s[(q_lo >> 5) + u * (kSpmThreads / 32) + wid];
             }
-            anyc = (cmask[0] ? 1u : 0u) | (cmask[1] ? 2u : 0u) | (cmask[2] ? 4u : 0u) | (cmask[3] ? 8u : 0u);
+#pragma unroll
+            for (int u = 0; u < kSpmFusedU; ++u) anyc |= cmask[u];
         } else {
 #pragma unroll
             for (int u = 0; u < kSpmFusedU; ++u) {
@@ -569,23 +581,26 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 }
             }
         }
-        // phase B: one pixel of a covered quad per lane, only for the warp instructions that have covered quads.  Deliberately
-        // NOT unrolled (the body is large: an unrolled copy per u made the kernel 113 KB of SASS and `no_instruction` the second
-        // largest stall).  The pixel's logit is re-read from L2 (the warp streamed it a moment ago) rather than shuffled out
-        // of pv[]: pv dies after phase A, which keeps the kernel inside 64 registers without spills.
-        while (anyc) {                                                   // warp-uniform
-            const int u = __ffs((int)anyc) - 1;
-            anyc &= anyc - 1u;
-            const unsigned cm = u == 0 ? cmask[0] : (u == 1 ? cmask[1] : (u == 2 ? cmask[2] : cmask[3]));
-            // slot k of the warp's scratch row = lane that owns the k-th covered quad
-            if ((cm >> lane) & 1u) s_src[wid][__popc(cm & ((1u << lane) - 1u))] = (unsigned char)lane;
-            __syncwarp();
-            const int total = __popc(cm) * 4;
-            const int qbase = q_lo + u * kSpmThreads + wid * 32;         // quad of lane 0
+        // phase B: one pixel of a covered quad per lane.  The covered quads of ALL the warp's instructions of this unit are
+        // pooled (slot k of the warp's scratch row = u*32 + lane of the k-th covered quad), so the long dependent chain below
+        // runs once per warp and unit with up to 32 useful lanes, not once per covered instruction with ~14.  Deliberately not
+        // unrolled over u (an unrolled copy per u made the kernel 113 KB of SASS and `no_instruction` the second largest
+        // stall).  The pixel's logit is re-read from L2 (the warp streamed it a moment ago) rather than shuffled out of pv[]:
+        // pv dies after phase A, which keeps the kernel inside 64 registers without spills.
+        if (anyc) {                                                      // warp-uniform
+            int nslot = 0;
+#pragma unroll
+            for (int u = 0; u < kSpmFusedU; ++u) {
+                if ((cmask[u] >> lane) & 1u) s_src[wid][nslot + __popc(cmask[u] & ((1u << lane) - 1u))] = (unsigned char)(u * 32 + lane);
+                nslot += __popc(cmask[u]);
+            }
+            __syncwarp();                                                // also orders phase A's zero stores before the overwrites
+            const int total = nslot * 4;
             for (int b = 0; b < total; b += 32) {
                 const int l = b + lane;
                 if (l >= total) continue;
-                const int qs = qbase + (int)s_src[wid][l >> 2];
+                const int sl = (int)s_src[wid][l >> 2];
+                const int qs = q_lo + (sl >> 5) * kSpmThreads + wid * 32 + (sl & 31);
                 const int e = l & 3;
                 const long long ei = (off + qs) * 4 + e;
                 float pe = 0.0f;
