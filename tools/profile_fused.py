@@ -20,6 +20,8 @@ kp[torch.rand(B, K, device=dev, generator=gen) >= 0.85] = -1
 for _ in range(4):
     if which == "fused":
         r = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0)
+    elif which == "val":          # validation step: loss + decode, no dlogits (read-only variant)
+        r = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=False, decode=True, conf_threshold=0.25, coord_scale=4.0)
     elif which == "decode":
         r = pb.decode_batch(logits, 0.25, 4.0, True)
     elif which == "dense":
