@@ -195,6 +195,42 @@ int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* 
 int pose_spm_gather(const float* roots, const float* disp, float* kps, int n_roots, int K, int R,
                     double dist_threshold, pose_stream_t stream);
 
+/* ---- OKS / AP -- the keypoint evaluation behind SBPmAPCOCO.result utils/sbp_utils.py:166-189, SPMmAPCOCO.result
+ *      utils/spm_utils.py:325-351 and SBPmAPPIS.result (utils/sbp_pis_utils.py), which the reference delegates to
+ *      pycocotools COCOeval(gt, dt, "keypoints").evaluate()/.accumulate() (third party, unpinned: PARITY UNPINNED).
+ * A group q = cat * n_images + img.  Detections [D] are sorted by (group, -score), at most max_det per group; ground
+ * truths [G] sorted by group in annotation order.  det_off / gt_off [Q+1] int32 prefix offsets; pair_off [Q+1] int64
+ * offsets of each group's D_q x G_q block in oks_out (row = detection).  All arithmetic is fp64.
+ *   det_kp [D][K][3], gt_kp [G][K][3] (x, y, v); gt_bbox [G][4] (x, y, w, h); gt_area [G]; sigmas [K] (K <= 32).
+ * pose_oks_matrix  = COCOeval.computeOks (+ the detection areas of COCO.loadRes -> det_area_out [D]). */
+int pose_oks_matrix(const double* det_kp, const double* gt_kp, const double* gt_bbox, const double* gt_area,
+                    const int* det_off, const int* gt_off, const long long* pair_off, const double* sigmas,
+                    double* oks_out, double* det_area_out, int Q, int D, int G, long long n_pairs, int K,
+                    pose_stream_t stream);
+
+/* pose_oks_match = COCOeval.evaluateImg for every (group, area range, OKS threshold).
+ *   gt_flags [G]: bit 0 = ignore (crowd or no labelled joint), bit 1 = iscrowd; area_rng [A][2]; iou_thrs [T].
+ *   dt_match [A][T][D] int32 (global ground-truth index + 1, 0 = unmatched); dt_ignore [A][T][D]; gt_ignore_out [A][G].
+ * workspace: pose_oks_match_workspace_bytes(A, T, G); contents need no initialisation. */
+unsigned long long pose_oks_match_workspace_bytes(int A, int T, int G);
+int pose_oks_match(const double* oks, const long long* pair_off, const int* det_off, const int* gt_off,
+                   const double* det_area, const double* gt_area, const unsigned char* gt_flags,
+                   const double* area_rng, const double* iou_thrs, int Q, int A, int T, int D, int G,
+                   int* dt_match, unsigned char* dt_ignore, unsigned char* gt_ignore_out,
+                   void* workspace, unsigned long long workspace_bytes, pose_stream_t stream);
+
+/* pose_ap_accumulate = COCOeval.accumulate (single max_det).
+ *   order [D] int64: detection indices sorted by (category, -score), stable, so that order[cat_det_off[c] ..
+ *   cat_det_off[c+1]) lists category c's detections by descending score; cat_det_off / cat_gt_off [C+1]; rec_thrs [R].
+ *   precision [T][R][C][A], recall [T][C][A] fp64, -1 where a category has no counted ground truth.
+ * workspace: pose_ap_accumulate_workspace_bytes(A, T, D), 8-byte aligned. */
+unsigned long long pose_ap_accumulate_workspace_bytes(int A, int T, int D);
+int pose_ap_accumulate(const long long* order, const int* dt_match, const unsigned char* dt_ignore,
+                       const unsigned char* gt_ignore, const int* cat_det_off, const int* cat_gt_off,
+                       const double* rec_thrs, int C, int A, int T, int R, int D, int G,
+                       double* precision, double* recall, void* workspace, unsigned long long workspace_bytes,
+                       pose_stream_t stream);
+
 /* ---- diagnostics -- exhaustive check that the device sigmoid used by decode is monotone
  * non-decreasing over all finite fp32 inputs (the INTERVAL decode mode relies on it).
  * violations_out [1] uint64 on device, zeroed by the call. */

@@ -8,12 +8,14 @@ hot-path modules:
     utils/spm_utils.py      -> pose_b200.spm_utils      (SPM*Generator, nms_spm, DecodeSPM, SPMmAPCOCO)
     models/loss/sbp_loss.py -> pose_b200.sbp_loss       (SBPLoss)
     models/loss/spm_loss.py -> pose_b200.spm_loss       (SPMLoss)
+    pycocotools COCOeval    -> pose_b200.coco_eval      (KeypointEval: OKS matching + AP behind the metric classes' result())
 
 All arithmetic runs in hand-written CUDA kernels behind the C ABI in include/pose_b200.h
 (libpose_b200.so, loaded with ctypes).  There is no CPU, PyTorch-op or Triton fallback: without the
 built library or without a CUDA device every entry point raises.
 """
 from ._cabi import LIB_PATH, PoseB200Error, launch_count, lib  # noqa: F401
+from .coco_eval import CocoKeypointsGT, KeypointEval  # noqa: F401
 from .sbp_loss import SBPLoss, sbp_fused  # noqa: F401
 from .sbp_pis_utils import SBPmAPPIS  # noqa: F401
 from .sbp_utils import (DecodeSBP, SBPHeatmapGenerator, SBPmAPCOCO, backproject_packed, backproject_rows, decode_batch,  # noqa: F401

@@ -42,6 +42,11 @@ SIGNATURES = {
     "pose_spm_decode_workspace_bytes": (_ull, [_i, _i]),
     "pose_spm_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _d, _i, _f, _vp, _ull, _vp]),
     "pose_spm_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp]),
+    "pose_oks_matrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _c.c_longlong, _i, _vp]),
+    "pose_oks_match_workspace_bytes": (_ull, [_i, _i, _i]),
+    "pose_oks_match": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _ull, _vp]),
+    "pose_ap_accumulate_workspace_bytes": (_ull, [_i, _i, _i]),
+    "pose_ap_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ull, _vp]),
     "pose_sigmoid_monotone_check": (_i, [_vp, _vp]),
 }
 

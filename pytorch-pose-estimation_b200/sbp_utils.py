@@ -180,7 +180,7 @@ def packed_to_results(packed, image_ids, category_ids, pad=0):
 
 class SBPmAPCOCO:
     """Drop-in for utils/sbp_utils.py:121-189.  `update_state` is batched on the device;
-    `result()` needs pycocotools exactly as the reference does (COCOeval is out of scope here)."""
+    `result()` evaluates OKS / AP with this package's own kernels (coco_eval.py) -- pycocotools is not needed."""
 
     _pad = 0
 
@@ -193,6 +193,8 @@ class SBPmAPCOCO:
         self.decoder = DecodeSBP(input_size, conf_threshold, True)
         self.result_list = []
         self.gather = gather
+        self._evaluator = None
+        self.stats = None
 
     def reset_states(self):
         self.result_list = []
@@ -211,24 +213,26 @@ class SBPmAPCOCO:
         self.result_list.extend(packed_to_results(packed, iid, cid, self._pad))
 
     def result(self):
-        if self.coco is None:
-            raise ImportError("SBPmAPCOCO.result() needs pycocotools (COCOeval); result_list holds the COCO rows")
-        from pycocotools.cocoeval import COCOeval
+        """AP at OKS 0.50 (`cocoEval.stats[1]`, utils/sbp_utils.py:189).  Writes ./results.json like the reference, then runs
+        the OKS / AP kernels (coco_eval.KeypointEval) instead of pycocotools; all ten numbers are kept in `self.stats`."""
         path = os.path.join(os.getcwd(), 'results.json')
         with open(path, "w") as f:
             json.dump(self.result_list, f, indent=4)
-        ev = COCOeval(self.coco, self.coco.loadRes(path), "keypoints")
-        ev.params.imgIds = sorted(self.coco.getImgIds())
-        ev.params.catIds = sorted(self.coco.getCatIds())
-        ev.evaluate()
-        ev.accumulate()
-        ev.summarize()
-        return ev.stats[1]
+        if not self.result_list:
+            raise IndexError("list index out of range")       # what COCO.loadRes raises on an empty results file
+        from .coco_eval import KeypointEval, summarize
+        if self.coco is None:
+            raise ValueError("result() needs the ground-truth annotations: pass json_path (or a parsed COCO dict)")
+        if self._evaluator is None:
+            self._evaluator = KeypointEval(self.coco)
+        out = self._evaluator.evaluate(self.result_list)
+        self.stats = summarize(out['precision'], out['recall'], verbose=True)
+        return self.stats[1]
 
 
 def _load_coco(json_path):
-    try:
-        from pycocotools.coco import COCO
-    except ImportError:
+    """The ground-truth annotations (`self.coco`): parsed here, no pycocotools needed."""
+    if json_path is None:            # rows only (tests, ranks that never call result())
         return None
-    return COCO(json_path)
+    from .coco_eval import CocoKeypointsGT
+    return CocoKeypointsGT(json_path)

@@ -263,7 +263,7 @@ def spm_rows_to_results(kps, counts, image_sizes, image_ids, category_ids, input
 
 
 class SPMmAPCOCO:
-    """Drop-in for utils/spm_utils.py:282-351 (batched `update_state`; `result()` needs pycocotools)."""
+    """Drop-in for utils/spm_utils.py:282-351 (batched `update_state`; `result()` runs the OKS / AP kernels of coco_eval.py)."""
 
     def __init__(self, json_path, input_size, sigma, conf_threshold, max_people=64, gather=False):
         """`gather=True` (not in the reference): under torch.distributed every rank's people are all-gathered in
@@ -274,6 +274,8 @@ class SPMmAPCOCO:
         self.decoder = DecodeSPM(input_size, sigma, conf_threshold, True, max_people)
         self.result_list = []
         self.gather = gather
+        self._evaluator = None
+        self.stats = None
 
     def reset_states(self):
         self.result_list = []
@@ -300,16 +302,14 @@ class SPMmAPCOCO:
     def result(self):
         if not self.result_list:
             return 0
-        if self.coco is None:
-            raise ImportError("SPMmAPCOCO.result() needs pycocotools (COCOeval); result_list holds the COCO rows")
-        from pycocotools.cocoeval import COCOeval
         path = os.path.join(os.getcwd(), 'results.json')
         with open(path, "w") as f:
             json.dump(self.result_list, f, indent=4)
-        ev = COCOeval(self.coco, self.coco.loadRes(path), "keypoints")
-        ev.params.imgIds = sorted(self.coco.getImgIds())
-        ev.params.catIds = sorted(self.coco.getCatIds())
-        ev.evaluate()
-        ev.accumulate()
-        ev.summarize()
-        return ev.stats[1]
+        from .coco_eval import KeypointEval, summarize
+        if self.coco is None:
+            raise ValueError("result() needs the ground-truth annotations: pass json_path (or a parsed COCO dict)")
+        if self._evaluator is None:
+            self._evaluator = KeypointEval(self.coco)
+        out = self._evaluator.evaluate(self.result_list)
+        self.stats = summarize(out['precision'], out['recall'], verbose=True)
+        return self.stats[1]
