@@ -151,6 +151,8 @@ class KeypointEval:
         ws = torch.empty(max(ws_m, ws_a, 8), dtype=torch.uint8, device=d)
         with torch.cuda.device(d):
             st = stream_ptr(d)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
             check(L.pose_oks_matrix(ptr(det_kp), ptr(self._gt_kp), ptr(self._gt_bbox), ptr(self._gt_area), ptr(t_det_off),
                                     ptr(self._gt_off), ptr(t_pair_off), ptr(self._sigmas), ptr(oks), ptr(det_area),
                                     Q, D, G, n_pairs, K, st), "pose_oks_matrix")
@@ -160,8 +162,9 @@ class KeypointEval:
             check(L.pose_ap_accumulate(ptr(t_order), ptr(dt_match), ptr(dt_ignore), ptr(gt_ignore), ptr(t_cat_det_off),
                                        ptr(self._cat_gt_off), ptr(self._rec_thrs), C, A, T, R, D, G, ptr(precision), ptr(recall),
                                        ptr(ws), ws.numel(), st), "pose_ap_accumulate")
+            ev1.record()
         prec, rec = precision.cpu().numpy()[..., None], recall.cpu().numpy()[..., None]     # trailing max_det axis, as COCOeval
-        return {'stats': summarize(prec, rec), 'precision': prec, 'recall': rec,
+        return {'stats': summarize(prec, rec), 'precision': prec, 'recall': rec, 'kernel_ms': ev0.elapsed_time(ev1),
                 'oks': oks[:n_pairs], 'pair_off': pair_off, 'det_off': det_off, 'det_src': src, 'det_area': det_area[:D],
                 'dt_match': dt_match[:, :, :D], 'dt_ignore': dt_ignore[:, :, :D], 'gt_ignore': gt_ignore[:, :G]}
 

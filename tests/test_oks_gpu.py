@@ -73,6 +73,25 @@ def test_matches_oracle_on_mixed_sets(pb, seed, n_images, max_people, n_cats, dp
     assert -1 <= got['stats'][1] <= 1
 
 
+def test_ground_truth_as_results_like_the_reference_script(pb):
+    """The reference's own check of its evaluation call (test_coco_keypoints_map.py:25-66): every ground-truth annotation
+    is submitted as a result with score 0.9.  With labelled, non-crowd people only, every number is 1 (medium / large
+    where such people exist); with crowd / unlabelled annotations mixed in, the oracle decides."""
+    rng = np.random.default_rng(5)
+    gts = []
+    for i in range(200):
+        for _ in range(int(rng.integers(1, 5))):
+            size = float(rng.choice([50, 90, 150, 240]))
+            gts.append(person(10 + i, len(gts) + 1, rng.uniform(size / 2, 600), rng.uniform(size / 2, 400), size,
+                              [int(v) for v in rng.choice([1, 2], 17)], rng=rng))
+    dts = [{'image_id': g['image_id'], 'category_id': g['category_id'], 'keypoints': g['keypoints'], 'score': float(0.9)} for g in gts]
+    got, _ = _compare(pb, gts, dts)
+    assert np.allclose(got['stats'], 1.0, rtol=1e-12)
+    gts2, _ = make_dataset(9, 80, 6)
+    dts2 = [{'image_id': g['image_id'], 'category_id': g['category_id'], 'keypoints': g['keypoints'], 'score': float(0.9)} for g in gts2]
+    _compare(pb, gts2, dts2)
+
+
 def test_score_ties_and_detection_src_order(pb):
     gts, dts = make_dataset(7, 25, 6, dets_per_image=(5, 25))
     for d in dts[::2]:

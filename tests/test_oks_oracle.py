@@ -40,6 +40,8 @@ def test_numpy_sum_order_is_what_the_kernel_restates():
 
 
 def test_perfect_detections_score_one():
+    """Same idea as the reference's own check of the evaluation call (test_coco_keypoints_map.py:25-66: the ground truth
+    submitted as results must score 1)."""
     gts = [person(1, 10, cx=100, cy=100, size=80), person(2, 11, cx=300, cy=200, size=120)]
     dts = [{'image_id': g['image_id'], 'category_id': 1, 'keypoints': list(g['keypoints']), 'score': 0.9} for g in gts]
     out = oo.evaluate(gts, dts)
