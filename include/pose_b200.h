@@ -141,6 +141,15 @@ int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W,
                     float conf_threshold, int apply_sigmoid, float coord_scale,
                     int refine, int mode, pose_stream_t stream);
 
+/* ---- SBP decode with flip-test averaging -- NOT in the reference (PARITY UNPINNED, opt-in).
+ * x, x_flip [N][K][H][W]: the maps of the image and of its horizontal mirror.  flip_perm [K] int32 (device): channel
+ * of x_flip holding joint k's mirrored map (left/right swap).  The decoded map is
+ *   heat[n][k][h][w] = 0.5 * (act(x[n][k][h][w]) + act(x_flip[n][flip_perm[k]][h][W-1-w]))
+ * evaluated on the fly; everything else (threshold, first-index tie-break, output rows, refine) as pose_sbp_decode. */
+int pose_sbp_decode_flip(const float* x, const float* x_flip, const int* flip_perm, float* joints,
+                         int N, int K, int H, int W, float conf_threshold, int apply_sigmoid,
+                         float coord_scale, int refine, pose_stream_t stream);
+
 /* ---- back-projection + COCO row fields -- SBPmAPCOCO.update_state utils/sbp_utils.py:141-163,
  *      SBPmAPPIS.update_state utils/sbp_pis_utils.py:23-45.
  * joints [N][K][3] (input-size scale, from decode); bbox [N][4] fp64 (x, y, w, h).

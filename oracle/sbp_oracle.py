@@ -194,6 +194,22 @@ def sbp_decode(x, input_w, conf_threshold, pred=True):
     return t
 
 
+def sbp_flip_average(x, x_flipped, flip_pairs, pred=True):
+    """PARITY UNPINNED (not in the reference).
+
+    Published Simple-Baselines flip test: the maps of the mirrored image are mirrored back (columns reversed), left /
+    right joints swapped, and averaged with the maps of the image: (h + flip_back(h_f)) * 0.5, in fp32.
+    x, x_flipped [B,K,H,W] -> post-activation averaged maps [B,K,H,W] (decode them with pred=False).
+    """
+    h = torch.sigmoid(x) if pred else x
+    hf = torch.sigmoid(x_flipped) if pred else x_flipped
+    perm = list(range(x.size(1)))
+    for a, b in flip_pairs:
+        perm[a], perm[b] = b, a
+    back = hf[:, perm].flip(-1)
+    return (h + back) * 0.5
+
+
 def sbp_refine_quarter(joints_px, heat):
     """PARITY UNPINNED (not in the reference).
 

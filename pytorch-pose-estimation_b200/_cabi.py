@@ -33,6 +33,7 @@ SIGNATURES = {
     "pose_loss_reduce": (_i, [_vp, _i, _c.c_longlong, _d, _d, _d, _vp, _vp, _vp]),
     "pose_scale_grad": (_i, [_vp, _vp, _ull, _vp]),
     "pose_sbp_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _f, _i, _i, _vp]),
+    "pose_sbp_decode_flip": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _f, _i, _vp]),
     "pose_sbp_backproject": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "pose_spm_render": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp]),
     "pose_spm_loss_workspace_bytes": (_ull, []),

@@ -346,6 +346,29 @@ int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W, f
     return check_launch("sbp_decode");
 }
 
+int pose_sbp_decode_flip(const float* x, const float* x_flip, const int* flip_perm, float* joints, int N, int K, int H, int W,
+                         float conf_threshold, int apply_sigmoid, float coord_scale, int refine, pose_stream_t stream) {
+    if (int rc = check_map_shape(N, K, H, W)) return rc;
+    if (N == 0) return POSE_OK;
+    if (!x || !x_flip || !flip_perm || !joints) return fail(POSE_EINVAL, "sbp_decode_flip: NULL pointer");
+    pose::SbpDecodeFlipParams P;
+    P.x = x; P.xf = x_flip; P.perm = flip_perm; P.joints = joints; P.thr = conf_threshold; P.scale = coord_scale;
+    P.n_maps = (long long)N * K; P.K = K; P.H = H; P.W = W; P.HW = H * W; P.divW = make_div(W); P.divK = make_div(K); P.refine = refine;
+    const bool vec = (W % 4 == 0) && aligned16(x) && aligned16(x_flip);
+    const long long ctas = (P.n_maps + pose::kSbpWarps - 1) / pose::kSbpWarps;
+    cudaStream_t st = (cudaStream_t)stream;
+#define POSE_DECF(V, S)                                                                                \
+    {                                                                                                  \
+        const int grid = persistent_grid(pose::sbp_decode_flip_kernel<V, S>, pose::kSbpThreads, 0, ctas); \
+        pose::sbp_decode_flip_kernel<V, S><<<grid, pose::kSbpThreads, 0, st>>>(P);                     \
+    }
+    const bool sig = apply_sigmoid != 0;
+    if (vec) { if (sig) POSE_DECF(4, true) else POSE_DECF(4, false) }
+    else { if (sig) POSE_DECF(1, true) else POSE_DECF(1, false) }
+#undef POSE_DECF
+    return check_launch("sbp_decode_flip");
+}
+
 int pose_sbp_backproject(const float* joints, const double* bbox, float* packed_out, int N, int K,
                          int input_h, int input_w, pose_stream_t stream) {
     if (N < 0 || K <= 0 || input_h <= 0 || input_w <= 0) return fail(POSE_EINVAL, "sbp_backproject: bad shape");

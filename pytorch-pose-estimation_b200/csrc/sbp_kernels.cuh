@@ -578,6 +578,85 @@ __global__ void __launch_bounds__(kSbpThreads) sbp_decode_kernel(SbpDecodeParams
     }
 }
 
+// ---------------------------------------------------------------- decode with flip-test averaging (NOT in the reference; opt-in)
+// heat[n,k,h,w] = 0.5 * (act(x[n,k,h,w]) + act(xf[n,perm[k],h,W-1-w])): the second forward pass saw the mirrored image, so
+// its maps are mirrored back (columns reversed) and left/right joints swapped (perm) before averaging -- the published
+// Simple-Baselines test-time rule.  Both maps stream through once; the averaged map is never materialised.
+struct SbpDecodeFlipParams {
+    const float* x;
+    const float* xf;
+    const int* perm;         // [K] channel of xf that holds joint k's mirrored map
+    float* joints;
+    float thr, scale;
+    long long n_maps; int K, H, W, HW; FastDiv divW, divK;
+    int refine;
+};
+
+template <int V, bool SIG>
+__global__ void __launch_bounds__(kSbpThreads) sbp_decode_flip_kernel(SbpDecodeFlipParams P) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * kSbpWarps + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kSbpWarps;
+    const int nvec = P.HW / V;
+    const int vec_per_row = P.W / V;             // V == 4 only when W % 4 == 0
+    constexpr int U = 4;
+
+    for (long long map = warp0; map < P.n_maps; map += nwarps) {
+        const long long n = map / P.K;
+        const int k = (int)(map - n * P.K);
+        const float* src = P.x + map * P.HW;
+        const float* srf = P.xf + (n * P.K + __ldg(P.perm + k)) * P.HW;
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        for (int base = lane; base < nvec; base += 32 * U) {
+            float xv[U][V], fv[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int vi = base + 32 * u;
+                if (vi < nvec) {
+                    const int row = (int)fdiv((uint32_t)(vi * V), P.divW);
+                    const int cv = vi - row * vec_per_row;                         // vector column inside the row
+                    Vec<V>::load(src, vi, xv[u]);
+                    Vec<V>::load(srf, row * vec_per_row + (vec_per_row - 1 - cv), fv[u]);     // mirrored chunk, reversed below
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int vi = base + 32 * u;
+                if (vi >= nvec) break;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float s = __fmul_rn(0.5f, __fadd_rn(act<SIG>(xv[u][j]), act<SIG>(fv[u][V - 1 - j])));
+                    if (s > best) { best = s; besti = vi * V + j; }
+                }
+            }
+        }
+        warp_argmax_first(best, besti);
+
+        if (lane == 0) {
+            float jx = -1.0f, jy = -1.0f, jc = -1.0f;
+            if (best > P.thr && besti != 0x7fffffff) {
+                const int row = (int)fdiv((uint32_t)besti, P.divW);
+                const int col = besti - row * P.W;
+                jx = (float)col; jy = (float)row; jc = best;
+                if (P.refine && col > 1 && col < P.W - 1 && row > 1 && row < P.H - 1) {
+                    auto heat = [&](int r, int c) {
+                        return __fmul_rn(0.5f, __fadd_rn(act<SIG>(__ldg(src + r * P.W + c)), act<SIG>(__ldg(srf + r * P.W + (P.W - 1 - c)))));
+                    };
+                    const float dx = heat(row, col + 1) - heat(row, col - 1);
+                    const float dy = heat(row + 1, col) - heat(row - 1, col);
+                    jx += dx > 0.0f ? 0.25f : (dx < 0.0f ? -0.25f : 0.0f);
+                    jy += dy > 0.0f ? 0.25f : (dy < 0.0f ? -0.25f : 0.0f);
+                }
+            }
+            float* jo = P.joints + map * 3;
+            jo[0] = __fmul_rn(jx, P.scale);
+            jo[1] = __fmul_rn(jy, P.scale);
+            jo[2] = jc;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- stand-alone back-projection (one warp per sample)
 __global__ void __launch_bounds__(256) sbp_backproject_kernel(const float* __restrict__ joints, const double* __restrict__ bbox,
                                                               float* __restrict__ packed, int N, int K, double in_h, double in_w) {

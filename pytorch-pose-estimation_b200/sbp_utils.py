@@ -101,13 +101,43 @@ class SBPHeatmapGenerator:
         return self.render_batch(kp)[0].cpu().numpy()
 
 
-def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False, refine=False, mode="direct"):
-    """[B,K,H,W] CUDA fp32 -> [B,K,3] (x*scale, y*scale, conf); undetected rows are (-scale,-scale,-1)."""
+COCO_FLIP_PAIRS = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]
+
+_perm_cache = {}
+
+
+def _flip_perm(flip_pairs, k, device):
+    """[K] int32 on `device`: channel of the mirrored pass that holds joint j (pairs swap, the rest stay)."""
+    key = (tuple(map(tuple, flip_pairs)), k, str(device))
+    t = _perm_cache.get(key)
+    if t is None:
+        perm = list(range(k))
+        for a, b in flip_pairs:
+            perm[a], perm[b] = b, a
+        t = _perm_cache[key] = torch.tensor(perm, dtype=torch.int32, device=device)
+    return t
+
+
+def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False, refine=False, mode="direct",
+                 flipped=None, flip_pairs=COCO_FLIP_PAIRS):
+    """[B,K,H,W] CUDA fp32 -> [B,K,3] (x*scale, y*scale, conf); undetected rows are (-scale,-scale,-1).
+
+    `flipped` (not in the reference, opt-in): the maps the network produced for the horizontally mirrored images; they
+    are mirrored back, left/right joints swapped (`flip_pairs`) and averaged with `heatmaps` inside the kernel."""
     x = dense(heatmaps, "heatmaps")
     assert x.dim() == 4
     b, k, h, w = x.shape
     out = torch.empty((b, k, 3), dtype=torch.float32, device=x.device)
     if b == 0:
+        return out
+    if flipped is not None:
+        xf = dense(flipped, "flipped")
+        assert xf.shape == x.shape and xf.device == x.device, "flipped must match heatmaps"
+        perm = _flip_perm(flip_pairs, k, x.device)
+        with torch.cuda.device(x.device):
+            check(lib().pose_sbp_decode_flip(ptr(x), ptr(xf), ptr(perm), ptr(out), b, k, h, w, float(conf_threshold),
+                                             int(bool(apply_sigmoid)), float(coord_scale), int(bool(refine)),
+                                             stream_ptr(x.device)), "pose_sbp_decode_flip")
         return out
     m = _cabi.DECODE_INTERVAL if mode == "interval" else _cabi.DECODE_DIRECT
     with torch.cuda.device(x.device):
@@ -124,20 +154,22 @@ def nms_sbp(heatmaps, conf_threshold=0.8):
 class DecodeSBP(nn.Module):
     """Drop-in for utils/sbp_utils.py:85-118 (same ctor / forward), plus `decode_batch` for B > 1."""
 
-    def __init__(self, input_size, conf_threshold, pred=True, refine=False, mode="direct"):
+    def __init__(self, input_size, conf_threshold, pred=True, refine=False, mode="direct", flip_pairs=COCO_FLIP_PAIRS):
         super().__init__()
         self.input_size = input_size[-1]
         self.conf_threshold = conf_threshold
         self.pred = pred
         self.refine = refine          # quarter-pixel refinement: NOT in the reference, default off
         self.mode = mode
+        self.flip_pairs = flip_pairs  # used only when the mirrored pass is handed to forward / decode_batch (flip test)
 
-    def decode_batch(self, x):
-        return decode_batch(x, self.conf_threshold, self.input_size / x.size(-1), self.pred, self.refine, self.mode)
+    def decode_batch(self, x, x_flipped=None):
+        return decode_batch(x, self.conf_threshold, self.input_size / x.size(-1), self.pred, self.refine, self.mode,
+                            flipped=x_flipped, flip_pairs=self.flip_pairs)
 
-    def forward(self, x):
+    def forward(self, x, x_flipped=None):
         assert x.size(0) == 1
-        return self.decode_batch(x)[0]
+        return self.decode_batch(x, x_flipped)[0]
 
 
 def backproject_packed(joints, bbox, input_size):

@@ -63,3 +63,23 @@ def test_spm_forms_agree(seed, res, k):
         roots, kps = po.spm_decode(tt[b:b + 1], res, 1, 0.99, False)
         found = {(int(r[0]), int(r[1])) for r in roots} if roots.dim() == 2 else set()
         assert found <= {(int(x), int(y)) for x, y in c[:, 0]}
+
+
+def test_flip_average_of_a_mirrored_copy_is_the_identity():
+    """PARITY UNPINNED helper: mirroring + swapping a prediction and averaging it back returns the prediction itself
+    ((h + h) * 0.5 is exact in fp32), so decode(flip-averaged) == decode(plain)."""
+    import torch
+    from oracle import sbp_oracle as so
+    torch.manual_seed(0)
+    x = torch.randn(3, 17, 64, 48)
+    pairs = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]
+    perm = list(range(17))
+    for a, b in pairs:
+        perm[a], perm[b] = b, a
+    xf = x[:, perm].flip(-1)
+    # (CPU torch.sigmoid is not bit-reproducible across memory positions -- vector body vs scalar tail -- hence 1e-6, not equality)
+    from helpers import allclose, assert_joints
+    assert allclose(so.sbp_flip_average(x, xf, pairs, True), torch.sigmoid(x), 1e-6)
+    assert_joints(so.sbp_decode(so.sbp_flip_average(x, xf, pairs, True), 192, 0.25, pred=False), so.sbp_decode(x, 192, 0.25, True), 1e-6)
+    h = torch.rand(2, 17, 8, 12)
+    assert torch.equal(so.sbp_flip_average(h, h[:, perm].flip(-1), pairs, False), h)          # without the activation it is exact

@@ -351,3 +351,41 @@ def test_full_size_fused_equals_staged_and_oracle_subset(pb, dev, big):
     assert allclose(tma["loss_num"], fused["loss_num"], 1e-12)
     other = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=False)["loss_num"]      # another variant: fp32 rounding differs
     assert allclose(other, fused["loss_num"], 1e-7)
+
+
+@pytest.mark.parametrize("shape", [(6, 17, 64, 48), (3, 11, 64, 48), (2, 17, 33, 27), (2, 5, 16, 20)])
+def test_flip_test_decode_unpinned(pb, dev, shape):
+    """PARITY UNPINNED: the reference has no flip test; checked against our restatement of the published rule
+    (oracle.sbp_oracle.sbp_flip_average) -- indices bit-exact, confidence 1e-5, including the refine option."""
+    b, k, h, w = shape
+    pairs = [[a, a + 1] for a in range(1, k - 1, 2)]
+    rng = np.random.default_rng(b * 1000 + k)
+    kp = np.stack([rng.uniform(3, w - 3, (b, k)), rng.uniform(3, h - 3, (b, k))], -1)
+    tgt = pb.SBPHeatmapGenerator([h, w], k, 2).render_batch(kp)
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.logit((tgt + 0.05 * torch.rand(tgt.shape, device=dev, generator=g)).clamp(1e-4, 1 - 1e-4))
+    # the mirrored pass: mirror + swap of a slightly different prediction
+    perm = list(range(k))
+    for a, c in pairs:
+        perm[a], perm[c] = c, a
+    x2 = torch.logit((tgt * 0.9 + 0.05 * torch.rand(tgt.shape, device=dev, generator=g)).clamp(1e-4, 1 - 1e-4))
+    xf = x2[:, perm].flip(-1).contiguous()
+    for pred in (True, False):
+        a_in, f_in = (x, xf) if pred else (torch.sigmoid(x), torch.sigmoid(xf))
+        heat = so.sbp_flip_average(a_in.cpu(), f_in.cpu(), pairs, pred)
+        want = so.sbp_decode(heat, 4 * w, 0.25, pred=False)
+        got = pb.decode_batch(a_in, 0.25, 4.0, pred, flipped=f_in, flip_pairs=pairs)
+        assert_joints(got, want, 1e-5)
+        base = so.sbp_decode(heat, w, 0.25, pred=False)
+        want_r = so.sbp_refine_quarter(base, heat)
+        got_r = pb.decode_batch(a_in, 0.25, 1.0, pred, refine=True, flipped=f_in, flip_pairs=pairs)
+        assert_joints(got_r, want_r, 1e-5)
+    # exact ties across the two passes (pred=False, dyadic values): first row-major index wins
+    t = torch.zeros(1, k, h, w, device=dev)
+    tf = torch.zeros(1, k, h, w, device=dev)
+    t[0, 0, 5, 7] = 0.5; tf[0, 0, 5, w - 1 - 7] = 0.5            # both passes agree -> 0.5
+    t[0, 0, 2, 3] = 1.0                                             # one pass only -> also 0.5, earlier index
+    got = pb.decode_batch(t, 0.25, 1.0, False, flipped=tf, flip_pairs=pairs).cpu()
+    assert got[0, 0].tolist() == [3.0, 2.0, 0.5]
+    mod = pb.DecodeSBP([4 * h, 4 * w], 0.25, True, flip_pairs=pairs)
+    assert torch.equal(mod(x[:1], xf[:1]), pb.decode_batch(x[:1], 0.25, 4.0, True, flipped=xf[:1], flip_pairs=pairs)[0])

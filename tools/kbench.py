@@ -125,6 +125,8 @@ def main():
         for mode in ("interval", "direct"):
             for src, tag in ((logits, "randn"), (realistic, "realistic")):
                 run(f"decode_{mode}_pred{int(pred)}_{tag}", lambda: pb.decode_batch(src, 0.25, 4.0, pred, mode=mode), map_bytes + 12)
+    xf = realistic.flip(-1).contiguous()
+    run("decode_flip_test_pred1_realistic", lambda: pb.decode_batch(realistic, 0.25, 4.0, True, flipped=xf), 2 * map_bytes + 12)
     run("decode_interval_pred0_target_thr.99", lambda: pb.decode_batch(target, 0.99, 4.0, False), map_bytes + 12)
     run("backproject_rows", lambda: pb.backproject_rows(joints, bbox, (256, 192)), 24)
 
