@@ -2,7 +2,7 @@
 """Headline benchmark: heatmaps/sec of the SBP hot path (render + loss + grad + decode) on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port), host cores
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port), all host cores
 
 One "step" = one pass of the hot path over one synthetic batch (BASELINE.json configs[1]: B=4096 per GPU,
 K=17, 64x48 fp32 heat maps, sigma 2, 256x192 input): fused render+loss+grad+decode kernel, back-projection /
@@ -102,57 +102,58 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_reference_pass(sample):
-    """The reference's CPU algorithm on `sample` images: per-sample render loop -> SBPLoss fwd+bwd -> per-sample
-    decode loop -> back-projection + COCO rows (utils/sbp_utils.py:33-53, :103-118, :131-164; models/loss/sbp_loss.py)."""
-    import numpy as np
-    import torch
+def make_cpu_pipeline(n, procs):
+    """The reference's CPU algorithm on `n` images per pass: per-sample render loop -> SBPLoss fwd+bwd -> per-sample
+    decode loop -> back-projection + COCO rows (utils/sbp_utils.py:33-53, :103-118, :131-164; models/loss/sbp_loss.py),
+    the per-sample loops spread over `procs` worker processes (oracle/cpu_pipeline.py)."""
     from oracle import sbp_oracle as so
-    kp, logits, bbox, iid, cid = sample
-    n = logits.size(0)
-    target = torch.from_numpy(np.stack([so.sbp_render_loop(kp[b], H, W, SIGMA) for b in range(n)]))
-    x = logits.detach().clone().requires_grad_(True)
-    loss = so.sbp_loss(x, target)
-    loss.backward()
-    joints = torch.stack([so.sbp_decode_loop(logits[b:b + 1], IN_W, THR, True) for b in range(n)])
-    rows = so.sbp_result_rows(so.sbp_backproject(joints, bbox, (IN_H, IN_W)), iid, cid)
-    return float(loss.detach()), len(rows)
+    from oracle.cpu_pipeline import ReferencePipeline
+    return ReferencePipeline(so.make_config1_inputs(n, K, H, W), H, W, SIGMA, IN_H, IN_W, THR, procs=procs)
 
 
-def make_cpu_sample(n):
-    from oracle import sbp_oracle as so
-    return so.make_config1_inputs(n, K, H, W)
+def ref_shape(args):
+    """(worker processes, images per pass) of the CPU arm: every usable core, at least 8 images per worker."""
+    from oracle.cpu_pipeline import usable_cores
+    cores = usable_cores()
+    procs = args.ref_procs if args.ref_procs > 0 else min(cores, 64)
+    n = args.ref_sample if args.ref_sample > 0 else max(64, 8 * procs)
+    return cores, procs, n
+
+
+def ref_sample_text(n, passes, procs, threads):
+    return (f"{n} images of the same workload x {passes} passes; oracle port of the reference's per-sample Python loops: render and "
+            f"decode over {procs} worker process(es), SBPLoss fwd+bwd on {threads} torch threads")
 
 
 def run_reference(args):
     """--impl reference: rank 0 times the oracle port (the reference is pure Python and cannot travel to the GPU box;
-    its CPU algorithm is restated in oracle/, pinned to it by tests/golden)."""
+    its CPU algorithm is restated in oracle/, pinned to it by tests/golden) on all the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count() or 1
+    cores, procs, n = ref_shape(args)
+    pipe = make_cpu_pipeline(n, procs)          # forks its workers before the parent's torch thread pool exists
     torch.set_num_threads(cores)
-    n = args.ref_sample
-    sample = make_cpu_sample(n)
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_reference_pass(sample)
+    warm = max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        pipe.run_pass()
     t0 = time.perf_counter()
     steps = max(1, min(args.steps, 20))
     for _ in range(steps):
-        cpu_reference_pass(sample)
+        pipe.run_pass()
     dt = (time.perf_counter() - t0) / steps
+    pipe.close()
     value = n * K / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"SBP 256x192: {K}x{H}x{W} heat maps, sigma {SIGMA}: render + JointsMSE fwd/bwd + decode + "
                                f"back-projection; bounded sample of {n} images per step (of the B=4096 workload)",
-                   "batch_per_step": n, "threads": torch.get_num_threads()},
+                   "batch_per_step": n, "threads": torch.get_num_threads(), "worker_processes": procs},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} images x {steps} steps, oracle port of the reference's per-sample Python loops, "
-                                   f"torch {torch.get_num_threads()} threads for the loss"},
+                         "sample": ref_sample_text(n, steps, procs, torch.get_num_threads())},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -169,6 +170,11 @@ def run_cuda(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_pipe = None
+    if world == 1 and not args.no_cpu_baseline:
+        # the CPU-baseline workers are forked now, before this process owns a CUDA context; they sleep until the GPU part is done
+        cpu_cores, cpu_procs, cpu_n = ref_shape(args)
+        cpu_pipe = make_cpu_pipeline(cpu_n, cpu_procs)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: pose_b200 has no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -345,24 +351,21 @@ def run_cuda(args):
             "gpu_launches": launches,
             "clocks": clk.summary(),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            sample = make_cpu_sample(args.ref_sample)
-            cpu_reference_pass(sample)
+        if cpu_pipe is not None:
+            torch.set_num_threads(cpu_cores)
+            cpu_pipe.run_pass()
             best = None
             t_start = time.perf_counter()
             passes = 0
             while passes < 3 or (time.perf_counter() - t_start < 10.0 and passes < 40):
                 t0 = time.perf_counter()
-                cpu_reference_pass(sample)
+                cpu_pipe.run_pass()
                 dt = time.perf_counter() - t0
                 best = dt if best is None else min(best, dt)
                 passes += 1
-            line["cpu_baseline"] = {"value": args.ref_sample * K / best, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.ref_sample} images of the same workload, best of {passes} passes; oracle port of "
-                                              f"the reference's per-sample loops (render, decode single-threaded Python; loss on "
-                                              f"{torch.get_num_threads()} torch threads)"}
+            cpu_pipe.close()
+            line["cpu_baseline"] = {"value": cpu_n * K / best, "unit": UNIT, "cores": cpu_cores, "kind": "port",
+                                    "sample": "best pass of: " + ref_sample_text(cpu_n, passes, cpu_procs, torch.get_num_threads())}
         _emit(json.dumps(line))
     if world > 1:
         # leave without tearing NCCL down: destroying a communicator whose collectives were captured in a CUDA graph
@@ -380,7 +383,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="images per GPU")
-    ap.add_argument("--ref-sample", type=int, default=64, help="images per CPU-baseline pass")
+    ap.add_argument("--ref-sample", type=int, default=0, help="images per CPU-baseline pass (0: max(64, 8 per worker process))")
+    ap.add_argument("--ref-procs", type=int, default=0, help="worker processes of the CPU arm (0: every usable core, 1: single process)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--defer", type=int, default=int(os.environ.get("POSE_B200_EXCHANGE_DEFER", "1")),
                     help="N>1, peer exchange: 1 = a step's wait kernel completes the PREVIOUS step's exchange (ranks may drift), 0 = lock-step")

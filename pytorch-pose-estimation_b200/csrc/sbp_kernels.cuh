@@ -26,6 +26,15 @@ namespace pose {
 #ifndef POSE_FUSED_MINB_NG
 #define POSE_FUSED_MINB_NG 4    // register cap 64
 #endif
+// Software-pipelined streaming loop of the render variants (0 = off): the map is cut into stages of PIPE 128-bit loads per lane and the
+// loads of stage i+1 -- across map boundaries too -- are issued before stage i is computed, so a warp always has PIPE..2*PIPE
+// loads in flight instead of alternating "load U, compute U".  Same registers as U = 2*PIPE.
+#ifndef POSE_FUSED_PIPE
+#define POSE_FUSED_PIPE 0
+#endif
+#ifndef POSE_FUSED_PIPE_NG
+#define POSE_FUSED_PIPE_NG 0
+#endif
 constexpr int kSbpThreads = 256;               // 8 warps per CTA
 constexpr int kSbpWarps = kSbpThreads / 32;
 constexpr int kMaxPartialBlocks = 148 * 16;    // upper bound on the persistent grid (workspace sizing)
@@ -227,6 +236,31 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
     }
 }
 
+// end of one map: flush the fp32 partials into fp64 (keeps the 2e8-term sum accurate and deterministic) and, when decoding,
+// reduce the lanes' argmax candidates and write the joint row
+template <bool DEC>
+__device__ __forceinline__ void finish_map(const SbpFusedParams& P, long long map, int lane, float apos, float aneg, float arem,
+                                           float best, int besti, double& dpos, double& dneg) {
+    dpos += (double)apos;
+    dneg += (double)aneg - (double)arem;
+    if (DEC) {
+        warp_argmax_first(best, besti);
+        if (lane == 0) {
+            float jx = -1.0f, jy = -1.0f, jc = -1.0f;
+            if (best > P.thr) {
+                const int row = (int)fdiv((uint32_t)besti, P.divW);
+                jx = (float)(besti - row * P.W);
+                jy = (float)row;
+                jc = best;
+            }
+            float* jo = P.joints + map * 3;
+            jo[0] = __fmul_rn(jx, P.scale);
+            jo[1] = __fmul_rn(jy, P.scale);
+            jo[2] = jc;
+        }
+    }
+}
+
 template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
 __global__ void __launch_bounds__(kSbpThreads, (GRAD || WTGT || TGT != 2) ? POSE_FUSED_MINB : POSE_FUSED_MINB_NG) sbp_fused_kernel(SbpFusedParams P) {
     extern __shared__ float lut_s[];
@@ -250,6 +284,59 @@ __global__ void __launch_bounds__(kSbpThreads, (GRAD || WTGT || TGT != 2) ? POSE
     double kx = -1.0, ky = -1.0;
     if (TGT == TGT_RENDER && warp0 < P.n_maps) load_kp(P.kp, P.kp_f64, warp0, kx, ky);
 
+    constexpr int PIPE = (V == 4 && TGT == TGT_RENDER) ? ((GRAD || WTGT) ? POSE_FUSED_PIPE : POSE_FUSED_PIPE_NG) : 0;
+    if constexpr (PIPE > 0) {
+        // (map, stage) items as one continuous stream per warp: a load cursor runs one stage ahead of the compute cursor
+        const int nstage = (nvec + 32 * PIPE - 1) / (32 * PIPE);
+        long long lmap = warp0, cmap = warp0;
+        int lst = 0, cst = 0;
+        float bufA[PIPE][V], bufB[PIPE][V];
+        Patch pt;
+        float apos = 0.0f, aneg = 0.0f, arem = 0.0f, best = -INFINITY;
+        int besti = 0x7fffffff;
+        auto issue = [&](float (&buf)[PIPE][V]) {
+            if (lmap < P.n_maps) {
+                const float* lg = P.logits + lmap * P.HW;
+#pragma unroll
+                for (int u = 0; u < PIPE; ++u) {
+                    const int vi = lane + 32 * (lst * PIPE + u);
+                    if (vi < nvec) Vec<V>::load(lg, vi, buf[u]);
+                }
+                if (++lst == nstage) { lst = 0; lmap += nwarps; }
+            }
+        };
+        auto compute = [&](float (&buf)[PIPE][V]) {
+            if (cst == 0) {
+                pt = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
+                if (cmap + nwarps < P.n_maps) load_kp(P.kp, P.kp_f64, cmap + nwarps, kx, ky);
+            }
+            float* dl = GRAD ? P.dlogits + cmap * P.HW : nullptr;
+            float* to = WTGT ? P.target_out + cmap * P.HW : nullptr;
+#pragma unroll
+            for (int u = 0; u < PIPE; ++u) {
+                const int vi = lane + 32 * (cst * PIPE + u);
+                if (vi >= nvec) break;
+                float g[V], tv[V];
+                render_loss_vec<V, GRAD, WTGT, DEC>(buf[u], g, tv, vi, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem,
+                                                    best, besti);
+                if (GRAD) Vec<V>::store(dl, vi, g);
+                if (WTGT) Vec<V>::store(to, vi, tv);
+            }
+            if (++cst == nstage) {
+                finish_map<DEC>(P, cmap, lane, apos, aneg, arem, best, besti, dpos, dneg);
+                apos = aneg = arem = 0.0f; best = -INFINITY; besti = 0x7fffffff;
+                cst = 0; cmap += nwarps;
+            }
+        };
+        issue(bufA);
+        while (cmap < P.n_maps) {
+            issue(bufB);
+            compute(bufA);
+            if (cmap >= P.n_maps) break;
+            issue(bufA);
+            compute(bufB);
+        }
+    } else
     for (long long map = warp0; map < P.n_maps; map += nwarps) {
         const float* lg = P.logits + map * P.HW;
         const float* tg = (TGT == TGT_DENSE) ? P.target_in + map * P.HW : nullptr;
@@ -294,26 +381,7 @@ __global__ void __launch_bounds__(kSbpThreads, (GRAD || WTGT || TGT != 2) ? POSE
                 if (WTGT) Vec<V>::store(to, vi, tv[u]);
             }
         }
-        // per-map flush of the fp32 partials into fp64 (keeps the 2e8-term sum accurate and deterministic)
-        dpos += (double)apos;
-        dneg += (double)aneg - (double)arem;
-
-        if (DEC) {
-            warp_argmax_first(best, besti);
-            if (lane == 0) {
-                float jx = -1.0f, jy = -1.0f, jc = -1.0f;
-                if (best > P.thr) {
-                    const int row = (int)fdiv((uint32_t)besti, P.divW);
-                    jx = (float)(besti - row * P.W);
-                    jy = (float)row;
-                    jc = best;
-                }
-                float* jo = P.joints + map * 3;
-                jo[0] = __fmul_rn(jx, P.scale);
-                jo[1] = __fmul_rn(jy, P.scale);
-                jo[2] = jc;
-            }
-        }
+        finish_map<DEC>(P, map, lane, apos, aneg, arem, best, besti, dpos, dneg);
     }
 
     dpos = warp_sum(dpos);

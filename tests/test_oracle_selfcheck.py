@@ -83,3 +83,18 @@ def test_flip_average_of_a_mirrored_copy_is_the_identity():
     assert_joints(so.sbp_decode(so.sbp_flip_average(x, xf, pairs, True), 192, 0.25, pred=False), so.sbp_decode(x, 192, 0.25, True), 1e-6)
     h = torch.rand(2, 17, 8, 12)
     assert torch.equal(so.sbp_flip_average(h, h[:, perm].flip(-1), pairs, False), h)          # without the activation it is exact
+
+
+def test_cpu_pipeline_serial_and_worker_processes_agree():
+    """bench.py's CPU arm: the forked-worker form computes exactly what the single-process loop form does."""
+    from oracle.cpu_pipeline import ReferencePipeline
+    sample = so.make_config1_inputs(6, 17, 64, 48)
+    one = ReferencePipeline(sample, 64, 48, 2, 256, 192, 0.25, procs=1)
+    two = ReferencePipeline(sample, 64, 48, 2, 256, 192, 0.25, procs=2)
+    try:
+        a, b = one.run_pass(), two.run_pass()
+    finally:
+        two.close()
+    assert a == b and a[1] == 6
+    want = so.sbp_loss(sample[1], torch.from_numpy(so.sbp_render(sample[0], 64, 48, 2)))
+    assert abs(a[0] - float(want)) <= 1e-6 * float(want)

@@ -23,20 +23,31 @@ TMA_VARIANTS = [(2, 8, 256), (3, 8, 256), (4, 8, 256), (3, 4, 256), (3, 16, 256)
                 (2, 8, 768), (2, 4, 768), (3, 4, 768)]
 
 
+# software-pipelined loop: (stage size for the grad kernel or 0, stage size for the read-only kernels or 0, resident CTAs per SM)
+PIPE_VARIANTS = [(2, 0, 3), (3, 0, 3), (4, 0, 3), (3, 0, 2), (6, 0, 2), (0, 2, 4), (0, 3, 4), (0, 3, 3), (0, 4, 3), (0, 6, 3), (0, 2, 5)]
+
+
 def build(which="all"):
     os.makedirs(OUT, exist_ok=True)
     procs = []
-    for u, m in (VARIANTS if which != "ng" else []):
+    for pg, pn, m in (PIPE_VARIANTS if which in ("all", "pipe") else []):
+        lib = os.path.join(OUT, f"libpose_pipe_g{pg}_n{pn}_m{m}.so")
+        knob = [f"-DPOSE_FUSED_PIPE={pg}", f"-DPOSE_FUSED_MINB={m}"] if pg else [f"-DPOSE_FUSED_PIPE_NG={pn}", f"-DPOSE_FUSED_MINB_NG={m}"]
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"] + knob + ["-o", lib, SRC]
+        procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    if which == "pipe":
+        which = "none"
+    for u, m in (VARIANTS if which == "all" else []):
         lib = os.path.join(OUT, f"libpose_u{u}_m{m}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                f"-DPOSE_FUSED_U={u}", f"-DPOSE_FUSED_MINB={m}", "-o", lib, SRC]
         procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for u, m in NG_VARIANTS:
+    for u, m in (NG_VARIANTS if which in ("all", "ng") else []):
         lib = os.path.join(OUT, f"libpose_ng_u{u}_m{m}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                f"-DPOSE_FUSED_U_NG={u}", f"-DPOSE_FUSED_MINB_NG={m}", "-o", lib, SRC]
         procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for st, w, tv in (TMA_VARIANTS if which != "ng" else []):
+    for st, w, tv in (TMA_VARIANTS if which == "all" else []):
         lib = os.path.join(OUT, f"libpose_tma_s{st}_w{w}_t{tv}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                f"-DPOSE_TMA_STAGES={st}", f"-DPOSE_TMA_WARPS={w}", f"-DPOSE_TMA_TILE_VEC={tv}", "-o", lib, SRC]
@@ -67,10 +78,19 @@ def run(reps, which="all"):
     res = {}
     ref = None
     jobs = []
-    if which != "ng":
+    if which == "pipe":
+        base = os.path.join(ROOT, "pytorch-pose-estimation_b200", "libpose_b200.so")
+        jobs += [("default[grad+decode]", base, 1 | 4), ("default[loss]", base, 0), ("default[loss+decode]", base, 4)]
+        for pg, pn, m in PIPE_VARIANTS:
+            lib = os.path.join(OUT, f"libpose_pipe_g{pg}_n{pn}_m{m}.so")
+            if pg:
+                jobs.append((f"PIPE{pg}_M{m}[grad+decode]", lib, 1 | 4))
+            else:
+                jobs += [(f"PIPE_NG{pn}_M{m}[loss]", lib, 0), (f"PIPE_NG{pn}_M{m}[loss+decode]", lib, 4)]
+    if which == "all":
         jobs += [(f"U{u}_M{m}", os.path.join(OUT, f"libpose_u{u}_m{m}.so"), 1 | 4) for u, m in VARIANTS]
         jobs += [(f"TMA_S{st}_W{w}_T{tv}", os.path.join(OUT, f"libpose_tma_s{st}_w{w}_t{tv}.so"), 1 | 4 | 8) for st, w, tv in TMA_VARIANTS]
-    for fl, tag in ((0, "loss"), (4, "loss+decode")):
+    for fl, tag in (((0, "loss"), (4, "loss+decode")) if which in ("all", "ng") else ()):
         jobs += [(f"NG[{tag}]_U{u}_M{m}", os.path.join(OUT, f"libpose_ng_u{u}_m{m}.so"), fl) for u, m in NG_VARIANTS]
     refs = {}
     for name, path, flags in jobs:
@@ -100,7 +120,7 @@ def run(reps, which="all"):
         ref = refs.setdefault(flags & 5, sig)
         nbytes = (24576 if flags & 1 else 12288) + 8 + (12 if flags & 4 else 0)
         res[name] = {"ms": min(ts), "GBps": nbytes * B * K / (min(ts) * 1e-3) / 1e9, "same_result": sig == ref}
-        print(f"{name:18s}: {min(ts)*1e3:7.1f} us  {res[name]['GBps']:7.1f} GB/s  same={sig == ref} {sig}", flush=True)
+        print(f"{name:30s}: {min(ts)*1e3:7.1f} us  {res[name]['GBps']:7.1f} GB/s  same={sig == ref} {sig}", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "tune_fused.json"), "w"), indent=1)
 
@@ -110,7 +130,7 @@ if __name__ == "__main__":
     ap.add_argument("--build", action="store_true")
     ap.add_argument("--run", action="store_true")
     ap.add_argument("--reps", type=int, default=40)
-    ap.add_argument("--which", default="all", choices=["all", "ng"], help="ng: only the read-only (no-grad) variants")
+    ap.add_argument("--which", default="all", choices=["all", "ng", "pipe"], help="ng: only the read-only (no-grad) variants")
     a = ap.parse_args()
     if a.build:
         build(a.which)
