@@ -237,9 +237,10 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
 
     int grid = 0;
     if (N > 0) {
-        const bool vec = (P.HW % 4 == 0) && W >= 4 && aligned16(logits) && (!target_in || aligned16(target_in)) &&
+        // rendered target: a 128-bit vector must lie in one row (the padded-template lookup of render_loss_vec)
+        const bool vec = (P.HW % 4 == 0) && W >= 4 && (!kp || W % 4 == 0) && aligned16(logits) && (!target_in || aligned16(target_in)) &&
                          (!(flags & POSE_F_GRAD) || aligned16(dlogits)) && (!(flags & POSE_F_TARGET_OUT) || aligned16(target_out));
-        const size_t smem = kp ? (size_t)lut_n * lut_n * sizeof(float) : 0;
+        const size_t smem = kp ? pose::lut_padded_floats(lut_n) * sizeof(float) : 0;
         int rc;
         const bool tma = (flags & POSE_F_TMA) && kp && vec && !(flags & POSE_F_TARGET_OUT) && lut_n <= 31;
         if (tma) {

@@ -18,13 +18,21 @@ namespace pose {
 #endif
 // The read-only render variants (validation: loss and/or decode from keypoints, no dlogits) have no store stream to carry half of the traffic:
 // they need more loads in flight per SM to hide the same latency, so they get their own knobs.
-// (tools/tune_fused.py --which ng, B=4096: U6/M4 158.6 us loss, 173.9 us loss+decode; U6/M3 171.9 / 185.4; U8/M4 160.3 / 199.0
-//  -- the decode variant spills at U8 under the 64-register cap.)
+// (tools/tune_fused.py --which ng, B=4096, loss only: U6/M4 144.9 us, U8/M4 143.5, U4/M5 144.7, U6/M3 150.8, U12/M3 148.3.)
 #ifndef POSE_FUSED_U_NG
 #define POSE_FUSED_U_NG 6
 #endif
 #ifndef POSE_FUSED_MINB_NG
 #define POSE_FUSED_MINB_NG 4    // register cap 64
+#endif
+// ... and the read-only variant that also decodes (running argmax: more registers per element) its own again
+// (tools/tune_fused.py --which ngd: U8/M3 158.3 us, U4/M4 158.5, U6/M3 163.8, U6/M4 169.8, U8/M2 182.7.  Tracking the maximum per
+//  128-bit vector and resolving the element once per map with a 16-byte re-read was measured too: 2 % slower in every shape.)
+#ifndef POSE_FUSED_U_NGD
+#define POSE_FUSED_U_NGD 8
+#endif
+#ifndef POSE_FUSED_MINB_NGD
+#define POSE_FUSED_MINB_NGD 3   // register cap 80
 #endif
 // Software-pipelined streaming loop of the render variants (0 = off): the map is cut into stages of PIPE 128-bit loads per lane and the
 // loads of stage i+1 -- across map boundaries too -- are issued before stage i is computed, so a warp always has PIPE..2*PIPE
@@ -71,7 +79,21 @@ struct Patch {
     int px0, px1, py0, py1;  // clipped destination window, empty when the joint is invisible
     // flat element range [e0, e0 + ecnt) of the rows the window touches (ecnt == 0: nothing): the cheap per-vector test
     int e0, ecnt;
+    int nrows;               // py1 - uly (0 when empty): template rows [0, nrows) minus the ones above the map are rendered
 };
+
+// Shared-memory template of the fused kernels: n+1 rows of n+8 floats -- 4 zeros, the n template values, 4 zeros -- the last row all
+// zeros, so a lane fetches the targets of 4 consecutive pixels of one row with two clamped indices instead of 4 x (row test,
+// column test) behind divergent branches.
+constexpr int kLutPad = 4;
+__host__ __device__ inline size_t lut_padded_floats(int n) { return (size_t)(n + 1) * (size_t)(n + 2 * kLutPad); }
+__device__ __forceinline__ void stage_lut_padded(float* __restrict__ lut_s, const float* __restrict__ lut, int n) {
+    const int pw = n + 2 * kLutPad;
+    for (int i = threadIdx.x; i < (n + 1) * pw; i += blockDim.x) {
+        const int r = i / pw, c = i - r * pw - kLutPad;
+        lut_s[i] = (r < n && c >= 0 && c < n) ? lut[r * n + c] : 0.0f;
+    }
+}
 
 __device__ __forceinline__ Patch make_patch(double x, double y, int H, int W, double three_sigma, int lut_n) {
     Patch p;
@@ -90,6 +112,7 @@ __device__ __forceinline__ Patch make_patch(double x, double y, int H, int W, do
     if (!visible) { p.px0 = p.px1 = p.py0 = p.py1 = 0; p.ulx = p.uly = 0; }
     p.e0 = p.py0 * W;
     p.ecnt = (p.py1 > p.py0 && p.px1 > p.px0) ? (p.py1 - p.py0) * W : 0;
+    p.nrows = p.ecnt ? p.py1 - p.uly : 0;
     return p;
 }
 
@@ -217,21 +240,43 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
     }
     const int e = vi * V;
     if ((unsigned)(e + (V - 1) - pt.e0) < (unsigned)(pt.ecnt + (V - 1))) {
-        int r = (int)fdiv((uint32_t)e, divW);
-        int cc = e - r * W;
+        // (the V elements of a vector lie in one row: the launcher takes V = 4 only when W % 4 == 0)
+        const int r = (int)fdiv((uint32_t)e, divW);
+        const int cc = e - r * W;
+        const int pw = lut_n + 2 * kLutPad;
+        if constexpr (GRAD) {
+            // training kernel (HBM-bound with issue slots to spare): per-element tests, only lanes inside the window do the
+            // extra gradient math.  Measured against the branch-free form below: 280 vs 284 us per 69 632 maps.
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            if (r >= pt.py0 && r < pt.py1 && cc >= pt.px0 && cc < pt.px1) {
-                const float t = lut_s[(r - pt.uly) * lut_n + (cc - pt.ulx)];
-                if (WTGT) tout[j] = t;
-                if (t > 0.0f) {      // t == 0 (underflowed template tail): the zero-target result stands
-                    const float d = sg[j] - t;
-                    arem = fmaf(sg[j], sg[j], arem);
-                    apos = fmaf(d, d, apos);
-                    if (GRAD) g[j] = gpos * d * ((1.0f - sg[j]) * sg[j]);
+            for (int j = 0; j < V; ++j) {
+                if (r >= pt.py0 && r < pt.py1 && cc + j >= pt.px0 && cc + j < pt.px1) {
+                    const float t = lut_s[(r - pt.uly) * pw + (cc + j - pt.ulx) + kLutPad];
+                    if (WTGT) tout[j] = t;
+                    if (t > 0.0f) {      // t == 0 (underflowed template tail): the zero-target result stands
+                        const float d = sg[j] - t;
+                        arem = fmaf(sg[j], sg[j], arem);
+                        apos = fmaf(d, d, apos);
+                        g[j] = gpos * d * ((1.0f - sg[j]) * sg[j]);
+                    }
                 }
             }
-            if (++cc >= W) { cc = 0; ++r; }
+        } else {
+            // read-only kernels (SFU / issue-bound): rows outside the window -> the all-zero row; columns clamped into the zero
+            // pads; `lim` cuts a window that is narrower than the template (non-integer sigma): no per-element branch.
+            // 104 -> 55 instructions on this path, 125 M -> 100 M warp instructions per launch; 158.5 -> 145.5 us (loss only).
+            const int ri = ((unsigned)(r - pt.uly) < (unsigned)pt.nrows) ? r - pt.uly : lut_n;
+            const int ci = min(max(cc - pt.ulx, -kLutPad), lut_n);
+            const float* lp = lut_s + ri * pw + ci + kLutPad;
+            const int lim = pt.px1 - cc;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float t = lp[j];
+                const bool pos = (j < lim) && t > 0.0f;   // t == 0 (pad, or underflowed template tail): the zero-target result stands
+                if (WTGT) tout[j] = (j < lim) ? t : 0.0f;
+                const float d = sg[j] - t;
+                arem = fmaf(pos ? sg[j] : 0.0f, sg[j], arem);
+                apos = fmaf(pos ? d : 0.0f, d, apos);
+            }
         }
     }
 }
@@ -262,13 +307,14 @@ __device__ __forceinline__ void finish_map(const SbpFusedParams& P, long long ma
 }
 
 template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
-__global__ void __launch_bounds__(kSbpThreads, (GRAD || WTGT || TGT != 2) ? POSE_FUSED_MINB : POSE_FUSED_MINB_NG) sbp_fused_kernel(SbpFusedParams P) {
+__global__ void __launch_bounds__(kSbpThreads, (GRAD || WTGT || TGT != 2) ? POSE_FUSED_MINB : DEC ? POSE_FUSED_MINB_NGD : POSE_FUSED_MINB_NG)
+sbp_fused_kernel(SbpFusedParams P) {
     extern __shared__ float lut_s[];
     __shared__ double red[kSbpWarps][2];
     pdl_launch_dependents();      // the epilogue grid may be scheduled as our CTAs retire; it waits for our completion itself
     if (P.xpub.world > 0 && blockIdx.x == 0 && threadIdx.x == 0) exchange_open_step(P.xpub);
     if (TGT == TGT_RENDER) {
-        for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
+        stage_lut_padded(lut_s, P.lut, P.lut_n);
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
@@ -276,7 +322,7 @@ __global__ void __launch_bounds__(kSbpThreads, (GRAD || WTGT || TGT != 2) ? POSE
     const long long warp0 = (long long)blockIdx.x * kSbpWarps + wid;
     const long long nwarps = (long long)gridDim.x * kSbpWarps;
     const int nvec = P.HW / V;
-    constexpr int U = (V == 4) ? ((GRAD || WTGT || TGT != TGT_RENDER) ? POSE_FUSED_U : POSE_FUSED_U_NG) : 8;
+    constexpr int U = (V == 4) ? ((GRAD || WTGT || TGT != TGT_RENDER) ? POSE_FUSED_U : DEC ? POSE_FUSED_U_NGD : POSE_FUSED_U_NG) : 8;
     double dpos = 0.0, dneg = 0.0;
 
     // the keypoint of the NEXT map is fetched while the current map streams, so its latency is off the per-map

@@ -31,7 +31,7 @@ constexpr int kTmaWarps = POSE_TMA_WARPS;
 constexpr int kTmaThreads = kTmaWarps * 32;
 
 __host__ __device__ inline size_t sbp_tma_smem_bytes(int lut_n) {
-    size_t lut = ((size_t)lut_n * lut_n * sizeof(float) + 15) / 16 * 16;
+    size_t lut = (lut_padded_floats(lut_n) * sizeof(float) + 15) / 16 * 16;
     return (size_t)kTmaWarps * kTmaStages * kTmaTileBytes + lut + (size_t)kTmaWarps * kTmaStages * sizeof(uint64_t);
 }
 
@@ -45,11 +45,11 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
     unsigned char* tiles = smem_raw + (size_t)wid * kTmaStages * kTmaTileBytes;
-    const size_t lut_bytes = ((size_t)P.lut_n * P.lut_n * sizeof(float) + 15) / 16 * 16;
+    const size_t lut_bytes = (lut_padded_floats(P.lut_n) * sizeof(float) + 15) / 16 * 16;
     float* lut_s = reinterpret_cast<float*>(smem_raw + (size_t)kTmaWarps * kTmaStages * kTmaTileBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTmaWarps * kTmaStages * kTmaTileBytes + lut_bytes) + wid * kTmaStages;
 
-    for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
+    stage_lut_padded(lut_s, P.lut, P.lut_n);
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kTmaStages; ++s) mbar_init(smem_u32(bars + s), 1);

@@ -229,6 +229,42 @@ def test_config1_batch32_matches_reference(pb, dev):
     assert_joints(pb.DecodeSBP([256, 192], 0.25, True).decode_batch(x.detach()), g["joints"], REL)
 
 
+@pytest.mark.parametrize("sigma", [0.7, 1.1, 1.5, 2.4, 2.5])
+@pytest.mark.parametrize("hw", [(32, 24), (30, 27), (64, 48), (21, 36)])
+def test_fused_padded_template_windows(pb, dev, sigma, hw):
+    """The fused kernels fetch targets from a zero-padded shared-memory template with clamped indices (no range tests):
+    windows narrower than the template (sigma = 0.7, 1.1, 2.4: 6s+3 is not an integer), half-to-even corners (1.5, 2.5),
+    windows clipped by every edge, joints beyond the map, W % 4 != 0 (scalar kernel) -- target bit-exact, loss/grad 1e-5."""
+    h, w = hw
+    k = 24
+    rng = np.random.default_rng(int(sigma * 10) * 100 + h)
+    b = 3
+    kp = np.stack([rng.uniform(-2, w + 3, (b, k)), rng.uniform(-2, h + 3, (b, k))], -1)
+    kp[0, :8] = [[0, 0], [w - 1, 0], [0, h - 1], [w - 1, h - 1], [w - 0.5, h / 2], [w / 2, h + 2.0], [0.99, 3.2], [3.0, 0.5]]
+    kp[1, :3] = -1.0
+    logits = torch.randn(b, k, h, w, generator=torch.Generator().manual_seed(h * w)) * 3
+    want_t = so.sbp_render(kp, h, w, sigma)
+    wl, wg = so.sbp_loss_closed_form_f64(logits, torch.from_numpy(want_t))
+    x = logits.to(dev)
+    r = pb.sbp_fused(x, keypoints=kp, sigma=sigma, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0, want_target=True)
+    assert np.array_equal(r["target"].cpu().numpy(), want_t)
+    assert close(r["loss"].item(), float(wl), REL) and allclose(r["dlogits"], wg, REL)
+    assert_joints(r["joints"], so.sbp_decode(logits, 4 * w, 0.25, True), REL)
+    for grad, dec in ((True, False), (False, True), (False, False)):        # the read-only variants take the branch-free path
+        v = pb.sbp_fused(x, keypoints=kp, sigma=sigma, want_grad=grad, decode=dec, conf_threshold=0.25, coord_scale=4.0,
+                         want_target=not grad)
+        assert close(v["loss"].item(), float(wl), REL)
+        if not grad:
+            assert np.array_equal(v["target"].cpu().numpy(), want_t)
+        if grad:
+            assert torch.equal(v["dlogits"], r["dlogits"])
+        if dec:
+            assert torch.equal(v["joints"], r["joints"])
+    if w % 4 == 0:
+        t = pb.sbp_fused(x, keypoints=kp, sigma=sigma, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0, tma=True)
+        assert torch.equal(t["dlogits"], r["dlogits"]) and close(t["loss"].item(), float(wl), REL)
+
+
 def test_odd_shapes_scalar_path_and_empty_batch(pb, dev):
     """H*W not a multiple of 4 -> scalar kernels; unaligned views; N == 0."""
     k, h, w, sigma = 3, 7, 9, 1

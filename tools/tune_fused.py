@@ -17,7 +17,7 @@ OUT = os.path.join(ROOT, "build", "tune")
 SRC = os.path.join(ROOT, "pytorch-pose-estimation_b200", "csrc", "api.cu")
 VARIANTS = [(u, m) for u in (4, 6, 8) for m in (2, 3, 4)]
 # read-only (validation) render variants: loads in flight per lane, resident CTAs per SM
-NG_VARIANTS = [(6, 3), (6, 4), (8, 3), (8, 4), (12, 2), (12, 3)]
+NG_VARIANTS = [(6, 3), (6, 4), (8, 3), (8, 4), (12, 2), (12, 3), (4, 4), (5, 4), (4, 5), (5, 5), (3, 6), (4, 6)]
 # TMA-staged kernel: (stages, warps per CTA, float4 per tile)
 TMA_VARIANTS = [(2, 8, 256), (3, 8, 256), (4, 8, 256), (3, 4, 256), (3, 16, 256), (2, 16, 256), (3, 8, 128), (4, 8, 128), (6, 8, 128),
                 (2, 8, 768), (2, 4, 768), (3, 4, 768)]
@@ -27,9 +27,18 @@ TMA_VARIANTS = [(2, 8, 256), (3, 8, 256), (4, 8, 256), (3, 4, 256), (3, 16, 256)
 PIPE_VARIANTS = [(2, 0, 3), (3, 0, 3), (4, 0, 3), (3, 0, 2), (6, 0, 2), (0, 2, 4), (0, 3, 4), (0, 3, 3), (0, 4, 3), (0, 6, 3), (0, 2, 5)]
 
 
+# read-only variant with decode: (loads in flight per lane, resident CTAs per SM)
+NGD_VARIANTS = [(8, 3), (6, 3), (4, 4), (6, 4), (8, 2)]
+
+
 def build(which="all"):
     os.makedirs(OUT, exist_ok=True)
     procs = []
+    for u, m in (NGD_VARIANTS if which == "ngd" else []):
+        lib = os.path.join(OUT, f"libpose_ngd_u{u}_m{m}.so")
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+               f"-DPOSE_FUSED_U_NGD={u}", f"-DPOSE_FUSED_MINB_NGD={m}", "-o", lib, SRC]
+        procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for pg, pn, m in (PIPE_VARIANTS if which in ("all", "pipe") else []):
         lib = os.path.join(OUT, f"libpose_pipe_g{pg}_n{pn}_m{m}.so")
         knob = [f"-DPOSE_FUSED_PIPE={pg}", f"-DPOSE_FUSED_MINB={m}"] if pg else [f"-DPOSE_FUSED_PIPE_NG={pn}", f"-DPOSE_FUSED_MINB_NG={m}"]
@@ -87,6 +96,14 @@ def run(reps, which="all"):
                 jobs.append((f"PIPE{pg}_M{m}[grad+decode]", lib, 1 | 4))
             else:
                 jobs += [(f"PIPE_NG{pn}_M{m}[loss]", lib, 0), (f"PIPE_NG{pn}_M{m}[loss+decode]", lib, 4)]
+    if which == "ngd":
+        jobs += [(f"NGD_U{u}_M{m}[loss+decode]", os.path.join(OUT, f"libpose_ngd_u{u}_m{m}.so"), 4) for u, m in NGD_VARIANTS]
+    if which == "ab":      # every build/tune/ab_*.so against the in-tree library, all four render variants
+        import glob
+        base = os.path.join(ROOT, "pytorch-pose-estimation_b200", "libpose_b200.so")
+        libs = [("tree", base)] + [(os.path.basename(f)[3:-3], f) for f in sorted(glob.glob(os.path.join(OUT, "ab_*.so")))]
+        for fl, tag in ((1 | 4, "grad+decode"), (1, "grad"), (0, "loss"), (4, "loss+decode")):
+            jobs += [(f"{n}[{tag}]", f, fl) for n, f in libs]
     if which == "all":
         jobs += [(f"U{u}_M{m}", os.path.join(OUT, f"libpose_u{u}_m{m}.so"), 1 | 4) for u, m in VARIANTS]
         jobs += [(f"TMA_S{st}_W{w}_T{tv}", os.path.join(OUT, f"libpose_tma_s{st}_w{w}_t{tv}.so"), 1 | 4 | 8) for st, w, tv in TMA_VARIANTS]
@@ -130,7 +147,7 @@ if __name__ == "__main__":
     ap.add_argument("--build", action="store_true")
     ap.add_argument("--run", action="store_true")
     ap.add_argument("--reps", type=int, default=40)
-    ap.add_argument("--which", default="all", choices=["all", "ng", "pipe"], help="ng: only the read-only (no-grad) variants")
+    ap.add_argument("--which", default="all", choices=["all", "ng", "pipe", "ab", "ngd"], help="ng: only the read-only (no-grad) variants")
     a = ap.parse_args()
     if a.build:
         build(a.which)
