@@ -237,8 +237,8 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
 
     int grid = 0;
     if (N > 0) {
-        // rendered target: a 128-bit vector must lie in one row (the padded-template lookup of render_loss_vec)
-        const bool vec = (P.HW % 4 == 0) && W >= 4 && (!kp || W % 4 == 0) && aligned16(logits) && (!target_in || aligned16(target_in)) &&
+        // rendered target, read-only variants: a 128-bit vector must lie in one row (the padded-template lookup of render_loss_vec)
+        const bool vec = (P.HW % 4 == 0) && W >= 4 && (!kp || (flags & POSE_F_GRAD) || W % 4 == 0) && aligned16(logits) && (!target_in || aligned16(target_in)) &&
                          (!(flags & POSE_F_GRAD) || aligned16(dlogits)) && (!(flags & POSE_F_TARGET_OUT) || aligned16(target_out));
         const size_t smem = kp ? pose::lut_padded_floats(lut_n) * sizeof(float) : 0;
         int rc;

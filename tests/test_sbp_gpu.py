@@ -230,11 +230,12 @@ def test_config1_batch32_matches_reference(pb, dev):
 
 
 @pytest.mark.parametrize("sigma", [0.7, 1.1, 1.5, 2.4, 2.5])
-@pytest.mark.parametrize("hw", [(32, 24), (30, 27), (64, 48), (21, 36)])
+@pytest.mark.parametrize("hw", [(32, 24), (30, 27), (64, 48), (21, 36), (10, 18), (12, 26)])
 def test_fused_padded_template_windows(pb, dev, sigma, hw):
     """The fused kernels fetch targets from a zero-padded shared-memory template with clamped indices (no range tests):
     windows narrower than the template (sigma = 0.7, 1.1, 2.4: 6s+3 is not an integer), half-to-even corners (1.5, 2.5),
-    windows clipped by every edge, joints beyond the map, W % 4 != 0 (scalar kernel) -- target bit-exact, loss/grad 1e-5."""
+    windows clipped by every edge, joints beyond the map, W % 4 != 0 (scalar kernel; with H*W % 4 == 0 the training kernel
+    keeps 128-bit vectors that wrap rows) -- target bit-exact, loss/grad 1e-5."""
     h, w = hw
     k = 24
     rng = np.random.default_rng(int(sigma * 10) * 100 + h)

@@ -22,6 +22,8 @@ for _ in range(4):
         r = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0)
     elif which == "val":          # validation step: loss + decode, no dlogits (read-only variant)
         r = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=False, decode=True, conf_threshold=0.25, coord_scale=4.0)
+    elif which == "val_loss":     # validation loss only (read-only variant, no decode)
+        r = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=False)
     elif which == "decode":
         r = pb.decode_batch(logits, 0.25, 4.0, True)
     elif which == "dense":
