@@ -400,7 +400,10 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
 // phase B is entered 2.4x less often -- the four separate 128-byte lines per access cost more than that saved: 253 -> 318 us
 // fused, 144 -> 177 us render-only per 256 images.  Likewise a warp owning U CONSECUTIVE rows of a unit instead of every 8th row
 // (a 9-row box then falls to ~3 warps with full phase-B passes instead of 8 sparse ones): 235 -> 290 us fused, 125 -> 175 us
-// read-only -- the few loaded warps become the critical path of the CTA's unit range.)
+// read-only -- the few loaded warps become the critical path of the CTA's unit range.  And a per-warp shared-memory ring filled
+// with cp.async (LDGSTS) so that the next units' loads fly during phase B and phase B reads its logit from the ring instead of
+// L2: 235 -> 235 us (N=256), 902 -> 872 us (N=1024) for the grad variant at 3 CTAs/SM, 125 -> 139 us read-only -- the L2
+// prefetch of the next unit already hides that latency; not worth 32 KB of shared memory per CTA.)
 template <bool LOSS, bool GRAD, bool WTGT, bool ROWG, bool MAP>
 __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
     // dynamic shared memory: [div_n] double quotients | [R] u64 row masks | [64*K] int2 joints | [R*wpr] u32 covered quads | template
