@@ -390,6 +390,36 @@ def test_full_size_fused_equals_staged_and_oracle_subset(pb, dev, big):
     assert allclose(other, fused["loss_num"], 1e-7)
 
 
+def test_config3_shard_size_properties(pb, dev):
+    """BASELINE.json configs[2]: B=32768 over 2 GPUs = 16384 images per rank (3.4 GB per tensor: byte offsets beyond 2^31).
+    Size-independent properties: render -> decode round trip, fused decode == decode kernel, loss numerators additive over
+    4096-image pieces, dlogits of the last piece identical to that piece run alone."""
+    b, k, h, w = 16384, 17, 64, 48
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < 16 << 30:
+        pytest.skip("needs 16 GB of free device memory")
+    gen = torch.Generator(device=dev).manual_seed(3)
+    logits = torch.randn(b, k, h, w, device=dev, generator=gen) * 3
+    kp = torch.stack([torch.rand(b, k, device=dev, generator=gen, dtype=torch.float64) * w,
+                      torch.rand(b, k, device=dev, generator=gen, dtype=torch.float64) * h], dim=-1)
+    vis = torch.rand(b, k, device=dev, generator=gen) < 0.85
+    kp[~vis] = -1.0
+    t = pb.SBPHeatmapGenerator([h, w], k, 2).render_batch(kp)
+    j = pb.decode_batch(t, 0.99, 4.0, False)
+    want = torch.where(vis[..., None], torch.stack([4 * kp[..., 0].floor(), 4 * kp[..., 1].floor(), torch.ones_like(kp[..., 0])], -1),
+                       torch.tensor([-4.0, -4.0, -1.0], device=dev, dtype=torch.float64)).float()
+    assert torch.equal(j, want)
+    del t, j, want
+    fused = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0)
+    assert torch.equal(fused["joints"], pb.decode_batch(logits, 0.25, 4.0, True))
+    parts = [pb.sbp_fused(logits[i:i + 4096], keypoints=kp[i:i + 4096], sigma=2, want_grad=True, decode=True, conf_threshold=0.25,
+                          coord_scale=4.0, global_batch=b) for i in range(0, b, 4096)]
+    assert allclose(torch.stack([p["loss_num"] for p in parts]).sum(0), fused["loss_num"], 1e-12)
+    assert torch.equal(parts[-1]["dlogits"], fused["dlogits"][-4096:]) and torch.equal(parts[-1]["joints"], fused["joints"][-4096:])
+    val = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=False, decode=True, conf_threshold=0.25, coord_scale=4.0)
+    assert torch.equal(val["joints"], fused["joints"]) and allclose(val["loss_num"], fused["loss_num"], 1e-7)
+
+
 @pytest.mark.parametrize("shape", [(6, 17, 64, 48), (3, 11, 64, 48), (2, 17, 33, 27), (2, 5, 16, 20)])
 def test_flip_test_decode_unpinned(pb, dev, shape):
     """PARITY UNPINNED: the reference has no flip test; checked against our restatement of the published rule
