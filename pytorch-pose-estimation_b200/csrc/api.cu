@@ -405,7 +405,7 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
         F.div_n = R <= 1024 ? 2 * R + 1 : 0;
         const size_t fsmem = pose::spm_fused_smem_bytes(F.div_n, R, K, F.wpr, lut_n);
         if (fsmem <= 200 * 1024) {
-            const int fchunk = pose::kSpmThreads * pose::spm_fused_u(false, true);
+            const int fchunk = pose::kSpmThreads * pose::spm_fused_u(false, true, false);
             const long long funits = (long long)N * (1 + 2 * K) * ((quads + fchunk - 1) / fchunk);
 #define POSE_SPMR(RG, MP)                                                                                                      \
     {                                                                                                                          \

@@ -342,17 +342,26 @@ struct __align__(16) SpmFusedPerson {
 #ifndef POSE_SPM_FUSED_MINB
 #define POSE_SPM_FUSED_MINB 4   // resident CTAs per SM the kernel is compiled for (register cap 64)
 #endif
-// float4 per thread and unit (1, 2, 4 or 8: the unit must divide a 128x128 plane).  Variants that write a full-size stream
-// (dlogits or the target) run best with 16 KB units; the read-only loss variant with 32 KB units (more covered quads pooled
-// per phase B, twice the loads in flight): 139.6 -> 123.1 us per 256 images, while U = 8 costs the grad variant 234 -> 245 us.
+// float4 per thread and unit (1, 2, 4 or 8: the unit must divide a 128x128 plane), per variant (tools/spm_skeleton.py,
+// profiles/r01_spm_unit_sweep.log, per 256 / 1024 images):
+//   loss + grad (read logits, write dlogits): 8 KB units -- U=2 222 / 817 us, U=4 235 / 907, U=8 242 / 924, U=1 272 / 1028;
+//   read-only loss: 32 KB units (more covered quads pooled per phase B, twice the loads in flight) -- U=8 123 / 415 us,
+//     U=4 138 / 488, U=2 166 / 633;
+//   render-only (LOSS = false, pose_spm_render): 32 KB units -- U=8 123 / 447 us, U=4 124 / 457, U=2 127 / 456.
 #ifndef POSE_SPM_FUSED_U
-#define POSE_SPM_FUSED_U 4
+#define POSE_SPM_FUSED_U 2
 #endif
 #ifndef POSE_SPM_FUSED_U_RO
 #define POSE_SPM_FUSED_U_RO 8
 #endif
-__host__ __device__ constexpr int spm_fused_u(bool grad, bool wtgt) { return (grad || wtgt) ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO; }
-constexpr int kSpmFusedUMax = POSE_SPM_FUSED_U > POSE_SPM_FUSED_U_RO ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
+#ifndef POSE_SPM_FUSED_U_RENDER
+#define POSE_SPM_FUSED_U_RENDER 8
+#endif
+__host__ __device__ constexpr int spm_fused_u(bool grad, bool wtgt, bool loss = true) {
+    return !loss ? POSE_SPM_FUSED_U_RENDER : (grad || wtgt) ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
+}
+constexpr int kSpmFusedUMax0 = POSE_SPM_FUSED_U > POSE_SPM_FUSED_U_RO ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
+constexpr int kSpmFusedUMax = kSpmFusedUMax0 > POSE_SPM_FUSED_U_RENDER ? kSpmFusedUMax0 : POSE_SPM_FUSED_U_RENDER;
 constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
 
 constexpr int kSpmMapMaxBytes = 16384;                        // per-image pixel map (one byte per pixel): R <= 128
@@ -417,7 +426,7 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
     unsigned char* map_s = reinterpret_cast<unsigned char*>(lut_s + P.lut_n * P.lut_n);      // MAP only
     __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
     __shared__ double red[kSpmThreads / 32][2];
-    constexpr int kSpmFusedU = spm_fused_u(GRAD, WTGT);
+    constexpr int kSpmFusedU = spm_fused_u(GRAD, WTGT, LOSS);
     constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;          // float4 per work unit
     __shared__ unsigned char s_src[kSpmThreads / 32][32 * kSpmFusedU];
     pdl_launch_dependents();
