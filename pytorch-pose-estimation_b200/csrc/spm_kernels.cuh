@@ -363,6 +363,20 @@ __host__ __device__ constexpr int spm_fused_u(bool grad, bool wtgt, bool loss = 
 constexpr int kSpmFusedUMax0 = POSE_SPM_FUSED_U > POSE_SPM_FUSED_U_RO ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
 constexpr int kSpmFusedUMax = kSpmFusedUMax0 > POSE_SPM_FUSED_U_RENDER ? kSpmFusedUMax0 : POSE_SPM_FUSED_U_RENDER;
 constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
+// PATCH (read-only loss variant at R = 128, i.e. ROWG && MAP): the covered quads of an image are listed once per image; the
+// stream (phase A) never stops for them and ONE pass per plane, by the whole CTA with one pixel per thread and full lanes,
+// computes the listed pixels.  Their logits are requested when the CTA enters the plane and consumed when it leaves it, so the
+// dependent chain of the per-warp phase B is off the streaming path: 124.0 -> 115.9 us per 256 images, 417.8 -> 407.9 us per
+// 1024.  POSE_SPM_PATCHPASS = 2 applies it to the variants that write dlogits / the target as well (phase A then skips the
+// zero stores of covered quads and the patch pass writes them): correct (all SPM GPU tests pass) but slower there -- 220.8 ->
+// 225.6 us, 819 -> 864 us -- the predicated stores cost the stream more than the per-warp phase B did.
+#ifndef POSE_SPM_PATCHPASS
+#define POSE_SPM_PATCHPASS 1
+#endif
+#ifndef POSE_SPM_PATCH_NPRE
+#define POSE_SPM_PATCH_NPRE 3   // pixels per thread whose logits are requested at plane entry (3 x 256 = 192 covered quads)
+#endif
+constexpr int kSpmPatchListCap = 4096;                        // all quads of a 128 x 128 plane
 
 constexpr int kSpmMapMaxBytes = 16384;                        // per-image pixel map (one byte per pixel): R <= 128
 
@@ -429,6 +443,11 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
     constexpr int kSpmFusedU = spm_fused_u(GRAD, WTGT, LOSS);
     constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;          // float4 per work unit
     __shared__ unsigned char s_src[kSpmThreads / 32][32 * kSpmFusedU];
+    // ROWG && MAP <=> R == 128: 32 quads per row, wpr == 1
+    constexpr bool PATCH = LOSS && ROWG && MAP && (POSE_SPM_PATCHPASS == 2 || (POSE_SPM_PATCHPASS == 1 && !GRAD && !WTGT));
+    constexpr int NPRE = POSE_SPM_PATCH_NPRE;
+    __shared__ unsigned short plist_s[PATCH ? kSpmPatchListCap : 1];   // covered quads of the staged image, ascending
+    __shared__ int s_nlist;
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
     for (int i = threadIdx.x; i < P.div_n; i += blockDim.x) div_s[i] = (double)(i - P.R) / P.z;
@@ -452,6 +471,8 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
     int chunk = (int)(u_begin - plane * upp);
     int img = (int)(plane / C), c = (int)(plane - (long long)img * C);
 
+    int q_first = 0, q_last = 0;                                       // PATCH: this CTA's quads [q_first, q_last) of the current plane
+    float pl[NPRE];                                                    // PATCH: logits requested at plane entry
     for (long long unit = u_begin; unit < u_end; ++unit) {
         if (img != staged_img) {                                       // CTA-uniform
             const int np = min(max(P.counts[img], 0), min(P.Pmax, kSpmFusedMaxPersons));
@@ -525,6 +546,30 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                     map_s[idx] = (unsigned char)(code | (mk ? 128u : 0u));
                   }
                 }
+                if (PATCH && wid == kSpmThreads / 32 - 1) {
+                    // the covered-quad bits (one word per row, 4 rows per lane) -> ascending list of quad indices
+                    unsigned int w4[4];
+                    int cnt = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { w4[k] = covq_s[4 * lane + k]; cnt += __popc(w4[k]); }
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(FULL_MASK, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    int pos = incl - cnt;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        unsigned int bits = w4[k];
+                        while (bits) {
+                            const int b = __ffs((int)bits) - 1;
+                            bits &= bits - 1u;
+                            plist_s[pos++] = (unsigned short)((4 * lane + k) * 32 + b);
+                        }
+                    }
+                    if (lane == 31) s_nlist = incl;
+                }
                 __syncthreads();
             }
             staged_img = img;
@@ -549,6 +594,20 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
         const bool disp = c != 0;
         const int jn = (c - 1) >> 1, axis = (c - 1) & 1;                 // displacement plane: joint and axis (0 = x, 1 = y)
         float acc = 0.f;
+        if (PATCH && (unit == u_begin || chunk == 0)) {                  // entering a plane (CTA-uniform)
+            q_first = q_lo;
+            q_last = (chunk + (int)min((long long)(upp - chunk), u_end - unit)) * kSpmFusedChunk;
+            const int nl4 = 4 * s_nlist;
+#pragma unroll
+            for (int k = 0; k < NPRE; ++k) {
+                const int i = (int)threadIdx.x + k * kSpmThreads;
+                pl[k] = 0.0f;
+                if (i < nl4) {
+                    const int q = (int)plist_s[i >> 2];
+                    if (q >= q_first && q < q_last) pl[k] = __ldg(P.logits + (off + q) * 4 + (i & 3));
+                }
+            }
+        }
         unsigned cmask[kSpmFusedU];
         float4* gdst = GRAD ? G4 + off + q_lo + threadIdx.x : nullptr;
         float4* tdst = WTGT ? T4 + off + q_lo + threadIdx.x : nullptr;
@@ -566,9 +625,11 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                     const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
                     if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
                 }
-                if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
-                if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
                 cmask[u] = covq_s[(q_lo >> 5) + u * (kSpmThreads / 32) + wid];
+                if (!PATCH || !((cmask[u] >> lane) & 1u)) {              // PATCH: covered quads are written by the plane's patch pass
+                    if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
+                    if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
+                }
             }
 #pragma unroll
             for (int u = 0; u < kSpmFusedU; ++u) anyc |= cmask[u];
@@ -601,7 +662,56 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
         // unrolled over u (an unrolled copy per u made the kernel 113 KB of SASS and `no_instruction` the second largest
         // stall).  The pixel's logit is re-read from L2 (the warp streamed it a moment ago) rather than shuffled out of pv[]:
         // pv dies after phase A, which keeps the kernel inside 64 registers without spills.
-        if (anyc) {                                                      // warp-uniform
+        // one covered pixel: element e of quad qs (plane-relative) with logit pe
+        auto pixel = [&](int qs, int e, float pe) {
+            const long long ei = (off + qs) * 4 + e;
+            const int row = (int)fdiv((uint32_t)qs, P.div_qpr), col = (qs - row * qpr) * 4 + e;
+            float t0 = 0.0f, te = 0.0f;
+            bool mk;
+            unsigned int code = 127u;
+            if (MAP && disp) code = map_s[row * P.R + col];
+            if (ROWG && MAP && disp && code == 0u) {                      // slack pixel of a covered quad
+                if (PATCH) {                                              // phase A left the covered quads unwritten
+                    if (GRAD) __stcs(P.dlogits + ei, 0.0f);
+                    if (WTGT) __stcs(P.target_out + ei, 0.0f);
+                }
+                return;                                                   // (not PATCH: phase A's zeros stand)
+            }
+            if (MAP && disp && (code & 127u) != 127u) {
+                mk = code >> 7;
+                if (code & 127u) {
+                    const int2 jv = s_j[((int)(code & 127u) - 1) * P.K + jn];
+                    if (!(jv.x <= 0 && jv.y <= 0)) {
+                        const int dd = axis ? jv.y - row : jv.x - col;
+                        te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
+                    }
+                }
+            } else {
+                spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
+                mk = t0 > 0.0f;
+            }
+            float ge = 0.0f;
+            if (!LOSS) {
+                if (!disp) te = t0;
+            } else if (!disp) {
+                const float sg = sigmoid_fast(pe);
+                const float d = (mk ? sg : sg * 0.0f) - t0;
+                acc = fmaf(d, d, acc);
+                ge = mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
+                te = t0;
+            } else {
+                // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
+                float th = 0.0f, pm = pe != pe ? pe : 0.0f;          // NaN logits propagate as in the reference
+                if (mk) { th = tanhf(pe); pm = th; }
+                const float d = pm - te;
+                const float ad = fabsf(d);
+                acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+                ge = mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
+            }
+            if (GRAD) __stcs(P.dlogits + ei, ge);
+            if (WTGT) __stcs(P.target_out + ei, te);
+        };
+        if (!PATCH && anyc) {                                            // warp-uniform
             int nslot = 0;
 #pragma unroll
             for (int u = 0; u < kSpmFusedU; ++u) {
@@ -616,50 +726,24 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 const int sl = (int)s_src[wid][l >> 2];
                 const int qs = q_lo + (sl >> 5) * kSpmThreads + wid * 32 + (sl & 31);
                 const int e = l & 3;
-                const long long ei = (off + qs) * 4 + e;
-                float pe = 0.0f;
-                if (LOSS) pe = __ldg(P.logits + ei);
-                const int row = (int)fdiv((uint32_t)qs, P.div_qpr), col = (qs - row * qpr) * 4 + e;
-                float t0 = 0.0f, te = 0.0f;
-                bool mk;
-                unsigned int code = 127u;
-                if (MAP && disp) code = map_s[row * P.R + col];
-                if (ROWG && MAP && disp && code == 0u) continue;      // slack pixel of a covered quad: phase A's zeros stand
-                if (MAP && disp && (code & 127u) != 127u) {
-                    mk = code >> 7;
-                    if (code & 127u) {
-                        const int2 jv = s_j[((int)(code & 127u) - 1) * P.K + jn];
-                        if (!(jv.x <= 0 && jv.y <= 0)) {
-                            const int dd = axis ? jv.y - row : jv.x - col;
-                            te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
-                        }
-                    }
-                } else {
-                    spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
-                    mk = t0 > 0.0f;
-                }
-                float ge = 0.0f;
-                if (!LOSS) {
-                    if (!disp) te = t0;
-                } else if (!disp) {
-                    const float sg = sigmoid_fast(pe);
-                    const float d = (mk ? sg : sg * 0.0f) - t0;
-                    acc = fmaf(d, d, acc);
-                    ge = mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
-                    te = t0;
-                } else {
-                    // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
-                    float th = 0.0f, pm = pe != pe ? pe : 0.0f;          // NaN logits propagate as in the reference
-                    if (mk) { th = tanhf(pe); pm = th; }
-                    const float d = pm - te;
-                    const float ad = fabsf(d);
-                    acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-                    ge = mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
-                }
-                if (GRAD) __stcs(P.dlogits + ei, ge);
-                if (WTGT) __stcs(P.target_out + ei, te);
+                pixel(qs, e, LOSS ? __ldg(P.logits + (off + qs) * 4 + e) : 0.0f);
             }
             __syncwarp();                                                // scratch row is rewritten by the next covered group
+        }
+        if (PATCH && (unit + 1 == u_end || chunk == upp - 1)) {          // leaving the plane (CTA-uniform): its patch pass
+            const int nl4 = 4 * s_nlist;
+#pragma unroll
+            for (int k = 0; k < NPRE; ++k) {
+                const int i = (int)threadIdx.x + k * kSpmThreads;
+                if (i < nl4) {
+                    const int q = (int)plist_s[i >> 2];
+                    if (q >= q_first && q < q_last) pixel(q, i & 3, pl[k]);
+                }
+            }
+            for (int i = (int)threadIdx.x + NPRE * kSpmThreads; i < nl4; i += kSpmThreads) {
+                const int q = (int)plist_s[i >> 2];
+                if (q >= q_first && q < q_last) pixel(q, i & 3, __ldg(P.logits + (off + q) * 4 + (i & 3)));
+            }
         }
         if (c == 0) droot += (double)acc; else ddisp += (double)acc;
         if (++chunk == upp) {
