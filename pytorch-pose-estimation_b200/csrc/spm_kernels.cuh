@@ -370,6 +370,9 @@ constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row 
 // 1024.  POSE_SPM_PATCHPASS = 2 applies it to the variants that write dlogits / the target as well (phase A then skips the
 // zero stores of covered quads and the patch pass writes them): correct (all SPM GPU tests pass) but slower there -- 220.8 ->
 // 225.6 us, 819 -> 864 us -- the predicated stores cost the stream more than the per-warp phase B did.
+// POSE_SPM_PATCHPASS = 3 (NOT YET RUN ON A GPU -- written after the round's GPU budget was spent; the next thing to test): the
+// writing variants keep their unconditional zero stores, the CTA meets at ONE barrier when it leaves a plane and the patch
+// pass then overwrites the covered pixels (the barrier orders the CTA's zero stores before them).
 #ifndef POSE_SPM_PATCHPASS
 #define POSE_SPM_PATCHPASS 1
 #endif
@@ -444,7 +447,8 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
     constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;          // float4 per work unit
     __shared__ unsigned char s_src[kSpmThreads / 32][32 * kSpmFusedU];
     // ROWG && MAP <=> R == 128: 32 quads per row, wpr == 1
-    constexpr bool PATCH = LOSS && ROWG && MAP && (POSE_SPM_PATCHPASS == 2 || (POSE_SPM_PATCHPASS == 1 && !GRAD && !WTGT));
+    constexpr bool PATCH = LOSS && ROWG && MAP && (POSE_SPM_PATCHPASS >= 2 || (POSE_SPM_PATCHPASS == 1 && !GRAD && !WTGT));
+    constexpr bool PATCH_BAR = PATCH && POSE_SPM_PATCHPASS == 3 && (GRAD || WTGT);   // zero stores stay; barrier, then overwrite
     constexpr int NPRE = POSE_SPM_PATCH_NPRE;
     __shared__ unsigned short plist_s[PATCH ? kSpmPatchListCap : 1];   // covered quads of the staged image, ascending
     __shared__ int s_nlist;
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                     if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
                 }
                 cmask[u] = covq_s[(q_lo >> 5) + u * (kSpmThreads / 32) + wid];
-                if (!PATCH || !((cmask[u] >> lane) & 1u)) {              // PATCH: covered quads are written by the plane's patch pass
+                if (!PATCH || PATCH_BAR || !((cmask[u] >> lane) & 1u)) {  // PATCH: covered quads are written by the plane's patch pass
                     if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
                     if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
                 }
@@ -671,7 +675,7 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
             unsigned int code = 127u;
             if (MAP && disp) code = map_s[row * P.R + col];
             if (ROWG && MAP && disp && code == 0u) {                      // slack pixel of a covered quad
-                if (PATCH) {                                              // phase A left the covered quads unwritten
+                if (PATCH && !PATCH_BAR) {                                // phase A left the covered quads unwritten
                     if (GRAD) __stcs(P.dlogits + ei, 0.0f);
                     if (WTGT) __stcs(P.target_out + ei, 0.0f);
                 }
@@ -731,6 +735,7 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
             __syncwarp();                                                // scratch row is rewritten by the next covered group
         }
         if (PATCH && (unit + 1 == u_end || chunk == upp - 1)) {          // leaving the plane (CTA-uniform): its patch pass
+            if (PATCH_BAR) __syncthreads();                              // every warp's zero stores of this plane are issued
             const int nl4 = 4 * s_nlist;
 #pragma unroll
             for (int k = 0; k < NPRE; ++k) {
