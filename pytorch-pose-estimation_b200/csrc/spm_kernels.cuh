@@ -447,7 +447,9 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
     constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;          // float4 per work unit
     __shared__ unsigned char s_src[kSpmThreads / 32][32 * kSpmFusedU];
     // ROWG && MAP <=> R == 128: 32 quads per row, wpr == 1
-    constexpr bool PATCH = LOSS && ROWG && MAP && (POSE_SPM_PATCHPASS >= 2 || (POSE_SPM_PATCHPASS == 1 && !GRAD && !WTGT));
+    // (mode 3 also covers the render-only form, LOSS = false: no logits, the pass only writes the covered target pixels)
+    constexpr bool PATCH = ROWG && MAP && ((LOSS && POSE_SPM_PATCHPASS >= 2) || POSE_SPM_PATCHPASS == 3 ||
+                                           (LOSS && POSE_SPM_PATCHPASS == 1 && !GRAD && !WTGT));
     constexpr bool PATCH_BAR = PATCH && POSE_SPM_PATCHPASS == 3 && (GRAD || WTGT);   // zero stores stay; barrier, then overwrite
     constexpr int NPRE = POSE_SPM_PATCH_NPRE;
     __shared__ unsigned short plist_s[PATCH ? kSpmPatchListCap : 1];   // covered quads of the staged image, ascending
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 pl[k] = 0.0f;
                 if (i < nl4) {
                     const int q = (int)plist_s[i >> 2];
-                    if (q >= q_first && q < q_last) pl[k] = __ldg(P.logits + (off + q) * 4 + (i & 3));
+                    if (LOSS && q >= q_first && q < q_last) pl[k] = __ldg(P.logits + (off + q) * 4 + (i & 3));
                 }
             }
         }
@@ -747,7 +749,7 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
             }
             for (int i = (int)threadIdx.x + NPRE * kSpmThreads; i < nl4; i += kSpmThreads) {
                 const int q = (int)plist_s[i >> 2];
-                if (q >= q_first && q < q_last) pixel(q, i & 3, __ldg(P.logits + (off + q) * 4 + (i & 3)));
+                if (q >= q_first && q < q_last) pixel(q, i & 3, LOSS ? __ldg(P.logits + (off + q) * 4 + (i & 3)) : 0.0f);
             }
         }
         if (c == 0) droot += (double)acc; else ddisp += (double)acc;

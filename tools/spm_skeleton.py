@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Times spm_fused (grad / read-only) with the usual persons and with none (the bare streaming skeleton)."""
+"""Times spm_fused (grad / read-only) and spm_render with the usual persons and with none (the bare streaming skeleton)."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -15,3 +15,5 @@ for n in (256, 1024):
             med, best = timeit(lambda: pb.spm_fused(x, c, j, cc, 1, want_grad=g), 30)
             gb = (2 if g else 1) * 35 * 128 * 128 * 4 * n / (med * 1e-3) / 1e9
             print(f"N={n:5d} {tag:8s} grad={int(g)}: {med*1e3:8.1f} us  {gb:7.1f} GB/s", flush=True)
+        med, best = timeit(lambda: pb.spm_render_batch(c, j, cc, 128, 1), 30)
+        print(f"N={n:5d} {tag:8s} render:  {med*1e3:8.1f} us  {35 * 128 * 128 * 4 * n / (med * 1e-3) / 1e9:7.1f} GB/s", flush=True)
