@@ -9,7 +9,9 @@
  * Conventions for every compute entry point:
  *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
  *   - asynchronous on `stream` (a cudaStream_t passed as void*); no allocation, no host
- *     synchronisation, no global mutable state (thread-safe; one library shared by all ranks);
+ *     synchronisation; thread-safe, one library shared by all ranks.  The only state kept between calls is a
+ *     mutex-protected cache of launch configurations (occupancy, shared-memory opt-in) per (kernel, device) and a
+ *     launch counter: a steady-state call makes no driver query and reads no environment variable;
  *   - the caller owns all memory, including workspaces (sizes from the *_workspace_bytes calls);
  *   - returns 0 on success, <0 for a bad argument (POSE_E*), >0 a cudaError_t from a launch;
  *     pose_b200_last_error() gives a thread-local message for the last non-zero return;
@@ -36,16 +38,24 @@ extern "C" {
 #define POSE_F_TARGET_OUT 2u    /* also materialise the rendered target (render mode only) */
 #define POSE_F_DECODE 4u        /* also decode joints from sigmoid(logits) in the same pass */
 #define POSE_F_TMA 8u           /* stage the maps through shared memory with bulk async copies (render mode, 16-byte aligned) */
+#define POSE_F_SIGMOID_CUDA 16u /* POSE_F_DECODE: rank with POSE_SIGMOID_ATEN_CUDA instead of POSE_SIGMOID_ATEN_CPU */
 
-/* decode modes */
-#define POSE_DECODE_DIRECT 0    /* activation on every element, argmax on activated values */
-#define POSE_DECODE_INTERVAL 1  /* max logit first, then first index inside the activation's pre-image of the max */
+/* Which torch.sigmoid the decoders reproduce BIT FOR BIT when they rank near-equal logits and report the confidence.
+ * "First row-major index of the largest sigmoid value" (nms_sbp utils/sbp_utils.py:73-78, nms_spm utils/spm_utils.py:112-115)
+ * depends on it: fp32 sigmoid is many-to-one and implementations one ulp apart merge different neighbours.
+ *   ATEN_CPU : 1/(1+Sleef_expf_u10(-x)) -- the reference run on CPU tensors (the golden vectors)
+ *   ATEN_CUDA: 1/(1+expf(-x)), libdevice expf, IEEE divide -- the reference run on CUDA tensors (the Lightning modules) */
+#define POSE_SIGMOID_ATEN_CPU 0
+#define POSE_SIGMOID_ATEN_CUDA 1
 
 typedef void* pose_stream_t;
 struct pose_exchange;
 
 /* ---- library ------------------------------------------------------------------------------- */
 int pose_b200_version(void);
+/* sha256 (hex) of the sources + compiler flags this binary was built from; the Python loader refuses a library whose
+ * hash differs from the tree it sits in (a stale binary must not pass for a fresh one) */
+const char* pose_b200_source_hash(void);
 const char* pose_b200_last_error(void);
 /* kernels launched by this library since load (statistics only; relaxed atomic) */
 unsigned long long pose_b200_launch_count(void);
@@ -136,10 +146,11 @@ int pose_scale_grad(float* dlogits, const float* grad_output, unsigned long long
 /* ---- SBP decode -- nms_sbp utils/sbp_utils.py:56-82 + DecodeSBP.forward :103-118, batched.
  * x [N][K][H][W]; joints [N][K][3].  apply_sigmoid = DecodeSBP.pred.  Both coordinates are
  * multiplied by coord_scale (= input_w / W, :116), undetected rows are (-1,-1,-1)*scale on x,y.
- * refine != 0 adds the quarter-pixel shift (NOT in the reference; off by default). */
+ * sigmoid_ref (apply_sigmoid only): POSE_SIGMOID_ATEN_CPU / _CUDA -- argmax indices and confidences are bit-identical to
+ * the reference evaluated with that torch.sigmoid.  refine != 0 adds the quarter-pixel shift (NOT in the reference; off by default). */
 int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W,
                     float conf_threshold, int apply_sigmoid, float coord_scale,
-                    int refine, int mode, pose_stream_t stream);
+                    int refine, int sigmoid_ref, pose_stream_t stream);
 
 /* ---- SBP decode with flip-test averaging -- NOT in the reference (PARITY UNPINNED, opt-in).
  * x, x_flip [N][K][H][W]: the maps of the image and of its horizontal mirror.  flip_perm [K] int32 (device): channel
@@ -191,13 +202,19 @@ int pose_spm_fused(const float* logits, const long long* centers, const long lon
 /* ---- SPM decode -- nms_spm :98-161, get_spm_keypoints :164-200, DecodeSPM.forward :225-250.
  * x [N][1+2K][R][R]; roots [N][Pmax][3], kps [N][Pmax][K][3], counts [N] (roots found, capped at
  * Pmax; total found incl. overflow in counts_total if non-NULL).  Ties between equal root
- * confidences break row-major (the reference's order is undefined there).
- * workspace: pose_spm_decode_workspace_bytes(N, R). */
-unsigned long long pose_spm_decode_workspace_bytes(int N, int R);
+ * confidences break row-major (the reference's order is undefined there).  apply_act = DecodeSPM.pred; the root
+ * confidences -- which decide the threshold test and the greedy order -- are then the reference's torch.sigmoid bit for
+ * bit (sigmoid_ref: POSE_SIGMOID_ATEN_CPU / _CUDA).  No workspace. */
 int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* counts_total,
                     int N, int Pmax, int K, int R, float conf_threshold, double dist_threshold,
-                    int apply_act, float input_size, void* workspace, unsigned long long workspace_bytes,
-                    pose_stream_t stream);
+                    int apply_act, int sigmoid_ref, float input_size, pose_stream_t stream);
+
+/* ---- SPM image-size rescale -- SPMmAPCOCO.update_state utils/spm_utils.py:302-304.
+ * kps [N][Pmax][K][3] at input scale (from pose_spm_decode), counts [N], image_w / image_h [N] int64 ->
+ * out [N][Pmax][K][3]: x * fp32(w / input_size), y * fp32(h / input_size), conf; rows >= counts[i] are not written.
+ * out may alias kps. */
+int pose_spm_rescale(const float* kps, const int* counts, const long long* image_w, const long long* image_h,
+                     float* out, int N, int Pmax, int K, float input_size, pose_stream_t stream);
 
 /* ---- SPM joint gather -- get_spm_keypoints utils/spm_utils.py:164-200 (no rescale).
  * roots [n][3] (x, y, conf) in map pixels, disp [2K][R][R] (already activated) -> kps [n][K][3]. */
@@ -240,10 +257,14 @@ int pose_ap_accumulate(const long long* order, const int* dt_match, const unsign
                        double* precision, double* recall, void* workspace, unsigned long long workspace_bytes,
                        pose_stream_t stream);
 
-/* ---- diagnostics -- exhaustive check that the device sigmoid used by decode is monotone
- * non-decreasing over all finite fp32 inputs (the INTERVAL decode mode relies on it).
- * violations_out [1] uint64 on device, zeroed by the call. */
-int pose_sigmoid_monotone_check(unsigned long long* violations_out, pose_stream_t stream);
+/* ---- diagnostics of the reference sigmoids (csrc/common.cuh).
+ * pose_sigmoid_ref_eval: y[i] = the device restatement of torch.sigmoid (sigmoid_ref) at x[i]; tests compare it with
+ *   torch.sigmoid on CPU / CUDA tensors bit for bit.
+ * pose_sigmoid_window_check: for every 61st fp32 m in (-80, inf], counts inputs below the candidate window of m whose
+ *   reference sigmoid is not strictly below that of m (must be 0: the decoders only rank elements inside the window).
+ *   violations_out [1] uint64 on device, zeroed by the call. */
+int pose_sigmoid_ref_eval(const float* x, float* y, unsigned long long n, int sigmoid_ref, pose_stream_t stream);
+int pose_sigmoid_window_check(unsigned long long* violations_out, int sigmoid_ref, pose_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,40 @@ def sbp_adversarial_maps(k=17, h=64, w=48, seed=5):
     return base
 
 
+NEARTIE_MAGNITUDES = (0.5, 3.0, 8.0, 12.0, 16.5, -2.0, 5.25, 10.0)
+
+
+def _ulp_step(v, n):
+    """v moved by n fp32 ulps (n may be negative)."""
+    a = np.float32(v)
+    for _ in range(abs(n)):
+        a = np.nextafter(a, np.float32(np.inf if n > 0 else -np.inf))
+    return a
+
+
+def sbp_neartie_maps(n=8, k=17, h=64, w=48, seed=11):
+    """[n,K,H,W] fp32 logits whose two (or three) largest values are 1-4 ulp apart at the magnitudes where fp32 sigmoid
+    starts to merge neighbours: which of them is "the first maximum of sigmoid(x)" depends on the last bit of the sigmoid
+    implementation.  Map (i, j): magnitude NEARTIE_MAGNITUDES[(i*K+j) % 8]; the earlier (row-major) pixel holds the
+    value that is d = 1 + (i*K+j) % 4 ulp SMALLER on even maps and LARGER on odd maps; every third map has a third
+    contender 2d ulp below, placed before both."""
+    rng = np.random.default_rng(seed)
+    x = rng.normal(-6.0, 0.5, size=(n, k, h, w)).astype(np.float32)
+    for i in range(n):
+        for j in range(k):
+            t = i * k + j
+            m = NEARTIE_MAGNITUDES[t % len(NEARTIE_MAGNITUDES)]
+            d = 1 + t % 4
+            p = np.sort(rng.choice(h * w, size=3, replace=False))
+            lo, hi = _ulp_step(m, -d), np.float32(m)
+            first, second = (lo, hi) if t % 2 == 0 else (hi, lo)
+            x[i, j].flat[p[1]] = first
+            x[i, j].flat[p[2]] = second
+            if t % 3 == 0:
+                x[i, j].flat[p[0]] = _ulp_step(m, -2 * d)
+    return torch.from_numpy(x)
+
+
 # --------------------------------------------------------------------------- SPM
 
 SPM_SHAPES = {

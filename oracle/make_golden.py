@@ -73,6 +73,11 @@ def golden_sbp_adversarial(ref):
         out[f"joints_pred_thr{thr}"] = np.stack([dec(maps[b:b + 1]).numpy() for b in range(maps.size(0))])
     dec = su.DecodeSBP([256, 192], 0.99, False)
     out["joints_raw_thr0.99"] = np.stack([dec(maps[b:b + 1]).numpy() for b in range(maps.size(0))])
+    # near-ties: top logits 1-4 ulp apart -- the pick depends on the last bit of torch.sigmoid (CPU tensors here)
+    near = cases.sbp_neartie_maps()
+    out["neartie_sha"] = np.array(cases.digest(near))
+    dec = su.DecodeSBP([256, 192], 0.25, True)
+    out["joints_neartie_thr0.25"] = np.stack([dec(near[b:b + 1]).numpy() for b in range(near.size(0))])
     np.savez_compressed(os.path.join(OUT, "sbp_adversarial.npz"), **out)
     print("sbp adversarial ok")
 

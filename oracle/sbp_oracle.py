@@ -175,21 +175,35 @@ def sbp_decode_loop(x, input_w, conf_threshold, pred=True):
     return joints
 
 
+def reference_sigmoid(x):
+    """torch.sigmoid applied the way DecodeSBP.forward does (utils/sbp_utils.py:104-109): one [1,K,H,W] sample per call.
+    Which elements go through ATen's vectorised body (Sleef expf) and which through its scalar tail (glibc expf) depends on
+    the size of the tensor handed to torch.sigmoid, so the batched oracle keeps the per-sample calls."""
+    if x.device.type != "cpu" or x.size(0) <= 1:
+        return torch.sigmoid(x)
+    return torch.cat([torch.sigmoid(x[b:b + 1]) for b in range(x.size(0))])
+
+
 def sbp_decode(x, input_w, conf_threshold, pred=True):
-    """Batched, vectorised: x [B,K,H,W] fp32 -> [B,K,3] fp32.  Same semantics as the loop form."""
+    """Batched, vectorised: x [B,K,H,W] fp32 -> [B,K,3] fp32.  Same semantics as the loop form.  Works on CPU tensors (the
+    oracle proper: ATen's CPU sigmoid) and on CUDA tensors (ATen's CUDA sigmoid -- what the reference computes when its
+    Lightning module runs on a GPU); the result is returned on the CPU."""
     b, k, hh, ww = x.shape
-    h = torch.sigmoid(x) if pred else x
-    flat = h.reshape(b * k, hh * ww).numpy()
-    thr = np.float32(conf_threshold)               # torch compares in the tensor dtype
+    h = reference_sigmoid(x) if pred else x
+    flat = h.reshape(b * k, hh * ww)
+    thr = torch.tensor(conf_threshold, dtype=torch.float32, device=x.device)      # torch compares in the tensor dtype
     cand = flat > thr
-    masked = np.where(cand, flat, -np.inf)
-    idx = np.argmax(masked, axis=1)                # first row-major maximum
-    any_c = cand.any(axis=1)
-    out = np.full((b * k, 3), -1.0, dtype=np.float32)
-    out[any_c, 0] = (idx % ww)[any_c]
-    out[any_c, 1] = (idx // ww)[any_c]
-    out[any_c, 2] = flat[np.arange(b * k), idx][any_c]
-    t = torch.from_numpy(out.reshape(b, k, 3))
+    masked = torch.where(cand, flat, torch.full_like(flat, -float("inf")))
+    best = masked.max(dim=1, keepdim=True).values
+    pos = torch.arange(hh * ww, device=x.device).expand_as(flat)
+    idx = torch.where(masked == best, pos, torch.full_like(pos, hh * ww)).min(dim=1).values   # first row-major maximum
+    any_c = cand.any(dim=1)
+    out = torch.full((b * k, 3), -1.0, dtype=torch.float32, device=x.device)
+    idx_c = idx.clamp(max=hh * ww - 1)
+    out[:, 0] = torch.where(any_c, (idx_c % ww).float(), out[:, 0])
+    out[:, 1] = torch.where(any_c, (idx_c // ww).float(), out[:, 1])
+    out[:, 2] = torch.where(any_c, flat.gather(1, idx_c[:, None])[:, 0], out[:, 2])
+    t = out.reshape(b, k, 3).cpu()
     t[..., :2] *= (input_w / ww)
     return t
 

@@ -11,8 +11,22 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("POSE_B200_LIB") or os.path.join(_HERE, "libpose_b200.so")
 
 KP_F32, KP_F64 = 0, 1
-F_GRAD, F_TARGET_OUT, F_DECODE, F_TMA = 1, 2, 4, 8
-DECODE_DIRECT, DECODE_INTERVAL = 0, 1
+F_GRAD, F_TARGET_OUT, F_DECODE, F_TMA, F_SIGMOID_CUDA = 1, 2, 4, 8, 16
+SIGMOID_ATEN_CPU, SIGMOID_ATEN_CUDA = 0, 1
+
+# Which torch.sigmoid the decoders reproduce bit for bit when ranking near-equal logits (include/pose_b200.h).
+# "cpu": the reference on CPU tensors (what the golden vectors hold) -- the default, it is what the parity tests pin;
+# "cuda": the reference on CUDA tensors (what the Lightning modules ran).  POSE_B200_SIGMOID_REF overrides the default.
+DEFAULT_SIGMOID_REF = os.environ.get("POSE_B200_SIGMOID_REF", "cpu")
+
+
+def sigmoid_ref_code(name=None):
+    name = DEFAULT_SIGMOID_REF if name is None else name
+    if name in ("cpu", "aten_cpu", SIGMOID_ATEN_CPU):
+        return SIGMOID_ATEN_CPU
+    if name in ("cuda", "aten_cuda", SIGMOID_ATEN_CUDA):
+        return SIGMOID_ATEN_CUDA
+    raise ValueError(f"sigmoid_ref must be 'cpu' or 'cuda', got {name!r}")
 
 _c = ctypes
 _vp, _i, _u, _f, _d, _ull = _c.c_void_p, _c.c_int, _c.c_uint, _c.c_float, _c.c_double, _c.c_ulonglong
@@ -20,6 +34,7 @@ _vp, _i, _u, _f, _d, _ull = _c.c_void_p, _c.c_int, _c.c_uint, _c.c_float, _c.c_d
 # name -> (restype, argtypes); mirrors include/pose_b200.h one to one
 SIGNATURES = {
     "pose_b200_version": (_i, []),
+    "pose_b200_source_hash": (_c.c_char_p, []),
     "pose_b200_last_error": (_c.c_char_p, []),
     "pose_b200_launch_count": (_ull, []),
     "pose_gauss_template_host": (_i, [_d, _vp, _i]),
@@ -40,15 +55,16 @@ SIGNATURES = {
     "pose_spm_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _d, _i, _vp, _ull, _vp]),
     "pose_spm_fused_workspace_bytes": (_ull, []),
     "pose_spm_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _f, _f, _d, _u, _vp, _ull, _vp]),
-    "pose_spm_decode_workspace_bytes": (_ull, [_i, _i]),
-    "pose_spm_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _d, _i, _f, _vp, _ull, _vp]),
+    "pose_spm_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _d, _i, _i, _f, _vp]),
+    "pose_spm_rescale": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "pose_spm_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp]),
     "pose_oks_matrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _c.c_longlong, _i, _vp]),
     "pose_oks_match_workspace_bytes": (_ull, [_i, _i, _i]),
     "pose_oks_match": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _ull, _vp]),
     "pose_ap_accumulate_workspace_bytes": (_ull, [_i, _i, _i]),
     "pose_ap_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ull, _vp]),
-    "pose_sigmoid_monotone_check": (_i, [_vp, _vp]),
+    "pose_sigmoid_ref_eval": (_i, [_vp, _vp, _ull, _i, _vp]),
+    "pose_sigmoid_window_check": (_i, [_vp, _i, _vp]),
 }
 
 MAX_PEERS = 16
@@ -82,6 +98,13 @@ def lib():
                     raise PoseB200Error(
                         f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(nvcc, sm_100a).  pose_b200 has no CPU or PyTorch fallback.")
+                if not os.environ.get("POSE_B200_LIB"):        # an explicitly named variant build is the caller's business
+                    from . import build as _build
+                    have, want = _build.embedded_hash(LIB_PATH), _build.source_hash()
+                    if have != want:
+                        raise PoseB200Error(
+                            f"{LIB_PATH} is stale: it was built from sources with hash {have}, the tree has {want}.  Rebuild it "
+                            "with `python -c 'import __graft_entry__ as g; g.build()'`.")
                 handle = ctypes.CDLL(LIB_PATH)
                 for name, (res, args) in SIGNATURES.items():
                     fn = getattr(handle, name)

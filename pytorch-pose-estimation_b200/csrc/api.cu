@@ -1,6 +1,8 @@
 // extern "C" boundary of libpose_b200.so (see include/pose_b200.h for the contract).
 #include <atomic>
 #include <cmath>
+#include <mutex>
+#include <unordered_map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +18,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local int g_err_code = 0;
 std::atomic<unsigned long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -23,8 +26,10 @@ int fail(int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+    g_err_code = code;
     return code;
 }
+int last_code() { return g_err_code ? g_err_code : POSE_EINVAL; }
 
 int check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -42,18 +47,79 @@ pose::FastDiv make_div(int d) {
     return f;
 }
 
-int sm_count() {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms > 0 ? sms : 148;
+// ---- launch-configuration cache.  The occupancy query, the device-attribute query and the opt-in to large dynamic shared
+// memory are properties of (kernel, device, block size, shared memory): they are resolved once and kept, so a steady-state
+// call is argument checks + the launches and nothing else (no driver queries, no getenv).
+struct CfgKey {
+    const void* fn; int dev, threads; size_t smem;
+    bool operator==(const CfgKey& o) const { return fn == o.fn && dev == o.dev && threads == o.threads && smem == o.smem; }
+};
+struct CfgHash {
+    size_t operator()(const CfgKey& k) const {
+        return std::hash<const void*>()(k.fn) ^ (std::hash<size_t>()(k.smem) * 1000003u) ^ ((size_t)k.dev << 20) ^ (size_t)k.threads;
+    }
+};
+std::mutex g_cfg_mutex;
+std::unordered_map<CfgKey, int, CfgHash> g_resident;      // -> resident CTAs on the whole device
+std::unordered_map<CfgKey, size_t, CfgHash> g_dyn_smem;   // (kernel, device, 0, 0) -> largest dynamic shared memory opted in to so far
+int g_sms[64];                                            // SM count per device ordinal (0: not queried yet)
+
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
 }
 
-// persistent grid: resident CTAs per SM (occupancy API) x SM count, capped by the amount of work
+int sm_count() {
+    const int dev = current_device();
+    if (dev >= 0 && dev < 64 && g_sms[dev] > 0) return g_sms[dev];
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    if (dev >= 0 && dev < 64) g_sms[dev] = sms;
+    return sms;
+}
+
+// resident CTAs of `kern` on the current device; the first call for a configuration also opts the kernel in to `smem` bytes
+// of dynamic shared memory (static + dynamic above 48 KB needs it) -- returns 0 and sets the error text when that fails
 template <typename Kern>
-int persistent_grid(Kern kern, int threads, size_t smem, long long work_ctas) {
+int resident_ctas(Kern kern, int threads, size_t smem, const char* what) {
+    const CfgKey key{reinterpret_cast<const void*>(kern), current_device(), threads, smem};
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        auto it = g_resident.find(key);
+        if (it != g_resident.end()) return it->second;
+    }
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e == cudaSuccess && fa.sharedSizeBytes + smem > 48 * 1024) {
+        // the attribute is per kernel, not per launch: only ever raise it
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        size_t& have = g_dyn_smem[CfgKey{key.fn, key.dev, 0, 0}];
+        if (smem > have) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) have = smem;
+        }
+    }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    long long g = (long long)per_sm * sm_count();
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess || per_sm < 1) {
+        fail(e != cudaSuccess ? (int)e : POSE_EINVAL, "%s: kernel cannot be configured (%d threads, %zu B shared memory): %s", what, threads, smem,
+             e != cudaSuccess ? cudaGetErrorString(e) : "no CTA fits on an SM");
+        cudaGetLastError();
+        return 0;                                         // not cached: the caller reports the failure every time
+    }
+    const int total = per_sm * sm_count();
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    g_resident[key] = total;
+    return total;
+}
+
+// persistent grid: resident CTAs (occupancy x SM count, cached), capped by the amount of work; 0 = configuration failed
+template <typename Kern>
+int persistent_grid(Kern kern, int threads, size_t smem, long long work_ctas, const char* what = "launch") {
+    long long g = resident_ctas(kern, threads, smem, what);
+    if (g <= 0) return 0;
     if (g > pose::kMaxPartialBlocks) g = pose::kMaxPartialBlocks;
     if (g > work_ctas) g = work_ctas;
     return (int)(g < 1 ? 1 : g);
@@ -77,9 +143,15 @@ void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStrea
 }
 
 long long exchange_timeout_cycles() {
-    // ~2 s at 2 GHz: a peer that never signals must not hang this GPU (POSE_B200_EXCHANGE_TIMEOUT_CYCLES overrides; diagnostics)
-    if (const char* e = getenv("POSE_B200_EXCHANGE_TIMEOUT_CYCLES")) return atoll(e);
-    return 4000000000ll;
+    // A peer that NEVER signals must not hang this GPU for good, but ranks legitimately drift by many seconds (checkpoint
+    // writes, a dataloader stall, rank-0-only validation): the wait gives up after ~10 minutes of SM clock, poisons the
+    // loss with NaN and sets ctrl->error, which PeerExchange.flush() / gathered_*() turn into an exception.
+    // POSE_B200_EXCHANGE_TIMEOUT_CYCLES overrides (read once).
+    static const long long cycles = [] {
+        const char* e = getenv("POSE_B200_EXCHANGE_TIMEOUT_CYCLES");
+        return e ? atoll(e) : 1200000000000ll;
+    }();
+    return cycles;
 }
 
 pose::ExchangeDev to_dev(const pose_exchange_t& x, double w0 = 0.0, double w1 = 0.0, double inv_norm = 0.0) {
@@ -109,7 +181,8 @@ template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
 int launch_fused(const pose::SbpFusedParams& P0, size_t smem, cudaStream_t st, int* grid_out) {
     pose::SbpFusedParams P = P0;
     const long long ctas = (P.n_maps + pose::kSbpWarps - 1) / pose::kSbpWarps;
-    const int grid = persistent_grid(pose::sbp_fused_kernel<V, TGT, GRAD, WTGT, DEC>, pose::kSbpThreads, smem, ctas);
+    const int grid = persistent_grid(pose::sbp_fused_kernel<V, TGT, GRAD, WTGT, DEC>, pose::kSbpThreads, smem, ctas, "sbp_fused");
+    if (grid == 0) return last_code();
     pose::sbp_fused_kernel<V, TGT, GRAD, WTGT, DEC><<<grid, pose::kSbpThreads, smem, st>>>(P);
     *grid_out = grid;
     return check_launch("sbp_fused");
@@ -118,10 +191,9 @@ template <bool GRAD, bool DEC>
 int launch_fused_tma(const pose::SbpFusedParams& P0, cudaStream_t st, int* grid_out) {
     pose::SbpFusedParams P = P0;
     const size_t smem = pose::sbp_tma_smem_bytes(P.lut_n);
-    cudaError_t e = cudaFuncSetAttribute(pose::sbp_fused_tma_kernel<GRAD, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "sbp_fused(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const long long ctas = (P.n_maps + pose::kTmaWarps - 1) / pose::kTmaWarps;
-    const int grid = persistent_grid(pose::sbp_fused_tma_kernel<GRAD, DEC>, pose::kTmaThreads, smem, ctas);
+    const int grid = persistent_grid(pose::sbp_fused_tma_kernel<GRAD, DEC>, pose::kTmaThreads, smem, ctas, "sbp_fused(tma)");
+    if (grid == 0) return last_code();
     pose::sbp_fused_tma_kernel<GRAD, DEC><<<grid, pose::kTmaThreads, smem, st>>>(P);
     *grid_out = grid;
     return check_launch("sbp_fused_tma");
@@ -143,7 +215,14 @@ int dispatch_fused(const pose::SbpFusedParams& P, unsigned flags, size_t smem, c
 
 extern "C" {
 
-int pose_b200_version(void) { return 100; }
+#ifndef POSE_B200_SOURCE_HASH_STR
+#define POSE_B200_SOURCE_HASH_STR "unhashed-build"
+#endif
+// searched for in the file by build.py / _cabi.py (no dlopen needed): the hash of the sources this binary was compiled from
+static const char g_source_hash[] = "POSE_B200_SOURCE_HASH=" POSE_B200_SOURCE_HASH_STR;
+
+int pose_b200_version(void) { return 200; }
+const char* pose_b200_source_hash(void) { return g_source_hash + sizeof("POSE_B200_SOURCE_HASH=") - 1; }
 const char* pose_b200_last_error(void) { return g_err; }
 unsigned long long pose_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -175,10 +254,12 @@ int pose_sbp_render(const void* kp, int kp_dtype, float* target, int N, int K, i
     const long long ctas = (P.n_maps + pose::kSbpWarps - 1) / pose::kSbpWarps;
     cudaStream_t st = (cudaStream_t)stream;
     if (vec) {
-        const int grid = persistent_grid(pose::sbp_render_kernel<4>, pose::kSbpThreads, smem, ctas);
+        const int grid = persistent_grid(pose::sbp_render_kernel<4>, pose::kSbpThreads, smem, ctas, "sbp_render");
+        if (grid == 0) return last_code();
         pose::sbp_render_kernel<4><<<grid, pose::kSbpThreads, smem, st>>>(P);
     } else {
-        const int grid = persistent_grid(pose::sbp_render_kernel<1>, pose::kSbpThreads, smem, ctas);
+        const int grid = persistent_grid(pose::sbp_render_kernel<1>, pose::kSbpThreads, smem, ctas, "sbp_render");
+        if (grid == 0) return last_code();
         pose::sbp_render_kernel<1><<<grid, pose::kSbpThreads, smem, st>>>(P);
     }
     return check_launch("sbp_render");
@@ -228,6 +309,7 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
     P.gpos = (float)(2.0 * (double)lambda_pos * inv_norm);
     P.gneg = (float)(2.0 * (double)lambda_neg * inv_norm);
     P.n_maps = (long long)N * K; P.H = H; P.W = W; P.HW = H * W; P.divW = make_div(W);
+    P.sig_ref = (flags & POSE_F_SIGMOID_CUDA) ? POSE_SIGMOID_ATEN_CUDA : POSE_SIGMOID_ATEN_CPU;
     if (exchange && exchange->defer) {           // in-band mode: the fused kernel publishes the previous step and opens this one
         if (N == 0) return fail(POSE_EINVAL, "sbp_fused: the in-band exchange needs a non-empty shard");
         P.xpub.world = exchange->world; P.xpub.rank = exchange->rank;
@@ -321,28 +403,26 @@ int pose_scale_grad(float* dlogits, const float* grad_output, unsigned long long
 }
 
 int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W, float conf_threshold, int apply_sigmoid,
-                    float coord_scale, int refine, int mode, pose_stream_t stream) {
+                    float coord_scale, int refine, int sigmoid_ref, pose_stream_t stream) {
     if (int rc = check_map_shape(N, K, H, W)) return rc;
-    if (mode != POSE_DECODE_DIRECT && mode != POSE_DECODE_INTERVAL) return fail(POSE_EINVAL, "sbp_decode: bad mode %d", mode);
+    if (sigmoid_ref != POSE_SIGMOID_ATEN_CPU && sigmoid_ref != POSE_SIGMOID_ATEN_CUDA) return fail(POSE_EINVAL, "sbp_decode: bad sigmoid_ref %d", sigmoid_ref);
     if (N == 0) return POSE_OK;
     if (!x || !joints) return fail(POSE_EINVAL, "sbp_decode: NULL pointer");
     pose::SbpDecodeParams P;
     P.x = x; P.joints = joints; P.thr = conf_threshold; P.scale = coord_scale;
-    P.n_maps = (long long)N * K; P.H = H; P.W = W; P.HW = H * W; P.divW = make_div(W); P.refine = refine;
+    P.n_maps = (long long)N * K; P.H = H; P.W = W; P.HW = H * W; P.divW = make_div(W); P.refine = refine; P.sig_ref = sigmoid_ref;
     const bool vec = (P.HW % 4 == 0) && aligned16(x);
     const long long ctas = (P.n_maps + pose::kSbpWarps - 1) / pose::kSbpWarps;
     cudaStream_t st = (cudaStream_t)stream;
-#define POSE_DEC(V, S, I)                                                                             \
-    {                                                                                                 \
-        const int grid = persistent_grid(pose::sbp_decode_kernel<V, S, I>, pose::kSbpThreads, 0, ctas); \
-        pose::sbp_decode_kernel<V, S, I><<<grid, pose::kSbpThreads, 0, st>>>(P);                      \
+#define POSE_DEC(V, S)                                                                                        \
+    {                                                                                                         \
+        const int grid = persistent_grid(pose::sbp_decode_kernel<V, S>, pose::kSbpThreads, 0, ctas, "sbp_decode"); \
+        if (grid == 0) return last_code();                                                                    \
+        pose::sbp_decode_kernel<V, S><<<grid, pose::kSbpThreads, 0, st>>>(P);                                 \
     }
-    const bool sig = apply_sigmoid != 0, itv = mode == POSE_DECODE_INTERVAL;
-    if (vec) {
-        if (sig && itv) POSE_DEC(4, true, true) else if (sig) POSE_DEC(4, true, false) else if (itv) POSE_DEC(4, false, true) else POSE_DEC(4, false, false)
-    } else {
-        if (sig && itv) POSE_DEC(1, true, true) else if (sig) POSE_DEC(1, true, false) else if (itv) POSE_DEC(1, false, true) else POSE_DEC(1, false, false)
-    }
+    const bool sig = apply_sigmoid != 0;
+    if (vec) { if (sig) POSE_DEC(4, true) else POSE_DEC(4, false) }
+    else { if (sig) POSE_DEC(1, true) else POSE_DEC(1, false) }
 #undef POSE_DEC
     return check_launch("sbp_decode");
 }
@@ -360,7 +440,8 @@ int pose_sbp_decode_flip(const float* x, const float* x_flip, const int* flip_pe
     cudaStream_t st = (cudaStream_t)stream;
 #define POSE_DECF(V, S)                                                                                \
     {                                                                                                  \
-        const int grid = persistent_grid(pose::sbp_decode_flip_kernel<V, S>, pose::kSbpThreads, 0, ctas); \
+        const int grid = persistent_grid(pose::sbp_decode_flip_kernel<V, S>, pose::kSbpThreads, 0, ctas, "sbp_decode_flip"); \
+        if (grid == 0) return last_code();                                                             \
         pose::sbp_decode_flip_kernel<V, S><<<grid, pose::kSbpThreads, 0, st>>>(P);                     \
     }
     const bool sig = apply_sigmoid != 0;
@@ -533,28 +614,32 @@ int pose_spm_fused(const float* logits, const long long* centers, const long lon
     return check_launch("loss_reduce");
 }
 
-unsigned long long pose_spm_decode_workspace_bytes(int N, int R) { (void)N; (void)R; return 0ull; }
-
 int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* counts_total, int N, int Pmax, int K, int R,
-                    float conf_threshold, double dist_threshold, int apply_act, float input_size, void* workspace,
-                    unsigned long long workspace_bytes, pose_stream_t stream) {
-    (void)workspace; (void)workspace_bytes;
+                    float conf_threshold, double dist_threshold, int apply_act, int sigmoid_ref, float input_size, pose_stream_t stream) {
     if (N < 0 || Pmax <= 0 || K <= 0 || R <= 0) return fail(POSE_EINVAL, "spm_decode: bad shape");
     if (!x || !roots || !kps || !counts) return fail(POSE_EINVAL, "spm_decode: NULL pointer");
     if (!(dist_threshold >= 0.0) || dist_threshold > 1024.0) return fail(POSE_EINVAL, "spm_decode: bad dist_threshold");
+    if (sigmoid_ref != POSE_SIGMOID_ATEN_CPU && sigmoid_ref != POSE_SIGMOID_ATEN_CUDA) return fail(POSE_EINVAL, "spm_decode: bad sigmoid_ref %d", sigmoid_ref);
     if (R > 8192) return fail(POSE_EINVAL, "spm_decode: R=%d too large", R);
     // suppressed-pixel bitmap of the dense-map fallback: R*R bits
     const size_t smem = ((size_t)R * R + 31) / 32 * sizeof(unsigned int);
     if (smem > 160 * 1024) return fail(POSE_EINVAL, "spm_decode: R=%d: the suppression bitmap does not fit in shared memory", R);
     if (N == 0) return POSE_OK;
-    if (smem > 32 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(pose::spm_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "spm_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    }
+    // (static + dynamic shared memory above 48 KB needs the opt-in: resolved once per (device, size) by the configuration cache)
+    if (resident_ctas(pose::spm_decode_kernel, pose::kSpmDecThreads, smem, "spm_decode") == 0) return last_code();
     pose::SpmDecodeParams P;
     P.x = x; P.roots = roots; P.kps = kps; P.counts = counts; P.counts_total = counts_total;
     P.N = N; P.Pmax = Pmax; P.K = K; P.R = R; P.C = 1 + 2 * K;
-    P.thr = conf_threshold; P.dist_thr = dist_threshold; P.apply_act = apply_act;
+    P.thr = conf_threshold; P.dist_thr = dist_threshold; P.apply_act = apply_act; P.sig_ref = sigmoid_ref;
+    {   // logits that cannot pass `sigmoid(x) > thr` under either reference sigmoid (relative error < 2^-20): x <= logit(thr (1 - 4e-6))
+        const double t = (double)conf_threshold;
+        if (!(t > 0.0)) P.x_lo = -INFINITY;                     // thr <= 0 (or NaN): every logit is evaluated exactly
+        else if (t >= 1.0) P.x_lo = INFINITY;                   // a sigmoid never exceeds 1
+        else {
+            const double tl = t * (1.0 - 4e-6);
+            P.x_lo = std::nextafterf((float)std::log(tl / (1.0 - tl)), -INFINITY);
+        }
+    }
     P.zf = (float)std::sqrt((double)((long long)R * R + (long long)R * R));
     P.input_size = input_size;
     {   // nms_spm keeps candidates with sqrt(dx^2+dy^2) > dist_thr (fp64 sqrt of an integer): the same predicate as an integer bound
@@ -567,6 +652,18 @@ int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* 
     return check_launch("spm_decode");
 }
 
+int pose_spm_rescale(const float* kps, const int* counts, const long long* image_w, const long long* image_h, float* out,
+                     int N, int Pmax, int K, float input_size, pose_stream_t stream) {
+    if (N < 0 || Pmax <= 0 || K <= 0 || !(input_size > 0.0f)) return fail(POSE_EINVAL, "spm_rescale: bad shape");
+    if (N == 0) return POSE_OK;
+    if (!kps || !counts || !image_w || !image_h || !out) return fail(POSE_EINVAL, "spm_rescale: NULL pointer");
+    const long long total = (long long)N * Pmax * K;
+    long long blocks = (total + 255) / 256, cap = (long long)sm_count() * 8;
+    pose::spm_rescale_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(kps, counts, image_w, image_h, out, N, Pmax, K,
+                                                                                                     input_size);
+    return check_launch("spm_rescale");
+}
+
 int pose_spm_gather(const float* roots, const float* disp, float* kps, int n_roots, int K, int R, double dist_threshold,
                     pose_stream_t stream) {
     if (n_roots < 0 || K <= 0 || R <= 0 || !disp || (n_roots > 0 && (!roots || !kps))) return fail(POSE_EINVAL, "spm_gather: bad argument");
@@ -577,13 +674,22 @@ int pose_spm_gather(const float* roots, const float* disp, float* kps, int n_roo
     return check_launch("spm_gather");
 }
 
-int pose_sigmoid_monotone_check(unsigned long long* violations_out, pose_stream_t stream) {
-    if (!violations_out) return fail(POSE_EINVAL, "monotone_check: NULL pointer");
+int pose_sigmoid_ref_eval(const float* x, float* y, unsigned long long n, int sigmoid_ref, pose_stream_t stream) {
+    if (sigmoid_ref != POSE_SIGMOID_ATEN_CPU && sigmoid_ref != POSE_SIGMOID_ATEN_CUDA) return fail(POSE_EINVAL, "sigmoid_ref_eval: bad sigmoid_ref %d", sigmoid_ref);
+    if (n == 0) return POSE_OK;
+    if (!x || !y) return fail(POSE_EINVAL, "sigmoid_ref_eval: NULL pointer");
+    pose::sigmoid_ref_eval_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(x, y, n, sigmoid_ref);
+    return check_launch("sigmoid_ref_eval");
+}
+
+int pose_sigmoid_window_check(unsigned long long* violations_out, int sigmoid_ref, pose_stream_t stream) {
+    if (!violations_out) return fail(POSE_EINVAL, "sigmoid_window_check: NULL pointer");
+    if (sigmoid_ref != POSE_SIGMOID_ATEN_CPU && sigmoid_ref != POSE_SIGMOID_ATEN_CUDA) return fail(POSE_EINVAL, "sigmoid_window_check: bad sigmoid_ref %d", sigmoid_ref);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(violations_out, 0, sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return fail((int)e, "monotone_check: %s", cudaGetErrorString(e));
-    pose::sigmoid_monotone_kernel<<<sm_count() * 8, 256, 0, st>>>(violations_out);
-    return check_launch("sigmoid_monotone");
+    if (e != cudaSuccess) return fail((int)e, "sigmoid_window_check: %s", cudaGetErrorString(e));
+    pose::sigmoid_window_check_kernel<<<sm_count() * 8, 256, 0, st>>>(violations_out, sigmoid_ref);
+    return check_launch("sigmoid_window_check");
 }
 
 int pose_oks_matrix(const double* det_kp, const double* gt_kp, const double* gt_bbox, const double* gt_area,

@@ -58,6 +58,62 @@ __device__ __forceinline__ float sigmoid_fast(float x) {
     return r;
 }
 
+// ---------------------------------------------------------------- the reference's sigmoid, bit for bit
+// "argmax of sigmoid(x), first row-major index among equal values" (utils/sbp_utils.py:73-78) depends on WHICH fp32
+// sigmoid is meant: fp32 sigmoid is many-to-one and two implementations that differ by one ulp merge different
+// neighbours.  sigmoid_fast above is neither of torch's, so decode never decides a tie with it: candidates are found
+// in logit space (sigmoid_window_lo) and ranked with one of the two functions below, selected by the caller.
+//
+// POSE_SIGMOID_ATEN_CPU: torch.sigmoid on a contiguous CPU tensor = 1 / (1 + Sleef_expf_u10(-x)) in the AVX2 / AVX512
+// kernels of ATen (identical results in both; verified against torch 2.11 for all 2^32 inputs with the C restatement kept
+// beside the tests, which this function follows operation for operation; every operation is IEEE so the device
+// reproduces it exactly).  [Elements of a tail shorter than two vectors go through glibc expf in ATen; the reference's
+// shapes (K*H*W a multiple of 32) have no tail.]
+__device__ __forceinline__ float sleef_expf_u10(float d) {
+    const int q = __float2int_rn(__fmul_rn(d, 1.442695040888963407359924681001892137426645954152985934135449406931f));
+    const float qf = (float)q;
+    float s = __fmaf_rn(qf, -0.693145751953125f, d);
+    s = __fmaf_rn(qf, -1.428606765330187045e-06f, s);
+    float u = 0.000198527617612853646278381f;
+    u = __fmaf_rn(u, s, 0.00139304355252534151077271f);
+    u = __fmaf_rn(u, s, 0.00833336077630519866943359f);
+    u = __fmaf_rn(u, s, 0.0416664853692054748535156f);
+    u = __fmaf_rn(u, s, 0.166666671633720397949219f);
+    u = __fmaf_rn(u, s, 0.5f);
+    u = __fadd_rn(1.0f, __fmaf_rn(__fmul_rn(s, s), u, s));
+    const int qh = q >> 1;
+    u = __fmul_rn(__fmul_rn(u, __int_as_float((qh + 0x7f) << 23)), __int_as_float((q - qh + 0x7f) << 23));
+    if (d < -104.0f) u = 0.0f;
+    if (100.0f < d) u = INFINITY;
+    return u;
+}
+__device__ __forceinline__ float sigmoid_aten_cpu(float x) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, sleef_expf_u10(-x)));
+}
+// POSE_SIGMOID_ATEN_CUDA: torch.sigmoid on a CUDA tensor = 1 / (1 + expf(-x)) compiled without fast-math
+// (ATen/native/cuda/UnarySpecialOpsKernel.cu): libdevice expf, IEEE add and divide.  This file is compiled without
+// --use_fast_math, so the same three operations are what nvcc emits here (a GPU test compares with torch bit for bit).
+__device__ __forceinline__ float sigmoid_aten_cuda(float x) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+constexpr int kSigmoidAtenCpu = 0;
+constexpr int kSigmoidAtenCuda = 1;
+// runtime selection: evaluated a handful of times per map (never in the streaming loop), so a uniform branch is free
+__device__ __forceinline__ float sigmoid_ref(float x, int ref) { return ref == kSigmoidAtenCuda ? sigmoid_aten_cuda(x) : sigmoid_aten_cpu(x); }
+
+// Lower end of the candidate window of a map whose largest logit is m: every x < sigmoid_window_lo(m) has
+// sigmoid_ref(x) < sigmoid_ref(m) for both references, so only elements >= lo can be the reference's argmax.
+// Both references are sigma(x) (1 + eta), |eta| <= d (1 - sigma(x)) + 2^-22 with d = 2^-21 (exp within 4 ulp -- Sleef u10:
+// 1, libdevice expf: 2 -- one rounding for 1 + e and one for the quotient).  With q = 1 - sigma(m), w = m - x <= 1/2:
+// ln sigma(m) - ln sigma(x) >= w q and 1 - sigma(x) <= q e^w, so w q > d q (1 + e^w) + 2^-21 suffices:
+// w = 2.7 d + 2^-21 / q (times a 1.125 safety factor; q from the fast sigmoid, relative error ~1e-6).  Where that exceeds 1/2
+// (m > 13.8: the sigmoid is within a few ulp of 1) the window is everything above 13: sigma(13.8) - sigma(13) is 21 ulp.
+__device__ __forceinline__ float sigmoid_window_lo(float m) {
+    const float q = sigmoid_fast(-m);                       // 1 - sigma(m); 1 for m -> -inf, 0 for m -> +inf
+    const float w = 1.125f * (2.7f * 4.76837158e-7f + __fdividef(4.76837158e-7f, q));
+    return (w < 0.5f) ? __fsub_rd(m, w) : 13.0f;
+}
+
 // ---------------------------------------------------------------- warp reductions
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

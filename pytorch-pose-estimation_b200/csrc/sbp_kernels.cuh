@@ -34,15 +34,6 @@ namespace pose {
 #ifndef POSE_FUSED_MINB_NGD
 #define POSE_FUSED_MINB_NGD 3   // register cap 80
 #endif
-// Software-pipelined streaming loop of the render variants (0 = off): the map is cut into stages of PIPE 128-bit loads per lane and the
-// loads of stage i+1 -- across map boundaries too -- are issued before stage i is computed, so a warp always has PIPE..2*PIPE
-// loads in flight instead of alternating "load U, compute U".  Same registers as U = 2*PIPE.
-#ifndef POSE_FUSED_PIPE
-#define POSE_FUSED_PIPE 0
-#endif
-#ifndef POSE_FUSED_PIPE_NG
-#define POSE_FUSED_PIPE_NG 0
-#endif
 constexpr int kSbpThreads = 256;               // 8 warps per CTA
 constexpr int kSbpWarps = kSbpThreads / 32;
 constexpr int kMaxPartialBlocks = 148 * 16;    // upper bound on the persistent grid (workspace sizing)
@@ -149,6 +140,83 @@ __device__ __forceinline__ bool patch_values(const Patch& p, const float* __rest
     return any;
 }
 
+// ---------------------------------------------------------------- argmax of sigmoid(x): search in logit space, rank with the reference's sigmoid
+// nms_sbp (utils/sbp_utils.py:71-80) takes the first row-major index of the largest sigmoid VALUE, and fp32 sigmoid is
+// many-to-one, so which neighbours tie depends on the sigmoid implementation to the last bit (common.cuh).  The streaming
+// loop therefore never evaluates a sigmoid for the decode: each lane tracks, per 128-bit vector, the largest logit of its
+// share of the map (value, vector index, the vector's 4 values) and the second-largest vector maximum; at the end of the map
+// the warp derives the candidate window [lo, m] from the map maximum m (sigmoid_window_lo: nothing below lo can reach
+// sigmoid_ref(m)), and ranks the candidates -- almost always exactly one element -- with the reference's own sigmoid
+// (sigmoid_ref, bit-exact, also the reported confidence).  Only when some lane holds two candidate vectors (it kept one) or
+// the map is degenerate does the warp look at the map a second time (L2 hit).  2 FMNMX3/FMNMX + 1 FSETP + 6 predicated
+// moves per vector, no MUFU.
+template <int V>
+struct ArgTrack {
+    float best, second;     // largest / second-largest vector maximum seen by this lane (NaNs ignored)
+    int bestvi;             // vector index of `best` (first occurrence)
+    float keep[V];          // the elements of that vector
+    __device__ __forceinline__ void reset() {
+        best = second = -INFINITY; bestvi = 0;
+#pragma unroll
+        for (int j = 0; j < V; ++j) keep[j] = -INFINITY;
+    }
+    template <bool SIG>
+    __device__ __forceinline__ void push(const float (&x)[V], int vi) {
+        float vm = x[0];
+#pragma unroll
+        for (int j = 1; j < V; ++j) vm = fmaxf(vm, x[j]);
+        if (SIG) second = fmaxf(second, fminf(vm, best));
+        if (vm > best) {
+            best = vm; bestvi = vi;
+#pragma unroll
+            for (int j = 0; j < V; ++j) keep[j] = x[j];
+        }
+    }
+};
+
+// -> (conf, idx): the reference's activation value at its argmax and the flat index (0x7fffffff: nothing comparable in the map).
+// SIG == false (heat maps that are already activated, DecodeSBP.pred == False): candidates are the elements equal to m.
+template <int V, bool SIG>
+__device__ __forceinline__ void resolve_argmax(const ArgTrack<V>& a, const float* __restrict__ src, int nvec, int lane, int sig_ref,
+                                               float& conf, int& idx) {
+    const float m = warp_max(a.best);
+    float lo = m;
+    bool again = false;
+    if (SIG) {
+        lo = sigmoid_window_lo(m);
+        // m <= -80 (or no finite element at all): the references' results are denormal / zero there and the error model of
+        // the window does not hold -- rank every element
+        const bool degenerate = !(m > -80.0f);
+        if (degenerate) lo = -INFINITY;
+        again = degenerate || __any_sync(FULL_MASK, a.second >= lo);
+    }
+    float fb = -INFINITY;
+    int fi = 0x7fffffff;
+    if (!again) {
+        if (a.best >= lo) {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                if (a.keep[j] >= lo) {
+                    const float f = SIG ? sigmoid_ref(a.keep[j], sig_ref) : a.keep[j];
+                    if (f > fb) { fb = f; fi = a.bestvi * V + j; }
+                }
+        }
+    } else {
+        for (int vi = lane; vi < nvec; vi += 32) {
+            float x[V];
+            Vec<V>::load_cached(src, vi, x);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                if (x[j] >= lo) {
+                    const float f = sigmoid_ref(x[j], sig_ref);
+                    if (f > fb) { fb = f; fi = vi * V + j; }
+                }
+        }
+    }
+    warp_argmax_first(fb, fi);
+    conf = fb; idx = fi;
+}
+
 // ---------------------------------------------------------------- render only
 struct SbpRenderParams {
     const void* kp; int kp_f64;
@@ -194,6 +262,7 @@ struct SbpFusedParams {
     float thr, scale;
     float gpos, gneg;            // 2*lambda*inv_norm
     long long n_maps; int H, W, HW; FastDiv divW;
+    int sig_ref;                 // DEC: which torch sigmoid ranks near-ties and gives the confidence (kSigmoidAtenCpu / kSigmoidAtenCuda)
     ExchangePub xpub;            // multi-GPU in-band exchange: block 0 publishes the previous step's flag (world == 0: off)
 };
 
@@ -213,16 +282,16 @@ __device__ __forceinline__ float loss_elem(float s, float t, float gpos, float g
     return (pos ? gpos : gneg) * d * ((1.0f - s) * s);
 }
 
-// One vector (V consecutive elements, flat index e = vi*V) of the fused render+loss(+grad)(+argmax) pass.
+// One vector (V consecutive elements, flat index e = vi*V) of the fused render+loss(+grad) pass.
 // Every lane first takes the zero-target result (the target is zero on ~93% of a map):
 //   S_neg += s^2,  dL/dp = gneg s^2 (1-s);
 // then one unsigned compare decides whether the vector can touch the rows of the joint's Gaussian patch; only those
 // lanes compute (row, col), look the template up and replace their elements' results (`arem` collects the s^2 terms
 // that have to be taken out of S_neg again, so the common path stays a single FFMA per element).
-template <int V, bool GRAD, bool WTGT, bool DEC>
+template <int V, bool GRAD, bool WTGT>
 __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[V], float (&tout)[V], int vi, const Patch& pt,
                                                 const float* __restrict__ lut_s, int lut_n, int W, FastDiv divW, float gpos, float gneg,
-                                                float& apos, float& aneg, float& arem, float& best, int& besti) {
+                                                float& apos, float& aneg, float& arem) {
     float sg[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -235,7 +304,6 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
         } else {
             aneg = fmaf(sj, sj, aneg);
         }
-        if (DEC && sj > best) { best = sj; besti = vi * V + j; }
         if (WTGT) tout[j] = 0.0f;
     }
     const int e = vi * V;
@@ -285,21 +353,23 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
 }
 
 // end of one map: flush the fp32 partials into fp64 (keeps the 2e8-term sum accurate and deterministic) and, when decoding,
-// reduce the lanes' argmax candidates and write the joint row
-template <bool DEC>
+// resolve the argmax and write the joint row
+template <int V, bool DEC>
 __device__ __forceinline__ void finish_map(const SbpFusedParams& P, long long map, int lane, float apos, float aneg, float arem,
-                                           float best, int besti, double& dpos, double& dneg) {
+                                           const ArgTrack<V>& arg, double& dpos, double& dneg) {
     dpos += (double)apos;
     dneg += (double)aneg - (double)arem;
     if (DEC) {
-        warp_argmax_first(best, besti);
+        float conf;
+        int idx;
+        resolve_argmax<V, true>(arg, P.logits + map * P.HW, P.HW / V, lane, P.sig_ref, conf, idx);
         if (lane == 0) {
             float jx = -1.0f, jy = -1.0f, jc = -1.0f;
-            if (best > P.thr) {
-                const int row = (int)fdiv((uint32_t)besti, P.divW);
-                jx = (float)(besti - row * P.W);
+            if (conf > P.thr && idx != 0x7fffffff) {
+                const int row = (int)fdiv((uint32_t)idx, P.divW);
+                jx = (float)(idx - row * P.W);
                 jy = (float)row;
-                jc = best;
+                jc = conf;
             }
             float* jo = P.joints + map * 3;
             jo[0] = __fmul_rn(jx, P.scale);
@@ -333,59 +403,6 @@ sbp_fused_kernel(SbpFusedParams P) {
     double kx = -1.0, ky = -1.0;
     if (TGT == TGT_RENDER && warp0 < P.n_maps) load_kp(P.kp, P.kp_f64, warp0, kx, ky);
 
-    constexpr int PIPE = (V == 4 && TGT == TGT_RENDER) ? ((GRAD || WTGT) ? POSE_FUSED_PIPE : POSE_FUSED_PIPE_NG) : 0;
-    if constexpr (PIPE > 0) {
-        // (map, stage) items as one continuous stream per warp: a load cursor runs one stage ahead of the compute cursor
-        const int nstage = (nvec + 32 * PIPE - 1) / (32 * PIPE);
-        long long lmap = warp0, cmap = warp0;
-        int lst = 0, cst = 0;
-        float bufA[PIPE][V], bufB[PIPE][V];
-        Patch pt;
-        float apos = 0.0f, aneg = 0.0f, arem = 0.0f, best = -INFINITY;
-        int besti = 0x7fffffff;
-        auto issue = [&](float (&buf)[PIPE][V]) {
-            if (lmap < P.n_maps) {
-                const float* lg = P.logits + lmap * P.HW;
-#pragma unroll
-                for (int u = 0; u < PIPE; ++u) {
-                    const int vi = lane + 32 * (lst * PIPE + u);
-                    if (vi < nvec) Vec<V>::load(lg, vi, buf[u]);
-                }
-                if (++lst == nstage) { lst = 0; lmap += nwarps; }
-            }
-        };
-        auto compute = [&](float (&buf)[PIPE][V]) {
-            if (cst == 0) {
-                pt = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
-                if (cmap + nwarps < P.n_maps) load_kp(P.kp, P.kp_f64, cmap + nwarps, kx, ky);
-            }
-            float* dl = GRAD ? P.dlogits + cmap * P.HW : nullptr;
-            float* to = WTGT ? P.target_out + cmap * P.HW : nullptr;
-#pragma unroll
-            for (int u = 0; u < PIPE; ++u) {
-                const int vi = lane + 32 * (cst * PIPE + u);
-                if (vi >= nvec) break;
-                float g[V], tv[V];
-                render_loss_vec<V, GRAD, WTGT, DEC>(buf[u], g, tv, vi, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem,
-                                                    best, besti);
-                if (GRAD) Vec<V>::store(dl, vi, g);
-                if (WTGT) Vec<V>::store(to, vi, tv);
-            }
-            if (++cst == nstage) {
-                finish_map<DEC>(P, cmap, lane, apos, aneg, arem, best, besti, dpos, dneg);
-                apos = aneg = arem = 0.0f; best = -INFINITY; besti = 0x7fffffff;
-                cst = 0; cmap += nwarps;
-            }
-        };
-        issue(bufA);
-        while (cmap < P.n_maps) {
-            issue(bufB);
-            compute(bufA);
-            if (cmap >= P.n_maps) break;
-            issue(bufA);
-            compute(bufB);
-        }
-    } else
     for (long long map = warp0; map < P.n_maps; map += nwarps) {
         const float* lg = P.logits + map * P.HW;
         const float* tg = (TGT == TGT_DENSE) ? P.target_in + map * P.HW : nullptr;
@@ -397,8 +414,8 @@ sbp_fused_kernel(SbpFusedParams P) {
             if (map + nwarps < P.n_maps) load_kp(P.kp, P.kp_f64, map + nwarps, kx, ky);
         }
         float apos = 0.0f, aneg = 0.0f, arem = 0.0f;
-        float best = -INFINITY;
-        int besti = 0x7fffffff;
+        ArgTrack<V> arg;
+        arg.reset();
 
         for (int base = lane; base < nvec; base += 32 * U) {
             float xv[U][V], tv[U][V];
@@ -415,22 +432,18 @@ sbp_fused_kernel(SbpFusedParams P) {
                 const int vi = base + 32 * u;
                 if (vi >= nvec) break;
                 float g[V];
+                if (DEC) arg.template push<true>(xv[u], vi);
                 if (TGT == TGT_RENDER) {
-                    render_loss_vec<V, GRAD, WTGT, DEC>(xv[u], g, tv[u], vi, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg,
-                                                        apos, aneg, arem, best, besti);
+                    render_loss_vec<V, GRAD, WTGT>(xv[u], g, tv[u], vi, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        const float sj = sigmoid_fast(xv[u][j]);
-                        g[j] = loss_elem<GRAD>(sj, tv[u][j], P.gpos, P.gneg, apos, aneg);
-                        if (DEC && sj > best) { best = sj; besti = vi * V + j; }
-                    }
+                    for (int j = 0; j < V; ++j) g[j] = loss_elem<GRAD>(sigmoid_fast(xv[u][j]), tv[u][j], P.gpos, P.gneg, apos, aneg);
                 }
                 if (GRAD) Vec<V>::store(dl, vi, g);
                 if (WTGT) Vec<V>::store(to, vi, tv[u]);
             }
         }
-        finish_map<DEC>(P, map, lane, apos, aneg, arem, best, besti, dpos, dneg);
+        finish_map<V, DEC>(P, map, lane, apos, aneg, arem, arg, dpos, dneg);
     }
 
     dpos = warp_sum(dpos);
@@ -553,125 +566,41 @@ struct SbpDecodeParams {
     float thr, scale;
     long long n_maps; int H, W, HW; FastDiv divW;
     int refine;
+    int sig_ref;             // SIG: kSigmoidAtenCpu / kSigmoidAtenCuda
 };
 
 template <bool SIG>
 __device__ __forceinline__ float act(float v) { return SIG ? sigmoid_fast(v) : v; }
 
-// Smallest float lo with act(lo) == s, given act(m) == s and act monotone non-decreasing: all elements
-// whose activation equals the maximum are exactly those with value >= lo.  Warp-cooperative: an
-// exponential probe below m (lane j tests key(m) - 2^j) followed by 32-ary search rounds.
-template <bool SIG>
-__device__ __forceinline__ float preimage_floor(float m, float s, int lane) {
-    if (!SIG) return m;
-    const uint32_t hi = float_key(m);
-    const uint32_t step = 1u << lane;
-    const uint32_t probe = hi >= step ? hi - step : 0u;
-    const bool same = act<SIG>(key_float(probe)) == s;
-    const unsigned bal = __ballot_sync(FULL_MASK, same);
-    if (!(bal & 1u)) return m;                       // even m's predecessor maps lower: lo == m
-    // first lane j whose probe is already below the pre-image: answer in (hi-2^j, hi-2^(j-1)]
-    const unsigned notsame = ~bal;
-    uint32_t L, R;
-    if (notsame == 0u) {                             // pre-image reaches below hi-2^31: search from key 0
-        L = 0u;
-        R = hi >= 0x80000000u ? hi - 0x80000000u : 0u;
-    } else {
-        const int j = __ffs(notsame) - 1;            // j >= 1: probe j is below the pre-image, probe j-1 inside
-        L = (hi >= (1u << j) ? hi - (1u << j) : 0u) + 1u;
-        R = hi - (1u << (j - 1));
-    }
-    // invariant: act(R) == s, answer in [L, R]
-    while (L < R) {
-        const uint64_t width = (uint64_t)(R - L);
-        const uint32_t p = L + (uint32_t)((width * (uint64_t)(lane + 1)) / 33u);
-        const bool ok = act<SIG>(key_float(p)) == s;
-        const unsigned b = __ballot_sync(FULL_MASK, ok);
-        if (b == 0u) {
-            L = __shfl_sync(FULL_MASK, p, 31) + 1u;
-        } else {
-            const int j = __ffs(b) - 1;
-            const uint32_t pj = __shfl_sync(FULL_MASK, p, j);
-            const uint32_t pjm = __shfl_sync(FULL_MASK, p, j > 0 ? j - 1 : 0);
-            R = pj;
-            if (j > 0) L = pjm + 1u;
-        }
-    }
-    return key_float(R);
-}
-
-template <int V, bool SIG, bool INTERVAL>
+template <int V, bool SIG>
 __global__ void __launch_bounds__(kSbpThreads) sbp_decode_kernel(SbpDecodeParams P) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * kSbpWarps + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kSbpWarps;
     const int nvec = P.HW / V;
-    constexpr int U = (V == 4) ? 8 : 8;
+    constexpr int U = 8;
 
     for (long long map = warp0; map < P.n_maps; map += nwarps) {
         const float* src = P.x + map * P.HW;
-        float best = -INFINITY;
-        int besti = 0x7fffffff;
-
-        if (INTERVAL) {
-            // pass 1: raw maximum (1 FMNMX per element, no SFU work); NaNs are ignored by fmaxf
-            float m = -INFINITY;
-            for (int base = lane; base < nvec; base += 32 * U) {
-                float xv[U][V];
+        ArgTrack<V> arg;
+        arg.reset();
+        for (int base = lane; base < nvec; base += 32 * U) {
+            float xv[U][V];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int vi = base + 32 * u;
-                    if (vi < nvec) Vec<V>::load_cached(src, vi, xv[u]);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < V; ++j) xv[u][j] = -INFINITY;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int j = 0; j < V; ++j) m = fmaxf(m, xv[u][j]);
+            for (int u = 0; u < U; ++u) {
+                const int vi = base + 32 * u;
+                if (vi < nvec) Vec<V>::load(src, vi, xv[u]);
             }
-            m = warp_max(m);
-            best = act<SIG>(m);
-            if (best > P.thr) {
-                const float lo = preimage_floor<SIG>(m, best, lane);
-                // pass 2: first row-major element >= lo; the map was just read by this warp (L1/L2 hit)
-                for (int base = 0; base < nvec; base += 32) {
-                    const int vi = base + lane;
-                    int hit = 0x7fffffff;
-                    if (vi < nvec) {
-                        float xv[V];
-                        Vec<V>::load_cached(src, vi, xv);
 #pragma unroll
-                        for (int j = V - 1; j >= 0; --j)
-                            if (xv[j] >= lo) hit = vi * V + j;
-                    }
-                    const unsigned b = __ballot_sync(FULL_MASK, hit != 0x7fffffff);
-                    if (b) { besti = __shfl_sync(FULL_MASK, hit, __ffs(b) - 1); break; }
-                }
+            for (int u = 0; u < U; ++u) {
+                const int vi = base + 32 * u;
+                if (vi >= nvec) break;
+                arg.template push<SIG>(xv[u], vi);
             }
-        } else {
-            for (int base = lane; base < nvec; base += 32 * U) {
-                float xv[U][V];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int vi = base + 32 * u;
-                    if (vi < nvec) Vec<V>::load(src, vi, xv[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int vi = base + 32 * u;
-                    if (vi >= nvec) break;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        const float s = act<SIG>(xv[u][j]);
-                        if (s > best) { best = s; besti = vi * V + j; }
-                    }
-                }
-            }
-            warp_argmax_first(best, besti);
         }
+        float best;
+        int besti;
+        resolve_argmax<V, SIG>(arg, src, nvec, lane, P.sig_ref, best, besti);
 
         if (lane == 0) {
             float jx = -1.0f, jy = -1.0f, jc = -1.0f;
@@ -781,20 +710,40 @@ __global__ void __launch_bounds__(256) sbp_backproject_kernel(const float* __res
     if (n < N) backproject_sample(joints, bbox, packed, n, K, in_h, in_w, threadIdx.x & 31);
 }
 
-// ---------------------------------------------------------------- sigmoid monotonicity (diagnostic)
-__global__ void sigmoid_monotone_kernel(unsigned long long* violations) {
-    // keys of all non-NaN floats: [key(-inf), key(+inf)]
-    const uint32_t k0 = float_key(-INFINITY), k1 = float_key(INFINITY);
+// ---------------------------------------------------------------- the reference sigmoids (diagnostics)
+// y[i] = sigmoid_ref(x[i]): lets a test compare the device restatements with torch.sigmoid bit for bit
+__global__ void sigmoid_ref_eval_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned long long n, int sig_ref) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = sigmoid_ref(x[i], sig_ref);
+}
+
+// For fp32 m in (-80, +inf], every 61st float: nothing below sigmoid_window_lo(m) may reach sigmoid_ref(m) -- probed at the 64 floats just below
+// the window and at 64 geometrically spaced points further down (the references are monotone up to a few ulp, so these are
+// where a violation would be).  Counts violations.
+__global__ void sigmoid_window_check_kernel(unsigned long long* violations, int sig_ref) {
+    const uint32_t k0 = float_key(-80.0f), k1 = float_key(INFINITY);
     const uint64_t total = (uint64_t)(k1 - k0);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    unsigned long long bad = 0;
+    unsigned bad = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const float a = key_float(k0 + (uint32_t)i), b = key_float(k0 + (uint32_t)i + 1u);
-        const float fa = sigmoid_fast(a), fb = sigmoid_fast(b);
-        if (!(fb >= fa)) ++bad;
+        // sampled m: all of them would be 2^32 x 128 evaluations; every 61st float still covers every binade densely
+        if (i % 61 != 0) continue;
+        const float m = key_float(k0 + (uint32_t)i);
+        const float fm = sigmoid_ref(m, sig_ref);
+        const float lo = sigmoid_window_lo(m);
+        const uint32_t kl = float_key(lo);
+        for (uint32_t d = 1; d <= 64; ++d) {
+            if (kl < d) break;
+            if (!(sigmoid_ref(key_float(kl - d), sig_ref) < fm)) ++bad;
+        }
+        float w = m - lo;
+        for (int d = 0; d < 64; ++d) {
+            w *= 1.25f;
+            if (!(sigmoid_ref(lo - w, sig_ref) < fm)) ++bad;
+        }
     }
-    bad = __reduce_add_sync(FULL_MASK, (unsigned)bad);
-    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(violations, bad);
+    bad = __reduce_add_sync(FULL_MASK, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(violations, (unsigned long long)bad);
 }
 
 }  // namespace pose

@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
         for (long long t = 0; t < D && t < total; ++t) issue_load(t);
 
     double dpos = 0.0, dneg = 0.0;
-    float apos = 0.0f, aneg = 0.0f, arem = 0.0f, best = -INFINITY;
-    int besti = 0x7fffffff;
+    float apos = 0.0f, aneg = 0.0f, arem = 0.0f;
+    ArgTrack<4> arg;
+    arg.reset();
     Patch pt;
     long long map = warp0;
     int c = 0;                                        // tile index inside the current map
@@ -93,8 +94,7 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
             load_kp(P.kp, P.kp_f64, map, x, y);
             pt = make_patch(x, y, P.H, P.W, P.three_sigma, P.lut_n);
             apos = aneg = arem = 0.0f;
-            best = -INFINITY;
-            besti = 0x7fffffff;
+            arg.reset();
         }
         mbar_wait(smem_u32(bars + b), (uint32_t)((t / kTmaStages) & 1));
         float4* tile = reinterpret_cast<float4*>(tiles + b * kTmaTileBytes);
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
                 const float4 xv4 = tile[li];
                 const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
                 float g[4], unused[4];
-                render_loss_vec<4, GRAD, false, DEC>(xv, g, unused, v0 + li, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg,
-                                                     apos, aneg, arem, best, besti);
+                if (DEC) arg.template push<true>(xv, v0 + li);
+                render_loss_vec<4, GRAD, false>(xv, g, unused, v0 + li, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
                 if (GRAD) tile[li] = make_float4(g[0], g[1], g[2], g[3]);
             }
         }
@@ -128,24 +128,7 @@ __global__ void __launch_bounds__(kTmaThreads) sbp_fused_tma_kernel(SbpFusedPara
             issue_load(t + D);
         }
         if (++c == tiles_per_map) {                   // last tile of the map: per-map results
-            dpos += (double)apos;
-            dneg += (double)aneg - (double)arem;
-            if (DEC) {
-                warp_argmax_first(best, besti);
-                if (lane == 0) {
-                    float jx = -1.0f, jy = -1.0f, jc = -1.0f;
-                    if (best > P.thr) {
-                        const int r = (int)fdiv((uint32_t)besti, P.divW);
-                        jx = (float)(besti - r * P.W);
-                        jy = (float)r;
-                        jc = best;
-                    }
-                    float* jo = P.joints + map * 3;
-                    jo[0] = __fmul_rn(jx, P.scale);
-                    jo[1] = __fmul_rn(jy, P.scale);
-                    jo[2] = jc;
-                }
-            }
+            finish_map<4, DEC>(P, map, lane, apos, aneg, arem, arg, dpos, dneg);
             c = 0;
             map += nwarps;
         }

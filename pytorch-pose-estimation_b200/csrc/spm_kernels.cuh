@@ -783,6 +783,8 @@ struct SpmDecodeParams {
     float* roots; float* kps; int* counts; int* counts_total;
     int N, Pmax, K, R, C;
     float thr; double dist_thr; int apply_act;
+    int sig_ref;                 // apply_act: which torch.sigmoid gives the root confidences (kSigmoidAtenCpu / kSigmoidAtenCuda)
+    float x_lo;                  // apply_act: logits <= x_lo cannot reach sigmoid > thr under either reference (host: logit(thr) minus a margin)
     float zf;                    // fp32(sqrt(2 R^2))
     float input_size;            // DecodeSPM.input_size
     long long s_min;             // smallest integer s with sqrt((double)s) > dist_thr: the radius test on integer offsets
@@ -830,6 +832,25 @@ __global__ void __launch_bounds__(128) spm_gather_kernel(const float* __restrict
     else { o[0] = kx; o[1] = ky; o[2] = c; }
 }
 
+// Tail of SPMmAPCOCO.update_state (utils/spm_utils.py:302-304): x *= img_w / input_size, y *= img_h / input_size -- the ratio is
+// an integer tensor divided by a python int, i.e. one fp32 division, then an in-place fp32 multiply.  Rows >= counts[i] are
+// not touched (they were never written by the decode kernel).
+__global__ void __launch_bounds__(256) spm_rescale_kernel(const float* __restrict__ kps, const int* __restrict__ counts,
+                                                          const long long* __restrict__ image_w, const long long* __restrict__ image_h,
+                                                          float* __restrict__ out, int N, int Pmax, int K, float input_size) {
+    const long long per_img = (long long)Pmax * K;
+    const long long total = (long long)N * per_img;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int img = (int)(t / per_img);
+        const int p = (int)((t - (long long)img * per_img) / K);
+        if (p >= counts[img]) continue;
+        const float rx = __fdiv_rn((float)image_w[img], input_size), ry = __fdiv_rn((float)image_h[img], input_size);
+        out[3 * t] = __fmul_rn(kps[3 * t], rx);
+        out[3 * t + 1] = __fmul_rn(kps[3 * t + 1], ry);
+        out[3 * t + 2] = kps[3 * t + 2];
+    }
+}
+
 // Root NMS + joint gather of one image per CTA (128 threads; ~9 CTAs per SM, so 1024 images are one wave).
 //  1. The root plane is streamed ONCE (128-bit loads, 8 in flight per lane); pixels with conf > thr are appended to a
 //     candidate list in shared memory (packed (y, x), value) with one shared atomic each -- real maps have a few dozen.
@@ -867,6 +888,13 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
     if (threadIdx.x == 0) s_ncand = 0;
     __syncthreads();
 
+    // root confidence = the reference's sigmoid, bit for bit (the greedy order and the threshold test depend on it); it is only
+    // evaluated for logits that can pass the threshold at all (x_lo), i.e. for the few dozen candidates of a real map -- the
+    // stream itself does no SFU work
+    auto conf_of = [&](float v) -> float {
+        if (!P.apply_act) return v;
+        return v > P.x_lo ? sigmoid_ref(v, P.sig_ref) : -INFINITY;
+    };
     auto append = [&](int i, float h) {
         const int pos = atomicAdd(&s_ncand, 1);
         if (pos < kSpmCandCap) {
@@ -893,15 +921,14 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
                 const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float h = P.apply_act ? sigmoid_fast(e[k]) : e[k];
+                    const float h = conf_of(e[k]);
                     if (h > P.thr) append(4 * q + k, h);
                 }
             }
         }
     } else {
         for (int i = threadIdx.x; i < RR; i += blockDim.x) {
-            const float v = ldg_stream(base + i);
-            const float h = P.apply_act ? sigmoid_fast(v) : v;
+            const float h = conf_of(ldg_stream(base + i));
             if (h > P.thr) append(i, h);
         }
     }
@@ -994,8 +1021,7 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
                 bkey = 0xffffffffu;
                 for (int i = threadIdx.x; i < RR; i += blockDim.x) {
                     if ((sup_bits[i >> 5] >> (i & 31)) & 1u) continue;
-                    const float v = __ldg(base + i);
-                    const float h = P.apply_act ? sigmoid_fast(v) : v;
+                    const float h = conf_of(__ldg(base + i));
                     if (h > P.thr && h > best) { best = h; const int y = i / P.R; bkey = ((unsigned)y << 16) | (unsigned)(i - y * P.R); }
                 }
             }

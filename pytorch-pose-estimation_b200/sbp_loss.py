@@ -22,7 +22,7 @@ DEFAULT_TMA = os.environ.get("POSE_B200_TMA", "0") == "1"
 
 def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, decode=False, conf_threshold=0.25,
               coord_scale=1.0, want_target=False, lambda_positive=5.0, lambda_negative=1.0, global_batch=None,
-              bbox=None, input_size=None, out=None, tma=None, exchange=None):
+              bbox=None, input_size=None, out=None, tma=None, exchange=None, sigmoid_ref=None):
     """One pass over the logits: loss (+dlogits) (+rendered target) (+decoded joints).
 
     Returns dict(loss 0-dim fp32, loss_num fp64[2] = un-normalised (S_pos, S_neg), dlogits, target, joints, packed);
@@ -31,7 +31,8 @@ def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, dec
     `input_size` (H_in, W_in) the same call also back-projects the decoded joints into `packed` [B,3K+1]
     (SBPmAPCOCO.update_state arithmetic).  `out` may carry preallocated `dlogits`, `joints`, `packed`, `loss`,
     `loss_num` tensors (e.g. views into a communication buffer).  `exchange` (a `dist.PeerExchange`) makes the
-    epilogue store the rows / loss numerators / ids into every rank's receive buffer over NVLink.
+    epilogue store the rows / loss numerators / ids into every rank's receive buffer over NVLink.  `sigmoid_ref` as in
+    `decode_batch`.
     """
     x = dense(logits, "input")
     assert x.dim() == 4, "input must be [B,K,H,W]"
@@ -64,6 +65,8 @@ def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, dec
         t_out = torch.empty_like(x)
     if decode or bbox is not None:
         flags |= _cabi.F_DECODE
+        if _cabi.sigmoid_ref_code(sigmoid_ref) == _cabi.SIGMOID_ATEN_CUDA:
+            flags |= _cabi.F_SIGMOID_CUDA
         joints = out.get("joints")
         if joints is None:
             joints = torch.empty((b, k, 3), dtype=torch.float32, device=dev)

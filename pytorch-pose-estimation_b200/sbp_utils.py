@@ -118,9 +118,13 @@ def _flip_perm(flip_pairs, k, device):
     return t
 
 
-def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False, refine=False, mode="direct",
+def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False, refine=False, sigmoid_ref=None,
                  flipped=None, flip_pairs=COCO_FLIP_PAIRS):
     """[B,K,H,W] CUDA fp32 -> [B,K,3] (x*scale, y*scale, conf); undetected rows are (-scale,-scale,-1).
+
+    `sigmoid_ref` ("cpu" | "cuda", default `_cabi.DEFAULT_SIGMOID_REF`): with `apply_sigmoid`, argmax indices and confidences
+    are bit-identical to the reference evaluated with torch.sigmoid on CPU / on CUDA tensors (they differ by an ulp, which
+    decides which of two nearly equal logits is "the first maximum").
 
     `flipped` (not in the reference, opt-in): the maps the network produced for the horizontally mirrored images; they
     are mirrored back, left/right joints swapped (`flip_pairs`) and averaged with `heatmaps` inside the kernel."""
@@ -139,10 +143,10 @@ def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False,
                                              int(bool(apply_sigmoid)), float(coord_scale), int(bool(refine)),
                                              stream_ptr(x.device)), "pose_sbp_decode_flip")
         return out
-    m = _cabi.DECODE_INTERVAL if mode == "interval" else _cabi.DECODE_DIRECT
     with torch.cuda.device(x.device):
         check(lib().pose_sbp_decode(ptr(x), ptr(out), b, k, h, w, float(conf_threshold), int(bool(apply_sigmoid)),
-                                    float(coord_scale), int(bool(refine)), m, stream_ptr(x.device)), "pose_sbp_decode")
+                                    float(coord_scale), int(bool(refine)), _cabi.sigmoid_ref_code(sigmoid_ref),
+                                    stream_ptr(x.device)), "pose_sbp_decode")
     return out
 
 
@@ -154,17 +158,17 @@ def nms_sbp(heatmaps, conf_threshold=0.8):
 class DecodeSBP(nn.Module):
     """Drop-in for utils/sbp_utils.py:85-118 (same ctor / forward), plus `decode_batch` for B > 1."""
 
-    def __init__(self, input_size, conf_threshold, pred=True, refine=False, mode="direct", flip_pairs=COCO_FLIP_PAIRS):
+    def __init__(self, input_size, conf_threshold, pred=True, refine=False, sigmoid_ref=None, flip_pairs=COCO_FLIP_PAIRS):
         super().__init__()
         self.input_size = input_size[-1]
         self.conf_threshold = conf_threshold
         self.pred = pred
         self.refine = refine          # quarter-pixel refinement: NOT in the reference, default off
-        self.mode = mode
+        self.sigmoid_ref = sigmoid_ref   # "cpu" | "cuda": which torch.sigmoid ranks near-ties (None: the package default)
         self.flip_pairs = flip_pairs  # used only when the mirrored pass is handed to forward / decode_batch (flip test)
 
     def decode_batch(self, x, x_flipped=None):
-        return decode_batch(x, self.conf_threshold, self.input_size / x.size(-1), self.pred, self.refine, self.mode,
+        return decode_batch(x, self.conf_threshold, self.input_size / x.size(-1), self.pred, self.refine, self.sigmoid_ref,
                             flipped=x_flipped, flip_pairs=self.flip_pairs)
 
     def forward(self, x, x_flipped=None):

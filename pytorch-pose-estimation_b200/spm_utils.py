@@ -155,9 +155,10 @@ class SPMDisplacementGenerator:
         return _render_one(np.ascontiguousarray(masks.centers[:, 0]), j, self.output_res, masks.sigma)[1:].cpu().numpy()
 
 
-def spm_decode_batch(x, input_size, sigma, conf_threshold, pred=True, max_people=64, dist_threshold=None):
+def spm_decode_batch(x, input_size, sigma, conf_threshold, pred=True, max_people=64, dist_threshold=None, sigmoid_ref=None):
     """x [N,1+2K,R,R] CUDA -> (roots [N,Pmax,3], kps [N,Pmax,K,3], counts [N], counts_total [N]) on the device.
-    Only the first counts[i] rows of image i are defined."""
+    Only the first counts[i] rows of image i are defined.  `sigmoid_ref` ("cpu" | "cuda"): with `pred`, the root confidences
+    -- hence the threshold test and the greedy order -- are the reference's torch.sigmoid on CPU / CUDA tensors bit for bit."""
     t = dense(x, "x")
     n, c, r, _ = t.shape
     k = (c - 1) // 2
@@ -170,8 +171,8 @@ def spm_decode_batch(x, input_size, sigma, conf_threshold, pred=True, max_people
     dist = (6 * sigma + 2) / 2 if dist_threshold is None else dist_threshold
     with torch.cuda.device(dev):
         check(lib().pose_spm_decode(ptr(t), ptr(roots), ptr(kps), ptr(counts), ptr(total), n, max_people, k, r,
-                                    float(conf_threshold), float(dist), int(bool(pred)), float(input_size), None, 0,
-                                    stream_ptr(dev)), "pose_spm_decode")
+                                    float(conf_threshold), float(dist), int(bool(pred)), _cabi.sigmoid_ref_code(sigmoid_ref),
+                                    float(input_size), stream_ptr(dev)), "pose_spm_decode")
     return roots, kps, counts, total
 
 
@@ -209,7 +210,7 @@ def get_spm_keypoints(root_joints, displacements, dist_threshold):
 class DecodeSPM(nn.Module):
     """Drop-in for utils/spm_utils.py:203-250; `decode_batch` keeps everything on the device."""
 
-    def __init__(self, input_size, sigma, conf_threshold, pred=True, max_people=64):
+    def __init__(self, input_size, sigma, conf_threshold, pred=True, max_people=64, sigmoid_ref=None):
         super().__init__()
         self.input_size = input_size
         self.sigma = sigma
@@ -217,16 +218,19 @@ class DecodeSPM(nn.Module):
         self.conf_threshold = conf_threshold
         self.pred = pred
         self.max_people = max_people
+        self.sigmoid_ref = sigmoid_ref
 
     def decode_batch(self, x):
-        return spm_decode_batch(x, self.input_size, self.sigma, self.conf_threshold, self.pred, self.max_people)
+        return spm_decode_batch(x, self.input_size, self.sigma, self.conf_threshold, self.pred, self.max_people,
+                                sigmoid_ref=self.sigmoid_ref)
 
     def forward(self, x):
         assert x.size(0) == 1
         roots, kps, counts, total = self.decode_batch(x)
         n, tot = int(counts[0]), int(total[0])
         if tot > self.max_people:        # rare: more roots than the fixed buffer -> redo with the exact size
-            roots, kps, counts, total = spm_decode_batch(x, self.input_size, self.sigma, self.conf_threshold, self.pred, tot)
+            roots, kps, counts, total = spm_decode_batch(x, self.input_size, self.sigma, self.conf_threshold, self.pred, tot,
+                                                         sigmoid_ref=self.sigmoid_ref)
             n = tot
         if n == 0:
             e = torch.zeros((0,), dtype=torch.float32, device=x.device)
@@ -237,14 +241,14 @@ class DecodeSPM(nn.Module):
 def spm_rows_to_results(kps, counts, image_sizes, image_ids, category_ids, input_size):
     """Batched tail of SPMmAPCOCO.update_state (utils/spm_utils.py:302-323): one D2H copy, then python dicts."""
     n, pmax, k, _ = kps.shape
-    w = torch.as_tensor(image_sizes[0]).to(kps.device)
-    h = torch.as_tensor(image_sizes[1]).to(kps.device)
-    # ratio: integer tensor / python int -> fp32 in torch; then an in-place fp32 multiply
-    rx = (w / input_size).to(torch.float32).view(n, 1, 1)
-    ry = (h / input_size).to(torch.float32).view(n, 1, 1)
-    scaled = kps.clone()
-    scaled[..., 0] *= rx
-    scaled[..., 1] *= ry
+    dev = kps.device
+    w = dense(torch.as_tensor(image_sizes[0]).to(dev), "image_w", torch.int64)
+    h = dense(torch.as_tensor(image_sizes[1]).to(dev), "image_h", torch.int64)
+    kd, cd = dense(kps, "kps"), dense(counts, "counts", torch.int32)
+    scaled = torch.empty_like(kd)            # rows >= counts[i] are never written by the kernel nor read below
+    with torch.cuda.device(dev):
+        check(lib().pose_spm_rescale(ptr(kd), ptr(cd), ptr(w), ptr(h), ptr(scaled), n, pmax, k, float(input_size), stream_ptr(dev)),
+              "pose_spm_rescale")
     host = scaled.cpu()
     cnt = counts.cpu().tolist()
     out = []

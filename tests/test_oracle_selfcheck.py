@@ -98,3 +98,24 @@ def test_cpu_pipeline_serial_and_worker_processes_agree():
     assert a == b and a[1] == 6
     want = so.sbp_loss(sample[1], torch.from_numpy(so.sbp_render(sample[0], 64, 48, 2)))
     assert abs(a[0] - float(want)) <= 1e-6 * float(want)
+
+
+def test_c_restatement_of_aten_cpu_sigmoid_matches_torch():
+    """oracle/csrc/aten_sigmoid.c (Sleef expf_u10 + IEEE add / divide) IS torch.sigmoid on contiguous CPU tensors: 2^24 random
+    bit patterns, every float in [-20, 20) at stride 16, and the saturation / underflow edges.  (`python -m
+    oracle.check_aten_sigmoid` repeats it for all 2^32 inputs: 0 mismatches on torch 2.11, AVX2 and AVX512 dispatch.)"""
+    import numpy as np
+    import torch
+    from oracle.build_native import aten_sigmoid
+    rng = np.random.default_rng(0)
+    rnd = rng.integers(0, 2 ** 32, 1 << 24, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    lo, hi = int(np.float32(1e-30).view(np.uint32)), int(np.float32(20).view(np.uint32))
+    pos = np.arange(lo, hi, 16, dtype=np.uint32).view(np.float32)
+    edge = np.array([0.0, -0.0, 16.6, 16.7, 17.0, 88.0, 89.0, 100.0, 104.0, 105.0, -87.0, -88.0, -88.8, -100.0, -104.0, -105.0, np.inf, -np.inf],
+                    dtype=np.float32)
+    x = np.concatenate([rnd, pos, -pos, np.tile(edge, 32)])
+    x = np.ascontiguousarray(x[: x.size // 32 * 32])          # whole vectors only: ATen's scalar tail is glibc expf
+    want = torch.sigmoid(torch.from_numpy(x)).numpy()
+    got = aten_sigmoid(x)
+    both_nan = np.isnan(want) & np.isnan(got)
+    assert np.array_equal(got.view(np.uint32)[~both_nan], want.view(np.uint32)[~both_nan])

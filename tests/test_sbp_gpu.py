@@ -32,23 +32,60 @@ def dev():
     return torch.device("cuda", 0)
 
 
-def test_device_sigmoid_is_monotone(pb, dev):
-    """The INTERVAL decode mode is exact iff the device sigmoid is monotone: check every adjacent fp32 pair."""
+def _sigmoid_ref_eval(pb, x, ref):
+    y = torch.empty_like(x)
+    C = pb._cabi
+    C.check(pb.lib().pose_sigmoid_ref_eval(C.ptr(x), C.ptr(y), x.numel(), C.sigmoid_ref_code(ref), C.stream_ptr(x.device)))
+    return y
+
+
+def _bits(t):
+    return t.view(torch.int32)
+
+
+def test_device_restatements_of_torch_sigmoid_are_bit_exact(pb, dev):
+    """The two functions that rank near-ties ARE torch.sigmoid: the CUDA flavour against torch on this GPU for ALL 2^32
+    inputs, the CPU flavour (Sleef expf_u10 + IEEE add / divide) against torch on the host for 2^27 random bit patterns
+    plus every float in [-20, 20) at stride 64 (the C restatement was compared exhaustively at build time)."""
+    chunk = 1 << 28
+    for start in range(0, 1 << 32, chunk):
+        x = (torch.arange(chunk, device=dev, dtype=torch.int64) + start).to(torch.int32).view(torch.float32)   # wraps to the bit pattern
+        got, want = _sigmoid_ref_eval(pb, x, "cuda"), torch.sigmoid(x)
+        nan = torch.isnan(want) & torch.isnan(got)
+        bad = (_bits(got) != _bits(want)) & ~nan
+        assert int(bad.sum()) == 0, (start, x[bad][:4], got[bad][:4], want[bad][:4])
+        del x, got, want, nan, bad
+    g = torch.Generator().manual_seed(5)
+    rnd = torch.randint(-(1 << 31), (1 << 31) - 1, (1 << 27,), generator=g, dtype=torch.int64).to(torch.int32).view(torch.float32)
+    lo, hi = np.float32(-20).view(np.int32), np.float32(-1e-30).view(np.int32)
+    neg = torch.arange(int(hi), int(lo), 64, dtype=torch.int64).to(torch.int32).view(torch.float32)       # negative floats, descending magnitude
+    xs = torch.cat([rnd, neg, -neg])
+    xs = xs[: xs.numel() // 32 * 32].contiguous()        # whole vectors only: ATen's scalar tail is glibc expf
+    want = torch.sigmoid(xs)
+    got = _sigmoid_ref_eval(pb, xs.to(dev), "cpu").cpu()
+    nan = torch.isnan(want) & torch.isnan(got)
+    bad = (_bits(got) != _bits(want)) & ~nan
+    assert int(bad.sum()) == 0, (xs[bad][:4], got[bad][:4], want[bad][:4])
+
+
+@pytest.mark.parametrize("ref", ["cpu", "cuda"])
+def test_candidate_window_excludes_nothing_that_could_win(pb, dev, ref):
+    """sigmoid_window_lo: no input below the window of m reaches sigmoid_ref(m) (every 61st float m, 128 probes each)."""
     v = torch.ones(1, dtype=torch.int64, device=dev)
-    pb._cabi.check(pb.lib().pose_sigmoid_monotone_check(pb._cabi.ptr(v), pb._cabi.stream_ptr(dev)))
+    C = pb._cabi
+    C.check(pb.lib().pose_sigmoid_window_check(C.ptr(v), C.sigmoid_ref_code(ref), C.stream_ptr(dev)))
     assert int(v.item()) == 0
 
 
-def test_device_sigmoid_accuracy(pb, dev):
-    """conf = sigmoid(logit) within 1e-5 of torch's sigmoid over the useful range; saturates to exactly 1 / 0."""
-    x = torch.linspace(-30, 30, 3072 * 8, device=dev).reshape(1, 8, 64, 48)
-    # one non-minimal element per map so the max is that element: decode returns its sigmoid as conf
+def test_decode_confidence_is_the_reference_sigmoid(pb, dev):
+    """conf = torch.sigmoid(logit) bit for bit (CPU flavour vs the host, CUDA flavour vs this GPU); saturates to exactly 1."""
     probe = torch.tensor([-20.0, -8.0, -2.5, -0.3, 0.0, 0.7, 3.0, 9.0], device=dev)
     maps = torch.full((1, 8, 64, 48), -50.0, device=dev)
     maps[0, torch.arange(8), 5, 7] = probe
-    j = pb.decode_batch(maps, -1.0, 1.0, True, mode="direct")[0, :, 2].cpu()
-    want = torch.sigmoid(probe.cpu())
-    assert torch.all((j - want).abs() <= REL * want)
+    j = pb.decode_batch(maps, -1.0, 1.0, True, sigmoid_ref="cpu")[0, :, 2].cpu()
+    assert torch.equal(j, torch.sigmoid(probe.cpu().repeat(4))[:8])
+    j = pb.decode_batch(maps, -1.0, 1.0, True, sigmoid_ref="cuda")[0, :, 2]
+    assert torch.equal(j, torch.sigmoid(probe))
     sat = torch.tensor([17.0, 30.0, 88.0, 1e4], device=dev).reshape(1, 4, 1, 1).expand(1, 4, 4, 4).contiguous()
     assert torch.all(pb.decode_batch(sat, 0.5, 1.0, True)[0, :, 2] == 1.0)
 
@@ -103,13 +140,15 @@ def test_decode_matches_reference(pb, dev, name):
     kp, logits, bbox, iid, cid, meta = cases.sbp_case(name)
     in_size = meta["input_size"]
     x = logits.to(dev)
-    for mode in ("interval", "direct"):
-        for thr in (0.25, 0.99):
-            dec = pb.DecodeSBP(list(in_size), thr, True, mode=mode)
-            assert_joints(dec.decode_batch(x), g[f"joints_pred_thr{thr}"], REL)
-        dec = pb.DecodeSBP(list(in_size), 0.99, False, mode=mode)
-        got = dec.decode_batch(torch.from_numpy(g["target"]).to(dev)).cpu().numpy()
-        assert np.array_equal(got, g["joints_target_thr0.99"])        # pred=False: no activation -> bit exact
+    for thr in (0.25, 0.99):
+        dec = pb.DecodeSBP(list(in_size), thr, True, sigmoid_ref="cpu")
+        got = dec.decode_batch(x).cpu().numpy()
+        assert np.array_equal(got, g[f"joints_pred_thr{thr}"])        # indices AND confidences bit for bit
+        dec = pb.DecodeSBP(list(in_size), thr, True, sigmoid_ref="cuda")
+        assert torch.equal(dec.decode_batch(x).cpu(), so.sbp_decode(x, in_size[1], thr, True))     # the reference's ops on this GPU
+    dec = pb.DecodeSBP(list(in_size), 0.99, False)
+    got = dec.decode_batch(torch.from_numpy(g["target"]).to(dev)).cpu().numpy()
+    assert np.array_equal(got, g["joints_target_thr0.99"])        # pred=False: no activation -> bit exact
     # reference call shape: batch of one -> [K,3]
     one = pb.DecodeSBP(list(in_size), 0.25, True)(x[2:3])
     assert tuple(one.shape) == (meta["k"], 3)
@@ -125,29 +164,46 @@ def test_decode_matches_reference(pb, dev, name):
 def test_decode_adversarial_ties_plateaus_borders(pb, dev):
     g = load_golden("sbp_adversarial")
     maps = cases.sbp_adversarial_maps().to(dev)
-    for mode in ("interval", "direct"):
-        for thr in (0.25, 0.5):
-            assert_joints(pb.decode_batch(maps, thr, 4.0, True, mode=mode), g[f"joints_pred_thr{thr}"], REL)
-        got = pb.decode_batch(maps, 0.99, 4.0, False, mode=mode).cpu().numpy()
-        assert np.array_equal(got, g["joints_raw_thr0.99"])
+    for thr in (0.25, 0.5):
+        assert np.array_equal(pb.decode_batch(maps, thr, 4.0, True, sigmoid_ref="cpu").cpu().numpy(), g[f"joints_pred_thr{thr}"])
+        assert torch.equal(pb.decode_batch(maps, thr, 4.0, True, sigmoid_ref="cuda").cpu(), so.sbp_decode(maps, 192, thr, True))
+    got = pb.decode_batch(maps, 0.99, 4.0, False).cpu().numpy()
+    assert np.array_equal(got, g["joints_raw_thr0.99"])
 
 
-def test_decode_fp32_threshold_and_modes_agree(pb, dev):
+def test_decode_near_ties_follow_the_reference_sigmoid_to_the_last_bit(pb, dev):
+    """Top logits 1-4 ulp apart at the magnitudes where fp32 sigmoid merges neighbours (0.5 ... 16.5): the reference's pick
+    (golden, CPU tensors) is reproduced bit for bit, and so is the reference's pick on CUDA tensors (its ops run here)."""
+    g = load_golden("sbp_adversarial")
+    near = cases.sbp_neartie_maps()
+    assert cases.digest(near) == str(g["neartie_sha"])
+    x = near.to(dev)
+    got = pb.decode_batch(x, 0.25, 4.0, True, sigmoid_ref="cpu").cpu().numpy()
+    assert np.array_equal(got, g["joints_neartie_thr0.25"])
+    assert torch.equal(pb.decode_batch(x, 0.25, 4.0, True, sigmoid_ref="cuda").cpu(), so.sbp_decode(x, 192, 0.25, True))
+    # the same maps through every fused variant that decodes
+    kp = np.full((near.size(0), near.size(1), 2), 10.0)
+    for grad in (True, False):
+        for ref in ("cpu", "cuda"):
+            r = pb.sbp_fused(x, keypoints=kp, sigma=2, want_grad=grad, decode=True, conf_threshold=0.25, coord_scale=4.0, sigmoid_ref=ref)
+            assert torch.equal(r["joints"], pb.decode_batch(x, 0.25, 4.0, True, sigmoid_ref=ref))
+
+
+def test_decode_fp32_threshold_and_tied_maps(pb, dev):
     x = torch.zeros(1, 2, 8, 8, device=dev)
     x[0, 0, 3, 4] = float(np.float32(0.99))
     x[0, 1, 3, 4] = float(np.nextafter(np.float32(0.99), np.float32(2)))
     j = pb.decode_batch(x, 0.99, 4.0, False).cpu().numpy()
     assert np.array_equal(j[0, 0], np.array([-4, -4, -1], dtype=np.float32))
     assert np.array_equal(j[0, 1, :2], np.array([16, 12], dtype=np.float32))
-    # both decode modes are bit-identical on random and on heavily tied data
+    # random and heavily tied data (7 distinct values per map: every lane holds several candidate vectors -> second look)
     gen = torch.Generator(device=dev).manual_seed(3)
     a = torch.randn(64, 17, 64, 48, device=dev, generator=gen) * 4
     b = torch.randint(-3, 4, (64, 17, 64, 48), device=dev, generator=gen).float() * 6.0
     for t in (a, b):
         for pred in (True, False):
-            d = pb.decode_batch(t, 0.25, 4.0, pred, mode="direct")
-            i = pb.decode_batch(t, 0.25, 4.0, pred, mode="interval")
-            assert torch.equal(d, i)
+            assert torch.equal(pb.decode_batch(t, 0.25, 4.0, pred, sigmoid_ref="cpu").cpu(), so.sbp_decode(t.cpu(), 192, 0.25, pred))
+            assert torch.equal(pb.decode_batch(t, 0.25, 4.0, pred, sigmoid_ref="cuda").cpu(), so.sbp_decode(t, 192, 0.25, pred))
 
 
 @pytest.mark.parametrize("name", ["coco", "hires"])
@@ -165,7 +221,7 @@ def test_fused_render_loss_grad_decode_single_pass(pb, dev, name):
     assert close(r["loss"].item(), float(g["loss"]), REL)
     assert allclose(r["dlogits"], g["dlogits"], REL)
     assert_joints(r["joints"], g["joints_pred_thr0.25"], REL)
-    assert torch.equal(r["joints"], pb.decode_batch(x, 0.25, scale, True, mode="direct"))
+    assert torch.equal(r["joints"], pb.decode_batch(x, 0.25, scale, True))
     # un-normalised numerators reproduce the loss: (5 S_pos + S_neg) / (2 K B)
     num = r["loss_num"].cpu().numpy()
     assert close((5 * num[0] + num[1]) / (2 * meta["k"] * x.size(0)), float(g["loss"]), REL)
@@ -278,8 +334,7 @@ def test_odd_shapes_scalar_path_and_empty_batch(pb, dev):
     loss = pb.SBPLoss(sigma=sigma)(x, torch.from_numpy(kp).to(dev))
     loss.backward()
     assert close(loss.item(), float(wl), REL) and allclose(x.grad, wg, REL)
-    for mode in ("interval", "direct"):
-        assert_joints(pb.decode_batch(logits.to(dev), 0.25, 4.0, True, mode=mode), so.sbp_decode(logits, 4 * w, 0.25, True), REL)
+    assert_joints(pb.decode_batch(logits.to(dev), 0.25, 4.0, True), so.sbp_decode(logits, 4 * w, 0.25, True), REL)
     # a 4-byte-offset view is not 16-byte aligned: dense() keeps it on the device and the kernels still agree
     big = torch.randn(2 * 17 * 64 * 48 + 1, device=dev)
     view = big[1:].view(2, 17, 64, 48)
@@ -316,6 +371,7 @@ def test_cabi_argument_errors(pb, dev):
     assert b"NULL" in L.pose_b200_last_error()
     assert L.pose_sbp_decode(C.ptr(x), C.ptr(j), 1, 0, 8, 8, 0.5, 1, 1.0, 0, 1, C.stream_ptr(dev)) == -1
     assert L.pose_sbp_decode(C.ptr(x), C.ptr(j), 1, 1, 8, 8, 0.5, 1, 1.0, 0, 7, C.stream_ptr(dev)) == -1
+    assert b"sigmoid_ref" in L.pose_b200_last_error()
     loss = torch.zeros((), device=dev)
     ws = torch.zeros(16, dtype=torch.uint8, device=dev)
     rc = L.pose_sbp_fused(C.ptr(x), C.ptr(x), None, 0, 1.0, None, 0, None, None, C.ptr(loss), None, None, 0.0, 1.0,
@@ -347,11 +403,10 @@ def test_full_size_render_decode_roundtrip(pb, dev, big):
     """decode(render(kp), thr .99, pred=False) == (4*int(x), 4*int(y), 1) for visible, (-4,-4,-1) for invisible joints."""
     logits, kp, vis = big
     t = pb.SBPHeatmapGenerator([64, 48], 17, 2).render_batch(kp)
-    for mode in ("interval", "direct"):
-        j = pb.decode_batch(t, 0.99, 4.0, False, mode=mode)
-        want = torch.where(vis[..., None], torch.stack([4 * kp[..., 0].floor(), 4 * kp[..., 1].floor(), torch.ones_like(kp[..., 0])], -1),
-                           torch.tensor([-4.0, -4.0, -1.0], device=dev, dtype=torch.float64)).float()
-        assert torch.equal(j, want)
+    j = pb.decode_batch(t, 0.99, 4.0, False)
+    want = torch.where(vis[..., None], torch.stack([4 * kp[..., 0].floor(), 4 * kp[..., 1].floor(), torch.ones_like(kp[..., 0])], -1),
+                       torch.tensor([-4.0, -4.0, -1.0], device=dev, dtype=torch.float64)).float()
+    assert torch.equal(j, want)
     # linearity-style checksum: every visible interior joint contributes the same template mass
     interior = vis & (kp[..., 0] >= 8) & (kp[..., 0] < 40) & (kp[..., 1] >= 8) & (kp[..., 1] < 56)
     mass = t.double().sum(dim=(2, 3))
@@ -367,8 +422,7 @@ def test_full_size_fused_equals_staged_and_oracle_subset(pb, dev, big):
     dense_ = pb.sbp_fused(logits, target=t, want_grad=True)
     assert close(fused["loss"].item(), dense_["loss"].item(), 1e-6)
     assert allclose(fused["dlogits"][:64], dense_["dlogits"][:64], 1e-6)
-    assert torch.equal(fused["joints"], pb.decode_batch(logits, 0.25, 4.0, True, mode="interval"))
-    assert torch.equal(fused["joints"], pb.decode_batch(logits, 0.25, 4.0, True, mode="direct"))
+    assert torch.equal(fused["joints"], pb.decode_batch(logits, 0.25, 4.0, True))
     # oracle on a 128-sample subset: loss numerators are additive over samples
     sub = slice(1000, 1128)
     ls, gs = so.sbp_loss_closed_form_f64(logits[sub].cpu(), torch.from_numpy(so.sbp_render(kp[sub].cpu().numpy(), 64, 48, 2)))
@@ -388,6 +442,71 @@ def test_full_size_fused_equals_staged_and_oracle_subset(pb, dev, big):
     assert allclose(tma["loss_num"], fused["loss_num"], 1e-12)
     other = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=False)["loss_num"]      # another variant: fp32 rounding differs
     assert allclose(other, fused["loss_num"], 1e-7)
+
+
+def _mismatch_count(pb, x, ref, thr=0.25, chunk=1024):
+    """Maps whose decoded row (x, y, conf -- all three bit for bit) differs from the reference's ops on the same logits:
+    ref "cpu" = torch.sigmoid on the host, one [1,K,H,W] call per sample as DecodeSBP.forward makes them; "cuda" = on this GPU."""
+    got = pb.decode_batch(x, thr, 4.0, True, sigmoid_ref=ref).cpu()
+    bad = 0
+    for i in range(0, x.size(0), chunk):
+        src = x[i:i + chunk].cpu() if ref == "cpu" else x[i:i + chunk]
+        want = so.sbp_decode(src, 4 * x.size(-1), thr, True)
+        bad += int((_bits(got[i:i + chunk]) != _bits(want)).any(-1).sum())
+    return bad
+
+
+def _record(name, value):
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        path = os.path.join(d, "argmax_mismatch.json")
+        rec = json.load(open(path)) if os.path.exists(path) else {}
+        rec[name] = value
+        json.dump(rec, open(path, "w"), indent=1)
+
+
+def _big_neartie(dev, b=4096, k=17, h=64, w=48, seed=17):
+    """On-device version of cases.sbp_neartie_maps for a full batch: every map has two contenders d = 1..4 ulp apart at a
+    magnitude from NEARTIE_MAGNITUDES, the earlier pixel holding the smaller value on even maps."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randn(b * k, h * w, device=dev, generator=gen) * 0.5 - 6.0
+    t = torch.arange(b * k, device=dev)
+    mags = torch.tensor(cases.NEARTIE_MAGNITUDES, device=dev)[t % len(cases.NEARTIE_MAGNITUDES)]
+    lo = mags.clone()
+    for d in range(1, 5):
+        lo = torch.where((t % 4) + 1 >= d, torch.nextafter(lo, torch.full_like(lo, -1e30)), lo)
+    p = torch.rand(b * k, 2, device=dev, generator=gen)
+    p1 = (p[:, 0] * (h * w - 2)).long()
+    p2 = p1 + 1 + (p[:, 1] * (h * w - 1 - p1).float()).long().clamp(max=h * w - 2)
+    p2 = p2.clamp(max=h * w - 1)
+    even = (t % 2 == 0)
+    x[t, p1] = torch.where(even, lo, mags)
+    x[t, p2] = torch.where(even, mags, lo)
+    return x.view(b, k, h, w)
+
+
+@pytest.mark.parametrize("kind", ["randn3", "realistic", "neartie"])
+def test_full_config_argmax_mismatches_are_zero(pb, dev, big, kind):
+    """BASELINE.json configs[1], all 69 632 maps: the decoded rows equal the reference's (torch.sigmoid -> first row-major
+    maximum) bit for bit -- against the host (ATen CPU sigmoid) and against the same ops on this GPU (ATen CUDA sigmoid)."""
+    logits, kp, vis = big
+    if kind == "randn3":
+        x = logits
+    elif kind == "realistic":
+        t = pb.SBPHeatmapGenerator([64, 48], 17, 2).render_batch(kp)
+        g = torch.Generator(device=dev).manual_seed(2)
+        x = torch.logit((t + 0.05 * torch.rand(t.shape, device=dev, generator=g)).clamp(1e-4, 1 - 1e-4))
+    else:
+        x = _big_neartie(dev)
+    for ref in ("cuda", "cpu"):
+        bad = _mismatch_count(pb, x, ref)
+        _record(f"B4096_{kind}_{ref}", {"maps": x.size(0) * x.size(1), "mismatches": bad})
+        assert bad == 0, (kind, ref, bad)
+    # the fused kernel's decode is the same code: identical rows
+    f = pb.sbp_fused(x, keypoints=kp, sigma=2, want_grad=False, decode=True, conf_threshold=0.25, coord_scale=4.0)
+    assert torch.equal(f["joints"], pb.decode_batch(x, 0.25, 4.0, True))
 
 
 def test_config3_shard_size_properties(pb, dev):
@@ -412,6 +531,10 @@ def test_config3_shard_size_properties(pb, dev):
     del t, j, want
     fused = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0)
     assert torch.equal(fused["joints"], pb.decode_batch(logits, 0.25, 4.0, True))
+    for ref in ("cuda", "cpu"):          # all 278 528 maps against the reference's ops
+        bad = _mismatch_count(pb, logits, ref)
+        _record(f"B16384_randn3_{ref}", {"maps": b * k, "mismatches": bad})
+        assert bad == 0, (ref, bad)
     parts = [pb.sbp_fused(logits[i:i + 4096], keypoints=kp[i:i + 4096], sigma=2, want_grad=True, decode=True, conf_threshold=0.25,
                           coord_scale=4.0, global_batch=b) for i in range(0, b, 4096)]
     assert allclose(torch.stack([p["loss_num"] for p in parts]).sum(0), fused["loss_num"], 1e-12)

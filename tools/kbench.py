@@ -122,12 +122,12 @@ def main():
     run("dense_loss_grad", lambda: pb.sbp_fused(logits, target=target), 3 * map_bytes)
     run("dense_loss_only(no grad)", lambda: pb.sbp_fused(logits, target=target, want_grad=False), 2 * map_bytes)
     for pred in (True, False):
-        for mode in ("interval", "direct"):
-            for src, tag in ((logits, "randn"), (realistic, "realistic")):
-                run(f"decode_{mode}_pred{int(pred)}_{tag}", lambda: pb.decode_batch(src, 0.25, 4.0, pred, mode=mode), map_bytes + 12)
+        for src, tag in ((logits, "randn"), (realistic, "realistic")):
+            run(f"decode_pred{int(pred)}_{tag}", lambda: pb.decode_batch(src, 0.25, 4.0, pred), map_bytes + 12)
+    run("decode_pred1_randn_sigmoid_cuda", lambda: pb.decode_batch(logits, 0.25, 4.0, True, sigmoid_ref="cuda"), map_bytes + 12)
     xf = realistic.flip(-1).contiguous()
     run("decode_flip_test_pred1_realistic", lambda: pb.decode_batch(realistic, 0.25, 4.0, True, flipped=xf), 2 * map_bytes + 12)
-    run("decode_interval_pred0_target_thr.99", lambda: pb.decode_batch(target, 0.99, 4.0, False), map_bytes + 12)
+    run("decode_pred0_target_thr.99", lambda: pb.decode_batch(target, 0.99, 4.0, False), map_bytes + 12)
     run("backproject_rows", lambda: pb.backproject_rows(joints, bbox, (256, 192)), 24)
 
     if (not args.only or "spm" in args.only) and not args.no_spm:
