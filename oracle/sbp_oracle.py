@@ -175,6 +175,28 @@ def sbp_decode_loop(x, input_w, conf_threshold, pred=True):
     return joints
 
 
+def sbp_decode_loop_torch(x, input_w, conf_threshold, pred=True):
+    """The reference's decode as the ATen OP CHAIN it is (utils/sbp_utils.py:56-82, :103-118), device-agnostic: per joint a
+    comparison, torch.where (-> nonzero, host sync), an advanced-index gather, torch.argmax, three element reads (host syncs)
+    and a torch.tensor() H2D write.  bench.py times it on CUDA tensors as the `aten_baseline` of decode."""
+    assert x.size(0) == 1
+    w_out = x.size(-1)
+    heatmaps = torch.sigmoid(x) if pred else x
+    hm = heatmaps[0]
+    k = hm.size(0)
+    joints = torch.zeros((k, 3), device=hm.device) - 1
+    for idx in torch.arange(k):
+        heatmap = hm[idx]
+        yy, xx = torch.where(heatmap > conf_threshold)
+        if yy.size(0) == 0:
+            continue
+        conf = heatmap[yy, xx]
+        a = torch.argmax(conf)
+        joints[idx] = torch.tensor([xx[a], yy[a], conf[a]])
+    joints[..., :2] *= (input_w / w_out)
+    return joints
+
+
 def reference_sigmoid(x):
     """torch.sigmoid applied the way DecodeSBP.forward does (utils/sbp_utils.py:104-109): one [1,K,H,W] sample per call.
     Which elements go through ATen's vectorised body (Sleef expf) and which through its scalar tail (glibc expf) depends on
@@ -182,6 +204,21 @@ def reference_sigmoid(x):
     if x.device.type != "cpu" or x.size(0) <= 1:
         return torch.sigmoid(x)
     return torch.cat([torch.sigmoid(x[b:b + 1]) for b in range(x.size(0))])
+
+
+def torch_sigmoid_vector_body(x):
+    """torch.sigmoid of a flat fp32 CPU tensor with EVERY element going through ATen's vectorised body (Sleef expf): one
+    thread (no chunk boundaries) and a length padded to whole vector pairs.  For pinning the restatements of that body."""
+    n = x.numel()
+    pad = (-n) % 64
+    xp = torch.cat([x.reshape(-1), x.new_zeros(pad)]) if pad else x.reshape(-1)
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        y = torch.sigmoid(xp)
+    finally:
+        torch.set_num_threads(threads)
+    return y[:n].reshape(x.shape)
 
 
 def sbp_decode(x, input_w, conf_threshold, pred=True):

@@ -42,6 +42,26 @@ __device__ __forceinline__ void store_all(const ExchangeDev& X, unsigned long lo
     }
 }
 
+// Threads [0, world) of the calling CTA wait (acquire, system scope) until every rank's flag is >= need; all threads of the
+// CTA must call it.  A peer that never signals must not hang this GPU for good: after `timeout_cycles` the wait gives up,
+// records 1 + the rank it waited for in ctrl->error (sticky; PeerExchange.flush() / gathered_*() raise on it) and returns
+// false -- the caller then poisons the loss of that step with NaN instead of handing out a number computed from stale rows.
+__device__ __forceinline__ bool wait_for_peers(const ExchangeDev& X, ExchangeCtrl* ctrl, unsigned long long need, long long timeout_cycles) {
+    __shared__ int s_timed_out;
+    if (threadIdx.x == 0) s_timed_out = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < X.world) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.off_flags) + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) < need) {
+            if (clock64() - t0 > timeout_cycles) { atomicExch(&ctrl->error, 1u + threadIdx.x); s_timed_out = 1; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    return s_timed_out == 0;
+}
+
 __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams P, ExchangeDev X) {
     pdl_wait();
     ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(X.peer[X.rank] + X.off_ctrl);
@@ -67,17 +87,11 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
             // in-band completion of the PREVIOUS step: every rank published flag step-1 when its fused kernel of this
             // step started (~one kernel duration ago), so this wait normally falls straight through
             const unsigned long long need = step - 1;
-            if ((int)threadIdx.x < X.world) {
-                const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.off_flags) + threadIdx.x;
-                const long long t0 = clock64();
-                while (ld_acquire_sys(flag) < need) {
-                    if (clock64() - t0 > X.timeout_cycles) { atomicExch(&ctrl->error, 1u + threadIdx.x); break; }
-                    __nanosleep(64);
-                }
-            }
-            __syncthreads();
+            const bool ok = wait_for_peers(X, ctrl, need, X.timeout_cycles);
             const double* prev = reinterpret_cast<const double*>(X.peer[X.rank] + X.off_nums[need % kExchangeSlots]);
             reduce_pairs_cta(prev, X.world, 2, X.w0, X.w1, X.inv_norm_global, X.loss_prev, nullptr);
+            __syncthreads();
+            if (!ok && threadIdx.x == 0 && X.loss_prev) *X.loss_prev = __int_as_float(0x7fc00000);   // a timed-out step has no loss
         }
     } else {
         // One warp per sample.  The sample's row (K x (x_img, y_img, flag) + score, zero-padded to a 16-byte multiple) is
@@ -149,19 +163,12 @@ __global__ void __launch_bounds__(256) exchange_wait_reduce_kernel(ExchangeDev X
     const unsigned long long need = step;
     if ((int)threadIdx.x < X.world && (mode == 0 || ctrl->step < step))
         st_release_sys(reinterpret_cast<unsigned long long*>(X.peer[threadIdx.x] + X.off_flags) + X.rank, step);
-    if (need > 0 && (int)threadIdx.x < X.world) {
-        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.off_flags) + threadIdx.x;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(flag) < need) {
-            if (clock64() - t0 > timeout_cycles) { atomicExch(&ctrl->error, 1u + threadIdx.x); break; }   // never hang the GPU
-            __nanosleep(64);
-        }
-    }
-    __syncthreads();
     if (need > 0) {
+        const bool ok = wait_for_peers(X, ctrl, need, timeout_cycles);
         const double* nums = reinterpret_cast<const double*>(X.peer[X.rank] + X.off_nums[need % kExchangeSlots]);
         reduce_pairs_cta(nums, X.world, 2, w0, w1, inv_norm, loss_out, nullptr);
         __syncthreads();
+        if (!ok && threadIdx.x == 0 && loss_out) *loss_out = __int_as_float(0x7fc00000);
     }
     if (threadIdx.x == 0) ctrl->step = step;
 }

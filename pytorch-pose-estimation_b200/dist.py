@@ -4,8 +4,10 @@ The hot path shards by image with no exchange inside render / loss / decode.  Tw
 (SURVEY.md 8 e), both latency-bound and both enqueued stream-ordered with no host synchronisation:
 
 * loss: all-reduce(SUM) of the two fp64 un-normalised numerators each rank's fused kernel produced;
-  every rank then holds the global-batch loss.  dlogits need no exchange -- each rank's kernel already
-  scales them by 1/(2*K*B_global).
+  every rank then holds the global-batch loss.  dlogits are never exchanged.  Their normalisation is the caller's
+  choice and must match how PARAMETER gradients are combined: under DDP (mean over ranks) keep the local batch
+  (`global_batch=None`, what the reference does -- mean of local-batch gradients == global-batch gradient); pass
+  `global_batch=B*world` only where the ranks' gradients are summed (or not exchanged at all).
 * predictions: all-gather of the fixed-size [B_local, K, 3] rows (+ scores, image ids) so that OKS/AP is
   evaluated over the whole validation set on every rank.  The reference never gathers (each rank writes
   its own results.json, utils/sbp_utils.py:167-169); this fixes that race.
@@ -131,9 +133,8 @@ class PeerExchange:
     of step s-1 (written by that epilogue), ranks may drift up to two steps apart, and `flush()` completes the last step.
     """
 
-    def __init__(self, batch_local, num_keypoints, device, image_ids, category_ids, group=None, multicast=None, defer=0):
+    def __init__(self, batch_local, num_keypoints, device, image_ids, category_ids, group=None, multicast=None, defer=0, _connect=True):
         import ctypes
-        import os
 
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -142,6 +143,7 @@ class PeerExchange:
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.b, self.k, self.device = batch_local, num_keypoints, device
+        # ---- local phase: nothing here talks to another rank
         d = ExchangeDesc()
         d.world, d.rank, d.batch_local, d.num_keypoints = self.world, self.rank, batch_local, num_keypoints
         d.defer = self.defer = int(defer)
@@ -149,24 +151,37 @@ class PeerExchange:
         if nbytes == 0:
             raise ValueError("bad exchange shape")
         self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
-        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.ids = torch.stack([image_ids.to(device, torch.int64), category_ids.to(device, torch.int64)], dim=1).contiguous()
+        d.ids_local = self.ids.data_ptr()
+        self.steps = 0
+        self.loss = torch.zeros((), dtype=torch.float32, device=device)
+        d.loss_prev = self.loss.data_ptr()
+        self.desc = d
+        self._multicast_wanted = multicast
+        self.multicast = False
+        self.handle = None
+        if _connect:
+            self._connect()
+
+    def _connect(self):
+        """Collective phase (every rank of the group must call it): map the peers' buffers, zero, barrier."""
+        import os
+
+        import torch.distributed._symmetric_memory as symm_mem
+        d = self.desc
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
         self.buf.zero_()
         for r, p in enumerate(self.handle.buffer_ptrs):
             d.peer_base[r] = int(p)
-        self.ids = torch.stack([image_ids.to(device, torch.int64), category_ids.to(device, torch.int64)], dim=1).contiguous()
-        d.ids_local = self.ids.data_ptr()
         # NVLS: one multimem.st reaches every rank's copy through the switch (egress independent of the world size)
+        multicast = self._multicast_wanted
         if multicast is None:
             multicast = os.environ.get("POSE_B200_MULTICAST", "1") == "1"
         mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
         self.multicast = bool(multicast and mc)
         d.multicast_base = mc if self.multicast else None
-        self.steps = 0
-        self.loss = torch.zeros((), dtype=torch.float32, device=device)
-        d.loss_prev = self.loss.data_ptr()
-        self.desc = d
-        torch.cuda.synchronize(device)
-        dist.barrier(group)            # every rank's buffer is zeroed before anyone's first peer store
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)            # every rank's buffer is zeroed before anyone's first peer store
 
     def _view(self, off, dtype, shape):
         n = 1
@@ -190,12 +205,16 @@ class PeerExchange:
         self.steps += 1
         return loss
 
-    def flush(self, global_batch, lambda_pos=5.0, lambda_neg=1.0):
-        """defer=1 only: complete the last published step (its rows / loss are what gathered_*() / the result refer to)."""
+    def flush(self, global_batch, lambda_pos=5.0, lambda_neg=1.0, check=False):
+        """defer=1 only: complete the last published step (its rows / loss are what gathered_*() / the result refer to).
+        `check=True` also synchronises and raises if any wait of this exchange has timed out (end of an epoch)."""
         if self.defer == 0:
-            return self.loss
-        loss = self._wait("pose_exchange_flush", global_batch, lambda_pos, lambda_neg)
-        self._flushed = self.steps
+            loss = self.loss
+        else:
+            loss = self._wait("pose_exchange_flush", global_batch, lambda_pos, lambda_neg)
+            self._flushed = self.steps
+        if check:
+            self.raise_on_error()
         return loss
 
     def _completed(self):
@@ -208,15 +227,29 @@ class PeerExchange:
         """Tell the host mirror that a captured step was replayed n more times."""
         self.steps += n
 
-    def gathered_padded(self):
-        """[world*B, row_stride] fp32: the receive region of the last finished step as it lies in memory (contiguous)."""
+    def raise_on_error(self):
+        """Host check of the sticky device error flag (one small D2H copy + sync).  A wait that timed out (a peer never
+        published its step) poisoned that step's loss with NaN; the rows of that step are stale.  Raises PoseB200Error."""
+        e = self.error()
+        if e:
+            from ._cabi import PoseB200Error
+            raise PoseB200Error(f"PeerExchange: rank {self.rank} gave up waiting for rank {e - 1} (exchange time-out): the gathered rows / "
+                                "losses since then are not valid")
+
+    def gathered_padded(self, check=False):
+        """[world*B, row_stride] fp32: the receive region of the last finished step as it lies in memory (contiguous).
+        `check=True`: synchronise and raise if a wait timed out (use where the rows are consumed, e.g. once per validation)."""
+        if check:
+            self.raise_on_error()
         return self._view(int(self.desc.off_rows[self._completed() % 4]), torch.float32, (self.world * self.b, int(self.desc.row_stride)))
 
-    def gathered_packed(self):
+    def gathered_packed(self, check=False):
         """[world*B, 3K+1] fp32 rows of the last finished step, image order (a strided view: rows are 16-byte padded)."""
-        return self.gathered_padded()[:, :3 * self.k + 1]
+        return self.gathered_padded(check)[:, :3 * self.k + 1]
 
-    def gathered_ids(self):
+    def gathered_ids(self, check=False):
+        if check:
+            self.raise_on_error()
         return self._view(int(self.desc.off_ids[self._completed() % 4]), torch.int64, (self.world * self.b, 2))
 
     def error(self):
@@ -225,23 +258,37 @@ class PeerExchange:
 
 
 def make_exchange(batch_local, num_keypoints, device, image_ids, category_ids, group=None, prefer_p2p=True, defer=0):
-    """PeerExchange when symmetric memory can be set up across the group, else the NCCL ShardExchange.  Returns (exchange, kind)."""
+    """PeerExchange when symmetric memory can be set up across the group, else the NCCL ShardExchange.  Returns (exchange, kind).
+
+    Failure-symmetric: the constructor's local phase (allocation, layout) runs under try on every rank, then ONE
+    all_reduce(MIN) agrees on whether everybody got that far, and only then do the ranks enter the collective phase
+    (rendezvous, barrier) together -- a rank that fails early can no longer leave the others inside a barrier."""
     if not _active(group):
         ex = ShardExchange(batch_local, num_keypoints, device, group)
         ex.ids.copy_(torch.stack([image_ids.to(device, torch.int64), category_ids.to(device, torch.int64)], dim=1))
         return ex, "single"
-    ok = torch.zeros(1, device=device)
     ex = None
     if prefer_p2p:
+        ok = torch.zeros(1, device=device)
         try:
-            ex = PeerExchange(batch_local, num_keypoints, device, image_ids, category_ids, group, defer=defer)
+            ex = PeerExchange(batch_local, num_keypoints, device, image_ids, category_ids, group, defer=defer, _connect=False)
             ok.fill_(1)
-        except Exception as e:          # noqa: BLE001 -- any set-up failure (no P2P, no VMM, old driver) means: use NCCL
+        except Exception as e:          # noqa: BLE001 -- any local set-up failure (no VMM, old driver) means: use NCCL
             import sys
             print(f"[pose_b200] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-    if ex is not None and float(ok.item()) == 1.0:
-        return ex, "p2p"
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if float(ok.item()) == 1.0:
+            # collective phase: every rank is here.  A failure inside it is a failure on all ranks (rendezvous is collective).
+            try:
+                ex._connect()
+                ok.fill_(1)
+            except Exception as e:      # noqa: BLE001
+                import sys
+                print(f"[pose_b200] symmetric-memory rendezvous failed ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+                ok.fill_(0)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if float(ok.item()) == 1.0:
+                return ex, "p2p"
     ex = ShardExchange(batch_local, num_keypoints, device, group)
     ex.ids.copy_(torch.stack([image_ids.to(device, torch.int64), category_ids.to(device, torch.int64)], dim=1))
     return ex, "nccl"
@@ -283,7 +330,8 @@ def gather_spm_people(kps, counts, image_ids, category_ids, image_w, image_h, gr
     [B_local] i32 + per-image ids / sizes [B_local] -> the same tensors with leading dimension B_global, in image order.
 
     The number of persons per image is data dependent, so the fixed-size decode buffers are what travels (SURVEY.md 8 e):
-    ONE all-gather of [kps | counts, ids, sizes] per rank; every rank must use the same Pmax.  Shards may differ in size
+    three collectives -- an all-gather of the shard sizes (one int64 per rank), one of the [Pmax*K*3] fp32 rows and one of
+    the [counts, ids, sizes] int64 records; every rank must use the same Pmax.  Shards may differ in size
     by at most one image (shard_bounds): they are padded to the longest shard with count 0 and the padding is stripped.
     """
     if not _active(group):

@@ -203,3 +203,70 @@ def test_two_gpu_metric_gather_matches_single_gpu():
     for rank, sbp_rows, spm_rows in got:
         assert sbp_rows == m.result_list
         assert spm_rows == s.result_list
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import pose_b200 as pb
+        from pose_b200 import dist as pd
+        feat, kp, head = _ddp_inputs(dev)
+        b = feat.size(0)
+        lo, hi = pd.shard_bounds(b, world, rank)
+        out = {}
+        for tag, gb in (("local", None), ("global", b)):
+            model = torch.nn.parallel.DistributedDataParallel(_make_head(head, dev), device_ids=[rank])
+            loss = pb.SBPLoss(sigma=2, global_batch=gb)(model(feat[lo:hi]), kp[lo:hi])
+            loss.backward()                                      # DDP averages the parameter gradients over the ranks
+            torch.cuda.synchronize()
+            out[tag] = [p.grad.detach().cpu() for p in model.module.parameters()]
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def _ddp_inputs(dev, b=16):
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    feat = torch.randn(b, 8, 64, 48, generator=gen).to(dev)
+    kp = torch.stack([torch.rand(b, 17, generator=gen, dtype=torch.float64) * 48, torch.rand(b, 17, generator=gen, dtype=torch.float64) * 64], -1).to(dev)
+    head = (torch.randn(17, 8, 1, 1, generator=gen) * 0.5, torch.randn(17, generator=gen) * 0.1)
+    return feat, kp, head
+
+
+def _make_head(head, dev):
+    m = torch.nn.Conv2d(8, 17, 1).to(dev)
+    with torch.no_grad():
+        m.weight.copy_(head[0].to(dev))
+        m.bias.copy_(head[1].to(dev))
+    return m
+
+
+def test_ddp_gradients_need_local_batch_normalisation():
+    """Under DDP (mean over ranks) the reference's local-batch normalisation (global_batch=None) gives exactly the parameter
+    gradients of the single-process global batch; global_batch=B*world there would make them `world` times too small."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import pose_b200 as pb
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    dev = torch.device("cuda", 0)
+    feat, kp, head = _ddp_inputs(dev)
+    model = _make_head(head, dev)
+    pb.SBPLoss(sigma=2)(model(feat), kp).backward()
+    want = [p.grad.detach().cpu() for p in model.parameters()]
+    for rank, out in got:
+        for g, w in zip(out["local"], want):
+            assert torch.allclose(g, w, rtol=1e-5, atol=1e-6 * float(w.abs().max())), float((g - w).abs().max())
+        for g, w in zip(out["global"], want):
+            assert torch.allclose(2.0 * g, w, rtol=1e-5, atol=1e-6 * float(w.abs().max()))

@@ -1,0 +1,159 @@
+"""The other BASELINE.json configurations as bench lines (bench.py appends them as `extra_workloads`, timed OUTSIDE the headline
+region): config 4 (SPM: fused render+loss+grad, render, root-peak + displacement decode on multi-person maps), config 5 (decode-
+only sweep: 96x72 maps, the 11-joint sbp_pis shape, B in {256, 16384}) and config 3 as written (global batch 32 768 split over
+the ranks).  Every entry: device time per call (CUDA-graph replay, CUDA events), the algorithmic bytes of SURVEY.md 8(d) and the
+fraction of the measured HBM peak.  Inputs are resident and (except B=256, marked) larger than L2.
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def graph_time(fn, reps=20, warm=3, rounds=3):
+    """ms per call: the call is captured once and replayed `reps` times between one event pair; median of `rounds`."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(rounds):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / reps)
+    return sorted(ts)[len(ts) // 2]
+
+
+def _entry(name, ms, units, unit_name, bytes_per_unit, peak, note=None):
+    gbs = bytes_per_unit * units / (ms * 1e-3) / 1e9
+    e = {"workload": name, "ms": ms, unit_name + "_per_s": units / (ms * 1e-3), "algorithmic_bytes": bytes_per_unit * units,
+         "achieved_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak}
+    if note:
+        e["note"] = note
+    return e
+
+
+def spm_config4(pb, dev, peak, n=1024, reps=10):
+    from _inputs import spm_inputs
+    c, j, cnt, target, x = spm_inputs(n, dev)
+    img = 35 * 128 * 128 * 4
+    out = []
+    out.append(_entry(f"config4 SPM fused render+loss+grad, N={n} x 35 x 128x128 (persons in, target never in HBM)",
+                      graph_time(lambda: pb.spm_fused(x, c, j, cnt, 1), reps), n, "images", 2 * img, peak))
+    out.append(_entry(f"config4 SPM fused render+loss (no grad), N={n}",
+                      graph_time(lambda: pb.spm_fused(x, c, j, cnt, 1, want_grad=False), reps), n, "images", img, peak))
+    out.append(_entry(f"config4 SPM target render, N={n}", graph_time(lambda: pb.spm_render_batch(c, j, cnt, 128, 1), reps), n, "images", img, peak))
+    out.append(_entry(f"config4 SPM dense-target loss+grad (reference signature), N={n}",
+                      graph_time(lambda: pb.spm_loss_fused(x, target), reps), n, "images", 3 * img, peak))
+    ms = graph_time(lambda: pb.spm_decode_batch(x, 512, 1, 0.5, True, 32), reps)
+    _, _, counts, _ = pb.spm_decode_batch(x, 512, 1, 0.5, True, 32)
+    roots = int(counts.sum().item())
+    per_img = 128 * 128 * 4 + (roots / n) * 34 * 32        # root plane + one 32-byte sector per gathered displacement
+    out.append(_entry(f"config4 SPM decode (root NMS + displacement gather), N={n}, thr 0.5, {roots / n:.1f} roots/image",
+                      ms, n, "images", per_img, peak, note="one wave of per-image CTAs: latency-bound tail (greedy NMS + scattered gathers)"))
+    return out
+
+
+def decode_config5(pb, dev, peak, reps=20):
+    out = []
+    gen = torch.Generator(device=dev).manual_seed(0)
+    for (h, w, k, b, in_w) in ((96, 72, 17, 4096, 288), (64, 48, 11, 4096, 192), (64, 48, 17, 16384, 192), (64, 48, 17, 256, 192)):
+        x = torch.randn(b, k, h, w, device=dev, generator=gen) * 3.0
+        maps = b * k
+        per = h * w * 4 + 12
+        note = "3.3 MB: L2-resident and launch-latency bound, not an HBM number" if b == 256 else None
+        for pred, thr in ((True, 0.25), (False, 0.99)):
+            src = x if pred else torch.sigmoid(x)
+            ms = graph_time(lambda: pb.decode_batch(src, thr, in_w / w, pred), reps)
+            out.append(_entry(f"config5 decode {h}x{w} K={k} B={b} pred={pred} thr={thr}", ms, maps, "heatmaps", per, peak, note))
+        del x
+    return out
+
+
+def config3_as_written(pb, pd, dev, peak, world, rank, global_batch=32768, reps=10):
+    """BASELINE.json configs[2]: global batch 32 768 split over the ranks (N=2: 16 384 images per GPU), fused step with the
+    exchange, graph replay, max over ranks."""
+    import torch.distributed as dist
+    K, H, W = 17, 64, 48
+    b = global_batch // world
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    logits = torch.randn(b, K, H, W, device=dev, generator=gen) * 3.0
+    kp = torch.stack([torch.rand(b, K, device=dev, generator=gen, dtype=torch.float64) * W,
+                      torch.rand(b, K, device=dev, generator=gen, dtype=torch.float64) * H], dim=-1)
+    kp[torch.rand(b, K, device=dev, generator=gen) >= 0.85] = -1.0
+    bbox = torch.rand(b, 4, device=dev, generator=gen, dtype=torch.float64) * 300 + 40
+    iid = torch.arange(b, device=dev, dtype=torch.int64) + rank * b
+    ex, kind = pd.make_exchange(b, K, dev, iid, torch.ones(b, device=dev, dtype=torch.int64), defer=1)
+    outs = dict(dlogits=torch.empty_like(logits), joints=torch.empty((b, K, 3), dtype=torch.float32, device=dev),
+                loss=torch.empty((), dtype=torch.float32, device=dev))
+    if kind != "p2p":
+        outs.update(ex.out_views())
+
+    def step():
+        if kind == "p2p":
+            pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0,
+                         global_batch=global_batch, bbox=bbox, input_size=(256, 192), out=outs, exchange=ex)
+            return ex.finish(global_batch)
+        r = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0,
+                         global_batch=global_batch, bbox=bbox, input_size=(256, 192), out=outs)
+        ex.exchange()
+        return ex.global_loss(global_batch, local_loss=r["loss"])
+
+    for _ in range(4):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(4):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    host_steps = getattr(ex, "steps", 0)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(4):                      # a whole turn of the exchange ring per replay
+            step()
+    if kind == "p2p":
+        ex.steps = host_steps
+    g.replay()
+    if kind == "p2p":
+        ex.advance(4)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    if kind == "p2p":
+        ex.advance(4 * reps)
+        ex.flush(global_batch)
+    e.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(e) / (4 * reps)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ent = _entry(f"config3 as written: global batch {global_batch} over {world} GPU(s) = {b} images per GPU, fused render+loss+grad+decode + "
+                 f"back-projection + exchange ({kind})", ms, global_batch * K, "heatmaps", 24596, peak * world)
+    ent["scaling"] = "strong"
+    ent["batch_per_gpu"] = b
+    return ent
