@@ -475,7 +475,8 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
     P.z = std::sqrt((double)((long long)R * R + (long long)R * R));
     P.N = N; P.Pmax = Pmax; P.K = K; P.R = R;
     const int quads = R * R / 4;
-    if (Pmax <= pose::kSpmFusedMaxPersons && !getenv("POSE_B200_SPM_RENDER_TWO_PASS")) {
+    static const bool two_pass = getenv("POSE_B200_SPM_RENDER_TWO_PASS") != nullptr;      // diagnostics: force the fill + patch pair (read once)
+    if (Pmax <= pose::kSpmFusedMaxPersons && !two_pass) {
         // single pass: the render-only form of the fused kernel (linear write stream, covered pixels filled in by the same pass)
         pose::SpmFusedParams F;
         memset(&F, 0, sizeof(F));
@@ -486,13 +487,13 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
         F.div_n = R <= 1024 ? 2 * R + 1 : 0;
         const size_t fsmem = pose::spm_fused_smem_bytes(F.div_n, R, K, F.wpr, lut_n);
         if (fsmem <= 200 * 1024) {
-            const int fchunk = pose::kSpmThreads * pose::spm_fused_u(false, true, false);
+            const int fchunk = pose::kSpmStreamThreads * pose::spm_fused_u(false, true, false);
             const long long funits = (long long)N * (1 + 2 * K) * ((quads + fchunk - 1) / fchunk);
 #define POSE_SPMR(RG, MP)                                                                                                      \
     {                                                                                                                          \
-        if (fsmem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<false, false, true, RG, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem); \
-        const int fgrid = persistent_grid(pose::spm_fused_kernel<false, false, true, RG, MP>, pose::kSpmThreads, fsmem, funits); \
-        pose::spm_fused_kernel<false, false, true, RG, MP><<<fgrid, pose::kSpmThreads, fsmem, (cudaStream_t)stream>>>(F);      \
+        const int fgrid = persistent_grid(pose::spm_fused_kernel<false, false, true, RG, MP>, pose::kSpmFusedThreads, fsmem, funits, "spm_render"); \
+        if (fgrid == 0) return last_code();                                                                                    \
+        pose::spm_fused_kernel<false, false, true, RG, MP><<<fgrid, pose::kSpmFusedThreads, fsmem, (cudaStream_t)stream>>>(F); \
     }
             if (pose::spm_fused_use_map(R)) { if (R % 128 == 0) POSE_SPMR(true, true) else POSE_SPMR(false, true) }
             else { if (R % 128 == 0) POSE_SPMR(true, false) else POSE_SPMR(false, false) }
@@ -502,7 +503,8 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
     }
     const size_t smem = (size_t)lut_n * lut_n * sizeof(float);
     const long long units = (long long)N * (1 + 2 * K) * ((quads + pose::kSpmRenderChunk - 1) / pose::kSpmRenderChunk);
-    const int grid = persistent_grid(pose::spm_fill_kernel, pose::kSpmThreads, smem, units);
+    const int grid = persistent_grid(pose::spm_fill_kernel, pose::kSpmThreads, smem, units, "spm_fill");
+    if (grid == 0) return last_code();
     pose::spm_fill_kernel<<<grid, pose::kSpmThreads, smem, (cudaStream_t)stream>>>(P);
     if (int rc = check_launch("spm_fill")) return rc;
     if (Pmax > 0) {
@@ -544,10 +546,12 @@ int pose_spm_loss(const float* logits, const float* target, float* dlogits, floa
     if (N > 0) {
         const long long ctas = P.planes * ((P.quads + pose::kSpmLossChunk - 1) / pose::kSpmLossChunk);
         if (write_grad) {
-            grid = persistent_grid(pose::spm_loss_kernel<true>, pose::kSpmThreads, 0, ctas);
+            grid = persistent_grid(pose::spm_loss_kernel<true>, pose::kSpmThreads, 0, ctas, "spm_loss");
+            if (grid == 0) return last_code();
             pose::spm_loss_kernel<true><<<grid, pose::kSpmThreads, 0, st>>>(P);
         } else {
-            grid = persistent_grid(pose::spm_loss_kernel<false>, pose::kSpmThreads, 0, ctas);
+            grid = persistent_grid(pose::spm_loss_kernel<false>, pose::kSpmThreads, 0, ctas, "spm_loss");
+            if (grid == 0) return last_code();
             pose::spm_loss_kernel<false><<<grid, pose::kSpmThreads, 0, st>>>(P);
         }
         if (int rc = check_launch("spm_loss")) return rc;
@@ -591,13 +595,13 @@ int pose_spm_fused(const float* logits, const long long* centers, const long lon
         P.gdisp = (float)((double)lambda_disp * inv_norm);
         const size_t smem = pose::spm_fused_smem_bytes(P.div_n, R, K, P.wpr, lut_n);
         if (smem > 200 * 1024) return fail(POSE_EINVAL, "spm_fused: R=%d K=%d needs %zu bytes of shared memory (use pose_spm_render + pose_spm_loss)", R, K, smem);
-        const int uchunk = pose::kSpmThreads * pose::spm_fused_u(grad, wtgt);
+        const int uchunk = pose::kSpmStreamThreads * pose::spm_fused_u(grad, wtgt);
         const long long units = (long long)N * (1 + 2 * K) * ((P.quads + uchunk - 1) / uchunk);
 #define POSE_SPMF3(G, T, RG, MP)                                                                                              \
     {                                                                                                                          \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(pose::spm_fused_kernel<true, G, T, RG, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        grid = persistent_grid(pose::spm_fused_kernel<true, G, T, RG, MP>, pose::kSpmThreads, smem, units);                    \
-        pose::spm_fused_kernel<true, G, T, RG, MP><<<grid, pose::kSpmThreads, smem, st>>>(P);                                  \
+        grid = persistent_grid(pose::spm_fused_kernel<true, G, T, RG, MP>, pose::kSpmFusedThreads, smem, units, "spm_fused");  \
+        if (grid == 0) return last_code();                                                                                     \
+        pose::spm_fused_kernel<true, G, T, RG, MP><<<grid, pose::kSpmFusedThreads, smem, st>>>(P);                             \
     }
 #define POSE_SPMF(G, T)                                                                                                        \
     {                                                                                                                          \

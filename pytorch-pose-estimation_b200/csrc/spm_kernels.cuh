@@ -339,54 +339,34 @@ struct __align__(16) SpmFusedPerson {
     int px0, px1, py0, py1;     // Gaussian patch window clipped to the map and to the template, [x0,x1) x [y0,y1); empty: all 0
 };
 
+// Launch shape: 8 STREAM warps + 1 PATCH warp per CTA (288 threads), 3 CTAs per SM (register cap 72).
 #ifndef POSE_SPM_FUSED_MINB
-#define POSE_SPM_FUSED_MINB 4   // resident CTAs per SM the kernel is compiled for (register cap 64)
+#define POSE_SPM_FUSED_MINB 3
 #endif
-// float4 per thread and unit (1, 2, 4 or 8: the unit must divide a 128x128 plane), per variant (tools/spm_skeleton.py,
-// profiles/r01_spm_unit_sweep.log, per 256 / 1024 images):
-//   loss + grad (read logits, write dlogits): 8 KB units -- U=2 222 / 817 us, U=4 235 / 907, U=8 242 / 924, U=1 272 / 1028;
-//   read-only loss: 32 KB units (more covered quads pooled per phase B, twice the loads in flight) -- U=8 123 / 415 us,
-//     U=4 138 / 488, U=2 166 / 633;
-//   render-only (LOSS = false, pose_spm_render): 32 KB units -- U=8 123 / 447 us, U=4 124 / 457, U=2 127 / 456.
+// float4 per stream thread and unit (the unit must divide a 128x128 plane: 1, 2, 4, 8 or 16), per variant
 #ifndef POSE_SPM_FUSED_U
-#define POSE_SPM_FUSED_U 2
+#define POSE_SPM_FUSED_U 4              // loss + grad: read logits, write dlogits (16 KB units)
 #endif
 #ifndef POSE_SPM_FUSED_U_RO
-#define POSE_SPM_FUSED_U_RO 8
+#define POSE_SPM_FUSED_U_RO 8           // read-only loss (32 KB units)
 #endif
 #ifndef POSE_SPM_FUSED_U_RENDER
-#define POSE_SPM_FUSED_U_RENDER 8
+#define POSE_SPM_FUSED_U_RENDER 8       // render only: write stream
 #endif
 __host__ __device__ constexpr int spm_fused_u(bool grad, bool wtgt, bool loss = true) {
     return !loss ? POSE_SPM_FUSED_U_RENDER : (grad || wtgt) ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
 }
-constexpr int kSpmFusedUMax0 = POSE_SPM_FUSED_U > POSE_SPM_FUSED_U_RO ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
-constexpr int kSpmFusedUMax = kSpmFusedUMax0 > POSE_SPM_FUSED_U_RENDER ? kSpmFusedUMax0 : POSE_SPM_FUSED_U_RENDER;
 constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
-// PATCH (read-only loss variant at R = 128, i.e. ROWG && MAP): the covered quads of an image are listed once per image; the
-// stream (phase A) never stops for them and ONE pass per plane, by the whole CTA with one pixel per thread and full lanes,
-// computes the listed pixels.  Their logits are requested when the CTA enters the plane and consumed when it leaves it, so the
-// dependent chain of the per-warp phase B is off the streaming path: 124.0 -> 115.9 us per 256 images, 417.8 -> 407.9 us per
-// 1024.  POSE_SPM_PATCHPASS = 2 applies it to the variants that write dlogits / the target as well (phase A then skips the
-// zero stores of covered quads and the patch pass writes them): correct (all SPM GPU tests pass) but slower there -- 220.8 ->
-// 225.6 us, 819 -> 864 us -- the predicated stores cost the stream more than the per-warp phase B did.
-// POSE_SPM_PATCHPASS = 3 (NOT YET RUN ON A GPU -- written after the round's GPU budget was spent; the next thing to test): the
-// writing variants keep their unconditional zero stores, the CTA meets at ONE barrier when it leaves a plane and the patch
-// pass then overwrites the covered pixels (the barrier orders the CTA's zero stores before them).
-#ifndef POSE_SPM_PATCHPASS
-#define POSE_SPM_PATCHPASS 1
-#endif
-#ifndef POSE_SPM_PATCH_NPRE
-#define POSE_SPM_PATCH_NPRE 3   // pixels per thread whose logits are requested at plane entry (3 x 256 = 192 covered quads)
-#endif
-constexpr int kSpmPatchListCap = 4096;                        // all quads of a 128 x 128 plane
-
+constexpr int kSpmStreamWarps = 8;
+constexpr int kSpmStreamThreads = kSpmStreamWarps * 32;
+constexpr int kSpmFusedThreads = kSpmStreamThreads + 32;      // + the patch warp
+constexpr int kSpmListCap = 2048;                             // covered quads of one image kept as a list (more: the bitmap is walked)
 constexpr int kSpmMapMaxBytes = 16384;                        // per-image pixel map (one byte per pixel): R <= 128
 
 __host__ __device__ inline bool spm_fused_use_map(int R) { return R * R <= kSpmMapMaxBytes; }
 __host__ __device__ inline size_t spm_fused_smem_bytes(int div_n, int R, int K, int wpr, int lut_n) {
     return (size_t)div_n * 8 + (size_t)R * 8 + (size_t)kSpmFusedMaxPersons * K * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4 +
-           (spm_fused_use_map(R) ? (size_t)R * R : 0);
+           (size_t)kSpmListCap * 4 + (spm_fused_use_map(R) ? (size_t)R * R : 0);
 }
 
 // target of one pixel: (root value t0 = max of the covering Gaussian patches, displacement te of plane (jn, axis))
@@ -412,54 +392,46 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
     }
 }
 
-// LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read, the target is
-// written as one linear stream with the covered pixels filled in by the same pass.
-// MAP (R*R <= 16 KB, i.e. R <= 128 -- configs/spm_coco.yaml): the geometry of a pixel is the same for all 2K displacement
-// planes of an image, so it is evaluated ONCE per image into a byte map in shared memory -- bit 7: root mask (t0 > 0), bits
-// 0-6: 0 = in no person's box, p+1 = in the box of person p only, 127 = in several boxes (replay them in order) -- and phase B
-// of a displacement plane is one byte load + one joint + one quotient look-up instead of a loop over the row's persons with
-// eight range compares each.  Larger maps keep the generic per-pixel evaluation.
-// ROWG (R % 128 == 0): the 32 quads of a warp instruction lie in one row and are exactly one word of that row's
-// covered-quad bits, and every unit is full: one broadcast LDS gives the warp's coverage mask (no per-lane look-up, no
-// ballot, no validity predicates on the stream).
-// (Tried and dropped: a 4-row x 8-quad tile per warp instruction, so that a 9x9 box touches ~3.75 tiles instead of 9 rows and
-// phase B is entered 2.4x less often -- the four separate 128-byte lines per access cost more than that saved: 253 -> 318 us
-// fused, 144 -> 177 us render-only per 256 images.  Likewise a warp owning U CONSECUTIVE rows of a unit instead of every 8th row
-// (a 9-row box then falls to ~3 warps with full phase-B passes instead of 8 sparse ones): 235 -> 290 us fused, 125 -> 175 us
-// read-only -- the few loaded warps become the critical path of the CTA's unit range.  And a per-warp shared-memory ring filled
-// with cp.async (LDGSTS) so that the next units' loads fly during phase B and phase B reads its logit from the ring instead of
-// L2: 235 -> 235 us (N=256), 902 -> 872 us (N=1024) for the grad variant at 3 CTAs/SM, 125 -> 139 us read-only -- the L2
-// prefetch of the next unit already hides that latency; not worth 32 KB of shared memory per CTA.)
+// The SPM target is ~97 % zeros and the zero part costs nothing but bandwidth: target 0, mask 0 => the loss term is 0 unless
+// the logit is NaN (sigmoid(p)*0 and tanh(p)*0 are 0 for every other p) and dlogits = 0.  The kernel is therefore two
+// programs that never touch the same bytes, run by different warps of one CTA:
+//   * 8 STREAM warps walk the CTA's contiguous range of 16/32 KB units linearly: one broadcast shared-memory word tells a warp
+//     which of its 32 float4 quads lie in some person's box or Gaussian patch ("covered"); the other quads are loaded (NaN
+//     check only), and zeros are stored to dlogits / the target.  No person data, no branches, no dependent chains.
+//   * 1 PATCH warp owns the covered quads (~3-6 % of a plane, the same set for all 1+2K planes of an image, listed once per
+//     image): one quad per lane -- 128-bit load of the logits (prefetched into L2 one plane ahead), the plane-independent
+//     geometry from a per-image byte map (MAP) or the generic person loop, template / quotient-table look-ups, tanhf only
+//     under the root mask -- and 128-bit stores of the 4 results.  Its long dependent chains (LDS -> LDG -> LDS -> SFU -> STG)
+//     delay nobody: the stream warps never wait for it except at an image boundary of the CTA's range.
+// LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read.
+// MAP (R*R <= 16 KB, i.e. R <= 128 -- configs/spm_coco.yaml): bit 7 = root mask (t0 > 0), bits 0-6: 0 = in no person's box,
+//   p+1 = in the box of person p only, 127 = in several boxes (replay them in order).
+// ROWG (R % 128 == 0): the 32 quads of a warp instruction are exactly one word of the covered-quad bitmap and every unit is full.
+// History (r01, per 256 images, loss + grad): covered pixels handled inside the streaming warps, pooled per warp and unit with
+// the logits re-read through L2 -- 220.9 us (81 % of the copy peak); a per-plane patch pass by the whole CTA: 225.6 us.
 template <bool LOSS, bool GRAD, bool WTGT, bool ROWG, bool MAP>
-__global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
+__global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
     // dynamic shared memory: [div_n] double quotients | [R] u64 row masks | [64*K] int2 joints | [R*wpr] u32 covered quads | template
-    //                        | MAP: [R*R] u8 pixel map
+    //                        | [kSpmListCap] u32 covered-quad list | MAP: [R*R] u8 pixel map
     extern __shared__ __align__(16) unsigned char spm_fused_smem[];
     double* div_s = reinterpret_cast<double*>(spm_fused_smem);
     unsigned long long* rowmask_s = reinterpret_cast<unsigned long long*>(div_s + P.div_n);
     int2* s_j = reinterpret_cast<int2*>(rowmask_s + P.R);
     unsigned int* covq_s = reinterpret_cast<unsigned int*>(s_j + kSpmFusedMaxPersons * P.K);
     float* lut_s = reinterpret_cast<float*>(covq_s + P.R * P.wpr);
-    unsigned char* map_s = reinterpret_cast<unsigned char*>(lut_s + P.lut_n * P.lut_n);      // MAP only
+    unsigned int* list_s = reinterpret_cast<unsigned int*>(lut_s + P.lut_n * P.lut_n);
+    unsigned char* map_s = reinterpret_cast<unsigned char*>(list_s + kSpmListCap);           // MAP only
     __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
-    __shared__ double red[kSpmThreads / 32][2];
-    constexpr int kSpmFusedU = spm_fused_u(GRAD, WTGT, LOSS);
-    constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;          // float4 per work unit
-    __shared__ unsigned char s_src[kSpmThreads / 32][32 * kSpmFusedU];
-    // ROWG && MAP <=> R == 128: 32 quads per row, wpr == 1
-    // (mode 3 also covers the render-only form, LOSS = false: no logits, the pass only writes the covered target pixels)
-    constexpr bool PATCH = ROWG && MAP && ((LOSS && POSE_SPM_PATCHPASS >= 2) || POSE_SPM_PATCHPASS == 3 ||
-                                           (LOSS && POSE_SPM_PATCHPASS == 1 && !GRAD && !WTGT));
-    constexpr bool PATCH_BAR = PATCH && POSE_SPM_PATCHPASS == 3 && (GRAD || WTGT);   // zero stores stay; barrier, then overwrite
-    constexpr int NPRE = POSE_SPM_PATCH_NPRE;
-    __shared__ unsigned short plist_s[PATCH ? kSpmPatchListCap : 1];   // covered quads of the staged image, ascending
-    __shared__ int s_nlist;
+    __shared__ double red[kSpmFusedThreads / 32][2];
+    __shared__ int s_nlist;                                            // covered quads of the staged image; -1: too many for the list
+    constexpr int U = spm_fused_u(GRAD, WTGT, LOSS);
+    constexpr int kChunk = kSpmStreamThreads * U;                      // float4 per work unit
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
     for (int i = threadIdx.x; i < P.div_n; i += blockDim.x) div_s[i] = (double)(i - P.R) / P.z;
 
     const int C = 1 + 2 * P.K;
-    const int upp = (P.quads + kSpmFusedChunk - 1) / kSpmFusedChunk;
+    const int upp = (P.quads + kChunk - 1) / kChunk;
     const long long units = (long long)P.N * C * upp;
     const long long u_begin = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
     const float4* L4 = reinterpret_cast<const float4*>(P.logits);
@@ -468,21 +440,17 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
     const int qpr = (int)P.div_qpr.d;
     const long long total_quads = (long long)P.N * C * P.quads;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool streamer = wid < kSpmStreamWarps;                       // warp-uniform role
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     double droot = 0.0, ddisp = 0.0;
-    int staged_img = -1;
 
-    // (image, channel, chunk) of the first unit; advanced incrementally (no 64-bit divisions in the loop)
-    long long plane = u_begin / upp;
-    int chunk = (int)(u_begin - plane * upp);
-    int img = (int)(plane / C), c = (int)(plane - (long long)img * C);
-
-    int q_first = 0, q_last = 0;                                       // PATCH: this CTA's quads [q_first, q_last) of the current plane
-    float pl[NPRE];                                                    // PATCH: logits requested at plane entry
-    for (long long unit = u_begin; unit < u_end; ++unit) {
-        if (img != staged_img) {                                       // CTA-uniform
+    for (long long seg = u_begin; seg < u_end;) {
+        // ---------------- one image's share of the CTA's range: [seg, seg_end)
+        const int img = (int)(seg / ((long long)C * upp));
+        const long long seg_end = min(u_end, (long long)(img + 1) * C * upp);
+        {
             const int np = min(max(P.counts[img], 0), min(P.Pmax, kSpmFusedMaxPersons));
-            __syncthreads();
+            __syncthreads();                                           // both roles are done with the previous image's tables
             for (int i = threadIdx.x; i < np; i += blockDim.x) {
                 SpmFusedPerson sp;
                 const long long pi = (long long)img * P.Pmax + i;
@@ -521,243 +489,217 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 if (xhi < xlo) continue;
                 atomicOr(&rowmask_s[row], 1ull << p);
                 const int q0 = xlo >> 2, q1 = xhi >> 2;
-                    for (int w = q0 >> 5; w <= (q1 >> 5); ++w) {
+                for (int w = q0 >> 5; w <= (q1 >> 5); ++w) {
                     const int lo = max(q0 - 32 * w, 0), hi = min(q1 - 32 * w, 31);
                     const unsigned int bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
                     atomicOr(&covq_s[row * P.wpr + w], bits);
                 }
             }
             __syncthreads();
-            if (MAP) {
-                // one warp per row; only rows that some person touches are ever looked up, the others are not even written
-                for (int row = wid; row < P.R; row += kSpmThreads / 32) {
+            if (MAP && streamer) {
+                // one stream warp per row; only rows that some person touches are ever looked up, the others are not even written
+                for (int row = wid; row < P.R; row += kSpmStreamWarps) {
                     const unsigned long long rm = rowmask_s[row];
                     if (rm == 0ull) continue;                           // warp-uniform
-                  for (int col = lane; col < P.R; col += 32) {
-                    const int idx = row * P.R + col;
-                    unsigned long long m = rm;
-                    unsigned int code = 0u, nbox = 0u;
-                    bool mk = false;
-                    while (m) {
-                        const int p = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        const SpmFusedPerson sp = s_p[p];
-                        if (row >= sp.py0 && row < sp.py1 && col >= sp.px0 && col < sp.px1 &&
-                            lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)] > 0.0f) mk = true;
-                        if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
-                            if (nbox++ == 0u) code = (unsigned)p + 1u;
+                    for (int col = lane; col < P.R; col += 32) {
+                        unsigned long long m = rm;
+                        unsigned int code = 0u, nbox = 0u;
+                        bool mk = false;
+                        while (m) {
+                            const int p = __ffsll((long long)m) - 1;
+                            m &= m - 1;
+                            const SpmFusedPerson sp = s_p[p];
+                            if (row >= sp.py0 && row < sp.py1 && col >= sp.px0 && col < sp.px1 &&
+                                lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)] > 0.0f) mk = true;
+                            if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
+                                if (nbox++ == 0u) code = (unsigned)p + 1u;
+                            }
                         }
+                        if (nbox > 1u) code = 127u;
+                        map_s[row * P.R + col] = (unsigned char)(code | (mk ? 128u : 0u));
                     }
-                    if (nbox > 1u) code = 127u;
-                    map_s[idx] = (unsigned char)(code | (mk ? 128u : 0u));
-                  }
                 }
-                if (PATCH && wid == kSpmThreads / 32 - 1) {
-                    // the covered-quad bits (one word per row, 4 rows per lane) -> ascending list of quad indices
-                    unsigned int w4[4];
-                    int cnt = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { w4[k] = covq_s[4 * lane + k]; cnt += __popc(w4[k]); }
+            }
+            if (!streamer) {
+                // the patch warp lists the covered quads (plane-relative quad index, ascending) from the bitmap: 32 words per step,
+                // a shuffle scan of their popcounts gives every lane its write position
+                const int nwords = P.R * P.wpr;
+                int base = 0;
+                bool fits = true;
+                for (int w0 = 0; w0 < nwords; w0 += 32) {
+                    const int wi = w0 + lane;
+                    unsigned int bits = wi < nwords ? covq_s[wi] : 0u;
+                    const int cnt = __popc(bits);
                     int incl = cnt;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const int t = __shfl_up_sync(FULL_MASK, incl, o);
                         if (lane >= o) incl += t;
                     }
-                    int pos = incl - cnt;
+                    const int tot = __shfl_sync(FULL_MASK, incl, 31);
+                    if (base + tot > kSpmListCap) { fits = false; break; }       // warp-uniform
+                    int pos = base + incl - cnt;
+                    const int row = wi / P.wpr, q0 = row * qpr + (wi - row * P.wpr) * 32;
+                    while (bits) {
+                        const int b = __ffs((int)bits) - 1;
+                        bits &= bits - 1u;
+                        list_s[pos++] = (unsigned int)(q0 + b);
+                    }
+                    base += tot;
+                }
+                if (lane == 0) s_nlist = fits ? base : -1;
+            }
+            __syncthreads();
+        }
+
+        if (streamer) {
+            // ---------------- STREAM: every quad that no person touches
+            long long plane = seg / upp;
+            int chunk = (int)(seg - plane * upp);
+            int c = (int)(plane - (long long)img * C);
+            const int tid = threadIdx.x;                               // 0 .. 255
+            for (long long unit = seg; unit < seg_end; ++unit) {
+                const long long off = plane * P.quads;
+                const int q_lo = chunk * kChunk;
+                float4 pv[U];
+                bool live[U];                                          // valid and not covered: this thread's quad of instruction u
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        unsigned int bits = w4[k];
-                        while (bits) {
-                            const int b = __ffs((int)bits) - 1;
-                            bits &= bits - 1u;
-                            plist_s[pos++] = (unsigned short)((4 * lane + k) * 32 + b);
+                for (int u = 0; u < U; ++u) {
+                    const int q = q_lo + u * kSpmStreamThreads + tid;
+                    if (ROWG) {
+                        // quads is a multiple of the chunk and a warp instruction is one word of the bitmap: one broadcast LDS
+                        live[u] = !((covq_s[(q_lo >> 5) + u * kSpmStreamWarps + wid] >> lane) & 1u);
+                    } else {
+                        live[u] = false;
+                        if (q < P.quads) {
+                            const int row = (int)fdiv((uint32_t)q, P.div_qpr), cq = q - row * qpr;
+                            live[u] = !((covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u);
                         }
                     }
-                    if (lane == 31) s_nlist = incl;
+                    if (LOSS && live[u]) pv[u] = ldg_stream(L4 + off + q);
                 }
-                __syncthreads();
-            }
-            staged_img = img;
-        }
-        const long long off = plane * P.quads;
-        const int q_lo = chunk * kSpmFusedChunk;
-        float4 pv[kSpmFusedU];
-        const float4* lsrc = L4 + off + q_lo + threadIdx.x;
-        // ROWG: quads is a multiple of the chunk, so every quad of every unit is valid (no predicates on the stream)
-#pragma unroll
-        for (int u = 0; u < kSpmFusedU; ++u)
-            if (LOSS && (ROWG || q_lo + u * kSpmThreads + (int)threadIdx.x < P.quads)) pv[u] = ldg_stream(lsrc + u * kSpmThreads);
-        if (LOSS && unit + 1 < u_end) {
-            // the next unit of this CTA is the next 16 KB in memory (planes are contiguous): pull it into L2 while this unit
-            // computes.  Measured alternatives, both SLOWER than this prefetch (252 us per 256 images): holding the next unit in
-            // a second register set (285-291 us at 3 CTAs/SM), and re-using pv for the next unit's loads right after phase A so
-            // that they fly during phase B (278 us: pv then lives across phase B and spills under the 64-register cap).
-            const char* nsrc = reinterpret_cast<const char*>(L4 + off + min(q_lo + kSpmFusedChunk, P.quads));
-            const char* lend = reinterpret_cast<const char*>(L4 + total_quads);
-            if (threadIdx.x < kSpmFusedChunk * 16 / 128 && nsrc + threadIdx.x * 128 < lend) prefetch_l2(nsrc + threadIdx.x * 128);
-        }
-        const bool disp = c != 0;
-        const int jn = (c - 1) >> 1, axis = (c - 1) & 1;                 // displacement plane: joint and axis (0 = x, 1 = y)
-        float acc = 0.f;
-        if (PATCH && (unit == u_begin || chunk == 0)) {                  // entering a plane (CTA-uniform)
-            q_first = q_lo;
-            q_last = (chunk + (int)min((long long)(upp - chunk), u_end - unit)) * kSpmFusedChunk;
-            const int nl4 = 4 * s_nlist;
-#pragma unroll
-            for (int k = 0; k < NPRE; ++k) {
-                const int i = (int)threadIdx.x + k * kSpmThreads;
-                pl[k] = 0.0f;
-                if (i < nl4) {
-                    const int q = (int)plist_s[i >> 2];
-                    if (LOSS && q >= q_first && q < q_last) pl[k] = __ldg(P.logits + (off + q) * 4 + (i & 3));
+                if (LOSS && unit + 1 < seg_end) {
+                    // the next unit of this CTA is the next 16/32 KB in memory (planes are contiguous): pull it into L2 meanwhile
+                    const char* nsrc = reinterpret_cast<const char*>(L4 + off + min(q_lo + kChunk, P.quads));
+                    const char* lend = reinterpret_cast<const char*>(L4 + total_quads);
+                    if (tid < kChunk * 16 / 128 && nsrc + tid * 128 < lend) prefetch_l2(nsrc + tid * 128);
                 }
-            }
-        }
-        unsigned cmask[kSpmFusedU];
-        float4* gdst = GRAD ? G4 + off + q_lo + threadIdx.x : nullptr;
-        float4* tdst = WTGT ? T4 + off + q_lo + threadIdx.x : nullptr;
-        unsigned anyc = 0u;
-        if (ROWG) {
-            // phase A, uniform: EVERY quad is treated as uncovered (zero target, zero mask: the loss term is 0 unless the logit
-            // is NaN -- sigmoid(p)*0 and tanh(p)*0 are 0 for every other p -- and dlogits = 0); phase B then overwrites the
-            // pixels of the covered quads (ordered after these stores by its __syncwarp; a NaN counted twice is still a NaN).
-            // The warp's coverage mask is one broadcast LDS: with wpr = qpr/32 the word index is the warp's group index in the
-            // plane.  No per-lane look-up, no ballot, no branch on the stream.
+                float acc = 0.f;
 #pragma unroll
-            for (int u = 0; u < kSpmFusedU; ++u) {
-                if (LOSS) {
-                    const float4 v = pv[u];
-                    const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-                    if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
-                }
-                cmask[u] = covq_s[(q_lo >> 5) + u * (kSpmThreads / 32) + wid];
-                if (!PATCH || PATCH_BAR || !((cmask[u] >> lane) & 1u)) {  // PATCH: covered quads are written by the plane's patch pass
-                    if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
-                    if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kSpmFusedU; ++u) anyc |= cmask[u];
-        } else {
-#pragma unroll
-            for (int u = 0; u < kSpmFusedU; ++u) {
-                const int qu = q_lo + u * kSpmThreads + (int)threadIdx.x;
-                const bool valid = qu < P.quads;
-                bool covered = false;
-                if (valid) {
-                    const int row = (int)fdiv((uint32_t)qu, P.div_qpr), cq = qu - row * qpr;
-                    covered = (covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u;
-                }
-                cmask[u] = __ballot_sync(FULL_MASK, covered);
-                if (cmask[u]) anyc |= 1u << u;
-                if (valid && !covered) {
+                for (int u = 0; u < U; ++u) {
+                    if (!live[u]) continue;
+                    const int q = q_lo + u * kSpmStreamThreads + tid;
                     if (LOSS) {
                         const float4 v = pv[u];
                         const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
                         if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
                     }
-                    if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
-                    if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
+                    if (GRAD) __stcs(G4 + off + q, z4);
+                    if (WTGT) __stcs(T4 + off + q, z4);
                 }
+                if (LOSS && acc != 0.f) { if (c == 0) droot += (double)acc; else ddisp += (double)acc; }     // NaN only
+                if (++chunk == upp) { chunk = 0; ++plane; ++c; }
             }
-        }
-        // phase B: one pixel of a covered quad per lane.  The covered quads of ALL the warp's instructions of this unit are
-        // pooled (slot k of the warp's scratch row = u*32 + lane of the k-th covered quad), so the long dependent chain below
-        // runs once per warp and unit with up to 32 useful lanes, not once per covered instruction with ~14.  Deliberately not
-        // unrolled over u (an unrolled copy per u made the kernel 113 KB of SASS and `no_instruction` the second largest
-        // stall).  The pixel's logit is re-read from L2 (the warp streamed it a moment ago) rather than shuffled out of pv[]:
-        // pv dies after phase A, which keeps the kernel inside 64 registers without spills.
-        // one covered pixel: element e of quad qs (plane-relative) with logit pe
-        auto pixel = [&](int qs, int e, float pe) {
-            const long long ei = (off + qs) * 4 + e;
-            const int row = (int)fdiv((uint32_t)qs, P.div_qpr), col = (qs - row * qpr) * 4 + e;
-            float t0 = 0.0f, te = 0.0f;
-            bool mk;
-            unsigned int code = 127u;
-            if (MAP && disp) code = map_s[row * P.R + col];
-            if (ROWG && MAP && disp && code == 0u) {                      // slack pixel of a covered quad
-                if (PATCH && !PATCH_BAR) {                                // phase A left the covered quads unwritten
-                    if (GRAD) __stcs(P.dlogits + ei, 0.0f);
-                    if (WTGT) __stcs(P.target_out + ei, 0.0f);
+        } else {
+            // ---------------- PATCH: the covered quads of every plane (or part of a plane) in [seg, seg_end), one quad per lane
+            const int nlist = s_nlist;
+            const long long p_first = seg / upp, p_last = (seg_end - 1) / upp;
+            // one covered quad: 4 pixels of row `row` starting at column col0, logits pe
+            auto quad = [&](long long off, int q, bool disp, int jn, int axis, float& acc) {
+                const int row = (int)fdiv((uint32_t)q, P.div_qpr), col0 = (q - row * qpr) * 4;
+                float pe[4] = {0.f, 0.f, 0.f, 0.f};
+                if (LOSS) {
+                    const float4 v = __ldg(L4 + off + q);
+                    pe[0] = v.x; pe[1] = v.y; pe[2] = v.z; pe[3] = v.w;
                 }
-                return;                                                   // (not PATCH: phase A's zeros stand)
-            }
-            if (MAP && disp && (code & 127u) != 127u) {
-                mk = code >> 7;
-                if (code & 127u) {
-                    const int2 jv = s_j[((int)(code & 127u) - 1) * P.K + jn];
-                    if (!(jv.x <= 0 && jv.y <= 0)) {
-                        const int dd = axis ? jv.y - row : jv.x - col;
-                        te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
+                unsigned int codes = 0x7f7f7f7fu;
+                if (MAP) codes = *reinterpret_cast<const unsigned int*>(map_s + row * P.R + col0);
+                float ge[4], te4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = col0 + e;
+                    const unsigned int code = (codes >> (8 * e)) & 255u;
+                    float t0 = 0.0f, te = 0.0f;
+                    bool mk;
+                    if (MAP && disp && (code & 127u) != 127u) {
+                        mk = code >> 7;
+                        if (code & 127u) {
+                            const int2 jv = s_j[((int)(code & 127u) - 1) * P.K + jn];
+                            if (!(jv.x <= 0 && jv.y <= 0)) {
+                                const int dd = axis ? jv.y - row : jv.x - col;
+                                te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
+                            }
+                        }
+                    } else if (MAP && !disp && (code & 128u) == 0u) {
+                        mk = false;                                       // root plane, pixel outside every Gaussian patch: t0 = 0
+                    } else {
+                        spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
+                        mk = t0 > 0.0f;
+                    }
+                    float g = 0.0f;
+                    if (!LOSS) {
+                        if (!disp) te = t0;
+                    } else if (!disp) {
+                        const float sg = sigmoid_fast(pe[e]);
+                        const float d = (mk ? sg : sg * 0.0f) - t0;
+                        acc = fmaf(d, d, acc);
+                        g = mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
+                        te = t0;
+                    } else {
+                        // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
+                        float th = 0.0f, pm = pe[e] != pe[e] ? pe[e] : 0.0f;   // NaN logits propagate as in the reference
+                        if (mk) { th = tanhf(pe[e]); pm = th; }
+                        const float d = pm - te;
+                        const float ad = fabsf(d);
+                        acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+                        g = mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
+                    }
+                    ge[e] = g;
+                    te4[e] = te;
+                }
+                if (GRAD) __stcs(G4 + off + q, make_float4(ge[0], ge[1], ge[2], ge[3]));
+                if (WTGT) __stcs(T4 + off + q, make_float4(te4[0], te4[1], te4[2], te4[3]));
+            };
+            for (long long plane = p_first; plane <= p_last; ++plane) {
+                const int c = (int)(plane - (long long)img * C);
+                const bool disp = c != 0;
+                const int jn = (c - 1) >> 1, axis = (c - 1) & 1;             // displacement plane: joint and axis (0 = x, 1 = y)
+                const long long off = plane * P.quads;
+                // this CTA's quads of the plane: [q_first, q_last)
+                const int q_first = plane == p_first ? (int)(seg - plane * upp) * kChunk : 0;
+                const int q_last = plane == p_last ? min(P.quads, (int)(seg_end - plane * upp) * kChunk) : P.quads;
+                float acc = 0.f;
+                if (nlist >= 0) {
+                    if (LOSS && plane < p_last) {
+                        // the next plane's covered logits travel to L2 while this plane is computed (no stream warp reads them)
+                        const int nq_last = plane + 1 == p_last ? min(P.quads, (int)(seg_end - (plane + 1) * upp) * kChunk) : P.quads;
+                        for (int i = lane; i < nlist; i += 32) {
+                            const int q = (int)list_s[i];
+                            if (q < nq_last) prefetch_l2(L4 + off + P.quads + q);
+                        }
+                    }
+                    for (int i = lane; i < nlist; i += 32) {
+                        const int q = (int)list_s[i];
+                        if (q >= q_first && q < q_last) quad(off, q, disp, jn, axis, acc);
+                    }
+                } else {
+                    // more covered quads than the list holds (dozens of persons on a large map): walk the bitmap, one word per lane
+                    const int nwords = P.R * P.wpr;
+                    for (int wi = lane; wi < nwords; wi += 32) {
+                        unsigned int bits = covq_s[wi];
+                        const int row = wi / P.wpr, q0 = row * qpr + (wi - row * P.wpr) * 32;
+                        while (bits) {
+                            const int b = __ffs((int)bits) - 1;
+                            bits &= bits - 1u;
+                            const int q = q0 + b;
+                            if (q >= q_first && q < q_last) quad(off, q, disp, jn, axis, acc);
+                        }
                     }
                 }
-            } else {
-                spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
-                mk = t0 > 0.0f;
-            }
-            float ge = 0.0f;
-            if (!LOSS) {
-                if (!disp) te = t0;
-            } else if (!disp) {
-                const float sg = sigmoid_fast(pe);
-                const float d = (mk ? sg : sg * 0.0f) - t0;
-                acc = fmaf(d, d, acc);
-                ge = mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
-                te = t0;
-            } else {
-                // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
-                float th = 0.0f, pm = pe != pe ? pe : 0.0f;          // NaN logits propagate as in the reference
-                if (mk) { th = tanhf(pe); pm = th; }
-                const float d = pm - te;
-                const float ad = fabsf(d);
-                acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-                ge = mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
-            }
-            if (GRAD) __stcs(P.dlogits + ei, ge);
-            if (WTGT) __stcs(P.target_out + ei, te);
-        };
-        if (!PATCH && anyc) {                                            // warp-uniform
-            int nslot = 0;
-#pragma unroll
-            for (int u = 0; u < kSpmFusedU; ++u) {
-                if ((cmask[u] >> lane) & 1u) s_src[wid][nslot + __popc(cmask[u] & ((1u << lane) - 1u))] = (unsigned char)(u * 32 + lane);
-                nslot += __popc(cmask[u]);
-            }
-            __syncwarp();                                                // also orders phase A's zero stores before the overwrites
-            const int total = nslot * 4;
-            for (int b = 0; b < total; b += 32) {
-                const int l = b + lane;
-                if (l >= total) continue;
-                const int sl = (int)s_src[wid][l >> 2];
-                const int qs = q_lo + (sl >> 5) * kSpmThreads + wid * 32 + (sl & 31);
-                const int e = l & 3;
-                pixel(qs, e, LOSS ? __ldg(P.logits + (off + qs) * 4 + e) : 0.0f);
-            }
-            __syncwarp();                                                // scratch row is rewritten by the next covered group
-        }
-        if (PATCH && (unit + 1 == u_end || chunk == upp - 1)) {          // leaving the plane (CTA-uniform): its patch pass
-            if (PATCH_BAR) __syncthreads();                              // every warp's zero stores of this plane are issued
-            const int nl4 = 4 * s_nlist;
-#pragma unroll
-            for (int k = 0; k < NPRE; ++k) {
-                const int i = (int)threadIdx.x + k * kSpmThreads;
-                if (i < nl4) {
-                    const int q = (int)plist_s[i >> 2];
-                    if (q >= q_first && q < q_last) pixel(q, i & 3, pl[k]);
-                }
-            }
-            for (int i = (int)threadIdx.x + NPRE * kSpmThreads; i < nl4; i += kSpmThreads) {
-                const int q = (int)plist_s[i >> 2];
-                if (q >= q_first && q < q_last) pixel(q, i & 3, LOSS ? __ldg(P.logits + (off + q) * 4 + (i & 3)) : 0.0f);
+                if (c == 0) droot += (double)acc; else ddisp += (double)acc;
             }
         }
-        if (c == 0) droot += (double)acc; else ddisp += (double)acc;
-        if (++chunk == upp) {
-            chunk = 0;
-            ++plane;
-            if (++c == C) { c = 0; ++img; }
-        }
+        seg = seg_end;
     }
     if (!LOSS) return;                                                   // render-only: no loss partials (P.partials is NULL)
     droot = warp_sum(droot);
@@ -767,7 +709,7 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int w = 0; w < kSpmThreads / 32; ++w) { a += red[w][0]; b += red[w][1]; }
+        for (int w = 0; w < kSpmFusedThreads / 32; ++w) { a += red[w][0]; b += red[w][1]; }
         P.partials[2 * blockIdx.x] = a;
         P.partials[2 * blockIdx.x + 1] = b;
     }

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B the fused SPM kernel's compile-time knobs (unit size per variant, resident CTAs per SM, patch-pass mode).
+"""A/B the fused SPM kernel's compile-time knobs (unit size per variant, resident CTAs per SM).
 
     python tools/tune_spm.py --build            # here (no GPU): nvcc one .so per variant into build/tune/
     python tools/tune_spm.py --run [--check]    # on the B200: time every variant (and the in-tree library) with tools/spm_skeleton.py;
@@ -17,16 +17,16 @@ OUT = os.path.join(ROOT, "build", "tune")
 SRC = os.path.join(ROOT, "pytorch-pose-estimation_b200", "csrc", "api.cu")
 NVCC = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
-# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: U=2 (grad), U_RO=8, U_RENDER=8, MINB=4, PATCHPASS=1.
+# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: U=4 (grad), U_RO=8, U_RENDER=8, MINB=3 (8 stream warps + 1 patch warp per CTA).
 VARIANTS = {
-    "patch0": ["-DPOSE_SPM_PATCHPASS=0"],                    # per-warp phase B everywhere
-    "patch2": ["-DPOSE_SPM_PATCHPASS=2"],                    # patch pass everywhere, covered quads' zero stores skipped
-    "patch3": ["-DPOSE_SPM_PATCHPASS=3"],                    # patch pass everywhere, barrier per plane (not yet run on a GPU)
-    "patch3_u4": ["-DPOSE_SPM_PATCHPASS=3", "-DPOSE_SPM_FUSED_U=4"],
-    "patch1_npre2": ["-DPOSE_SPM_PATCH_NPRE=2"],
-    "patch1_npre4": ["-DPOSE_SPM_PATCH_NPRE=4"],
-    "patch1_ro4": ["-DPOSE_SPM_FUSED_U_RO=4"],               # with the patch pass the read-only variant may prefer smaller units
-    "patch1_ro2": ["-DPOSE_SPM_FUSED_U_RO=2"],
+    "m4": ["-DPOSE_SPM_FUSED_MINB=4"],                                   # 4 CTAs per SM: 56 registers
+    "u8": ["-DPOSE_SPM_FUSED_U=8"],                                      # grad: 32 KB units
+    "u2": ["-DPOSE_SPM_FUSED_U=2"],                                      # grad: 8 KB units
+    "u8_m4": ["-DPOSE_SPM_FUSED_U=8", "-DPOSE_SPM_FUSED_MINB=4"],
+    "u2_m4": ["-DPOSE_SPM_FUSED_U=2", "-DPOSE_SPM_FUSED_MINB=4"],
+    "ro16_render16": ["-DPOSE_SPM_FUSED_U_RO=16", "-DPOSE_SPM_FUSED_U_RENDER=16"],
+    "ro4_render4": ["-DPOSE_SPM_FUSED_U_RO=4", "-DPOSE_SPM_FUSED_U_RENDER=4"],
+    "ro4_render4_m4": ["-DPOSE_SPM_FUSED_U_RO=4", "-DPOSE_SPM_FUSED_U_RENDER=4", "-DPOSE_SPM_FUSED_MINB=4"],
 }
 
 
