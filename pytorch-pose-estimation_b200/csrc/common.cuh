@@ -58,6 +58,39 @@ __device__ __forceinline__ float sigmoid_fast(float x) {
     return r;
 }
 
+// Sigmoids of 4 logits with ONE reciprocal (5 SFU operations instead of 8): with d_i = 1 + 2^(-x_i log2 e),
+//   r = 1 / (d0 d1 d2 d3),  s0 = r d1 (d2 d3),  s1 = r d0 (d2 d3),  s2 = r (d0 d1) d3,  s3 = r (d0 d1) d2.
+// The exponent is clamped at 30 (x < -20.8 reads as x = -20.8, an absolute error below 1e-9) so that the product of four
+// denominators stays finite.  A few ulp less accurate than sigmoid_fast (3 more roundings), far inside the 1e-5 tolerance of
+// the loss; used by the read-only loss kernels, which are bound by the SFU pipe, never by the decoders.
+__device__ __forceinline__ void sigmoid_fast4(const float (&x)[4], float (&s)[4]) {
+    float d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float e;
+        const float t = fminf(x[j] * -1.4426950408889634f, 30.0f);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+        d[j] = 1.0f + e;
+    }
+    const float p01 = d[0] * d[1], p23 = d[2] * d[3];
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+    const float a = r * p23, b = r * p01;
+    s[0] = a * d[1]; s[1] = a * d[0]; s[2] = b * d[3]; s[3] = b * d[2];
+}
+#ifndef POSE_SIGMOID_SHARE
+#define POSE_SIGMOID_SHARE 4            // read-only loss kernels: 4 = one reciprocal per 128-bit vector, 1 = one per element
+#endif
+template <int V, bool SHARE>
+__device__ __forceinline__ void sigmoid_vec(const float (&x)[V], float (&s)[V]) {
+    if constexpr (V == 4 && SHARE && POSE_SIGMOID_SHARE == 4) {
+        sigmoid_fast4(x, s);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) s[j] = sigmoid_fast(x[j]);
+    }
+}
+
 // ---------------------------------------------------------------- the reference's sigmoid, bit for bit
 // "argmax of sigmoid(x), first row-major index among equal values" (utils/sbp_utils.py:73-78) depends on WHICH fp32
 // sigmoid is meant: fp32 sigmoid is many-to-one and two implementations that differ by one ulp merge different

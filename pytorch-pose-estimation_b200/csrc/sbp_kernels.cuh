@@ -174,11 +174,14 @@ struct ArgTrack {
     }
 };
 
-// -> (conf, idx): the reference's activation value at its argmax and the flat index (0x7fffffff: nothing comparable in the map).
+// -> (conf, idx) in the lane(s) named by the return value: the reference's activation value at its argmax and the flat index
+// (0x7fffffff: nothing comparable in the map).  Returns the lane that holds the result when exactly one lane holds exactly one
+// candidate (the overwhelmingly common case: no shuffle reduction, the winner evaluates the reference sigmoid once on its own),
+// else 0 after a warp reduction (every lane then holds the result).
 // SIG == false (heat maps that are already activated, DecodeSBP.pred == False): candidates are the elements equal to m.
 template <int V, bool SIG>
-__device__ __forceinline__ void resolve_argmax(const ArgTrack<V>& a, const float* __restrict__ src, int nvec, int lane, int sig_ref,
-                                               float& conf, int& idx) {
+__device__ __forceinline__ int resolve_argmax(const ArgTrack<V>& a, const float* __restrict__ src, int nvec, int lane, int sig_ref,
+                                              float& conf, int& idx) {
     const float m = warp_max(a.best);
     float lo = m;
     bool again = false;
@@ -193,7 +196,25 @@ __device__ __forceinline__ void resolve_argmax(const ArgTrack<V>& a, const float
     float fb = -INFINITY;
     int fi = 0x7fffffff;
     if (!again) {
+        // candidates of this lane: elements of its best vector inside the window
+        int ncand = 0, jc = 0;
+        float xc = 0.0f;
         if (a.best >= lo) {
+#pragma unroll
+            for (int j = V - 1; j >= 0; --j)
+                if (a.keep[j] >= lo) { ++ncand; jc = j; xc = a.keep[j]; }   // (jc, xc): the first of them
+        }
+        const unsigned holders = __ballot_sync(FULL_MASK, ncand > 0);
+        const bool single = __popc(holders) == 1 && !__any_sync(FULL_MASK, ncand > 1);
+        if (single) {                                                     // warp-uniform
+            const int owner = __ffs(holders) - 1;
+            if (lane == owner) {
+                conf = SIG ? sigmoid_ref(xc, sig_ref) : xc;
+                idx = a.bestvi * V + jc;
+            }
+            return owner;
+        }
+        if (ncand > 0) {
 #pragma unroll
             for (int j = 0; j < V; ++j)
                 if (a.keep[j] >= lo) {
@@ -215,6 +236,7 @@ __device__ __forceinline__ void resolve_argmax(const ArgTrack<V>& a, const float
     }
     warp_argmax_first(fb, fi);
     conf = fb; idx = fi;
+    return 0;
 }
 
 // ---------------------------------------------------------------- render only
@@ -293,10 +315,10 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
                                                 const float* __restrict__ lut_s, int lut_n, int W, FastDiv divW, float gpos, float gneg,
                                                 float& apos, float& aneg, float& arem) {
     float sg[V];
+    sigmoid_vec<V, !GRAD>(x, sg);           // read-only variants: SFU-bound, one reciprocal per vector
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        const float sj = sigmoid_fast(x[j]);
-        sg[j] = sj;
+        const float sj = sg[j];
         if (GRAD) {
             const float c = sj * sj;
             aneg += c;
@@ -360,10 +382,10 @@ __device__ __forceinline__ void finish_map(const SbpFusedParams& P, long long ma
     dpos += (double)apos;
     dneg += (double)aneg - (double)arem;
     if (DEC) {
-        float conf;
-        int idx;
-        resolve_argmax<V, true>(arg, P.logits + map * P.HW, P.HW / V, lane, P.sig_ref, conf, idx);
-        if (lane == 0) {
+        float conf = -INFINITY;
+        int idx = 0x7fffffff;
+        const int owner = resolve_argmax<V, true>(arg, P.logits + map * P.HW, P.HW / V, lane, P.sig_ref, conf, idx);
+        if (lane == owner) {
             float jx = -1.0f, jy = -1.0f, jc = -1.0f;
             if (conf > P.thr && idx != 0x7fffffff) {
                 const int row = (int)fdiv((uint32_t)idx, P.divW);
@@ -436,8 +458,10 @@ sbp_fused_kernel(SbpFusedParams P) {
                 if (TGT == TGT_RENDER) {
                     render_loss_vec<V, GRAD, WTGT>(xv[u], g, tv[u], vi, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
                 } else {
+                    float sg[V];
+                    sigmoid_vec<V, !GRAD>(xv[u], sg);
 #pragma unroll
-                    for (int j = 0; j < V; ++j) g[j] = loss_elem<GRAD>(sigmoid_fast(xv[u][j]), tv[u][j], P.gpos, P.gneg, apos, aneg);
+                    for (int j = 0; j < V; ++j) g[j] = loss_elem<GRAD>(sg[j], tv[u][j], P.gpos, P.gneg, apos, aneg);
                 }
                 if (GRAD) Vec<V>::store(dl, vi, g);
                 if (WTGT) Vec<V>::store(to, vi, tv[u]);
@@ -598,11 +622,11 @@ __global__ void __launch_bounds__(kSbpThreads) sbp_decode_kernel(SbpDecodeParams
                 arg.template push<SIG>(xv[u], vi);
             }
         }
-        float best;
-        int besti;
-        resolve_argmax<V, SIG>(arg, src, nvec, lane, P.sig_ref, best, besti);
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        const int owner = resolve_argmax<V, SIG>(arg, src, nvec, lane, P.sig_ref, best, besti);
 
-        if (lane == 0) {
+        if (lane == owner) {
             float jx = -1.0f, jy = -1.0f, jc = -1.0f;
             if (best > P.thr && besti != 0x7fffffff) {
                 const int row = (int)fdiv((uint32_t)besti, P.divW);

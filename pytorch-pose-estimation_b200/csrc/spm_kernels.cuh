@@ -339,7 +339,10 @@ struct __align__(16) SpmFusedPerson {
     int px0, px1, py0, py1;     // Gaussian patch window clipped to the map and to the template, [x0,x1) x [y0,y1); empty: all 0
 };
 
-// Launch shape: 8 STREAM warps + 1 PATCH warp per CTA (288 threads), 3 CTAs per SM (register cap 72).
+// Launch shape: 8 STREAM warps + POSE_SPM_PATCH_WARPS PATCH warps per CTA, POSE_SPM_FUSED_MINB CTAs per SM.
+#ifndef POSE_SPM_PATCH_WARPS
+#define POSE_SPM_PATCH_WARPS 2
+#endif
 #ifndef POSE_SPM_FUSED_MINB
 #define POSE_SPM_FUSED_MINB 3
 #endif
@@ -348,7 +351,7 @@ struct __align__(16) SpmFusedPerson {
 #define POSE_SPM_FUSED_U 4              // loss + grad: read logits, write dlogits (16 KB units)
 #endif
 #ifndef POSE_SPM_FUSED_U_RO
-#define POSE_SPM_FUSED_U_RO 8           // read-only loss (32 KB units)
+#define POSE_SPM_FUSED_U_RO 4           // read-only loss (16 KB units)
 #endif
 #ifndef POSE_SPM_FUSED_U_RENDER
 #define POSE_SPM_FUSED_U_RENDER 8       // render only: write stream
@@ -359,14 +362,16 @@ __host__ __device__ constexpr int spm_fused_u(bool grad, bool wtgt, bool loss = 
 constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
 constexpr int kSpmStreamWarps = 8;
 constexpr int kSpmStreamThreads = kSpmStreamWarps * 32;
-constexpr int kSpmFusedThreads = kSpmStreamThreads + 32;      // + the patch warp
+constexpr int kSpmPatchWarps = POSE_SPM_PATCH_WARPS;
+constexpr int kSpmFusedThreads = kSpmStreamThreads + 32 * kSpmPatchWarps;
 constexpr int kSpmListCap = 2048;                             // covered quads of one image kept as a list (more: the bitmap is walked)
+constexpr int kSpmOvCap = 512;                                // pixels of one image that lie in SEVERAL persons' boxes, kept as a list (MAP)
 constexpr int kSpmMapMaxBytes = 16384;                        // per-image pixel map (one byte per pixel): R <= 128
 
 __host__ __device__ inline bool spm_fused_use_map(int R) { return R * R <= kSpmMapMaxBytes; }
 __host__ __device__ inline size_t spm_fused_smem_bytes(int div_n, int R, int K, int wpr, int lut_n) {
     return (size_t)div_n * 8 + (size_t)R * 8 + (size_t)kSpmFusedMaxPersons * K * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4 +
-           (size_t)kSpmListCap * 4 + (spm_fused_use_map(R) ? (size_t)R * R : 0);
+           (size_t)kSpmListCap * 4 + (spm_fused_use_map(R) ? (size_t)R * R + (size_t)kSpmOvCap * 12 : 0);
 }
 
 // target of one pixel: (root value t0 = max of the covering Gaussian patches, displacement te of plane (jn, axis))
@@ -409,10 +414,30 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
 // ROWG (R % 128 == 0): the 32 quads of a warp instruction are exactly one word of the covered-quad bitmap and every unit is full.
 // History (r01, per 256 images, loss + grad): covered pixels handled inside the streaming warps, pooled per warp and unit with
 // the logits re-read through L2 -- 220.9 us (81 % of the copy peak); a per-plane patch pass by the whole CTA: 225.6 us.
+// loss term and gradient of one pixel given its logit pe, its target (root: t0, displacement: te) and the root mask mk
+template <bool LOSS>
+__device__ __forceinline__ float spm_pixel_loss(const SpmFusedParams& P, bool disp, float pe, float t0, float te, bool mk, float& acc) {
+    if (!LOSS) return 0.0f;
+    if (!disp) {
+        const float sg = sigmoid_fast(pe);
+        const float d = (mk ? sg : sg * 0.0f) - t0;
+        acc = fmaf(d, d, acc);
+        return mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
+    }
+    // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
+    float th = 0.0f, pm = pe != pe ? pe : 0.0f;                   // NaN logits propagate as in the reference
+    if (mk) { th = tanhf(pe); pm = th; }
+    const float d = pm - te;
+    const float ad = fabsf(d);
+    acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+    return mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
+}
+
 template <bool LOSS, bool GRAD, bool WTGT, bool ROWG, bool MAP>
 __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
     // dynamic shared memory: [div_n] double quotients | [R] u64 row masks | [64*K] int2 joints | [R*wpr] u32 covered quads | template
-    //                        | [kSpmListCap] u32 covered-quad list | MAP: [R*R] u8 pixel map
+    //                        | [kSpmListCap] u32 covered-quad list | MAP: [kSpmOvCap] u64 overlap person masks | [kSpmOvCap] u32 overlap pixels
+    //                        | [R*R] u8 pixel map
     extern __shared__ __align__(16) unsigned char spm_fused_smem[];
     double* div_s = reinterpret_cast<double*>(spm_fused_smem);
     unsigned long long* rowmask_s = reinterpret_cast<unsigned long long*>(div_s + P.div_n);
@@ -420,12 +445,18 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
     unsigned int* covq_s = reinterpret_cast<unsigned int*>(s_j + kSpmFusedMaxPersons * P.K);
     float* lut_s = reinterpret_cast<float*>(covq_s + P.R * P.wpr);
     unsigned int* list_s = reinterpret_cast<unsigned int*>(lut_s + P.lut_n * P.lut_n);
-    unsigned char* map_s = reinterpret_cast<unsigned char*>(list_s + kSpmListCap);           // MAP only
+    // (the template has an odd number of floats for odd n: round up so the 64-bit masks are aligned)
+    unsigned long long* ovmask_s = reinterpret_cast<unsigned long long*>(
+        (reinterpret_cast<uintptr_t>(list_s + kSpmListCap) + 7) & ~uintptr_t(7));                // MAP only
+    unsigned int* ovpix_s = reinterpret_cast<unsigned int*>(ovmask_s + kSpmOvCap);               // MAP only
+    unsigned char* map_s = reinterpret_cast<unsigned char*>(ovpix_s + kSpmOvCap);                // MAP only
     __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
     __shared__ double red[kSpmFusedThreads / 32][2];
     __shared__ int s_nlist;                                            // covered quads of the staged image; -1: too many for the list
+    __shared__ int s_nov;                                              // MAP: pixels in several boxes; -1: too many for the list
     constexpr int U = spm_fused_u(GRAD, WTGT, LOSS);
     constexpr int kChunk = kSpmStreamThreads * U;                      // float4 per work unit
+    constexpr int NP = kSpmPatchWarps;
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
     for (int i = threadIdx.x; i < P.div_n; i += blockDim.x) div_s[i] = (double)(i - P.R) / P.z;
@@ -441,6 +472,7 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
     const long long total_quads = (long long)P.N * C * P.quads;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool streamer = wid < kSpmStreamWarps;                       // warp-uniform role
+    const int pw = wid - kSpmStreamWarps;                              // patch warps: 0 .. NP-1
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     double droot = 0.0, ddisp = 0.0;
 
@@ -520,8 +552,8 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                     }
                 }
             }
-            if (!streamer) {
-                // the patch warp lists the covered quads (plane-relative quad index, ascending) from the bitmap: 32 words per step,
+            if (!streamer && pw == 0) {
+                // patch warp 0 lists the covered quads (plane-relative quad index, ascending) from the bitmap: 32 words per step,
                 // a shuffle scan of their popcounts gives every lane its write position
                 const int nwords = P.R * P.wpr;
                 int base = 0;
@@ -548,6 +580,36 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                     base += tot;
                 }
                 if (lane == 0) s_nlist = fits ? base : -1;
+            }
+            __syncthreads();
+            if (MAP && !streamer && pw == 0) {
+                // ... and the pixels that lie in several boxes (map code 127), in row-major order, each with the bit mask of the
+                // persons whose box covers it: their displacement targets are sums over those persons, replayed in index order
+                int base = 0;
+                for (int row = 0; row < P.R; ++row) {
+                    const unsigned long long rm = rowmask_s[row];
+                    if (rm == 0ull) continue;                           // warp-uniform
+                    for (int c0 = 0; c0 < P.R; c0 += 32) {
+                        const int col = c0 + lane;
+                        const bool ov = col < P.R && (map_s[row * P.R + col] & 127u) == 127u;
+                        const unsigned b = __ballot_sync(FULL_MASK, ov);
+                        if (b == 0u) continue;
+                        const int pos = base + __popc(b & ((1u << lane) - 1u));
+                        if (ov && pos < kSpmOvCap) {
+                            unsigned long long m = rm, cover = 0ull;
+                            while (m) {
+                                const int p = __ffsll((long long)m) - 1;
+                                m &= m - 1;
+                                const SpmFusedPerson sp = s_p[p];
+                                if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) cover |= 1ull << p;
+                            }
+                            ovmask_s[pos] = cover;
+                            ovpix_s[pos] = (unsigned int)(row * P.R + col);
+                        }
+                        base += __popc(b);
+                    }
+                }
+                if (lane == 0) s_nov = base <= kSpmOvCap ? base : -1;
             }
             __syncthreads();
         }
@@ -601,10 +663,11 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                 if (++chunk == upp) { chunk = 0; ++plane; ++c; }
             }
         } else {
-            // ---------------- PATCH: the covered quads of every plane (or part of a plane) in [seg, seg_end), one quad per lane
+            // ---------------- PATCH: the covered quads of every plane (or part of a plane) in [seg, seg_end)
             const int nlist = s_nlist;
+            const int nov = MAP ? s_nov : -1;                          // >= 0: pixels in several boxes are handled by the second pass
             const long long p_first = seg / upp, p_last = (seg_end - 1) / upp;
-            // one covered quad: 4 pixels of row `row` starting at column col0, logits pe
+            // pass 1, one covered quad per lane: 4 pixels of one row, logits in one 128-bit load, results in one 128-bit store
             auto quad = [&](long long off, int q, bool disp, int jn, int axis, float& acc) {
                 const int row = (int)fdiv((uint32_t)q, P.div_qpr), col0 = (q - row * qpr) * 4;
                 float pe[4] = {0.f, 0.f, 0.f, 0.f};
@@ -620,7 +683,7 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                     const int col = col0 + e;
                     const unsigned int code = (codes >> (8 * e)) & 255u;
                     float t0 = 0.0f, te = 0.0f;
-                    bool mk;
+                    bool mk, skip = false;
                     if (MAP && disp && (code & 127u) != 127u) {
                         mk = code >> 7;
                         if (code & 127u) {
@@ -630,32 +693,16 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                                 te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
                             }
                         }
+                    } else if (MAP && disp && nov >= 0) {
+                        mk = false; skip = true;                          // in several boxes: the second pass computes and writes it
                     } else if (MAP && !disp && (code & 128u) == 0u) {
                         mk = false;                                       // root plane, pixel outside every Gaussian patch: t0 = 0
                     } else {
                         spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
                         mk = t0 > 0.0f;
                     }
-                    float g = 0.0f;
-                    if (!LOSS) {
-                        if (!disp) te = t0;
-                    } else if (!disp) {
-                        const float sg = sigmoid_fast(pe[e]);
-                        const float d = (mk ? sg : sg * 0.0f) - t0;
-                        acc = fmaf(d, d, acc);
-                        g = mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
-                        te = t0;
-                    } else {
-                        // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
-                        float th = 0.0f, pm = pe[e] != pe[e] ? pe[e] : 0.0f;   // NaN logits propagate as in the reference
-                        if (mk) { th = tanhf(pe[e]); pm = th; }
-                        const float d = pm - te;
-                        const float ad = fabsf(d);
-                        acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-                        g = mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
-                    }
-                    ge[e] = g;
-                    te4[e] = te;
+                    ge[e] = skip ? 0.0f : spm_pixel_loss<LOSS>(P, disp, pe[e], t0, te, mk, acc);
+                    te4[e] = disp ? te : t0;
                 }
                 if (GRAD) __stcs(G4 + off + q, make_float4(ge[0], ge[1], ge[2], ge[3]));
                 if (WTGT) __stcs(T4 + off + q, make_float4(te4[0], te4[1], te4[2], te4[3]));
@@ -673,19 +720,19 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                     if (LOSS && plane < p_last) {
                         // the next plane's covered logits travel to L2 while this plane is computed (no stream warp reads them)
                         const int nq_last = plane + 1 == p_last ? min(P.quads, (int)(seg_end - (plane + 1) * upp) * kChunk) : P.quads;
-                        for (int i = lane; i < nlist; i += 32) {
+                        for (int i = pw * 32 + lane; i < nlist; i += 32 * NP) {
                             const int q = (int)list_s[i];
                             if (q < nq_last) prefetch_l2(L4 + off + P.quads + q);
                         }
                     }
-                    for (int i = lane; i < nlist; i += 32) {
+                    for (int i = pw * 32 + lane; i < nlist; i += 32 * NP) {
                         const int q = (int)list_s[i];
                         if (q >= q_first && q < q_last) quad(off, q, disp, jn, axis, acc);
                     }
                 } else {
                     // more covered quads than the list holds (dozens of persons on a large map): walk the bitmap, one word per lane
                     const int nwords = P.R * P.wpr;
-                    for (int wi = lane; wi < nwords; wi += 32) {
+                    for (int wi = pw * 32 + lane; wi < nwords; wi += 32 * NP) {
                         unsigned int bits = covq_s[wi];
                         const int row = wi / P.wpr, q0 = row * qpr + (wi - row * P.wpr) * 32;
                         while (bits) {
@@ -694,6 +741,34 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                             const int q = q0 + b;
                             if (q >= q_first && q < q_last) quad(off, q, disp, jn, axis, acc);
                         }
+                    }
+                }
+                if (MAP && disp && nov > 0) {
+                    // pass 2, one pixel per lane: the pixels in several boxes.  Their quads were stored by pass 1 (possibly by another
+                    // patch warp): the barrier of the patch warps orders those stores before the 4-byte overwrites below.
+                    if (NP > 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * NP) : "memory"); else __syncwarp();
+                    for (int i = pw * 32 + lane; i < nov; i += 32 * NP) {
+                        const int pix = (int)ovpix_s[i];
+                        const int q = pix >> 2;
+                        if (q < q_first || q >= q_last) continue;
+                        const int row = pix / P.R, col = pix - row * P.R;
+                        unsigned long long m = ovmask_s[i];
+                        float te = 0.0f;
+                        while (m) {
+                            const int p = __ffsll((long long)m) - 1;
+                            m &= m - 1;
+                            const int2 jv = s_j[p * P.K + jn];
+                            if (!(jv.x <= 0 && jv.y <= 0)) {
+                                const int dd = axis ? jv.y - row : jv.x - col;
+                                const double qd = (P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z;
+                                te = (float)((double)te + qd);               // fp32(fp64(acc) + q): numpy's mixed-precision +=
+                            }
+                        }
+                        const bool mk = map_s[pix] >> 7;
+                        const long long ei = off * 4 + pix;
+                        const float g = spm_pixel_loss<LOSS>(P, true, LOSS ? __ldg(P.logits + ei) : 0.0f, 0.0f, te, mk, acc);
+                        if (GRAD) __stcs(P.dlogits + ei, g);
+                        if (WTGT) __stcs(P.target_out + ei, te);
                     }
                 }
                 if (c == 0) droot += (double)acc; else ddisp += (double)acc;
