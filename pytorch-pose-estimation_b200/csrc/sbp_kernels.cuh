@@ -20,7 +20,7 @@ namespace pose {
 // they need more loads in flight per SM to hide the same latency, so they get their own knobs.
 // (tools/tune_fused.py --which ng, B=4096, loss only: U6/M4 144.9 us, U8/M4 143.5, U4/M5 144.7, U6/M3 150.8, U12/M3 148.3.)
 #ifndef POSE_FUSED_U_NG
-#define POSE_FUSED_U_NG 6
+#define POSE_FUSED_U_NG 8
 #endif
 #ifndef POSE_FUSED_MINB_NG
 #define POSE_FUSED_MINB_NG 4    // register cap 64
@@ -425,49 +425,72 @@ sbp_fused_kernel(SbpFusedParams P) {
     double kx = -1.0, ky = -1.0;
     if (TGT == TGT_RENDER && warp0 < P.n_maps) load_kp(P.kp, P.kp_f64, warp0, kx, ky);
 
-    for (long long map = warp0; map < P.n_maps; map += nwarps) {
-        const float* lg = P.logits + map * P.HW;
-        const float* tg = (TGT == TGT_DENSE) ? P.target_in + map * P.HW : nullptr;
-        float* dl = GRAD ? P.dlogits + map * P.HW : nullptr;
-        float* to = WTGT ? P.target_out + map * P.HW : nullptr;
-        Patch pt;
+    // One stream of (map, batch of U vectors per lane) items per warp.  The loads of the NEXT item -- the next batch of this map
+    // or the first batch of the warp's next map -- are issued right after the current batch has been consumed and BEFORE the
+    // per-map tail (loss flush, argmax resolution with its shuffles, votes and the reference sigmoid), so that tail runs
+    // under memory latency instead of in front of it.  Same registers as the plain "load U, compute U" loop.
+    float xv[U][V], tv[U][V];
+    auto issue = [&](long long m, int b0) {
+        const float* lg = P.logits + m * P.HW;
+        const float* tg = (TGT == TGT_DENSE) ? P.target_in + m * P.HW : nullptr;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int vi = b0 + 32 * u;
+            if (vi < nvec) {
+                Vec<V>::load(lg, vi, xv[u]);
+                if (TGT == TGT_DENSE) Vec<V>::load(tg, vi, tv[u]);
+            }
+        }
+    };
+    long long map = warp0;
+    int base = lane;
+    Patch pt;
+    float apos = 0.0f, aneg = 0.0f, arem = 0.0f;
+    ArgTrack<V> arg;
+    arg.reset();
+    if (map < P.n_maps) {
+        issue(map, base);
         if (TGT == TGT_RENDER) {
             pt = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
             if (map + nwarps < P.n_maps) load_kp(P.kp, P.kp_f64, map + nwarps, kx, ky);
         }
-        float apos = 0.0f, aneg = 0.0f, arem = 0.0f;
-        ArgTrack<V> arg;
-        arg.reset();
-
-        for (int base = lane; base < nvec; base += 32 * U) {
-            float xv[U][V], tv[U][V];
+    }
+    while (map < P.n_maps) {
+        float* dl = GRAD ? P.dlogits + map * P.HW : nullptr;
+        float* to = WTGT ? P.target_out + map * P.HW : nullptr;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int vi = base + 32 * u;
-                if (vi < nvec) {
-                    Vec<V>::load(lg, vi, xv[u]);
-                    if (TGT == TGT_DENSE) Vec<V>::load(tg, vi, tv[u]);
-                }
+        for (int u = 0; u < U; ++u) {
+            const int vi = base + 32 * u;
+            if (vi >= nvec) break;
+            float g[V];
+            if (DEC) arg.template push<true>(xv[u], vi);
+            if (TGT == TGT_RENDER) {
+                render_loss_vec<V, GRAD, WTGT>(xv[u], g, tv[u], vi, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
+            } else {
+                float sg[V];
+                sigmoid_vec<V, !GRAD>(xv[u], sg);
+#pragma unroll
+                for (int j = 0; j < V; ++j) g[j] = loss_elem<GRAD>(sg[j], tv[u][j], P.gpos, P.gneg, apos, aneg);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int vi = base + 32 * u;
-                if (vi >= nvec) break;
-                float g[V];
-                if (DEC) arg.template push<true>(xv[u], vi);
-                if (TGT == TGT_RENDER) {
-                    render_loss_vec<V, GRAD, WTGT>(xv[u], g, tv[u], vi, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
-                } else {
-                    float sg[V];
-                    sigmoid_vec<V, !GRAD>(xv[u], sg);
-#pragma unroll
-                    for (int j = 0; j < V; ++j) g[j] = loss_elem<GRAD>(sg[j], tv[u][j], P.gpos, P.gneg, apos, aneg);
-                }
-                if (GRAD) Vec<V>::store(dl, vi, g);
-                if (WTGT) Vec<V>::store(to, vi, tv[u]);
+            if (GRAD) Vec<V>::store(dl, vi, g);
+            if (WTGT) Vec<V>::store(to, vi, tv[u]);
+        }
+        int nbase = base + 32 * U;
+        long long nmap = map;
+        const bool last = nbase >= nvec;
+        if (last) { nbase = lane; nmap = map + nwarps; }
+        if (nmap < P.n_maps) issue(nmap, nbase);
+        if (last) {
+            finish_map<V, DEC>(P, map, lane, apos, aneg, arem, arg, dpos, dneg);
+            apos = aneg = arem = 0.0f;
+            arg.reset();
+            if (TGT == TGT_RENDER && nmap < P.n_maps) {
+                pt = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
+                if (nmap + nwarps < P.n_maps) load_kp(P.kp, P.kp_f64, nmap + nwarps, kx, ky);
             }
         }
-        finish_map<V, DEC>(P, map, lane, apos, aneg, arem, arg, dpos, dneg);
+        map = nmap;
+        base = nbase;
     }
 
     dpos = warp_sum(dpos);
@@ -604,47 +627,61 @@ __global__ void __launch_bounds__(kSbpThreads) sbp_decode_kernel(SbpDecodeParams
     const int nvec = P.HW / V;
     constexpr int U = 8;
 
-    for (long long map = warp0; map < P.n_maps; map += nwarps) {
-        const float* src = P.x + map * P.HW;
-        ArgTrack<V> arg;
-        arg.reset();
-        for (int base = lane; base < nvec; base += 32 * U) {
-            float xv[U][V];
+    // (map, batch) items as one stream per warp; the next item's loads are issued before the per-map tail (see sbp_fused_kernel)
+    float xv[U][V];
+    auto issue = [&](long long m, int b0) {
+        const float* src = P.x + m * P.HW;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int vi = base + 32 * u;
-                if (vi < nvec) Vec<V>::load(src, vi, xv[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int vi = base + 32 * u;
-                if (vi >= nvec) break;
-                arg.template push<SIG>(xv[u], vi);
-            }
+        for (int u = 0; u < U; ++u) {
+            const int vi = b0 + 32 * u;
+            if (vi < nvec) Vec<V>::load(src, vi, xv[u]);
         }
-        float best = -INFINITY;
-        int besti = 0x7fffffff;
-        const int owner = resolve_argmax<V, SIG>(arg, src, nvec, lane, P.sig_ref, best, besti);
-
-        if (lane == owner) {
-            float jx = -1.0f, jy = -1.0f, jc = -1.0f;
-            if (best > P.thr && besti != 0x7fffffff) {
-                const int row = (int)fdiv((uint32_t)besti, P.divW);
-                const int col = besti - row * P.W;
-                jx = (float)col; jy = (float)row; jc = best;
-                if (P.refine && col > 1 && col < P.W - 1 && row > 1 && row < P.H - 1) {
-                    // quarter-pixel shift toward the higher neighbour (NOT in the reference; opt-in)
-                    const float dx = act<SIG>(__ldg(src + besti + 1)) - act<SIG>(__ldg(src + besti - 1));
-                    const float dy = act<SIG>(__ldg(src + besti + P.W)) - act<SIG>(__ldg(src + besti - P.W));
-                    jx += dx > 0.0f ? 0.25f : (dx < 0.0f ? -0.25f : 0.0f);
-                    jy += dy > 0.0f ? 0.25f : (dy < 0.0f ? -0.25f : 0.0f);
+    };
+    long long map = warp0;
+    int base = lane;
+    ArgTrack<V> arg;
+    arg.reset();
+    if (map < P.n_maps) issue(map, base);
+    while (map < P.n_maps) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int vi = base + 32 * u;
+            if (vi >= nvec) break;
+            arg.template push<SIG>(xv[u], vi);
+        }
+        int nbase = base + 32 * U;
+        long long nmap = map;
+        const bool last = nbase >= nvec;
+        if (last) { nbase = lane; nmap = map + nwarps; }
+        if (nmap < P.n_maps) issue(nmap, nbase);
+        if (last) {
+            const float* src = P.x + map * P.HW;
+            float best = -INFINITY;
+            int besti = 0x7fffffff;
+            const int owner = resolve_argmax<V, SIG>(arg, src, nvec, lane, P.sig_ref, best, besti);
+            if (lane == owner) {
+                float jx = -1.0f, jy = -1.0f, jc = -1.0f;
+                if (best > P.thr && besti != 0x7fffffff) {
+                    const int row = (int)fdiv((uint32_t)besti, P.divW);
+                    const int col = besti - row * P.W;
+                    jx = (float)col; jy = (float)row; jc = best;
+                    if (P.refine && col > 1 && col < P.W - 1 && row > 1 && row < P.H - 1) {
+                        // quarter-pixel shift toward the higher neighbour (NOT in the reference; opt-in)
+                        const float dx = act<SIG>(__ldg(src + besti + 1)) - act<SIG>(__ldg(src + besti - 1));
+                        const float dy = act<SIG>(__ldg(src + besti + P.W)) - act<SIG>(__ldg(src + besti - P.W));
+                        jx += dx > 0.0f ? 0.25f : (dx < 0.0f ? -0.25f : 0.0f);
+                        jy += dy > 0.0f ? 0.25f : (dy < 0.0f ? -0.25f : 0.0f);
+                    }
                 }
+                float* jo = P.joints + map * 3;
+                jo[0] = __fmul_rn(jx, P.scale);
+                jo[1] = __fmul_rn(jy, P.scale);
+                jo[2] = jc;
             }
-            float* jo = P.joints + map * 3;
-            jo[0] = __fmul_rn(jx, P.scale);
-            jo[1] = __fmul_rn(jy, P.scale);
-            jo[2] = jc;
+            arg.reset();
         }
+        map = nmap;
+        base = nbase;
     }
 }
 

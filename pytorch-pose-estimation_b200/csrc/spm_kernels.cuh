@@ -341,10 +341,10 @@ struct __align__(16) SpmFusedPerson {
 
 // Launch shape: 8 STREAM warps + POSE_SPM_PATCH_WARPS PATCH warps per CTA, POSE_SPM_FUSED_MINB CTAs per SM.
 #ifndef POSE_SPM_PATCH_WARPS
-#define POSE_SPM_PATCH_WARPS 2
+#define POSE_SPM_PATCH_WARPS 4
 #endif
 #ifndef POSE_SPM_FUSED_MINB
-#define POSE_SPM_FUSED_MINB 3
+#define POSE_SPM_FUSED_MINB 2
 #endif
 // float4 per stream thread and unit (the unit must divide a 128x128 plane: 1, 2, 4, 8 or 16), per variant
 #ifndef POSE_SPM_FUSED_U
@@ -365,13 +365,13 @@ constexpr int kSpmStreamThreads = kSpmStreamWarps * 32;
 constexpr int kSpmPatchWarps = POSE_SPM_PATCH_WARPS;
 constexpr int kSpmFusedThreads = kSpmStreamThreads + 32 * kSpmPatchWarps;
 constexpr int kSpmListCap = 2048;                             // covered quads of one image kept as a list (more: the bitmap is walked)
-constexpr int kSpmOvCap = 512;                                // pixels of one image that lie in SEVERAL persons' boxes, kept as a list (MAP)
+constexpr int kSpmOvSlots = 1024;                             // MAP: hash table (pixel -> mask of covering persons) of the pixels in SEVERAL boxes
 constexpr int kSpmMapMaxBytes = 16384;                        // per-image pixel map (one byte per pixel): R <= 128
 
 __host__ __device__ inline bool spm_fused_use_map(int R) { return R * R <= kSpmMapMaxBytes; }
 __host__ __device__ inline size_t spm_fused_smem_bytes(int div_n, int R, int K, int wpr, int lut_n) {
     return (size_t)div_n * 8 + (size_t)R * 8 + (size_t)kSpmFusedMaxPersons * K * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4 +
-           (size_t)kSpmListCap * 4 + (spm_fused_use_map(R) ? (size_t)R * R + (size_t)kSpmOvCap * 12 : 0);
+           (size_t)kSpmListCap * 4 + (spm_fused_use_map(R) ? (size_t)R * R + (size_t)kSpmOvSlots * 12 + 8 : 0);
 }
 
 // target of one pixel: (root value t0 = max of the covering Gaussian patches, displacement te of plane (jn, axis))
@@ -403,7 +403,7 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
 //   * 8 STREAM warps walk the CTA's contiguous range of 16/32 KB units linearly: one broadcast shared-memory word tells a warp
 //     which of its 32 float4 quads lie in some person's box or Gaussian patch ("covered"); the other quads are loaded (NaN
 //     check only), and zeros are stored to dlogits / the target.  No person data, no branches, no dependent chains.
-//   * 1 PATCH warp owns the covered quads (~3-6 % of a plane, the same set for all 1+2K planes of an image, listed once per
+//   * the PATCH warps own the covered quads (~3-6 % of a plane, the same set for all 1+2K planes of an image, listed once per
 //     image): one quad per lane -- 128-bit load of the logits (prefetched into L2 one plane ahead), the plane-independent
 //     geometry from a per-image byte map (MAP) or the generic person loop, template / quotient-table look-ups, tanhf only
 //     under the root mask -- and 128-bit stores of the 4 results.  Its long dependent chains (LDS -> LDG -> LDS -> SFU -> STG)
@@ -436,7 +436,7 @@ __device__ __forceinline__ float spm_pixel_loss(const SpmFusedParams& P, bool di
 template <bool LOSS, bool GRAD, bool WTGT, bool ROWG, bool MAP>
 __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
     // dynamic shared memory: [div_n] double quotients | [R] u64 row masks | [64*K] int2 joints | [R*wpr] u32 covered quads | template
-    //                        | [kSpmListCap] u32 covered-quad list | MAP: [kSpmOvCap] u64 overlap person masks | [kSpmOvCap] u32 overlap pixels
+    //                        | [kSpmListCap] u32 covered-quad list | MAP: [kSpmOvSlots] u64 person masks | [kSpmOvSlots] u32 keys (pixel + 1)
     //                        | [R*R] u8 pixel map
     extern __shared__ __align__(16) unsigned char spm_fused_smem[];
     double* div_s = reinterpret_cast<double*>(spm_fused_smem);
@@ -448,12 +448,12 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
     // (the template has an odd number of floats for odd n: round up so the 64-bit masks are aligned)
     unsigned long long* ovmask_s = reinterpret_cast<unsigned long long*>(
         (reinterpret_cast<uintptr_t>(list_s + kSpmListCap) + 7) & ~uintptr_t(7));                // MAP only
-    unsigned int* ovpix_s = reinterpret_cast<unsigned int*>(ovmask_s + kSpmOvCap);               // MAP only
-    unsigned char* map_s = reinterpret_cast<unsigned char*>(ovpix_s + kSpmOvCap);                // MAP only
+    unsigned int* ovkey_s = reinterpret_cast<unsigned int*>(ovmask_s + kSpmOvSlots);             // MAP only
+    unsigned char* map_s = reinterpret_cast<unsigned char*>(ovkey_s + kSpmOvSlots);              // MAP only
     __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
     __shared__ double red[kSpmFusedThreads / 32][2];
     __shared__ int s_nlist;                                            // covered quads of the staged image; -1: too many for the list
-    __shared__ int s_nov;                                              // MAP: pixels in several boxes; -1: too many for the list
+    __shared__ int s_ovfull;                                           // MAP: the overlap table overflowed: code 127 falls back to the person loop
     constexpr int U = spm_fused_u(GRAD, WTGT, LOSS);
     constexpr int kChunk = kSpmStreamThreads * U;                      // float4 per work unit
     constexpr int NP = kSpmPatchWarps;
@@ -504,6 +504,10 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
             }
             for (int i = threadIdx.x; i < P.R; i += blockDim.x) rowmask_s[i] = 0ull;
             for (int i = threadIdx.x; i < P.R * P.wpr; i += blockDim.x) covq_s[i] = 0u;
+            if (MAP) {
+                for (int i = threadIdx.x; i < kSpmOvSlots; i += blockDim.x) ovkey_s[i] = 0u;
+                if (threadIdx.x == 0) s_ovfull = 0;
+            }
             __syncthreads();
             // one thread per (person, row of the union of its box and patch): row mask bit + covered-quad bits
             const int span = 2 * P.half + 1 + P.lut_n;                 // upper bound on the rows of the union
@@ -534,7 +538,7 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                     const unsigned long long rm = rowmask_s[row];
                     if (rm == 0ull) continue;                           // warp-uniform
                     for (int col = lane; col < P.R; col += 32) {
-                        unsigned long long m = rm;
+                        unsigned long long m = rm, cover = 0ull;
                         unsigned int code = 0u, nbox = 0u;
                         bool mk = false;
                         while (m) {
@@ -545,9 +549,22 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                                 lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)] > 0.0f) mk = true;
                             if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
                                 if (nbox++ == 0u) code = (unsigned)p + 1u;
+                                cover |= 1ull << p;
                             }
                         }
-                        if (nbox > 1u) code = 127u;
+                        if (nbox > 1u) {
+                            // in several boxes: the displacement target is a sum over those persons (replayed in index order by the
+                            // patch warps) -- their bit mask goes into a small hash table keyed by the pixel (insertion order is
+                            // irrelevant: look-ups return the same mask whatever the order, so the result stays deterministic)
+                            code = 127u;
+                            const unsigned int key = (unsigned int)(row * P.R + col) + 1u;
+                            unsigned int h = (key * 2654435761u) >> 22;
+                            bool placed = false;
+                            for (int probe = 0; probe < 32 && !placed; ++probe, h = (h + 1u) & (kSpmOvSlots - 1)) {
+                                if (atomicCAS(&ovkey_s[h], 0u, key) == 0u) { ovmask_s[h] = cover; placed = true; }
+                            }
+                            if (!placed) s_ovfull = 1;
+                        }
                         map_s[row * P.R + col] = (unsigned char)(code | (mk ? 128u : 0u));
                     }
                 }
@@ -582,36 +599,6 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                 if (lane == 0) s_nlist = fits ? base : -1;
             }
             __syncthreads();
-            if (MAP && !streamer && pw == 0) {
-                // ... and the pixels that lie in several boxes (map code 127), in row-major order, each with the bit mask of the
-                // persons whose box covers it: their displacement targets are sums over those persons, replayed in index order
-                int base = 0;
-                for (int row = 0; row < P.R; ++row) {
-                    const unsigned long long rm = rowmask_s[row];
-                    if (rm == 0ull) continue;                           // warp-uniform
-                    for (int c0 = 0; c0 < P.R; c0 += 32) {
-                        const int col = c0 + lane;
-                        const bool ov = col < P.R && (map_s[row * P.R + col] & 127u) == 127u;
-                        const unsigned b = __ballot_sync(FULL_MASK, ov);
-                        if (b == 0u) continue;
-                        const int pos = base + __popc(b & ((1u << lane) - 1u));
-                        if (ov && pos < kSpmOvCap) {
-                            unsigned long long m = rm, cover = 0ull;
-                            while (m) {
-                                const int p = __ffsll((long long)m) - 1;
-                                m &= m - 1;
-                                const SpmFusedPerson sp = s_p[p];
-                                if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) cover |= 1ull << p;
-                            }
-                            ovmask_s[pos] = cover;
-                            ovpix_s[pos] = (unsigned int)(row * P.R + col);
-                        }
-                        base += __popc(b);
-                    }
-                }
-                if (lane == 0) s_nov = base <= kSpmOvCap ? base : -1;
-            }
-            __syncthreads();
         }
 
         if (streamer) {
@@ -624,21 +611,24 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                 const long long off = plane * P.quads;
                 const int q_lo = chunk * kChunk;
                 float4 pv[U];
-                bool live[U];                                          // valid and not covered: this thread's quad of instruction u
+                unsigned live = 0u;                                    // bit u: this thread's quad of instruction u is valid and not covered
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int q = q_lo + u * kSpmStreamThreads + tid;
+                    bool lv;
                     if (ROWG) {
                         // quads is a multiple of the chunk and a warp instruction is one word of the bitmap: one broadcast LDS
-                        live[u] = !((covq_s[(q_lo >> 5) + u * kSpmStreamWarps + wid] >> lane) & 1u);
+                        lv = !((covq_s[(q_lo >> 5) + u * kSpmStreamWarps + wid] >> lane) & 1u);
                     } else {
-                        live[u] = false;
+                        lv = false;
                         if (q < P.quads) {
                             const int row = (int)fdiv((uint32_t)q, P.div_qpr), cq = q - row * qpr;
-                            live[u] = !((covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u);
+                            lv = !((covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u);
                         }
                     }
-                    if (LOSS && live[u]) pv[u] = ldg_stream(L4 + off + q);
+                    pv[u] = z4;
+                    if (LOSS && lv) pv[u] = ldg_stream(L4 + off + q);
+                    live |= (lv ? 1u : 0u) << u;
                 }
                 if (LOSS && unit + 1 < seg_end) {
                     // the next unit of this CTA is the next 16/32 KB in memory (planes are contiguous): pull it into L2 meanwhile
@@ -649,7 +639,7 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                 float acc = 0.f;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (!live[u]) continue;
+                    if (!((live >> u) & 1u)) continue;
                     const int q = q_lo + u * kSpmStreamThreads + tid;
                     if (LOSS) {
                         const float4 v = pv[u];
@@ -665,9 +655,8 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
         } else {
             // ---------------- PATCH: the covered quads of every plane (or part of a plane) in [seg, seg_end)
             const int nlist = s_nlist;
-            const int nov = MAP ? s_nov : -1;                          // >= 0: pixels in several boxes are handled by the second pass
+            const bool ov_table = MAP && s_ovfull == 0;                 // pixels in several boxes: person masks come from the hash table
             const long long p_first = seg / upp, p_last = (seg_end - 1) / upp;
-            // pass 1, one covered quad per lane: 4 pixels of one row, logits in one 128-bit load, results in one 128-bit store
             auto quad = [&](long long off, int q, bool disp, int jn, int axis, float& acc) {
                 const int row = (int)fdiv((uint32_t)q, P.div_qpr), col0 = (q - row * qpr) * 4;
                 float pe[4] = {0.f, 0.f, 0.f, 0.f};
@@ -683,7 +672,7 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                     const int col = col0 + e;
                     const unsigned int code = (codes >> (8 * e)) & 255u;
                     float t0 = 0.0f, te = 0.0f;
-                    bool mk, skip = false;
+                    bool mk;
                     if (MAP && disp && (code & 127u) != 127u) {
                         mk = code >> 7;
                         if (code & 127u) {
@@ -693,15 +682,30 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                                 te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
                             }
                         }
-                    } else if (MAP && disp && nov >= 0) {
-                        mk = false; skip = true;                          // in several boxes: the second pass computes and writes it
+                    } else if (MAP && disp && ov_table) {
+                        // in several boxes: sum over the covering persons in index order, fp32(fp64(acc) + q) each (numpy's +=)
+                        mk = code >> 7;
+                        const unsigned int key = (unsigned int)(row * P.R + col) + 1u;
+                        unsigned int h = (key * 2654435761u) >> 22;
+                        while (ovkey_s[h] != key) h = (h + 1u) & (kSpmOvSlots - 1);
+                        unsigned long long m = ovmask_s[h];
+                        while (m) {
+                            const int p = __ffsll((long long)m) - 1;
+                            m &= m - 1;
+                            const int2 jv = s_j[p * P.K + jn];
+                            if (!(jv.x <= 0 && jv.y <= 0)) {
+                                const int dd = axis ? jv.y - row : jv.x - col;
+                                const double qd = (P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z;
+                                te = (float)((double)te + qd);
+                            }
+                        }
                     } else if (MAP && !disp && (code & 128u) == 0u) {
                         mk = false;                                       // root plane, pixel outside every Gaussian patch: t0 = 0
                     } else {
                         spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
                         mk = t0 > 0.0f;
                     }
-                    ge[e] = skip ? 0.0f : spm_pixel_loss<LOSS>(P, disp, pe[e], t0, te, mk, acc);
+                    ge[e] = spm_pixel_loss<LOSS>(P, disp, pe[e], t0, te, mk, acc);
                     te4[e] = disp ? te : t0;
                 }
                 if (GRAD) __stcs(G4 + off + q, make_float4(ge[0], ge[1], ge[2], ge[3]));
@@ -741,34 +745,6 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                             const int q = q0 + b;
                             if (q >= q_first && q < q_last) quad(off, q, disp, jn, axis, acc);
                         }
-                    }
-                }
-                if (MAP && disp && nov > 0) {
-                    // pass 2, one pixel per lane: the pixels in several boxes.  Their quads were stored by pass 1 (possibly by another
-                    // patch warp): the barrier of the patch warps orders those stores before the 4-byte overwrites below.
-                    if (NP > 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * NP) : "memory"); else __syncwarp();
-                    for (int i = pw * 32 + lane; i < nov; i += 32 * NP) {
-                        const int pix = (int)ovpix_s[i];
-                        const int q = pix >> 2;
-                        if (q < q_first || q >= q_last) continue;
-                        const int row = pix / P.R, col = pix - row * P.R;
-                        unsigned long long m = ovmask_s[i];
-                        float te = 0.0f;
-                        while (m) {
-                            const int p = __ffsll((long long)m) - 1;
-                            m &= m - 1;
-                            const int2 jv = s_j[p * P.K + jn];
-                            if (!(jv.x <= 0 && jv.y <= 0)) {
-                                const int dd = axis ? jv.y - row : jv.x - col;
-                                const double qd = (P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z;
-                                te = (float)((double)te + qd);               // fp32(fp64(acc) + q): numpy's mixed-precision +=
-                            }
-                        }
-                        const bool mk = map_s[pix] >> 7;
-                        const long long ei = off * 4 + pix;
-                        const float g = spm_pixel_loss<LOSS>(P, true, LOSS ? __ldg(P.logits + ei) : 0.0f, 0.0f, te, mk, acc);
-                        if (GRAD) __stcs(P.dlogits + ei, g);
-                        if (WTGT) __stcs(P.target_out + ei, te);
                     }
                 }
                 if (c == 0) droot += (double)acc; else ddisp += (double)acc;

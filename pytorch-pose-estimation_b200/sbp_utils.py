@@ -200,10 +200,17 @@ def _ids(v):
     return v.tolist() if isinstance(v, torch.Tensor) else [int(i) for i in v]
 
 
-def packed_to_results(packed, image_ids, category_ids, pad=0):
-    """One D2H copy, then plain-Python COCO result dicts (utils/sbp_utils.py:148-164)."""
+def packed_to_results(packed, image_ids, category_ids, pad=0, arrays=None):
+    """One D2H copy, then plain-Python COCO result dicts (utils/sbp_utils.py:148-164).  `arrays` (a list) additionally receives
+    (kp [B,3K] f64 as emitted, score [B] f64, image ids, category ids): what `result()` hands to the evaluator instead of
+    walking the dicts again."""
     host = packed.cpu()
     kps, sc = host[:, :-1], host[:, -1]
+    if arrays is not None:
+        k3 = kps.double().numpy().copy()
+        k3[:, 2::3] = (k3[:, 2::3] != 0)
+        arrays.append((np.concatenate([k3, np.zeros((k3.shape[0], pad))], axis=1) if pad else k3, sc.double().numpy().copy(),
+                       [int(i) for i in _ids(image_ids)], [int(c) for c in _ids(category_ids)]))
     out = []
     tail = [0] * pad
     for i, (iid, cid) in enumerate(zip(_ids(image_ids), _ids(category_ids))):
@@ -230,10 +237,12 @@ class SBPmAPCOCO:
         self.result_list = []
         self.gather = gather
         self._evaluator = None
+        self._arrays = []               # the arrays result_list was made from (used by result() while the two agree in length)
         self.stats = None
 
     def reset_states(self):
         self.result_list = []
+        self._arrays = []
 
     def update_state(self, target, y_pred):
         joints = self.decoder.decode_batch(y_pred)                       # [B,K,3] at input scale
@@ -246,7 +255,7 @@ class SBPmAPCOCO:
             rows, score, iid, cid = pd.gather_rows_ragged(packed[:, :3 * k].unflatten(1, (k, 3)), packed[:, 3 * k],
                                                           torch.as_tensor(iid).to(dev), torch.as_tensor(cid).to(dev))
             packed = torch.cat([rows.flatten(1), score[:, None]], dim=1)
-        self.result_list.extend(packed_to_results(packed, iid, cid, self._pad))
+        self.result_list.extend(packed_to_results(packed, iid, cid, self._pad, arrays=self._arrays))
 
     def result(self):
         """AP at OKS 0.50 (`cocoEval.stats[1]`, utils/sbp_utils.py:189).  Writes ./results.json like the reference, then runs
@@ -261,7 +270,13 @@ class SBPmAPCOCO:
             raise ValueError("result() needs the ground-truth annotations: pass json_path (or a parsed COCO dict)")
         if self._evaluator is None:
             self._evaluator = KeypointEval(self.coco)
-        out = self._evaluator.evaluate(self.result_list)
+        if self._arrays and sum(len(a[1]) for a in self._arrays) == len(self.result_list):
+            # nobody edited result_list: evaluate the arrays it was built from (skips ~85 ms of dict walking per 35 k rows)
+            kp = np.concatenate([a[0] for a in self._arrays])
+            out = self._evaluator.evaluate_arrays(kp, np.concatenate([a[1] for a in self._arrays]),
+                                                  sum((a[2] for a in self._arrays), []), sum((a[3] for a in self._arrays), []))
+        else:
+            out = self._evaluator.evaluate(self.result_list)
         self.stats = summarize(out['precision'], out['recall'], verbose=True)
         return self.stats[1]
 

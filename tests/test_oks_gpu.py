@@ -164,6 +164,13 @@ def test_metric_class_result_end_to_end(pb, tmp_path, monkeypatch):
     assert json.loads((tmp_path / "results.json").read_text()) == m.result_list
     want = oo.evaluate(gts, m.result_list)['stats']
     assert np.allclose(m.stats, want, rtol=1e-12, atol=0)
+    # result() evaluated the arrays result_list was built from (no dict walk); the dict path gives the same bits, and an edited
+    # result_list switches to it
+    assert m._arrays and np.array_equal(m.stats, m._evaluator.evaluate(m.result_list)['stats'])
+    fast = m.stats.copy()
+    m.result_list.pop()
+    m.result()
+    assert not np.array_equal(m.stats, fast)
     m.reset_states()
     with pytest.raises(IndexError):
         m.result()

@@ -20,20 +20,18 @@ OUT = os.path.join(ROOT, "build", "tune")
 SRC = os.path.join(ROOT, "pytorch-pose-estimation_b200", "csrc", "api.cu")
 NVCC = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
-# name -> (-D knobs, kernels worth timing for it).  Shipped: U=6/MINB=3 (grad), U_NG=6/MINB_NG=4, U_NGD=8/MINB_NGD=3, SIGMOID_SHARE=4.
+# name -> (-D knobs, kernels worth timing for it).  Shipped: U=6/MINB=3 (grad), U_NG=8/MINB_NG=4, U_NGD=8/MINB_NGD=3, SIGMOID_SHARE=4.
 GD, G, L, LD = "grad+decode", "grad", "loss", "loss+decode"
 VARIANTS = {
     "share1": (["-DPOSE_SIGMOID_SHARE=1"], (L, LD)),                                            # one reciprocal per element (r01)
     "ngd_u6_m3": (["-DPOSE_FUSED_U_NGD=6"], (LD,)),
     "ngd_u4_m4": (["-DPOSE_FUSED_U_NGD=4", "-DPOSE_FUSED_MINB_NGD=4"], (LD,)),
-    "ngd_u6_m4": (["-DPOSE_FUSED_U_NGD=6", "-DPOSE_FUSED_MINB_NGD=4"], (LD,)),
-    "ngd_u12_m2": (["-DPOSE_FUSED_U_NGD=12", "-DPOSE_FUSED_MINB_NGD=2"], (LD,)),
-    "ng_u8_m4": (["-DPOSE_FUSED_U_NG=8"], (L,)),
-    "ng_u4_m5": (["-DPOSE_FUSED_U_NG=4", "-DPOSE_FUSED_MINB_NG=5"], (L,)),
-    "ng_u12_m3": (["-DPOSE_FUSED_U_NG=12", "-DPOSE_FUSED_MINB_NG=3"], (L,)),
+    "ngd_u4_m3": (["-DPOSE_FUSED_U_NGD=4"], (LD,)),
+    "ng_u6_m4": (["-DPOSE_FUSED_U_NG=6"], (L,)),
+    "ng_u4_m4": (["-DPOSE_FUSED_U_NG=4"], (L,)),
+    "ng_u8_m3": (["-DPOSE_FUSED_MINB_NG=3"], (L,)),
+    "g_u4_m3": (["-DPOSE_FUSED_U=4"], (GD, G)),
     "g_u8_m3": (["-DPOSE_FUSED_U=8"], (GD, G)),
-    "g_u4_m4": (["-DPOSE_FUSED_U=4", "-DPOSE_FUSED_MINB=4"], (GD, G)),
-    "g_u6_m4": (["-DPOSE_FUSED_MINB=4"], (GD, G)),
 }
 FLAGS = {GD: 1 | 4, G: 1, L: 0, LD: 4}
 

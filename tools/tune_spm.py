@@ -17,16 +17,15 @@ OUT = os.path.join(ROOT, "build", "tune")
 SRC = os.path.join(ROOT, "pytorch-pose-estimation_b200", "csrc", "api.cu")
 NVCC = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
-# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: 8 stream + 2 patch warps per CTA, MINB=3, U=4 (grad), U_RO=4, U_RENDER=8.
+# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: 8 stream + 4 patch warps per CTA, MINB=2, U=4 (grad), U_RO=4, U_RENDER=8.
 VARIANTS = {
-    "np1": ["-DPOSE_SPM_PATCH_WARPS=1"],
-    "np4": ["-DPOSE_SPM_PATCH_WARPS=4"],
-    "np4_m2": ["-DPOSE_SPM_PATCH_WARPS=4", "-DPOSE_SPM_FUSED_MINB=2"],
-    "np4_m2_u8": ["-DPOSE_SPM_PATCH_WARPS=4", "-DPOSE_SPM_FUSED_MINB=2", "-DPOSE_SPM_FUSED_U=8", "-DPOSE_SPM_FUSED_U_RO=8"],
-    "np2_m4": ["-DPOSE_SPM_FUSED_MINB=4"],
-    "np2_u2": ["-DPOSE_SPM_FUSED_U=2", "-DPOSE_SPM_FUSED_U_RO=2", "-DPOSE_SPM_FUSED_U_RENDER=4"],
-    "np2_u8": ["-DPOSE_SPM_FUSED_U=8", "-DPOSE_SPM_FUSED_U_RO=8", "-DPOSE_SPM_FUSED_U_RENDER=16"],
-    "np8_m2": ["-DPOSE_SPM_PATCH_WARPS=8", "-DPOSE_SPM_FUSED_MINB=2"],
+    "np2_m3": ["-DPOSE_SPM_PATCH_WARPS=2", "-DPOSE_SPM_FUSED_MINB=3"],
+    "np4_m3": ["-DPOSE_SPM_FUSED_MINB=3"],
+    "np8_m2": ["-DPOSE_SPM_PATCH_WARPS=8"],
+    "np2_m2": ["-DPOSE_SPM_PATCH_WARPS=2"],
+    "np4_m2_u8": ["-DPOSE_SPM_FUSED_U=8", "-DPOSE_SPM_FUSED_U_RO=8", "-DPOSE_SPM_FUSED_U_RENDER=16"],
+    "np4_m2_u2": ["-DPOSE_SPM_FUSED_U=2", "-DPOSE_SPM_FUSED_U_RO=2", "-DPOSE_SPM_FUSED_U_RENDER=4"],
+    "np1_m4": ["-DPOSE_SPM_PATCH_WARPS=1", "-DPOSE_SPM_FUSED_MINB=4"],
 }
 
 
