@@ -37,7 +37,7 @@ extern "C" {
 #define POSE_F_GRAD 1u          /* write dlogits                                   */
 #define POSE_F_TARGET_OUT 2u    /* also materialise the rendered target (render mode only) */
 #define POSE_F_DECODE 4u        /* also decode joints from sigmoid(logits) in the same pass */
-#define POSE_F_TMA 8u           /* stage the maps through shared memory with bulk async copies (render mode, 16-byte aligned) */
+#define POSE_F_TMA 8u           /* stage the maps through shared memory with bulk async copies (render mode, 16-byte aligned maps): the fast path */
 #define POSE_F_SIGMOID_CUDA 16u /* POSE_F_DECODE: rank with POSE_SIGMOID_ATEN_CUDA instead of POSE_SIGMOID_ATEN_CPU */
 
 /* Which torch.sigmoid the decoders reproduce BIT FOR BIT when they rank near-equal logits and report the confidence.
@@ -65,6 +65,10 @@ unsigned long long pose_b200_launch_count(void);
  * Writes n*n fp32 values (n = number of samples of arange(0, 6*sigma+3)) row-major to out_host,
  * computed in double and rounded once to fp32.  Returns n, or POSE_EINVAL if capacity < n*n. */
 int pose_gauss_template_host(double sigma, float* out_host, int capacity);
+/* The same template in the layout pose_sbp_fused reads: n+1 rows of n+8 floats -- 4 zeros, the n values, 4 zeros -- and
+ * an all-zero last row (a thread then fetches the targets of 4 consecutive pixels with two clamped indices, no range
+ * branches).  Returns n, or POSE_EINVAL if capacity < (n+1)*(n+8). */
+int pose_gauss_template_padded_host(double sigma, float* out_host, int capacity);
 
 /* ---- SBP render -- SBPHeatmapGenerator.__call__ utils/sbp_utils.py:33-53, batched.
  * kp [N][K][2] (x, y) in heat-map pixels, fp32 or fp64 (kp_dtype); x<0 or y<0 = invisible.
@@ -77,7 +81,8 @@ int pose_sbp_render(const void* kp, int kp_dtype, float* target, int N, int K, i
  *      SBPHeatmapGenerator.__call__ utils/sbp_utils.py:33-53 when kp != NULL,
  *      DecodeSBP.forward/nms_sbp utils/sbp_utils.py:56-118 when POSE_F_DECODE.
  * Exactly one of `target_in` (dense target, [N][K][H][W]) or `kp` (keypoints, rendered in
- * registers) must be non-NULL.
+ * registers) must be non-NULL.  With kp, `lut` is the device copy of the PADDED template
+ * (pose_gauss_template_padded_host: (lut_n+1) x (lut_n+8) floats).
  *   loss      = (lambda_pos * S_pos + lambda_neg * S_neg) * inv_norm,    inv_norm = 1/(2*K*B_global)
  *   dlogits   = dloss/dlogits (scaled by inv_norm; written iff POSE_F_GRAD)
  *   loss_out  [1] fp32; loss_num_out [2] fp64 = (S_pos, S_neg) un-normalised (may be NULL)
@@ -85,10 +90,11 @@ int pose_sbp_render(const void* kp, int kp_dtype, float* target, int N, int K, i
  *   bbox [N][4] fp64 + packed_out [N][3K+1] (both or neither; needs POSE_F_DECODE): the epilogue launch also
  *             back-projects the joints exactly like pose_sbp_backproject (SBPmAPCOCO.update_state :141-163)
  *   exchange (may be NULL; needs bbox): multi-GPU -- see pose_exchange_t below; packed_out may then be NULL
- * Two launches: the fused streaming kernel, then one epilogue grid (fixed-order loss reduction + back-projection)
- * issued with programmatic dependent launch.
- * workspace: pose_sbp_fused_workspace_bytes(); contents need no initialisation. */
-unsigned long long pose_sbp_fused_workspace_bytes(void);
+ * Two launches: the fused streaming kernel (one CTA per heat map), then one epilogue grid (fixed-order two-level loss
+ * reduction + back-projection) issued with programmatic dependent launch.
+ * workspace: pose_sbp_fused_workspace_bytes(N, K) -- one fp64 (S_pos, S_neg) pair per heat map + the reduction's slice
+ * sums and counter; contents need no initialisation. */
+unsigned long long pose_sbp_fused_workspace_bytes(int N, int K);
 int pose_sbp_fused(const float* logits, const float* target_in,
                    const void* kp, int kp_dtype, double sigma, const float* lut, int lut_n,
                    float* dlogits, float* target_out,
@@ -147,7 +153,11 @@ int pose_scale_grad(float* dlogits, const float* grad_output, unsigned long long
  * x [N][K][H][W]; joints [N][K][3].  apply_sigmoid = DecodeSBP.pred.  Both coordinates are
  * multiplied by coord_scale (= input_w / W, :116), undetected rows are (-1,-1,-1)*scale on x,y.
  * sigmoid_ref (apply_sigmoid only): POSE_SIGMOID_ATEN_CPU / _CUDA -- argmax indices and confidences are bit-identical to
- * the reference evaluated with that torch.sigmoid.  refine != 0 adds the quarter-pixel shift (NOT in the reference; off by default). */
+ * the reference evaluated with that torch.sigmoid.  refine: bit 0 (POSE_DEC_REFINE) adds the quarter-pixel shift (NOT in the
+ * reference; off by default); bit 1 (POSE_DEC_NO_TMA) selects the register-staged kernel instead of the bulk-async (TMA)
+ * staged one, which is used whenever the maps are 16-byte aligned (same results bit for bit; a GPU test compares them). */
+#define POSE_DEC_REFINE 1
+#define POSE_DEC_NO_TMA 2
 int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W,
                     float conf_threshold, int apply_sigmoid, float coord_scale,
                     int refine, int sigmoid_ref, pose_stream_t stream);

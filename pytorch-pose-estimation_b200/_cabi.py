@@ -18,6 +18,9 @@ SIGMOID_ATEN_CPU, SIGMOID_ATEN_CUDA = 0, 1
 # "cpu": the reference on CPU tensors (what the golden vectors hold) -- the default, it is what the parity tests pin;
 # "cuda": the reference on CUDA tensors (what the Lightning modules ran).  POSE_B200_SIGMOID_REF overrides the default.
 DEFAULT_SIGMOID_REF = os.environ.get("POSE_B200_SIGMOID_REF", "cpu")
+# stage heat maps through shared memory with the TMA engine (cp.async.bulk + mbarrier) instead of per-thread LDG: the fast path
+# (maps in flight live in shared memory, not in registers); POSE_B200_TMA=0 selects the register-staged kernels
+DEFAULT_TMA = os.environ.get("POSE_B200_TMA", "1") == "1"
 
 
 def sigmoid_ref_code(name=None):
@@ -38,8 +41,9 @@ SIGNATURES = {
     "pose_b200_last_error": (_c.c_char_p, []),
     "pose_b200_launch_count": (_ull, []),
     "pose_gauss_template_host": (_i, [_d, _vp, _i]),
+    "pose_gauss_template_padded_host": (_i, [_d, _vp, _i]),
     "pose_sbp_render": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp]),
-    "pose_sbp_fused_workspace_bytes": (_ull, []),
+    "pose_sbp_fused_workspace_bytes": (_ull, [_i, _i]),
     "pose_sbp_fused": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f,
                             _i, _i, _i, _i, _f, _f, _d, _u, _vp, _vp, _i, _i, _vp, _vp, _ull, _vp]),
     "pose_exchange_layout": (_ull, [_vp]),

@@ -8,6 +8,9 @@
 
 namespace pose {
 
+constexpr int kTemplatePad = 4;                // zero columns either side of the padded Gaussian template (sbp_kernels.cuh)
+constexpr int kMaxPartialBlocks = 148 * 16;    // upper bound on a persistent grid (sizes the loss-partials workspaces)
+
 // ---------------------------------------------------------------- memory: 128-bit streaming accesses
 // Every byte of logits / target / dlogits is touched exactly once per pass, so loads bypass L1
 // allocation and stores are streaming: nothing here is worth keeping in L1.
@@ -78,12 +81,10 @@ __device__ __forceinline__ void sigmoid_fast4(const float (&x)[4], float (&s)[4]
     const float a = r * p23, b = r * p01;
     s[0] = a * d[1]; s[1] = a * d[0]; s[2] = b * d[3]; s[3] = b * d[2];
 }
-#ifndef POSE_SIGMOID_SHARE
-#define POSE_SIGMOID_SHARE 4            // read-only loss kernels: 4 = one reciprocal per 128-bit vector, 1 = one per element
-#endif
+// SHARE: one reciprocal per 128-bit vector (which kernels ask for it: POSE_FUSED_SHARE_* in sbp_kernels.cuh)
 template <int V, bool SHARE>
 __device__ __forceinline__ void sigmoid_vec(const float (&x)[V], float (&s)[V]) {
-    if constexpr (V == 4 && SHARE && POSE_SIGMOID_SHARE == 4) {
+    if constexpr (V == 4 && SHARE) {
         sigmoid_fast4(x, s);
     } else {
 #pragma unroll
@@ -142,8 +143,11 @@ __device__ __forceinline__ float sigmoid_ref(float x, int ref) { return ref == k
 // w = 2.7 d + 2^-21 / q (times a 1.125 safety factor; q from the fast sigmoid, relative error ~1e-6).  Where that exceeds 1/2
 // (m > 13.8: the sigmoid is within a few ulp of 1) the window is everything above 13: sigma(13.8) - sigma(13) is 21 ulp.
 __device__ __forceinline__ float sigmoid_window_lo(float m) {
-    const float q = sigmoid_fast(-m);                       // 1 - sigma(m); 1 for m -> -inf, 0 for m -> +inf
-    const float w = 1.125f * (2.7f * 4.76837158e-7f + __fdividef(4.76837158e-7f, q));
+    // 1/q = 1 + e^m exactly, so w = 1.125 d (2.7 + 1 + e^m): one MUFU.EX2 and an FMA (no reciprocal, no division -- this sits
+    // on the dependent chain at the end of every map)
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(m * 1.4426950408889634f));
+    const float w = 1.125f * 4.76837158e-7f * (3.7f + e);
     return (w < 0.5f) ? __fsub_rd(m, w) : 13.0f;
 }
 

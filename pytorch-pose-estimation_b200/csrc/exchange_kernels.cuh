@@ -71,10 +71,12 @@ __global__ void __launch_bounds__(256) sbp_epilogue_p2p_kernel(SbpEpilogueParams
     const int par = (int)(step % kExchangeSlots);
     const int stride = 3 * P.K + 1;
 
-    if (blockIdx.x == gridDim.x - 1) {
-        // loss partials -> local loss / numerators, then the numerators to every rank's slot [rank]
+    if ((int)blockIdx.x >= P.bp_ctas) {
+        // loss partials -> local loss / numerators (two-level, fixed order: only the slice CTA that finishes last goes on),
+        // then the numerators to every rank's slot [rank]
+        if (!reduce_slice_and_elect(P.partials, P.n_pairs, P.slices, P.ticket, P.R, (int)blockIdx.x - P.bp_ctas)) return;
         __shared__ double nums[2];
-        reduce_pairs_cta(P.partials, P.nblocks, 2, P.w0, P.w1, P.inv_norm, P.loss_out, nums);
+        reduce_pairs_cta(P.slices, P.R, 2, P.w0, P.w1, P.inv_norm, P.loss_out, nums);
         __syncthreads();
         if (P.num_out && threadIdx.x == 0) { P.num_out[0] = nums[0]; P.num_out[1] = nums[1]; }
         if (threadIdx.x == 0) {

@@ -1,42 +1,31 @@
 // Simple-Baselines hot path kernels: render, fused render+loss+grad(+decode), decode, back-projection.
 //
-// Work unit = one heat map (H*W fp32, 12 288 B at 64x48).  One warp owns one map at a time and a
-// persistent grid (SM count x resident CTAs) strides over all N*K maps, so every global access is
-// a fully coalesced 128-bit load/store of 512 contiguous bytes per warp instruction, the per-map
-// reductions (argmax, loss partials) are warp shuffles only, and no __syncthreads() appears in
-// the streaming loop.  All stages are HBM-bound; nothing here is a contraction (no tensor cores).
+// Work unit = one heat map (H*W fp32, 12 288 B at 64x48) = ONE CTA, and the grid covers all N*K maps (not persistent): every
+// thread issues all of its 128-bit loads the moment the CTA starts (3 per thread at 64x48: the whole map is in flight at
+// once), the per-map reductions (loss partials, argmax) go through shared memory with one or two barriers, the CTA retires
+// and the hardware scheduler hands the SM the next map in memory order.  Measured on B200 (tools/stream_patterns.cu,
+// profiles/r02_stream_patterns.log) for a 1 read : 1 write stream with this kernel's arithmetic:
+//   persistent grid, one warp per map, 6 loads per lane (the r01 layout)      282-288 us   5.95-6.06 TB/s  (0.91-0.93 of copy peak)
+//   non-persistent, one warp per map (8 maps per CTA)                          261 us       6.55 TB/s
+//   non-persistent, one CTA per map + block reduction (this file)              249 us       6.87 TB/s  (1.05 of copy peak)
+// read-only 119 us (7.2 TB/s), write-only 115 us (7.4 TB/s).  Resident CTAs (6-8 per SM) supply the memory-level parallelism
+// that the persistent form had to build from registers (U loads per lane) and lost in every load -> compute -> store phase.
+// All stages are HBM-bound; nothing here is a contraction (no tensor cores).
 #pragma once
 #include "common.cuh"
 
 namespace pose {
 
-#ifndef POSE_FUSED_U
-#define POSE_FUSED_U 6          // independent 128-bit loads in flight per lane in the fused kernel (tuned: tools/tune_fused.py)
-#endif
-#ifndef POSE_FUSED_MINB
-#define POSE_FUSED_MINB 3       // resident CTAs per SM the fused kernel is compiled for (register cap 80)
-#endif
-// The read-only render variants (validation: loss and/or decode from keypoints, no dlogits) have no store stream to carry half of the traffic:
-// they need more loads in flight per SM to hide the same latency, so they get their own knobs.
-// (tools/tune_fused.py --which ng, B=4096, loss only: U6/M4 144.9 us, U8/M4 143.5, U4/M5 144.7, U6/M3 150.8, U12/M3 148.3.)
-#ifndef POSE_FUSED_U_NG
-#define POSE_FUSED_U_NG 8
-#endif
-#ifndef POSE_FUSED_MINB_NG
-#define POSE_FUSED_MINB_NG 4    // register cap 64
-#endif
-// ... and the read-only variant that also decodes (running argmax: more registers per element) its own again
-// (tools/tune_fused.py --which ngd: U8/M3 158.3 us, U4/M4 158.5, U6/M3 163.8, U6/M4 169.8, U8/M2 182.7.  Tracking the maximum per
-//  128-bit vector and resolving the element once per map with a 16-byte re-read was measured too: 2 % slower in every shape.)
-#ifndef POSE_FUSED_U_NGD
-#define POSE_FUSED_U_NGD 8
-#endif
-#ifndef POSE_FUSED_MINB_NGD
-#define POSE_FUSED_MINB_NGD 3   // register cap 80
-#endif
 constexpr int kSbpThreads = 256;               // 8 warps per CTA
 constexpr int kSbpWarps = kSbpThreads / 32;
-constexpr int kMaxPartialBlocks = 148 * 16;    // upper bound on the persistent grid (workspace sizing)
+constexpr int kMapU = 3;                       // 128-bit vectors per thread and round: 256 x 3 x 16 B = one 64x48 map per round
+// resident CTAs per SM the map kernels are compiled for (register caps 40 / 48 / 64 at 6 / 5 / 4)
+#ifndef POSE_MAP_MINB_GRAD
+#define POSE_MAP_MINB_GRAD 5
+#endif
+#ifndef POSE_MAP_MINB_RO
+#define POSE_MAP_MINB_RO 6
+#endif
 
 // ---------------------------------------------------------------- vector helpers
 template <int V> struct Vec;
@@ -50,6 +39,11 @@ template <> struct Vec<4> {
         float4 v = ldg_cached(reinterpret_cast<const float4*>(base) + vi);
         o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
     }
+    // generic address (the map may sit in shared memory: the bulk-staged kernels)
+    static __device__ __forceinline__ void load_any(const float* base, int vi, float (&o)[4]) {
+        float4 v = reinterpret_cast<const float4*>(base)[vi];
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
     static __device__ __forceinline__ void store(float* base, int vi, const float (&o)[4]) {
         __stcs(reinterpret_cast<float4*>(base) + vi, make_float4(o[0], o[1], o[2], o[3]));
     }
@@ -58,6 +52,7 @@ template <> struct Vec<1> {
     using T = float;
     static __device__ __forceinline__ void load(const float* base, int vi, float (&o)[1]) { o[0] = ldg_stream(base + vi); }
     static __device__ __forceinline__ void load_cached(const float* base, int vi, float (&o)[1]) { o[0] = ldg_cached(base + vi); }
+    static __device__ __forceinline__ void load_any(const float* base, int vi, float (&o)[1]) { o[0] = base[vi]; }
     static __device__ __forceinline__ void store(float* base, int vi, const float (&o)[1]) { __stcs(base + vi, o[0]); }
 };
 
@@ -73,18 +68,12 @@ struct Patch {
     int nrows;               // py1 - uly (0 when empty): template rows [0, nrows) minus the ones above the map are rendered
 };
 
-// Shared-memory template of the fused kernels: n+1 rows of n+8 floats -- 4 zeros, the n template values, 4 zeros -- the last row all
-// zeros, so a lane fetches the targets of 4 consecutive pixels of one row with two clamped indices instead of 4 x (row test,
-// column test) behind divergent branches.
-constexpr int kLutPad = 4;
+// Template of the fused kernels: n+1 rows of n+8 floats -- 4 zeros, the n template values, 4 zeros -- the last row all zeros, so a
+// thread fetches the targets of 4 consecutive pixels of one row with two clamped indices instead of 4 x (row test, column
+// test) behind divergent branches.  The caller passes it in this layout (pose_gauss_template_padded_host; 1.5 KB at sigma 2)
+// and the kernels read it through L1 (__ldg): with one CTA per map there is no per-CTA staging pass to amortise.
+constexpr int kLutPad = kTemplatePad;
 __host__ __device__ inline size_t lut_padded_floats(int n) { return (size_t)(n + 1) * (size_t)(n + 2 * kLutPad); }
-__device__ __forceinline__ void stage_lut_padded(float* __restrict__ lut_s, const float* __restrict__ lut, int n) {
-    const int pw = n + 2 * kLutPad;
-    for (int i = threadIdx.x; i < (n + 1) * pw; i += blockDim.x) {
-        const int r = i / pw, c = i - r * pw - kLutPad;
-        lut_s[i] = (r < n && c >= 0 && c < n) ? lut[r * n + c] : 0.0f;
-    }
-}
 
 __device__ __forceinline__ Patch make_patch(double x, double y, int H, int W, double three_sigma, int lut_n) {
     Patch p;
@@ -143,100 +132,95 @@ __device__ __forceinline__ bool patch_values(const Patch& p, const float* __rest
 // ---------------------------------------------------------------- argmax of sigmoid(x): search in logit space, rank with the reference's sigmoid
 // nms_sbp (utils/sbp_utils.py:71-80) takes the first row-major index of the largest sigmoid VALUE, and fp32 sigmoid is
 // many-to-one, so which neighbours tie depends on the sigmoid implementation to the last bit (common.cuh).  The streaming
-// loop therefore never evaluates a sigmoid for the decode: each lane tracks, per 128-bit vector, the largest logit of its
-// share of the map (value, vector index, the vector's 4 values) and the second-largest vector maximum; at the end of the map
-// the warp derives the candidate window [lo, m] from the map maximum m (sigmoid_window_lo: nothing below lo can reach
-// sigmoid_ref(m)), and ranks the candidates -- almost always exactly one element -- with the reference's own sigmoid
-// (sigmoid_ref, bit-exact, also the reported confidence).  Only when some lane holds two candidate vectors (it kept one) or
-// the map is degenerate does the warp look at the map a second time (L2 hit).  2 FMNMX3/FMNMX + 1 FSETP + 6 predicated
-// moves per vector, no MUFU.
+// part therefore never evaluates a sigmoid for the decode: each thread tracks, per 128-bit vector, the largest logit of its
+// share of the map (value, vector index) and the second-largest vector maximum.  Each WARP then derives a candidate window
+// [lo, m_w] from its own maximum m_w (sigmoid_window_lo: nothing below lo can reach sigmoid_ref(m_w) -- true for any subset
+// of the map), ranks its candidates -- almost always exactly one element, re-read from L2 -- with the reference's own sigmoid
+// (sigmoid_ref, bit-exact, also the reported confidence) and offers its winner to the CTA through ONE 64-bit shared-memory
+// atomicMax on (ordered value, ~index): larger value first, then the smaller flat index.  The maximum over the warps'
+// winners is the map's argmax, so the CTA needs no second barrier and no block-wide maximum.
 template <int V>
 struct ArgTrack {
-    float best, second;     // largest / second-largest vector maximum seen by this lane (NaNs ignored)
+    float best, second;     // largest / second-largest vector maximum seen by this thread (NaNs ignored)
     int bestvi;             // vector index of `best` (first occurrence)
-    float keep[V];          // the elements of that vector
-    __device__ __forceinline__ void reset() {
-        best = second = -INFINITY; bestvi = 0;
-#pragma unroll
-        for (int j = 0; j < V; ++j) keep[j] = -INFINITY;
-    }
+    __device__ __forceinline__ void reset() { best = second = -INFINITY; bestvi = 0; }
     template <bool SIG>
     __device__ __forceinline__ void push(const float (&x)[V], int vi) {
         float vm = x[0];
 #pragma unroll
         for (int j = 1; j < V; ++j) vm = fmaxf(vm, x[j]);
         if (SIG) second = fmaxf(second, fminf(vm, best));
-        if (vm > best) {
-            best = vm; bestvi = vi;
-#pragma unroll
-            for (int j = 0; j < V; ++j) keep[j] = x[j];
-        }
+        if (vm > best) { best = vm; bestvi = vi; }
     }
 };
 
-// -> (conf, idx) in the lane(s) named by the return value: the reference's activation value at its argmax and the flat index
-// (0x7fffffff: nothing comparable in the map).  Returns the lane that holds the result when exactly one lane holds exactly one
-// candidate (the overwhelmingly common case: no shuffle reduction, the winner evaluates the reference sigmoid once on its own),
-// else 0 after a warp reduction (every lane then holds the result).
-// SIG == false (heat maps that are already activated, DecodeSBP.pred == False): candidates are the elements equal to m.
+// (float_key(value) << 32) | (0xffffffff - flat index); 0 = no candidate.  (+ 0.0f: -0 and +0 are equal to the reference's
+// comparison, so they must share one key.)
+__device__ __forceinline__ unsigned long long arg_key(float f, int i) {
+    return ((unsigned long long)float_key(f + 0.0f) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+}
+
+// Warp-level resolution; every lane of the warp calls it.  `vi0`/`vstride`: the warp's lanes own vectors vi0 + lane + k*vstride.
+// Offers the warp's winner (if any) to *key.  SIG == false (heat maps that are already activated, DecodeSBP.pred == False):
+// candidates are the elements equal to the warp maximum.
 template <int V, bool SIG>
-__device__ __forceinline__ int resolve_argmax(const ArgTrack<V>& a, const float* __restrict__ src, int nvec, int lane, int sig_ref,
-                                              float& conf, int& idx) {
+__device__ __forceinline__ void warp_offer_argmax(const ArgTrack<V>& a, const float* __restrict__ src, int nvec, int first_vi, int vstride,
+                                                  int sig_ref, unsigned long long* key) {
     const float m = warp_max(a.best);
     float lo = m;
     bool again = false;
     if (SIG) {
         lo = sigmoid_window_lo(m);
         // m <= -80 (or no finite element at all): the references' results are denormal / zero there and the error model of
-        // the window does not hold -- rank every element
+        // the window does not hold -- rank every element of the warp's share
         const bool degenerate = !(m > -80.0f);
         if (degenerate) lo = -INFINITY;
         again = degenerate || __any_sync(FULL_MASK, a.second >= lo);
     }
-    float fb = -INFINITY;
-    int fi = 0x7fffffff;
+    unsigned long long k = 0ull;
     if (!again) {
-        // candidates of this lane: elements of its best vector inside the window
-        int ncand = 0, jc = 0;
-        float xc = 0.0f;
+        // candidates of this lane: elements of its best vector inside the window (one 16-byte re-read, L2)
         if (a.best >= lo) {
-#pragma unroll
-            for (int j = V - 1; j >= 0; --j)
-                if (a.keep[j] >= lo) { ++ncand; jc = j; xc = a.keep[j]; }   // (jc, xc): the first of them
-        }
-        const unsigned holders = __ballot_sync(FULL_MASK, ncand > 0);
-        const bool single = __popc(holders) == 1 && !__any_sync(FULL_MASK, ncand > 1);
-        if (single) {                                                     // warp-uniform
-            const int owner = __ffs(holders) - 1;
-            if (lane == owner) {
-                conf = SIG ? sigmoid_ref(xc, sig_ref) : xc;
-                idx = a.bestvi * V + jc;
-            }
-            return owner;
-        }
-        if (ncand > 0) {
+            float x[V];
+            Vec<V>::load_any(src, a.bestvi, x);
 #pragma unroll
             for (int j = 0; j < V; ++j)
-                if (a.keep[j] >= lo) {
-                    const float f = SIG ? sigmoid_ref(a.keep[j], sig_ref) : a.keep[j];
-                    if (f > fb) { fb = f; fi = a.bestvi * V + j; }
-                }
+                if (x[j] >= lo) k = max(k, arg_key(SIG ? sigmoid_ref(x[j], sig_ref) : x[j], a.bestvi * V + j));
         }
     } else {
-        for (int vi = lane; vi < nvec; vi += 32) {
+        for (int vi = first_vi; vi < nvec; vi += vstride) {
             float x[V];
-            Vec<V>::load_cached(src, vi, x);
+            Vec<V>::load_any(src, vi, x);
 #pragma unroll
             for (int j = 0; j < V; ++j)
-                if (x[j] >= lo) {
-                    const float f = sigmoid_ref(x[j], sig_ref);
-                    if (f > fb) { fb = f; fi = vi * V + j; }
-                }
+                if (x[j] >= lo) k = max(k, arg_key(SIG ? sigmoid_ref(x[j], sig_ref) : x[j], vi * V + j));
         }
     }
-    warp_argmax_first(fb, fi);
-    conf = fb; idx = fi;
-    return 0;
+    if (k != 0ull) atomicMax(key, k);
+}
+
+__device__ __forceinline__ void key_to_argmax(unsigned long long key, float& conf, int& idx) {
+    conf = -INFINITY;
+    idx = 0x7fffffff;
+    if (key != 0ull) {
+        conf = key_float((uint32_t)(key >> 32));
+        idx = (int)(0xffffffffu - (uint32_t)key);
+    }
+}
+
+// joint row of one map from its (confidence, flat index): nms_sbp + the coordinate scale of DecodeSBP.forward (:116)
+__device__ __forceinline__ void write_joint(float* __restrict__ jo, float conf, int idx, float thr, float scale, int W, FastDiv divW,
+                                            float dx = 0.0f, float dy = 0.0f) {
+    float jx = -1.0f, jy = -1.0f, jc = -1.0f;
+    if (conf > thr && idx != 0x7fffffff) {
+        const int row = (int)fdiv((uint32_t)idx, divW);
+        jx = (float)(idx - row * W) + dx;
+        jy = (float)row + dy;
+        jc = conf;
+    }
+    jo[0] = __fmul_rn(jx, scale);
+    jo[1] = __fmul_rn(jy, scale);
+    jo[2] = jc;
 }
 
 // ---------------------------------------------------------------- render only
@@ -248,26 +232,27 @@ struct SbpRenderParams {
     long long n_maps; int H, W, HW; FastDiv divW;
 };
 
+// one CTA per map: thread 0 derives the patch geometry while the template is staged; then a pure write stream
 template <int V>
 __global__ void __launch_bounds__(kSbpThreads) sbp_render_kernel(SbpRenderParams P) {
     extern __shared__ float lut_s[];
-    for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * kSbpWarps + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * kSbpWarps;
-    const int nvec = P.HW / V;
-    for (long long map = warp0; map < P.n_maps; map += nwarps) {
+    __shared__ Patch s_patch;
+    const long long map = blockIdx.x;
+    if (threadIdx.x == 0) {
         double x, y;
         load_kp(P.kp, P.kp_f64, map, x, y);
-        const Patch pt = make_patch(x, y, P.H, P.W, P.three_sigma, P.lut_n);
-        float* out = P.target + map * P.HW;
-#pragma unroll 4
-        for (int vi = lane; vi < nvec; vi += 32) {
-            float t[V];
-            patch_values<V>(pt, lut_s, P.lut_n, vi * V, P.W, P.divW, t);
-            Vec<V>::store(out, vi, t);
-        }
+        s_patch = make_patch(x, y, P.H, P.W, P.three_sigma, P.lut_n);
+    }
+    for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
+    __syncthreads();
+    const Patch pt = s_patch;
+    const int nvec = P.HW / V;
+    float* out = P.target + map * P.HW;
+#pragma unroll 3
+    for (int vi = threadIdx.x; vi < nvec; vi += kSbpThreads) {
+        float t[V];
+        patch_values<V>(pt, lut_s, P.lut_n, vi * V, P.W, P.divW, t);
+        Vec<V>::store(out, vi, t);
     }
 }
 
@@ -280,12 +265,13 @@ struct SbpFusedParams {
     float* dlogits;              // GRAD
     float* target_out;           // WTGT
     float* joints;               // DEC
-    double* partials;            // [gridDim.x][2]  (S_pos, S_neg)
+    double* partials;            // [n_maps][2]  (S_pos, S_neg) of every map
+    unsigned int* ticket;        // the epilogue's two-level reduction counts its slice CTAs here; zeroed by CTA 0 of this grid
     float thr, scale;
     float gpos, gneg;            // 2*lambda*inv_norm
     long long n_maps; int H, W, HW; FastDiv divW;
     int sig_ref;                 // DEC: which torch sigmoid ranks near-ties and gives the confidence (kSigmoidAtenCpu / kSigmoidAtenCuda)
-    ExchangePub xpub;            // multi-GPU in-band exchange: block 0 publishes the previous step's flag (world == 0: off)
+    ExchangePub xpub;            // multi-GPU in-band exchange: CTA 0 publishes the previous step's flag (world == 0: off)
 };
 
 constexpr int TGT_DENSE = 1;
@@ -310,12 +296,12 @@ __device__ __forceinline__ float loss_elem(float s, float t, float gpos, float g
 // then one unsigned compare decides whether the vector can touch the rows of the joint's Gaussian patch; only those
 // lanes compute (row, col), look the template up and replace their elements' results (`arem` collects the s^2 terms
 // that have to be taken out of S_neg again, so the common path stays a single FFMA per element).
-template <int V, bool GRAD, bool WTGT>
+template <int V, bool GRAD, bool WTGT, bool SHARE>
 __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[V], float (&tout)[V], int vi, const Patch& pt,
-                                                const float* __restrict__ lut_s, int lut_n, int W, FastDiv divW, float gpos, float gneg,
+                                                const float* __restrict__ lut, int lut_n, int W, FastDiv divW, float gpos, float gneg,
                                                 float& apos, float& aneg, float& arem) {
     float sg[V];
-    sigmoid_vec<V, !GRAD>(x, sg);           // read-only variants: SFU-bound, one reciprocal per vector
+    sigmoid_vec<V, SHARE>(x, sg);           // read-only variants: SFU-bound, one reciprocal per vector
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const float sj = sg[j];
@@ -342,7 +328,7 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 if (r2 >= pt.py0 && r2 < pt.py1 && c2 >= pt.px0 && c2 < pt.px1) {
-                    const float t = lut_s[(r2 - pt.uly) * pw + (c2 - pt.ulx) + kLutPad];
+                    const float t = __ldg(lut + (r2 - pt.uly) * pw + (c2 - pt.ulx) + kLutPad);
                     if (WTGT) tout[j] = t;
                     if (t > 0.0f) {      // t == 0 (underflowed template tail): the zero-target result stands
                         const float d = sg[j] - t;
@@ -359,11 +345,11 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
             // 104 -> 55 instructions on this path, 125 M -> 100 M warp instructions per launch; 158.5 -> 145.5 us (loss only).
             const int ri = ((unsigned)(r - pt.uly) < (unsigned)pt.nrows) ? r - pt.uly : lut_n;
             const int ci = min(max(cc - pt.ulx, -kLutPad), lut_n);
-            const float* lp = lut_s + ri * pw + ci + kLutPad;
+            const float* lp = lut + ri * pw + ci + kLutPad;
             const int lim = pt.px1 - cc;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                const float t = lp[j];
+                const float t = __ldg(lp + j);
                 const bool pos = (j < lim) && t > 0.0f;   // t == 0 (pad, or underflowed template tail): the zero-target result stands
                 if (WTGT) tout[j] = (j < lim) ? t : 0.0f;
                 const float d = sg[j] - t;
@@ -374,145 +360,228 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
     }
 }
 
-// end of one map: flush the fp32 partials into fp64 (keeps the 2e8-term sum accurate and deterministic) and, when decoding,
-// resolve the argmax and write the joint row
-template <int V, bool DEC>
-__device__ __forceinline__ void finish_map(const SbpFusedParams& P, long long map, int lane, float apos, float aneg, float arem,
-                                           const ArgTrack<V>& arg, double& dpos, double& dneg) {
-    dpos += (double)apos;
-    dneg += (double)aneg - (double)arem;
-    if (DEC) {
-        float conf = -INFINITY;
-        int idx = 0x7fffffff;
-        const int owner = resolve_argmax<V, true>(arg, P.logits + map * P.HW, P.HW / V, lane, P.sig_ref, conf, idx);
-        if (lane == owner) {
-            float jx = -1.0f, jy = -1.0f, jc = -1.0f;
-            if (conf > P.thr && idx != 0x7fffffff) {
-                const int row = (int)fdiv((uint32_t)idx, P.divW);
-                jx = (float)(idx - row * P.W);
-                jy = (float)row;
-                jc = conf;
-            }
-            float* jo = P.joints + map * 3;
-            jo[0] = __fmul_rn(jx, P.scale);
-            jo[1] = __fmul_rn(jy, P.scale);
-            jo[2] = jc;
-        }
-    }
-}
-
+// One CTA per heat map.  Order inside the CTA: (1) every thread issues the 128-bit loads of its share of the map -- nothing
+// else has been waited for yet, so the whole map is in flight within the CTA's first instructions; (2) thread 0 turns the
+// keypoint into the patch geometry (shared memory, one barrier -- under the latency of (1)); (3) the arithmetic and the
+// stores; (4) fp32 partial sums of the map -> warp shuffles -> shared memory, and each warp's argmax winner -> one shared
+// atomicMax; ONE barrier; thread 0 adds the 8 warps in fixed order, in fp64, writes the map's (S_pos, S_neg) pair -- no float
+// atomics anywhere: the loss is run-to-run deterministic -- and the joint row.
 template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
-__global__ void __launch_bounds__(kSbpThreads, (GRAD || WTGT || TGT != 2) ? POSE_FUSED_MINB : DEC ? POSE_FUSED_MINB_NGD : POSE_FUSED_MINB_NG)
-sbp_fused_kernel(SbpFusedParams P) {
-    extern __shared__ float lut_s[];
-    __shared__ double red[kSbpWarps][2];
+__global__ void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE_MAP_MINB_RO) sbp_fused_kernel(SbpFusedParams P) {
+    __shared__ Patch s_patch;
+    __shared__ float s_sum[kSbpWarps][3];
+    __shared__ unsigned long long s_key;
     pdl_launch_dependents();      // the epilogue grid may be scheduled as our CTAs retire; it waits for our completion itself
-    if (P.xpub.world > 0 && blockIdx.x == 0 && threadIdx.x == 0) exchange_open_step(P.xpub);
-    if (TGT == TGT_RENDER) {
-        stage_lut_padded(lut_s, P.lut, P.lut_n);
-        __syncthreads();
-    }
-    const int lane = threadIdx.x & 31;
-    const int wid = threadIdx.x >> 5;
-    const long long warp0 = (long long)blockIdx.x * kSbpWarps + wid;
-    const long long nwarps = (long long)gridDim.x * kSbpWarps;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long map = blockIdx.x;
     const int nvec = P.HW / V;
-    constexpr int U = (V == 4) ? ((GRAD || WTGT || TGT != TGT_RENDER) ? POSE_FUSED_U : DEC ? POSE_FUSED_U_NGD : POSE_FUSED_U_NG) : 8;
-    double dpos = 0.0, dneg = 0.0;
+    constexpr int U = kMapU;
+    // read-only variants: SFU-bound once the stream is this fast -- one reciprocal per 128-bit vector (common.cuh: sigmoid_fast4)
+    constexpr bool SHARE = !GRAD;
+    const float* lg = P.logits + map * P.HW;
+    const float* tg = (TGT == TGT_DENSE) ? P.target_in + map * P.HW : nullptr;
 
-    // the keypoint of the NEXT map is fetched while the current map streams, so its latency is off the per-map
-    // dependency chain (kp -> patch geometry -> first batch of loads)
-    double kx = -1.0, ky = -1.0;
-    if (TGT == TGT_RENDER && warp0 < P.n_maps) load_kp(P.kp, P.kp_f64, warp0, kx, ky);
-
-    // One stream of (map, batch of U vectors per lane) items per warp.  The loads of the NEXT item -- the next batch of this map
-    // or the first batch of the warp's next map -- are issued right after the current batch has been consumed and BEFORE the
-    // per-map tail (loss flush, argmax resolution with its shuffles, votes and the reference sigmoid), so that tail runs
-    // under memory latency instead of in front of it.  Same registers as the plain "load U, compute U" loop.
     float xv[U][V], tv[U][V];
-    auto issue = [&](long long m, int b0) {
-        const float* lg = P.logits + m * P.HW;
-        const float* tg = (TGT == TGT_DENSE) ? P.target_in + m * P.HW : nullptr;
+    auto issue = [&](int b0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int vi = b0 + 32 * u;
+            const int vi = b0 + tid + kSbpThreads * u;
             if (vi < nvec) {
                 Vec<V>::load(lg, vi, xv[u]);
                 if (TGT == TGT_DENSE) Vec<V>::load(tg, vi, tv[u]);
             }
         }
     };
-    long long map = warp0;
-    int base = lane;
-    Patch pt;
+    issue(0);
+    if (tid == 0) {
+        if (map == 0) {
+            if (P.xpub.world > 0) exchange_open_step(P.xpub);
+            *P.ticket = 0u;
+        }
+        if (TGT == TGT_RENDER) {
+            double kx, ky;
+            load_kp(P.kp, P.kp_f64, map, kx, ky);
+            s_patch = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
+        }
+        if (DEC) s_key = 0ull;
+    }
+    if (TGT == TGT_RENDER || DEC) __syncthreads();
+
     float apos = 0.0f, aneg = 0.0f, arem = 0.0f;
     ArgTrack<V> arg;
     arg.reset();
-    if (map < P.n_maps) {
-        issue(map, base);
-        if (TGT == TGT_RENDER) {
-            pt = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
-            if (map + nwarps < P.n_maps) load_kp(P.kp, P.kp_f64, map + nwarps, kx, ky);
-        }
-    }
-    while (map < P.n_maps) {
+    for (int b0 = 0; b0 < nvec; b0 += kSbpThreads * U) {
+        if (b0 > 0) issue(b0);                                  // maps larger than one round (96x72: three)
         float* dl = GRAD ? P.dlogits + map * P.HW : nullptr;
         float* to = WTGT ? P.target_out + map * P.HW : nullptr;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int vi = base + 32 * u;
+            const int vi = b0 + tid + kSbpThreads * u;
             if (vi >= nvec) break;
             float g[V];
             if (DEC) arg.template push<true>(xv[u], vi);
             if (TGT == TGT_RENDER) {
-                render_loss_vec<V, GRAD, WTGT>(xv[u], g, tv[u], vi, pt, lut_s, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
+                render_loss_vec<V, GRAD, WTGT, SHARE>(xv[u], g, tv[u], vi, s_patch, P.lut, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
             } else {
                 float sg[V];
-                sigmoid_vec<V, !GRAD>(xv[u], sg);
+                sigmoid_vec<V, SHARE>(xv[u], sg);
 #pragma unroll
                 for (int j = 0; j < V; ++j) g[j] = loss_elem<GRAD>(sg[j], tv[u][j], P.gpos, P.gneg, apos, aneg);
             }
             if (GRAD) Vec<V>::store(dl, vi, g);
             if (WTGT) Vec<V>::store(to, vi, tv[u]);
         }
-        int nbase = base + 32 * U;
-        long long nmap = map;
-        const bool last = nbase >= nvec;
-        if (last) { nbase = lane; nmap = map + nwarps; }
-        if (nmap < P.n_maps) issue(nmap, nbase);
-        if (last) {
-            finish_map<V, DEC>(P, map, lane, apos, aneg, arem, arg, dpos, dneg);
-            apos = aneg = arem = 0.0f;
-            arg.reset();
-            if (TGT == TGT_RENDER && nmap < P.n_maps) {
-                pt = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
-                if (nmap + nwarps < P.n_maps) load_kp(P.kp, P.kp_f64, nmap + nwarps, kx, ky);
-            }
-        }
-        map = nmap;
-        base = nbase;
     }
 
-    dpos = warp_sum(dpos);
-    dneg = warp_sum(dneg);
-    if (lane == 0) { red[wid][0] = dpos; red[wid][1] = dneg; }
+    apos = warp_sum(apos);
+    aneg = warp_sum(aneg);
+    arem = warp_sum(arem);
+    if (lane == 0) { s_sum[wid][0] = apos; s_sum[wid][1] = aneg; s_sum[wid][2] = arem; }
+    if (DEC) warp_offer_argmax<V, true>(arg, lg, nvec, tid, kSbpThreads, P.sig_ref, &s_key);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
+    if (tid == 0) {
+        double a = 0.0, b = 0.0, r = 0.0;
 #pragma unroll
-        for (int w = 0; w < kSbpWarps; ++w) { a += red[w][0]; b += red[w][1]; }
-        P.partials[2 * blockIdx.x] = a;
-        P.partials[2 * blockIdx.x + 1] = b;
+        for (int w = 0; w < kSbpWarps; ++w) { a += (double)s_sum[w][0]; b += (double)s_sum[w][1]; r += (double)s_sum[w][2]; }
+        reinterpret_cast<double2*>(P.partials)[map] = make_double2(a, b - r);
+        if (DEC) {
+            float conf;
+            int idx;
+            key_to_argmax(s_key, conf, idx);
+            write_joint(P.joints + map * 3, conf, idx, P.thr, P.scale, P.W, P.divW);
+        }
     }
 }
 
-// Deterministic second stage of the loss: sum `n` (a, b) fp64 pairs, `stride` doubles apart, in a fixed order (no float
-// atomics), then loss = (w0*A + w1*B) * inv_norm.  Runs in one CTA.
+// ---------------------------------------------------------------- bulk-async (TMA engine) staged forms: render mode, 16-byte aligned maps
+// What bounds the register-staged kernels above is bytes in flight and instructions per map: at ~2 us loaded DRAM latency a
+// B200 SM needs ~90 KB of reads outstanding to draw its share of 6.9 TB/s, i.e. 8 maps, and a CTA that holds its map in 12
+// registers per thread gets 5-6 CTAs per SM at the 40-48 registers the arithmetic needs; and with 256 threads on one map
+// every thread's prologue and tail (index arithmetic, three warp reductions, the argmax offer) is paid for just 3 vectors:
+// 292 instructions per thread and map, twice the r01 kernel's count per map -- ncu: issue slots 78-83 % busy, DRAM 57 %.
+// Here the maps in flight live in SHARED MEMORY: one thread issues a cp.async.bulk (UBLKCP, completion on an mbarrier) for
+// each of the CTA's POSE_TMA_MPC consecutive maps the moment the CTA starts; POSE_TMA_WPM warps then work on each map (all
+// maps of the CTA concurrently), one 128-bit vector per thread at a time out of shared memory, so the per-thread overhead is
+// spread over 12-24 vectors and the number of maps in flight is set by shared memory (18 maps fit), not by registers.
+// The arithmetic per element is that of sbp_fused_kernel, so dlogits and joints are bit-identical (a GPU test compares the
+// two); the fp32 partial sums of a map are grouped differently (loss equal to ~1e-7).  Candidates of the argmax are re-read
+// from shared memory.
+#ifndef POSE_TMA_MPC
+#define POSE_TMA_MPC 4          // maps per CTA
+#endif
+#ifndef POSE_TMA_WPM
+#define POSE_TMA_WPM 2          // warps per map
+#endif
+#ifndef POSE_TMA_MINB_GRAD
+#define POSE_TMA_MINB_GRAD 4
+#endif
+#ifndef POSE_TMA_MINB_RO
+#define POSE_TMA_MINB_RO 4
+#endif
+constexpr int kTmaThreads = 32 * POSE_TMA_WPM * POSE_TMA_MPC;
+__host__ __device__ inline size_t sbp_tma_smem_bytes(int HW) { return (size_t)POSE_TMA_MPC * (size_t)HW * sizeof(float); }
+
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+
+// stage the CTA's maps: thread 0 initialises one mbarrier per map and issues the bulk copies (the caller's next CTA barrier
+// makes the initialised mbarriers visible to the waiting threads)
+__device__ __forceinline__ void tma_stage_maps(float* tiles, unsigned long long* bars, const float* __restrict__ src, long long map0, int nmap,
+                                               int HW) {
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < nmap; ++k) mbar_init(smem_u32(&bars[k]), 1);
+        mbar_init_fence();
+        const uint32_t bytes = (uint32_t)HW * 4u;
+        for (int k = 0; k < nmap; ++k) {
+            mbar_arrive_expect_tx(smem_u32(&bars[k]), bytes);
+            bulk_load(smem_u32(tiles + (size_t)k * HW), src + (map0 + k) * HW, bytes, smem_u32(&bars[k]));
+        }
+    }
+}
+
+template <bool GRAD, bool DEC>
+__global__ void __launch_bounds__(kTmaThreads, GRAD ? POSE_TMA_MINB_GRAD : POSE_TMA_MINB_RO) sbp_fused_tma_kernel(SbpFusedParams P) {
+    constexpr int V = 4, MPC = POSE_TMA_MPC, WPM = POSE_TMA_WPM, TPM = 32 * WPM;
+    extern __shared__ __align__(128) float tiles[];            // MPC maps of HW floats
+    __shared__ __align__(8) unsigned long long s_bar[MPC];
+    __shared__ Patch s_patch[MPC];
+    __shared__ float s_sum[MPC][WPM][3];
+    __shared__ unsigned long long s_key[MPC];
+    pdl_launch_dependents();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = wid / WPM, ws = wid - k * WPM;               // this warp's map slot and its index among the map's warps
+    const int t = ws * 32 + lane;                              // thread index within the map
+    const long long map0 = (long long)blockIdx.x * MPC;
+    const int nmap = (int)min((long long)MPC, P.n_maps - map0);
+    const int nvec = P.HW / V;
+    constexpr bool SHARE = !GRAD;
+    tma_stage_maps(tiles, s_bar, P.logits, map0, nmap, P.HW);
+    if (tid == 0 && map0 == 0) {
+        if (P.xpub.world > 0) exchange_open_step(P.xpub);
+        *P.ticket = 0u;
+    }
+    if (t == 0 && k < nmap) {
+        double kx, ky;
+        load_kp(P.kp, P.kp_f64, map0 + k, kx, ky);
+        s_patch[k] = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
+        s_key[k] = 0ull;
+    }
+    __syncthreads();
+    if (k < nmap) {
+        const float* tile = tiles + (size_t)k * P.HW;
+        float* dl = GRAD ? P.dlogits + (map0 + k) * P.HW : nullptr;
+        float apos = 0.0f, aneg = 0.0f, arem = 0.0f;
+        ArgTrack<V> arg;
+        arg.reset();
+        mbar_wait_parity(&s_bar[k], 0);
+#pragma unroll 4
+        for (int vi = t; vi < nvec; vi += TPM) {
+            float x[V], g[V], unused[V];
+            Vec<V>::load_any(tile, vi, x);
+            if (DEC) arg.template push<true>(x, vi);
+            render_loss_vec<V, GRAD, false, SHARE>(x, g, unused, vi, s_patch[k], P.lut, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
+            if (GRAD) Vec<V>::store(dl, vi, g);
+        }
+        apos = warp_sum(apos);
+        aneg = warp_sum(aneg);
+        arem = warp_sum(arem);
+        if (lane == 0) { s_sum[k][ws][0] = apos; s_sum[k][ws][1] = aneg; s_sum[k][ws][2] = arem; }
+        if (DEC) warp_offer_argmax<V, true>(arg, tile, nvec, t, TPM, P.sig_ref, &s_key[k]);
+    }
+    __syncthreads();
+    if (tid < nmap) {
+        const int m = tid;
+        double a = 0.0, b = 0.0, r = 0.0;
+#pragma unroll
+        for (int w = 0; w < WPM; ++w) { a += (double)s_sum[m][w][0]; b += (double)s_sum[m][w][1]; r += (double)s_sum[m][w][2]; }
+        reinterpret_cast<double2*>(P.partials)[map0 + m] = make_double2(a, b - r);
+        if (DEC) {
+            float conf;
+            int idx;
+            key_to_argmax(s_key[m], conf, idx);
+            write_joint(P.joints + (map0 + m) * 3, conf, idx, P.thr, P.scale, P.W, P.divW);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- loss reduction (deterministic, fixed order, no float atomics)
+// sum `n` (a, b) fp64 pairs, `stride` doubles apart, then loss = (w0*A + w1*B) * inv_norm.  Runs in one CTA.
 __device__ __forceinline__ void reduce_pairs_cta(const double* __restrict__ pairs, int n, long long stride, double w0, double w1,
                                                  double inv_norm, float* __restrict__ loss_out, double* __restrict__ num_out) {
     __shared__ double sa[256], sb[256];
     double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) { a += pairs[i * stride]; b += pairs[i * stride + 1]; }
+    for (int i = threadIdx.x; i < n; i += 256) { a += __ldcg(pairs + i * stride); b += __ldcg(pairs + i * stride + 1); }
     sa[threadIdx.x] = a; sb[threadIdx.x] = b;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
@@ -529,6 +598,49 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const double* __restri
                                                           double inv_norm, float* __restrict__ loss_out, double* __restrict__ num_out) {
     pdl_wait();
     reduce_pairs_cta(pairs, n, stride, w0, w1, inv_norm, loss_out, num_out);
+}
+
+// Two-level form for the per-map pairs of the fused kernel (69 632 of them at B = 4096): slice CTA r sums pairs
+// [r*kReduceSlice, (r+1)*kReduceSlice) -- 8 independent 16-byte loads per thread, then a fixed tree -- into slices[r]; the
+// slice CTA that finishes LAST (a ticket counter, zeroed by the fused kernel) returns true and goes on to add the R slice sums in
+// index order.  Which CTA is last varies from run to run; the order of every addition does not.
+constexpr int kReduceSlice = 2048;
+__host__ __device__ inline int reduce_slices(long long n_pairs) { return n_pairs <= kReduceSlice ? 1 : (int)((n_pairs + kReduceSlice - 1) / kReduceSlice); }
+
+__device__ __forceinline__ bool reduce_slice_and_elect(const double* __restrict__ pairs, long long n, double* __restrict__ slices,
+                                                       unsigned int* __restrict__ ticket, int R, int r) {
+    __shared__ double ta[256], tb[256];
+    __shared__ int s_last;
+    const double2* p2 = reinterpret_cast<const double2*>(pairs);
+    const long long i0 = (long long)r * kReduceSlice + threadIdx.x;
+    double2 v[kReduceSlice / 256];
+#pragma unroll
+    for (int k = 0; k < kReduceSlice / 256; ++k) {
+        const long long i = i0 + 256 * k;
+        v[k] = i < n ? __ldcg(p2 + i) : make_double2(0.0, 0.0);
+    }
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int k = 0; k < kReduceSlice / 256; ++k) { a += v[k].x; b += v[k].y; }
+    ta[threadIdx.x] = a; tb[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { ta[threadIdx.x] += ta[threadIdx.x + s]; tb[threadIdx.x] += tb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        slices[2 * r] = ta[0];
+        slices[2 * r + 1] = tb[0];
+        int last = 1;
+        if (R > 1) {
+            __threadfence();                                   // slice sum visible device-wide before the ticket is taken
+            last = atomicAdd(ticket, 1u) == (unsigned)(R - 1);
+            if (last) __threadfence();                         // ... and the others' sums before they are read
+        }
+        s_last = last;
+    }
+    __syncthreads();
+    return s_last != 0;
 }
 
 // back-projection + COCO row fields of one sample by one warp.
@@ -568,18 +680,21 @@ __device__ __forceinline__ void backproject_sample(const float* __restrict__ joi
     if (lane == 0) packed[(long long)n * stride + 3 * K] = __fdiv_rn(sum, (float)K);
 }
 
-// Epilogue of the fused step, one launch: the LAST CTA reduces the loss partials, the others back-project the decoded
-// joints (8 samples per CTA).  Launched with programmatic stream serialisation: it is scheduled while the fused kernel
-// drains and blocks in griddepcontrol.wait until that grid has completed and its writes are visible.
+// Epilogue of the fused step, one launch: CTAs [0, bp_ctas) back-project the decoded joints (8 samples per CTA), CTAs
+// [bp_ctas, bp_ctas + R) reduce the per-map loss pairs (two levels, see reduce_slice_and_elect).  Launched with programmatic
+// stream serialisation: it is scheduled while the fused kernel drains and blocks in griddepcontrol.wait until that grid has
+// completed and its writes are visible.
 struct SbpEpilogueParams {
-    const double* partials; int nblocks; double w0, w1, inv_norm; float* loss_out; double* num_out;
+    const double* partials; long long n_pairs; double* slices; unsigned int* ticket; int R; int bp_ctas;
+    double w0, w1, inv_norm; float* loss_out; double* num_out;
     const float* joints; const double* bbox; float* packed; int N, K; double in_h, in_w;
 };
 
 __global__ void __launch_bounds__(256) sbp_epilogue_kernel(SbpEpilogueParams P) {
     pdl_wait();
-    if (blockIdx.x == gridDim.x - 1) {
-        reduce_pairs_cta(P.partials, P.nblocks, 2, P.w0, P.w1, P.inv_norm, P.loss_out, P.num_out);
+    if ((int)blockIdx.x >= P.bp_ctas) {
+        if (reduce_slice_and_elect(P.partials, P.n_pairs, P.slices, P.ticket, P.R, (int)blockIdx.x - P.bp_ctas))
+            reduce_pairs_cta(P.slices, P.R, 2, P.w0, P.w1, P.inv_norm, P.loss_out, P.num_out);
         return;
     }
     const int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -619,69 +734,107 @@ struct SbpDecodeParams {
 template <bool SIG>
 __device__ __forceinline__ float act(float v) { return SIG ? sigmoid_fast(v) : v; }
 
+// one CTA per map, every load issued up front (see the file header); no SFU work in the stream; one barrier
 template <int V, bool SIG>
-__global__ void __launch_bounds__(kSbpThreads) sbp_decode_kernel(SbpDecodeParams P) {
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * kSbpWarps + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * kSbpWarps;
+__global__ void __launch_bounds__(kSbpThreads, POSE_MAP_MINB_RO) sbp_decode_kernel(SbpDecodeParams P) {
+    __shared__ unsigned long long s_key;
+    const int tid = threadIdx.x;
+    const long long map = blockIdx.x;
     const int nvec = P.HW / V;
-    constexpr int U = 8;
-
-    // (map, batch) items as one stream per warp; the next item's loads are issued before the per-map tail (see sbp_fused_kernel)
+    constexpr int U = kMapU;
+    const float* src = P.x + map * P.HW;
     float xv[U][V];
-    auto issue = [&](long long m, int b0) {
-        const float* src = P.x + m * P.HW;
+    auto issue = [&](int b0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int vi = b0 + 32 * u;
+            const int vi = b0 + tid + kSbpThreads * u;
             if (vi < nvec) Vec<V>::load(src, vi, xv[u]);
         }
     };
-    long long map = warp0;
-    int base = lane;
+    issue(0);
+    if (tid == 0) s_key = 0ull;
+    __syncthreads();
     ArgTrack<V> arg;
     arg.reset();
-    if (map < P.n_maps) issue(map, base);
-    while (map < P.n_maps) {
+    for (int b0 = 0; b0 < nvec; b0 += kSbpThreads * U) {
+        if (b0 > 0) issue(b0);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int vi = base + 32 * u;
+            const int vi = b0 + tid + kSbpThreads * u;
             if (vi >= nvec) break;
             arg.template push<SIG>(xv[u], vi);
         }
-        int nbase = base + 32 * U;
-        long long nmap = map;
-        const bool last = nbase >= nvec;
-        if (last) { nbase = lane; nmap = map + nwarps; }
-        if (nmap < P.n_maps) issue(nmap, nbase);
-        if (last) {
-            const float* src = P.x + map * P.HW;
-            float best = -INFINITY;
-            int besti = 0x7fffffff;
-            const int owner = resolve_argmax<V, SIG>(arg, src, nvec, lane, P.sig_ref, best, besti);
-            if (lane == owner) {
-                float jx = -1.0f, jy = -1.0f, jc = -1.0f;
-                if (best > P.thr && besti != 0x7fffffff) {
-                    const int row = (int)fdiv((uint32_t)besti, P.divW);
-                    const int col = besti - row * P.W;
-                    jx = (float)col; jy = (float)row; jc = best;
-                    if (P.refine && col > 1 && col < P.W - 1 && row > 1 && row < P.H - 1) {
-                        // quarter-pixel shift toward the higher neighbour (NOT in the reference; opt-in)
-                        const float dx = act<SIG>(__ldg(src + besti + 1)) - act<SIG>(__ldg(src + besti - 1));
-                        const float dy = act<SIG>(__ldg(src + besti + P.W)) - act<SIG>(__ldg(src + besti - P.W));
-                        jx += dx > 0.0f ? 0.25f : (dx < 0.0f ? -0.25f : 0.0f);
-                        jy += dy > 0.0f ? 0.25f : (dy < 0.0f ? -0.25f : 0.0f);
-                    }
-                }
-                float* jo = P.joints + map * 3;
-                jo[0] = __fmul_rn(jx, P.scale);
-                jo[1] = __fmul_rn(jy, P.scale);
-                jo[2] = jc;
+    }
+    warp_offer_argmax<V, SIG>(arg, src, nvec, tid, kSbpThreads, P.sig_ref, &s_key);
+    __syncthreads();
+    if (tid == 0) {
+        float best;
+        int besti;
+        key_to_argmax(s_key, best, besti);
+        float dx = 0.0f, dy = 0.0f;
+        if (P.refine && best > P.thr && besti != 0x7fffffff) {
+            const int row = (int)fdiv((uint32_t)besti, P.divW);
+            const int col = besti - row * P.W;
+            if (col > 1 && col < P.W - 1 && row > 1 && row < P.H - 1) {
+                // quarter-pixel shift toward the higher neighbour (NOT in the reference; opt-in)
+                const float ddx = act<SIG>(__ldg(src + besti + 1)) - act<SIG>(__ldg(src + besti - 1));
+                const float ddy = act<SIG>(__ldg(src + besti + P.W)) - act<SIG>(__ldg(src + besti - P.W));
+                dx = ddx > 0.0f ? 0.25f : (ddx < 0.0f ? -0.25f : 0.0f);
+                dy = ddy > 0.0f ? 0.25f : (ddy < 0.0f ? -0.25f : 0.0f);
             }
-            arg.reset();
         }
-        map = nmap;
-        base = nbase;
+        write_joint(P.joints + map * 3, best, besti, P.thr, P.scale, P.W, P.divW, dx, dy);
+    }
+}
+
+// bulk-async staged form of sbp_decode_kernel (16-byte aligned maps): POSE_TMA_MPC maps per CTA, POSE_TMA_WPM warps per map,
+// see sbp_fused_tma_kernel
+template <bool SIG>
+__global__ void __launch_bounds__(kTmaThreads, POSE_TMA_MINB_RO) sbp_decode_tma_kernel(SbpDecodeParams P) {
+    constexpr int V = 4, MPC = POSE_TMA_MPC, WPM = POSE_TMA_WPM, TPM = 32 * WPM;
+    extern __shared__ __align__(128) float tiles[];
+    __shared__ __align__(8) unsigned long long s_bar[MPC];
+    __shared__ unsigned long long s_key[MPC];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = wid / WPM, ws = wid - k * WPM, t = ws * 32 + lane;
+    const long long map0 = (long long)blockIdx.x * MPC;
+    const int nmap = (int)min((long long)MPC, P.n_maps - map0);
+    const int nvec = P.HW / V;
+    tma_stage_maps(tiles, s_bar, P.x, map0, nmap, P.HW);
+    if (tid < MPC) s_key[tid] = 0ull;
+    __syncthreads();
+    if (k < nmap) {
+        const float* tile = tiles + (size_t)k * P.HW;
+        ArgTrack<V> arg;
+        arg.reset();
+        mbar_wait_parity(&s_bar[k], 0);
+#pragma unroll 4
+        for (int vi = t; vi < nvec; vi += TPM) {
+            float x[V];
+            Vec<V>::load_any(tile, vi, x);
+            arg.template push<SIG>(x, vi);
+        }
+        warp_offer_argmax<V, SIG>(arg, tile, nvec, t, TPM, P.sig_ref, &s_key[k]);
+    }
+    __syncthreads();
+    if (tid < nmap) {
+        const int m = tid;
+        const float* tile = tiles + (size_t)m * P.HW;
+        float best;
+        int besti;
+        key_to_argmax(s_key[m], best, besti);
+        float dx = 0.0f, dy = 0.0f;
+        if (P.refine && best > P.thr && besti != 0x7fffffff) {
+            const int row = (int)fdiv((uint32_t)besti, P.divW);
+            const int col = besti - row * P.W;
+            if (col > 1 && col < P.W - 1 && row > 1 && row < P.H - 1) {
+                const float ddx = act<SIG>(tile[besti + 1]) - act<SIG>(tile[besti - 1]);
+                const float ddy = act<SIG>(tile[besti + P.W]) - act<SIG>(tile[besti - P.W]);
+                dx = ddx > 0.0f ? 0.25f : (ddx < 0.0f ? -0.25f : 0.0f);
+                dy = ddy > 0.0f ? 0.25f : (ddy < 0.0f ? -0.25f : 0.0f);
+            }
+        }
+        write_joint(P.joints + (map0 + m) * 3, best, besti, P.thr, P.scale, P.W, P.divW, dx, dy);
     }
 }
 

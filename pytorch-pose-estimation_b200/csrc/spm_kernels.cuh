@@ -339,39 +339,48 @@ struct __align__(16) SpmFusedPerson {
     int px0, px1, py0, py1;     // Gaussian patch window clipped to the map and to the template, [x0,x1) x [y0,y1); empty: all 0
 };
 
-// Launch shape: 8 STREAM warps + POSE_SPM_PATCH_WARPS PATCH warps per CTA, POSE_SPM_FUSED_MINB CTAs per SM.
-#ifndef POSE_SPM_PATCH_WARPS
-#define POSE_SPM_PATCH_WARPS 4
-#endif
 #ifndef POSE_SPM_FUSED_MINB
-#define POSE_SPM_FUSED_MINB 2
+#define POSE_SPM_FUSED_MINB 4   // resident CTAs per SM the kernel is compiled for (register cap 64)
 #endif
-// float4 per stream thread and unit (the unit must divide a 128x128 plane: 1, 2, 4, 8 or 16), per variant
+// float4 per thread and unit (1, 2, 4 or 8: the unit must divide a 128x128 plane), per variant (tools/spm_skeleton.py,
+// profiles/r01_spm_unit_sweep.log, per 256 / 1024 images):
+//   loss + grad (read logits, write dlogits): 8 KB units -- U=2 222 / 817 us, U=4 235 / 907, U=8 242 / 924, U=1 272 / 1028;
+//   read-only loss: 32 KB units (more covered quads pooled per phase B, twice the loads in flight) -- U=8 123 / 415 us,
+//     U=4 138 / 488, U=2 166 / 633;
+//   render-only (LOSS = false, pose_spm_render): 32 KB units -- U=8 123 / 447 us, U=4 124 / 457, U=2 127 / 456.
 #ifndef POSE_SPM_FUSED_U
-#define POSE_SPM_FUSED_U 4              // loss + grad: read logits, write dlogits (16 KB units)
+#define POSE_SPM_FUSED_U 2
 #endif
 #ifndef POSE_SPM_FUSED_U_RO
-#define POSE_SPM_FUSED_U_RO 4           // read-only loss (16 KB units)
+#define POSE_SPM_FUSED_U_RO 8
 #endif
 #ifndef POSE_SPM_FUSED_U_RENDER
-#define POSE_SPM_FUSED_U_RENDER 8       // render only: write stream
+#define POSE_SPM_FUSED_U_RENDER 8
 #endif
 __host__ __device__ constexpr int spm_fused_u(bool grad, bool wtgt, bool loss = true) {
     return !loss ? POSE_SPM_FUSED_U_RENDER : (grad || wtgt) ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
 }
+constexpr int kSpmFusedUMax0 = POSE_SPM_FUSED_U > POSE_SPM_FUSED_U_RO ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
+constexpr int kSpmFusedUMax = kSpmFusedUMax0 > POSE_SPM_FUSED_U_RENDER ? kSpmFusedUMax0 : POSE_SPM_FUSED_U_RENDER;
 constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
-constexpr int kSpmStreamWarps = 8;
-constexpr int kSpmStreamThreads = kSpmStreamWarps * 32;
-constexpr int kSpmPatchWarps = POSE_SPM_PATCH_WARPS;
-constexpr int kSpmFusedThreads = kSpmStreamThreads + 32 * kSpmPatchWarps;
-constexpr int kSpmListCap = 2048;                             // covered quads of one image kept as a list (more: the bitmap is walked)
-constexpr int kSpmOvSlots = 1024;                             // MAP: hash table (pixel -> mask of covering persons) of the pixels in SEVERAL boxes
+// PATCH (read-only loss variant at R = 128, i.e. ROWG && MAP): the covered quads of an image are listed once per image; the
+// stream (phase A) never stops for them and ONE pass per plane, by the whole CTA with one pixel per thread and full lanes,
+// computes the listed pixels.  Their logits are requested when the CTA enters the plane and consumed when it leaves it, so the
+// dependent chain of the per-warp phase B is off the streaming path: 124.0 -> 115.9 us per 256 images, 417.8 -> 407.9 us per
+// 1024.  The variants that write dlogits / the target keep the per-warp phase B: a patch pass that writes (phase A skipping the
+// zero stores of covered quads) was measured slower there (220.8 -> 225.6 us, 819 -> 864 us), and so were three forms with
+// dedicated patch warps beside 8 streaming warps (r02: 241-464 us) -- fewer streaming warps per SM cost more than phase B does.
+#ifndef POSE_SPM_PATCH_NPRE
+#define POSE_SPM_PATCH_NPRE 3   // pixels per thread whose logits are requested at plane entry (3 x 256 = 192 covered quads)
+#endif
+constexpr int kSpmPatchListCap = 4096;                        // all quads of a 128 x 128 plane
+
 constexpr int kSpmMapMaxBytes = 16384;                        // per-image pixel map (one byte per pixel): R <= 128
 
 __host__ __device__ inline bool spm_fused_use_map(int R) { return R * R <= kSpmMapMaxBytes; }
 __host__ __device__ inline size_t spm_fused_smem_bytes(int div_n, int R, int K, int wpr, int lut_n) {
     return (size_t)div_n * 8 + (size_t)R * 8 + (size_t)kSpmFusedMaxPersons * K * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4 +
-           (size_t)kSpmListCap * 4 + (spm_fused_use_map(R) ? (size_t)R * R + (size_t)kSpmOvSlots * 12 + 8 : 0);
+           (spm_fused_use_map(R) ? (size_t)R * R : 0);
 }
 
 // target of one pixel: (root value t0 = max of the covering Gaussian patches, displacement te of plane (jn, axis))
@@ -397,72 +406,51 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
     }
 }
 
-// The SPM target is ~97 % zeros and the zero part costs nothing but bandwidth: target 0, mask 0 => the loss term is 0 unless
-// the logit is NaN (sigmoid(p)*0 and tanh(p)*0 are 0 for every other p) and dlogits = 0.  The kernel is therefore two
-// programs that never touch the same bytes, run by different warps of one CTA:
-//   * 8 STREAM warps walk the CTA's contiguous range of 16/32 KB units linearly: one broadcast shared-memory word tells a warp
-//     which of its 32 float4 quads lie in some person's box or Gaussian patch ("covered"); the other quads are loaded (NaN
-//     check only), and zeros are stored to dlogits / the target.  No person data, no branches, no dependent chains.
-//   * the PATCH warps own the covered quads (~3-6 % of a plane, the same set for all 1+2K planes of an image, listed once per
-//     image): one quad per lane -- 128-bit load of the logits (prefetched into L2 one plane ahead), the plane-independent
-//     geometry from a per-image byte map (MAP) or the generic person loop, template / quotient-table look-ups, tanhf only
-//     under the root mask -- and 128-bit stores of the 4 results.  Its long dependent chains (LDS -> LDG -> LDS -> SFU -> STG)
-//     delay nobody: the stream warps never wait for it except at an image boundary of the CTA's range.
-// LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read.
-// MAP (R*R <= 16 KB, i.e. R <= 128 -- configs/spm_coco.yaml): bit 7 = root mask (t0 > 0), bits 0-6: 0 = in no person's box,
-//   p+1 = in the box of person p only, 127 = in several boxes (replay them in order).
-// ROWG (R % 128 == 0): the 32 quads of a warp instruction are exactly one word of the covered-quad bitmap and every unit is full.
-// History (r01, per 256 images, loss + grad): covered pixels handled inside the streaming warps, pooled per warp and unit with
-// the logits re-read through L2 -- 220.9 us (81 % of the copy peak); a per-plane patch pass by the whole CTA: 225.6 us.
-// loss term and gradient of one pixel given its logit pe, its target (root: t0, displacement: te) and the root mask mk
-template <bool LOSS>
-__device__ __forceinline__ float spm_pixel_loss(const SpmFusedParams& P, bool disp, float pe, float t0, float te, bool mk, float& acc) {
-    if (!LOSS) return 0.0f;
-    if (!disp) {
-        const float sg = sigmoid_fast(pe);
-        const float d = (mk ? sg : sg * 0.0f) - t0;
-        acc = fmaf(d, d, acc);
-        return mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
-    }
-    // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
-    float th = 0.0f, pm = pe != pe ? pe : 0.0f;                   // NaN logits propagate as in the reference
-    if (mk) { th = tanhf(pe); pm = th; }
-    const float d = pm - te;
-    const float ad = fabsf(d);
-    acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-    return mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
-}
-
+// LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read, the target is
+// written as one linear stream with the covered pixels filled in by the same pass.
+// MAP (R*R <= 16 KB, i.e. R <= 128 -- configs/spm_coco.yaml): the geometry of a pixel is the same for all 2K displacement
+// planes of an image, so it is evaluated ONCE per image into a byte map in shared memory -- bit 7: root mask (t0 > 0), bits
+// 0-6: 0 = in no person's box, p+1 = in the box of person p only, 127 = in several boxes (replay them in order) -- and phase B
+// of a displacement plane is one byte load + one joint + one quotient look-up instead of a loop over the row's persons with
+// eight range compares each.  Larger maps keep the generic per-pixel evaluation.
+// ROWG (R % 128 == 0): the 32 quads of a warp instruction lie in one row and are exactly one word of that row's
+// covered-quad bits, and every unit is full: one broadcast LDS gives the warp's coverage mask (no per-lane look-up, no
+// ballot, no validity predicates on the stream).
+// (Tried and dropped: a 4-row x 8-quad tile per warp instruction, so that a 9x9 box touches ~3.75 tiles instead of 9 rows and
+// phase B is entered 2.4x less often -- the four separate 128-byte lines per access cost more than that saved: 253 -> 318 us
+// fused, 144 -> 177 us render-only per 256 images.  Likewise a warp owning U CONSECUTIVE rows of a unit instead of every 8th row
+// (a 9-row box then falls to ~3 warps with full phase-B passes instead of 8 sparse ones): 235 -> 290 us fused, 125 -> 175 us
+// read-only -- the few loaded warps become the critical path of the CTA's unit range.  And a per-warp shared-memory ring filled
+// with cp.async (LDGSTS) so that the next units' loads fly during phase B and phase B reads its logit from the ring instead of
+// L2: 235 -> 235 us (N=256), 902 -> 872 us (N=1024) for the grad variant at 3 CTAs/SM, 125 -> 139 us read-only -- the L2
+// prefetch of the next unit already hides that latency; not worth 32 KB of shared memory per CTA.)
 template <bool LOSS, bool GRAD, bool WTGT, bool ROWG, bool MAP>
-__global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
+__global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
     // dynamic shared memory: [div_n] double quotients | [R] u64 row masks | [64*K] int2 joints | [R*wpr] u32 covered quads | template
-    //                        | [kSpmListCap] u32 covered-quad list | MAP: [kSpmOvSlots] u64 person masks | [kSpmOvSlots] u32 keys (pixel + 1)
-    //                        | [R*R] u8 pixel map
+    //                        | MAP: [R*R] u8 pixel map
     extern __shared__ __align__(16) unsigned char spm_fused_smem[];
     double* div_s = reinterpret_cast<double*>(spm_fused_smem);
     unsigned long long* rowmask_s = reinterpret_cast<unsigned long long*>(div_s + P.div_n);
     int2* s_j = reinterpret_cast<int2*>(rowmask_s + P.R);
     unsigned int* covq_s = reinterpret_cast<unsigned int*>(s_j + kSpmFusedMaxPersons * P.K);
     float* lut_s = reinterpret_cast<float*>(covq_s + P.R * P.wpr);
-    unsigned int* list_s = reinterpret_cast<unsigned int*>(lut_s + P.lut_n * P.lut_n);
-    // (the template has an odd number of floats for odd n: round up so the 64-bit masks are aligned)
-    unsigned long long* ovmask_s = reinterpret_cast<unsigned long long*>(
-        (reinterpret_cast<uintptr_t>(list_s + kSpmListCap) + 7) & ~uintptr_t(7));                // MAP only
-    unsigned int* ovkey_s = reinterpret_cast<unsigned int*>(ovmask_s + kSpmOvSlots);             // MAP only
-    unsigned char* map_s = reinterpret_cast<unsigned char*>(ovkey_s + kSpmOvSlots);              // MAP only
+    unsigned char* map_s = reinterpret_cast<unsigned char*>(lut_s + P.lut_n * P.lut_n);      // MAP only
     __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
-    __shared__ double red[kSpmFusedThreads / 32][2];
-    __shared__ int s_nlist;                                            // covered quads of the staged image; -1: too many for the list
-    __shared__ int s_ovfull;                                           // MAP: the overlap table overflowed: code 127 falls back to the person loop
-    constexpr int U = spm_fused_u(GRAD, WTGT, LOSS);
-    constexpr int kChunk = kSpmStreamThreads * U;                      // float4 per work unit
-    constexpr int NP = kSpmPatchWarps;
+    __shared__ double red[kSpmThreads / 32][2];
+    constexpr int kSpmFusedU = spm_fused_u(GRAD, WTGT, LOSS);
+    constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;          // float4 per work unit
+    __shared__ unsigned char s_src[kSpmThreads / 32][32 * kSpmFusedU];
+    // ROWG && MAP <=> R == 128: 32 quads per row, wpr == 1
+    constexpr bool PATCH = ROWG && MAP && LOSS && !GRAD && !WTGT;
+    constexpr int NPRE = POSE_SPM_PATCH_NPRE;
+    __shared__ unsigned short plist_s[PATCH ? kSpmPatchListCap : 1];   // covered quads of the staged image, ascending
+    __shared__ int s_nlist;
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
     for (int i = threadIdx.x; i < P.div_n; i += blockDim.x) div_s[i] = (double)(i - P.R) / P.z;
 
     const int C = 1 + 2 * P.K;
-    const int upp = (P.quads + kChunk - 1) / kChunk;
+    const int upp = (P.quads + kSpmFusedChunk - 1) / kSpmFusedChunk;
     const long long units = (long long)P.N * C * upp;
     const long long u_begin = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
     const float4* L4 = reinterpret_cast<const float4*>(P.logits);
@@ -471,18 +459,21 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
     const int qpr = (int)P.div_qpr.d;
     const long long total_quads = (long long)P.N * C * P.quads;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool streamer = wid < kSpmStreamWarps;                       // warp-uniform role
-    const int pw = wid - kSpmStreamWarps;                              // patch warps: 0 .. NP-1
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     double droot = 0.0, ddisp = 0.0;
+    int staged_img = -1;
 
-    for (long long seg = u_begin; seg < u_end;) {
-        // ---------------- one image's share of the CTA's range: [seg, seg_end)
-        const int img = (int)(seg / ((long long)C * upp));
-        const long long seg_end = min(u_end, (long long)(img + 1) * C * upp);
-        {
+    // (image, channel, chunk) of the first unit; advanced incrementally (no 64-bit divisions in the loop)
+    long long plane = u_begin / upp;
+    int chunk = (int)(u_begin - plane * upp);
+    int img = (int)(plane / C), c = (int)(plane - (long long)img * C);
+
+    int q_first = 0, q_last = 0;                                       // PATCH: this CTA's quads [q_first, q_last) of the current plane
+    float pl[NPRE];                                                    // PATCH: logits requested at plane entry
+    for (long long unit = u_begin; unit < u_end; ++unit) {
+        if (img != staged_img) {                                       // CTA-uniform
             const int np = min(max(P.counts[img], 0), min(P.Pmax, kSpmFusedMaxPersons));
-            __syncthreads();                                           // both roles are done with the previous image's tables
+            __syncthreads();
             for (int i = threadIdx.x; i < np; i += blockDim.x) {
                 SpmFusedPerson sp;
                 const long long pi = (long long)img * P.Pmax + i;
@@ -504,10 +495,6 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
             }
             for (int i = threadIdx.x; i < P.R; i += blockDim.x) rowmask_s[i] = 0ull;
             for (int i = threadIdx.x; i < P.R * P.wpr; i += blockDim.x) covq_s[i] = 0u;
-            if (MAP) {
-                for (int i = threadIdx.x; i < kSpmOvSlots; i += blockDim.x) ovkey_s[i] = 0u;
-                if (threadIdx.x == 0) s_ovfull = 0;
-            }
             __syncthreads();
             // one thread per (person, row of the union of its box and patch): row mask bit + covered-quad bits
             const int span = 2 * P.half + 1 + P.lut_n;                 // upper bound on the rows of the union
@@ -525,232 +512,234 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
                 if (xhi < xlo) continue;
                 atomicOr(&rowmask_s[row], 1ull << p);
                 const int q0 = xlo >> 2, q1 = xhi >> 2;
-                for (int w = q0 >> 5; w <= (q1 >> 5); ++w) {
+                    for (int w = q0 >> 5; w <= (q1 >> 5); ++w) {
                     const int lo = max(q0 - 32 * w, 0), hi = min(q1 - 32 * w, 31);
                     const unsigned int bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
                     atomicOr(&covq_s[row * P.wpr + w], bits);
                 }
             }
             __syncthreads();
-            if (MAP && streamer) {
-                // one stream warp per row; only rows that some person touches are ever looked up, the others are not even written
-                for (int row = wid; row < P.R; row += kSpmStreamWarps) {
+            if (MAP) {
+                // one warp per row; only rows that some person touches are ever looked up, the others are not even written
+                for (int row = wid; row < P.R; row += kSpmThreads / 32) {
                     const unsigned long long rm = rowmask_s[row];
                     if (rm == 0ull) continue;                           // warp-uniform
-                    for (int col = lane; col < P.R; col += 32) {
-                        unsigned long long m = rm, cover = 0ull;
-                        unsigned int code = 0u, nbox = 0u;
-                        bool mk = false;
-                        while (m) {
-                            const int p = __ffsll((long long)m) - 1;
-                            m &= m - 1;
-                            const SpmFusedPerson sp = s_p[p];
-                            if (row >= sp.py0 && row < sp.py1 && col >= sp.px0 && col < sp.px1 &&
-                                lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)] > 0.0f) mk = true;
-                            if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
-                                if (nbox++ == 0u) code = (unsigned)p + 1u;
-                                cover |= 1ull << p;
-                            }
+                  for (int col = lane; col < P.R; col += 32) {
+                    const int idx = row * P.R + col;
+                    unsigned long long m = rm;
+                    unsigned int code = 0u, nbox = 0u;
+                    bool mk = false;
+                    while (m) {
+                        const int p = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const SpmFusedPerson sp = s_p[p];
+                        if (row >= sp.py0 && row < sp.py1 && col >= sp.px0 && col < sp.px1 &&
+                            lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)] > 0.0f) mk = true;
+                        if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
+                            if (nbox++ == 0u) code = (unsigned)p + 1u;
                         }
-                        if (nbox > 1u) {
-                            // in several boxes: the displacement target is a sum over those persons (replayed in index order by the
-                            // patch warps) -- their bit mask goes into a small hash table keyed by the pixel (insertion order is
-                            // irrelevant: look-ups return the same mask whatever the order, so the result stays deterministic)
-                            code = 127u;
-                            const unsigned int key = (unsigned int)(row * P.R + col) + 1u;
-                            unsigned int h = (key * 2654435761u) >> 22;
-                            bool placed = false;
-                            for (int probe = 0; probe < 32 && !placed; ++probe, h = (h + 1u) & (kSpmOvSlots - 1)) {
-                                if (atomicCAS(&ovkey_s[h], 0u, key) == 0u) { ovmask_s[h] = cover; placed = true; }
-                            }
-                            if (!placed) s_ovfull = 1;
-                        }
-                        map_s[row * P.R + col] = (unsigned char)(code | (mk ? 128u : 0u));
                     }
+                    if (nbox > 1u) code = 127u;
+                    map_s[idx] = (unsigned char)(code | (mk ? 128u : 0u));
+                  }
                 }
-            }
-            if (!streamer && pw == 0) {
-                // patch warp 0 lists the covered quads (plane-relative quad index, ascending) from the bitmap: 32 words per step,
-                // a shuffle scan of their popcounts gives every lane its write position
-                const int nwords = P.R * P.wpr;
-                int base = 0;
-                bool fits = true;
-                for (int w0 = 0; w0 < nwords; w0 += 32) {
-                    const int wi = w0 + lane;
-                    unsigned int bits = wi < nwords ? covq_s[wi] : 0u;
-                    const int cnt = __popc(bits);
+                if (PATCH && wid == kSpmThreads / 32 - 1) {
+                    // the covered-quad bits (one word per row, 4 rows per lane) -> ascending list of quad indices
+                    unsigned int w4[4];
+                    int cnt = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { w4[k] = covq_s[4 * lane + k]; cnt += __popc(w4[k]); }
                     int incl = cnt;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const int t = __shfl_up_sync(FULL_MASK, incl, o);
                         if (lane >= o) incl += t;
                     }
-                    const int tot = __shfl_sync(FULL_MASK, incl, 31);
-                    if (base + tot > kSpmListCap) { fits = false; break; }       // warp-uniform
-                    int pos = base + incl - cnt;
-                    const int row = wi / P.wpr, q0 = row * qpr + (wi - row * P.wpr) * 32;
-                    while (bits) {
-                        const int b = __ffs((int)bits) - 1;
-                        bits &= bits - 1u;
-                        list_s[pos++] = (unsigned int)(q0 + b);
-                    }
-                    base += tot;
-                }
-                if (lane == 0) s_nlist = fits ? base : -1;
-            }
-            __syncthreads();
-        }
-
-        if (streamer) {
-            // ---------------- STREAM: every quad that no person touches
-            long long plane = seg / upp;
-            int chunk = (int)(seg - plane * upp);
-            int c = (int)(plane - (long long)img * C);
-            const int tid = threadIdx.x;                               // 0 .. 255
-            for (long long unit = seg; unit < seg_end; ++unit) {
-                const long long off = plane * P.quads;
-                const int q_lo = chunk * kChunk;
-                float4 pv[U];
-                unsigned live = 0u;                                    // bit u: this thread's quad of instruction u is valid and not covered
+                    int pos = incl - cnt;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int q = q_lo + u * kSpmStreamThreads + tid;
-                    bool lv;
-                    if (ROWG) {
-                        // quads is a multiple of the chunk and a warp instruction is one word of the bitmap: one broadcast LDS
-                        lv = !((covq_s[(q_lo >> 5) + u * kSpmStreamWarps + wid] >> lane) & 1u);
-                    } else {
-                        lv = false;
-                        if (q < P.quads) {
-                            const int row = (int)fdiv((uint32_t)q, P.div_qpr), cq = q - row * qpr;
-                            lv = !((covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u);
+                    for (int k = 0; k < 4; ++k) {
+                        unsigned int bits = w4[k];
+                        while (bits) {
+                            const int b = __ffs((int)bits) - 1;
+                            bits &= bits - 1u;
+                            plist_s[pos++] = (unsigned short)((4 * lane + k) * 32 + b);
                         }
                     }
-                    pv[u] = z4;
-                    if (LOSS && lv) pv[u] = ldg_stream(L4 + off + q);
-                    live |= (lv ? 1u : 0u) << u;
+                    if (lane == 31) s_nlist = incl;
                 }
-                if (LOSS && unit + 1 < seg_end) {
-                    // the next unit of this CTA is the next 16/32 KB in memory (planes are contiguous): pull it into L2 meanwhile
-                    const char* nsrc = reinterpret_cast<const char*>(L4 + off + min(q_lo + kChunk, P.quads));
-                    const char* lend = reinterpret_cast<const char*>(L4 + total_quads);
-                    if (tid < kChunk * 16 / 128 && nsrc + tid * 128 < lend) prefetch_l2(nsrc + tid * 128);
-                }
-                float acc = 0.f;
+                __syncthreads();
+            }
+            staged_img = img;
+        }
+        const long long off = plane * P.quads;
+        const int q_lo = chunk * kSpmFusedChunk;
+        float4 pv[kSpmFusedU];
+        const float4* lsrc = L4 + off + q_lo + threadIdx.x;
+        // ROWG: quads is a multiple of the chunk, so every quad of every unit is valid (no predicates on the stream)
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (!((live >> u) & 1u)) continue;
-                    const int q = q_lo + u * kSpmStreamThreads + tid;
+        for (int u = 0; u < kSpmFusedU; ++u)
+            if (LOSS && (ROWG || q_lo + u * kSpmThreads + (int)threadIdx.x < P.quads)) pv[u] = ldg_stream(lsrc + u * kSpmThreads);
+        if (LOSS && unit + 1 < u_end) {
+            // the next unit of this CTA is the next 16 KB in memory (planes are contiguous): pull it into L2 while this unit
+            // computes.  Measured alternatives, both SLOWER than this prefetch (252 us per 256 images): holding the next unit in
+            // a second register set (285-291 us at 3 CTAs/SM), and re-using pv for the next unit's loads right after phase A so
+            // that they fly during phase B (278 us: pv then lives across phase B and spills under the 64-register cap).
+            const char* nsrc = reinterpret_cast<const char*>(L4 + off + min(q_lo + kSpmFusedChunk, P.quads));
+            const char* lend = reinterpret_cast<const char*>(L4 + total_quads);
+            if (threadIdx.x < kSpmFusedChunk * 16 / 128 && nsrc + threadIdx.x * 128 < lend) prefetch_l2(nsrc + threadIdx.x * 128);
+        }
+        const bool disp = c != 0;
+        const int jn = (c - 1) >> 1, axis = (c - 1) & 1;                 // displacement plane: joint and axis (0 = x, 1 = y)
+        float acc = 0.f;
+        if (PATCH && (unit == u_begin || chunk == 0)) {                  // entering a plane (CTA-uniform)
+            q_first = q_lo;
+            q_last = (chunk + (int)min((long long)(upp - chunk), u_end - unit)) * kSpmFusedChunk;
+            const int nl4 = 4 * s_nlist;
+#pragma unroll
+            for (int k = 0; k < NPRE; ++k) {
+                const int i = (int)threadIdx.x + k * kSpmThreads;
+                pl[k] = 0.0f;
+                if (i < nl4) {
+                    const int q = (int)plist_s[i >> 2];
+                    if (LOSS && q >= q_first && q < q_last) pl[k] = __ldg(P.logits + (off + q) * 4 + (i & 3));
+                }
+            }
+        }
+        unsigned cmask[kSpmFusedU];
+        float4* gdst = GRAD ? G4 + off + q_lo + threadIdx.x : nullptr;
+        float4* tdst = WTGT ? T4 + off + q_lo + threadIdx.x : nullptr;
+        unsigned anyc = 0u;
+        if (ROWG) {
+            // phase A, uniform: EVERY quad is treated as uncovered (zero target, zero mask: the loss term is 0 unless the logit
+            // is NaN -- sigmoid(p)*0 and tanh(p)*0 are 0 for every other p -- and dlogits = 0); phase B then overwrites the
+            // pixels of the covered quads (ordered after these stores by its __syncwarp; a NaN counted twice is still a NaN).
+            // The warp's coverage mask is one broadcast LDS: with wpr = qpr/32 the word index is the warp's group index in the
+            // plane.  No per-lane look-up, no ballot, no branch on the stream.
+#pragma unroll
+            for (int u = 0; u < kSpmFusedU; ++u) {
+                if (LOSS) {
+                    const float4 v = pv[u];
+                    const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+                    if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
+                }
+                cmask[u] = covq_s[(q_lo >> 5) + u * (kSpmThreads / 32) + wid];
+                if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
+                if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
+            }
+#pragma unroll
+            for (int u = 0; u < kSpmFusedU; ++u) anyc |= cmask[u];
+        } else {
+#pragma unroll
+            for (int u = 0; u < kSpmFusedU; ++u) {
+                const int qu = q_lo + u * kSpmThreads + (int)threadIdx.x;
+                const bool valid = qu < P.quads;
+                bool covered = false;
+                if (valid) {
+                    const int row = (int)fdiv((uint32_t)qu, P.div_qpr), cq = qu - row * qpr;
+                    covered = (covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u;
+                }
+                cmask[u] = __ballot_sync(FULL_MASK, covered);
+                if (cmask[u]) anyc |= 1u << u;
+                if (valid && !covered) {
                     if (LOSS) {
                         const float4 v = pv[u];
                         const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
                         if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
                     }
-                    if (GRAD) __stcs(G4 + off + q, z4);
-                    if (WTGT) __stcs(T4 + off + q, z4);
+                    if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
+                    if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
                 }
-                if (LOSS && acc != 0.f) { if (c == 0) droot += (double)acc; else ddisp += (double)acc; }     // NaN only
-                if (++chunk == upp) { chunk = 0; ++plane; ++c; }
-            }
-        } else {
-            // ---------------- PATCH: the covered quads of every plane (or part of a plane) in [seg, seg_end)
-            const int nlist = s_nlist;
-            const bool ov_table = MAP && s_ovfull == 0;                 // pixels in several boxes: person masks come from the hash table
-            const long long p_first = seg / upp, p_last = (seg_end - 1) / upp;
-            auto quad = [&](long long off, int q, bool disp, int jn, int axis, float& acc) {
-                const int row = (int)fdiv((uint32_t)q, P.div_qpr), col0 = (q - row * qpr) * 4;
-                float pe[4] = {0.f, 0.f, 0.f, 0.f};
-                if (LOSS) {
-                    const float4 v = __ldg(L4 + off + q);
-                    pe[0] = v.x; pe[1] = v.y; pe[2] = v.z; pe[3] = v.w;
-                }
-                unsigned int codes = 0x7f7f7f7fu;
-                if (MAP) codes = *reinterpret_cast<const unsigned int*>(map_s + row * P.R + col0);
-                float ge[4], te4[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int col = col0 + e;
-                    const unsigned int code = (codes >> (8 * e)) & 255u;
-                    float t0 = 0.0f, te = 0.0f;
-                    bool mk;
-                    if (MAP && disp && (code & 127u) != 127u) {
-                        mk = code >> 7;
-                        if (code & 127u) {
-                            const int2 jv = s_j[((int)(code & 127u) - 1) * P.K + jn];
-                            if (!(jv.x <= 0 && jv.y <= 0)) {
-                                const int dd = axis ? jv.y - row : jv.x - col;
-                                te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
-                            }
-                        }
-                    } else if (MAP && disp && ov_table) {
-                        // in several boxes: sum over the covering persons in index order, fp32(fp64(acc) + q) each (numpy's +=)
-                        mk = code >> 7;
-                        const unsigned int key = (unsigned int)(row * P.R + col) + 1u;
-                        unsigned int h = (key * 2654435761u) >> 22;
-                        while (ovkey_s[h] != key) h = (h + 1u) & (kSpmOvSlots - 1);
-                        unsigned long long m = ovmask_s[h];
-                        while (m) {
-                            const int p = __ffsll((long long)m) - 1;
-                            m &= m - 1;
-                            const int2 jv = s_j[p * P.K + jn];
-                            if (!(jv.x <= 0 && jv.y <= 0)) {
-                                const int dd = axis ? jv.y - row : jv.x - col;
-                                const double qd = (P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z;
-                                te = (float)((double)te + qd);
-                            }
-                        }
-                    } else if (MAP && !disp && (code & 128u) == 0u) {
-                        mk = false;                                       // root plane, pixel outside every Gaussian patch: t0 = 0
-                    } else {
-                        spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
-                        mk = t0 > 0.0f;
-                    }
-                    ge[e] = spm_pixel_loss<LOSS>(P, disp, pe[e], t0, te, mk, acc);
-                    te4[e] = disp ? te : t0;
-                }
-                if (GRAD) __stcs(G4 + off + q, make_float4(ge[0], ge[1], ge[2], ge[3]));
-                if (WTGT) __stcs(T4 + off + q, make_float4(te4[0], te4[1], te4[2], te4[3]));
-            };
-            for (long long plane = p_first; plane <= p_last; ++plane) {
-                const int c = (int)(plane - (long long)img * C);
-                const bool disp = c != 0;
-                const int jn = (c - 1) >> 1, axis = (c - 1) & 1;             // displacement plane: joint and axis (0 = x, 1 = y)
-                const long long off = plane * P.quads;
-                // this CTA's quads of the plane: [q_first, q_last)
-                const int q_first = plane == p_first ? (int)(seg - plane * upp) * kChunk : 0;
-                const int q_last = plane == p_last ? min(P.quads, (int)(seg_end - plane * upp) * kChunk) : P.quads;
-                float acc = 0.f;
-                if (nlist >= 0) {
-                    if (LOSS && plane < p_last) {
-                        // the next plane's covered logits travel to L2 while this plane is computed (no stream warp reads them)
-                        const int nq_last = plane + 1 == p_last ? min(P.quads, (int)(seg_end - (plane + 1) * upp) * kChunk) : P.quads;
-                        for (int i = pw * 32 + lane; i < nlist; i += 32 * NP) {
-                            const int q = (int)list_s[i];
-                            if (q < nq_last) prefetch_l2(L4 + off + P.quads + q);
-                        }
-                    }
-                    for (int i = pw * 32 + lane; i < nlist; i += 32 * NP) {
-                        const int q = (int)list_s[i];
-                        if (q >= q_first && q < q_last) quad(off, q, disp, jn, axis, acc);
-                    }
-                } else {
-                    // more covered quads than the list holds (dozens of persons on a large map): walk the bitmap, one word per lane
-                    const int nwords = P.R * P.wpr;
-                    for (int wi = pw * 32 + lane; wi < nwords; wi += 32 * NP) {
-                        unsigned int bits = covq_s[wi];
-                        const int row = wi / P.wpr, q0 = row * qpr + (wi - row * P.wpr) * 32;
-                        while (bits) {
-                            const int b = __ffs((int)bits) - 1;
-                            bits &= bits - 1u;
-                            const int q = q0 + b;
-                            if (q >= q_first && q < q_last) quad(off, q, disp, jn, axis, acc);
-                        }
-                    }
-                }
-                if (c == 0) droot += (double)acc; else ddisp += (double)acc;
             }
         }
-        seg = seg_end;
+        // phase B: one pixel of a covered quad per lane.  The covered quads of ALL the warp's instructions of this unit are
+        // pooled (slot k of the warp's scratch row = u*32 + lane of the k-th covered quad), so the long dependent chain below
+        // runs once per warp and unit with up to 32 useful lanes, not once per covered instruction with ~14.  Deliberately not
+        // unrolled over u (an unrolled copy per u made the kernel 113 KB of SASS and `no_instruction` the second largest
+        // stall).  The pixel's logit is re-read from L2 (the warp streamed it a moment ago) rather than shuffled out of pv[]:
+        // pv dies after phase A, which keeps the kernel inside 64 registers without spills.
+        // one covered pixel: element e of quad qs (plane-relative) with logit pe
+        auto pixel = [&](int qs, int e, float pe) {
+            const long long ei = (off + qs) * 4 + e;
+            const int row = (int)fdiv((uint32_t)qs, P.div_qpr), col = (qs - row * qpr) * 4 + e;
+            float t0 = 0.0f, te = 0.0f;
+            bool mk;
+            unsigned int code = 127u;
+            if (MAP && disp) code = map_s[row * P.R + col];
+            if (ROWG && MAP && disp && code == 0u) return;               // slack pixel of a covered quad: phase A's zeros stand
+            if (MAP && disp && (code & 127u) != 127u) {
+                mk = code >> 7;
+                if (code & 127u) {
+                    const int2 jv = s_j[((int)(code & 127u) - 1) * P.K + jn];
+                    if (!(jv.x <= 0 && jv.y <= 0)) {
+                        const int dd = axis ? jv.y - row : jv.x - col;
+                        te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
+                    }
+                }
+            } else {
+                spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
+                mk = t0 > 0.0f;
+            }
+            float ge = 0.0f;
+            if (!LOSS) {
+                if (!disp) te = t0;
+            } else if (!disp) {
+                const float sg = sigmoid_fast(pe);
+                const float d = (mk ? sg : sg * 0.0f) - t0;
+                acc = fmaf(d, d, acc);
+                ge = mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
+                te = t0;
+            } else {
+                // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
+                float th = 0.0f, pm = pe != pe ? pe : 0.0f;          // NaN logits propagate as in the reference
+                if (mk) { th = tanhf(pe); pm = th; }
+                const float d = pm - te;
+                const float ad = fabsf(d);
+                acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+                ge = mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
+            }
+            if (GRAD) __stcs(P.dlogits + ei, ge);
+            if (WTGT) __stcs(P.target_out + ei, te);
+        };
+        if (!PATCH && anyc) {                                            // warp-uniform
+            int nslot = 0;
+#pragma unroll
+            for (int u = 0; u < kSpmFusedU; ++u) {
+                if ((cmask[u] >> lane) & 1u) s_src[wid][nslot + __popc(cmask[u] & ((1u << lane) - 1u))] = (unsigned char)(u * 32 + lane);
+                nslot += __popc(cmask[u]);
+            }
+            __syncwarp();                                                // also orders phase A's zero stores before the overwrites
+            const int total = nslot * 4;
+            for (int b = 0; b < total; b += 32) {
+                const int l = b + lane;
+                if (l >= total) continue;
+                const int sl = (int)s_src[wid][l >> 2];
+                const int qs = q_lo + (sl >> 5) * kSpmThreads + wid * 32 + (sl & 31);
+                const int e = l & 3;
+                pixel(qs, e, LOSS ? __ldg(P.logits + (off + qs) * 4 + e) : 0.0f);
+            }
+            __syncwarp();                                                // scratch row is rewritten by the next covered group
+        }
+        if (PATCH && (unit + 1 == u_end || chunk == upp - 1)) {          // leaving the plane (CTA-uniform): its patch pass
+            const int nl4 = 4 * s_nlist;
+#pragma unroll
+            for (int k = 0; k < NPRE; ++k) {
+                const int i = (int)threadIdx.x + k * kSpmThreads;
+                if (i < nl4) {
+                    const int q = (int)plist_s[i >> 2];
+                    if (q >= q_first && q < q_last) pixel(q, i & 3, pl[k]);
+                }
+            }
+            for (int i = (int)threadIdx.x + NPRE * kSpmThreads; i < nl4; i += kSpmThreads) {
+                const int q = (int)plist_s[i >> 2];
+                if (q >= q_first && q < q_last) pixel(q, i & 3, LOSS ? __ldg(P.logits + (off + q) * 4 + (i & 3)) : 0.0f);
+            }
+        }
+        if (c == 0) droot += (double)acc; else ddisp += (double)acc;
+        if (++chunk == upp) {
+            chunk = 0;
+            ++plane;
+            if (++c == C) { c = 0; ++img; }
+        }
     }
     if (!LOSS) return;                                                   // render-only: no loss partials (P.partials is NULL)
     droot = warp_sum(droot);
@@ -760,7 +749,7 @@ __global__ void __launch_bounds__(kSpmFusedThreads, POSE_SPM_FUSED_MINB) spm_fus
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int w = 0; w < kSpmFusedThreads / 32; ++w) { a += red[w][0]; b += red[w][1]; }
+        for (int w = 0; w < kSpmThreads / 32; ++w) { a += red[w][0]; b += red[w][1]; }
         P.partials[2 * blockIdx.x] = a;
         P.partials[2 * blockIdx.x + 1] = b;
     }
@@ -881,10 +870,13 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
     if (threadIdx.x == 0) s_ncand = 0;
     __syncthreads();
 
-    // root confidence = the reference's sigmoid, bit for bit (the greedy order and the threshold test depend on it); it is only
-    // evaluated for logits that can pass the threshold at all (x_lo), i.e. for the few dozen candidates of a real map -- the
-    // stream itself does no SFU work
-    auto conf_of = [&](float v) -> float {
+    // root confidence = the reference's sigmoid, bit for bit (the greedy order and the threshold test depend on it).  The stream
+    // only compares the raw value with a bound (apply_act: x_lo, the logit below which neither reference can exceed thr; else thr
+    // itself) and lists what passes; the reference sigmoid is evaluated afterwards, on the list -- a few dozen entries of a real
+    // map, all lanes busy -- so the streaming loop holds no SFU work, no divisions and no divergent branch.  (Evaluating it
+    // inside the stream behind `v > x_lo` cost 8-10 us per launch: 18.6 -> 26.7 us per 256 images.)
+    const float pass_lo = P.apply_act ? P.x_lo : P.thr;
+    auto conf_of = [&](float v) -> float {                     // dense fallback only
         if (!P.apply_act) return v;
         return v > P.x_lo ? sigmoid_ref(v, P.sig_ref) : -INFINITY;
     };
@@ -913,20 +905,26 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
                 if (q >= nq) break;
                 const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float h = conf_of(e[k]);
-                    if (h > P.thr) append(4 * q + k, h);
-                }
+                for (int k = 0; k < 4; ++k)
+                    if (e[k] > pass_lo) append(4 * q + k, e[k]);
             }
         }
     } else {
         for (int i = threadIdx.x; i < RR; i += blockDim.x) {
-            const float h = conf_of(ldg_stream(base + i));
-            if (h > P.thr) append(i, h);
+            const float v = ldg_stream(base + i);
+            if (v > pass_lo) append(i, v);
         }
     }
     __syncthreads();
     const int ncand = s_ncand;
+    if (P.apply_act && ncand <= kSpmCandCap) {
+        // listed logits -> reference confidences; entries that do not pass the threshold after all are struck out
+        for (int e = threadIdx.x; e < ncand; e += blockDim.x) {
+            const float h = sigmoid_ref(s_val[e], P.sig_ref);
+            s_val[e] = h > P.thr ? h : -INFINITY;
+        }
+        __syncthreads();
+    }
 
     int found = 0, flushed = 0;
     float* roots = P.roots + (long long)img * P.Pmax * 3;

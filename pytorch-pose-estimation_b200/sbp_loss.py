@@ -16,8 +16,7 @@ from ._cabi import check, dense, lib, ptr, stream_ptr
 from .sbp_utils import _gauss_template, _kp_tensor, _templates
 
 
-# stage heat maps through shared memory with the TMA engine (cp.async.bulk) instead of per-lane LDG/STG
-DEFAULT_TMA = os.environ.get("POSE_B200_TMA", "0") == "1"
+DEFAULT_TMA = _cabi.DEFAULT_TMA
 
 
 def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, decode=False, conf_threshold=0.25,
@@ -51,7 +50,7 @@ def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, dec
         kp = _kp_tensor(keypoints, dev)
         assert tuple(kp.shape) == (b, k, 2), "keypoints must be [B,K,2]"
         g = _gauss_template(sig)
-        lut, lut_n = _templates.get(g, sig, dev), g.shape[0]
+        lut, lut_n = _templates.get(g, sig, dev, padded=True), g.shape[0]
         kp_dtype = _cabi.KP_F64 if kp.dtype == torch.float64 else _cabi.KP_F32
     out = out or {}
     dlogits = t_out = joints = packed = bb = None
@@ -85,7 +84,7 @@ def sbp_fused(logits, target=None, keypoints=None, sigma=-1, want_grad=True, dec
     num = out.get("loss_num")
     if num is None:
         num = torch.empty((2,), dtype=torch.float64, device=dev)
-    nbytes = int(lib().pose_sbp_fused_workspace_bytes())
+    nbytes = int(lib().pose_sbp_fused_workspace_bytes(b, k))
     ws = _cabi.workspace(dev, nbytes)
     inv_norm = 1.0 / (2.0 * k * (global_batch if global_batch is not None else b)) if b > 0 else 0.0
     with torch.cuda.device(dev):

@@ -29,11 +29,15 @@ class _TemplateCache:
     def __init__(self):
         self._dev = {}
 
-    def get(self, g64, sigma, device):
-        key = (float(sigma), device.type, device.index)
+    def get(self, g64, sigma, device, padded=False):
+        """`padded`: the layout pose_sbp_fused reads (n+1 rows of n+8 floats: 4 zero columns either side, an all-zero last row)."""
+        key = (float(sigma), device.type, device.index, bool(padded))
         t = self._dev.get(key)
         if t is None:
-            t = torch.from_numpy(np.ascontiguousarray(g64.astype(np.float32))).to(device)
+            g = g64.astype(np.float32)
+            if padded:
+                g = np.pad(g, ((0, 1), (4, 4)))
+            t = torch.from_numpy(np.ascontiguousarray(g)).to(device)
             self._dev[key] = t
         return t
 
@@ -119,7 +123,7 @@ def _flip_perm(flip_pairs, k, device):
 
 
 def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False, refine=False, sigmoid_ref=None,
-                 flipped=None, flip_pairs=COCO_FLIP_PAIRS):
+                 flipped=None, flip_pairs=COCO_FLIP_PAIRS, tma=None):
     """[B,K,H,W] CUDA fp32 -> [B,K,3] (x*scale, y*scale, conf); undetected rows are (-scale,-scale,-1).
 
     `sigmoid_ref` ("cpu" | "cuda", default `_cabi.DEFAULT_SIGMOID_REF`): with `apply_sigmoid`, argmax indices and confidences
@@ -127,7 +131,10 @@ def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False,
     decides which of two nearly equal logits is "the first maximum").
 
     `flipped` (not in the reference, opt-in): the maps the network produced for the horizontally mirrored images; they
-    are mirrored back, left/right joints swapped (`flip_pairs`) and averaged with `heatmaps` inside the kernel."""
+    are mirrored back, left/right joints swapped (`flip_pairs`) and averaged with `heatmaps` inside the kernel.
+
+    `tma` (default `_cabi.DEFAULT_TMA`, on): stage the maps through shared memory with bulk async copies -- the fast path;
+    False selects the register-staged kernel (same results bit for bit)."""
     x = dense(heatmaps, "heatmaps")
     assert x.dim() == 4
     b, k, h, w = x.shape
@@ -145,8 +152,8 @@ def decode_batch(heatmaps, conf_threshold, coord_scale=1.0, apply_sigmoid=False,
         return out
     with torch.cuda.device(x.device):
         check(lib().pose_sbp_decode(ptr(x), ptr(out), b, k, h, w, float(conf_threshold), int(bool(apply_sigmoid)),
-                                    float(coord_scale), int(bool(refine)), _cabi.sigmoid_ref_code(sigmoid_ref),
-                                    stream_ptr(x.device)), "pose_sbp_decode")
+                                    float(coord_scale), int(bool(refine)) | (0 if (tma if tma is not None else _cabi.DEFAULT_TMA) else 2),
+                                    _cabi.sigmoid_ref_code(sigmoid_ref), stream_ptr(x.device)), "pose_sbp_decode")
     return out
 
 

@@ -67,7 +67,9 @@ def test_version_and_host_template(pb):
 def test_workspace_sizes_and_cpu_tensor_rejected(pb):
     import torch
     L = pb.lib()
-    assert L.pose_sbp_fused_workspace_bytes() >= 148 * 2 * 8
+    # one fp64 pair per heat map + the slice sums of the two-level reduction + its counter
+    assert L.pose_sbp_fused_workspace_bytes(4096, 17) >= 4096 * 17 * 16 + 34 * 16 + 4
+    assert L.pose_sbp_fused_workspace_bytes(0, 17) >= 16 + 4
     assert L.pose_spm_loss_workspace_bytes() >= 148 * 2 * 8
     with pytest.raises(pb.PoseB200Error):
         pb.decode_batch(torch.zeros(1, 1, 8, 8), 0.5)

@@ -236,7 +236,8 @@ def test_fused_render_loss_grad_decode_single_pass(pb, dev, name):
 
 @pytest.mark.parametrize("name", ["coco", "hires", "sigma3", "sigma1"])
 def test_tma_staged_kernel_matches_ldg_kernel(pb, dev, name):
-    """The bulk-async (TMA) staged variant is the same arithmetic in the same per-lane order: bit-identical outputs."""
+    """The bulk-async (TMA) staged kernels and the register-staged ones do the same arithmetic per element: dlogits and joints are
+    bit-identical; the fp32 partial sums of a map are grouped over different threads, so the loss agrees to fp32 rounding."""
     g = load_golden("sbp_" + name)
     kp, logits, bbox, iid, cid, meta = cases.sbp_case(name)
     x = logits.to(dev)
@@ -245,7 +246,7 @@ def test_tma_staged_kernel_matches_ldg_kernel(pb, dev, name):
         for dec in (True, False):
             a = pb.sbp_fused(x, keypoints=kp, sigma=meta["sigma"], want_grad=grad, decode=dec, conf_threshold=0.25, coord_scale=scale, tma=False)
             b = pb.sbp_fused(x, keypoints=kp, sigma=meta["sigma"], want_grad=grad, decode=dec, conf_threshold=0.25, coord_scale=scale, tma=True)
-            assert close(b["loss"].item(), a["loss"].item(), 1e-7) and allclose(b["loss_num"], a["loss_num"], 1e-12)
+            assert close(b["loss"].item(), a["loss"].item(), 1e-6) and allclose(b["loss_num"], a["loss_num"], 1e-6)
             if grad:
                 assert torch.equal(a["dlogits"], b["dlogits"])
             if dec:
@@ -376,7 +377,7 @@ def test_cabi_argument_errors(pb, dev):
     rc = L.pose_sbp_fused(C.ptr(x), C.ptr(x), None, 0, 1.0, None, 0, None, None, C.ptr(loss), None, None, 0.0, 1.0,
                           1, 1, 8, 8, 5.0, 1.0, 0.5, 0, None, None, 0, 0, None, C.ptr(ws), ws.numel(), C.stream_ptr(dev))
     assert rc == -3      # workspace too small
-    big_ws = torch.zeros(int(L.pose_sbp_fused_workspace_bytes()), dtype=torch.uint8, device=dev)
+    big_ws = torch.zeros(int(L.pose_sbp_fused_workspace_bytes(1, 1)), dtype=torch.uint8, device=dev)
     bb = torch.zeros(1, 4, dtype=torch.float64, device=dev)
     rc = L.pose_sbp_fused(C.ptr(x), C.ptr(x), None, 0, 1.0, None, 0, None, None, C.ptr(loss), None, C.ptr(j), 0.0, 1.0,
                           1, 1, 8, 8, 5.0, 1.0, 0.5, 4, C.ptr(bb), None, 256, 192, None, C.ptr(big_ws), big_ws.numel(), C.stream_ptr(dev))
@@ -436,9 +437,9 @@ def test_full_size_fused_equals_staged_and_oracle_subset(pb, dev, big):
                           coord_scale=4.0)["loss_num"] for i in range(0, b, 1024)]
     tot = torch.stack(parts).sum(0)
     assert allclose(tot, fused["loss_num"], 1e-12)
-    tma = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0, tma=True)
-    assert torch.equal(tma["dlogits"], fused["dlogits"]) and torch.equal(tma["joints"], fused["joints"])
-    assert allclose(tma["loss_num"], fused["loss_num"], 1e-12)
+    ldg = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0, tma=False)
+    assert torch.equal(ldg["dlogits"], fused["dlogits"]) and torch.equal(ldg["joints"], fused["joints"])
+    assert allclose(ldg["loss_num"], fused["loss_num"], 1e-7)         # register-staged kernel: other grouping of the fp32 partial sums
     other = pb.sbp_fused(logits, keypoints=kp, sigma=2, want_grad=False)["loss_num"]      # another variant: fp32 rounding differs
     assert allclose(other, fused["loss_num"], 1e-7)
 

@@ -73,7 +73,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--hw", default="64x48")
     ap.add_argument("--k", type=int, default=17)
-    ap.add_argument("--tma", action="store_true", help="fused render variants through the TMA-staged kernel")
+    ap.add_argument("--no-tma", dest="tma", action="store_false", help="register-staged kernels instead of the bulk-async (TMA) staged ones")
     ap.add_argument("--no-spm", action="store_true")
     ap.add_argument("--spm-n", type=int, default=1024, help="second SPM batch size (config 4: 1024 images)")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph: queue-saturated eager launches")

@@ -11,39 +11,56 @@ import argparse
 import ctypes
 import json
 import os
-import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "tune")
-SRC = os.path.join(ROOT, "pytorch-pose-estimation_b200", "csrc", "api.cu")
-NVCC = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
-# name -> (-D knobs, kernels worth timing for it).  Shipped: U=6/MINB=3 (grad), U_NG=8/MINB_NG=4, U_NGD=8/MINB_NGD=3, SIGMOID_SHARE=4.
+# name -> (-D knobs, kernels worth timing for it).  Shipped ("tree"): see the POSE_MAP_* defaults in csrc/sbp_kernels.cuh.
 GD, G, L, LD = "grad+decode", "grad", "loss", "loss+decode"
 VARIANTS = {
-    "share1": (["-DPOSE_SIGMOID_SHARE=1"], (L, LD)),                                            # one reciprocal per element (r01)
-    "ngd_u6_m3": (["-DPOSE_FUSED_U_NGD=6"], (LD,)),
-    "ngd_u4_m4": (["-DPOSE_FUSED_U_NGD=4", "-DPOSE_FUSED_MINB_NGD=4"], (LD,)),
-    "ngd_u4_m3": (["-DPOSE_FUSED_U_NGD=4"], (LD,)),
-    "ng_u6_m4": (["-DPOSE_FUSED_U_NG=6"], (L,)),
-    "ng_u4_m4": (["-DPOSE_FUSED_U_NG=4"], (L,)),
-    "ng_u8_m3": (["-DPOSE_FUSED_MINB_NG=3"], (L,)),
-    "g_u4_m3": (["-DPOSE_FUSED_U=4"], (GD, G)),
-    "g_u8_m3": (["-DPOSE_FUSED_U=8"], (GD, G)),
+    "w2m2": (['-DPOSE_TMA_MPC=2', '-DPOSE_TMA_WPM=2', '-DPOSE_TMA_MINB_GRAD=8', '-DPOSE_TMA_MINB_RO=8'], (GD, G, L, LD)),
+    "w2m3": (['-DPOSE_TMA_MPC=3', '-DPOSE_TMA_WPM=2', '-DPOSE_TMA_MINB_GRAD=6', '-DPOSE_TMA_MINB_RO=6'], (GD, G, L, LD)),
+    "w2m6": (['-DPOSE_TMA_MPC=6', '-DPOSE_TMA_WPM=2', '-DPOSE_TMA_MINB_GRAD=3', '-DPOSE_TMA_MINB_RO=3'], (GD, G, L, LD)),
+    "w1m4": (['-DPOSE_TMA_MPC=4', '-DPOSE_TMA_WPM=1', '-DPOSE_TMA_MINB_GRAD=4', '-DPOSE_TMA_MINB_RO=4'], (GD, G, L, LD)),
+    "w1m6": (['-DPOSE_TMA_MPC=6', '-DPOSE_TMA_WPM=1', '-DPOSE_TMA_MINB_GRAD=3', '-DPOSE_TMA_MINB_RO=3'], (GD, G, L, LD)),
+    "w1m8": (['-DPOSE_TMA_MPC=8', '-DPOSE_TMA_WPM=1', '-DPOSE_TMA_MINB_GRAD=2', '-DPOSE_TMA_MINB_RO=2'], (GD, G, L, LD)),
+    "w4m2": (['-DPOSE_TMA_MPC=2', '-DPOSE_TMA_WPM=4', '-DPOSE_TMA_MINB_GRAD=4', '-DPOSE_TMA_MINB_RO=4'], (GD, G, L, LD)),
+    "w4m3": (['-DPOSE_TMA_MPC=3', '-DPOSE_TMA_WPM=4', '-DPOSE_TMA_MINB_GRAD=3', '-DPOSE_TMA_MINB_RO=3'], (GD, G, L, LD)),
+    "w3m3": (['-DPOSE_TMA_MPC=3', '-DPOSE_TMA_WPM=3', '-DPOSE_TMA_MINB_GRAD=4', '-DPOSE_TMA_MINB_RO=4'], (GD, G, L, LD)),
+    "w2m4_b3": (['-DPOSE_TMA_MPC=4', '-DPOSE_TMA_WPM=2', '-DPOSE_TMA_MINB_GRAD=3', '-DPOSE_TMA_MINB_RO=3'], (GD, G, L, LD)),
 }
-FLAGS = {GD: 1 | 4, G: 1, L: 0, LD: 4}
+FLAGS = {GD: 1 | 4 | 8, G: 1 | 8, L: 0 | 8, LD: 4 | 8}        # | 8: POSE_F_TMA (bulk-async staged kernels)
+
+
+def _build_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pose_b200_build", os.path.join(ROOT, "pytorch-pose-estimation_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def build():
+    """one library per variant: only api_sbp.cu is recompiled with the variant's knobs, the other units come from the object cache"""
+    from concurrent.futures import ThreadPoolExecutor
+    bm = _build_module()
     os.makedirs(OUT, exist_ok=True)
-    procs = [(n, subprocess.Popen(NVCC + k + ["-Xptxas", "-v", "-o", os.path.join(OUT, f"sbp_{n}.so"), SRC], stdout=subprocess.PIPE,
-                                  stderr=subprocess.STDOUT, text=True)) for n, (k, _) in VARIANTS.items()]
-    for n, p in procs:
-        out, _ = p.communicate()
-        spills = [ln for ln in out.splitlines() if "spill" in ln and "0 bytes spill stores, 0 bytes spill loads" not in ln]
-        print(n, "ok" if p.returncode == 0 else "FAILED\n" + out[-2000:], f"({len(spills)} kernels with spills)")
+    bm.build()                                            # the tree library first: fills the object cache for the shared units
+
+    def one(item):
+        n, (k, _) = item
+        try:
+            bm.build_library(os.path.join(OUT, f"sbp_{n}.so"), {"api_sbp.cu": k})
+            log = bm.ptxas_log("api_sbp.cu", k)
+            spills = [ln for ln in log.splitlines() if "spill" in ln and "0 bytes spill stores, 0 bytes spill loads" not in ln]
+            return f"{n} ok ({len(spills)} kernels with spills)"
+        except RuntimeError as e:
+            return f"{n} FAILED\n{str(e)[-2000:]}"
+    with ThreadPoolExecutor(max_workers=max(2, (os.cpu_count() or 4) - 1)) as pool:
+        for line in pool.map(one, VARIANTS.items()):
+            print(line, flush=True)
 
 
 def run(reps):
@@ -57,12 +74,13 @@ def run(reps):
     kp = torch.stack([torch.rand(B, K, device=dev, generator=gen, dtype=torch.float64) * W,
                       torch.rand(B, K, device=dev, generator=gen, dtype=torch.float64) * H], -1)
     kp[torch.rand(B, K, device=dev, generator=gen) >= 0.85] = -1
-    lut = torch.from_numpy(_gauss_template(2).astype("float32")).to(dev)
+    import numpy as np
+    lut = torch.from_numpy(np.pad(_gauss_template(2).astype("float32"), ((0, 1), (4, 4)))).to(dev)
     dl = torch.empty_like(logits)
     joints = torch.empty(B, K, 3, device=dev)
     loss = torch.empty((), device=dev)
     num = torch.empty(2, dtype=torch.float64, device=dev)
-    ws = torch.empty(1 << 17, dtype=torch.uint8, device=dev)
+    ws = torch.empty(int(_cabi.lib().pose_sbp_fused_workspace_bytes(B, K)), dtype=torch.uint8, device=dev)
     st = _cabi.stream_ptr(dev)
     res, refs = {}, {}
     tree = os.path.join(ROOT, "pytorch-pose-estimation_b200", "libpose_b200.so")

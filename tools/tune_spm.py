@@ -14,28 +14,45 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "build", "tune")
-SRC = os.path.join(ROOT, "pytorch-pose-estimation_b200", "csrc", "api.cu")
-NVCC = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
-# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: 8 stream + 4 patch warps per CTA, MINB=2, U=4 (grad), U_RO=4, U_RENDER=8.
+# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: 256 threads, MINB=4, U=2 (grad), U_RO=8, U_RENDER=8, NPRE=3.
 VARIANTS = {
-    "np2_m3": ["-DPOSE_SPM_PATCH_WARPS=2", "-DPOSE_SPM_FUSED_MINB=3"],
-    "np4_m3": ["-DPOSE_SPM_FUSED_MINB=3"],
-    "np8_m2": ["-DPOSE_SPM_PATCH_WARPS=8"],
-    "np2_m2": ["-DPOSE_SPM_PATCH_WARPS=2"],
-    "np4_m2_u8": ["-DPOSE_SPM_FUSED_U=8", "-DPOSE_SPM_FUSED_U_RO=8", "-DPOSE_SPM_FUSED_U_RENDER=16"],
-    "np4_m2_u2": ["-DPOSE_SPM_FUSED_U=2", "-DPOSE_SPM_FUSED_U_RO=2", "-DPOSE_SPM_FUSED_U_RENDER=4"],
-    "np1_m4": ["-DPOSE_SPM_PATCH_WARPS=1", "-DPOSE_SPM_FUSED_MINB=4"],
+    "m3": ["-DPOSE_SPM_FUSED_MINB=3"],
+    "m5": ["-DPOSE_SPM_FUSED_MINB=5"],
+    "u4": ["-DPOSE_SPM_FUSED_U=4"],
+    "u1": ["-DPOSE_SPM_FUSED_U=1"],
+    "ro4": ["-DPOSE_SPM_FUSED_U_RO=4"],
+    "render4": ["-DPOSE_SPM_FUSED_U_RENDER=4"],
+    "npre2": ["-DPOSE_SPM_PATCH_NPRE=2"],
+    "npre4": ["-DPOSE_SPM_PATCH_NPRE=4"],
 }
 
 
+def _build_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pose_b200_build", os.path.join(ROOT, "pytorch-pose-estimation_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def build():
+    """one library per variant: only api_spm.cu is recompiled with the variant's knobs, the other units come from the object cache"""
+    from concurrent.futures import ThreadPoolExecutor
+    bm = _build_module()
     os.makedirs(OUT, exist_ok=True)
-    procs = [(n, subprocess.Popen(NVCC + k + ["-o", os.path.join(OUT, f"spm_{n}.so"), SRC], stdout=subprocess.PIPE,
-                                  stderr=subprocess.STDOUT, text=True)) for n, k in VARIANTS.items()]
-    for n, p in procs:
-        out, _ = p.communicate()
-        print(n, "ok" if p.returncode == 0 else "FAILED\n" + out)
+    bm.build()
+
+    def one(item):
+        n, k = item
+        try:
+            bm.build_library(os.path.join(OUT, f"spm_{n}.so"), {"api_spm.cu": k})
+            return f"{n} ok"
+        except RuntimeError as e:
+            return f"{n} FAILED\n{str(e)[-2000:]}"
+    with ThreadPoolExecutor(max_workers=max(2, (os.cpu_count() or 4) - 1)) as pool:
+        for line in pool.map(one, VARIANTS.items()):
+            print(line, flush=True)
 
 
 def run(check):
