@@ -519,7 +519,7 @@ def run_cuda(args):
                        "kp_dtype": "f64", "sigmoid_ref": pb._cabi.DEFAULT_SIGMOID_REF, "loss": loss_ref, "cuda_graph": graph is not None,
                        "cpu_affinity": affinity},
             "eager_ms_per_step": eager_ms,
-            "roofline": {"bound": "hbm", "kernel": "sbp_fused_kernel<4,RENDER,GRAD,DECODE> (+ its 1-CTA loss-reduce epilogue launch)",
+            "roofline": {"bound": "hbm", "kernel": "sbp_fused_tma_kernel<GRAD,DECODE> (bulk-async staged, one 64-thread CTA per heat map; + its epilogue launch: two-level loss reduce + back-projection)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "peak_source": peak_src, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": BYTES_FUSED * B * K},

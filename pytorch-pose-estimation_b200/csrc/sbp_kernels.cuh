@@ -132,25 +132,25 @@ __device__ __forceinline__ bool patch_values(const Patch& p, const float* __rest
 // ---------------------------------------------------------------- argmax of sigmoid(x): search in logit space, rank with the reference's sigmoid
 // nms_sbp (utils/sbp_utils.py:71-80) takes the first row-major index of the largest sigmoid VALUE, and fp32 sigmoid is
 // many-to-one, so which neighbours tie depends on the sigmoid implementation to the last bit (common.cuh).  The streaming
-// part therefore never evaluates a sigmoid for the decode: each thread tracks, per 128-bit vector, the largest logit of its
-// share of the map (value, vector index) and the second-largest vector maximum.  Each WARP then derives a candidate window
-// [lo, m_w] from its own maximum m_w (sigmoid_window_lo: nothing below lo can reach sigmoid_ref(m_w) -- true for any subset
-// of the map), ranks its candidates -- almost always exactly one element, re-read from L2 -- with the reference's own sigmoid
-// (sigmoid_ref, bit-exact, also the reported confidence) and offers its winner to the CTA through ONE 64-bit shared-memory
-// atomicMax on (ordered value, ~index): larger value first, then the smaller flat index.  The maximum over the warps'
-// winners is the map's argmax, so the CTA needs no second barrier and no block-wide maximum.
+// part therefore never evaluates a sigmoid for the decode and does not even track an index: a thread keeps the running
+// maximum of the logits it sees (one FMNMX3 per two elements).  At the end of the map each WARP derives a candidate window
+// [lo, m_w] from its own maximum m_w (sigmoid_window_lo: nothing below lo can reach sigmoid_ref(m_w) -- true for any subset of
+// the map), finds the lanes whose maximum lies in it -- almost always exactly one -- and re-reads THOSE lanes' vectors
+// cooperatively (lane i takes the owner's i-th vector; shared memory or L2); elements inside the window are ranked with the
+// reference's own sigmoid (sigmoid_ref, bit-exact, also the reported confidence) through a 64-bit atomicMax in shared memory on
+// (ordered value, ~index): larger value first, then the smaller flat index.  The maximum over the warps' winners is the map's
+// argmax, so the CTA needs no block-wide maximum and no extra barrier.  (r02 history: tracking (value, vector index, second
+// best) per vector cost 7-8 ALU instructions per vector and made the staged kernels issue-bound: grad+decode 278 vs 263 us.)
 template <int V>
 struct ArgTrack {
-    float best, second;     // largest / second-largest vector maximum seen by this thread (NaNs ignored)
-    int bestvi;             // vector index of `best` (first occurrence)
-    __device__ __forceinline__ void reset() { best = second = -INFINITY; bestvi = 0; }
-    template <bool SIG>
-    __device__ __forceinline__ void push(const float (&x)[V], int vi) {
-        float vm = x[0];
+    float best;             // largest logit seen by this thread (NaNs ignored)
+    __device__ __forceinline__ void reset() { best = -INFINITY; }
+    __device__ __forceinline__ void push(const float (&x)[V]) {
+        if (V == 4) best = fmaxf(fmaxf(best, fmaxf(x[0], x[1])), fmaxf(x[2], x[V - 1]));
+        else {
 #pragma unroll
-        for (int j = 1; j < V; ++j) vm = fmaxf(vm, x[j]);
-        if (SIG) second = fmaxf(second, fminf(vm, best));
-        if (vm > best) { best = vm; bestvi = vi; }
+            for (int j = 0; j < V; ++j) best = fmaxf(best, x[j]);
+        }
     }
 };
 
@@ -160,40 +160,50 @@ __device__ __forceinline__ unsigned long long arg_key(float f, int i) {
     return ((unsigned long long)float_key(f + 0.0f) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
 }
 
-// Warp-level resolution; every lane of the warp calls it.  `vi0`/`vstride`: the warp's lanes own vectors vi0 + lane + k*vstride.
-// Offers the warp's winner (if any) to *key.  SIG == false (heat maps that are already activated, DecodeSBP.pred == False):
-// candidates are the elements equal to the warp maximum.
+// Warp-level resolution; every lane of the warp calls it.  The warp's lane l owns vectors first_vi(l) + k*vstride with
+// first_vi(l) = first_vi0 + l (k = 0, 1, ...; < nvec).  Offers the warp's winner (if any) to *key.
+// SIG == false (heat maps that are already activated, DecodeSBP.pred == False): candidates are the elements equal to the
+// warp maximum.
 template <int V, bool SIG>
-__device__ __forceinline__ void warp_offer_argmax(const ArgTrack<V>& a, const float* __restrict__ src, int nvec, int first_vi, int vstride,
+__device__ __forceinline__ void warp_offer_argmax(const ArgTrack<V>& a, const float* __restrict__ src, int nvec, int first_vi0, int vstride,
                                                   int sig_ref, unsigned long long* key) {
+    const int lane = threadIdx.x & 31;
     const float m = warp_max(a.best);
     float lo = m;
-    bool again = false;
     if (SIG) {
         lo = sigmoid_window_lo(m);
         // m <= -80 (or no finite element at all): the references' results are denormal / zero there and the error model of
         // the window does not hold -- rank every element of the warp's share
-        const bool degenerate = !(m > -80.0f);
-        if (degenerate) lo = -INFINITY;
-        again = degenerate || __any_sync(FULL_MASK, a.second >= lo);
+        if (!(m > -80.0f)) lo = -INFINITY;
     }
+    unsigned owners = __ballot_sync(FULL_MASK, a.best >= lo);
     unsigned long long k = 0ull;
-    if (!again) {
-        // candidates of this lane: elements of its best vector inside the window (one 16-byte re-read, L2)
-        if (a.best >= lo) {
-            float x[V];
-            Vec<V>::load_any(src, a.bestvi, x);
+    if (__popc(owners) <= 2) {
+        // the usual case: one lane (rarely two) holds the maximum -- the warp reads that lane's vectors together
+        while (owners) {                                        // warp-uniform
+            const int o = __ffs((int)owners) - 1;
+            owners &= owners - 1u;
+            for (int vi = first_vi0 + o + vstride * lane; vi < nvec; vi += vstride * 32) {
+                float x[V];
+                Vec<V>::load_any(src, vi, x);
 #pragma unroll
-            for (int j = 0; j < V; ++j)
-                if (x[j] >= lo) k = max(k, arg_key(SIG ? sigmoid_ref(x[j], sig_ref) : x[j], a.bestvi * V + j));
+                for (int j = 0; j < V; ++j)
+                    if (x[j] >= lo) k = max(k, arg_key(SIG ? sigmoid_ref(x[j], sig_ref) : x[j], vi * V + j));
+            }
         }
-    } else {
-        for (int vi = first_vi; vi < nvec; vi += vstride) {
+    } else if (a.best >= lo) {
+        // plateaus (an all-zero target map, saturated or constant logits): every owner scans its own vectors, in index order;
+        // without an activation all candidates carry the same value m, so a lane's first hit is its best
+        bool hit = false;
+        for (int vi = first_vi0 + lane; vi < nvec && !hit; vi += vstride) {
             float x[V];
             Vec<V>::load_any(src, vi, x);
 #pragma unroll
             for (int j = 0; j < V; ++j)
-                if (x[j] >= lo) k = max(k, arg_key(SIG ? sigmoid_ref(x[j], sig_ref) : x[j], vi * V + j));
+                if (x[j] >= lo && !hit) {
+                    k = max(k, arg_key(SIG ? sigmoid_ref(x[j], sig_ref) : x[j], vi * V + j));
+                    if (!SIG) hit = true;
+                }
         }
     }
     if (k != 0ull) atomicMax(key, k);
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE_
             const int vi = b0 + tid + kSbpThreads * u;
             if (vi >= nvec) break;
             float g[V];
-            if (DEC) arg.template push<true>(xv[u], vi);
+            if (DEC) arg.push(xv[u]);
             if (TGT == TGT_RENDER) {
                 render_loss_vec<V, GRAD, WTGT, SHARE>(xv[u], g, tv[u], vi, s_patch, P.lut, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
             } else {
@@ -437,7 +447,7 @@ __global__ void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE_
     aneg = warp_sum(aneg);
     arem = warp_sum(arem);
     if (lane == 0) { s_sum[wid][0] = apos; s_sum[wid][1] = aneg; s_sum[wid][2] = arem; }
-    if (DEC) warp_offer_argmax<V, true>(arg, lg, nvec, tid, kSbpThreads, P.sig_ref, &s_key);
+    if (DEC) warp_offer_argmax<V, true>(arg, lg, nvec, wid * 32, kSbpThreads, P.sig_ref, &s_key);
     __syncthreads();
     if (tid == 0) {
         double a = 0.0, b = 0.0, r = 0.0;
@@ -460,26 +470,34 @@ __global__ void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE_
 // every thread's prologue and tail (index arithmetic, three warp reductions, the argmax offer) is paid for just 3 vectors:
 // 292 instructions per thread and map, twice the r01 kernel's count per map -- ncu: issue slots 78-83 % busy, DRAM 57 %.
 // Here the maps in flight live in SHARED MEMORY: one thread issues a cp.async.bulk (UBLKCP, completion on an mbarrier) for
-// each of the CTA's POSE_TMA_MPC consecutive maps the moment the CTA starts; POSE_TMA_WPM warps then work on each map (all
+// each of the CTA's POSE_TMA_MPC_* consecutive maps the moment the CTA starts; POSE_TMA_WPM warps then work on each map (all
 // maps of the CTA concurrently), one 128-bit vector per thread at a time out of shared memory, so the per-thread overhead is
 // spread over 12-24 vectors and the number of maps in flight is set by shared memory (18 maps fit), not by registers.
 // The arithmetic per element is that of sbp_fused_kernel, so dlogits and joints are bit-identical (a GPU test compares the
 // two); the fp32 partial sums of a map are grouped differently (loss equal to ~1e-7).  Candidates of the argmax are re-read
 // from shared memory.
-#ifndef POSE_TMA_MPC
-#define POSE_TMA_MPC 4          // maps per CTA
-#endif
+// CTA shape per variant class (tools/tune_fused.py, profiles/r02_tune_tma_*.log; 69 632 maps): the kernels that write dlogits
+// run best as 64-thread CTAs with ONE map, 16 of them per SM (grad+decode 259.3 us, grad 259.1; 2 maps per CTA: 267 / 260; 4:
+// 277 / 265), the read-only ones as 256-thread CTAs with 4 maps (loss 136 us, loss+decode 158, decode 120.9).  Always 2 warps
+// per map: 1 warp per map loses 25 % (grad), 3-4 warps per map pay the per-thread overhead too often.
 #ifndef POSE_TMA_WPM
 #define POSE_TMA_WPM 2          // warps per map
 #endif
+#ifndef POSE_TMA_MPC_GRAD
+#define POSE_TMA_MPC_GRAD 1     // maps per CTA, kernels that write dlogits
+#endif
+#ifndef POSE_TMA_MPC_RO
+#define POSE_TMA_MPC_RO 4       // maps per CTA, read-only kernels
+#endif
 #ifndef POSE_TMA_MINB_GRAD
-#define POSE_TMA_MINB_GRAD 4
+#define POSE_TMA_MINB_GRAD 16
 #endif
 #ifndef POSE_TMA_MINB_RO
 #define POSE_TMA_MINB_RO 4
 #endif
-constexpr int kTmaThreads = 32 * POSE_TMA_WPM * POSE_TMA_MPC;
-__host__ __device__ inline size_t sbp_tma_smem_bytes(int HW) { return (size_t)POSE_TMA_MPC * (size_t)HW * sizeof(float); }
+__host__ __device__ constexpr int tma_mpc(bool grad) { return grad ? POSE_TMA_MPC_GRAD : POSE_TMA_MPC_RO; }
+__host__ __device__ constexpr int tma_threads(bool grad) { return 32 * POSE_TMA_WPM * tma_mpc(grad); }
+__host__ __device__ inline size_t sbp_tma_smem_bytes(int HW, bool grad) { return (size_t)tma_mpc(grad) * (size_t)HW * sizeof(float); }
 
 __device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -511,8 +529,8 @@ __device__ __forceinline__ void tma_stage_maps(float* tiles, unsigned long long*
 }
 
 template <bool GRAD, bool DEC>
-__global__ void __launch_bounds__(kTmaThreads, GRAD ? POSE_TMA_MINB_GRAD : POSE_TMA_MINB_RO) sbp_fused_tma_kernel(SbpFusedParams P) {
-    constexpr int V = 4, MPC = POSE_TMA_MPC, WPM = POSE_TMA_WPM, TPM = 32 * WPM;
+__global__ void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD : POSE_TMA_MINB_RO) sbp_fused_tma_kernel(SbpFusedParams P) {
+    constexpr int V = 4, MPC = tma_mpc(GRAD), WPM = POSE_TMA_WPM, TPM = 32 * WPM;
     extern __shared__ __align__(128) float tiles[];            // MPC maps of HW floats
     __shared__ __align__(8) unsigned long long s_bar[MPC];
     __shared__ Patch s_patch[MPC];
@@ -549,7 +567,7 @@ __global__ void __launch_bounds__(kTmaThreads, GRAD ? POSE_TMA_MINB_GRAD : POSE_
         for (int vi = t; vi < nvec; vi += TPM) {
             float x[V], g[V], unused[V];
             Vec<V>::load_any(tile, vi, x);
-            if (DEC) arg.template push<true>(x, vi);
+            if (DEC) arg.push(x);
             render_loss_vec<V, GRAD, false, SHARE>(x, g, unused, vi, s_patch[k], P.lut, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
             if (GRAD) Vec<V>::store(dl, vi, g);
         }
@@ -557,7 +575,7 @@ __global__ void __launch_bounds__(kTmaThreads, GRAD ? POSE_TMA_MINB_GRAD : POSE_
         aneg = warp_sum(aneg);
         arem = warp_sum(arem);
         if (lane == 0) { s_sum[k][ws][0] = apos; s_sum[k][ws][1] = aneg; s_sum[k][ws][2] = arem; }
-        if (DEC) warp_offer_argmax<V, true>(arg, tile, nvec, t, TPM, P.sig_ref, &s_key[k]);
+        if (DEC) warp_offer_argmax<V, true>(arg, tile, nvec, ws * 32, TPM, P.sig_ref, &s_key[k]);
     }
     __syncthreads();
     if (tid < nmap) {
@@ -762,10 +780,10 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_MAP_MINB_RO) sbp_decode_kern
         for (int u = 0; u < U; ++u) {
             const int vi = b0 + tid + kSbpThreads * u;
             if (vi >= nvec) break;
-            arg.template push<SIG>(xv[u], vi);
+            arg.push(xv[u]);
         }
     }
-    warp_offer_argmax<V, SIG>(arg, src, nvec, tid, kSbpThreads, P.sig_ref, &s_key);
+    warp_offer_argmax<V, SIG>(arg, src, nvec, (tid >> 5) * 32, kSbpThreads, P.sig_ref, &s_key);
     __syncthreads();
     if (tid == 0) {
         float best;
@@ -787,11 +805,11 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_MAP_MINB_RO) sbp_decode_kern
     }
 }
 
-// bulk-async staged form of sbp_decode_kernel (16-byte aligned maps): POSE_TMA_MPC maps per CTA, POSE_TMA_WPM warps per map,
+// bulk-async staged form of sbp_decode_kernel (16-byte aligned maps): POSE_TMA_MPC_RO maps per CTA, POSE_TMA_WPM warps per map,
 // see sbp_fused_tma_kernel
 template <bool SIG>
-__global__ void __launch_bounds__(kTmaThreads, POSE_TMA_MINB_RO) sbp_decode_tma_kernel(SbpDecodeParams P) {
-    constexpr int V = 4, MPC = POSE_TMA_MPC, WPM = POSE_TMA_WPM, TPM = 32 * WPM;
+__global__ void __launch_bounds__(tma_threads(false), POSE_TMA_MINB_RO) sbp_decode_tma_kernel(SbpDecodeParams P) {
+    constexpr int V = 4, MPC = tma_mpc(false), WPM = POSE_TMA_WPM, TPM = 32 * WPM;
     extern __shared__ __align__(128) float tiles[];
     __shared__ __align__(8) unsigned long long s_bar[MPC];
     __shared__ unsigned long long s_key[MPC];
@@ -812,9 +830,9 @@ __global__ void __launch_bounds__(kTmaThreads, POSE_TMA_MINB_RO) sbp_decode_tma_
         for (int vi = t; vi < nvec; vi += TPM) {
             float x[V];
             Vec<V>::load_any(tile, vi, x);
-            arg.template push<SIG>(x, vi);
+            arg.push(x);
         }
-        warp_offer_argmax<V, SIG>(arg, tile, nvec, t, TPM, P.sig_ref, &s_key[k]);
+        warp_offer_argmax<V, SIG>(arg, tile, nvec, ws * 32, TPM, P.sig_ref, &s_key[k]);
     }
     __syncthreads();
     if (tid < nmap) {

@@ -20,16 +20,15 @@ OUT = os.path.join(ROOT, "build", "tune")
 # name -> (-D knobs, kernels worth timing for it).  Shipped ("tree"): see the POSE_MAP_* defaults in csrc/sbp_kernels.cuh.
 GD, G, L, LD = "grad+decode", "grad", "loss", "loss+decode"
 VARIANTS = {
-    "w2m2": (['-DPOSE_TMA_MPC=2', '-DPOSE_TMA_WPM=2', '-DPOSE_TMA_MINB_GRAD=8', '-DPOSE_TMA_MINB_RO=8'], (GD, G, L, LD)),
-    "w2m3": (['-DPOSE_TMA_MPC=3', '-DPOSE_TMA_WPM=2', '-DPOSE_TMA_MINB_GRAD=6', '-DPOSE_TMA_MINB_RO=6'], (GD, G, L, LD)),
-    "w2m6": (['-DPOSE_TMA_MPC=6', '-DPOSE_TMA_WPM=2', '-DPOSE_TMA_MINB_GRAD=3', '-DPOSE_TMA_MINB_RO=3'], (GD, G, L, LD)),
-    "w1m4": (['-DPOSE_TMA_MPC=4', '-DPOSE_TMA_WPM=1', '-DPOSE_TMA_MINB_GRAD=4', '-DPOSE_TMA_MINB_RO=4'], (GD, G, L, LD)),
-    "w1m6": (['-DPOSE_TMA_MPC=6', '-DPOSE_TMA_WPM=1', '-DPOSE_TMA_MINB_GRAD=3', '-DPOSE_TMA_MINB_RO=3'], (GD, G, L, LD)),
-    "w1m8": (['-DPOSE_TMA_MPC=8', '-DPOSE_TMA_WPM=1', '-DPOSE_TMA_MINB_GRAD=2', '-DPOSE_TMA_MINB_RO=2'], (GD, G, L, LD)),
-    "w4m2": (['-DPOSE_TMA_MPC=2', '-DPOSE_TMA_WPM=4', '-DPOSE_TMA_MINB_GRAD=4', '-DPOSE_TMA_MINB_RO=4'], (GD, G, L, LD)),
-    "w4m3": (['-DPOSE_TMA_MPC=3', '-DPOSE_TMA_WPM=4', '-DPOSE_TMA_MINB_GRAD=3', '-DPOSE_TMA_MINB_RO=3'], (GD, G, L, LD)),
-    "w3m3": (['-DPOSE_TMA_MPC=3', '-DPOSE_TMA_WPM=3', '-DPOSE_TMA_MINB_GRAD=4', '-DPOSE_TMA_MINB_RO=4'], (GD, G, L, LD)),
-    "w2m4_b3": (['-DPOSE_TMA_MPC=4', '-DPOSE_TMA_WPM=2', '-DPOSE_TMA_MINB_GRAD=3', '-DPOSE_TMA_MINB_RO=3'], (GD, G, L, LD)),
+    "g_m1": (["-DPOSE_TMA_MPC_GRAD=1", "-DPOSE_TMA_MINB_GRAD=16"], (GD, G)),
+    "g_m2_b6": (["-DPOSE_TMA_MINB_GRAD=6"], (GD, G)),
+    "g_m2_b10": (["-DPOSE_TMA_MINB_GRAD=10"], (GD, G)),
+    "g_m3": (["-DPOSE_TMA_MPC_GRAD=3", "-DPOSE_TMA_MINB_GRAD=5"], (GD, G)),
+    "g_w1m4": (["-DPOSE_TMA_WPM=1", "-DPOSE_TMA_MPC_GRAD=4", "-DPOSE_TMA_MINB_GRAD=8"], (GD, G)),
+    "ro_m3": (["-DPOSE_TMA_MPC_RO=3", "-DPOSE_TMA_MINB_RO=5"], (L, LD)),
+    "ro_m6": (["-DPOSE_TMA_MPC_RO=6", "-DPOSE_TMA_MINB_RO=3"], (L, LD)),
+    "ro_m8": (["-DPOSE_TMA_MPC_RO=8", "-DPOSE_TMA_MINB_RO=2"], (L, LD)),
+    "ro_m4_b3": (["-DPOSE_TMA_MINB_RO=3"], (L, LD)),
 }
 FLAGS = {GD: 1 | 4 | 8, G: 1 | 8, L: 0 | 8, LD: 4 | 8}        # | 8: POSE_F_TMA (bulk-async staged kernels)
 
