@@ -182,10 +182,14 @@ int pose_sbp_backproject(const float* joints, const double* bbox, float* packed_
 /* ---- SPM render -- SPMHeatmapGenerator/MaskGenerator/DisplacementGenerator
  *      utils/spm_utils.py:16-95 + concat dataset/spm_coco_dataset.py:77-86, batched.
  * centers [N][Pmax][2] int64, joints [N][Pmax][K][2] int64, counts [N] int32 (persons per image).
- * target [N][1+2K][R][R] fully overwritten. */
+ * target [N][1+2K][R][R] fully overwritten.
+ * workspace (may be NULL): pose_spm_fused_workspace_bytes(N, K, R) bytes, 16-byte aligned -- with it (and Pmax <= 64) the
+ * target is written in ONE pass by the render-only form of the fused path (a per-image geometry pre-pass + a pure write
+ * stream); without it the older zero-fill + patch pair runs (any number of persons).  Same bits either way. */
 int pose_spm_render(const long long* centers, const long long* joints, const int* counts,
                     float* target, int N, int Pmax, int K, int R, double sigma,
-                    const float* lut, int lut_n, pose_stream_t stream);
+                    const float* lut, int lut_n, void* workspace, unsigned long long workspace_bytes,
+                    pose_stream_t stream);
 
 /* ---- SPM loss fwd(+bwd) -- SPMLoss.forward models/loss/spm_loss.py:23-105.
  * logits/target/dlogits [N][1+2K][R][R]; loss = (lambda_root*S_root + lambda_disp*S_disp)*inv_norm,
@@ -201,8 +205,12 @@ int pose_spm_loss(const float* logits, const float* target, float* dlogits,
  *      (+ autograd backward): the target never touches HBM.  Persons as for pose_spm_render (Pmax <= 64);
  *      logits/dlogits/target_out [N][1+2K][R][R].  flags: POSE_F_GRAD (write dlogits), POSE_F_TARGET_OUT (also
  *      materialise the rendered target, bit-identical to pose_spm_render).  loss = (lambda_root*S_root +
- *      lambda_disp*S_disp)*inv_norm, inv_norm = 1/B_global; loss_num_out [2] fp64 = (S_root, S_disp). */
-unsigned long long pose_spm_fused_workspace_bytes(void);
+ *      lambda_disp*S_disp)*inv_norm, inv_norm = 1/B_global; loss_num_out [2] fp64 = (S_root, S_disp).
+ *      Three launches: a geometry pre-pass (one CTA per image: person boxes, covered-quad bits, a byte of geometry per
+ *      pixel -> workspace), the streaming kernel (one CTA per 16 KB of a channel plane, logits staged with bulk async
+ *      copies) and the deterministic two-level loss reduction.
+ *      workspace: pose_spm_fused_workspace_bytes(N, K, R) (loss pairs + ~20 KB of geometry per image at R = 128). */
+unsigned long long pose_spm_fused_workspace_bytes(int N, int K, int R);
 int pose_spm_fused(const float* logits, const long long* centers, const long long* joints, const int* counts,
                    float* dlogits, float* target_out, float* loss_out, double* loss_num_out,
                    int N, int Pmax, int K, int R, double sigma, const float* lut, int lut_n,

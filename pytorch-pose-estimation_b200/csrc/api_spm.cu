@@ -4,10 +4,59 @@
 
 using namespace pose_host;
 
+namespace {
+// workspace of the fused / single-pass render path:
+//   [units][2] fp64 loss pairs | [R][2] slice sums | ticket (16 B) | [2R+1] fp64 quotient table | per-image geometry records
+struct SpmWs {
+    double* partials; double* slices; unsigned int* ticket; double* div_tab; unsigned char* geom;
+    long long units; int slices_n; unsigned long long bytes;
+};
+SpmWs spm_ws_layout(void* base, int N, int K, int R) {
+    SpmWs w;
+    w.units = pose::spm_units(N, K, R);
+    w.slices_n = pose::reduce_slices(w.units);
+    unsigned long long off = 0;
+    const uintptr_t b = reinterpret_cast<uintptr_t>(base);          // (base may be NULL: size query)
+    w.partials = reinterpret_cast<double*>(b + off); off += (unsigned long long)w.units * 16;
+    w.slices = reinterpret_cast<double*>(b + off); off += (unsigned long long)w.slices_n * 16;
+    w.ticket = reinterpret_cast<unsigned int*>(b + off); off += 16;
+    w.div_tab = reinterpret_cast<double*>(b + off); off += (unsigned long long)(2 * R + 1) * 8;
+    off = (off + 255) / 256 * 256;
+    w.geom = reinterpret_cast<unsigned char*>(b + off); off += (unsigned long long)(N > 0 ? N : 0) * pose::spm_geom_layout(R).stride;
+    w.bytes = off;
+    return w;
+}
+
+void fill_fused_params(pose::SpmFusedParams& P, const SpmWs& w, int N, int Pmax, int K, int R, double sigma, const float* lut, int lut_n) {
+    P.lut = lut; P.lut_n = lut_n;
+    P.three_sigma = 3 * sigma; P.half = (int)((6 * sigma + 2) / 2);
+    P.z = std::sqrt((double)((long long)R * R + (long long)R * R));
+    P.partials = w.partials; P.ticket = w.ticket; P.geom = w.geom; P.div_tab = w.div_tab; P.gl = pose::spm_geom_layout(R);
+    P.N = N; P.Pmax = Pmax; P.K = K; P.R = R; P.quads = R * R / 4; P.div_qpr = make_div(R / 4);
+    P.wpr = (R / 4 + 31) / 32;
+    P.div_n = R <= 1024 ? 2 * R + 1 : 0;
+}
+
+// geometry pre-pass + the unit kernel (programmatic dependent launch: the unit CTAs start their bulk loads while the pre-pass drains)
+template <bool LOSS, bool GRAD, bool WTGT>
+int launch_spm_units(const pose::SpmFusedParams& P, const SpmWs& w, cudaStream_t st, const char* what) {
+    const size_t gsmem = pose::spm_geom_smem_bytes(P.R, P.lut_n);
+    if (resident_ctas(pose::spm_geometry_kernel, pose::kSpmGeomThreads, gsmem, what) == 0) return last_code();
+    pose::spm_geometry_kernel<<<P.N, pose::kSpmGeomThreads, gsmem, st>>>(P);
+    if (int rc = check_launch("spm_geometry")) return rc;
+    const size_t smem = pose::spm_unit_smem_bytes(LOSS);
+    if (resident_ctas(pose::spm_unit_kernel<LOSS, GRAD, WTGT>, pose::kSpmUnitThreads, smem, what) == 0) return last_code();
+    if (w.units > 0x7fffffffll) return fail(POSE_EINVAL, "%s: %lld work units exceed one grid", what, w.units);
+    launch_pdl(pose::spm_unit_kernel<LOSS, GRAD, WTGT>, (unsigned)w.units, (unsigned)pose::kSpmUnitThreads, smem, st, P);
+    return check_launch(what);
+}
+}  // namespace
+
 extern "C" {
 
 int pose_spm_render(const long long* centers, const long long* joints, const int* counts, float* target, int N, int Pmax,
-                    int K, int R, double sigma, const float* lut, int lut_n, pose_stream_t stream) {
+                    int K, int R, double sigma, const float* lut, int lut_n, void* workspace, unsigned long long workspace_bytes,
+                    pose_stream_t stream) {
     if (N < 0 || Pmax < 0 || K <= 0 || R <= 0 || R % 4 != 0 || R > 2048) return fail(POSE_EINVAL, "spm_render: bad shape (R must be a multiple of 4)");
     if (!counts || !target || !lut || lut_n <= 0 || lut_n > 64 || !(sigma > 0.0) || (Pmax > 0 && (!centers || !joints)))
         return fail(POSE_EINVAL, "spm_render: bad argument");
@@ -20,30 +69,15 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
     P.N = N; P.Pmax = Pmax; P.K = K; P.R = R;
     const int quads = R * R / 4;
     static const bool two_pass = getenv("POSE_B200_SPM_RENDER_TWO_PASS") != nullptr;      // diagnostics: force the fill + patch pair (read once)
-    if (Pmax <= pose::kSpmFusedMaxPersons && !two_pass) {
-        // single pass: the render-only form of the fused kernel (linear write stream, covered pixels filled in by the same pass)
+    if (Pmax <= pose::kSpmFusedMaxPersons && !two_pass && workspace && workspace_bytes >= pose_spm_fused_workspace_bytes(N, K, R) &&
+        aligned16(workspace)) {
+        // single pass: the render-only form of the fused path (geometry pre-pass + one CTA per 16 KB unit, a pure write stream)
+        const SpmWs w = spm_ws_layout(workspace, N, K, R);
         pose::SpmFusedParams F;
         memset(&F, 0, sizeof(F));
-        F.target_out = target; F.centers = centers; F.joints = joints; F.counts = counts; F.lut = lut; F.lut_n = lut_n;
-        F.three_sigma = P.three_sigma; F.half = P.half; F.z = P.z;
-        F.N = N; F.Pmax = Pmax; F.K = K; F.R = R; F.quads = quads; F.div_qpr = make_div(R / 4);
-        F.wpr = (R / 4 + 31) / 32;
-        F.div_n = R <= 1024 ? 2 * R + 1 : 0;
-        const size_t fsmem = pose::spm_fused_smem_bytes(F.div_n, R, K, F.wpr, lut_n);
-        if (fsmem <= 200 * 1024) {
-            const int fchunk = pose::kSpmThreads * pose::spm_fused_u(false, true, false);
-            const long long funits = (long long)N * (1 + 2 * K) * ((quads + fchunk - 1) / fchunk);
-#define POSE_SPMR(RG, MP)                                                                                                      \
-    {                                                                                                                          \
-        const int fgrid = persistent_grid(pose::spm_fused_kernel<false, false, true, RG, MP>, pose::kSpmThreads, fsmem, funits, "spm_render"); \
-        if (fgrid == 0) return last_code();                                                                                    \
-        pose::spm_fused_kernel<false, false, true, RG, MP><<<fgrid, pose::kSpmThreads, fsmem, (cudaStream_t)stream>>>(F); \
-    }
-            if (pose::spm_fused_use_map(R)) { if (R % 128 == 0) POSE_SPMR(true, true) else POSE_SPMR(false, true) }
-            else { if (R % 128 == 0) POSE_SPMR(true, false) else POSE_SPMR(false, false) }
-#undef POSE_SPMR
-            return check_launch("spm_render(single pass)");
-        }
+        F.target_out = target; F.centers = centers; F.joints = joints; F.counts = counts;
+        fill_fused_params(F, w, N, Pmax, K, R, sigma, lut, lut_n);
+        return launch_spm_units<false, false, true>(F, w, (cudaStream_t)stream, "spm_render(single pass)");
     }
     const size_t smem = (size_t)lut_n * lut_n * sizeof(float);
     const long long units = (long long)N * (1 + 2 * K) * ((quads + pose::kSpmRenderChunk - 1) / pose::kSpmRenderChunk);
@@ -95,7 +129,10 @@ int pose_spm_loss(const float* logits, const float* target, float* dlogits, floa
     return pose_loss_reduce(P.partials, grid, 2ll, (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out, stream);
 }
 
-unsigned long long pose_spm_fused_workspace_bytes(void) { return (unsigned long long)pose::kMaxPartialBlocks * 2 * sizeof(double); }
+unsigned long long pose_spm_fused_workspace_bytes(int N, int K, int R) {
+    if (N < 0 || K <= 0 || R <= 0) return 0ull;
+    return spm_ws_layout(nullptr, N, K, R).bytes;
+}
 
 int pose_spm_fused(const float* logits, const long long* centers, const long long* joints, const int* counts, float* dlogits,
                    float* target_out, float* loss_out, double* loss_num_out, int N, int Pmax, int K, int R, double sigma,
@@ -106,9 +143,10 @@ int pose_spm_fused(const float* logits, const long long* centers, const long lon
     if (flags & ~(POSE_F_GRAD | POSE_F_TARGET_OUT)) return fail(POSE_EINVAL, "spm_fused: unsupported flags 0x%x", flags);
     const bool grad = flags & POSE_F_GRAD, wtgt = flags & POSE_F_TARGET_OUT;
     if (!loss_out && !loss_num_out) return fail(POSE_EINVAL, "spm_fused: no loss output");
-    if (!workspace || workspace_bytes < pose_spm_fused_workspace_bytes() || !aligned16(workspace)) return fail(POSE_EWORKSPACE, "spm_fused: workspace too small / unaligned");
+    if (!workspace || workspace_bytes < pose_spm_fused_workspace_bytes(N, K, R) || !aligned16(workspace))
+        return fail(POSE_EWORKSPACE, "spm_fused: workspace too small / unaligned (%llu bytes needed)", pose_spm_fused_workspace_bytes(N, K, R));
     cudaStream_t st = (cudaStream_t)stream;
-    int grid = 0;
+    const SpmWs w = spm_ws_layout(workspace, N, K, R);
     if (N > 0) {
         if (!logits || !counts || !lut || lut_n <= 0 || lut_n > 64 || !(sigma > 0.0) || (Pmax > 0 && (!centers || !joints)) ||
             (grad && !dlogits) || (wtgt && !target_out))
@@ -118,36 +156,22 @@ int pose_spm_fused(const float* logits, const long long* centers, const long lon
         pose::SpmFusedParams P;
         memset(&P, 0, sizeof(P));
         P.logits = logits; P.dlogits = dlogits; P.target_out = target_out;
-        P.centers = centers; P.joints = joints; P.counts = counts; P.lut = lut; P.lut_n = lut_n;
-        P.three_sigma = 3 * sigma; P.half = (int)((6 * sigma + 2) / 2);
-        P.z = std::sqrt((double)((long long)R * R + (long long)R * R));
-        P.partials = reinterpret_cast<double*>(workspace);
-        P.N = N; P.Pmax = Pmax; P.K = K; P.R = R; P.quads = R * R / 4; P.div_qpr = make_div(R / 4);
-        P.wpr = (R / 4 + 31) / 32;
-        P.div_n = R <= 1024 ? 2 * R + 1 : 0;
+        P.centers = centers; P.joints = joints; P.counts = counts;
+        fill_fused_params(P, w, N, Pmax, K, R, sigma, lut, lut_n);
         P.groot = (float)(2.0 * (double)lambda_root * inv_norm);
         P.gdisp = (float)((double)lambda_disp * inv_norm);
-        const size_t smem = pose::spm_fused_smem_bytes(P.div_n, R, K, P.wpr, lut_n);
-        if (smem > 200 * 1024) return fail(POSE_EINVAL, "spm_fused: R=%d K=%d needs %zu bytes of shared memory (use pose_spm_render + pose_spm_loss)", R, K, smem);
-        const int uchunk = pose::kSpmThreads * pose::spm_fused_u(grad, wtgt);
-        const long long units = (long long)N * (1 + 2 * K) * ((P.quads + uchunk - 1) / uchunk);
-#define POSE_SPMF3(G, T, RG, MP)                                                                                              \
-    {                                                                                                                          \
-        grid = persistent_grid(pose::spm_fused_kernel<true, G, T, RG, MP>, pose::kSpmThreads, smem, units, "spm_fused");  \
-        if (grid == 0) return last_code();                                                                                     \
-        pose::spm_fused_kernel<true, G, T, RG, MP><<<grid, pose::kSpmThreads, smem, st>>>(P);                             \
+        int rc;
+        if (grad && wtgt) rc = launch_spm_units<true, true, true>(P, w, st, "spm_fused");
+        else if (grad) rc = launch_spm_units<true, true, false>(P, w, st, "spm_fused");
+        else if (wtgt) rc = launch_spm_units<true, false, true>(P, w, st, "spm_fused");
+        else rc = launch_spm_units<true, false, false>(P, w, st, "spm_fused");
+        if (rc) return rc;
+        launch_pdl(pose::spm_loss_reduce_kernel, (unsigned)w.slices_n, 256u, 0, st, (const double*)w.partials, w.units, w.slices, w.ticket, w.slices_n,
+                   (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out);
+        return check_launch("spm_loss_reduce");
     }
-#define POSE_SPMF(G, T)                                                                                                        \
-    {                                                                                                                          \
-        if (pose::spm_fused_use_map(R)) { if (R % 128 == 0) POSE_SPMF3(G, T, true, true) else POSE_SPMF3(G, T, false, true) }  \
-        else { if (R % 128 == 0) POSE_SPMF3(G, T, true, false) else POSE_SPMF3(G, T, false, false) }                           \
-    }
-        if (grad && wtgt) POSE_SPMF(true, true) else if (grad) POSE_SPMF(true, false) else if (wtgt) POSE_SPMF(false, true) else POSE_SPMF(false, false)
-#undef POSE_SPMF3
-#undef POSE_SPMF
-        if (int rc = check_launch("spm_fused")) return rc;
-    }
-    return pose_loss_reduce((const double*)workspace, grid, 2ll, (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out, stream);
+    // an empty batch reduces zero pairs: loss 0
+    return pose_loss_reduce((const double*)workspace, 0, 2ll, (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out, stream);
 }
 
 int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* counts_total, int N, int Pmax, int K, int R,

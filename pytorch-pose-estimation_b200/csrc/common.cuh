@@ -182,6 +182,68 @@ __device__ __forceinline__ void warp_argmax_first(float& v, int& i) {
     }
 }
 
+// ---------------------------------------------------------------- loss reduction (deterministic, fixed order, no float atomics)
+// sum `n` (a, b) fp64 pairs, `stride` doubles apart, then loss = (w0*A + w1*B) * inv_norm.  Runs in one CTA.
+__device__ __forceinline__ void reduce_pairs_cta(const double* __restrict__ pairs, int n, long long stride, double w0, double w1,
+                                                 double inv_norm, float* __restrict__ loss_out, double* __restrict__ num_out) {
+    __shared__ double sa[256], sb[256];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) { a += __ldcg(pairs + i * stride); b += __ldcg(pairs + i * stride + 1); }
+    sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (num_out) { num_out[0] = sa[0]; num_out[1] = sb[0]; }
+        if (loss_out) loss_out[0] = (float)((w0 * sa[0] + w1 * sb[0]) * inv_norm);
+    }
+}
+
+// Two-level form for the per-map pairs of the fused kernel (69 632 of them at B = 4096): slice CTA r sums pairs
+// [r*kReduceSlice, (r+1)*kReduceSlice) -- 8 independent 16-byte loads per thread, then a fixed tree -- into slices[r]; the
+// slice CTA that finishes LAST (a ticket counter, zeroed by the fused kernel) returns true and goes on to add the R slice sums in
+// index order.  Which CTA is last varies from run to run; the order of every addition does not.
+constexpr int kReduceSlice = 2048;
+__host__ __device__ inline int reduce_slices(long long n_pairs) { return n_pairs <= kReduceSlice ? 1 : (int)((n_pairs + kReduceSlice - 1) / kReduceSlice); }
+
+__device__ __forceinline__ bool reduce_slice_and_elect(const double* __restrict__ pairs, long long n, double* __restrict__ slices,
+                                                       unsigned int* __restrict__ ticket, int R, int r) {
+    __shared__ double ta[256], tb[256];
+    __shared__ int s_last;
+    const double2* p2 = reinterpret_cast<const double2*>(pairs);
+    const long long i0 = (long long)r * kReduceSlice + threadIdx.x;
+    double2 v[kReduceSlice / 256];
+#pragma unroll
+    for (int k = 0; k < kReduceSlice / 256; ++k) {
+        const long long i = i0 + 256 * k;
+        v[k] = i < n ? __ldcg(p2 + i) : make_double2(0.0, 0.0);
+    }
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int k = 0; k < kReduceSlice / 256; ++k) { a += v[k].x; b += v[k].y; }
+    ta[threadIdx.x] = a; tb[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { ta[threadIdx.x] += ta[threadIdx.x + s]; tb[threadIdx.x] += tb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        slices[2 * r] = ta[0];
+        slices[2 * r + 1] = tb[0];
+        int last = 1;
+        if (R > 1) {
+            __threadfence();                                   // slice sum visible device-wide before the ticket is taken
+            last = atomicAdd(ticket, 1u) == (unsigned)(R - 1);
+            if (last) __threadfence();                         // ... and the others' sums before they are read
+        }
+        s_last = last;
+    }
+    __syncthreads();
+    return s_last != 0;
+}
+
 // ---------------------------------------------------------------- order-preserving float <-> uint key
 __device__ __forceinline__ uint32_t float_key(float f) {
     uint32_t b = __float_as_uint(f);
@@ -239,6 +301,21 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+
 
 // ---------------------------------------------------------------- multi-GPU exchange: control block and flags
 constexpr int kMaxPeers = 16;

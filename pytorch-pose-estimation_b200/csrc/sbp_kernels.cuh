@@ -499,20 +499,6 @@ __host__ __device__ constexpr int tma_mpc(bool grad) { return grad ? POSE_TMA_MP
 __host__ __device__ constexpr int tma_threads(bool grad) { return 32 * POSE_TMA_WPM * tma_mpc(grad); }
 __host__ __device__ inline size_t sbp_tma_smem_bytes(int HW, bool grad) { return (size_t)tma_mpc(grad) * (size_t)HW * sizeof(float); }
 
-__device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    }
-}
-
 // stage the CTA's maps: thread 0 initialises one mbarrier per map and issues the bulk copies (the caller's next CTA barrier
 // makes the initialised mbarriers visible to the waiting threads)
 __device__ __forceinline__ void tma_stage_maps(float* tiles, unsigned long long* bars, const float* __restrict__ src, long long map0, int nmap,
@@ -593,72 +579,11 @@ __global__ void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD :
     }
 }
 
-// ---------------------------------------------------------------- loss reduction (deterministic, fixed order, no float atomics)
-// sum `n` (a, b) fp64 pairs, `stride` doubles apart, then loss = (w0*A + w1*B) * inv_norm.  Runs in one CTA.
-__device__ __forceinline__ void reduce_pairs_cta(const double* __restrict__ pairs, int n, long long stride, double w0, double w1,
-                                                 double inv_norm, float* __restrict__ loss_out, double* __restrict__ num_out) {
-    __shared__ double sa[256], sb[256];
-    double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) { a += __ldcg(pairs + i * stride); b += __ldcg(pairs + i * stride + 1); }
-    sa[threadIdx.x] = a; sb[threadIdx.x] = b;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        if (num_out) { num_out[0] = sa[0]; num_out[1] = sb[0]; }
-        if (loss_out) loss_out[0] = (float)((w0 * sa[0] + w1 * sb[0]) * inv_norm);
-    }
-}
-
+// ---------------------------------------------------------------- loss reduction kernel (helpers: common.cuh)
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const double* __restrict__ pairs, int n, long long stride, double w0, double w1,
                                                           double inv_norm, float* __restrict__ loss_out, double* __restrict__ num_out) {
     pdl_wait();
     reduce_pairs_cta(pairs, n, stride, w0, w1, inv_norm, loss_out, num_out);
-}
-
-// Two-level form for the per-map pairs of the fused kernel (69 632 of them at B = 4096): slice CTA r sums pairs
-// [r*kReduceSlice, (r+1)*kReduceSlice) -- 8 independent 16-byte loads per thread, then a fixed tree -- into slices[r]; the
-// slice CTA that finishes LAST (a ticket counter, zeroed by the fused kernel) returns true and goes on to add the R slice sums in
-// index order.  Which CTA is last varies from run to run; the order of every addition does not.
-constexpr int kReduceSlice = 2048;
-__host__ __device__ inline int reduce_slices(long long n_pairs) { return n_pairs <= kReduceSlice ? 1 : (int)((n_pairs + kReduceSlice - 1) / kReduceSlice); }
-
-__device__ __forceinline__ bool reduce_slice_and_elect(const double* __restrict__ pairs, long long n, double* __restrict__ slices,
-                                                       unsigned int* __restrict__ ticket, int R, int r) {
-    __shared__ double ta[256], tb[256];
-    __shared__ int s_last;
-    const double2* p2 = reinterpret_cast<const double2*>(pairs);
-    const long long i0 = (long long)r * kReduceSlice + threadIdx.x;
-    double2 v[kReduceSlice / 256];
-#pragma unroll
-    for (int k = 0; k < kReduceSlice / 256; ++k) {
-        const long long i = i0 + 256 * k;
-        v[k] = i < n ? __ldcg(p2 + i) : make_double2(0.0, 0.0);
-    }
-    double a = 0.0, b = 0.0;
-#pragma unroll
-    for (int k = 0; k < kReduceSlice / 256; ++k) { a += v[k].x; b += v[k].y; }
-    ta[threadIdx.x] = a; tb[threadIdx.x] = b;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) { ta[threadIdx.x] += ta[threadIdx.x + s]; tb[threadIdx.x] += tb[threadIdx.x + s]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        slices[2 * r] = ta[0];
-        slices[2 * r + 1] = tb[0];
-        int last = 1;
-        if (R > 1) {
-            __threadfence();                                   // slice sum visible device-wide before the ticket is taken
-            last = atomicAdd(ticket, 1u) == (unsigned)(R - 1);
-            if (last) __threadfence();                         // ... and the others' sums before they are read
-        }
-        s_last = last;
-    }
-    __syncthreads();
-    return s_last != 0;
 }
 
 // back-projection + COCO row fields of one sample by one warp.

@@ -304,20 +304,54 @@ __global__ void __launch_bounds__(kSpmThreads) spm_loss_kernel(SpmLossParams P) 
 }
 
 // ---------------------------------------------------------------- fused render + loss (+ grad)
-// SPMHeatmapGenerator + SPMMaskGenerator + SPMDisplacementGenerator (utils/spm_utils.py:16-95) evaluated in registers and fed
+// SPMHeatmapGenerator + SPMMaskGenerator + SPMDisplacementGenerator (utils/spm_utils.py:16-95) evaluated on the fly and fed
 // straight into SPMLoss.forward (models/loss/spm_loss.py:23-105): the [N,1+2K,R,R] target is never written to or read from
 // HBM, so a training step moves 2 tensor passes (read logits, write dlogits) instead of 1 (render) + 3 (dense loss).
 //
-// Work unit = 16 KB of one channel plane, streamed linearly exactly like spm_loss_kernel; every CTA owns a CONTIGUOUS range
-// of units, so an image's persons are staged in shared memory once per image, not once per unit: centres + patch corners,
-// all body joints, a per-row bitmask of the persons touching the row and a per-row bitmask of the COVERED float4 quads
-// (quads that intersect some person's box or Gaussian patch: ~3% of an image).
-//   phase A (every lane, per quad): not covered -> target 0, mask 0: the loss term is 0 unless the logit is NaN and
-//     dlogits = 0: a handful of instructions per element, no person data touched.
-//   phase B (per warp, only if some lane's quad is covered): the covered quads' elements are re-distributed over the lanes,
-//     one PIXEL per lane (logit fetched from the owning lane by shuffle), so the expensive part -- replaying the covering
-//     persons in order, template look-ups, tanhf -- runs once per warp at up to 32 useful lanes.  (v1 ran it inside the
-//     per-quad loop, 4 elements per lane at ~3 useful lanes per warp: 436 us per 256 images, slower than render + dense loss.)
+// The SPM target is ~97 % zeros and the zero part costs nothing but bandwidth: target 0, mask 0 => the loss term is 0 unless the
+// logit is NaN (sigmoid(p)*0 and tanh(p)*0 are 0 for every other p) and dlogits = 0.  Two launches:
+//   (1) spm_geometry_kernel, one CTA per image: everything about an image that is the same for all of its 1+2K planes -- the
+//       persons' boxes and Gaussian-patch windows, a per-row bitmask of the persons touching the row, a per-row bitmask of the
+//       COVERED float4 quads (quads that intersect some person's box or patch) and, for R <= 256, one byte per pixel (bit 7:
+//       root mask t0 > 0; bits 0-6: 0 = in no person's box, p+1 = in the box of person p only, 127 = in several) -- goes to a
+//       per-image record in the caller's workspace (20 KB at R = 128; ~5 us for 1024 images);
+//   (2) spm_unit_kernel, NOT persistent: one 128-thread CTA per 16 KB unit of one channel plane, handed out in memory order
+//       by the hardware scheduler.  One thread issues a cp.async.bulk (TMA engine, mbarrier completion) for the unit's logits
+//       the moment the CTA starts; while they fly the CTA fetches the unit's coverage bits and the persons;
+//       phase A: every uncovered quad -- NaN check from shared memory, one 128-bit store of zeros;
+//       phase B: the covered quads of the unit are listed (deterministic positions from prefix pop-counts, no atomics) and
+//       their PIXELS are dealt out one per thread: logit from shared memory, geometry byte, joint, quotient table, tanhf only
+//       under the root mask, one 32-bit store.  Pixels in several boxes replay the covering persons in index order.
+// Why not persistent (r01: every CTA owned a contiguous range of units and staged an image's geometry in shared memory once
+// per image): measured on B200, the same streaming work runs 10-15 % faster when the grid covers the data and CTAs retire
+// (tools/stream_patterns.cu), and with the maps in flight held in shared memory by the bulk copies (9 CTAs x 16 KB per SM)
+// rather than in registers.  r01: 222.9 us per 256 images (loss + grad), 116 us read-only, 125 us render-only.
+struct SpmFusedPerson;
+struct SpmGeomLayout {
+    unsigned long long stride;      // bytes per image
+    unsigned off_persons, off_rowmask, off_covq, off_map;
+    int use_map;
+};
+constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
+struct __align__(16) SpmFusedPerson {
+    int cx, cy;                 // centre (box = [cx-half, cx+half] x [cy-half, cy+half])
+    int ulx, uly;               // template origin in map coordinates
+    int px0, px1, py0, py1;     // Gaussian patch window clipped to the map and to the template, [x0,x1) x [y0,y1); empty: all 0
+};
+__host__ __device__ inline SpmGeomLayout spm_geom_layout(int R) {
+    SpmGeomLayout L;
+    const int wpr = (R / 4 + 31) / 32;
+    unsigned long long off = 0;
+    L.off_persons = (unsigned)off; off += (unsigned long long)kSpmFusedMaxPersons * sizeof(SpmFusedPerson);
+    L.off_rowmask = (unsigned)off; off += (unsigned long long)R * 8;
+    L.off_covq = (unsigned)off; off += (unsigned long long)R * wpr * 4;
+    off = (off + 15) / 16 * 16;
+    L.use_map = (long long)R * R <= 65536;
+    L.off_map = (unsigned)off; off += L.use_map ? (unsigned long long)R * R : 0ull;
+    L.stride = (off + 255) / 256 * 256;
+    return L;
+}
+
 struct SpmFusedParams {
     const float* logits; float* dlogits; float* target_out;
     const long long* centers;   // [N][Pmax][2]
@@ -325,68 +359,117 @@ struct SpmFusedParams {
     const int* counts;          // [N]
     const float* lut; int lut_n;
     double three_sigma; int half; double z;
-    double* partials;           // [grid][2]  (S_root, S_disp)
+    double* partials;           // [units][2]  (S_root, S_disp) per work unit
+    unsigned int* ticket;       // two-level loss reduction counter (zeroed by the geometry kernel)
+    unsigned char* geom;        // [N] per-image records (SpmGeomLayout)
+    double* div_tab;            // [div_n] (i - R) / z, or unused when div_n == 0
+    SpmGeomLayout gl;
     int N, Pmax, K, R;
     int quads; FastDiv div_qpr; // float4 per plane; quads per row (R/4)
     int wpr;                    // 32-bit words of covered-quad bits per row: ceil(R/4/32)
-    int div_n;                  // 2R+1 entries of the quotient table in shared memory, or 0 (R too large: divide directly)
+    int div_n;                  // 2R+1 entries of the quotient table, or 0 (R too large: divide directly)
     float groot, gdisp;         // 2*lambda_root*inv_norm, lambda_disp*inv_norm
 };
 
-struct __align__(16) SpmFusedPerson {
-    int cx, cy;                 // centre (box = [cx-half, cx+half] x [cy-half, cy+half])
-    int ulx, uly;               // template origin in map coordinates
-    int px0, px1, py0, py1;     // Gaussian patch window clipped to the map and to the template, [x0,x1) x [y0,y1); empty: all 0
-};
-
-#ifndef POSE_SPM_FUSED_MINB
-#define POSE_SPM_FUSED_MINB 4   // resident CTAs per SM the kernel is compiled for (register cap 64)
-#endif
-// float4 per thread and unit (1, 2, 4 or 8: the unit must divide a 128x128 plane), per variant (tools/spm_skeleton.py,
-// profiles/r01_spm_unit_sweep.log, per 256 / 1024 images):
-//   loss + grad (read logits, write dlogits): 8 KB units -- U=2 222 / 817 us, U=4 235 / 907, U=8 242 / 924, U=1 272 / 1028;
-//   read-only loss: 32 KB units (more covered quads pooled per phase B, twice the loads in flight) -- U=8 123 / 415 us,
-//     U=4 138 / 488, U=2 166 / 633;
-//   render-only (LOSS = false, pose_spm_render): 32 KB units -- U=8 123 / 447 us, U=4 124 / 457, U=2 127 / 456.
-#ifndef POSE_SPM_FUSED_U
-#define POSE_SPM_FUSED_U 2
-#endif
-#ifndef POSE_SPM_FUSED_U_RO
-#define POSE_SPM_FUSED_U_RO 8
-#endif
-#ifndef POSE_SPM_FUSED_U_RENDER
-#define POSE_SPM_FUSED_U_RENDER 8
-#endif
-__host__ __device__ constexpr int spm_fused_u(bool grad, bool wtgt, bool loss = true) {
-    return !loss ? POSE_SPM_FUSED_U_RENDER : (grad || wtgt) ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
-}
-constexpr int kSpmFusedUMax0 = POSE_SPM_FUSED_U > POSE_SPM_FUSED_U_RO ? POSE_SPM_FUSED_U : POSE_SPM_FUSED_U_RO;
-constexpr int kSpmFusedUMax = kSpmFusedUMax0 > POSE_SPM_FUSED_U_RENDER ? kSpmFusedUMax0 : POSE_SPM_FUSED_U_RENDER;
-constexpr int kSpmFusedMaxPersons = 64;                       // one 64-bit row mask
-// PATCH (read-only loss variant at R = 128, i.e. ROWG && MAP): the covered quads of an image are listed once per image; the
-// stream (phase A) never stops for them and ONE pass per plane, by the whole CTA with one pixel per thread and full lanes,
-// computes the listed pixels.  Their logits are requested when the CTA enters the plane and consumed when it leaves it, so the
-// dependent chain of the per-warp phase B is off the streaming path: 124.0 -> 115.9 us per 256 images, 417.8 -> 407.9 us per
-// 1024.  The variants that write dlogits / the target keep the per-warp phase B: a patch pass that writes (phase A skipping the
-// zero stores of covered quads) was measured slower there (220.8 -> 225.6 us, 819 -> 864 us), and so were three forms with
-// dedicated patch warps beside 8 streaming warps (r02: 241-464 us) -- fewer streaming warps per SM cost more than phase B does.
-#ifndef POSE_SPM_PATCH_NPRE
-#define POSE_SPM_PATCH_NPRE 3   // pixels per thread whose logits are requested at plane entry (3 x 256 = 192 covered quads)
-#endif
-constexpr int kSpmPatchListCap = 4096;                        // all quads of a 128 x 128 plane
-
-constexpr int kSpmMapMaxBytes = 16384;                        // per-image pixel map (one byte per pixel): R <= 128
-
-__host__ __device__ inline bool spm_fused_use_map(int R) { return R * R <= kSpmMapMaxBytes; }
-__host__ __device__ inline size_t spm_fused_smem_bytes(int div_n, int R, int K, int wpr, int lut_n) {
-    return (size_t)div_n * 8 + (size_t)R * 8 + (size_t)kSpmFusedMaxPersons * K * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4 +
-           (spm_fused_use_map(R) ? (size_t)R * R : 0);
+constexpr int kSpmGeomThreads = 256;
+__host__ __device__ inline size_t spm_geom_smem_bytes(int R, int lut_n) {
+    const int wpr = (R / 4 + 31) / 32;
+    return (size_t)R * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4;
 }
 
-// target of one pixel: (root value t0 = max of the covering Gaussian patches, displacement te of plane (jn, axis))
+__global__ void __launch_bounds__(kSpmGeomThreads) spm_geometry_kernel(SpmFusedParams P) {
+    // dynamic shared memory: [R] u64 row masks | [R*wpr] u32 covered quads | template
+    extern __shared__ __align__(16) unsigned char spm_geom_smem[];
+    unsigned long long* rowmask_s = reinterpret_cast<unsigned long long*>(spm_geom_smem);
+    unsigned int* covq_s = reinterpret_cast<unsigned int*>(rowmask_s + P.R);
+    float* lut_s = reinterpret_cast<float*>(covq_s + P.R * P.wpr);
+    __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
+    pdl_launch_dependents();                                          // the unit kernel's CTAs may be scheduled: they wait for us before reading the records
+    const int img = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (img == 0) {
+        if (threadIdx.x == 0) *P.ticket = 0u;
+        for (int i = threadIdx.x; i < P.div_n; i += blockDim.x) P.div_tab[i] = (double)(i - P.R) / P.z;
+    }
+    unsigned char* rec = P.geom + (unsigned long long)img * P.gl.stride;
+    const int np = min(max(P.counts[img], 0), min(P.Pmax, kSpmFusedMaxPersons));
+    for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        SpmFusedPerson sp;
+        const long long pi = (long long)img * P.Pmax + i;
+        sp.cx = (int)max(min(P.centers[pi * 2], 1ll << 30), -(1ll << 30));
+        sp.cy = (int)max(min(P.centers[pi * 2 + 1], 1ll << 30), -(1ll << 30));
+        sp.ulx = (int)rint(((double)sp.cx - P.three_sigma) - 1.0);
+        sp.uly = (int)rint(((double)sp.cy - P.three_sigma) - 1.0);
+        const int brx = (int)rint(((double)sp.cx + P.three_sigma) + 2.0);
+        const int bry = (int)rint(((double)sp.cy + P.three_sigma) + 2.0);
+        sp.px0 = max(0, sp.ulx); sp.px1 = min(min(brx, P.R), sp.ulx + P.lut_n);
+        sp.py0 = max(0, sp.uly); sp.py1 = min(min(bry, P.R), sp.uly + P.lut_n);
+        if (sp.px1 <= sp.px0 || sp.py1 <= sp.py0) sp.px0 = sp.px1 = sp.py0 = sp.py1 = 0;
+        s_p[i] = sp;
+        reinterpret_cast<SpmFusedPerson*>(rec + P.gl.off_persons)[i] = sp;
+    }
+    for (int i = threadIdx.x; i < P.R; i += blockDim.x) rowmask_s[i] = 0ull;
+    for (int i = threadIdx.x; i < P.R * P.wpr; i += blockDim.x) covq_s[i] = 0u;
+    __syncthreads();
+    // one thread per (person, row of the union of its box and patch): row mask bit + covered-quad bits
+    const int span = 2 * P.half + 1 + P.lut_n;                 // upper bound on the rows of the union
+    for (int t = threadIdx.x; t < np * span; t += blockDim.x) {
+        const int p = t / span;
+        const SpmFusedPerson sp = s_p[p];
+        if (sp.cx <= 0 && sp.cy <= 0) continue;                 // skipped by all three generators
+        const bool patch = sp.px1 > sp.px0;
+        const int ylo = patch ? min(sp.cy - P.half, sp.py0) : sp.cy - P.half;
+        const int yhi = patch ? max(sp.cy + P.half, sp.py1 - 1) : sp.cy + P.half;
+        const int row = ylo + (t - p * span);
+        if (row < 0 || row >= P.R || row > yhi) continue;
+        const int xlo = max(0, patch ? min(sp.cx - P.half, sp.px0) : sp.cx - P.half);
+        const int xhi = min(P.R - 1, patch ? max(sp.cx + P.half, sp.px1 - 1) : sp.cx + P.half);
+        if (xhi < xlo) continue;
+        atomicOr(&rowmask_s[row], 1ull << p);
+        const int q0 = xlo >> 2, q1 = xhi >> 2;
+        for (int w = q0 >> 5; w <= (q1 >> 5); ++w) {
+            const int lo = max(q0 - 32 * w, 0), hi = min(q1 - 32 * w, 31);
+            const unsigned int bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            atomicOr(&covq_s[row * P.wpr + w], bits);
+        }
+    }
+    __syncthreads();
+    unsigned long long* rowmask_g = reinterpret_cast<unsigned long long*>(rec + P.gl.off_rowmask);
+    unsigned int* covq_g = reinterpret_cast<unsigned int*>(rec + P.gl.off_covq);
+    for (int i = threadIdx.x; i < P.R; i += blockDim.x) rowmask_g[i] = rowmask_s[i];
+    for (int i = threadIdx.x; i < P.R * P.wpr; i += blockDim.x) covq_g[i] = covq_s[i];
+    if (P.gl.use_map) {
+        // one warp per row; only rows that some person touches are ever looked up, the others are not even written
+        unsigned char* map_g = rec + P.gl.off_map;
+        for (int row = wid; row < P.R; row += kSpmGeomThreads / 32) {
+            const unsigned long long rm = rowmask_s[row];
+            if (rm == 0ull) continue;                           // warp-uniform
+            for (int col = lane; col < P.R; col += 32) {
+                unsigned long long m = rm;
+                unsigned int code = 0u, nbox = 0u;
+                bool mk = false;
+                while (m) {
+                    const int p = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const SpmFusedPerson sp = s_p[p];
+                    if (row >= sp.py0 && row < sp.py1 && col >= sp.px0 && col < sp.px1 &&
+                        lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)] > 0.0f) mk = true;
+                    if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
+                        if (nbox++ == 0u) code = (unsigned)p + 1u;
+                    }
+                }
+                if (nbox > 1u) code = 127u;
+                map_g[row * P.R + col] = (unsigned char)(code | (mk ? 128u : 0u));
+            }
+        }
+    }
+}
+
+// target of one pixel: (root value t0 = max of the covering Gaussian patches, displacement te of the plane's joint / axis);
+// s_j[p] = person p's joint of this plane
 __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const SpmFusedPerson* __restrict__ s_p, const int2* __restrict__ s_j,
-                                                 const double* __restrict__ div_s, const float* __restrict__ lut_s, unsigned long long m,
-                                                 int row, int col, bool disp, int jn, int axis, float& t0, float& te) {
+                                                 unsigned long long m, int row, int col, bool disp, int axis, float& t0, float& te) {
     t0 = 0.0f;
     te = 0.0f;
     while (m) {
@@ -394,289 +477,155 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
         m &= m - 1;
         const SpmFusedPerson sp = s_p[p];
         if (row >= sp.py0 && row < sp.py1 && col >= sp.px0 && col < sp.px1)
-            t0 = fmaxf(t0, lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)]);
+            t0 = fmaxf(t0, __ldg(P.lut + (row - sp.uly) * P.lut_n + (col - sp.ulx)));
         if (disp && row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
-            const int2 jv = s_j[p * P.K + jn];
+            const int2 jv = s_j[p];
             if (!(jv.x <= 0 && jv.y <= 0)) {
                 const int dd = axis ? jv.y - row : jv.x - col;
-                const double qd = (P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z;
+                const double qd = (P.div_n && dd >= -P.R && dd <= P.R) ? __ldg(P.div_tab + dd + P.R) : (double)dd / P.z;
                 te = (float)((double)te + qd);                       // fp32(fp64(acc) + q): numpy's mixed-precision +=
             }
         }
     }
 }
 
-// LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read, the target is
-// written as one linear stream with the covered pixels filled in by the same pass.
-// MAP (R*R <= 16 KB, i.e. R <= 128 -- configs/spm_coco.yaml): the geometry of a pixel is the same for all 2K displacement
-// planes of an image, so it is evaluated ONCE per image into a byte map in shared memory -- bit 7: root mask (t0 > 0), bits
-// 0-6: 0 = in no person's box, p+1 = in the box of person p only, 127 = in several boxes (replay them in order) -- and phase B
-// of a displacement plane is one byte load + one joint + one quotient look-up instead of a loop over the row's persons with
-// eight range compares each.  Larger maps keep the generic per-pixel evaluation.
-// ROWG (R % 128 == 0): the 32 quads of a warp instruction lie in one row and are exactly one word of that row's
-// covered-quad bits, and every unit is full: one broadcast LDS gives the warp's coverage mask (no per-lane look-up, no
-// ballot, no validity predicates on the stream).
-// (Tried and dropped: a 4-row x 8-quad tile per warp instruction, so that a 9x9 box touches ~3.75 tiles instead of 9 rows and
-// phase B is entered 2.4x less often -- the four separate 128-byte lines per access cost more than that saved: 253 -> 318 us
-// fused, 144 -> 177 us render-only per 256 images.  Likewise a warp owning U CONSECUTIVE rows of a unit instead of every 8th row
-// (a 9-row box then falls to ~3 warps with full phase-B passes instead of 8 sparse ones): 235 -> 290 us fused, 125 -> 175 us
-// read-only -- the few loaded warps become the critical path of the CTA's unit range.  And a per-warp shared-memory ring filled
-// with cp.async (LDGSTS) so that the next units' loads fly during phase B and phase B reads its logit from the ring instead of
-// L2: 235 -> 235 us (N=256), 902 -> 872 us (N=1024) for the grad variant at 3 CTAs/SM, 125 -> 139 us read-only -- the L2
-// prefetch of the next unit already hides that latency; not worth 32 KB of shared memory per CTA.)
-template <bool LOSS, bool GRAD, bool WTGT, bool ROWG, bool MAP>
-__global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_kernel(SpmFusedParams P) {
-    // dynamic shared memory: [div_n] double quotients | [R] u64 row masks | [64*K] int2 joints | [R*wpr] u32 covered quads | template
-    //                        | MAP: [R*R] u8 pixel map
-    extern __shared__ __align__(16) unsigned char spm_fused_smem[];
-    double* div_s = reinterpret_cast<double*>(spm_fused_smem);
-    unsigned long long* rowmask_s = reinterpret_cast<unsigned long long*>(div_s + P.div_n);
-    int2* s_j = reinterpret_cast<int2*>(rowmask_s + P.R);
-    unsigned int* covq_s = reinterpret_cast<unsigned int*>(s_j + kSpmFusedMaxPersons * P.K);
-    float* lut_s = reinterpret_cast<float*>(covq_s + P.R * P.wpr);
-    unsigned char* map_s = reinterpret_cast<unsigned char*>(lut_s + P.lut_n * P.lut_n);      // MAP only
+constexpr int kSpmUnitQuads = 1024;                           // float4 per work unit: 16 KB of one channel plane
+#ifndef POSE_SPM_UNIT_THREADS
+#define POSE_SPM_UNIT_THREADS 128
+#endif
+#ifndef POSE_SPM_UNIT_MINB
+#define POSE_SPM_UNIT_MINB 8
+#endif
+constexpr int kSpmUnitThreads = POSE_SPM_UNIT_THREADS;
+constexpr int kSpmUnitWarps = kSpmUnitThreads / 32;
+__host__ __device__ inline size_t spm_unit_smem_bytes(bool loss) { return loss ? (size_t)kSpmUnitQuads * 16 : 0; }
+__host__ __device__ inline long long spm_units(int N, int K, int R) {
+    const long long quads = (long long)R * R / 4;
+    return (long long)N * (1 + 2 * K) * ((quads + kSpmUnitQuads - 1) / kSpmUnitQuads);
+}
+
+// LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read.
+template <bool LOSS, bool GRAD, bool WTGT>
+__global__ void __launch_bounds__(kSpmUnitThreads, POSE_SPM_UNIT_MINB) spm_unit_kernel(SpmFusedParams P) {
+    extern __shared__ __align__(128) float tile[];                     // LOSS: the unit's logits
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
-    __shared__ double red[kSpmThreads / 32][2];
-    constexpr int kSpmFusedU = spm_fused_u(GRAD, WTGT, LOSS);
-    constexpr int kSpmFusedChunk = kSpmThreads * kSpmFusedU;          // float4 per work unit
-    __shared__ unsigned char s_src[kSpmThreads / 32][32 * kSpmFusedU];
-    // ROWG && MAP <=> R == 128: 32 quads per row, wpr == 1
-    constexpr bool PATCH = ROWG && MAP && LOSS && !GRAD && !WTGT;
-    constexpr int NPRE = POSE_SPM_PATCH_NPRE;
-    __shared__ unsigned short plist_s[PATCH ? kSpmPatchListCap : 1];   // covered quads of the staged image, ascending
-    __shared__ int s_nlist;
-    pdl_launch_dependents();
-    for (int i = threadIdx.x; i < P.lut_n * P.lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
-    for (int i = threadIdx.x; i < P.div_n; i += blockDim.x) div_s[i] = (double)(i - P.R) / P.z;
-
+    __shared__ int2 s_j[kSpmFusedMaxPersons];
+    __shared__ unsigned int s_cov[kSpmUnitQuads / 32];                 // coverage of the unit's quads, 32 consecutive quads per word
+    __shared__ unsigned short s_list[kSpmUnitQuads];                   // covered quads of the unit (unit-relative), ascending
+    __shared__ float s_acc[kSpmUnitWarps];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int C = 1 + 2 * P.K;
-    const int upp = (P.quads + kSpmFusedChunk - 1) / kSpmFusedChunk;
-    const long long units = (long long)P.N * C * upp;
-    const long long u_begin = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
-    const float4* L4 = reinterpret_cast<const float4*>(P.logits);
-    float4* G4 = reinterpret_cast<float4*>(P.dlogits);
-    float4* T4 = reinterpret_cast<float4*>(P.target_out);
+    const int upp = (P.quads + kSpmUnitQuads - 1) / kSpmUnitQuads;
+    const long long unit = blockIdx.x;
+    const long long plane = unit / upp;
+    const int chunk = (int)(unit - plane * upp);
+    const int img = (int)(plane / C), c = (int)(plane - (long long)img * C);
+    const int q_lo = chunk * kSpmUnitQuads;
+    const int nq = min(kSpmUnitQuads, P.quads - q_lo);                  // quads of this unit
+    const long long off = plane * P.quads + q_lo;                       // first quad of the unit in the tensor
+    const bool disp = c != 0;
+    const int jn = (c - 1) >> 1, axis = (c - 1) & 1;                    // displacement plane: joint and axis (0 = x, 1 = y)
     const int qpr = (int)P.div_qpr.d;
-    const long long total_quads = (long long)P.N * C * P.quads;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    if (LOSS && tid == 0) {
+        mbar_init(smem_u32(&s_bar), 1);
+        mbar_init_fence();
+        mbar_arrive_expect_tx(smem_u32(&s_bar), (uint32_t)nq * 16u);
+        bulk_load(smem_u32(tile), reinterpret_cast<const float4*>(P.logits) + off, (uint32_t)nq * 16u, smem_u32(&s_bar));
+    }
+    // inputs of the call (not produced by the geometry kernel): the persons' joint of this plane
+    const int np = min(max(P.counts[img], 0), min(P.Pmax, kSpmFusedMaxPersons));
+    if (disp) {
+        const long long* jimg = P.joints + ((long long)img * P.Pmax * P.K + jn) * 2;
+        for (int p = tid; p < np; p += kSpmUnitThreads) {
+            const longlong2 jv = __ldg(reinterpret_cast<const longlong2*>(jimg + (long long)p * P.K * 2));
+            s_j[p] = make_int2((int)max(min(jv.x, 1ll << 30), -(1ll << 30)), (int)max(min(jv.y, 1ll << 30), -(1ll << 30)));
+        }
+    }
+    pdl_wait();                                                         // the image records are complete and visible
+    const unsigned char* rec = P.geom + (unsigned long long)img * P.gl.stride;
+    const unsigned int* covq_g = reinterpret_cast<const unsigned int*>(rec + P.gl.off_covq);
+    const unsigned long long* rowmask_g = reinterpret_cast<const unsigned long long*>(rec + P.gl.off_rowmask);
+    const unsigned char* map_g = rec + P.gl.off_map;
+    for (int p = tid; p < np; p += kSpmUnitThreads) s_p[p] = reinterpret_cast<const SpmFusedPerson*>(rec + P.gl.off_persons)[p];
+    // coverage words of the unit: word i = quads [32 i, 32 i + 32) of the unit
+    if (qpr == 32) {
+        if (tid < kSpmUnitQuads / 32) s_cov[tid] = (32 * tid < nq) ? __ldcg(covq_g + (q_lo >> 5) + tid) : 0u;
+    } else {
+#pragma unroll 2
+        for (int i = wid; i < kSpmUnitQuads / 32; i += kSpmUnitWarps) {
+            const int q = q_lo + 32 * i + lane;
+            bool covered = false;
+            if (32 * i + lane < nq) {
+                const int row = (int)fdiv((uint32_t)q, P.div_qpr), cq = q - row * qpr;
+                covered = (__ldcg(covq_g + row * P.wpr + (cq >> 5)) >> (cq & 31)) & 1u;
+            }
+            const unsigned w = __ballot_sync(FULL_MASK, covered);
+            if (lane == 0) s_cov[i] = w;
+        }
+    }
+    __syncthreads();                                                    // s_cov, s_p, s_j, the initialised mbarrier
+    // list of the covered quads: every warp scans the 32 word pop-counts itself (no second barrier), then fills its words' part
+    int ncov;
+    {
+        const unsigned w = s_cov[lane];
+        const int cnt = __popc(w);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        ncov = __shfl_sync(FULL_MASK, incl, 31);
+        if (ncov) {                                                     // warp-uniform
+            for (int i = wid; i < kSpmUnitQuads / 32; i += kSpmUnitWarps) {
+                const unsigned wi = __shfl_sync(FULL_MASK, w, i);
+                const int base = __shfl_sync(FULL_MASK, incl - cnt, i);
+                if ((wi >> lane) & 1u) s_list[base + __popc(wi & ((1u << lane) - 1u))] = (unsigned short)(32 * i + lane);
+            }
+        }
+    }
+    float4* G4 = reinterpret_cast<float4*>(P.dlogits) + off;
+    float4* T4 = reinterpret_cast<float4*>(P.target_out) + off;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    double droot = 0.0, ddisp = 0.0;
-    int staged_img = -1;
-
-    // (image, channel, chunk) of the first unit; advanced incrementally (no 64-bit divisions in the loop)
-    long long plane = u_begin / upp;
-    int chunk = (int)(u_begin - plane * upp);
-    int img = (int)(plane / C), c = (int)(plane - (long long)img * C);
-
-    int q_first = 0, q_last = 0;                                       // PATCH: this CTA's quads [q_first, q_last) of the current plane
-    float pl[NPRE];                                                    // PATCH: logits requested at plane entry
-    for (long long unit = u_begin; unit < u_end; ++unit) {
-        if (img != staged_img) {                                       // CTA-uniform
-            const int np = min(max(P.counts[img], 0), min(P.Pmax, kSpmFusedMaxPersons));
-            __syncthreads();
-            for (int i = threadIdx.x; i < np; i += blockDim.x) {
-                SpmFusedPerson sp;
-                const long long pi = (long long)img * P.Pmax + i;
-                sp.cx = (int)max(min(P.centers[pi * 2], 1ll << 30), -(1ll << 30));
-                sp.cy = (int)max(min(P.centers[pi * 2 + 1], 1ll << 30), -(1ll << 30));
-                sp.ulx = (int)rint(((double)sp.cx - P.three_sigma) - 1.0);
-                sp.uly = (int)rint(((double)sp.cy - P.three_sigma) - 1.0);
-                const int brx = (int)rint(((double)sp.cx + P.three_sigma) + 2.0);
-                const int bry = (int)rint(((double)sp.cy + P.three_sigma) + 2.0);
-                sp.px0 = max(0, sp.ulx); sp.px1 = min(min(brx, P.R), sp.ulx + P.lut_n);
-                sp.py0 = max(0, sp.uly); sp.py1 = min(min(bry, P.R), sp.uly + P.lut_n);
-                if (sp.px1 <= sp.px0 || sp.py1 <= sp.py0) sp.px0 = sp.px1 = sp.py0 = sp.py1 = 0;
-                s_p[i] = sp;
-            }
-            const long long* jimg = P.joints + (long long)img * P.Pmax * P.K * 2;
-            for (int i = threadIdx.x; i < np * P.K; i += blockDim.x) {
-                const longlong2 jv = __ldg(reinterpret_cast<const longlong2*>(jimg) + i);
-                s_j[i] = make_int2((int)max(min(jv.x, 1ll << 30), -(1ll << 30)), (int)max(min(jv.y, 1ll << 30), -(1ll << 30)));
-            }
-            for (int i = threadIdx.x; i < P.R; i += blockDim.x) rowmask_s[i] = 0ull;
-            for (int i = threadIdx.x; i < P.R * P.wpr; i += blockDim.x) covq_s[i] = 0u;
-            __syncthreads();
-            // one thread per (person, row of the union of its box and patch): row mask bit + covered-quad bits
-            const int span = 2 * P.half + 1 + P.lut_n;                 // upper bound on the rows of the union
-            for (int t = threadIdx.x; t < np * span; t += blockDim.x) {
-                const int p = t / span;
-                const SpmFusedPerson sp = s_p[p];
-                if (sp.cx <= 0 && sp.cy <= 0) continue;                 // skipped by all three generators
-                const bool patch = sp.px1 > sp.px0;
-                const int ylo = patch ? min(sp.cy - P.half, sp.py0) : sp.cy - P.half;
-                const int yhi = patch ? max(sp.cy + P.half, sp.py1 - 1) : sp.cy + P.half;
-                const int row = ylo + (t - p * span);
-                if (row < 0 || row >= P.R || row > yhi) continue;
-                const int xlo = max(0, patch ? min(sp.cx - P.half, sp.px0) : sp.cx - P.half);
-                const int xhi = min(P.R - 1, patch ? max(sp.cx + P.half, sp.px1 - 1) : sp.cx + P.half);
-                if (xhi < xlo) continue;
-                atomicOr(&rowmask_s[row], 1ull << p);
-                const int q0 = xlo >> 2, q1 = xhi >> 2;
-                    for (int w = q0 >> 5; w <= (q1 >> 5); ++w) {
-                    const int lo = max(q0 - 32 * w, 0), hi = min(q1 - 32 * w, 31);
-                    const unsigned int bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-                    atomicOr(&covq_s[row * P.wpr + w], bits);
-                }
-            }
-            __syncthreads();
-            if (MAP) {
-                // one warp per row; only rows that some person touches are ever looked up, the others are not even written
-                for (int row = wid; row < P.R; row += kSpmThreads / 32) {
-                    const unsigned long long rm = rowmask_s[row];
-                    if (rm == 0ull) continue;                           // warp-uniform
-                  for (int col = lane; col < P.R; col += 32) {
-                    const int idx = row * P.R + col;
-                    unsigned long long m = rm;
-                    unsigned int code = 0u, nbox = 0u;
-                    bool mk = false;
-                    while (m) {
-                        const int p = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        const SpmFusedPerson sp = s_p[p];
-                        if (row >= sp.py0 && row < sp.py1 && col >= sp.px0 && col < sp.px1 &&
-                            lut_s[(row - sp.uly) * P.lut_n + (col - sp.ulx)] > 0.0f) mk = true;
-                        if (row >= sp.cy - P.half && row <= sp.cy + P.half && col >= sp.cx - P.half && col <= sp.cx + P.half) {
-                            if (nbox++ == 0u) code = (unsigned)p + 1u;
-                        }
-                    }
-                    if (nbox > 1u) code = 127u;
-                    map_s[idx] = (unsigned char)(code | (mk ? 128u : 0u));
-                  }
-                }
-                if (PATCH && wid == kSpmThreads / 32 - 1) {
-                    // the covered-quad bits (one word per row, 4 rows per lane) -> ascending list of quad indices
-                    unsigned int w4[4];
-                    int cnt = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { w4[k] = covq_s[4 * lane + k]; cnt += __popc(w4[k]); }
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(FULL_MASK, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    int pos = incl - cnt;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        unsigned int bits = w4[k];
-                        while (bits) {
-                            const int b = __ffs((int)bits) - 1;
-                            bits &= bits - 1u;
-                            plist_s[pos++] = (unsigned short)((4 * lane + k) * 32 + b);
-                        }
-                    }
-                    if (lane == 31) s_nlist = incl;
-                }
-                __syncthreads();
-            }
-            staged_img = img;
+    float acc = 0.f;
+    if (LOSS) mbar_wait_parity(&s_bar, 0);
+    // phase A: the quads no person touches
+#pragma unroll 4
+    for (int q = tid; q < nq; q += kSpmUnitThreads) {
+        if ((s_cov[q >> 5] >> (q & 31)) & 1u) continue;
+        if (LOSS) {
+            const float4 v = reinterpret_cast<const float4*>(tile)[q];
+            const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+            if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
         }
-        const long long off = plane * P.quads;
-        const int q_lo = chunk * kSpmFusedChunk;
-        float4 pv[kSpmFusedU];
-        const float4* lsrc = L4 + off + q_lo + threadIdx.x;
-        // ROWG: quads is a multiple of the chunk, so every quad of every unit is valid (no predicates on the stream)
-#pragma unroll
-        for (int u = 0; u < kSpmFusedU; ++u)
-            if (LOSS && (ROWG || q_lo + u * kSpmThreads + (int)threadIdx.x < P.quads)) pv[u] = ldg_stream(lsrc + u * kSpmThreads);
-        if (LOSS && unit + 1 < u_end) {
-            // the next unit of this CTA is the next 16 KB in memory (planes are contiguous): pull it into L2 while this unit
-            // computes.  Measured alternatives, both SLOWER than this prefetch (252 us per 256 images): holding the next unit in
-            // a second register set (285-291 us at 3 CTAs/SM), and re-using pv for the next unit's loads right after phase A so
-            // that they fly during phase B (278 us: pv then lives across phase B and spills under the 64-register cap).
-            const char* nsrc = reinterpret_cast<const char*>(L4 + off + min(q_lo + kSpmFusedChunk, P.quads));
-            const char* lend = reinterpret_cast<const char*>(L4 + total_quads);
-            if (threadIdx.x < kSpmFusedChunk * 16 / 128 && nsrc + threadIdx.x * 128 < lend) prefetch_l2(nsrc + threadIdx.x * 128);
-        }
-        const bool disp = c != 0;
-        const int jn = (c - 1) >> 1, axis = (c - 1) & 1;                 // displacement plane: joint and axis (0 = x, 1 = y)
-        float acc = 0.f;
-        if (PATCH && (unit == u_begin || chunk == 0)) {                  // entering a plane (CTA-uniform)
-            q_first = q_lo;
-            q_last = (chunk + (int)min((long long)(upp - chunk), u_end - unit)) * kSpmFusedChunk;
-            const int nl4 = 4 * s_nlist;
-#pragma unroll
-            for (int k = 0; k < NPRE; ++k) {
-                const int i = (int)threadIdx.x + k * kSpmThreads;
-                pl[k] = 0.0f;
-                if (i < nl4) {
-                    const int q = (int)plist_s[i >> 2];
-                    if (LOSS && q >= q_first && q < q_last) pl[k] = __ldg(P.logits + (off + q) * 4 + (i & 3));
-                }
-            }
-        }
-        unsigned cmask[kSpmFusedU];
-        float4* gdst = GRAD ? G4 + off + q_lo + threadIdx.x : nullptr;
-        float4* tdst = WTGT ? T4 + off + q_lo + threadIdx.x : nullptr;
-        unsigned anyc = 0u;
-        if (ROWG) {
-            // phase A, uniform: EVERY quad is treated as uncovered (zero target, zero mask: the loss term is 0 unless the logit
-            // is NaN -- sigmoid(p)*0 and tanh(p)*0 are 0 for every other p -- and dlogits = 0); phase B then overwrites the
-            // pixels of the covered quads (ordered after these stores by its __syncwarp; a NaN counted twice is still a NaN).
-            // The warp's coverage mask is one broadcast LDS: with wpr = qpr/32 the word index is the warp's group index in the
-            // plane.  No per-lane look-up, no ballot, no branch on the stream.
-#pragma unroll
-            for (int u = 0; u < kSpmFusedU; ++u) {
-                if (LOSS) {
-                    const float4 v = pv[u];
-                    const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-                    if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
-                }
-                cmask[u] = covq_s[(q_lo >> 5) + u * (kSpmThreads / 32) + wid];
-                if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
-                if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
-            }
-#pragma unroll
-            for (int u = 0; u < kSpmFusedU; ++u) anyc |= cmask[u];
-        } else {
-#pragma unroll
-            for (int u = 0; u < kSpmFusedU; ++u) {
-                const int qu = q_lo + u * kSpmThreads + (int)threadIdx.x;
-                const bool valid = qu < P.quads;
-                bool covered = false;
-                if (valid) {
-                    const int row = (int)fdiv((uint32_t)qu, P.div_qpr), cq = qu - row * qpr;
-                    covered = (covq_s[row * P.wpr + (cq >> 5)] >> (cq & 31)) & 1u;
-                }
-                cmask[u] = __ballot_sync(FULL_MASK, covered);
-                if (cmask[u]) anyc |= 1u << u;
-                if (valid && !covered) {
-                    if (LOSS) {
-                        const float4 v = pv[u];
-                        const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-                        if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
-                    }
-                    if (GRAD) __stcs(gdst + u * kSpmThreads, z4);
-                    if (WTGT) __stcs(tdst + u * kSpmThreads, z4);
-                }
-            }
-        }
-        // phase B: one pixel of a covered quad per lane.  The covered quads of ALL the warp's instructions of this unit are
-        // pooled (slot k of the warp's scratch row = u*32 + lane of the k-th covered quad), so the long dependent chain below
-        // runs once per warp and unit with up to 32 useful lanes, not once per covered instruction with ~14.  Deliberately not
-        // unrolled over u (an unrolled copy per u made the kernel 113 KB of SASS and `no_instruction` the second largest
-        // stall).  The pixel's logit is re-read from L2 (the warp streamed it a moment ago) rather than shuffled out of pv[]:
-        // pv dies after phase A, which keeps the kernel inside 64 registers without spills.
-        // one covered pixel: element e of quad qs (plane-relative) with logit pe
-        auto pixel = [&](int qs, int e, float pe) {
-            const long long ei = (off + qs) * 4 + e;
-            const int row = (int)fdiv((uint32_t)qs, P.div_qpr), col = (qs - row * qpr) * 4 + e;
+        if (GRAD) __stcs(G4 + q, z4);
+        if (WTGT) __stcs(T4 + q, z4);
+    }
+    if (ncov) {
+        __syncthreads();                                                // the list is complete (CTA-uniform branch)
+        // phase B: one pixel of a covered quad per thread
+        for (int i = tid; i < 4 * ncov; i += kSpmUnitThreads) {
+            const int qu = (int)s_list[i >> 2], e = i & 3;              // unit-relative quad, element
+            const int q = q_lo + qu;                                    // plane-relative quad
+            const int row = (int)fdiv((uint32_t)q, P.div_qpr), col = (q - row * qpr) * 4 + e;
+            const float pe = LOSS ? tile[qu * 4 + e] : 0.0f;
             float t0 = 0.0f, te = 0.0f;
             bool mk;
             unsigned int code = 127u;
-            if (MAP && disp) code = map_s[row * P.R + col];
-            if (ROWG && MAP && disp && code == 0u) return;               // slack pixel of a covered quad: phase A's zeros stand
-            if (MAP && disp && (code & 127u) != 127u) {
+            if (P.gl.use_map && disp) code = __ldg(map_g + row * P.R + col);
+            if (P.gl.use_map && disp && (code & 127u) != 127u) {
                 mk = code >> 7;
                 if (code & 127u) {
-                    const int2 jv = s_j[((int)(code & 127u) - 1) * P.K + jn];
+                    const int2 jv = s_j[(int)(code & 127u) - 1];
                     if (!(jv.x <= 0 && jv.y <= 0)) {
                         const int dd = axis ? jv.y - row : jv.x - col;
-                        te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? div_s[dd + P.R] : (double)dd / P.z);
+                        te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? __ldg(P.div_tab + dd + P.R) : (double)dd / P.z);
                     }
                 }
             } else {
-                spm_pixel_target(P, s_p, s_j, div_s, lut_s, rowmask_s[row], row, col, disp, jn, axis, t0, te);
+                spm_pixel_target(P, s_p, s_j, __ldg(rowmask_g + row), row, col, disp, axis, t0, te);
                 mk = t0 > 0.0f;
             }
             float ge = 0.0f;
@@ -697,62 +646,29 @@ __global__ void __launch_bounds__(kSpmThreads, POSE_SPM_FUSED_MINB) spm_fused_ke
                 acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
                 ge = mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
             }
+            const long long ei = (off + qu) * 4 + e;
             if (GRAD) __stcs(P.dlogits + ei, ge);
             if (WTGT) __stcs(P.target_out + ei, te);
-        };
-        if (!PATCH && anyc) {                                            // warp-uniform
-            int nslot = 0;
-#pragma unroll
-            for (int u = 0; u < kSpmFusedU; ++u) {
-                if ((cmask[u] >> lane) & 1u) s_src[wid][nslot + __popc(cmask[u] & ((1u << lane) - 1u))] = (unsigned char)(u * 32 + lane);
-                nslot += __popc(cmask[u]);
-            }
-            __syncwarp();                                                // also orders phase A's zero stores before the overwrites
-            const int total = nslot * 4;
-            for (int b = 0; b < total; b += 32) {
-                const int l = b + lane;
-                if (l >= total) continue;
-                const int sl = (int)s_src[wid][l >> 2];
-                const int qs = q_lo + (sl >> 5) * kSpmThreads + wid * 32 + (sl & 31);
-                const int e = l & 3;
-                pixel(qs, e, LOSS ? __ldg(P.logits + (off + qs) * 4 + e) : 0.0f);
-            }
-            __syncwarp();                                                // scratch row is rewritten by the next covered group
-        }
-        if (PATCH && (unit + 1 == u_end || chunk == upp - 1)) {          // leaving the plane (CTA-uniform): its patch pass
-            const int nl4 = 4 * s_nlist;
-#pragma unroll
-            for (int k = 0; k < NPRE; ++k) {
-                const int i = (int)threadIdx.x + k * kSpmThreads;
-                if (i < nl4) {
-                    const int q = (int)plist_s[i >> 2];
-                    if (q >= q_first && q < q_last) pixel(q, i & 3, pl[k]);
-                }
-            }
-            for (int i = (int)threadIdx.x + NPRE * kSpmThreads; i < nl4; i += kSpmThreads) {
-                const int q = (int)plist_s[i >> 2];
-                if (q >= q_first && q < q_last) pixel(q, i & 3, LOSS ? __ldg(P.logits + (off + q) * 4 + (i & 3)) : 0.0f);
-            }
-        }
-        if (c == 0) droot += (double)acc; else ddisp += (double)acc;
-        if (++chunk == upp) {
-            chunk = 0;
-            ++plane;
-            if (++c == C) { c = 0; ++img; }
         }
     }
-    if (!LOSS) return;                                                   // render-only: no loss partials (P.partials is NULL)
-    droot = warp_sum(droot);
-    ddisp = warp_sum(ddisp);
-    if (lane == 0) { red[wid][0] = droot; red[wid][1] = ddisp; }
+    if (!LOSS) return;                                                   // render-only: no loss partials
+    acc = warp_sum(acc);
+    if (lane == 0) s_acc[wid] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
+    if (tid == 0) {
+        double a = 0.0;
 #pragma unroll
-        for (int w = 0; w < kSpmThreads / 32; ++w) { a += red[w][0]; b += red[w][1]; }
-        P.partials[2 * blockIdx.x] = a;
-        P.partials[2 * blockIdx.x + 1] = b;
+        for (int w = 0; w < kSpmUnitWarps; ++w) a += (double)s_acc[w];
+        reinterpret_cast<double2*>(P.partials)[unit] = disp ? make_double2(0.0, a) : make_double2(a, 0.0);
     }
+}
+
+// two-level deterministic reduction of the per-unit (S_root, S_disp) pairs (common.cuh); grid = R slice CTAs
+__global__ void __launch_bounds__(256) spm_loss_reduce_kernel(const double* __restrict__ pairs, long long n, double* __restrict__ slices,
+                                                              unsigned int* __restrict__ ticket, int R, double w0, double w1, double inv_norm,
+                                                              float* __restrict__ loss_out, double* __restrict__ num_out) {
+    pdl_wait();
+    if (reduce_slice_and_elect(pairs, n, slices, ticket, R, (int)blockIdx.x)) reduce_pairs_cta(slices, R, 2, w0, w1, inv_norm, loss_out, num_out);
 }
 
 // ---------------------------------------------------------------- decode

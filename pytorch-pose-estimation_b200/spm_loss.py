@@ -47,7 +47,7 @@ def spm_fused(logits, centers, joints, counts, sigma=-1, want_grad=True, want_ta
     target = torch.empty_like(x) if want_target else None
     loss = torch.empty((), dtype=torch.float32, device=dev)
     num = torch.empty((2,), dtype=torch.float64, device=dev)
-    ws = _cabi.workspace(dev, int(lib().pose_spm_fused_workspace_bytes()))
+    ws = _cabi.workspace(dev, int(lib().pose_spm_fused_workspace_bytes(n, k, r)))
     inv_norm = 1.0 / (global_batch if global_batch is not None else n) if n > 0 else 0.0
     flags = (_cabi.F_GRAD if want_grad else 0) | (_cabi.F_TARGET_OUT if want_target else 0)
     with torch.cuda.device(dev):

@@ -55,9 +55,10 @@ def spm_render_batch(centers, joints, counts, output_res, sigma=-1, device=None)
     c, j, cnt, sig, lut, lut_n = _render_args(centers, joints, counts, output_res, sigma, dev)
     n, pmax, k = j.size(0), j.size(1), j.size(2)
     out = torch.empty((n, 1 + 2 * k, output_res, output_res), dtype=torch.float32, device=dev)
+    ws = _cabi.workspace(dev, int(lib().pose_spm_fused_workspace_bytes(n, k, output_res)))      # single-pass render needs the geometry records
     with torch.cuda.device(dev):
         check(lib().pose_spm_render(ptr(c), ptr(j), ptr(cnt), ptr(out), n, pmax, k, output_res, sig, ptr(lut), lut_n,
-                                    stream_ptr(dev)), "pose_spm_render")
+                                    ptr(ws), ws.numel(), stream_ptr(dev)), "pose_spm_render")
     return out
 
 

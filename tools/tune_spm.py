@@ -15,16 +15,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "build", "tune")
 
-# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: 256 threads, MINB=4, U=2 (grad), U_RO=8, U_RENDER=8, NPRE=3.
+# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: 128 threads per 16 KB unit, compiled for 8 CTAs per SM.
 VARIANTS = {
-    "m3": ["-DPOSE_SPM_FUSED_MINB=3"],
-    "m5": ["-DPOSE_SPM_FUSED_MINB=5"],
-    "u4": ["-DPOSE_SPM_FUSED_U=4"],
-    "u1": ["-DPOSE_SPM_FUSED_U=1"],
-    "ro4": ["-DPOSE_SPM_FUSED_U_RO=4"],
-    "render4": ["-DPOSE_SPM_FUSED_U_RENDER=4"],
-    "npre2": ["-DPOSE_SPM_PATCH_NPRE=2"],
-    "npre4": ["-DPOSE_SPM_PATCH_NPRE=4"],
+    "t64_b12": ["-DPOSE_SPM_UNIT_THREADS=64", "-DPOSE_SPM_UNIT_MINB=12"],
+    "t64_b8": ["-DPOSE_SPM_UNIT_THREADS=64", "-DPOSE_SPM_UNIT_MINB=8"],
+    "t128_b6": ["-DPOSE_SPM_UNIT_MINB=6"],
+    "t128_b10": ["-DPOSE_SPM_UNIT_MINB=10"],
+    "t256_b4": ["-DPOSE_SPM_UNIT_THREADS=256", "-DPOSE_SPM_UNIT_MINB=4"],
 }
 
 
