@@ -46,8 +46,20 @@ int launch_spm_units(const pose::SpmFusedParams& P, const SpmWs& w, cudaStream_t
     if (int rc = check_launch("spm_geometry")) return rc;
     const size_t smem = pose::spm_unit_smem_bytes(LOSS);
     if (resident_ctas(pose::spm_unit_kernel<LOSS, GRAD, WTGT>, pose::kSpmUnitThreads, smem, what) == 0) return last_code();
-    if (w.units > 0x7fffffffll) return fail(POSE_EINVAL, "%s: %lld work units exceed one grid", what, w.units);
-    launch_pdl(pose::spm_unit_kernel<LOSS, GRAD, WTGT>, (unsigned)w.units, (unsigned)pose::kSpmUnitThreads, smem, st, P);
+    if (P.N > 65535 || 1 + 2 * P.K > 65535) return fail(POSE_EINVAL, "%s: N=%d / K=%d exceed the grid (65535 images per call)", what, P.N, P.K);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)pose::spm_units_per_plane(P.R, LOSS), (unsigned)(1 + 2 * P.K), (unsigned)P.N);
+        cfg.blockDim = dim3((unsigned)pose::kSpmUnitThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, pose::spm_unit_kernel<LOSS, GRAD, WTGT>, P);
+    }
     return check_launch(what);
 }
 }  // namespace

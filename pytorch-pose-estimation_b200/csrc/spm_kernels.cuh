@@ -489,38 +489,52 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
     }
 }
 
-constexpr int kSpmUnitQuads = 1024;                           // float4 per work unit: 16 KB of one channel plane
+// float4 per work unit (512 ... 4096 = 8 ... 64 KB of one channel plane), per variant class (tools/tune_spm.py,
+// profiles/r02_tune_spm_unit_*.log): the kernels that read logits want SMALL units -- a CTA cannot start before its whole
+// bulk copy has landed, so 32 KB units cost 9 % and 64 KB units 60 % against 16 KB -- the render-only write stream wants 32 KB
+// (fewer CTAs, the per-CTA prologue amortised: 100 vs 109 us per 256 images).
+#ifndef POSE_SPM_UNIT_QUADS_LOSS
+#define POSE_SPM_UNIT_QUADS_LOSS 1024
+#endif
+#ifndef POSE_SPM_UNIT_QUADS_RENDER
+#define POSE_SPM_UNIT_QUADS_RENDER 2048
+#endif
 #ifndef POSE_SPM_UNIT_THREADS
 #define POSE_SPM_UNIT_THREADS 128
 #endif
-#ifndef POSE_SPM_UNIT_MINB
-#define POSE_SPM_UNIT_MINB 8
+#ifndef POSE_SPM_UNIT_MINB_LOSS
+#define POSE_SPM_UNIT_MINB_LOSS 10
 #endif
+#ifndef POSE_SPM_UNIT_MINB_RENDER
+#define POSE_SPM_UNIT_MINB_RENDER 6
+#endif
+__host__ __device__ constexpr int spm_unit_quads(bool loss) { return loss ? POSE_SPM_UNIT_QUADS_LOSS : POSE_SPM_UNIT_QUADS_RENDER; }
+static_assert(POSE_SPM_UNIT_QUADS_LOSS % 512 == 0 && POSE_SPM_UNIT_QUADS_LOSS <= 4096 && POSE_SPM_UNIT_QUADS_RENDER % 512 == 0 &&
+              POSE_SPM_UNIT_QUADS_RENDER <= 4096, "unit size");
 constexpr int kSpmUnitThreads = POSE_SPM_UNIT_THREADS;
 constexpr int kSpmUnitWarps = kSpmUnitThreads / 32;
-__host__ __device__ inline size_t spm_unit_smem_bytes(bool loss) { return loss ? (size_t)kSpmUnitQuads * 16 : 0; }
-__host__ __device__ inline long long spm_units(int N, int K, int R) {
-    const long long quads = (long long)R * R / 4;
-    return (long long)N * (1 + 2 * K) * ((quads + kSpmUnitQuads - 1) / kSpmUnitQuads);
-}
+__host__ __device__ inline size_t spm_unit_smem_bytes(bool loss) { return loss ? (size_t)spm_unit_quads(true) * 16 : 0; }
+__host__ __device__ inline int spm_units_per_plane(int R, bool loss) { return (R * R / 4 + spm_unit_quads(loss) - 1) / spm_unit_quads(loss); }
+// (the loss pairs: one per unit of the kernels that read logits)
+__host__ __device__ inline long long spm_units(int N, int K, int R) { return (long long)N * (1 + 2 * K) * spm_units_per_plane(R, true); }
 
 // LOSS = false is the render-only form (pose_spm_render for <= 64 persons per image): no logits are read.
 template <bool LOSS, bool GRAD, bool WTGT>
-__global__ void __launch_bounds__(kSpmUnitThreads, POSE_SPM_UNIT_MINB) spm_unit_kernel(SpmFusedParams P) {
+__global__ void __launch_bounds__(kSpmUnitThreads, LOSS ? POSE_SPM_UNIT_MINB_LOSS : POSE_SPM_UNIT_MINB_RENDER) spm_unit_kernel(SpmFusedParams P) {
+    constexpr int kSpmUnitQuads = spm_unit_quads(LOSS);
+    constexpr int kSpmUnitWords = kSpmUnitQuads / 32;                  // coverage words per unit (<= 128: up to four per lane in the scan)
     extern __shared__ __align__(128) float tile[];                     // LOSS: the unit's logits
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ SpmFusedPerson s_p[kSpmFusedMaxPersons];
     __shared__ int2 s_j[kSpmFusedMaxPersons];
-    __shared__ unsigned int s_cov[kSpmUnitQuads / 32];                 // coverage of the unit's quads, 32 consecutive quads per word
+    __shared__ unsigned int s_cov[kSpmUnitWords];                      // coverage of the unit's quads, 32 consecutive quads per word
     __shared__ unsigned short s_list[kSpmUnitQuads];                   // covered quads of the unit (unit-relative), ascending
     __shared__ float s_acc[kSpmUnitWarps];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int C = 1 + 2 * P.K;
-    const int upp = (P.quads + kSpmUnitQuads - 1) / kSpmUnitQuads;
-    const long long unit = blockIdx.x;
-    const long long plane = unit / upp;
-    const int chunk = (int)(unit - plane * upp);
-    const int img = (int)(plane / C), c = (int)(plane - (long long)img * C);
+    // grid = (units per plane, 1+2K channels, N images): the hardware hands the CTAs out in memory order, no index divisions
+    const int chunk = blockIdx.x, c = blockIdx.y, img = blockIdx.z;
+    const long long plane = (long long)img * gridDim.y + c;
+    const long long unit = plane * gridDim.x + chunk;
     const int q_lo = chunk * kSpmUnitQuads;
     const int nq = min(kSpmUnitQuads, P.quads - q_lo);                  // quads of this unit
     const long long off = plane * P.quads + q_lo;                       // first quad of the unit in the tensor
@@ -534,8 +548,11 @@ __global__ void __launch_bounds__(kSpmUnitThreads, POSE_SPM_UNIT_MINB) spm_unit_
         mbar_arrive_expect_tx(smem_u32(&s_bar), (uint32_t)nq * 16u);
         bulk_load(smem_u32(tile), reinterpret_cast<const float4*>(P.logits) + off, (uint32_t)nq * 16u, smem_u32(&s_bar));
     }
-    // inputs of the call (not produced by the geometry kernel): the persons' joint of this plane
-    const int np = min(max(P.counts[img], 0), min(P.Pmax, kSpmFusedMaxPersons));
+    // inputs of the call (not produced by the geometry kernel): the persons' joint of this plane.  All Pmax slots are fetched:
+    // waiting for counts[img] first would put one more L2 round trip in front of everything; slots beyond the image's count
+    // are never referenced by the geometry.  (Fetching them only in units that turn out to contain covered quads -- 40 % --
+    // was measured: no gain for the loss kernels, 9 % slower for the render-only one, which has no bulk copy to hide it under.)
+    const int np = min(P.Pmax, kSpmFusedMaxPersons);
     if (disp) {
         const long long* jimg = P.joints + ((long long)img * P.Pmax * P.K + jn) * 2;
         for (int p = tid; p < np; p += kSpmUnitThreads) {
@@ -548,13 +565,12 @@ __global__ void __launch_bounds__(kSpmUnitThreads, POSE_SPM_UNIT_MINB) spm_unit_
     const unsigned int* covq_g = reinterpret_cast<const unsigned int*>(rec + P.gl.off_covq);
     const unsigned long long* rowmask_g = reinterpret_cast<const unsigned long long*>(rec + P.gl.off_rowmask);
     const unsigned char* map_g = rec + P.gl.off_map;
-    for (int p = tid; p < np; p += kSpmUnitThreads) s_p[p] = reinterpret_cast<const SpmFusedPerson*>(rec + P.gl.off_persons)[p];
     // coverage words of the unit: word i = quads [32 i, 32 i + 32) of the unit
     if (qpr == 32) {
-        if (tid < kSpmUnitQuads / 32) s_cov[tid] = (32 * tid < nq) ? __ldcg(covq_g + (q_lo >> 5) + tid) : 0u;
+        for (int i = tid; i < kSpmUnitWords; i += kSpmUnitThreads) s_cov[i] = (32 * i < nq) ? __ldcg(covq_g + (q_lo >> 5) + i) : 0u;
     } else {
 #pragma unroll 2
-        for (int i = wid; i < kSpmUnitQuads / 32; i += kSpmUnitWarps) {
+        for (int i = wid; i < kSpmUnitWords; i += kSpmUnitWarps) {
             const int q = q_lo + 32 * i + lane;
             bool covered = false;
             if (32 * i + lane < nq) {
@@ -565,12 +581,20 @@ __global__ void __launch_bounds__(kSpmUnitThreads, POSE_SPM_UNIT_MINB) spm_unit_
             if (lane == 0) s_cov[i] = w;
         }
     }
+    for (int p = tid; p < np; p += kSpmUnitThreads) s_p[p] = reinterpret_cast<const SpmFusedPerson*>(rec + P.gl.off_persons)[p];
     __syncthreads();                                                    // s_cov, s_p, s_j, the initialised mbarrier
-    // list of the covered quads: every warp scans the 32 word pop-counts itself (no second barrier), then fills its words' part
+    // list of the covered quads: every warp scans the word pop-counts itself (no extra barrier; a lane takes WPL consecutive
+    // words), then fills the part of the list that belongs to its own words
     int ncov;
     {
-        const unsigned w = s_cov[lane];
-        const int cnt = __popc(w);
+        constexpr int WPL = (kSpmUnitWords + 31) / 32;                  // words per lane: 1, 2 or 4
+        unsigned w[WPL];
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+            w[k] = (lane * WPL + k < kSpmUnitWords) ? s_cov[lane * WPL + k] : 0u;
+            cnt += __popc(w[k]);
+        }
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -579,64 +603,60 @@ __global__ void __launch_bounds__(kSpmUnitThreads, POSE_SPM_UNIT_MINB) spm_unit_
         }
         ncov = __shfl_sync(FULL_MASK, incl, 31);
         if (ncov) {                                                     // warp-uniform
-            for (int i = wid; i < kSpmUnitQuads / 32; i += kSpmUnitWarps) {
-                const unsigned wi = __shfl_sync(FULL_MASK, w, i);
-                const int base = __shfl_sync(FULL_MASK, incl - cnt, i);
-                if ((wi >> lane) & 1u) s_list[base + __popc(wi & ((1u << lane) - 1u))] = (unsigned short)(32 * i + lane);
-            }
-        }
-    }
-    float4* G4 = reinterpret_cast<float4*>(P.dlogits) + off;
-    float4* T4 = reinterpret_cast<float4*>(P.target_out) + off;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float acc = 0.f;
-    if (LOSS) mbar_wait_parity(&s_bar, 0);
-    // phase A: the quads no person touches
-#pragma unroll 4
-    for (int q = tid; q < nq; q += kSpmUnitThreads) {
-        if ((s_cov[q >> 5] >> (q & 31)) & 1u) continue;
-        if (LOSS) {
-            const float4 v = reinterpret_cast<const float4*>(tile)[q];
-            const bool nan = (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-            if (nan) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
-        }
-        if (GRAD) __stcs(G4 + q, z4);
-        if (WTGT) __stcs(T4 + q, z4);
-    }
-    if (ncov) {
-        __syncthreads();                                                // the list is complete (CTA-uniform branch)
-        // phase B: one pixel of a covered quad per thread
-        for (int i = tid; i < 4 * ncov; i += kSpmUnitThreads) {
-            const int qu = (int)s_list[i >> 2], e = i & 3;              // unit-relative quad, element
-            const int q = q_lo + qu;                                    // plane-relative quad
-            const int row = (int)fdiv((uint32_t)q, P.div_qpr), col = (q - row * qpr) * 4 + e;
-            const float pe = LOSS ? tile[qu * 4 + e] : 0.0f;
-            float t0 = 0.0f, te = 0.0f;
-            bool mk;
-            unsigned int code = 127u;
-            if (P.gl.use_map && disp) code = __ldg(map_g + row * P.R + col);
-            if (P.gl.use_map && disp && (code & 127u) != 127u) {
-                mk = code >> 7;
-                if (code & 127u) {
-                    const int2 jv = s_j[(int)(code & 127u) - 1];
-                    if (!(jv.x <= 0 && jv.y <= 0)) {
-                        const int dd = axis ? jv.y - row : jv.x - col;
-                        te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? __ldg(P.div_tab + dd + P.R) : (double)dd / P.z);
+            // lane l of warp `wid` lists the words l*WPL .. l*WPL+WPL-1 when l % warps == wid (every word exactly once)
+            if ((lane % kSpmUnitWarps) == wid) {
+                int pos = incl - cnt;
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) {
+                    unsigned bits = w[k];
+                    const int q0 = 32 * (lane * WPL + k);
+                    while (bits) {
+                        const int b = __ffs((int)bits) - 1;
+                        bits &= bits - 1u;
+                        s_list[pos++] = (unsigned short)(q0 + b);
                     }
                 }
-            } else {
-                spm_pixel_target(P, s_p, s_j, __ldg(rowmask_g + row), row, col, disp, axis, t0, te);
-                mk = t0 > 0.0f;
             }
-            float ge = 0.0f;
-            if (!LOSS) {
-                if (!disp) te = t0;
-            } else if (!disp) {
+        }
+    }
+    if (ncov) __syncthreads();                                          // the list is complete (CTA-uniform branch)
+
+    // target of covered pixel i of the unit (4 pixels per listed quad): nothing here depends on the logits
+    auto target_of = [&](int i, float& t0, float& te, bool& mk) {
+        const int qu = (int)s_list[i >> 2], e = i & 3;                  // unit-relative quad, element
+        const int q = q_lo + qu;                                        // plane-relative quad
+        const int row = (int)fdiv((uint32_t)q, P.div_qpr), col = (q - row * qpr) * 4 + e;
+        t0 = 0.0f;
+        te = 0.0f;
+        unsigned int code = 127u;
+        if (P.gl.use_map && disp) code = __ldg(map_g + row * P.R + col);
+        if (P.gl.use_map && disp && (code & 127u) != 127u) {
+            mk = code >> 7;
+            if (code & 127u) {
+                const int2 jv = s_j[(int)(code & 127u) - 1];
+                if (!(jv.x <= 0 && jv.y <= 0)) {
+                    const int dd = axis ? jv.y - row : jv.x - col;
+                    te = (float)((P.div_n && dd >= -P.R && dd <= P.R) ? __ldg(P.div_tab + dd + P.R) : (double)dd / P.z);
+                }
+            }
+        } else {
+            spm_pixel_target(P, s_p, s_j, __ldg(rowmask_g + row), row, col, disp, axis, t0, te);
+            mk = t0 > 0.0f;
+        }
+        if (!disp) te = t0;                                             // (root plane: the target value itself)
+    };
+    float acc = 0.f;
+    // loss term + gradient of covered pixel i given its target; stores the results
+    auto finish = [&](int i, float t0, float te, bool mk) {
+        const int qu = (int)s_list[i >> 2], e = i & 3;
+        float ge = 0.0f;
+        if (LOSS) {
+            const float pe = tile[qu * 4 + e];
+            if (!disp) {
                 const float sg = sigmoid_fast(pe);
                 const float d = (mk ? sg : sg * 0.0f) - t0;
                 acc = fmaf(d, d, acc);
                 ge = mk ? P.groot * d * ((1.0f - sg) * sg) : 0.0f;
-                te = t0;
             } else {
                 // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
                 float th = 0.0f, pm = pe != pe ? pe : 0.0f;          // NaN logits propagate as in the reference
@@ -646,10 +666,53 @@ __global__ void __launch_bounds__(kSpmUnitThreads, POSE_SPM_UNIT_MINB) spm_unit_
                 acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
                 ge = mk ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
             }
-            const long long ei = (off + qu) * 4 + e;
-            if (GRAD) __stcs(P.dlogits + ei, ge);
-            if (WTGT) __stcs(P.target_out + ei, te);
         }
+        const long long ei = (off + qu) * 4 + e;
+        if (GRAD) __stcs(P.dlogits + ei, ge);
+        if (WTGT) __stcs(P.target_out + ei, te);
+    };
+    // render-only form: the targets of this thread's first covered pixels are requested BEFORE the zero stores of phase A, so
+    // their dependent chain (geometry byte from L2 -> joint -> quotient table) runs under the store stream: 100 vs 108 us per
+    // 256 images.  (With logits to wait for the same trick gains nothing: 123 vs 119 us read-only.)
+    constexpr int NPRE = LOSS ? 0 : 2;
+    float pt0[NPRE + 1], pte[NPRE + 1];
+    bool pmk[NPRE + 1];
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+        const int i = tid + k * kSpmUnitThreads;
+        pt0[k] = 0.0f; pte[k] = 0.0f; pmk[k] = false;
+        if (i < 4 * ncov) target_of(i, pt0[k], pte[k], pmk[k]);
+    }
+    float4* G4 = reinterpret_cast<float4*>(P.dlogits) + off;
+    float4* T4 = reinterpret_cast<float4*>(P.target_out) + off;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (LOSS) mbar_wait_parity(&s_bar, 0);
+    // phase A: the quads no person touches
+#pragma unroll 4
+    for (int q = tid; q < nq; q += kSpmUnitThreads) {
+        if ((s_cov[q >> 5] >> (q & 31)) & 1u) continue;
+        if (LOSS) {
+            // (the sum of the four is NaN whenever one of them is; +inf + -inf also lands here and adds nothing)
+            const float4 v = reinterpret_cast<const float4*>(tile)[q];
+            const float sum4 = (v.x + v.y) + (v.z + v.w);
+            if (sum4 != sum4) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
+        }
+        if (GRAD) __stcs(G4 + q, z4);
+        if (WTGT) __stcs(T4 + q, z4);
+    }
+    // phase B: one pixel of a covered quad per thread.  (Measured and dropped: working the targets out before the wait for the
+    // bulk copy -- 123 vs 119 us read-only; a per-image hash table pixel -> covering persons for the pixels in several boxes
+    // instead of the person walk -- 131 vs 123 us; profiles/r02_tune_spm_experiments.log.)
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+        const int i = tid + k * kSpmUnitThreads;
+        if (i < 4 * ncov) finish(i, pt0[k], pte[k], pmk[k]);
+    }
+    for (int i = tid + NPRE * kSpmUnitThreads; i < 4 * ncov; i += kSpmUnitThreads) {
+        float t0, te;
+        bool mk;
+        target_of(i, t0, te, mk);
+        finish(i, t0, te, mk);
     }
     if (!LOSS) return;                                                   // render-only: no loss partials
     acc = warp_sum(acc);

@@ -15,13 +15,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "build", "tune")
 
-# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: 128 threads per 16 KB unit, compiled for 8 CTAs per SM.
+# name -> -D knobs (csrc/spm_kernels.cuh).  Shipped: see the POSE_SPM_UNIT_* defaults.
 VARIANTS = {
-    "t64_b12": ["-DPOSE_SPM_UNIT_THREADS=64", "-DPOSE_SPM_UNIT_MINB=12"],
-    "t64_b8": ["-DPOSE_SPM_UNIT_THREADS=64", "-DPOSE_SPM_UNIT_MINB=8"],
-    "t128_b6": ["-DPOSE_SPM_UNIT_MINB=6"],
-    "t128_b10": ["-DPOSE_SPM_UNIT_MINB=10"],
-    "t256_b4": ["-DPOSE_SPM_UNIT_THREADS=256", "-DPOSE_SPM_UNIT_MINB=4"],
+    "l512_t128_b12": ["-DPOSE_SPM_UNIT_QUADS_LOSS=512", "-DPOSE_SPM_UNIT_MINB_LOSS=12"],
+    "l1024_b8": ["-DPOSE_SPM_UNIT_MINB_LOSS=8"],
+    "l2048_b5": ["-DPOSE_SPM_UNIT_QUADS_LOSS=2048", "-DPOSE_SPM_UNIT_MINB_LOSS=5"],
+    "r1024_b10": ["-DPOSE_SPM_UNIT_QUADS_RENDER=1024", "-DPOSE_SPM_UNIT_MINB_RENDER=10"],
+    "r4096_b3": ["-DPOSE_SPM_UNIT_QUADS_RENDER=4096", "-DPOSE_SPM_UNIT_MINB_RENDER=3"],
 }
 
 
