@@ -39,6 +39,8 @@ extern "C" {
 #define POSE_F_DECODE 4u        /* also decode joints from sigmoid(logits) in the same pass */
 #define POSE_F_TMA 8u           /* stage the maps through shared memory with bulk async copies (render mode, 16-byte aligned maps): the fast path */
 #define POSE_F_SIGMOID_CUDA 16u /* POSE_F_DECODE: rank with POSE_SIGMOID_ATEN_CUDA instead of POSE_SIGMOID_ATEN_CPU */
+#define POSE_F_HEAD_LOGITS_OUT 32u   /* pose_sbp_head_fused: also write the logits (tests / debugging: the point of the call is not to) */
+#define POSE_F_HEAD_NO_RESIDUAL 64u  /* pose_sbp_head_fused: skip the feature residual (plain TF32 features: 2^-11 relative error; diagnostics) */
 
 /* Which torch.sigmoid the decoders reproduce BIT FOR BIT when they rank near-equal logits and report the confidence.
  * "First row-major index of the largest sigmoid value" (nms_sbp utils/sbp_utils.py:73-78, nms_spm utils/spm_utils.py:112-115)
@@ -274,6 +276,32 @@ int pose_ap_accumulate(const long long* order, const int* dt_match, const unsign
                        const double* rec_thrs, int C, int A, int T, int R, int D, int G,
                        double* precision, double* recall, void* workspace, unsigned long long workspace_bytes,
                        pose_stream_t stream);
+
+/* ---- head fusion -- the detector's last layer, nn.Conv2d(512, num_keypoints, 1, 1, bias=False)
+ *      models/detector/sbp.py:35-37,47, fused with what consumes its output: SBPLoss.forward models/loss/sbp_loss.py:20-66
+ *      (+ autograd backward w.r.t. the logits), SBPHeatmapGenerator.__call__ utils/sbp_utils.py:33-53 (target rendered from
+ *      kp), DecodeSBP.forward / nms_sbp utils/sbp_utils.py:56-118 and SBPmAPCOCO.update_state :141-163 -- the logits
+ *      [N][K][H][W] never exist in HBM.
+ *   features [N][C][H][W] fp32 NCHW (the head's input), weight [K][C] fp32 (conv weight [K,C,1,1]), kp / lut as in
+ *   pose_sbp_fused except that `lut` is the UNPADDED n*n template (pose_gauss_template_host).
+ *   The contraction runs on the tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, features through TMA tensor
+ *   maps) with both operands split into a tf32 head and a residual, so the logits carry fp32-level error (csrc/head_kernels.cuh).
+ *   Outputs as pose_sbp_fused (dlogits iff POSE_F_GRAD: the caller's autograd needs it for dW and dX; joints / packed_out iff
+ *   POSE_F_DECODE); logits_out only with POSE_F_HEAD_LOGITS_OUT.  Decode: argmax in LOGIT space, first index among equal
+ *   logits (all logits >= 17.5 tie: their sigmoid is 1.0f), confidence = the reference sigmoid of the maximum.
+ *   Constraints (POSE_EINVAL otherwise): C % 32 == 0 and 48*C*4 bytes + 4 tiles must fit in shared memory (C <= 640),
+ *   (H*W) % 128 == 0, K <= 24, template side <= 24.
+ *   tuning: 0 = defaults; bits 0-7 feature stages in shared memory; bit 24 selects the variant that keeps the feature
+ *   residuals in shared memory instead of tensor memory (bits 8-15: its residual stages) -- slower, kept for comparison.
+ *   Three launches: weight split, the fused kernel (persistent, one CTA per SM, whole images), the epilogue of pose_sbp_fused.
+ * workspace: pose_sbp_head_workspace_bytes(N, K, C), 256-byte aligned. */
+unsigned long long pose_sbp_head_workspace_bytes(int N, int K, int C);
+int pose_sbp_head_fused(const float* features, const float* weight, const void* kp, int kp_dtype, double sigma,
+                        const float* lut, int lut_n, float* dlogits, float* logits_out, float* loss_out,
+                        double* loss_num_out, float* joints, float conf_threshold, float coord_scale, int N, int C,
+                        int K, int H, int W, float lambda_pos, float lambda_neg, double inv_norm, unsigned flags,
+                        const double* bbox, float* packed_out, int input_h, int input_w, int tuning,
+                        void* workspace, unsigned long long workspace_bytes, pose_stream_t stream);
 
 /* ---- diagnostics of the reference sigmoids (csrc/common.cuh).
  * pose_sigmoid_ref_eval: y[i] = the device restatement of torch.sigmoid (sigmoid_ref) at x[i]; tests compare it with

@@ -7,6 +7,7 @@ hot-path modules:
     utils/sbp_pis_utils.py  -> pose_b200.sbp_pis_utils  (SBPmAPPIS)
     utils/spm_utils.py      -> pose_b200.spm_utils      (SPM*Generator, nms_spm, DecodeSPM, SPMmAPCOCO)
     models/loss/sbp_loss.py -> pose_b200.sbp_loss       (SBPLoss)
+    models/detector/sbp.py:35-37 (the 1x1 head) + SBPLoss / DecodeSBP -> pose_b200.sbp_head (sbp_head_fused, HeadFusedSBPLoss)
     models/loss/spm_loss.py -> pose_b200.spm_loss       (SPMLoss)
     pycocotools COCOeval    -> pose_b200.coco_eval      (KeypointEval: OKS matching + AP behind the metric classes' result())
 
@@ -16,6 +17,7 @@ built library or without a CUDA device every entry point raises.
 """
 from ._cabi import LIB_PATH, PoseB200Error, launch_count, lib  # noqa: F401
 from .coco_eval import CocoKeypointsGT, KeypointEval  # noqa: F401
+from .sbp_head import HeadFusedSBPLoss, head_tuning, sbp_head_fused  # noqa: F401
 from .sbp_loss import SBPLoss, sbp_fused  # noqa: F401
 from .sbp_pis_utils import SBPmAPPIS  # noqa: F401
 from .sbp_utils import (DecodeSBP, SBPHeatmapGenerator, SBPmAPCOCO, backproject_packed, backproject_rows, decode_batch,  # noqa: F401

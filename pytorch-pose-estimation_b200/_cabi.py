@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("POSE_B200_LIB") or os.path.join(_HERE, "libpose_b200.
 
 KP_F32, KP_F64 = 0, 1
 F_GRAD, F_TARGET_OUT, F_DECODE, F_TMA, F_SIGMOID_CUDA = 1, 2, 4, 8, 16
+F_HEAD_LOGITS_OUT, F_HEAD_NO_RESIDUAL = 32, 64
 SIGMOID_ATEN_CPU, SIGMOID_ATEN_CUDA = 0, 1
 
 # Which torch.sigmoid the decoders reproduce bit for bit when ranking near-equal logits (include/pose_b200.h).
@@ -67,6 +68,9 @@ SIGNATURES = {
     "pose_oks_match": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _ull, _vp]),
     "pose_ap_accumulate_workspace_bytes": (_ull, [_i, _i, _i]),
     "pose_ap_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ull, _vp]),
+    "pose_sbp_head_workspace_bytes": (_ull, [_i, _i, _i]),
+    "pose_sbp_head_fused": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _f, _f, _d, _u,
+                                 _vp, _vp, _i, _i, _i, _vp, _ull, _vp]),
     "pose_sigmoid_ref_eval": (_i, [_vp, _vp, _ull, _i, _vp]),
     "pose_sigmoid_window_check": (_i, [_vp, _i, _vp]),
 }

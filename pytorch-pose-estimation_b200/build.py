@@ -20,7 +20,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-UNITS = ["api_core.cu", "api_sbp.cu", "api_spm.cu", "api_oks.cu"]
+UNITS = ["api_core.cu", "api_sbp.cu", "api_spm.cu", "api_oks.cu", "api_head.cu"]
 DEPS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
     os.path.join(ROOT, "include", "pose_b200.h")]
 LIB = os.path.join(HERE, "libpose_b200.so")

@@ -14,6 +14,12 @@
 #pragma once
 #include "common.cuh"
 
+// linkage of the non-template kernels of this header: a second translation unit that includes it (api_head.cu) compiles them
+// as file-local copies
+#ifndef POSE_GLOBAL
+#define POSE_GLOBAL __global__
+#endif
+
 namespace pose {
 
 constexpr int kSbpThreads = 256;               // 8 warps per CTA
@@ -244,7 +250,7 @@ struct SbpRenderParams {
 
 // one CTA per map: thread 0 derives the patch geometry while the template is staged; then a pure write stream
 template <int V>
-__global__ void __launch_bounds__(kSbpThreads) sbp_render_kernel(SbpRenderParams P) {
+POSE_GLOBAL void __launch_bounds__(kSbpThreads) sbp_render_kernel(SbpRenderParams P) {
     extern __shared__ float lut_s[];
     __shared__ Patch s_patch;
     const long long map = blockIdx.x;
@@ -377,7 +383,7 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
 // atomicMax; ONE barrier; thread 0 adds the 8 warps in fixed order, in fp64, writes the map's (S_pos, S_neg) pair -- no float
 // atomics anywhere: the loss is run-to-run deterministic -- and the joint row.
 template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
-__global__ void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE_MAP_MINB_RO) sbp_fused_kernel(SbpFusedParams P) {
+POSE_GLOBAL void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE_MAP_MINB_RO) sbp_fused_kernel(SbpFusedParams P) {
     __shared__ Patch s_patch;
     __shared__ float s_sum[kSbpWarps][3];
     __shared__ unsigned long long s_key;
@@ -515,7 +521,7 @@ __device__ __forceinline__ void tma_stage_maps(float* tiles, unsigned long long*
 }
 
 template <bool GRAD, bool DEC>
-__global__ void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD : POSE_TMA_MINB_RO) sbp_fused_tma_kernel(SbpFusedParams P) {
+POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD : POSE_TMA_MINB_RO) sbp_fused_tma_kernel(SbpFusedParams P) {
     constexpr int V = 4, MPC = tma_mpc(GRAD), WPM = POSE_TMA_WPM, TPM = 32 * WPM;
     extern __shared__ __align__(128) float tiles[];            // MPC maps of HW floats
     __shared__ __align__(8) unsigned long long s_bar[MPC];
@@ -580,7 +586,7 @@ __global__ void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD :
 }
 
 // ---------------------------------------------------------------- loss reduction kernel (helpers: common.cuh)
-__global__ void __launch_bounds__(256) loss_reduce_kernel(const double* __restrict__ pairs, int n, long long stride, double w0, double w1,
+POSE_GLOBAL void __launch_bounds__(256) loss_reduce_kernel(const double* __restrict__ pairs, int n, long long stride, double w0, double w1,
                                                           double inv_norm, float* __restrict__ loss_out, double* __restrict__ num_out) {
     pdl_wait();
     reduce_pairs_cta(pairs, n, stride, w0, w1, inv_norm, loss_out, num_out);
@@ -633,7 +639,7 @@ struct SbpEpilogueParams {
     const float* joints; const double* bbox; float* packed; int N, K; double in_h, in_w;
 };
 
-__global__ void __launch_bounds__(256) sbp_epilogue_kernel(SbpEpilogueParams P) {
+POSE_GLOBAL void __launch_bounds__(256) sbp_epilogue_kernel(SbpEpilogueParams P) {
     pdl_wait();
     if ((int)blockIdx.x >= P.bp_ctas) {
         if (reduce_slice_and_elect(P.partials, P.n_pairs, P.slices, P.ticket, P.R, (int)blockIdx.x - P.bp_ctas))
@@ -645,7 +651,7 @@ __global__ void __launch_bounds__(256) sbp_epilogue_kernel(SbpEpilogueParams P) 
 }
 
 // dlogits *= *g, whole launch is a no-op when *g == 1 (the usual loss.backward())
-__global__ void __launch_bounds__(256) scale_grad_kernel(float* __restrict__ d, const float* __restrict__ g, unsigned long long n) {
+POSE_GLOBAL void __launch_bounds__(256) scale_grad_kernel(float* __restrict__ d, const float* __restrict__ g, unsigned long long n) {
     const float s = __ldg(g);
     if (s == 1.0f) return;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -679,7 +685,7 @@ __device__ __forceinline__ float act(float v) { return SIG ? sigmoid_fast(v) : v
 
 // one CTA per map, every load issued up front (see the file header); no SFU work in the stream; one barrier
 template <int V, bool SIG>
-__global__ void __launch_bounds__(kSbpThreads, POSE_MAP_MINB_RO) sbp_decode_kernel(SbpDecodeParams P) {
+POSE_GLOBAL void __launch_bounds__(kSbpThreads, POSE_MAP_MINB_RO) sbp_decode_kernel(SbpDecodeParams P) {
     __shared__ unsigned long long s_key;
     const int tid = threadIdx.x;
     const long long map = blockIdx.x;
@@ -733,7 +739,7 @@ __global__ void __launch_bounds__(kSbpThreads, POSE_MAP_MINB_RO) sbp_decode_kern
 // bulk-async staged form of sbp_decode_kernel (16-byte aligned maps): POSE_TMA_MPC_RO maps per CTA, POSE_TMA_WPM warps per map,
 // see sbp_fused_tma_kernel
 template <bool SIG>
-__global__ void __launch_bounds__(tma_threads(false), POSE_TMA_MINB_RO) sbp_decode_tma_kernel(SbpDecodeParams P) {
+POSE_GLOBAL void __launch_bounds__(tma_threads(false), POSE_TMA_MINB_RO) sbp_decode_tma_kernel(SbpDecodeParams P) {
     constexpr int V = 4, MPC = tma_mpc(false), WPM = POSE_TMA_WPM, TPM = 32 * WPM;
     extern __shared__ __align__(128) float tiles[];
     __shared__ __align__(8) unsigned long long s_bar[MPC];
@@ -796,7 +802,7 @@ struct SbpDecodeFlipParams {
 };
 
 template <int V, bool SIG>
-__global__ void __launch_bounds__(kSbpThreads) sbp_decode_flip_kernel(SbpDecodeFlipParams P) {
+POSE_GLOBAL void __launch_bounds__(kSbpThreads) sbp_decode_flip_kernel(SbpDecodeFlipParams P) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * kSbpWarps + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kSbpWarps;
@@ -861,7 +867,7 @@ __global__ void __launch_bounds__(kSbpThreads) sbp_decode_flip_kernel(SbpDecodeF
 }
 
 // ---------------------------------------------------------------- stand-alone back-projection (one warp per sample)
-__global__ void __launch_bounds__(256) sbp_backproject_kernel(const float* __restrict__ joints, const double* __restrict__ bbox,
+POSE_GLOBAL void __launch_bounds__(256) sbp_backproject_kernel(const float* __restrict__ joints, const double* __restrict__ bbox,
                                                               float* __restrict__ packed, int N, int K, double in_h, double in_w) {
     const int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (n < N) backproject_sample(joints, bbox, packed, n, K, in_h, in_w, threadIdx.x & 31);
@@ -869,7 +875,7 @@ __global__ void __launch_bounds__(256) sbp_backproject_kernel(const float* __res
 
 // ---------------------------------------------------------------- the reference sigmoids (diagnostics)
 // y[i] = sigmoid_ref(x[i]): lets a test compare the device restatements with torch.sigmoid bit for bit
-__global__ void sigmoid_ref_eval_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned long long n, int sig_ref) {
+POSE_GLOBAL void sigmoid_ref_eval_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned long long n, int sig_ref) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = sigmoid_ref(x[i], sig_ref);
 }
@@ -877,7 +883,7 @@ __global__ void sigmoid_ref_eval_kernel(const float* __restrict__ x, float* __re
 // For fp32 m in (-80, +inf], every 61st float: nothing below sigmoid_window_lo(m) may reach sigmoid_ref(m) -- probed at the 64 floats just below
 // the window and at 64 geometrically spaced points further down (the references are monotone up to a few ulp, so these are
 // where a violation would be).  Counts violations.
-__global__ void sigmoid_window_check_kernel(unsigned long long* violations, int sig_ref) {
+POSE_GLOBAL void sigmoid_window_check_kernel(unsigned long long* violations, int sig_ref) {
     const uint32_t k0 = float_key(-80.0f), k1 = float_key(INFINITY);
     const uint64_t total = (uint64_t)(k1 - k0);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
