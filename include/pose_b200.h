@@ -290,7 +290,7 @@ int pose_ap_accumulate(const long long* order, const int* dt_match, const unsign
  *   POSE_F_DECODE); logits_out only with POSE_F_HEAD_LOGITS_OUT.  Decode: argmax in LOGIT space, first index among equal
  *   logits (all logits >= 17.5 tie: their sigmoid is 1.0f), confidence = the reference sigmoid of the maximum.
  *   Constraints (POSE_EINVAL otherwise): C % 32 == 0 and 48*C*4 bytes + 4 tiles must fit in shared memory (C <= 640),
- *   (H*W) % 128 == 0, K <= 24, template side <= 24.
+ *   (H*W) % 128 == 0, K <= 17, template side <= 24.
  *   tuning: 0 = defaults; bits 0-7 feature stages in shared memory; bit 24 selects the variant that keeps the feature
  *   residuals in shared memory instead of tensor memory (bits 8-15: its residual stages) -- slower, kept for comparison.
  *   Three launches: weight split, the fused kernel (persistent, one CTA per SM, whole images), the epilogue of pose_sbp_fused.

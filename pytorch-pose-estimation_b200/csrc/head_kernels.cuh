@@ -13,15 +13,15 @@
 //                  [24, 24+K) hold Wl -- both sets ride in ONE N = 48 instruction, and the epilogue adds column k and column 24+k;
 //   X  = Xh + Xl   Xh is what the tensor core sees when it reads the raw fp32 tile; Xl = X - (X & 0xffffe000) is computed by four
 //                  "residual" warps from the staged tile into a second shared-memory tile and multiplied by the same B operand.
-// D = Xh Wh + Xh Wl + Xl Wh + Xl Wl, every product exact in the fp32 accumulator: what is left is the rounding of the
-// accumulation itself (measured: tests/test_head_gpu.py compares with an fp64 convolution next to cuDNN's fp32 result).
+// D = Xh Wh + Xh Wl (main accumulator) + Xl Wh + Xl Wl (correction accumulator), every product exact in fp32: what is left is the
+// rounding of the accumulation itself (measured: tests/test_head_gpu.py compares with an fp64 convolution next to cuDNN's fp32 result).
 //
 // Data flow of one CTA (persistent, one per SM, whole images: the per-map reductions of loss and argmax stay inside the CTA):
 //   warp 0      producer: TMA tensor loads (cp.async.bulk.tensor.4d, 128-byte swizzle with 32-byte atoms) of [32 channels x 128 pixels] fp32 tiles
 //               (16 KB) of X into a ring of shared-memory stages, completion on mbarriers; W (hi|lo, 48 x C) is loaded once and
 //               stays in shared memory (96 KB at C = 512);
-//   warps 6-9   residual: raw stage -> Xl stage (same swizzled layout, element for element), fence.proxy.async, mbarrier arrive;
-//   warp 1      MMA issuer (one thread): 4 + 4 tcgen05.mma per stage (A = MN-major SW128-base-32B descriptor on the raw / residual tile,
+//   warps 6-13  residual (two groups of four, alternate stages): raw stage -> Xl stage (same swizzled layout, element for element), fence.proxy.async, mbarrier arrive;
+//   warps 1, 14 MMA issuers (one thread each: raw / residual products into separate accumulators): 4 + 4 tcgen05.mma per stage (A = MN-major SW128-base-32B descriptor on the raw / residual tile,
 //               B = K-major SW128 descriptor on the W chunk), tcgen05.commit releases the stages and, after the last channel
 //               chunk, hands the accumulator (128 lanes x 48 columns of TMEM, double buffered) to the epilogue;
 //   warps 2-5   epilogue: tcgen05.ld (lane = pixel, 48 columns), logit = D[k] + D[24+k], then the arithmetic of
@@ -42,10 +42,12 @@ constexpr int kHeadM = 128;                      // pixels per tile = UMMA M
 constexpr int kHeadKC = 32;                      // channels per stage = one 128-byte swizzle span of a W row
 constexpr int kHeadN = 48;                       // UMMA N: rows [0,K) tf32 heads of W, rows [24,24+K) residuals
 constexpr int kHeadLoRow = 24;
-constexpr int kHeadMaxK = 24;                    // joints supported (17 COCO, 11 PIS)
+constexpr int kHeadMaxK = 17;                    // joints supported (17 COCO, 11 PIS); sizes the per-thread accumulators of the epilogue
 constexpr int kHeadStageBytes = kHeadM * kHeadKC * 4;        // 16 KB
 constexpr int kHeadWChunkBytes = kHeadN * 128;               // 6 KB: 48 rows x 32 channels
-constexpr int kHeadThreads = 320;
+constexpr int kHeadConvGroups = 2;               // groups of four residual warps (tensor-memory variant)
+constexpr int kHeadIssuer2 = 6 + 4 * kHeadConvGroups;        // warp that issues the residual MMAs (tensor-memory variant)
+constexpr int kHeadThreads = (kHeadIssuer2 + 1) * 32;
 constexpr int kHeadMaxStages = 8;
 constexpr int kHeadAccCols = 64;                 // TMEM columns reserved per accumulator (48 used)
 constexpr int kHeadTmemRing = 4;                 // A tiles (raw + residual, 64 columns each) in tensor memory
@@ -117,19 +119,22 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     uint8_t* const lo_s = raw_s + (size_t)P.raw_stages * kHeadStageBytes;
     const bool residual = !(P.flags & kHeadNoResidual);
     const int tiles = P.tiles_per_img;
-    // TMEM: columns [0,128) two accumulators; RT: columns [128, 128 + 64*kHeadTmemRing) the A ring (32 raw + 32 residual columns per stage)
-    constexpr uint32_t kTmemCols = RT ? 512 : 128;
-    constexpr uint32_t kARing0 = 2 * kHeadAccCols;
+    // TMEM: columns [0,256) two buffers x (main accumulator | correction accumulator); RT: columns [256, 256 + 64*kHeadTmemRing) the A
+    // ring (32 raw + 32 residual columns per stage).  The residual products go to their OWN accumulator: back-to-back MMAs into one
+    // accumulator serialise on the accumulate latency (~125 cycles measured for these N = 48 instructions, whose work is 24 cycles),
+    // and the small terms do not suffer the rounding of the large running sum.
+    constexpr uint32_t kTmemCols = RT ? 512 : 256;
+    constexpr uint32_t kARing0 = 4 * kHeadAccCols;
 
     if (tid == 0) {
         for (int s = 0; s < kHeadMaxStages; ++s) {
             head::mbar_init(&bar_full_raw[s], 1);
             head::mbar_init(&bar_empty_raw[s], RT ? 4 : 1);
             head::mbar_init(&bar_full_lo[s], 4);
-            head::mbar_init(&bar_empty_lo[s], 1);
+            head::mbar_init(&bar_empty_lo[s], (RT && residual) ? 2 : 1);        // RT: one commit per issuing thread
         }
         head::mbar_init(&bar_w, 1);
-        for (int b = 0; b < 2; ++b) { head::mbar_init(&bar_acc_full[b], 1); head::mbar_init(&bar_acc_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { head::mbar_init(&bar_acc_full[b], (RT && residual) ? 2 : 1); head::mbar_init(&bar_acc_empty[b], 4); }
         head::mbar_init_fence();
         head::tma_prefetch_desc(&tmX);
         head::tma_prefetch_desc(&tmW);
@@ -158,41 +163,54 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                         if (++s == P.raw_stages) { s = 0; ph ^= 1u; }
                     }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+    } else if (warp == 1 || warp == kHeadIssuer2) {
+        // ------------------------------------------------------------ MMA issuers (one thread each)
+        // What bounds an issuing thread is its own instruction stream (a lone thread on the uniform datapath: ~45 cycles per
+        // tcgen05.mma in the tightest loop, tools/umma_bench.cu; 125 measured with descriptors rebuilt per instruction), not the
+        // tensor pipe (N = 48: 24 cycles of work).  So the descriptors are advanced with one 32-bit add, barriers are addressed
+        // by 32-bit shared addresses, and -- RT -- the raw and the residual MMAs are issued by TWO threads in different warps into
+        // separate accumulators.
+        const bool second = warp == kHeadIssuer2;
+        if (lane == 0 && (!second || (RT && residual))) {
             head::mbar_wait(&bar_w, 0);
             head::tc_fence_after();
             constexpr uint32_t idesc_smem_a = head::umma_idesc_tf32(kHeadN, /*A MN-major*/ 1, /*B K-major*/ 0);
             constexpr uint32_t idesc_tmem_a = head::umma_idesc_tf32(kHeadN, 0, 0);
             const uint32_t w_addr = head::smem_u32(w_s), raw_addr = head::smem_u32(raw_s), lo_addr = head::smem_u32(lo_s);
+            const uint32_t full_lo0 = head::smem_u32(&bar_full_lo[0]), empty_lo0 = head::smem_u32(&bar_empty_lo[0]);
+            const uint32_t acc_full0 = head::smem_u32(&bar_acc_full[0]), acc_empty0 = head::smem_u32(&bar_acc_empty[0]);
+            // B descriptor of W chunk 0, k-step 0 (K-major SW128: LBO 16, SBO 1024): low word carries the address, +384 per chunk, +2 per k-step
+            const uint64_t bdesc0 = head::umma_smem_desc(w_addr, 16, 1024, head::kUmmaSw128);
+            const uint32_t bd_hi = (uint32_t)(bdesc0 >> 32), bd_lo0 = (uint32_t)bdesc0;
             int rs = 0, ls = 0;
             uint32_t rph = 0, lph = 0;
             int it = 0;
             for (int img = blockIdx.x; img < P.N; img += gridDim.x)
                 for (int t = 0; t < tiles; ++t, ++it) {
                     const int buf = it & 1;
-                    head::mbar_wait(&bar_acc_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);      // epilogue has drained this buffer
+                    head::mbar_wait_u32(acc_empty0 + 8u * buf, (((uint32_t)it >> 1) & 1u) ^ 1u);      // epilogue has drained this buffer
                     head::tc_fence_after();
-                    const uint32_t d = tmem + (uint32_t)(buf * kHeadAccCols);
-                    for (int kc = 0; kc < P.n_kc; ++kc) {
-                        const uint32_t wb = w_addr + (uint32_t)(kc * kHeadWChunkBytes);
-                        if (RT) {
-                            head::mbar_wait(&bar_full_lo[ls], lph);
+                    const uint32_t d = tmem + (uint32_t)(buf * 2 * kHeadAccCols), dc = d + kHeadAccCols;
+                    if (RT) {
+                        const uint32_t dd = second ? dc : d;
+                        const uint32_t a_off = tmem + kARing0 + (second ? 32u : 0u);
+                        uint32_t bd_lo = bd_lo0;
+                        uint32_t acc = 0u;
+                        for (int kc = 0; kc < P.n_kc; ++kc, bd_lo += kHeadWChunkBytes / 16) {
+                            head::mbar_wait_u32(full_lo0 + 8u * ls, lph);
                             head::tc_fence_after();
-                            const uint32_t a_t = tmem + kARing0 + (uint32_t)(ls * 64);
-#pragma unroll
-                            for (int ks = 0; ks < kHeadKC / 8; ++ks)
-                                head::umma_tf32_ts(d, a_t + ks * 8, head::umma_smem_desc(wb + ks * 32, 16, 1024, head::kUmmaSw128), idesc_tmem_a,
-                                                   (uint32_t)((kc | ks) != 0));
-                            if (residual) {
-#pragma unroll
-                                for (int ks = 0; ks < kHeadKC / 8; ++ks)
-                                    head::umma_tf32_ts(d, a_t + 32 + ks * 8, head::umma_smem_desc(wb + ks * 32, 16, 1024, head::kUmmaSw128), idesc_tmem_a, 1u);
-                            }
-                            head::umma_commit(&bar_empty_lo[ls]);
+                            const uint32_t a_t = a_off + (uint32_t)(ls * 64);
+                            head::umma_tf32_ts(dd, a_t, ((uint64_t)bd_hi << 32) | bd_lo, idesc_tmem_a, acc);
+                            head::umma_tf32_ts(dd, a_t + 8, ((uint64_t)bd_hi << 32) | (bd_lo + 2), idesc_tmem_a, 1u);
+                            head::umma_tf32_ts(dd, a_t + 16, ((uint64_t)bd_hi << 32) | (bd_lo + 4), idesc_tmem_a, 1u);
+                            head::umma_tf32_ts(dd, a_t + 24, ((uint64_t)bd_hi << 32) | (bd_lo + 6), idesc_tmem_a, 1u);
+                            head::umma_commit_u32(empty_lo0 + 8u * ls);
+                            acc = 1u;
                             if (++ls == kHeadTmemRing) { ls = 0; lph ^= 1u; }
-                        } else {
+                        }
+                    } else {
+                        for (int kc = 0; kc < P.n_kc; ++kc) {
+                            const uint32_t wb = w_addr + (uint32_t)(kc * kHeadWChunkBytes);
                             head::mbar_wait(&bar_full_raw[rs], rph);
                             head::tc_fence_after();
                             const uint32_t a0 = raw_addr + (uint32_t)(rs * kHeadStageBytes);
@@ -206,8 +224,8 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                                 const uint32_t l0 = lo_addr + (uint32_t)(ls * kHeadStageBytes);
 #pragma unroll
                                 for (int ks = 0; ks < kHeadKC / 8; ++ks)
-                                    head::umma_tf32(d, head::umma_smem_desc(l0 + ks * 1024, 32 * 128, 512, head::kUmmaSw128Base32),
-                                                    head::umma_smem_desc(wb + ks * 32, 16, 1024, head::kUmmaSw128), idesc_smem_a, 1u);
+                                    head::umma_tf32(dc, head::umma_smem_desc(l0 + ks * 1024, 32 * 128, 512, head::kUmmaSw128Base32),
+                                                    head::umma_smem_desc(wb + ks * 32, 16, 1024, head::kUmmaSw128), idesc_smem_a, (uint32_t)((kc | ks) != 0));
                                 head::umma_commit(&bar_empty_lo[ls]);
                                 if (++ls == P.lo_stages) { ls = 0; lph ^= 1u; }
                             }
@@ -215,10 +233,10 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                             if (++rs == P.raw_stages) { rs = 0; rph ^= 1u; }
                         }
                     }
-                    head::umma_commit(&bar_acc_full[buf]);
+                    head::umma_commit_u32(acc_full0 + 8u * buf);
                 }
         }
-    } else if (warp >= 6) {
+    } else if (warp >= 6 && warp < kHeadIssuer2) {
         // ------------------------------------------------------------ residual warps
         const int n_stage_img = tiles * P.n_kc;
         if (RT) {
@@ -227,35 +245,48 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             // staged tile: [4 pixel blocks][32 channels][128-byte rows], 32-byte chunks XOR-swizzled with (channel & 3)
             const uint32_t lane_off = (uint32_t)(q * 4096 + (lane & 7) * 4);
             const uint32_t chunk = (uint32_t)(lane >> 3);
-            int rs = 0, ls = 0;
+            // Two groups of four warps take alternate stages (group = (warp - 6) / 4): what bounds this role is the latency of its
+            // serial chain per stage (two mbarrier waits, 32 loads, two tcgen05.st, wait::st, fence, arrive: ~1000 cycles measured
+            // with one group, ncu source view), not any pipe, so a second group doubles its rate.
+            const int grp = (warp - 6) >> 2;
+            int n_img = 0;
+            for (int img = blockIdx.x; img < P.N; img += gridDim.x) ++n_img;
+            const long long total = (long long)n_img * n_stage_img;
+            int rs = grp, ls = grp;                     // stage st uses feature stage st % raw_stages and A-ring slot st % 4
             uint32_t rph = 0, lph = 0;
-            for (int img = blockIdx.x; img < P.N; img += gridDim.x)
-                for (int st = 0; st < n_stage_img; ++st) {
-                    head::mbar_wait(&bar_full_raw[rs], rph);
-                    const uint8_t* src = raw_s + (size_t)rs * kHeadStageBytes + lane_off;
-                    uint32_t v[32];
+            if (rs >= P.raw_stages) { rs -= P.raw_stages; rph ^= 1u; }
+            const uint32_t full_raw0 = head::smem_u32(&bar_full_raw[0]), empty_raw0 = head::smem_u32(&bar_empty_raw[0]);
+            const uint32_t full_lo0 = head::smem_u32(&bar_full_lo[0]), empty_lo0 = head::smem_u32(&bar_empty_lo[0]);
+            const uint32_t src0 = head::smem_u32(raw_s) + lane_off;
+            const uint32_t a_ring = tmem + ((uint32_t)(q * 32) << 16) + kARing0;
+            for (long long st = grp; st < total; st += kHeadConvGroups) {
+                head::mbar_wait_u32(full_raw0 + 8u * rs, rph);
+                const uint32_t src = src0 + (uint32_t)rs * kHeadStageBytes;
+                uint32_t v[32];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = *reinterpret_cast<const uint32_t*>(src + c * 128 + ((chunk ^ (uint32_t)(c & 3)) << 5));
-                    head::mbar_wait(&bar_empty_lo[ls], lph ^ 1u);
-                    head::tc_fence_after();
-                    const uint32_t a_t = tmem + ((uint32_t)(q * 32) << 16) + kARing0 + (uint32_t)(ls * 64);
-                    head::tmem_st_32x32(a_t, v);
-                    if (residual) {
+                for (int c = 0; c < 32; ++c) v[c] = head::lds_u32(src + c * 128 + ((chunk ^ (uint32_t)(c & 3)) << 5));
+                head::mbar_wait_u32(empty_lo0 + 8u * ls, lph ^ 1u);
+                head::tc_fence_after();
+                const uint32_t a_t = a_ring + (uint32_t)(ls * 64);
+                head::tmem_st_32x32(a_t, v);
+                if (residual) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(head_residual(__uint_as_float(v[c])));
-                        head::tmem_st_32x32(a_t + 32, v);
-                    }
-                    head::tmem_st_wait();
-                    head::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        head::mbar_arrive(&bar_full_lo[ls]);
-                        head::mbar_arrive(&bar_empty_raw[rs]);       // the tile is in registers / TMEM: the stage may be refilled
-                    }
-                    if (++rs == P.raw_stages) { rs = 0; rph ^= 1u; }
-                    if (++ls == kHeadTmemRing) { ls = 0; lph ^= 1u; }
+                    for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(head_residual(__uint_as_float(v[c])));
+                    head::tmem_st_32x32(a_t + 32, v);
                 }
-        } else if (residual) {
+                head::tmem_st_wait();
+                head::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    head::mbar_arrive_u32(full_lo0 + 8u * ls);
+                    head::mbar_arrive_u32(empty_raw0 + 8u * rs);         // the tile is in TMEM: the stage may be refilled
+                }
+                rs += kHeadConvGroups;
+                if (rs >= P.raw_stages) { rs -= P.raw_stages; rph ^= 1u; }
+                ls += kHeadConvGroups;
+                if (ls >= kHeadTmemRing) { ls -= kHeadTmemRing; lph ^= 1u; }
+            }
+        } else if (residual && warp < 10) {
             const int ct = tid - 6 * 32;
             int rs = 0, ls = 0;
             uint32_t rph = 0, lph = 0;
@@ -281,7 +312,7 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     if (++ls == P.lo_stages) { ls = 0; lph ^= 1u; }
                 }
         }
-    } else {
+    } else if (warp >= 2 && warp < 6) {
         // ------------------------------------------------------------ epilogue warps 2-5: TMEM lane quarter = warp % 4
         const int q = warp & 3;
         const int et = q * 32 + lane;                  // row of the tile = pixel within the tile (also the index among the 128 epilogue threads)
@@ -296,20 +327,38 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 s_patch[pb][et] = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
             }
             head::bar_sync(1, 128);
-            float apos[kHeadMaxK], aneg[kHeadMaxK], bv[kHeadMaxK];
+            // loss sums: every (tile, joint) contribution is summed over the warp at once and kept by lane k (two registers per
+            // thread instead of 2 x 17); the running argmax stays per thread (the pixels of a thread come in increasing order)
+            float my_pos = 0.0f, my_neg = 0.0f, bv[kHeadMaxK];
             int bi[kHeadMaxK];
 #pragma unroll
-            for (int k = 0; k < kHeadMaxK; ++k) { apos[k] = 0.0f; aneg[k] = 0.0f; bv[k] = -INFINITY; bi[k] = 0x7fffffff; }
+            for (int k = 0; k < kHeadMaxK; ++k) { bv[k] = -INFINITY; bi[k] = 0x7fffffff; }
             for (int t = 0; t < tiles; ++t, ++it) {
                 const int buf = it & 1;
                 head::mbar_wait(&bar_acc_full[buf], ((uint32_t)it >> 1) & 1u);
                 head::tc_fence_after();
                 {
-                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kHeadAccCols);
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * kHeadAccCols);
                     uint32_t r0[32], r1[16];
+                    float xs[kHeadMaxK];
+                    auto fold = [&](bool first) {              // xs[k] (+)= D[k] + D[24 + k]
+#pragma unroll
+                        for (int k = 0; k < kHeadMaxK; ++k) {
+                            const float lo = __uint_as_float(k + kHeadLoRow < 32 ? r0[(k + kHeadLoRow) & 31] : r1[(k + kHeadLoRow - 32) & 15]);
+                            const float v = __uint_as_float(r0[k]) + lo;
+                            xs[k] = first ? v : xs[k] + v;
+                        }
+                    };
+                    if (residual) {                            // the correction accumulator first: small terms are summed before the large one
+                        head::tmem_ld_32x32(taddr + kHeadAccCols, r0);
+                        head::tmem_ld_32x16(taddr + kHeadAccCols + 32, r1);
+                        head::tmem_ld_wait();
+                        fold(true);
+                    }
                     head::tmem_ld_32x32(taddr, r0);
                     head::tmem_ld_32x16(taddr + 32, r1);
                     head::tmem_ld_wait();
+                    fold(!residual);
                     head::tc_fence_before();                   // the accumulator is in registers: give the buffer back to the MMA warp
                     __syncwarp();
                     if (lane == 0) head::mbar_arrive(&bar_acc_empty[buf]);
@@ -319,13 +368,16 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < kHeadMaxK; ++k) {
                         if (k < K) {
-                            const float lo = __uint_as_float(k + kHeadLoRow < 32 ? r0[(k + kHeadLoRow) & 31] : r1[(k + kHeadLoRow - 32) & 15]);
-                            const float x = __uint_as_float(r0[k]) + lo;
+                            const float x = xs[k];
                             const Patch& pt = s_patch[pb][k];
                             float tt = 0.0f;
                             if (row >= pt.py0 && row < pt.py1 && col >= pt.px0 && col < pt.px1) tt = s_lut[(row - pt.uly) * P.lut_n + (col - pt.ulx)];
                             const float s = sigmoid_fast(x);
-                            const float g = loss_elem<true>(s, tt, P.gpos, P.gneg, apos[k], aneg[k]);
+                            float cp = 0.0f, cn = 0.0f;
+                            const float g = loss_elem<true>(s, tt, P.gpos, P.gneg, cp, cn);
+                            cp = warp_sum(cp);
+                            cn = warp_sum(cn);
+                            if (lane == k) { my_pos += cp; my_neg += cn; }
                             if (want_grad) __stcs(P.dlogits + o0 + (size_t)k * HW, g);
                             if (want_logits) __stcs(P.logits_out + o0 + (size_t)k * HW, x);
                             const float xc = x > 17.5f ? 17.5f : x;       // sigmoid is exactly 1 in fp32 from ~17.33 on: a plateau, first index wins
@@ -338,13 +390,13 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 #pragma unroll
             for (int k = 0; k < kHeadMaxK; ++k) {
                 if (k < K) {
-                    const float a = warp_sum(apos[k]), b = warp_sum(aneg[k]);
                     float v = bv[k];
                     int i = bi[k];
                     if (want_dec) warp_argmax_first(v, i);
-                    if (lane == 0) { s_sum[q][k][0] = a; s_sum[q][k][1] = b; s_bv[q][k] = v; s_bi[q][k] = i; }
+                    if (lane == 0) { s_bv[q][k] = v; s_bi[q][k] = i; }
                 }
             }
+            if (lane < K) { s_sum[q][lane][0] = my_pos; s_sum[q][lane][1] = my_neg; }
             head::bar_sync(1, 128);
             if (et < K) {
                 double a = 0.0, b = 0.0;

@@ -43,6 +43,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// the same on 32-bit shared-window addresses (no generic -> shared conversion in the loop)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
+    uint32_t done = 0;
+#if POSE_HEAD_SPIN_LIMIT
+    long long spins = 0;
+#endif
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+#if POSE_HEAD_SPIN_LIMIT
+        if (!done && ++spins > (long long)POSE_HEAD_SPIN_LIMIT) { asm volatile("trap;"); }
+#endif
+    }
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---------------------------------------------------------------- TMA: 2-D tiled tensor load, completion on an mbarrier
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tensor_map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -93,6 +121,10 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 // all MMAs issued so far by this thread -> one arrival on `bar` when they have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte offsets (all >> 4),
