@@ -19,7 +19,7 @@ memory).  Prints ONE JSON line on rank 0:
                           the per-sample / per-joint nms_sbp loop on a bounded sample
     cpu_baseline          the reference's CPU algorithm (oracle port) on this box's host cores (N=1 only)
     exchange_check        N>1: parity of the three exchange implementations + a 20 000-step stress of the in-band mode
-    extra_workloads       configs 3 (as written), 4 (SPM) and 5 (decode sweep), timed outside the headline region
+    extra_workloads       configs 3 (as written), 4 (SPM), 5 (decode sweep) and the f-3 head fusion, timed outside the headline region
 """
 import argparse
 import json
@@ -492,7 +492,7 @@ def run_cuda(args):
         except Exception as e:      # noqa: BLE001
             extras.append({"workload": "config3 as written", "error": f"{type(e).__name__}: {e}"})
         if rank == 0 and world == 1:
-            for fn in (xw.spm_config4, xw.decode_config5):
+            for fn in (xw.spm_config4, xw.decode_config5, xw.head_fusion):
                 try:
                     extras += fn(pb, dev, peak)
                 except Exception as e:      # noqa: BLE001

@@ -85,6 +85,43 @@ def decode_config5(pb, dev, peak, reps=20):
     return out
 
 
+def head_fusion(pb, dev, peak, b=1024, c=512, k=17, h=64, w=48, reps=5):
+    """the detector's 1x1 head (512 -> 17, models/detector/sbp.py:35-37) fused with loss + dlogits + decode on tcgen05
+    (pose_sbp_head_fused), next to the unfused pair on the same box: torch's fp32 conv2d (cuDNN / cuBLAS, TF32 off -- the
+    reference's arithmetic) writing the logits, then the fused loss kernel reading them."""
+    gen = torch.Generator(device=dev).manual_seed(0)
+    feats = torch.randn((b, c, h, w), generator=gen, device=dev).relu_()
+    weight = torch.randn((k, c), generator=gen, device=dev) * (2.0 / c) ** 0.5
+    kp = torch.stack([torch.rand(b, k, device=dev, generator=gen, dtype=torch.float64) * w,
+                      torch.rand(b, k, device=dev, generator=gen, dtype=torch.float64) * h], dim=-1)
+    kp[torch.rand(b, k, device=dev, generator=gen) >= 0.85] = -1.0
+    dl = torch.empty((b, k, h, w), device=dev)
+    jo = torch.empty((b, k, 3), device=dev)
+    fbytes, lbytes = feats.numel() * 4, dl.numel() * 4
+    out = []
+    ms = graph_time(lambda: pb.sbp_head_fused(feats, weight, kp, sigma=2, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0,
+                                              out={"dlogits": dl, "joints": jo}), reps)
+    e = _entry(f"f-3 head fusion, training form: 1x1 conv {c}->{k} (tcgen05, 3xTF32) + loss + dlogits + decode, B={b} x {c} x {h}x{w} features; "
+               "logits never in HBM", ms, b, "images", (fbytes + lbytes) / b, peak)
+    out.append(e)
+    ms_v = graph_time(lambda: pb.sbp_head_fused(feats, weight, kp, sigma=2, want_grad=False, decode=True, conf_threshold=0.25, coord_scale=4.0,
+                                                out={"joints": jo}), reps)
+    out.append(_entry(f"f-3 head fusion, validation form (loss + decode, nothing written but {b * k} joint rows), B={b}", ms_v, b, "images",
+                      fbytes / b, peak))
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    w4 = weight.view(k, c, 1, 1)
+    ms_conv = graph_time(lambda: torch.nn.functional.conv2d(feats, w4), reps)
+    ms_pair = graph_time(lambda: pb.sbp_fused(torch.nn.functional.conv2d(feats, w4), keypoints=kp, sigma=2, want_grad=True, decode=True,
+                                              conf_threshold=0.25, coord_scale=4.0, out={"dlogits": dl, "joints": jo}), reps)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    e["unfused_baseline"] = {"what": "torch conv2d fp32 (library kernel, TF32 off) -> logits in HBM -> pose_sbp_fused (render+loss+grad+decode), same inputs",
+                             "conv2d_ms": ms_conv, "conv2d_then_fused_loss_ms": ms_pair, "speedup": ms_pair / ms,
+                             "algorithmic_bytes": fbytes + 3 * lbytes}
+    return out
+
+
 def config3_as_written(pb, pd, dev, peak, world, rank, global_batch=32768, reps=10):
     """BASELINE.json configs[2]: global batch 32 768 split over the ranks (N=2: 16 384 images per GPU), fused step with the
     exchange, graph replay, max over ranks."""
