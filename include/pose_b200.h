@@ -241,6 +241,14 @@ int pose_spm_rescale(const float* kps, const int* counts, const long long* image
 int pose_spm_gather(const float* roots, const float* disp, float* kps, int n_roots, int K, int R,
                     double dist_threshold, pose_stream_t stream);
 
+/* ---- SPM joint gather with hierarchical displacement chaining -- NOT in the reference (get_spm_keypoints reads every joint at
+ *      the root pixel, utils/spm_utils.py:187-189); SURVEY 8 f-4, opt-in, parity unpinned.  parent [K] int32 on the device:
+ *      parent[k] = the joint k's displacement is relative to (-1 = the root).  Joint k is read at its parent's decoded position
+ *      (truncated to a pixel) and added to it with the arithmetic of get_spm_keypoints; an absent / off-map parent makes every
+ *      descendant (0,0,0); chains longer than 16 are rejected as absent.  All parent[k] = -1: bit-identical to pose_spm_gather. */
+int pose_spm_gather_chain(const float* roots, const float* disp, const int* parent, float* kps, int n_roots, int K, int R,
+                          double dist_threshold, pose_stream_t stream);
+
 /* ---- OKS / AP -- the keypoint evaluation behind SBPmAPCOCO.result utils/sbp_utils.py:166-189, SPMmAPCOCO.result
  *      utils/spm_utils.py:325-351 and SBPmAPPIS.result (utils/sbp_pis_utils.py), which the reference delegates to
  *      pycocotools COCOeval(gt, dt, "keypoints").evaluate()/.accumulate() (third party, unpinned: PARITY UNPINNED).

@@ -194,6 +194,45 @@ def spm_keypoints(root_joints, disp, dist_threshold):
     return torch.stack(out)
 
 
+def spm_keypoints_chained(root_joints, disp, parents, dist_threshold, max_depth=16):
+    """PARITY UNPINNED (not in the reference: get_spm_keypoints is single hop, utils/spm_utils.py:187-189).
+
+    Hierarchical SPR decode in the reference's arithmetic: joint k is read at the decoded position of parents[k] (-1 = the root),
+    truncated to a pixel, and added to that position (fp32 mul by z, fp32 add); the fp64 sqrt of the fp32 squared distance to the
+    parent `< dist_threshold`, an off-map parent or a chain deeper than `max_depth` make the joint and its descendants (0,0,0)."""
+    if root_joints.size(0) == 0:
+        return root_joints
+    k2, res, _ = disp.shape
+    z = math.sqrt(res ** 2 + res ** 2)
+    out = []
+    for r in root_joints:
+        x0, y0, c = r
+        row = []
+        for k in range(k2 // 2):
+            path, j = [], k
+            while j >= 0 and len(path) < max_depth:
+                path.append(j)
+                j = int(parents[j])
+            ok = j < 0
+            px, py = x0, y0
+            for j in reversed(path):
+                if not ok:
+                    break
+                xi, yi = int(px), int(py)
+                if not (0 <= xi < res and 0 <= yi < res):
+                    ok = False
+                    break
+                kx = disp[2 * j][yi, xi] * z + px
+                ky = disp[2 * j + 1][yi, xi] * z + py
+                if math.sqrt((px - kx) ** 2 + (py - ky) ** 2) < dist_threshold:
+                    ok = False
+                    break
+                px, py = kx, ky
+            row.append(torch.stack([px, py, c]) if ok else torch.zeros(3))
+        out.append(torch.stack(row))
+    return torch.stack(out)
+
+
 def spm_decode(x, input_size, sigma, conf_threshold, pred=True):
     """x [1,1+2K,R,R] -> (root_joints [N,3], keypoints [N,K,3]) at input-size scale (utils/spm_utils.py:225-250)."""
     assert x.size(0) == 1

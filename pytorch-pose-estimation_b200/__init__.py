@@ -24,6 +24,6 @@ from .sbp_utils import (DecodeSBP, SBPHeatmapGenerator, SBPmAPCOCO, backproject_
                         nms_sbp, packed_to_results)
 from .spm_loss import SPMLoss, spm_fused, spm_loss_fused  # noqa: F401
 from .spm_utils import (DecodeSPM, SPMDisplacementGenerator, SPMHeatmapGenerator, SPMMaskGenerator, SPMmAPCOCO,  # noqa: F401
-                        get_spm_keypoints, nms_spm, spm_decode_batch, spm_render_batch)
+                        get_spm_keypoints, get_spm_keypoints_chained, nms_spm, spm_decode_batch, spm_render_batch)
 
 __version__ = "0.1.0"

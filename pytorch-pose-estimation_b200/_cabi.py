@@ -63,6 +63,7 @@ SIGNATURES = {
     "pose_spm_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _d, _i, _i, _f, _vp]),
     "pose_spm_rescale": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "pose_spm_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp]),
+    "pose_spm_gather_chain": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _vp]),
     "pose_oks_matrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _c.c_longlong, _i, _vp]),
     "pose_oks_match_workspace_bytes": (_ull, [_i, _i, _i]),
     "pose_oks_match": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _ull, _vp]),

@@ -246,4 +246,14 @@ int pose_spm_gather(const float* roots, const float* disp, float* kps, int n_roo
     return check_launch("spm_gather");
 }
 
+int pose_spm_gather_chain(const float* roots, const float* disp, const int* parent, float* kps, int n_roots, int K, int R,
+                          double dist_threshold, pose_stream_t stream) {
+    if (n_roots < 0 || K <= 0 || R <= 0 || !disp || !parent || (n_roots > 0 && (!roots || !kps))) return fail(POSE_EINVAL, "spm_gather_chain: bad argument");
+    if (n_roots == 0) return POSE_OK;
+    const float zf = (float)std::sqrt((double)((long long)R * R + (long long)R * R));
+    const int total = n_roots * K;
+    pose::spm_gather_chain_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(roots, disp, parent, kps, n_roots, K, R, zf, dist_threshold);
+    return check_launch("spm_gather_chain");
+}
+
 }  // extern "C"

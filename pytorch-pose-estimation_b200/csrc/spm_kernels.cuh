@@ -793,6 +793,43 @@ __global__ void __launch_bounds__(128) spm_gather_kernel(const float* __restrict
     else { o[0] = kx; o[1] = ky; o[2] = c; }
 }
 
+// Hierarchical displacement chaining (NOT in the reference, which reads every joint at the root pixel -- single hop,
+// utils/spm_utils.py:187-189; opt-in, parity unpinned; the hierarchical SPR decode of the SPM paper): joint k hangs off
+// parent[k] (-1 = the root); its displacement is read at the PARENT's decoded position (truncated to a pixel, like the
+// reference's .long() on the root) and added to that position with the reference's arithmetic (fp32 multiply by fp32(z), fp32
+// add; fp64 sqrt of the fp32 squared distance to the parent, `< dist_thr` -> the joint is absent).  An absent or off-map parent
+// makes every descendant absent (0,0,0).  One thread per (root, joint) walks its own ancestor path from the root down, so
+// `parent` needs no particular order; with parent[k] = -1 for every k the result is bit-identical to spm_gather_kernel.
+constexpr int kSpmChainDepth = 16;
+__global__ void __launch_bounds__(128) spm_gather_chain_kernel(const float* __restrict__ roots, const float* __restrict__ disp,
+                                                               const int* __restrict__ parent, float* __restrict__ kps, int n, int K, int R,
+                                                               float zf, double dist_thr) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * K) return;
+    const int r = t / K, k = t - r * K;
+    float* o = kps + 3 * t;
+    int path[kSpmChainDepth];
+    int depth = 0;
+    for (int j = k; j >= 0 && depth < kSpmChainDepth; j = __ldg(parent + j)) path[depth++] = j;
+    float px = roots[3 * r], py = roots[3 * r + 1];
+    const float c = roots[3 * r + 2];
+    bool ok = depth < kSpmChainDepth || __ldg(parent + path[depth - 1]) < 0;       // a longer chain (or a cycle) is rejected
+    for (int i = depth - 1; i >= 0 && ok; --i) {
+        const int j = path[i];
+        const int xi = (int)px, yi = (int)py;
+        if (xi < 0 || xi >= R || yi < 0 || yi >= R) { ok = false; break; }
+        const float dx = __ldg(disp + (long long)(2 * j) * R * R + yi * R + xi);
+        const float dy = __ldg(disp + (long long)(2 * j + 1) * R * R + yi * R + xi);
+        const float kx = __fadd_rn(__fmul_rn(dx, zf), px), ky = __fadd_rn(__fmul_rn(dy, zf), py);
+        const float ex = __fsub_rn(px, kx), ey = __fsub_rn(py, ky);
+        const float q = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+        if (sqrt((double)q) < dist_thr) { ok = false; break; }
+        px = kx; py = ky;
+    }
+    if (ok) { o[0] = px; o[1] = py; o[2] = c; }
+    else { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
+}
+
 // Tail of SPMmAPCOCO.update_state (utils/spm_utils.py:302-304): x *= img_w / input_size, y *= img_h / input_size -- the ratio is
 // an integer tensor divided by a python int, i.e. one fp32 division, then an in-place fp32 multiply.  Rows >= counts[i] are
 // not touched (they were never written by the decode kernel).

@@ -208,6 +208,27 @@ def get_spm_keypoints(root_joints, displacements, dist_threshold):
     return out
 
 
+def get_spm_keypoints_chained(root_joints, displacements, parents, dist_threshold):
+    """Hierarchical displacement chaining -- NOT in the reference (single hop, utils/spm_utils.py:187-189); opt-in, parity unpinned.
+
+    `parents[k]` = the joint that joint k's displacement is relative to (-1 = the root joint).  Same arguments and result as
+    `get_spm_keypoints` otherwise; with every parent -1 the result is bit-identical to it."""
+    if root_joints.size(0) == 0:
+        return root_joints
+    r = dense(root_joints, "root_joints")
+    d = dense(displacements, "displacements")
+    k, res = d.size(0) // 2, d.size(-1)
+    par = torch.as_tensor(parents, dtype=torch.int32).reshape(-1)
+    assert par.numel() == k, "parents must have one entry per joint"
+    assert int(par.max()) < k and int(par.min()) >= -1, "parents must be joint indices or -1"
+    par = par.to(r.device)
+    out = torch.empty((r.size(0), k, 3), dtype=torch.float32, device=r.device)
+    with torch.cuda.device(r.device):
+        check(lib().pose_spm_gather_chain(ptr(r), ptr(d), ptr(par), ptr(out), r.size(0), k, res, float(dist_threshold), stream_ptr(r.device)),
+              "pose_spm_gather_chain")
+    return out
+
+
 class DecodeSPM(nn.Module):
     """Drop-in for utils/spm_utils.py:203-250; `decode_batch` keeps everything on the device."""
 

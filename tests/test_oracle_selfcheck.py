@@ -65,6 +65,51 @@ def test_spm_forms_agree(seed, res, k):
         assert found <= {(int(x), int(y)) for x, y in c[:, 0]}
 
 
+def _chained_field(res=64, k=5, seed=3):
+    """A displacement field that encodes a 2-person, 5-joint skeleton HIERARCHICALLY (joint k relative to parents[k]): every
+    joint's (dx, dy)/z is written at its parent's pixel (3x3 neighbourhood), the way the SPM paper's hierarchical SPR is trained."""
+    rng = np.random.default_rng(seed)
+    parents = [-1, 0, 1, -1, 3]
+    z = np.sqrt(2.0 * res * res)
+    disp = np.zeros((2 * k, res, res), np.float32)
+    roots, joints = [], []
+    for centre in ((16, 20), (44, 40)):
+        pos = {-1: centre}
+        for j in range(k):
+            px, py = pos[parents[j]]
+            jx, jy = px + int(rng.integers(5, 9)), py + int(rng.integers(-8, -4))
+            pos[j] = (jx, jy)
+            disp[2 * j, py - 1:py + 2, px - 1:px + 2] = (jx - px) / z
+            disp[2 * j + 1, py - 1:py + 2, px - 1:px + 2] = (jy - py) / z
+        roots.append([float(centre[0]), float(centre[1]), 0.9])
+        joints.append([pos[j] for j in range(k)])
+    return torch.tensor(roots), torch.from_numpy(disp), parents, np.array(joints, np.float64)
+
+
+def test_spm_chained_keypoints_restatement():
+    """PARITY UNPINNED helper (hierarchical chaining is not in the reference): with every parent = -1 it IS the reference's single
+    hop (bit for bit against the pinned restatement), and a field encoded joint-to-parent decodes to the skeleton it encodes."""
+    people = po.make_config4_people(1, k=4, res=48, max_people=3, seed=11)
+    target = torch.from_numpy(np.stack([po.spm_render(c, j, 48, 1) for c, j in people]))
+    roots = po.spm_nms(target[0, 0:1], 0.99, 4.0)
+    assert roots.shape[0] >= 1
+    single = po.spm_keypoints(roots, target[0, 1:], 4.0)
+    assert torch.equal(po.spm_keypoints_chained(roots, target[0, 1:], [-1] * 4, 4.0), single)
+    r, disp, parents, joints = _chained_field()
+    got = po.spm_keypoints_chained(r, disp, parents, 4.0)
+    assert np.allclose(got[..., :2].numpy(), joints, atol=1e-3) and torch.all(got[..., 2] == 0.9)
+    # single hop on the same field reads every displacement at the root: joints deeper than one hop come out wrong / absent
+    flat = po.spm_keypoints(r, disp, 4.0)
+    assert not np.allclose(flat[:, 2, :2].numpy(), joints[:, 2], atol=0.5)
+    # a joint that decodes off the map is reported as the reference reports it (no clamp) but takes its descendants with it;
+    # a cycle is rejected
+    far = disp.clone()
+    far[0] = 5.0
+    gone = po.spm_keypoints_chained(r, far, parents, 4.0)
+    assert torch.all(gone[:, 0, 0] > 64) and torch.all(gone[:, 1] == 0) and torch.all(gone[:, 2] == 0) and torch.all(gone[:, 3, 2] == 0.9)
+    assert torch.all(po.spm_keypoints_chained(r, disp, [1, 0, -1, -1, 3], 4.0)[:, :2] == 0)
+
+
 def test_flip_average_of_a_mirrored_copy_is_the_identity():
     """PARITY UNPINNED helper: mirroring + swapping a prediction and averaging it back returns the prediction itself
     ((h + h) * 0.5 is exact in fp32), so decode(flip-averaged) == decode(plain)."""

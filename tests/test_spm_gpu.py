@@ -187,6 +187,33 @@ def test_nms_rules_empty_overflow_and_gather(pb, dev):
     assert allclose(got_k, want_k, REL) and torch.equal(got_k.cpu() == 0, want_k == 0)
 
 
+def test_hierarchical_chain_opt_in(pb, dev):
+    """SURVEY 8 f-4, PARITY UNPINNED (not in the reference): get_spm_keypoints_chained against the oracle's restatement; with
+    every parent = -1 it is the pinned single hop, bit for bit."""
+    from tests.test_oracle_selfcheck import _chained_field
+    people, target, logits, meta = cases.spm_case("coco", 4, seed=31)
+    tt = torch.from_numpy(target)
+    k = tt.shape[1] // 2
+    for b in range(4):
+        roots = po.spm_nms(tt[b, 0:1], 0.99, 4.0)
+        if roots.dim() != 2 or roots.shape[0] == 0:
+            continue
+        single = pb.get_spm_keypoints(roots.to(dev), tt[b, 1:].to(dev), 4.0)
+        assert torch.equal(pb.get_spm_keypoints_chained(roots.to(dev), tt[b, 1:].to(dev), [-1] * k, 4.0), single)
+        # a COCO-like tree on the (single-hop encoded) field: compared with the oracle's restatement of the same chain
+        parents = [-1, 0, 0, 1, 2, -1, -1, 5, 6, 7, 8, -1, -1, 11, 12, 13, 14][:k]
+        want = po.spm_keypoints_chained(roots, tt[b, 1:], parents, 4.0)
+        got = pb.get_spm_keypoints_chained(roots.to(dev), tt[b, 1:].to(dev), parents, 4.0)
+        assert allclose(got, want, REL) and torch.equal(got.cpu() == 0, want == 0)
+    r, disp, parents, joints = _chained_field()
+    got = pb.get_spm_keypoints_chained(r.to(dev), disp.to(dev), parents, 4.0)
+    want = po.spm_keypoints_chained(r, disp, parents, 4.0)
+    assert torch.equal(got.cpu(), want)
+    assert np.allclose(got[..., :2].cpu().numpy(), joints, atol=1e-3)
+    cyc = pb.get_spm_keypoints_chained(r.to(dev), disp.to(dev), [1, 0, -1, -1, 3], 4.0)
+    assert torch.equal(cyc.cpu(), po.spm_keypoints_chained(r, disp, [1, 0, -1, -1, 3], 4.0))
+
+
 def test_config4_batch_decode_against_oracle(pb, dev):
     """Config 4 at a larger batch: 64 multi-person images, every image's picks against the oracle."""
     people, target, logits, meta = cases.spm_case("coco", 64, seed=777)
