@@ -68,3 +68,25 @@ def assert_spm_people(got_roots, got_kps, want_roots, want_kps, rel):
     zg, zw = np.all(gk == 0, axis=-1), np.all(wk == 0, axis=-1)
     assert np.array_equal(zg, zw)
     assert allclose(gk, wk, rel)
+
+
+def chained_field(res=64, k=5, seed=3):
+    """A displacement field that encodes a 2-person, 5-joint skeleton HIERARCHICALLY (joint k relative to parents[k]): every
+    joint's (dx, dy)/z is written at its parent's pixel (3x3 neighbourhood), the way the SPM paper's hierarchical SPR is trained."""
+    rng = np.random.default_rng(seed)
+    parents = [-1, 0, 1, -1, 3]
+    z = np.sqrt(2.0 * res * res)
+    disp = np.zeros((2 * k, res, res), np.float32)
+    roots, joints = [], []
+    for centre in ((16, 20), (44, 40)):
+        pos = {-1: centre}
+        for j in range(k):
+            px, py = pos[parents[j]]
+            jx, jy = px + int(rng.integers(5, 9)), py + int(rng.integers(-8, -4))
+            pos[j] = (jx, jy)
+            disp[2 * j, py - 1:py + 2, px - 1:px + 2] = (jx - px) / z
+            disp[2 * j + 1, py - 1:py + 2, px - 1:px + 2] = (jy - py) / z
+        roots.append([float(centre[0]), float(centre[1]), 0.9])
+        joints.append([pos[j] for j in range(k)])
+    import torch
+    return torch.tensor(roots), torch.from_numpy(disp), parents, np.array(joints, np.float64)

@@ -5,6 +5,7 @@ import torch
 from hypothesis import given, settings
 from hypothesis import strategies as st
 
+from helpers import chained_field as _chained_field
 from oracle import sbp_oracle as so
 from oracle import spm_oracle as po
 
@@ -63,27 +64,6 @@ def test_spm_forms_agree(seed, res, k):
         roots, kps = po.spm_decode(tt[b:b + 1], res, 1, 0.99, False)
         found = {(int(r[0]), int(r[1])) for r in roots} if roots.dim() == 2 else set()
         assert found <= {(int(x), int(y)) for x, y in c[:, 0]}
-
-
-def _chained_field(res=64, k=5, seed=3):
-    """A displacement field that encodes a 2-person, 5-joint skeleton HIERARCHICALLY (joint k relative to parents[k]): every
-    joint's (dx, dy)/z is written at its parent's pixel (3x3 neighbourhood), the way the SPM paper's hierarchical SPR is trained."""
-    rng = np.random.default_rng(seed)
-    parents = [-1, 0, 1, -1, 3]
-    z = np.sqrt(2.0 * res * res)
-    disp = np.zeros((2 * k, res, res), np.float32)
-    roots, joints = [], []
-    for centre in ((16, 20), (44, 40)):
-        pos = {-1: centre}
-        for j in range(k):
-            px, py = pos[parents[j]]
-            jx, jy = px + int(rng.integers(5, 9)), py + int(rng.integers(-8, -4))
-            pos[j] = (jx, jy)
-            disp[2 * j, py - 1:py + 2, px - 1:px + 2] = (jx - px) / z
-            disp[2 * j + 1, py - 1:py + 2, px - 1:px + 2] = (jy - py) / z
-        roots.append([float(centre[0]), float(centre[1]), 0.9])
-        joints.append([pos[j] for j in range(k)])
-    return torch.tensor(roots), torch.from_numpy(disp), parents, np.array(joints, np.float64)
 
 
 def test_spm_chained_keypoints_restatement():

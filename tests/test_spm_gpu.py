@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from conftest import golden_rows, load_golden
-from helpers import allclose, assert_rows, assert_spm_people, close
+from helpers import allclose, assert_rows, assert_spm_people, chained_field as _chained_field, close
 from oracle import cases
 from oracle import spm_oracle as po
 
@@ -190,7 +190,6 @@ def test_nms_rules_empty_overflow_and_gather(pb, dev):
 def test_hierarchical_chain_opt_in(pb, dev):
     """SURVEY 8 f-4, PARITY UNPINNED (not in the reference): get_spm_keypoints_chained against the oracle's restatement; with
     every parent = -1 it is the pinned single hop, bit for bit."""
-    from tests.test_oracle_selfcheck import _chained_field
     people, target, logits, meta = cases.spm_case("coco", 4, seed=31)
     tt = torch.from_numpy(target)
     k = tt.shape[1] // 2
