@@ -376,6 +376,40 @@ __device__ __forceinline__ void render_loss_vec(const float (&x)[V], float (&g)[
     }
 }
 
+// Read-only two-phase form (the bulk-staged kernels, whose map sits in shared memory): phase 1 streams EVERY vector as if the
+// target were zero -- sigmoid, S_neg += s^2, nothing else: no patch test, no row / column arithmetic -- and phase 2 deals the
+// vectors that intersect the joint's window (<= 15 rows x 5 vectors at sigma 2: 9 % of the map, where the per-vector row test of
+// render_loss_vec sends 26 % down the patch path) out to the map's threads, which re-read them from shared memory, evaluate the
+// same sigmoid again (bit-identical, so the s^2 taken out of S_neg is exactly the one phase 1 put in) and apply the corrections.
+// 984 -> ~870 instructions per thread and map; validation loss 142 -> 128 us, loss + decode 167 -> 150 us per 69 632 maps.
+template <int V, bool SHARE>
+__device__ __forceinline__ void zero_target_vec(const float (&x)[V], float& aneg) {
+    float sg[V];
+    sigmoid_vec<V, SHARE>(x, sg);
+#pragma unroll
+    for (int j = 0; j < V; ++j) aneg = fmaf(sg[j], sg[j], aneg);
+}
+// the correction of one window vector: row r, first column cc (a multiple of 4) -- the branch-free padded-template lookup of render_loss_vec
+template <bool SHARE>
+__device__ __forceinline__ void patch_correct_vec(const float (&x)[4], int r, int cc, const Patch& pt, const float* __restrict__ lut, int lut_n,
+                                                  float& apos, float& arem) {
+    float sg[4];
+    sigmoid_vec<4, SHARE>(x, sg);
+    const int pw = lut_n + 2 * kLutPad;
+    const int ri = ((unsigned)(r - pt.uly) < (unsigned)pt.nrows) ? r - pt.uly : lut_n;
+    const int ci = min(max(cc - pt.ulx, -kLutPad), lut_n);
+    const float* lp = lut + ri * pw + ci + kLutPad;
+    const int lim = pt.px1 - cc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float t = __ldg(lp + j);
+        const bool pos = (j < lim) && t > 0.0f;
+        const float d = sg[j] - t;
+        arem = fmaf(pos ? sg[j] : 0.0f, sg[j], arem);
+        apos = fmaf(pos ? d : 0.0f, d, apos);
+    }
+}
+
 // One CTA per heat map.  Order inside the CTA: (1) every thread issues the 128-bit loads of its share of the map -- nothing
 // else has been waited for yet, so the whole map is in flight within the CTA's first instructions; (2) thread 0 turns the
 // keypoint into the patch geometry (shared memory, one barrier -- under the latency of (1)); (3) the arithmetic and the
@@ -526,6 +560,7 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD 
     extern __shared__ __align__(128) float tiles[];            // MPC maps of HW floats
     __shared__ __align__(8) unsigned long long s_bar[MPC];
     __shared__ Patch s_patch[MPC];
+    __shared__ FastDiv s_div[MPC];                             // read-only form: division by the window's width in vectors
     __shared__ float s_sum[MPC][WPM][3];
     __shared__ unsigned long long s_key[MPC];
     pdl_launch_dependents();
@@ -544,7 +579,12 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD 
     if (t == 0 && k < nmap) {
         double kx, ky;
         load_kp(P.kp, P.kp_f64, map0 + k, kx, ky);
-        s_patch[k] = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
+        const Patch pt = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
+        s_patch[k] = pt;
+        if (!GRAD) {
+            const uint32_t nvx = pt.ecnt ? (uint32_t)(((pt.px1 - 1) >> 2) - (pt.px0 >> 2) + 1) : 1u;
+            s_div[k] = FastDiv{nvx, nvx > 1 ? (uint32_t)((0xffffffffu / nvx) + 1u) : 0u};      // ceil(2^32 / nvx) for nvx that is no power of two; exact for id < 2^16
+        }
         s_key[k] = 0ull;
     }
     __syncthreads();
@@ -555,13 +595,37 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD 
         ArgTrack<V> arg;
         arg.reset();
         mbar_wait_parity(&s_bar[k], 0);
+        if constexpr (GRAD) {
 #pragma unroll 4
-        for (int vi = t; vi < nvec; vi += TPM) {
-            float x[V], g[V], unused[V];
-            Vec<V>::load_any(tile, vi, x);
-            if (DEC) arg.push(x);
-            render_loss_vec<V, GRAD, false, SHARE>(x, g, unused, vi, s_patch[k], P.lut, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
-            if (GRAD) Vec<V>::store(dl, vi, g);
+            for (int vi = t; vi < nvec; vi += TPM) {
+                float x[V], g[V], unused[V];
+                Vec<V>::load_any(tile, vi, x);
+                if (DEC) arg.push(x);
+                render_loss_vec<V, GRAD, false, SHARE>(x, g, unused, vi, s_patch[k], P.lut, P.lut_n, P.W, P.divW, P.gpos, P.gneg, apos, aneg, arem);
+                Vec<V>::store(dl, vi, g);
+            }
+        } else {
+            // phase 1: the whole map as zero target
+#pragma unroll 4
+            for (int vi = t; vi < nvec; vi += TPM) {
+                float x[V];
+                Vec<V>::load_any(tile, vi, x);
+                if (DEC) arg.push(x);
+                zero_target_vec<V, SHARE>(x, aneg);
+            }
+            // phase 2: the vectors of the joint's window, dealt out to the map's threads
+            const Patch& pt = s_patch[k];
+            if (pt.ecnt) {
+                const FastDiv dv = s_div[k];
+                const int cv0 = pt.px0 >> 2, nvx = (int)dv.d, wq = P.W >> 2;
+                const int total = nvx * (pt.py1 - pt.py0);
+                for (int id = t; id < total; id += TPM) {
+                    const int ry = (int)fdiv((uint32_t)id, dv), cv = cv0 + id - ry * nvx, r = pt.py0 + ry;
+                    float x[V];
+                    Vec<V>::load_any(tile, r * wq + cv, x);
+                    patch_correct_vec<SHARE>(x, r, 4 * cv, pt, P.lut, P.lut_n, apos, arem);
+                }
+            }
         }
         apos = warp_sum(apos);
         aneg = warp_sum(aneg);
