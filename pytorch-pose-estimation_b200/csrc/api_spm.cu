@@ -198,7 +198,14 @@ int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* 
     if (smem > 160 * 1024) return fail(POSE_EINVAL, "spm_decode: R=%d: the suppression bitmap does not fit in shared memory", R);
     if (N == 0) return POSE_OK;
     // (static + dynamic shared memory above 48 KB needs the opt-in: resolved once per (device, size) by the configuration cache)
-    if (resident_ctas(pose::spm_decode_kernel, pose::kSpmDecThreads, smem, "spm_decode") == 0) return last_code();
+    const int threads = N <= 2 * sm_count() ? 512 : (N <= 4 * sm_count() ? 256 : 128);
+    {
+        int ok;
+        if (threads == 512) ok = resident_ctas(pose::spm_decode_kernel<512>, 512, smem, "spm_decode");
+        else if (threads == 256) ok = resident_ctas(pose::spm_decode_kernel<256>, 256, smem, "spm_decode");
+        else ok = resident_ctas(pose::spm_decode_kernel<128>, 128, smem, "spm_decode");
+        if (ok == 0) return last_code();
+    }
     pose::SpmDecodeParams P;
     P.x = x; P.roots = roots; P.kps = kps; P.counts = counts; P.counts_total = counts_total;
     P.N = N; P.Pmax = Pmax; P.K = K; P.R = R; P.C = 1 + 2 * K;
@@ -220,7 +227,9 @@ int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* 
         while (!(std::sqrt((double)s) > dist_threshold)) ++s;
         P.s_min = s;
     }
-    pose::spm_decode_kernel<<<N, pose::kSpmDecThreads, smem, (cudaStream_t)stream>>>(P);
+    if (threads == 512) pose::spm_decode_kernel<512><<<N, 512, smem, (cudaStream_t)stream>>>(P);
+    else if (threads == 256) pose::spm_decode_kernel<256><<<N, 256, smem, (cudaStream_t)stream>>>(P);
+    else pose::spm_decode_kernel<128><<<N, 128, smem, (cudaStream_t)stream>>>(P);
     return check_launch("spm_decode");
 }
 

@@ -861,11 +861,15 @@ __global__ void __launch_bounds__(256) spm_rescale_kernel(const float* __restric
 //  suppressed-pixel bitmap in shared memory replaces the strike-out.  Slow, bounded, same picks.
 // History: v1 kept the whole activated map in shared memory (64 KB: 3 CTAs per SM), scanned it with the CTA for every
 // root (3 barriers per root) and gathered joints inside the loop: 58 us per 256 images; this version 13 us.
-constexpr int kSpmDecThreads = 128;
+// CTA size: 128 threads when the launch has enough images to fill the GPU (1024 images = one wave of 7 CTAs per SM); with fewer
+// images than ~4 per SM more threads per image stream its plane faster (N=256: 16.6 us at 128, 14.4 at 256, 12.5 at 512;
+// N=1024: 22.7 / 24.9 / 27.6 -- profiles/r02_tune_spm_decode.log).  Loads in flight per thread: 8 at 128 threads, 4 above.
+constexpr int kSpmDecThreadsMax = 512;
 constexpr int kSpmCandCap = 2048;
 constexpr int kSpmWarpList = 256;
 constexpr int kSpmRootCap = 256;              // picked roots recorded in shared memory before their joints are gathered
 
+template <int kSpmDecThreads>
 __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodeParams P) {
     extern __shared__ __align__(16) unsigned int sup_bits[];   // dense fallback only: R*R bits, 1 = suppressed
     __shared__ unsigned int s_cand[kSpmCandCap];               // (y << 16) | x  == row-major order for ties
@@ -907,7 +911,7 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
     if ((RR & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
         const float4* b4 = reinterpret_cast<const float4*>(base);
         const int nq = RR >> 2;
-        constexpr int U = 8;
+        constexpr int U = kSpmDecThreads == 128 ? 8 : 4;
         for (int q0 = threadIdx.x; q0 < nq; q0 += kSpmDecThreads * U) {
             float4 v[U];
 #pragma unroll
