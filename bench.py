@@ -492,7 +492,7 @@ def run_cuda(args):
         except Exception as e:      # noqa: BLE001
             extras.append({"workload": "config3 as written", "error": f"{type(e).__name__}: {e}"})
         if rank == 0 and world == 1:
-            for fn in (xw.spm_config4, xw.decode_config5, xw.head_fusion):
+            for fn in (xw.validation_config2, xw.spm_config4, xw.decode_config5, xw.head_fusion):
                 try:
                     extras += fn(pb, dev, peak)
                 except Exception as e:      # noqa: BLE001

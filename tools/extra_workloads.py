@@ -85,6 +85,24 @@ def decode_config5(pb, dev, peak, reps=20):
     return out
 
 
+def validation_config2(pb, dev, peak, b=4096, k=17, h=64, w=48, reps=20):
+    """configs[1] shapes, the VALIDATION forms of the fused kernel (module/sbp_detector.py:33-41: loss, then update_state): nothing is
+    stored but the joint rows, so the bytes per heat map are the logits alone (SURVEY 8 d: 12 296 / 12 308)."""
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(b, k, h, w, device=dev, generator=gen) * 3.0
+    kp = torch.stack([torch.rand(b, k, device=dev, generator=gen, dtype=torch.float64) * w,
+                      torch.rand(b, k, device=dev, generator=gen, dtype=torch.float64) * h], dim=-1)
+    kp[torch.rand(b, k, device=dev, generator=gen) >= 0.85] = -1.0
+    jo = torch.empty((b, k, 3), device=dev)
+    out = []
+    ms = graph_time(lambda: pb.sbp_fused(x, keypoints=kp, sigma=2, want_grad=False), reps)
+    out.append(_entry(f"config2 validation loss (render + loss, no grad), B={b}", ms, b * k, "heatmaps", h * w * 4 + 8, peak))
+    ms = graph_time(lambda: pb.sbp_fused(x, keypoints=kp, sigma=2, want_grad=False, decode=True, conf_threshold=0.25, coord_scale=4.0,
+                                         out={"joints": jo}), reps)
+    out.append(_entry(f"config2 validation step (render + loss + decode, no grad), B={b}", ms, b * k, "heatmaps", h * w * 4 + 20, peak))
+    return out
+
+
 def head_fusion(pb, dev, peak, b=1024, c=512, k=17, h=64, w=48, reps=5):
     """the detector's 1x1 head (512 -> 17, models/detector/sbp.py:35-37) fused with loss + dlogits + decode on tcgen05
     (pose_sbp_head_fused), next to the unfused pair on the same box: torch's fp32 conv2d (cuDNN / cuBLAS, TF32 off -- the
