@@ -17,17 +17,22 @@
 // rounding of the accumulation itself (measured: tests/test_head_gpu.py compares with an fp64 convolution next to cuDNN's fp32 result).
 //
 // Data flow of one CTA (persistent, one per SM, whole images: the per-map reductions of loss and argmax stay inside the CTA):
-//   warp 0      producer: TMA tensor loads (cp.async.bulk.tensor.4d, 128-byte swizzle with 32-byte atoms) of [32 channels x 128 pixels] fp32 tiles
-//               (16 KB) of X into a ring of shared-memory stages, completion on mbarriers; W (hi|lo, 48 x C) is loaded once and
-//               stays in shared memory (96 KB at C = 512);
-//   warps 6-13  residual (two groups of four, alternate stages): raw stage -> Xl stage (same swizzled layout, element for element), fence.proxy.async, mbarrier arrive;
-//   warps 1, 14 MMA issuers (one thread each: raw / residual products into separate accumulators): 4 + 4 tcgen05.mma per stage (A = MN-major SW128-base-32B descriptor on the raw / residual tile,
-//               B = K-major SW128 descriptor on the W chunk), tcgen05.commit releases the stages and, after the last channel
-//               chunk, hands the accumulator (128 lanes x 48 columns of TMEM, double buffered) to the epilogue;
-//   warps 2-5   epilogue: tcgen05.ld (lane = pixel, 48 columns), logit = D[k] + D[24+k], then the arithmetic of
-//               sbp_fused_kernel per (pixel, joint): sigmoid, Gaussian target from the joint's patch, loss pair, dL/dlogit written
-//               as 128-byte rows (32 consecutive pixels of one map per warp store), running argmax; per image: warp shuffles +
-//               a 4-way fixed-order combine -> the map's (S_pos, S_neg) fp64 pair and its joint row.
+//   warp 0       producer: TMA tensor loads (cp.async.bulk.tensor.4d, 128-byte swizzle with 32-byte atoms) of [32 channels x 128
+//                pixels] fp32 tiles (16 KB) of X into a ring of shared-memory stages, completion on mbarriers; W (hi|lo, 48 x C) is
+//                loaded once and stays in shared memory (96 KB at C = 512);
+//   warps 6-13   residual warps, two groups of four on alternate stages: lane = pixel, 32 conflict-free LDS.32 bring one pixel's 32
+//                channel values into registers, tcgen05.st writes them and their residuals into a ring of A tiles in TENSOR MEMORY
+//                (128 lanes x 64 columns per stage), tcgen05.wait::st, fence, mbarrier arrive; the shared-memory stage is released
+//                as soon as it is in registers;
+//   warps 1, 14  MMA issuers (one thread each): 4 tcgen05.mma kind::tf32 (M = 128, N = 48, K = 8) per stage with A from TMEM and
+//                B = a K-major SW128 descriptor on the W chunk -- raw products into the main accumulator (warp 1), residual products
+//                into the correction accumulator (warp 14); tcgen05.commit frees the A slot and, after the last channel chunk,
+//                hands the double-buffered accumulators to the epilogue;
+//   warps 2-5    epilogue: tcgen05.ld (lane = pixel, 48 columns per accumulator), logit = D[k] + D[24+k] of both accumulators, then
+//                the arithmetic of sbp_fused_kernel per (pixel, joint): sigmoid, Gaussian target from the joint's patch, loss pair,
+//                dL/dlogit written as 128-byte rows (32 consecutive pixels of one map per warp store), running argmax; per image:
+//                warp shuffles + a 4-way fixed-order combine -> the map's (S_pos, S_neg) fp64 pair and its joint row.
+// (`tuning` bit 24 keeps the first version for comparison: residual tile written back to shared memory, MN-major A descriptors.)
 // HBM traffic per image: C*H*W*4 bytes of features read once (+ K*H*W*4 of dlogits written when training) -- the logits' write
 // and re-read (2 x K*H*W*4) of the unfused pair "conv kernel -> fused loss kernel" are gone.
 #pragma once
@@ -120,9 +125,8 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const bool residual = !(P.flags & kHeadNoResidual);
     const int tiles = P.tiles_per_img;
     // TMEM: columns [0,256) two buffers x (main accumulator | correction accumulator); RT: columns [256, 256 + 64*kHeadTmemRing) the A
-    // ring (32 raw + 32 residual columns per stage).  The residual products go to their OWN accumulator: back-to-back MMAs into one
-    // accumulator serialise on the accumulate latency (~125 cycles measured for these N = 48 instructions, whose work is 24 cycles),
-    // and the small terms do not suffer the rounding of the large running sum.
+    // ring (32 raw + 32 residual columns per stage).  The residual products go to their OWN accumulator: the small terms do not
+    // suffer the rounding of the large running sum (logit error halved), and two threads can issue into the two accumulators.
     constexpr uint32_t kTmemCols = RT ? 512 : 256;
     constexpr uint32_t kARing0 = 4 * kHeadAccCols;
 
