@@ -13,10 +13,17 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def graph_time(fn, reps=20, warm=3, rounds=3):
-    """ms per call: the call is captured once and replayed `reps` times between one event pair; median of `rounds`."""
+    """ms per call: the call is captured in a CUDA graph -- as many back-to-back copies as fill ~1 ms, so that the host's replay
+    rate never shows in the number -- and replayed `reps` times between one event pair; median of `rounds`."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    torch.cuda.synchronize()
+    inner = max(1, min(16, int(1.0 / max(a.elapsed_time(b), 1e-3))))
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -24,7 +31,8 @@ def graph_time(fn, reps=20, warm=3, rounds=3):
     torch.cuda.current_stream().wait_stream(side)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        fn()
+        for _ in range(inner):
+            fn()
     g.replay()
     torch.cuda.synchronize()
     ts = []
@@ -35,7 +43,7 @@ def graph_time(fn, reps=20, warm=3, rounds=3):
             g.replay()
         b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b) / reps)
+        ts.append(a.elapsed_time(b) / (reps * inner))
     return sorted(ts)[len(ts) // 2]
 
 
