@@ -996,7 +996,66 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
         }
     };
 
-    if (ncand <= kSpmWarpList) {
+    if (ncand <= 64) {
+        // The usual case (a few dozen candidates; config 4: 23 on average, 40 at most): the greedy loop "best remaining, strike its
+        // neighbourhood" costs ~1000 cycles per ROOT as a chain of warp reductions (measured with clock64 stamps: 5 700 cycles per
+        // image, 11 600 for an 8-person image -- more than the 64 KB stream of the plane at N = 256).  Here one warp does the same
+        // selection in closed form, two candidates per lane:
+        //   1. rank of every candidate under (value desc, row-major index asc) by comparison with all others (broadcast LDS);
+        //   2. candidates re-read in rank order; for each, the 64-bit mask of the ranks it would strike (same integer radius test);
+        //   3. the greedy walk over a warp-uniform `alive` mask: lowest set bit = next root, alive &= ~its mask -- four shuffles and
+        //      three logic operations per root, no reduction.
+        // Same picks in the same order as the loop below.
+        if (wid == 0) {
+            unsigned int* s_skey = reinterpret_cast<unsigned int*>(s_root_i) + kSpmRootCap / 2;      // scratch: upper half of the root record
+            float* s_sval = s_root_c + kSpmRootCap / 2;                                             // (a warp-list image records <= 64 roots)
+            const int n = ncand;
+            const int i0 = lane, i1 = lane + 32;
+            const float v0 = i0 < n ? s_val[i0] : -INFINITY, v1 = i1 < n ? s_val[i1] : -INFINITY;
+            const unsigned k0 = i0 < n ? s_cand[i0] : 0xffffffffu, k1 = i1 < n ? s_cand[i1] : 0xffffffffu;
+            int r0 = 0, r1 = 0;
+            for (int i = 0; i < n; ++i) {
+                const float vi = s_val[i];
+                const unsigned ki = s_cand[i];
+                r0 += (vi > v0 || (vi == v0 && ki < k0)) ? 1 : 0;
+                r1 += (vi > v1 || (vi == v1 && ki < k1)) ? 1 : 0;
+            }
+            if (i0 < n) { s_skey[r0] = k0; s_sval[r0] = v0; }
+            if (i1 < n) { s_skey[r1] = k1; s_sval[r1] = v1; }
+            __syncwarp();
+            const unsigned sk0 = i0 < n ? s_skey[i0] : 0u, sk1 = i1 < n ? s_skey[i1] : 0u;         // lane owns ranks `lane` and `lane + 32`
+            const float sv0 = i0 < n ? s_sval[i0] : -INFINITY, sv1 = i1 < n ? s_sval[i1] : -INFINITY;
+            unsigned long long m0 = 0ull, m1 = 0ull;
+            const int y0 = (int)(sk0 >> 16), x0 = (int)(sk0 & 0xffffu), y1 = (int)(sk1 >> 16), x1 = (int)(sk1 & 0xffffu);
+            for (int q = 0; q < n; ++q) {
+                const unsigned kq = s_skey[q];
+                const int yq = (int)(kq >> 16), xq = (int)(kq & 0xffffu);
+                const long long a = (long long)(yq - y0) * (yq - y0) + (long long)(xq - x0) * (xq - x0);
+                const long long b = (long long)(yq - y1) * (yq - y1) + (long long)(xq - x1) * (xq - x1);
+                if (a < P.s_min) m0 |= 1ull << q;
+                if (b < P.s_min) m1 |= 1ull << q;
+            }
+            __syncwarp();                                                   // the scratch is read; the record may be written
+            unsigned long long alive = (unsigned long long)__ballot_sync(FULL_MASK, sv0 > -INFINITY) |
+                                       ((unsigned long long)__ballot_sync(FULL_MASK, sv1 > -INFINITY) << 32);
+            while (alive) {                                                 // warp-uniform
+                const int p = __ffsll((long long)alive) - 1, src = p & 31;
+                const bool hi = p >= 32;
+                const unsigned key = __shfl_sync(FULL_MASK, hi ? sk1 : sk0, src);
+                const float val = __shfl_sync(FULL_MASK, hi ? sv1 : sv0, src);
+                const unsigned long long mm = hi ? m1 : m0;
+                const unsigned mlo = __shfl_sync(FULL_MASK, (unsigned)mm, src), mhi = __shfl_sync(FULL_MASK, (unsigned)(mm >> 32), src);
+                if (lane == 0 && found < P.Pmax) { s_root_i[found] = (int)key; s_root_c[found] = val; }
+                alive &= ~(((unsigned long long)mhi << 32) | (unsigned long long)mlo);
+                alive &= ~(1ull << p);
+                ++found;
+            }
+            if (lane == 0) s_found = found;
+        }
+        __syncthreads();
+        found = s_found;
+        flush(found);
+    } else if (ncand <= kSpmWarpList) {
         // one warp, no block barriers; at most ncand <= kSpmRootCap roots, so the record never overflows
         if (wid == 0) {
             while (true) {
