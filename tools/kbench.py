@@ -28,12 +28,18 @@ def peak():
 
 
 def timeit(fn, reps, warm=5):
-    """Device time per call: the call is captured once in a CUDA graph and replayed `reps` times between one event pair
-    (no host launch overhead in the number; the eager queue-saturated loop is the fallback if capture fails); best and
-    median of 3 such measurements."""
+    """Device time per call: the call is captured in a CUDA graph -- as many back-to-back copies as fill ~1 ms, so the host's
+    replay rate never shows in a short kernel's number -- and replayed `reps` times between one event pair (the eager
+    queue-saturated loop is the fallback if capture fails); best and median of 3 such measurements."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    torch.cuda.synchronize()
+    inner = max(1, min(16, int(1.0 / max(a.elapsed_time(b), 1e-3))))
     run = None
     try:
         if EAGER:
@@ -45,13 +51,15 @@ def timeit(fn, reps, warm=5):
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            fn()
+            for _ in range(inner):
+                fn()
         g.replay()
         torch.cuda.synchronize()
         run = g.replay
     except Exception:       # noqa: BLE001
         torch.cuda.synchronize()
         run = fn
+        inner = 1
     ts = []
     for _ in range(3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -60,7 +68,7 @@ def timeit(fn, reps, warm=5):
             run()
         b.record()
         b.synchronize()
-        ts.append(a.elapsed_time(b) / reps)
+        ts.append(a.elapsed_time(b) / (reps * inner))
     ts.sort()
     return ts[1], ts[0]
 
