@@ -1,5 +1,5 @@
 #!/bin/bash
-# final round-2 evidence: ncu of the two-phase validation kernels, bench (both arms) with the current code
+# ncu --set full of the two-phase validation kernels, then bench.py (both arms)
 mkdir -p gpurun_out
 for w in val val_loss; do
   timeout 120 python tools/profile_fused.py $w > /dev/null 2>&1 && \
