@@ -291,7 +291,8 @@ int pose_ap_accumulate(const long long* order, const int* dt_match, const unsign
  *      kp), DecodeSBP.forward / nms_sbp utils/sbp_utils.py:56-118 and SBPmAPCOCO.update_state :141-163 -- the logits
  *      [N][K][H][W] never exist in HBM.
  *   features [N][C][H][W] fp32 NCHW (the head's input), weight [K][C] fp32 (conv weight [K,C,1,1]), kp / lut as in
- *   pose_sbp_fused except that `lut` is the UNPADDED n*n template (pose_gauss_template_host).
+ *   pose_sbp_fused except that `lut` is the UNPADDED n*n template (pose_gauss_template_host).  kp may be NULL with
+ *   POSE_F_DECODE alone: the inference form (head -> DecodeSBP, inference_sbp.py:57-58,73), no target involved.
  *   The contraction runs on the tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, features through TMA tensor
  *   maps) with both operands split into a tf32 head and a residual, so the logits carry fp32-level error (csrc/head_kernels.cuh).
  *   Outputs as pose_sbp_fused (dlogits iff POSE_F_GRAD: the caller's autograd needs it for dW and dX; joints / packed_out iff

@@ -75,8 +75,11 @@ int pose_sbp_head_fused(const float* features, const float* weight, const void* 
     if (C % pose::kHeadKC) return fail(POSE_EINVAL, "sbp_head_fused: C=%d must be a multiple of %d", C, pose::kHeadKC);
     const long long HW = (long long)H * W;
     if (HW % pose::kHeadM || HW >= (1ll << 20) || W >= (1 << 11)) return fail(POSE_EINVAL, "sbp_head_fused: H*W=%lld must be a multiple of %d (and < 2^20)", HW, pose::kHeadM);
-    if (!features || !weight || !kp || !lut) return fail(POSE_EINVAL, "sbp_head_fused: NULL input");
-    if (lut_n <= 0 || lut_n > pose::kHeadMaxLut || !(sigma > 0.0)) return fail(POSE_EINVAL, "sbp_head_fused: template side %d (at most %d), sigma must be > 0", lut_n, pose::kHeadMaxLut);
+    if (!features || !weight) return fail(POSE_EINVAL, "sbp_head_fused: NULL input");
+    // kp == NULL: decode-only call (inference: head -> DecodeSBP, no target): the loss outputs then hold the loss against an all-zero target
+    if (!kp && ((flags & POSE_F_GRAD) || !(flags & POSE_F_DECODE))) return fail(POSE_EINVAL, "sbp_head_fused: without keypoints only POSE_F_DECODE (no POSE_F_GRAD) makes sense");
+    if (kp && (!lut || lut_n <= 0 || lut_n > pose::kHeadMaxLut || !(sigma > 0.0))) return fail(POSE_EINVAL, "sbp_head_fused: template side %d (at most %d), sigma must be > 0", lut_n, pose::kHeadMaxLut);
+    if (!kp) { lut_n = 0; sigma = 1.0; }
     if ((flags & POSE_F_GRAD) && !dlogits) return fail(POSE_EINVAL, "sbp_head_fused: POSE_F_GRAD without dlogits");
     if ((flags & POSE_F_DECODE) && !joints) return fail(POSE_EINVAL, "sbp_head_fused: POSE_F_DECODE without joints");
     if ((flags & POSE_F_HEAD_LOGITS_OUT) && !logits_out) return fail(POSE_EINVAL, "sbp_head_fused: POSE_F_HEAD_LOGITS_OUT without logits_out");

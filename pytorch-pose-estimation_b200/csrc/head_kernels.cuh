@@ -326,8 +326,8 @@ sbp_head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         for (int img = blockIdx.x; img < P.N; img += gridDim.x, ++ii) {
             const int pb = ii & 1;
             if (et < K) {
-                double kx, ky;
-                load_kp(P.kp, P.kp_f64, (long long)img * K + et, kx, ky);
+                double kx = -1.0, ky = -1.0;                    // no keypoints (decode-only call): every joint invisible, the target is zero
+                if (P.kp) load_kp(P.kp, P.kp_f64, (long long)img * K + et, kx, ky);
                 s_patch[pb][et] = make_patch(kx, ky, P.H, P.W, P.three_sigma, P.lut_n);
             }
             head::bar_sync(1, 128);

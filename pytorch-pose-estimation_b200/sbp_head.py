@@ -24,13 +24,14 @@ def head_tuning(raw_stages=0, residual_stages=0, residual_in_smem=False):
     return (int(raw_stages) & 0xff) | ((int(residual_stages) & 0xff) << 8) | ((1 << 24) if residual_in_smem else 0)
 
 
-def sbp_head_fused(features, weight, keypoints, sigma=-1, want_grad=True, decode=False, conf_threshold=0.25, coord_scale=1.0,
+def sbp_head_fused(features, weight, keypoints=None, sigma=-1, want_grad=True, decode=False, conf_threshold=0.25, coord_scale=1.0,
                    lambda_positive=5.0, lambda_negative=1.0, global_batch=None, bbox=None, input_size=None, want_logits=False,
                    residual=True, sigmoid_ref=None, tuning=0, out=None):
     """features [B,C,H,W] fp32 (NCHW), weight [K,C] or [K,C,1,1] fp32, keypoints [B,K,2] in heat-map pixels.
 
     Returns dict(loss, loss_num, dlogits, logits, joints, packed) like `sbp_fused`; `logits` only with `want_logits`
-    (tests).  `residual=False` drops the feature residual (plain TF32 features; diagnostics)."""
+    (tests).  `residual=False` drops the feature residual (plain TF32 features; diagnostics).  `keypoints=None` is the inference
+    form (the head followed by DecodeSBP, inference_sbp.py:57-58,73): only `joints` / `packed` are meaningful then."""
     x = dense(features, "features")
     assert x.dim() == 4, "features must be [B,C,H,W]"
     b, c, h, w = x.shape
@@ -39,11 +40,16 @@ def sbp_head_fused(features, weight, keypoints, sigma=-1, want_grad=True, decode
     assert wt.shape[1] == c, "weight must be [K,C] / [K,C,1,1]"
     dev = x.device
     sig = float(h / 64 if sigma < 0 else sigma)
-    kp = _kp_tensor(keypoints, dev)
-    assert tuple(kp.shape) == (b, k, 2), "keypoints must be [B,K,2]"
-    g = _gauss_template(sig)
-    lut, lut_n = _templates.get(g, sig, dev), g.shape[0]
-    kp_dtype = _cabi.KP_F64 if kp.dtype == torch.float64 else _cabi.KP_F32
+    kp = lut = None
+    lut_n, kp_dtype = 0, _cabi.KP_F64
+    if keypoints is not None:
+        kp = _kp_tensor(keypoints, dev)
+        assert tuple(kp.shape) == (b, k, 2), "keypoints must be [B,K,2]"
+        g = _gauss_template(sig)
+        lut, lut_n = _templates.get(g, sig, dev), g.shape[0]
+        kp_dtype = _cabi.KP_F64 if kp.dtype == torch.float64 else _cabi.KP_F32
+    else:                                    # inference: head -> decode, no target
+        want_grad, decode = False, True
     out = out or {}
     flags = 0
     dlogits = logits = joints = packed = bb = None

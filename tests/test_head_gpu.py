@@ -113,6 +113,18 @@ def test_back_projection_rows_equal_unfused_pipeline(pb):
     assert abs(r["loss"].item() - u["loss"].item()) <= 1e-6 * abs(u["loss"].item())
 
 
+def test_decode_only_without_keypoints(pb):
+    """Inference form (head -> DecodeSBP, no target): the same joints as the training-form call."""
+    feats, weight, kp = _inputs(3, 512, 17, 64, 48, seed=13)
+    a = pb.sbp_head_fused(feats, weight, kp, sigma=2, decode=True, conf_threshold=0.25, coord_scale=4.0)
+    b = pb.sbp_head_fused(feats, weight, None, conf_threshold=0.25, coord_scale=4.0)
+    torch.cuda.synchronize()
+    assert b["dlogits"] is None and torch.equal(a["joints"], b["joints"])
+    ref32, _ = _reference(feats, weight)
+    want = so.sbp_decode(ref32.cpu(), 192, 0.25, True)
+    assert torch.equal(b["joints"].cpu()[..., :2], want[..., :2])
+
+
 def test_many_images_per_cta_and_determinism(pb):
     """More images than SMs (several images per persistent CTA, both accumulator buffers, every ring wrap) and run-to-run identical results."""
     b, c, k, h, w = 300, 64, 17, 16, 16
