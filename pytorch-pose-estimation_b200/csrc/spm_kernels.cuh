@@ -371,7 +371,7 @@ struct SpmFusedParams {
     float groot, gdisp;         // 2*lambda_root*inv_norm, lambda_disp*inv_norm
 };
 
-constexpr int kSpmGeomThreads = 256;
+constexpr int kSpmGeomThreads = 512;
 __host__ __device__ inline size_t spm_geom_smem_bytes(int R, int lut_n) {
     const int wpr = (R / 4 + 31) / 32;
     return (size_t)R * 8 + (size_t)R * wpr * 4 + (size_t)lut_n * lut_n * 4;
