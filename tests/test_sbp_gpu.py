@@ -285,7 +285,7 @@ def test_config1_batch32_matches_reference(pb, dev):
     assert_joints(pb.DecodeSBP([256, 192], 0.25, True).decode_batch(x.detach()), g["joints"], REL)
 
 
-@pytest.mark.parametrize("sigma", [0.7, 1.1, 1.5, 2.4, 2.5])
+@pytest.mark.parametrize("sigma", [0.7, 1.1, 1.5, 2.4, 2.5, 4.0])
 @pytest.mark.parametrize("hw", [(32, 24), (30, 27), (64, 48), (21, 36), (10, 18), (12, 26)])
 def test_fused_padded_template_windows(pb, dev, sigma, hw):
     """The fused kernels fetch targets from a zero-padded shared-memory template with clamped indices (no range tests):
@@ -320,6 +320,13 @@ def test_fused_padded_template_windows(pb, dev, sigma, hw):
     if w % 4 == 0:
         t = pb.sbp_fused(x, keypoints=kp, sigma=sigma, want_grad=True, decode=True, conf_threshold=0.25, coord_scale=4.0, tma=True)
         assert torch.equal(t["dlogits"], r["dlogits"]) and close(t["loss"].item(), float(wl), REL)
+    # no target out: where the shape allows it these go through the bulk-staged kernels -- the read-only ones in their two-phase
+    # form (whole map as zero target, then the window's vectors dealt out to the map's threads)
+    for dec in (False, True):
+        v = pb.sbp_fused(x, keypoints=kp, sigma=sigma, want_grad=False, decode=dec, conf_threshold=0.25, coord_scale=4.0)
+        assert close(v["loss"].item(), float(wl), REL), (v["loss"].item(), float(wl))
+        if dec:
+            assert torch.equal(v["joints"], r["joints"])
 
 
 def test_odd_shapes_scalar_path_and_empty_batch(pb, dev):
