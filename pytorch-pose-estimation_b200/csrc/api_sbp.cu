@@ -57,7 +57,7 @@ int launch_fused_tma(const pose::SbpFusedParams& P0, cudaStream_t st) {
     const size_t smem = pose::sbp_tma_smem_bytes(P.HW, GRAD);
     if (resident_ctas(pose::sbp_fused_tma_kernel<GRAD, DEC>, threads, smem, "sbp_fused(tma)") == 0) return last_code();
     const long long ctas = (P.n_maps + mpc - 1) / mpc;
-    pose::sbp_fused_tma_kernel<GRAD, DEC><<<(unsigned)ctas, threads, smem, st>>>(P);
+    launch_pdl(pose::sbp_fused_tma_kernel<GRAD, DEC>, (unsigned)ctas, (unsigned)threads, smem, st, P);
     return check_launch("sbp_fused_tma");
 }
 

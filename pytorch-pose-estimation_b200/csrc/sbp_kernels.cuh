@@ -563,6 +563,9 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD 
     __shared__ FastDiv s_div[MPC];                             // read-only form: division by the window's width in vectors
     __shared__ float s_sum[MPC][WPM][3];
     __shared__ unsigned long long s_key[MPC];
+    // launched with programmatic stream serialisation: the grid may be scheduled while its predecessor (in a training loop the
+    // epilogue of the previous step) drains; nothing the predecessor produced is touched before this wait
+    pdl_wait();
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = wid / WPM, ws = wid - k * WPM;               // this warp's map slot and its index among the map's warps
@@ -705,6 +708,7 @@ struct SbpEpilogueParams {
 
 POSE_GLOBAL void __launch_bounds__(256) sbp_epilogue_kernel(SbpEpilogueParams P) {
     pdl_wait();
+    pdl_launch_dependents();      // a successor launched the same way (the next step's fused kernel) may be scheduled now; it waits for us itself
     if ((int)blockIdx.x >= P.bp_ctas) {
         if (reduce_slice_and_elect(P.partials, P.n_pairs, P.slices, P.ticket, P.R, (int)blockIdx.x - P.bp_ctas))
             reduce_pairs_cta(P.slices, P.R, 2, P.w0, P.w1, P.inv_norm, P.loss_out, P.num_out);
