@@ -152,10 +152,18 @@ __device__ __forceinline__ float sigmoid_window_lo(float m) {
 }
 
 // ---------------------------------------------------------------- warp reductions
+// (sm_100a: one CREDUX.MAX.F32 instead of five shuffle + FMNMX rounds; NaNs are ignored like fmaxf does)
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
-    return v;
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+// largest 64-bit key of the warp, in every lane: two 32-bit CREDUX.MAX (high words, then the low words of the lanes that hold the
+// largest high word)
+__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long k) {
+    const unsigned hi = __reduce_max_sync(FULL_MASK, (unsigned)(k >> 32));
+    const unsigned lo = __reduce_max_sync(FULL_MASK, (unsigned)(k >> 32) == hi ? (unsigned)k : 0u);
+    return ((unsigned long long)hi << 32) | (unsigned long long)lo;
 }
 __device__ __forceinline__ int warp_min(int v) {
 #pragma unroll

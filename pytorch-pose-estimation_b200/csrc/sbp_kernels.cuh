@@ -170,7 +170,9 @@ __device__ __forceinline__ unsigned long long arg_key(float f, int i) {
 // first_vi(l) = first_vi0 + l (k = 0, 1, ...; < nvec).  Offers the warp's winner (if any) to *key.
 // SIG == false (heat maps that are already activated, DecodeSBP.pred == False): candidates are the elements equal to the
 // warp maximum.
-template <int V, bool SIG>
+// SLOT == false: *key is shared by several warps and takes the warp's winner through one atomicMax (lane 0).  SLOT == true: *key is
+// this warp's own slot and is always written (0 = no candidate): no atomic, the caller takes the largest slot after its barrier.
+template <int V, bool SIG, bool SLOT = false>
 __device__ __forceinline__ void warp_offer_argmax(const ArgTrack<V>& a, const float* __restrict__ src, int nvec, int first_vi0, int vstride,
                                                   int sig_ref, unsigned long long* key) {
     const int lane = threadIdx.x & 31;
@@ -182,6 +184,9 @@ __device__ __forceinline__ void warp_offer_argmax(const ArgTrack<V>& a, const fl
         // the window does not hold -- rank every element of the warp's share
         if (!(m > -80.0f)) lo = -INFINITY;
     }
+    // the reference sigmoid of the warp's maximum is evaluated NEXT TO the candidate scan, not behind it (one dependent chain of
+    // ~250 cycles off the end of every map), and re-used for every candidate equal to m -- usually the only one
+    const float sm = SIG ? sigmoid_ref(m, sig_ref) : m;
     unsigned owners = __ballot_sync(FULL_MASK, a.best >= lo);
     unsigned long long k = 0ull;
     if (__popc(owners) <= 2) {
@@ -194,7 +199,11 @@ __device__ __forceinline__ void warp_offer_argmax(const ArgTrack<V>& a, const fl
                 Vec<V>::load_any(src, vi, x);
 #pragma unroll
                 for (int j = 0; j < V; ++j)
-                    if (x[j] >= lo) k = max(k, arg_key(SIG ? sigmoid_ref(x[j], sig_ref) : x[j], vi * V + j));
+                    if (x[j] >= lo) {
+                        float v = sm;
+                        if (SIG && x[j] != m) v = sigmoid_ref(x[j], sig_ref);
+                        k = max(k, arg_key(v, vi * V + j));
+                    }
             }
         }
     } else if (a.best >= lo) {
@@ -207,12 +216,19 @@ __device__ __forceinline__ void warp_offer_argmax(const ArgTrack<V>& a, const fl
 #pragma unroll
             for (int j = 0; j < V; ++j)
                 if (x[j] >= lo && !hit) {
-                    k = max(k, arg_key(SIG ? sigmoid_ref(x[j], sig_ref) : x[j], vi * V + j));
+                    float v = sm;
+                    if (SIG && x[j] != m) v = sigmoid_ref(x[j], sig_ref);
+                    k = max(k, arg_key(v, vi * V + j));
                     if (!SIG) hit = true;
                 }
         }
     }
-    if (k != 0ull) atomicMax(key, k);
+    k = warp_max_key(k);                                        // two CREDUX.MAX
+    if (SLOT) {
+        if (lane == 0) *key = k;
+    } else if (lane == 0 && k != 0ull) {
+        atomicMax(key, k);
+    }
 }
 
 __device__ __forceinline__ void key_to_argmax(unsigned long long key, float& conf, int& idx) {
@@ -527,13 +543,13 @@ POSE_GLOBAL void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE
 #define POSE_TMA_MPC_GRAD 1     // maps per CTA, kernels that write dlogits
 #endif
 #ifndef POSE_TMA_MPC_RO
-#define POSE_TMA_MPC_RO 4       // maps per CTA, read-only kernels
+#define POSE_TMA_MPC_RO 2       // maps per CTA, read-only kernels
 #endif
 #ifndef POSE_TMA_MINB_GRAD
 #define POSE_TMA_MINB_GRAD 16
 #endif
 #ifndef POSE_TMA_MINB_RO
-#define POSE_TMA_MINB_RO 4
+#define POSE_TMA_MINB_RO 8
 #endif
 __host__ __device__ constexpr int tma_mpc(bool grad) { return grad ? POSE_TMA_MPC_GRAD : POSE_TMA_MPC_RO; }
 __host__ __device__ constexpr int tma_threads(bool grad) { return 32 * POSE_TMA_WPM * tma_mpc(grad); }
@@ -562,7 +578,7 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD 
     __shared__ Patch s_patch[MPC];
     __shared__ FastDiv s_div[MPC];                             // read-only form: division by the window's width in vectors
     __shared__ float s_sum[MPC][WPM][3];
-    __shared__ unsigned long long s_key[MPC];
+    __shared__ unsigned long long s_key[MPC][WPM];              // one slot per warp: no atomics
     // launched with programmatic stream serialisation: the grid may be scheduled while its predecessor (in a training loop the
     // epilogue of the previous step) drains; nothing the predecessor produced is touched before this wait
     pdl_wait();
@@ -588,7 +604,6 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD 
             const uint32_t nvx = pt.ecnt ? (uint32_t)(((pt.px1 - 1) >> 2) - (pt.px0 >> 2) + 1) : 1u;
             s_div[k] = FastDiv{nvx, nvx > 1 ? (uint32_t)((0xffffffffu / nvx) + 1u) : 0u};      // ceil(2^32 / nvx) for nvx that is no power of two; exact for id < 2^16
         }
-        s_key[k] = 0ull;
     }
     __syncthreads();
     if (k < nmap) {
@@ -634,7 +649,7 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD 
         aneg = warp_sum(aneg);
         arem = warp_sum(arem);
         if (lane == 0) { s_sum[k][ws][0] = apos; s_sum[k][ws][1] = aneg; s_sum[k][ws][2] = arem; }
-        if (DEC) warp_offer_argmax<V, true>(arg, tile, nvec, ws * 32, TPM, P.sig_ref, &s_key[k]);
+        if (DEC) warp_offer_argmax<V, true, true>(arg, tile, nvec, ws * 32, TPM, P.sig_ref, &s_key[k][ws]);
     }
     __syncthreads();
     if (tid < nmap) {
@@ -646,7 +661,10 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD 
         if (DEC) {
             float conf;
             int idx;
-            key_to_argmax(s_key[m], conf, idx);
+            unsigned long long key = 0ull;
+#pragma unroll
+            for (int w = 0; w < WPM; ++w) key = max(key, s_key[m][w]);
+            key_to_argmax(key, conf, idx);
             write_joint(P.joints + (map0 + m) * 3, conf, idx, P.thr, P.scale, P.W, P.divW);
         }
     }
@@ -811,14 +829,13 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(false), POSE_TMA_MINB_RO) sbp_dec
     constexpr int V = 4, MPC = tma_mpc(false), WPM = POSE_TMA_WPM, TPM = 32 * WPM;
     extern __shared__ __align__(128) float tiles[];
     __shared__ __align__(8) unsigned long long s_bar[MPC];
-    __shared__ unsigned long long s_key[MPC];
+    __shared__ unsigned long long s_key[MPC][WPM];              // one slot per warp: no atomics
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = wid / WPM, ws = wid - k * WPM, t = ws * 32 + lane;
     const long long map0 = (long long)blockIdx.x * MPC;
     const int nmap = (int)min((long long)MPC, P.n_maps - map0);
     const int nvec = P.HW / V;
     tma_stage_maps(tiles, s_bar, P.x, map0, nmap, P.HW);
-    if (tid < MPC) s_key[tid] = 0ull;
     __syncthreads();
     if (k < nmap) {
         const float* tile = tiles + (size_t)k * P.HW;
@@ -831,7 +848,7 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(false), POSE_TMA_MINB_RO) sbp_dec
             Vec<V>::load_any(tile, vi, x);
             arg.push(x);
         }
-        warp_offer_argmax<V, SIG>(arg, tile, nvec, ws * 32, TPM, P.sig_ref, &s_key[k]);
+        warp_offer_argmax<V, SIG, true>(arg, tile, nvec, ws * 32, TPM, P.sig_ref, &s_key[k][ws]);
     }
     __syncthreads();
     if (tid < nmap) {
@@ -839,7 +856,10 @@ POSE_GLOBAL void __launch_bounds__(tma_threads(false), POSE_TMA_MINB_RO) sbp_dec
         const float* tile = tiles + (size_t)m * P.HW;
         float best;
         int besti;
-        key_to_argmax(s_key[m], best, besti);
+        unsigned long long key = 0ull;
+#pragma unroll
+        for (int w = 0; w < WPM; ++w) key = max(key, s_key[m][w]);
+        key_to_argmax(key, best, besti);
         float dx = 0.0f, dy = 0.0f;
         if (P.refine && best > P.thr && besti != 0x7fffffff) {
             const int row = (int)fdiv((uint32_t)besti, P.divW);

@@ -29,6 +29,13 @@ VARIANTS = {
     "ro_m6": (["-DPOSE_TMA_MPC_RO=6", "-DPOSE_TMA_MINB_RO=3"], (L, LD)),
     "ro_m8": (["-DPOSE_TMA_MPC_RO=8", "-DPOSE_TMA_MINB_RO=2"], (L, LD)),
     "ro_m4_b3": (["-DPOSE_TMA_MINB_RO=3"], (L, LD)),
+    "ro_m2_b8": (["-DPOSE_TMA_MPC_RO=2", "-DPOSE_TMA_MINB_RO=8"], (L, LD)),
+    "ro_m1_b16": (["-DPOSE_TMA_MPC_RO=1", "-DPOSE_TMA_MINB_RO=16"], (L, LD)),
+    "ro_m3_b5": (["-DPOSE_TMA_MPC_RO=3", "-DPOSE_TMA_MINB_RO=5"], (L, LD)),
+    "ro_m4_b4": (["-DPOSE_TMA_MPC_RO=4", "-DPOSE_TMA_MINB_RO=4"], (L, LD)),
+    "ro_w4m1_b16": (["-DPOSE_TMA_WPM=4", "-DPOSE_TMA_MPC_RO=1", "-DPOSE_TMA_MINB_RO=16"], (L, LD)),
+    "ro_w4m2_b8": (["-DPOSE_TMA_WPM=4", "-DPOSE_TMA_MPC_RO=2", "-DPOSE_TMA_MINB_RO=8"], (L, LD)),
+    "ro_w3m2_b8": (["-DPOSE_TMA_WPM=3", "-DPOSE_TMA_MPC_RO=2", "-DPOSE_TMA_MINB_RO=8"], (L, LD)),
 }
 FLAGS = {GD: 1 | 4 | 8, G: 1 | 8, L: 0 | 8, LD: 4 | 8}        # | 8: POSE_F_TMA (bulk-async staged kernels)
 
