@@ -40,6 +40,9 @@ int check_map_shape(int N, int K, int H, int W) {
 
 }  // namespace
 
+#ifndef POSE_TMA_FUSED_PDL
+#define POSE_TMA_FUSED_PDL 1       // fused bulk-staged kernel launched with programmatic stream serialisation (A/B: tools/tune_fused.py)
+#endif
 namespace {
 template <int V, int TGT, bool GRAD, bool WTGT, bool DEC>
 int launch_fused(const pose::SbpFusedParams& P0, size_t smem, cudaStream_t st) {
@@ -57,7 +60,11 @@ int launch_fused_tma(const pose::SbpFusedParams& P0, cudaStream_t st) {
     const size_t smem = pose::sbp_tma_smem_bytes(P.HW, GRAD);
     if (resident_ctas(pose::sbp_fused_tma_kernel<GRAD, DEC>, threads, smem, "sbp_fused(tma)") == 0) return last_code();
     const long long ctas = (P.n_maps + mpc - 1) / mpc;
+#if POSE_TMA_FUSED_PDL
     launch_pdl(pose::sbp_fused_tma_kernel<GRAD, DEC>, (unsigned)ctas, (unsigned)threads, smem, st, P);
+#else
+    pose::sbp_fused_tma_kernel<GRAD, DEC><<<(unsigned)ctas, threads, smem, st>>>(P);
+#endif
     return check_launch("sbp_fused_tma");
 }
 

@@ -30,6 +30,7 @@ VARIANTS = {
     "ro_m8": (["-DPOSE_TMA_MPC_RO=8", "-DPOSE_TMA_MINB_RO=2"], (L, LD)),
     "ro_m4_b3": (["-DPOSE_TMA_MINB_RO=3"], (L, LD)),
     "ro_m2_b8": (["-DPOSE_TMA_MPC_RO=2", "-DPOSE_TMA_MINB_RO=8"], (L, LD)),
+    "nopdl": (["-DPOSE_TMA_FUSED_PDL=0"], (GD, G, L, LD)),
     "ro_m1_b16": (["-DPOSE_TMA_MPC_RO=1", "-DPOSE_TMA_MINB_RO=16"], (L, LD)),
     "ro_m3_b5": (["-DPOSE_TMA_MPC_RO=3", "-DPOSE_TMA_MINB_RO=5"], (L, LD)),
     "ro_m4_b4": (["-DPOSE_TMA_MPC_RO=4", "-DPOSE_TMA_MINB_RO=4"], (L, LD)),
