@@ -56,8 +56,8 @@ int launch_fused(const pose::SbpFusedParams& P0, size_t smem, cudaStream_t st) {
 template <bool GRAD, bool DEC>
 int launch_fused_tma(const pose::SbpFusedParams& P0, cudaStream_t st) {
     pose::SbpFusedParams P = P0;
-    constexpr int mpc = pose::tma_mpc(GRAD), threads = pose::tma_threads(GRAD);
-    const size_t smem = pose::sbp_tma_smem_bytes(P.HW, GRAD);
+    constexpr int cls = pose::tma_cls(GRAD), mpc = pose::tma_mpc(cls), threads = pose::tma_threads(cls);
+    const size_t smem = pose::sbp_tma_smem_bytes(P.HW, pose::tma_cls(GRAD));
     if (resident_ctas(pose::sbp_fused_tma_kernel<GRAD, DEC>, threads, smem, "sbp_fused(tma)") == 0) return last_code();
     const long long ctas = (P.n_maps + mpc - 1) / mpc;
 #if POSE_TMA_FUSED_PDL
@@ -175,7 +175,7 @@ int pose_sbp_fused(const float* logits, const float* target_in, const void* kp, 
         const size_t smem = 0;
         int rc;
         // bulk-async staging (the default of the Python layer): render mode, aligned maps that fit in shared memory
-        const bool tma = (flags & POSE_F_TMA) && kp && vec && !(flags & POSE_F_TARGET_OUT) && pose::sbp_tma_smem_bytes(P.HW, flags & POSE_F_GRAD) <= 112 * 1024;
+        const bool tma = (flags & POSE_F_TMA) && kp && vec && !(flags & POSE_F_TARGET_OUT) && pose::sbp_tma_smem_bytes(P.HW, pose::tma_cls((flags & POSE_F_GRAD) != 0)) <= 112 * 1024;
         if (tma) {
             const bool g = flags & POSE_F_GRAD, d = flags & POSE_F_DECODE;
             rc = g ? (d ? launch_fused_tma<true, true>(P, st) : launch_fused_tma<true, false>(P, st))
@@ -268,8 +268,8 @@ int pose_sbp_decode(const float* x, float* joints, int N, int K, int H, int W, f
     if (P.n_maps > 0x7fffffffll) return fail(POSE_EINVAL, "sbp_decode: N*K=%lld maps exceed one grid", P.n_maps);
     cudaStream_t st = (cudaStream_t)stream;
     const bool sig = apply_sigmoid != 0;
-    const size_t tsmem = pose::sbp_tma_smem_bytes(P.HW, false);
-    constexpr int tthreads = pose::tma_threads(false), tmpc = pose::tma_mpc(false);
+    const size_t tsmem = pose::sbp_tma_smem_bytes(P.HW, pose::kTmaDec);
+    constexpr int tthreads = pose::tma_threads(pose::kTmaDec), tmpc = pose::tma_mpc(pose::kTmaDec);
     if (vec && !(refine & POSE_DEC_NO_TMA) && tsmem <= 112 * 1024) {
         // bulk-async staging: several maps per CTA
         const long long ctas = (P.n_maps + tmpc - 1) / tmpc;

@@ -526,7 +526,7 @@ POSE_GLOBAL void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE
 // every thread's prologue and tail (index arithmetic, three warp reductions, the argmax offer) is paid for just 3 vectors:
 // 292 instructions per thread and map, twice the r01 kernel's count per map -- ncu: issue slots 78-83 % busy, DRAM 57 %.
 // Here the maps in flight live in SHARED MEMORY: one thread issues a cp.async.bulk (UBLKCP, completion on an mbarrier) for
-// each of the CTA's POSE_TMA_MPC_* consecutive maps the moment the CTA starts; POSE_TMA_WPM warps then work on each map (all
+// each of the CTA's POSE_TMA_MPC_* consecutive maps the moment the CTA starts; POSE_TMA_WPM_* warps then work on each map (all
 // maps of the CTA concurrently), one 128-bit vector per thread at a time out of shared memory, so the per-thread overhead is
 // spread over 12-24 vectors and the number of maps in flight is set by shared memory (18 maps fit), not by registers.
 // The arithmetic per element is that of sbp_fused_kernel, so dlogits and joints are bit-identical (a GPU test compares the
@@ -534,16 +534,29 @@ POSE_GLOBAL void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE
 // from shared memory.
 // CTA shape per variant class (tools/tune_fused.py, profiles/r02_tune_tma_*.log; 69 632 maps): the kernels that write dlogits
 // run best as 64-thread CTAs with ONE map, 16 of them per SM (grad+decode 259.3 us, grad 259.1; 2 maps per CTA: 267 / 260; 4:
-// 277 / 265), the read-only ones as 256-thread CTAs with 4 maps (loss 136 us, loss+decode 158, decode 120.9).  Always 2 warps
-// per map: 1 warp per map loses 25 % (grad), 3-4 warps per map pay the per-thread overhead too often.
-#ifndef POSE_TMA_WPM
-#define POSE_TMA_WPM 2          // warps per map
+// 277 / 265) and 2 warps per map (1 warp per map loses 25 %, 3-4 warps per map pay the per-thread overhead too often); the first
+// sweep put the read-only ones at 256-thread CTAs with 4 maps (loss 136 us, loss+decode 158, decode 120.9).
+// Round 2, later: the read-only fused kernels (validation: loss, loss + decode) are bound by issue slots, and everything a map
+// costs per WARP (three loss sums, the argmax offer, prologue) is paid once with ONE warp per map: 2 maps per 64-thread CTA,
+// 8 CTAs per SM -- loss + decode 152 (4 maps x 2 warps) -> 133 (2 x 2) -> 129.6 us (2 x 1); profiles/r02_tune_tma_readonly_mpc2.log.
+// The decode-only kernel (HBM-bound) keeps 2 warps per map.
+#ifndef POSE_TMA_WPM_GRAD
+#define POSE_TMA_WPM_GRAD 2     // warps per map, kernels that write dlogits
+#endif
+#ifndef POSE_TMA_WPM_RO
+#define POSE_TMA_WPM_RO 1       // warps per map, read-only fused kernels
+#endif
+#ifndef POSE_TMA_WPM_DEC
+#define POSE_TMA_WPM_DEC 2      // warps per map, decode-only kernel
 #endif
 #ifndef POSE_TMA_MPC_GRAD
 #define POSE_TMA_MPC_GRAD 1     // maps per CTA, kernels that write dlogits
 #endif
 #ifndef POSE_TMA_MPC_RO
-#define POSE_TMA_MPC_RO 2       // maps per CTA, read-only kernels
+#define POSE_TMA_MPC_RO 2       // maps per CTA, read-only fused kernels
+#endif
+#ifndef POSE_TMA_MPC_DEC
+#define POSE_TMA_MPC_DEC 2      // maps per CTA, decode-only kernel
 #endif
 #ifndef POSE_TMA_MINB_GRAD
 #define POSE_TMA_MINB_GRAD 16
@@ -551,9 +564,16 @@ POSE_GLOBAL void __launch_bounds__(kSbpThreads, GRAD ? POSE_MAP_MINB_GRAD : POSE
 #ifndef POSE_TMA_MINB_RO
 #define POSE_TMA_MINB_RO 8
 #endif
-__host__ __device__ constexpr int tma_mpc(bool grad) { return grad ? POSE_TMA_MPC_GRAD : POSE_TMA_MPC_RO; }
-__host__ __device__ constexpr int tma_threads(bool grad) { return 32 * POSE_TMA_WPM * tma_mpc(grad); }
-__host__ __device__ inline size_t sbp_tma_smem_bytes(int HW, bool grad) { return (size_t)tma_mpc(grad) * (size_t)HW * sizeof(float); }
+#ifndef POSE_TMA_MINB_DEC
+#define POSE_TMA_MINB_DEC 8
+#endif
+constexpr int kTmaGrad = 0, kTmaRo = 1, kTmaDec = 2;            // kernel classes of the bulk-staged forms
+__host__ __device__ constexpr int tma_cls(bool grad) { return grad ? kTmaGrad : kTmaRo; }
+__host__ __device__ constexpr int tma_mpc(int cls) { return cls == kTmaGrad ? POSE_TMA_MPC_GRAD : cls == kTmaRo ? POSE_TMA_MPC_RO : POSE_TMA_MPC_DEC; }
+__host__ __device__ constexpr int tma_wpm(int cls) { return cls == kTmaGrad ? POSE_TMA_WPM_GRAD : cls == kTmaRo ? POSE_TMA_WPM_RO : POSE_TMA_WPM_DEC; }
+__host__ __device__ constexpr int tma_minb(int cls) { return cls == kTmaGrad ? POSE_TMA_MINB_GRAD : cls == kTmaRo ? POSE_TMA_MINB_RO : POSE_TMA_MINB_DEC; }
+__host__ __device__ constexpr int tma_threads(int cls) { return 32 * tma_wpm(cls) * tma_mpc(cls); }
+__host__ __device__ inline size_t sbp_tma_smem_bytes(int HW, int cls) { return (size_t)tma_mpc(cls) * (size_t)HW * sizeof(float); }
 
 // stage the CTA's maps: thread 0 initialises one mbarrier per map and issues the bulk copies (the caller's next CTA barrier
 // makes the initialised mbarriers visible to the waiting threads)
@@ -571,8 +591,8 @@ __device__ __forceinline__ void tma_stage_maps(float* tiles, unsigned long long*
 }
 
 template <bool GRAD, bool DEC>
-POSE_GLOBAL void __launch_bounds__(tma_threads(GRAD), GRAD ? POSE_TMA_MINB_GRAD : POSE_TMA_MINB_RO) sbp_fused_tma_kernel(SbpFusedParams P) {
-    constexpr int V = 4, MPC = tma_mpc(GRAD), WPM = POSE_TMA_WPM, TPM = 32 * WPM;
+POSE_GLOBAL void __launch_bounds__(tma_threads(tma_cls(GRAD)), tma_minb(tma_cls(GRAD))) sbp_fused_tma_kernel(SbpFusedParams P) {
+    constexpr int V = 4, MPC = tma_mpc(tma_cls(GRAD)), WPM = tma_wpm(tma_cls(GRAD)), TPM = 32 * WPM;
     extern __shared__ __align__(128) float tiles[];            // MPC maps of HW floats
     __shared__ __align__(8) unsigned long long s_bar[MPC];
     __shared__ Patch s_patch[MPC];
@@ -822,11 +842,11 @@ POSE_GLOBAL void __launch_bounds__(kSbpThreads, POSE_MAP_MINB_RO) sbp_decode_ker
     }
 }
 
-// bulk-async staged form of sbp_decode_kernel (16-byte aligned maps): POSE_TMA_MPC_RO maps per CTA, POSE_TMA_WPM warps per map,
+// bulk-async staged form of sbp_decode_kernel (16-byte aligned maps): POSE_TMA_MPC_DEC maps per CTA, POSE_TMA_WPM_DEC warps per map,
 // see sbp_fused_tma_kernel
 template <bool SIG>
-POSE_GLOBAL void __launch_bounds__(tma_threads(false), POSE_TMA_MINB_RO) sbp_decode_tma_kernel(SbpDecodeParams P) {
-    constexpr int V = 4, MPC = tma_mpc(false), WPM = POSE_TMA_WPM, TPM = 32 * WPM;
+POSE_GLOBAL void __launch_bounds__(tma_threads(kTmaDec), tma_minb(kTmaDec)) sbp_decode_tma_kernel(SbpDecodeParams P) {
+    constexpr int V = 4, MPC = tma_mpc(kTmaDec), WPM = tma_wpm(kTmaDec), TPM = 32 * WPM;
     extern __shared__ __align__(128) float tiles[];
     __shared__ __align__(8) unsigned long long s_bar[MPC];
     __shared__ unsigned long long s_key[MPC][WPM];              // one slot per warp: no atomics

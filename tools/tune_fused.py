@@ -17,26 +17,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "tune")
 
-# name -> (-D knobs, kernels worth timing for it).  Shipped ("tree"): see the POSE_MAP_* defaults in csrc/sbp_kernels.cuh.
+# name -> (-D knobs, kernels worth timing for it).  Shipped ("tree"): see the POSE_TMA_* defaults in csrc/sbp_kernels.cuh
+# (read-only fused kernels: 1 warp per map, 2 maps per CTA, 8 CTAs per SM).
 GD, G, L, LD = "grad+decode", "grad", "loss", "loss+decode"
 VARIANTS = {
-    "g_m1": (["-DPOSE_TMA_MPC_GRAD=1", "-DPOSE_TMA_MINB_GRAD=16"], (GD, G)),
-    "g_m2_b6": (["-DPOSE_TMA_MINB_GRAD=6"], (GD, G)),
-    "g_m2_b10": (["-DPOSE_TMA_MINB_GRAD=10"], (GD, G)),
-    "g_m3": (["-DPOSE_TMA_MPC_GRAD=3", "-DPOSE_TMA_MINB_GRAD=5"], (GD, G)),
-    "g_w1m4": (["-DPOSE_TMA_WPM=1", "-DPOSE_TMA_MPC_GRAD=4", "-DPOSE_TMA_MINB_GRAD=8"], (GD, G)),
-    "ro_m3": (["-DPOSE_TMA_MPC_RO=3", "-DPOSE_TMA_MINB_RO=5"], (L, LD)),
-    "ro_m6": (["-DPOSE_TMA_MPC_RO=6", "-DPOSE_TMA_MINB_RO=3"], (L, LD)),
-    "ro_m8": (["-DPOSE_TMA_MPC_RO=8", "-DPOSE_TMA_MINB_RO=2"], (L, LD)),
-    "ro_m4_b3": (["-DPOSE_TMA_MINB_RO=3"], (L, LD)),
-    "ro_m2_b8": (["-DPOSE_TMA_MPC_RO=2", "-DPOSE_TMA_MINB_RO=8"], (L, LD)),
+    "g_m2_b8": (["-DPOSE_TMA_MPC_GRAD=2", "-DPOSE_TMA_MINB_GRAD=8"], (GD, G)),
+    "g_w1m2": (["-DPOSE_TMA_WPM_GRAD=1", "-DPOSE_TMA_MPC_GRAD=2", "-DPOSE_TMA_MINB_GRAD=16"], (GD, G)),
     "nopdl": (["-DPOSE_TMA_FUSED_PDL=0"], (GD, G, L, LD)),
-    "ro_m1_b16": (["-DPOSE_TMA_MPC_RO=1", "-DPOSE_TMA_MINB_RO=16"], (L, LD)),
-    "ro_m3_b5": (["-DPOSE_TMA_MPC_RO=3", "-DPOSE_TMA_MINB_RO=5"], (L, LD)),
-    "ro_m4_b4": (["-DPOSE_TMA_MPC_RO=4", "-DPOSE_TMA_MINB_RO=4"], (L, LD)),
-    "ro_w4m1_b16": (["-DPOSE_TMA_WPM=4", "-DPOSE_TMA_MPC_RO=1", "-DPOSE_TMA_MINB_RO=16"], (L, LD)),
-    "ro_w4m2_b8": (["-DPOSE_TMA_WPM=4", "-DPOSE_TMA_MPC_RO=2", "-DPOSE_TMA_MINB_RO=8"], (L, LD)),
-    "ro_w3m2_b8": (["-DPOSE_TMA_WPM=3", "-DPOSE_TMA_MPC_RO=2", "-DPOSE_TMA_MINB_RO=8"], (L, LD)),
+    "ro_w2m2_b8": (["-DPOSE_TMA_WPM_RO=2"], (L, LD)),
+    "ro_w2m4_b4": (["-DPOSE_TMA_WPM_RO=2", "-DPOSE_TMA_MPC_RO=4", "-DPOSE_TMA_MINB_RO=4"], (L, LD)),
+    "ro_w1m1_b16": (["-DPOSE_TMA_MPC_RO=1", "-DPOSE_TMA_MINB_RO=16"], (L, LD)),
+    "ro_w1m3_b5": (["-DPOSE_TMA_MPC_RO=3", "-DPOSE_TMA_MINB_RO=5"], (L, LD)),
+    "ro_w1m4_b4": (["-DPOSE_TMA_MPC_RO=4", "-DPOSE_TMA_MINB_RO=4"], (L, LD)),
 }
 FLAGS = {GD: 1 | 4 | 8, G: 1 | 8, L: 0 | 8, LD: 4 | 8}        # | 8: POSE_F_TMA (bulk-async staged kernels)
 
