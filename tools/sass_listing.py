@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 LIB = "pytorch-pose-estimation_b200/libpose_b200.so"
-KEY = re.compile(r"UTC\w*|LDTM\S*|STTM\S*|UTMALDG\S*|UTMASTG\S*|UBLKCP\S*|SYNCS\S*|UTCATOMSWS\S*|MUFU\S*|LDG\S*|STG\S*|LDS\S*|STS\S*")
+KEY = re.compile(r"CREDUX\S*|UTC\w*|LDTM\S*|STTM\S*|UTMALDG\S*|UTMASTG\S*|UBLKCP\S*|SYNCS\S*|UTCATOMSWS\S*|MUFU\S*|LDG\S*|STG\S*|LDS\S*|STS\S*")
 
 
 def main():
