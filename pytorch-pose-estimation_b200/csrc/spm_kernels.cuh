@@ -499,6 +499,9 @@ __device__ __forceinline__ void spm_pixel_target(const SpmFusedParams& P, const 
 #ifndef POSE_SPM_UNIT_QUADS_RENDER
 #define POSE_SPM_UNIT_QUADS_RENDER 2048
 #endif
+#ifndef POSE_SPM_RO_SCREEN_ALL
+#define POSE_SPM_RO_SCREEN_ALL 1
+#endif
 #ifndef POSE_SPM_UNIT_THREADS
 #define POSE_SPM_UNIT_THREADS 128
 #endif
@@ -689,8 +692,11 @@ __global__ void __launch_bounds__(kSpmUnitThreads, LOSS ? POSE_SPM_UNIT_MINB_LOS
     if (LOSS) mbar_wait_parity(&s_bar, 0);
     // phase A: the quads no person touches
 #pragma unroll 4
+    // (read-only form: the screen runs over EVERY quad, covered or not -- a NaN under a person makes the sum NaN in phase B anyway,
+    // every other covered logit adds 0 here -- so the stream carries no coverage test: SCREEN_ALL)
+    constexpr bool SCREEN_ALL = LOSS && !GRAD && !WTGT && POSE_SPM_RO_SCREEN_ALL;
     for (int q = tid; q < nq; q += kSpmUnitThreads) {
-        if ((s_cov[q >> 5] >> (q & 31)) & 1u) continue;
+        if (!SCREEN_ALL && ((s_cov[q >> 5] >> (q & 31)) & 1u)) continue;
         if (LOSS) {
             // (the sum of the four is NaN whenever one of them is; +inf + -inf also lands here and adds nothing)
             const float4 v = reinterpret_cast<const float4*>(tile)[q];

@@ -22,11 +22,7 @@ VARIANTS = {
     "l2048_b5": ["-DPOSE_SPM_UNIT_QUADS_LOSS=2048", "-DPOSE_SPM_UNIT_MINB_LOSS=5"],
     "r1024_b10": ["-DPOSE_SPM_UNIT_QUADS_RENDER=1024", "-DPOSE_SPM_UNIT_MINB_RENDER=10"],
     "r4096_b3": ["-DPOSE_SPM_UNIT_QUADS_RENDER=4096", "-DPOSE_SPM_UNIT_MINB_RENDER=3"],
-    "t64_l512_b20": ["-DPOSE_SPM_UNIT_THREADS=64", "-DPOSE_SPM_UNIT_QUADS_LOSS=512", "-DPOSE_SPM_UNIT_MINB_LOSS=20"],
-    "t64_l512_b16": ["-DPOSE_SPM_UNIT_THREADS=64", "-DPOSE_SPM_UNIT_QUADS_LOSS=512", "-DPOSE_SPM_UNIT_MINB_LOSS=16"],
-    "t64_l1024_b10": ["-DPOSE_SPM_UNIT_THREADS=64", "-DPOSE_SPM_UNIT_QUADS_LOSS=1024", "-DPOSE_SPM_UNIT_MINB_LOSS=10"],
-    "t256_l1024_b8": ["-DPOSE_SPM_UNIT_THREADS=256", "-DPOSE_SPM_UNIT_QUADS_LOSS=1024", "-DPOSE_SPM_UNIT_MINB_LOSS=8"],
-    "t256_l2048_b5": ["-DPOSE_SPM_UNIT_THREADS=256", "-DPOSE_SPM_UNIT_QUADS_LOSS=2048", "-DPOSE_SPM_UNIT_MINB_LOSS=5"],
+    "ro_screen_covtest": ["-DPOSE_SPM_RO_SCREEN_ALL=0"],
 }
 
 
