@@ -556,36 +556,77 @@ __global__ void __launch_bounds__(kSpmUnitThreads, LOSS ? POSE_SPM_UNIT_MINB_LOS
     // are never referenced by the geometry.  (Fetching them only in units that turn out to contain covered quads -- 40 % --
     // was measured: no gain for the loss kernels, 9 % slower for the render-only one, which has no bulk copy to hide it under.)
     const int np = min(P.Pmax, kSpmFusedMaxPersons);
-    if (disp) {
-        const long long* jimg = P.joints + ((long long)img * P.Pmax * P.K + jn) * 2;
-        for (int p = tid; p < np; p += kSpmUnitThreads) {
-            const longlong2 jv = __ldg(reinterpret_cast<const longlong2*>(jimg + (long long)p * P.K * 2));
-            s_j[p] = make_int2((int)max(min(jv.x, 1ll << 30), -(1ll << 30)), (int)max(min(jv.y, 1ll << 30), -(1ll << 30)));
+    // Read-only form (SCREEN_ALL): phase A needs nothing but the logits, so the prologue's global loads (joints, coverage word,
+    // person record -- at most one of each per thread) are only ISSUED here, phase A runs under their latency, and they are
+    // parked in shared memory afterwards.  ncu before: 24 % of all stall samples sat behind the barrier that waited for them.
+    constexpr bool SCREEN_ALL = LOSS && !GRAD && !WTGT && POSE_SPM_RO_SCREEN_ALL;
+    const bool early_a = SCREEN_ALL && qpr == 32;
+    float acc = 0.f;
+    auto screen_quad = [&](int q) {
+        // (the sum of the four is NaN whenever one of them is; +inf + -inf also lands here and adds nothing)
+        const float4 v = reinterpret_cast<const float4*>(tile)[q];
+        const float sum4 = (v.x + v.y) + (v.z + v.w);
+        if (sum4 != sum4) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
+    };
+    if (early_a) {
+        static_assert(kSpmFusedMaxPersons <= kSpmUnitThreads || !SCREEN_ALL, "one person per thread");
+        static_assert(kSpmUnitWords <= kSpmUnitThreads || !SCREEN_ALL, "one coverage word per thread");
+        longlong2 jv = make_longlong2(0, 0);
+        if (disp && tid < np) jv = __ldg(reinterpret_cast<const longlong2*>(P.joints + ((long long)img * P.Pmax * P.K + jn) * 2 + (long long)tid * P.K * 2));
+        pdl_wait();                                                     // the image records are complete and visible
+        const unsigned char* rec0 = P.geom + (unsigned long long)img * P.gl.stride;
+        unsigned cw = 0u;
+        if (tid < kSpmUnitWords && 32 * tid < nq) cw = __ldcg(reinterpret_cast<const unsigned int*>(rec0 + P.gl.off_covq) + (q_lo >> 5) + tid);
+        uint4 sp0 = make_uint4(0, 0, 0, 0), sp1 = sp0;
+        if (tid < np) {
+            const uint4* ps = reinterpret_cast<const uint4*>(rec0 + P.gl.off_persons) + 2 * tid;
+            sp0 = __ldcg(ps);
+            sp1 = __ldcg(ps + 1);
         }
+        __syncthreads();                                                // the initialised mbarrier
+        mbar_wait_parity(&s_bar, 0);
+#pragma unroll 4
+        for (int q = tid; q < nq; q += kSpmUnitThreads) screen_quad(q);
+        if (disp && tid < np) s_j[tid] = make_int2((int)max(min(jv.x, 1ll << 30), -(1ll << 30)), (int)max(min(jv.y, 1ll << 30), -(1ll << 30)));
+        if (tid < kSpmUnitWords) s_cov[tid] = cw;
+        if (tid < np) {
+            reinterpret_cast<uint4*>(s_p)[2 * tid] = sp0;
+            reinterpret_cast<uint4*>(s_p)[2 * tid + 1] = sp1;
+        }
+    } else {
+        if (disp) {
+            const long long* jimg = P.joints + ((long long)img * P.Pmax * P.K + jn) * 2;
+            for (int p = tid; p < np; p += kSpmUnitThreads) {
+                const longlong2 jv = __ldg(reinterpret_cast<const longlong2*>(jimg + (long long)p * P.K * 2));
+                s_j[p] = make_int2((int)max(min(jv.x, 1ll << 30), -(1ll << 30)), (int)max(min(jv.y, 1ll << 30), -(1ll << 30)));
+            }
+        }
+        pdl_wait();                                                     // the image records are complete and visible
     }
-    pdl_wait();                                                         // the image records are complete and visible
     const unsigned char* rec = P.geom + (unsigned long long)img * P.gl.stride;
     const unsigned int* covq_g = reinterpret_cast<const unsigned int*>(rec + P.gl.off_covq);
     const unsigned long long* rowmask_g = reinterpret_cast<const unsigned long long*>(rec + P.gl.off_rowmask);
     const unsigned char* map_g = rec + P.gl.off_map;
-    // coverage words of the unit: word i = quads [32 i, 32 i + 32) of the unit
-    if (qpr == 32) {
-        for (int i = tid; i < kSpmUnitWords; i += kSpmUnitThreads) s_cov[i] = (32 * i < nq) ? __ldcg(covq_g + (q_lo >> 5) + i) : 0u;
-    } else {
+    if (!early_a) {
+        // coverage words of the unit: word i = quads [32 i, 32 i + 32) of the unit
+        if (qpr == 32) {
+            for (int i = tid; i < kSpmUnitWords; i += kSpmUnitThreads) s_cov[i] = (32 * i < nq) ? __ldcg(covq_g + (q_lo >> 5) + i) : 0u;
+        } else {
 #pragma unroll 2
-        for (int i = wid; i < kSpmUnitWords; i += kSpmUnitWarps) {
-            const int q = q_lo + 32 * i + lane;
-            bool covered = false;
-            if (32 * i + lane < nq) {
-                const int row = (int)fdiv((uint32_t)q, P.div_qpr), cq = q - row * qpr;
-                covered = (__ldcg(covq_g + row * P.wpr + (cq >> 5)) >> (cq & 31)) & 1u;
+            for (int i = wid; i < kSpmUnitWords; i += kSpmUnitWarps) {
+                const int q = q_lo + 32 * i + lane;
+                bool covered = false;
+                if (32 * i + lane < nq) {
+                    const int row = (int)fdiv((uint32_t)q, P.div_qpr), cq = q - row * qpr;
+                    covered = (__ldcg(covq_g + row * P.wpr + (cq >> 5)) >> (cq & 31)) & 1u;
+                }
+                const unsigned w = __ballot_sync(FULL_MASK, covered);
+                if (lane == 0) s_cov[i] = w;
             }
-            const unsigned w = __ballot_sync(FULL_MASK, covered);
-            if (lane == 0) s_cov[i] = w;
         }
+        for (int p = tid; p < np; p += kSpmUnitThreads) s_p[p] = reinterpret_cast<const SpmFusedPerson*>(rec + P.gl.off_persons)[p];
     }
-    for (int p = tid; p < np; p += kSpmUnitThreads) s_p[p] = reinterpret_cast<const SpmFusedPerson*>(rec + P.gl.off_persons)[p];
-    __syncthreads();                                                    // s_cov, s_p, s_j, the initialised mbarrier
+    __syncthreads();                                                    // s_cov, s_p, s_j (and, not early_a, the initialised mbarrier)
     // list of the covered quads: every warp scans the word pop-counts itself (no extra barrier; a lane takes WPL consecutive
     // words), then fills the part of the list that belongs to its own words
     int ncov;
@@ -648,7 +689,6 @@ __global__ void __launch_bounds__(kSpmUnitThreads, LOSS ? POSE_SPM_UNIT_MINB_LOS
         }
         if (!disp) te = t0;                                             // (root plane: the target value itself)
     };
-    float acc = 0.f;
     // loss term + gradient of covered pixel i given its target; stores the results
     auto finish = [&](int i, float t0, float te, bool mk) {
         const int qu = (int)s_list[i >> 2], e = i & 3;
@@ -689,22 +729,18 @@ __global__ void __launch_bounds__(kSpmUnitThreads, LOSS ? POSE_SPM_UNIT_MINB_LOS
     float4* G4 = reinterpret_cast<float4*>(P.dlogits) + off;
     float4* T4 = reinterpret_cast<float4*>(P.target_out) + off;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (LOSS) mbar_wait_parity(&s_bar, 0);
+    if (LOSS && !early_a) mbar_wait_parity(&s_bar, 0);
     // phase A: the quads no person touches
-#pragma unroll 4
     // (read-only form: the screen runs over EVERY quad, covered or not -- a NaN under a person makes the sum NaN in phase B anyway,
-    // every other covered logit adds 0 here -- so the stream carries no coverage test: SCREEN_ALL)
-    constexpr bool SCREEN_ALL = LOSS && !GRAD && !WTGT && POSE_SPM_RO_SCREEN_ALL;
-    for (int q = tid; q < nq; q += kSpmUnitThreads) {
-        if (!SCREEN_ALL && ((s_cov[q >> 5] >> (q & 31)) & 1u)) continue;
-        if (LOSS) {
-            // (the sum of the four is NaN whenever one of them is; +inf + -inf also lands here and adds nothing)
-            const float4 v = reinterpret_cast<const float4*>(tile)[q];
-            const float sum4 = (v.x + v.y) + (v.z + v.w);
-            if (sum4 != sum4) acc += (v.x != v.x ? v.x : 0.f) + (v.y != v.y ? v.y : 0.f) + (v.z != v.z ? v.z : 0.f) + (v.w != v.w ? v.w : 0.f);
+    // every other covered logit adds 0 here -- so the stream carries no coverage test: SCREEN_ALL; done above when early_a)
+    if (!early_a) {
+#pragma unroll 4
+        for (int q = tid; q < nq; q += kSpmUnitThreads) {
+            if (!SCREEN_ALL && ((s_cov[q >> 5] >> (q & 31)) & 1u)) continue;
+            if (LOSS) screen_quad(q);
+            if (GRAD) __stcs(G4 + q, z4);
+            if (WTGT) __stcs(T4 + q, z4);
         }
-        if (GRAD) __stcs(G4 + q, z4);
-        if (WTGT) __stcs(T4 + q, z4);
     }
     // phase B: one pixel of a covered quad per thread.  (Measured and dropped: working the targets out before the wait for the
     // bulk copy -- 123 vs 119 us read-only; a per-image hash table pixel -> covering persons for the pixels in several boxes
