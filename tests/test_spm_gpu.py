@@ -306,6 +306,50 @@ def test_fused_crowded_edges_and_nan(pb, dev):
     assert e["loss"].item() == 0.0 and e["dlogits"].shape[0] == 0
 
 
+@pytest.mark.parametrize("res", [128, 64])
+def test_fused_readonly_screen_nan_and_inf(pb, dev, res):
+    """The read-only form screens EVERY quad for NaN (covered or not) and, at R=128, does so before the covered-quad list exists:
+    NaN anywhere -> NaN loss in both forms; +-inf under a zero mask adds nothing (sigmoid / tanh of +-inf times 0), also when
+    +inf and -inf share a quad (their sum is NaN, the per-element screen is not); results equal the writing form and the oracle."""
+    rng = np.random.default_rng(5)
+    k, sigma = 3, 1
+    people = []
+    for p in (4, 0, 7):
+        c = rng.integers(8, res - 8, size=(p, 1, 2), dtype=np.int64)
+        j = np.clip(c + rng.integers(-12, 13, size=(p, k, 2), dtype=np.int64), 0, res - 1)
+        people.append((c, j))
+    target = np.stack([po.spm_render(c, j, res, sigma) for c, j in people])
+    c, j, cnt = cases.pack_people(people)
+    x0 = torch.randn((3, 1 + 2 * k, res, res), generator=torch.Generator().manual_seed(9)) * 3
+    cx, cy = int(people[0][0][0, 0, 0]), int(people[0][0][0, 0, 1])          # a root centre of image 0: covered, mask set
+    free = np.argwhere(target[0, 0] == 0)                                       # uncovered pixels of image 0's root plane
+    fy, fx = (int(v) for v in free[len(free) // 2])
+    fx &= ~3                                                                    # first element of its quad
+    assert target[0, 0, fy, fx] == 0 and target[0, 0, fy, fx + 1] == 0
+
+    def both(x):
+        g = pb.spm_fused(x.to(dev), c, j, cnt, sigma, want_grad=True)
+        r = pb.spm_fused(x.to(dev), c, j, cnt, sigma, want_grad=False)
+        return g["loss"].item(), r["loss"].item()
+    lg, lr = both(x0)
+    l64, _ = po.spm_loss_closed_form_f64(x0, torch.from_numpy(target))
+    assert lg == lr and close(lr, float(l64), REL)
+    # +-inf under a zero mask: same quad, root plane and a displacement plane; the empty image too
+    xi = x0.clone()
+    xi[0, 0, fy, fx], xi[0, 0, fy, fx + 1] = float("inf"), float("-inf")
+    xi[0, 2, fy, fx], xi[0, 2, fy, fx + 1] = float("inf"), float("-inf")
+    xi[1, 4, 5, 8] = float("inf")
+    li64, _ = po.spm_loss_closed_form_f64(xi, torch.from_numpy(target))
+    lgi, lri = both(xi)
+    assert np.isfinite(lri) and lgi == lri and close(lri, float(li64), REL)
+    # NaN: uncovered pixel / covered pixel, root plane / displacement plane, first / last image
+    for (n, ch, y, x) in ((0, 0, fy, fx), (0, 3, fy, fx + 1), (0, 0, cy, cx), (0, 5, cy, cx), (1, 6, res - 1, res - 1), (2, 1, 0, 0)):
+        xn = x0.clone()
+        xn[n, ch, y, x] = float("nan")
+        lgn, lrn = both(xn)
+        assert np.isnan(lgn) and np.isnan(lrn), (n, ch, y, x)
+
+
 def test_fused_config4_batch(pb, dev):
     """Config 4 at N=64: fused kernel against the dense path on the same rendered target (every image, every plane)."""
     people, target, logits, meta = cases.spm_case("coco", 64, seed=777)
