@@ -158,14 +158,15 @@ def ref_shape(args):
 CPU_WARM, CPU_MAX_PASSES, CPU_MAX_SECONDS = 2, 20, 15.0
 
 
-def time_cpu_pipeline(pipe, max_passes=CPU_MAX_PASSES):
-    """ONE protocol for both places the CPU port is timed (the `cpu_baseline` key of the CUDA line and the `--impl reference`
-    arm): 2 warm-up passes, then up to 20 passes or 15 s, the MEDIAN pass time.  -> (seconds per pass, passes)."""
-    for _ in range(CPU_WARM):
+def time_cpu_pipeline(pipe, max_passes=CPU_MAX_PASSES, warm=CPU_WARM, exact=False):
+    """ONE statistic for both places the CPU port is timed (the `cpu_baseline` key of the CUDA line and the `--impl reference`
+    arm): `warm` warm-up passes, then the MEDIAN pass time of up to 20 passes or 15 s (`cpu_baseline`), or of EXACTLY
+    `max_passes` passes (`exact`: the reference arm runs the --steps / --warmup it was given).  -> (seconds per pass, passes)."""
+    for _ in range(warm):
         pipe.run_pass()
     ts = []
     t_start = time.perf_counter()
-    while len(ts) < 3 or (len(ts) < max_passes and time.perf_counter() - t_start < CPU_MAX_SECONDS):
+    while (len(ts) < max_passes) if exact else (len(ts) < 3 or (len(ts) < max_passes and time.perf_counter() - t_start < CPU_MAX_SECONDS)):
         t0 = time.perf_counter()
         pipe.run_pass()
         ts.append(time.perf_counter() - t0)
@@ -173,9 +174,9 @@ def time_cpu_pipeline(pipe, max_passes=CPU_MAX_PASSES):
     return ts[len(ts) // 2], len(ts)
 
 
-def cpu_baseline_record(value, n, passes, procs, threads, cores):
+def cpu_baseline_record(value, n, passes, procs, threads, cores, warm=CPU_WARM):
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "statistic": "median pass",
-            "sample": (f"{n} images of the same workload per pass, {CPU_WARM} warm-up + {passes} timed passes (median); oracle PORT of the "
+            "sample": (f"{n} images of the same workload per pass, {warm} warm-up + {passes} timed passes (median); oracle PORT of the "
                        f"reference's per-sample Python loops (the reference is pure Python and is not on this box; the port is pinned to it by "
                        f"tests/golden): render and decode over {procs} worker process(es), SBPLoss fwd+bwd on {threads} torch threads")}
 
@@ -188,15 +189,26 @@ def run_reference(args):
         return
     import torch
     cores, procs, n = ref_shape(args)
+    # exactly --warmup warm-up and --steps timed passes, each a bounded sample of the workload; the sample shrinks (never below
+    # one image per worker) if the requested passes would not finish within ~3 minutes at the first pass's speed
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     pipe = make_cpu_pipeline(n, procs)          # forks its workers before the parent's torch thread pool exists
     torch.set_num_threads(cores)
-    dt, passes = time_cpu_pipeline(pipe, max(3, min(args.steps, CPU_MAX_PASSES)))
+    t0 = time.perf_counter()
+    pipe.run_pass()
+    first = time.perf_counter() - t0
+    if first * (steps + warm) > 180.0 and not args.ref_sample:
+        pipe.close()
+        n = max(procs, int(n * 180.0 / (first * (steps + warm))))
+        pipe = make_cpu_pipeline(n, procs)
+        pipe.run_pass()
+    dt, passes = time_cpu_pipeline(pipe, steps, warm=warm, exact=True)
     pipe.close()
     value = n * K / dt
-    rec = cpu_baseline_record(value, n, passes, procs, torch.get_num_threads(), cores)
+    rec = cpu_baseline_record(value, n, passes, procs, torch.get_num_threads(), cores, warm=warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": passes,
-        "warmup": CPU_WARM, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"SBP 256x192 (configs[1]): {K}x{H}x{W} heat maps, sigma {SIGMA}: render + JointsMSE fwd/bwd + decode + "
                                f"back-projection; bounded sample of {n} images per step (of the B=4096 workload)",
