@@ -195,8 +195,10 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
 
 /* ---- SPM loss fwd(+bwd) -- SPMLoss.forward models/loss/spm_loss.py:23-105.
  * logits/target/dlogits [N][1+2K][R][R]; loss = (lambda_root*S_root + lambda_disp*S_disp)*inv_norm,
- * inv_norm = 1/B_global.  loss_num_out [2] fp64 = (S_root, S_disp). */
-unsigned long long pose_spm_loss_workspace_bytes(void);
+ * inv_norm = 1/B_global.  loss_num_out [2] fp64 = (S_root, S_disp).  Three launches: the root mask of every image as bits
+ * (the displacement planes need m = t0 > 0 of their pixel), one CTA per 16 KB unit of one plane, the fixed-order reduction of
+ * the per-unit loss pairs; the workspace holds the pairs (16 B per unit) and the mask bits (R*R/8 B per image). */
+unsigned long long pose_spm_loss_workspace_bytes(int N, int K, int R);
 int pose_spm_loss(const float* logits, const float* target, float* dlogits,
                   float* loss_out, double* loss_num_out, int N, int K, int R,
                   float lambda_root, float lambda_disp, double inv_norm, int write_grad,

@@ -56,7 +56,7 @@ SIGNATURES = {
     "pose_sbp_decode_flip": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _f, _i, _vp]),
     "pose_sbp_backproject": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "pose_spm_render": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp, _ull, _vp]),
-    "pose_spm_loss_workspace_bytes": (_ull, []),
+    "pose_spm_loss_workspace_bytes": (_ull, [_i, _i, _i]),
     "pose_spm_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _d, _i, _vp, _ull, _vp]),
     "pose_spm_fused_workspace_bytes": (_ull, [_i, _i, _i]),
     "pose_spm_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _f, _f, _d, _u, _vp, _ull, _vp]),

@@ -107,7 +107,33 @@ int pose_spm_render(const long long* centers, const long long* joints, const int
     return check_launch("spm_render");
 }
 
-unsigned long long pose_spm_loss_workspace_bytes(void) { return (unsigned long long)pose::kMaxPartialBlocks * 2 * sizeof(double); }
+// workspace of pose_spm_loss: one fp64 pair per 16 KB unit, the slice sums and the ticket of the two-level reduction, the root-mask bits
+namespace {
+struct SpmLossWs {
+    double* partials; double* slices; unsigned int* ticket; unsigned int* mask;
+    long long units; int slices_n, mask_words; unsigned long long bytes;
+};
+SpmLossWs spm_loss_ws_layout(void* base, int N, int K, int R) {
+    SpmLossWs w;
+    const long long n = N > 0 ? N : 0;
+    w.units = n * (1 + 2 * K) * pose::spm_loss_units_per_plane(R);
+    w.slices_n = pose::reduce_slices(w.units);
+    w.mask_words = pose::spm_mask_words(R);
+    unsigned long long off = 0;
+    const uintptr_t b = reinterpret_cast<uintptr_t>(base);          // (base may be NULL: size query)
+    w.partials = reinterpret_cast<double*>(b + off); off += (unsigned long long)w.units * 16;
+    w.slices = reinterpret_cast<double*>(b + off); off += (unsigned long long)w.slices_n * 16;
+    w.ticket = reinterpret_cast<unsigned int*>(b + off); off += 16;
+    w.mask = reinterpret_cast<unsigned int*>(b + off); off += (unsigned long long)n * w.mask_words * 4;
+    w.bytes = off > 16 ? off : 16;
+    return w;
+}
+}  // namespace
+
+unsigned long long pose_spm_loss_workspace_bytes(int N, int K, int R) {
+    if (N < 0 || K <= 0 || R <= 0) return 0ull;
+    return spm_loss_ws_layout(nullptr, N, K, R).bytes;
+}
 
 int pose_spm_loss(const float* logits, const float* target, float* dlogits, float* loss_out, double* loss_num_out, int N,
                   int K, int R, float lambda_root, float lambda_disp, double inv_norm, int write_grad, void* workspace,
@@ -115,30 +141,41 @@ int pose_spm_loss(const float* logits, const float* target, float* dlogits, floa
     if (N < 0 || K <= 0 || R <= 0 || R % 4 != 0) return fail(POSE_EINVAL, "spm_loss: bad shape (R must be a multiple of 4)");
     if (!logits || !target || (write_grad && !dlogits) || (!loss_out && !loss_num_out)) return fail(POSE_EINVAL, "spm_loss: NULL pointer");
     if (!aligned16(logits) || !aligned16(target) || (write_grad && !aligned16(dlogits))) return fail(POSE_EALIGN, "spm_loss: tensors must be 16-byte aligned");
-    if (!workspace || workspace_bytes < pose_spm_loss_workspace_bytes() || !aligned16(workspace)) return fail(POSE_EWORKSPACE, "spm_loss: workspace too small / unaligned");
+    if (!workspace || workspace_bytes < pose_spm_loss_workspace_bytes(N, K, R) || !aligned16(workspace))
+        return fail(POSE_EWORKSPACE, "spm_loss: workspace too small / unaligned (%llu bytes needed)", pose_spm_loss_workspace_bytes(N, K, R));
     if (write_grad && dlogits == logits) return fail(POSE_EINVAL, "spm_loss: dlogits must not alias logits");
+    if (N > 65535 || 1 + 2 * K > 65535) return fail(POSE_EINVAL, "spm_loss: N=%d / K=%d exceed the grid (65535 images per call)", N, K);
     cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0)    // an empty batch reduces zero pairs: loss 0
+        return pose_loss_reduce((const double*)workspace, 0, 2ll, (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out, stream);
+    const SpmLossWs w = spm_loss_ws_layout(workspace, N, K, R);
     pose::SpmLossParams P;
-    P.logits = logits; P.target = target; P.dlogits = dlogits; P.partials = reinterpret_cast<double*>(workspace);
-    P.quads = R * R / 4; P.C = 1 + 2 * K; P.planes = (long long)N * P.C;
+    P.logits = logits; P.target = target; P.dlogits = dlogits; P.partials = w.partials; P.mask = w.mask; P.ticket = w.ticket;
+    P.quads = R * R / 4; P.mask_words = w.mask_words; P.C = 1 + 2 * K;
     P.groot = (float)(2.0 * (double)lambda_root * inv_norm);
     P.gdisp = (float)((double)lambda_disp * inv_norm);
-    int grid = 0;
-    if (N > 0) {
-        const long long ctas = P.planes * ((P.quads + pose::kSpmLossChunk - 1) / pose::kSpmLossChunk);
-        if (write_grad) {
-            grid = persistent_grid(pose::spm_loss_kernel<true>, pose::kSpmThreads, 0, ctas, "spm_loss");
-            if (grid == 0) return last_code();
-            pose::spm_loss_kernel<true><<<grid, pose::kSpmThreads, 0, st>>>(P);
-        } else {
-            grid = persistent_grid(pose::spm_loss_kernel<false>, pose::kSpmThreads, 0, ctas, "spm_loss");
-            if (grid == 0) return last_code();
-            pose::spm_loss_kernel<false><<<grid, pose::kSpmThreads, 0, st>>>(P);
-        }
-        if (int rc = check_launch("spm_loss")) return rc;
+    // (1) root-mask bits of every image; (2) one CTA per 16 KB unit, launched with programmatic stream serialisation: its loads
+    // are in flight while (1) drains; (3) the two-level fixed-order reduction of the per-unit pairs
+    pose::spm_root_mask_kernel<<<dim3((unsigned)((P.quads + 255) / 256), (unsigned)N), 256, 0, st>>>(P);
+    if (int rc = check_launch("spm_root_mask")) return rc;
+    const unsigned upp = (unsigned)pose::spm_loss_units_per_plane(R);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(upp, (unsigned)P.C, (unsigned)N);
+        cfg.blockDim = dim3((unsigned)pose::kSpmThreads);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (write_grad) cudaLaunchKernelEx(&cfg, pose::spm_loss_kernel<true>, P);
+        else cudaLaunchKernelEx(&cfg, pose::spm_loss_kernel<false>, P);
     }
-    // (an empty batch reduces zero pairs: loss 0)
-    return pose_loss_reduce(P.partials, grid, 2ll, (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out, stream);
+    if (int rc = check_launch("spm_loss")) return rc;
+    launch_pdl(pose::spm_loss_reduce_kernel, (unsigned)w.slices_n, 256u, 0, st, (const double*)w.partials, w.units, w.slices, w.ticket, w.slices_n,
+               (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out);
+    return check_launch("spm_loss_reduce");
 }
 
 unsigned long long pose_spm_fused_workspace_bytes(int N, int K, int R) {

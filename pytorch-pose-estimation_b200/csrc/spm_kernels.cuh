@@ -218,88 +218,114 @@ __global__ void __launch_bounds__(kSpmThreads) spm_patch_kernel(SpmRenderParams 
 //   dL/dp0 = lr 2 (s m - t0) m s (1-s) inv_norm;  dL/dp = ld clip(d,-1,1) m (1 - tanh^2) inv_norm
 struct SpmLossParams {
     const float* logits; const float* target; float* dlogits;
-    double* partials;            // [grid][2]  (S_root, S_disp)
-    long long planes;            // N * C channel planes
+    double* partials;            // [units][2]  (S_root, S_disp) of every 16 KB unit
+    unsigned int* mask;          // [N][mask_words]: bit i of an image = (root target of pixel i > 0), written by spm_root_mask_kernel
+    unsigned int* ticket;        // two-level loss reduction counter (zeroed by spm_root_mask_kernel)
     int quads;                   // R*R/4 float4 per plane
+    int mask_words;              // 32-bit words per image (a multiple of 4)
     int C;                       // 1 + 2K
     float groot, gdisp;          // 2*lambda_root*inv_norm, lambda_disp*inv_norm
 };
 
 constexpr int kSpmLossU = 4;                                  // float4 per thread and tensor in flight
 constexpr int kSpmLossChunk = kSpmThreads * kSpmLossU;        // float4 per work unit (1024 -> 16 KB per tensor)
+__host__ __device__ inline int spm_loss_units_per_plane(int R) { return (R * R / 4 + kSpmLossChunk - 1) / kSpmLossChunk; }
+__host__ __device__ inline int spm_mask_words(int R) { return ((R * R + 31) / 32 + 3) / 4 * 4; }
 
-// The tensors are streamed linearly, plane by plane (unit = 16 KB of one channel plane), exactly like the SBP kernels;
-// the root mask of a displacement plane comes from channel 0 of the same image, re-read through L2 (64 KB per image).
+// Root mask of every image as bits (2 KB per image at R = 128): the displacement planes of the dense loss need m = (t0 > 0) of
+// their pixel, and re-reading the image's root TARGET plane for it (r01: a third 128-bit load per quad, through L2) cost the
+// streaming kernel 7 % (1 159 vs 1 079 us per 1024 images with the load taken out); here it is 4 bits per quad from a word that
+// eight neighbouring threads share.  grid = (ceil(quads / 256), N), 256 threads, one quad per thread.
+__global__ void __launch_bounds__(256) spm_root_mask_kernel(SpmLossParams P) {
+    pdl_launch_dependents();
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.ticket = 0u;
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    const long long img = blockIdx.y;
+    unsigned nib = 0u;
+    if (q < P.quads) {
+        const float4 v = ldg_stream(reinterpret_cast<const float4*>(P.target) + img * P.C * P.quads + q);
+        nib = (v.x > 0.0f ? 1u : 0u) | (v.y > 0.0f ? 2u : 0u) | (v.z > 0.0f ? 4u : 0u) | (v.w > 0.0f ? 8u : 0u);
+    }
+    unsigned w = nib << ((threadIdx.x & 7) * 4);
+    w |= __shfl_xor_sync(FULL_MASK, w, 1);
+    w |= __shfl_xor_sync(FULL_MASK, w, 2);
+    w |= __shfl_xor_sync(FULL_MASK, w, 4);
+    if ((threadIdx.x & 7) == 0 && (q >> 3) < P.mask_words) P.mask[img * P.mask_words + (q >> 3)] = w;
+}
+
+// NOT persistent (round 2, later): one 256-thread CTA per 16 KB unit of one channel plane, grid = (units per plane, 1+2K, N) --
+// no index divisions, CTAs handed out in memory order; every thread's loads (4 quads of logits + 4 of target) are issued before
+// anything else.  One fp64 (S_root, S_disp) pair per unit, reduced in a fixed order by spm_loss_reduce_kernel.  Against the
+// persistent r01 form (every CTA strode over the units, root mask from the target's root plane): 1 189 -> see DESIGN 3.5.
 template <bool GRAD>
 __global__ void __launch_bounds__(kSpmThreads) spm_loss_kernel(SpmLossParams P) {
-    __shared__ double red[kSpmThreads / 32][2];
+    __shared__ float red[kSpmThreads / 32];
     pdl_launch_dependents();
-    const int upp = (P.quads + kSpmLossChunk - 1) / kSpmLossChunk;          // units per plane
-    const long long units = P.planes * upp;
+    const int chunk = blockIdx.x, c = blockIdx.y;
+    const long long img = blockIdx.z;
+    const long long plane = img * gridDim.y + c;
+    const long long unit = plane * gridDim.x + chunk;
+    const long long off = plane * P.quads;
     const float4* L4 = reinterpret_cast<const float4*>(P.logits);
     const float4* T4 = reinterpret_cast<const float4*>(P.target);
     float4* G4 = reinterpret_cast<float4*>(P.dlogits);
-    double droot = 0.0, ddisp = 0.0;
-    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        const long long plane = unit / upp;
-        const int chunk = (int)(unit - plane * upp);
-        const int c = (int)(plane % P.C);
-        const long long off = plane * P.quads, off0 = (plane - c) * P.quads;  // this plane / the image's root plane
-        float4 pv[kSpmLossU], tv[kSpmLossU], t0[kSpmLossU];
-        int q[kSpmLossU];
+    float4 pv[kSpmLossU], tv[kSpmLossU];
+    int q[kSpmLossU];
 #pragma unroll
-        for (int u = 0; u < kSpmLossU; ++u) {
-            q[u] = chunk * kSpmLossChunk + u * kSpmThreads + threadIdx.x;
-            if (q[u] < P.quads) {
-                pv[u] = ldg_stream(L4 + off + q[u]);
-                tv[u] = ldg_stream(T4 + off + q[u]);
-                if (c != 0) t0[u] = __ldg(T4 + off0 + q[u]);
-            }
+    for (int u = 0; u < kSpmLossU; ++u) {
+        q[u] = chunk * kSpmLossChunk + u * kSpmThreads + threadIdx.x;
+        if (q[u] < P.quads) {
+            pv[u] = ldg_stream(L4 + off + q[u]);
+            tv[u] = ldg_stream(T4 + off + q[u]);
         }
-        float acc = 0.f;
-#pragma unroll
-        for (int u = 0; u < kSpmLossU; ++u) {
-            if (q[u] >= P.quads) break;
-            const float pe[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w}, te[4] = {tv[u].x, tv[u].y, tv[u].z, tv[u].w};
-            float ge[4];
-            if (c == 0) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const bool m = te[e] > 0.0f;
-                    const float s = sigmoid_fast(pe[e]);
-                    const float d = (m ? s : s * 0.0f) - te[e];
-                    acc = fmaf(d, d, acc);
-                    ge[e] = m ? P.groot * d * ((1.0f - s) * s) : 0.0f;
-                }
-            } else {
-                const float me[4] = {t0[u].x, t0[u].y, t0[u].z, t0[u].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
-                    const bool m = me[e] > 0.0f;
-                    float th = 0.0f, pm = pe[e] != pe[e] ? pe[e] : 0.0f;    // NaN logits propagate as in the reference
-                    if (m) { th = tanhf(pe[e]); pm = th; }
-                    const float d = pm - te[e];
-                    const float ad = fabsf(d);
-                    acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-                    ge[e] = m ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
-                }
-            }
-            if (GRAD) __stcs(G4 + off + q[u], make_float4(ge[0], ge[1], ge[2], ge[3]));
-        }
-        if (c == 0) droot += (double)acc; else ddisp += (double)acc;
     }
-    droot = warp_sum(droot);
-    ddisp = warp_sum(ddisp);
+    unsigned mw[kSpmLossU];
+    if (c != 0) {
+        pdl_wait();                                             // the mask bits of spm_root_mask_kernel
+        const unsigned int* mimg = P.mask + img * P.mask_words;
+#pragma unroll
+        for (int u = 0; u < kSpmLossU; ++u) mw[u] = q[u] < P.quads ? __ldg(mimg + (q[u] >> 3)) : 0u;
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < kSpmLossU; ++u) {
+        if (q[u] >= P.quads) break;
+        const float pe[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w}, te[4] = {tv[u].x, tv[u].y, tv[u].z, tv[u].w};
+        float ge[4];
+        if (c == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool m = te[e] > 0.0f;
+                const float s = sigmoid_fast(pe[e]);
+                const float d = (m ? s : s * 0.0f) - te[e];
+                acc = fmaf(d, d, acc);
+                ge[e] = m ? P.groot * d * ((1.0f - s) * s) : 0.0f;
+            }
+        } else {
+            const unsigned nib = (mw[u] >> ((q[u] & 7) * 4)) & 15u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                // tanh only where the root mask is set; elsewhere tanh(p)*0 == 0 for every finite or infinite p
+                const bool m = (nib >> e) & 1u;
+                float th = 0.0f, pm = pe[e] != pe[e] ? pe[e] : 0.0f;    // NaN logits propagate as in the reference
+                if (m) { th = tanhf(pe[e]); pm = th; }
+                const float d = pm - te[e];
+                const float ad = fabsf(d);
+                acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+                ge[e] = m ? P.gdisp * fminf(fmaxf(d, -1.0f), 1.0f) * (1.0f - th * th) : 0.0f;
+            }
+        }
+        if (GRAD) __stcs(G4 + off + q[u], make_float4(ge[0], ge[1], ge[2], ge[3]));
+    }
+    acc = warp_sum(acc);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) { red[wid][0] = droot; red[wid][1] = ddisp; }
+    if (lane == 0) red[wid] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
+        double a = 0.0;
 #pragma unroll
-        for (int w = 0; w < kSpmThreads / 32; ++w) { a += red[w][0]; b += red[w][1]; }
-        P.partials[2 * blockIdx.x] = a;
-        P.partials[2 * blockIdx.x + 1] = b;
+        for (int w = 0; w < kSpmThreads / 32; ++w) a += (double)red[w];
+        reinterpret_cast<double2*>(P.partials)[unit] = c == 0 ? make_double2(a, 0.0) : make_double2(0.0, a);
     }
 }
 

@@ -18,7 +18,7 @@ def spm_loss_fused(logits, target, want_grad=True, lambda_root=1.0, lambda_disp=
     dlogits = torch.empty_like(x) if want_grad else None
     loss = torch.empty((), dtype=torch.float32, device=dev)
     num = torch.empty((2,), dtype=torch.float64, device=dev)
-    ws = _cabi.workspace(dev, int(lib().pose_spm_loss_workspace_bytes()))
+    ws = _cabi.workspace(dev, int(lib().pose_spm_loss_workspace_bytes(n, k, r)))
     inv_norm = 1.0 / (global_batch if global_batch is not None else n) if n > 0 else 0.0
     with torch.cuda.device(dev):
         check(lib().pose_spm_loss(ptr(x), ptr(t), ptr(dlogits), ptr(loss), ptr(num), n, k, r, float(lambda_root),

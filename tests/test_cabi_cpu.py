@@ -70,7 +70,7 @@ def test_workspace_sizes_and_cpu_tensor_rejected(pb):
     # one fp64 pair per heat map + the slice sums of the two-level reduction + its counter
     assert L.pose_sbp_fused_workspace_bytes(4096, 17) >= 4096 * 17 * 16 + 34 * 16 + 4
     assert L.pose_sbp_fused_workspace_bytes(0, 17) >= 16 + 4
-    assert L.pose_spm_loss_workspace_bytes() >= 148 * 2 * 8
+    assert L.pose_spm_loss_workspace_bytes(4, 17, 128) >= 4 * 35 * 4 * 16 + 4 * 2048
     with pytest.raises(pb.PoseB200Error):
         pb.decode_batch(torch.zeros(1, 1, 8, 8), 0.5)
     with pytest.raises(pb.PoseB200Error):
