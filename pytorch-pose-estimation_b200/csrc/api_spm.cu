@@ -139,15 +139,16 @@ int pose_spm_loss(const float* logits, const float* target, float* dlogits, floa
                   int K, int R, float lambda_root, float lambda_disp, double inv_norm, int write_grad, void* workspace,
                   unsigned long long workspace_bytes, pose_stream_t stream) {
     if (N < 0 || K <= 0 || R <= 0 || R % 4 != 0) return fail(POSE_EINVAL, "spm_loss: bad shape (R must be a multiple of 4)");
-    if (!logits || !target || (write_grad && !dlogits) || (!loss_out && !loss_num_out)) return fail(POSE_EINVAL, "spm_loss: NULL pointer");
-    if (!aligned16(logits) || !aligned16(target) || (write_grad && !aligned16(dlogits))) return fail(POSE_EALIGN, "spm_loss: tensors must be 16-byte aligned");
+    if (!loss_out && !loss_num_out) return fail(POSE_EINVAL, "spm_loss: no loss output");
     if (!workspace || workspace_bytes < pose_spm_loss_workspace_bytes(N, K, R) || !aligned16(workspace))
         return fail(POSE_EWORKSPACE, "spm_loss: workspace too small / unaligned (%llu bytes needed)", pose_spm_loss_workspace_bytes(N, K, R));
+    if (N == 0)    // an empty batch (its tensors may have no storage at all) reduces zero pairs: loss 0
+        return pose_loss_reduce((const double*)workspace, 0, 2ll, (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out, stream);
+    if (!logits || !target || (write_grad && !dlogits)) return fail(POSE_EINVAL, "spm_loss: NULL pointer");
+    if (!aligned16(logits) || !aligned16(target) || (write_grad && !aligned16(dlogits))) return fail(POSE_EALIGN, "spm_loss: tensors must be 16-byte aligned");
     if (write_grad && dlogits == logits) return fail(POSE_EINVAL, "spm_loss: dlogits must not alias logits");
     if (N > 65535 || 1 + 2 * K > 65535) return fail(POSE_EINVAL, "spm_loss: N=%d / K=%d exceed the grid (65535 images per call)", N, K);
     cudaStream_t st = (cudaStream_t)stream;
-    if (N == 0)    // an empty batch reduces zero pairs: loss 0
-        return pose_loss_reduce((const double*)workspace, 0, 2ll, (double)lambda_root, (double)lambda_disp, inv_norm, loss_out, loss_num_out, stream);
     const SpmLossWs w = spm_loss_ws_layout(workspace, N, K, R);
     pose::SpmLossParams P;
     P.logits = logits; P.target = target; P.dlogits = dlogits; P.partials = w.partials; P.mask = w.mask; P.ticket = w.ticket;

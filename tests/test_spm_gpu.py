@@ -84,6 +84,30 @@ def test_generator_dropins(pb, dev):
         assert np.array_equal(np.concatenate([hm, disp], axis=0), g["target"][i])
 
 
+@pytest.mark.parametrize("res,k,n", [(20, 2, 3), (36, 1, 5), (132, 3, 2), (256, 2, 1)])
+def test_dense_loss_odd_sizes_and_mask_bits(pb, dev, res, k, n):
+    """Dense-target loss at map sizes whose planes are not whole 16 KB units / whose quads do not fill the mask words: the root
+    mask travels as bits (spm_root_mask_kernel); target values <= 0, NaN and -0.0 in the root plane are mask 0 like the
+    reference's torch.where(t > 0); loss / gradients against the fp64 closed form, with and without dlogits; empty batch."""
+    rng = np.random.default_rng(res)
+    people = []
+    for p in rng.integers(0, 5, size=n):
+        c = rng.integers(0, res, size=(p, 1, 2), dtype=np.int64)
+        j = np.clip(c + rng.integers(-9, 10, size=(p, k, 2), dtype=np.int64), 0, res - 1)
+        people.append((c, j))
+    target = torch.from_numpy(np.stack([po.spm_render(c, j, res, 1) for c, j in people]))
+    target[0, 0, 0, :3] = torch.tensor([-0.0, -1.0, 1e-30])                     # mask 0, 0, 1
+    x = torch.randn(target.shape, generator=torch.Generator().manual_seed(res)) * 2
+    l64, g64 = po.spm_loss_closed_form_f64(x, target)
+    r = pb.spm_loss_fused(x.to(dev), target.to(dev))
+    assert close(r["loss"].item(), float(l64), REL) and allclose(r["dlogits"], g64, REL, atol_frac=1.0)
+    r0 = pb.spm_loss_fused(x.to(dev), target.to(dev), want_grad=False)
+    assert r0["dlogits"] is None and r0["loss"].item() == r["loss"].item()
+    assert torch.equal(r["loss_num"], r0["loss_num"])
+    e = pb.spm_loss_fused(torch.zeros((0, 1 + 2 * k, res, res), device=dev), torch.zeros((0, 1 + 2 * k, res, res), device=dev))
+    assert e["loss"].item() == 0.0
+
+
 @pytest.mark.parametrize("name,n", [("small", 6), ("coco", 4)])
 def test_loss_and_grad(pb, dev, name, n):
     g = load_golden("spm_" + name)
