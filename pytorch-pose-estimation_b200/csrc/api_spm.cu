@@ -264,6 +264,11 @@ int pose_spm_decode(const float* x, float* roots, float* kps, int* counts, int* 
         while (s > 0 && std::sqrt((double)(s - 1)) > dist_threshold) --s;
         while (!(std::sqrt((double)s) > dist_threshold)) ++s;
         P.s_min = s;
+        // the joint test of get_spm_keypoints, sqrt_fp64(fp32 q) < dist_thr, as an fp32 bound (sqrt is monotone and correctly rounded)
+        float ql = (float)(dist_threshold * dist_threshold);
+        while (ql > 0.0f && !(std::sqrt((double)std::nextafterf(ql, -INFINITY)) < dist_threshold)) ql = std::nextafterf(ql, -INFINITY);
+        while (std::sqrt((double)ql) < dist_threshold) ql = std::nextafterf(ql, INFINITY);
+        P.q_lt = ql;
     }
     if (threads == 512) pose::spm_decode_kernel<512><<<N, 512, smem, (cudaStream_t)stream>>>(P);
     else if (threads == 256) pose::spm_decode_kernel<256><<<N, 256, smem, (cudaStream_t)stream>>>(P);

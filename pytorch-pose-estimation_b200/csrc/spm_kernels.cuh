@@ -818,13 +818,15 @@ struct SpmDecodeParams {
     float zf;                    // fp32(sqrt(2 R^2))
     float input_size;            // DecodeSPM.input_size
     long long s_min;             // smallest integer s with sqrt((double)s) > dist_thr: the radius test on integer offsets
+    float q_lt;                  // smallest fp32 q with sqrt((double)q) >= dist_thr: the joint test `sqrt_fp64(q) < dist_thr` is q < q_lt
 };
 
 // One body joint of one root (get_spm_keypoints utils/spm_utils.py:187-197 + the rescale at :247-248):
 //   kx = disp[2k][y,x] * fp32(z) + x   (fp32 multiply, then fp32 add: two roundings, no FMA)
 //   d  = sqrt_fp64( fp32((x-kx)^2 + (y-ky)^2) );  d < dist_thr -> (0,0,0) else (kx, ky, conf) * num / den
+// (sqrt_fp64 of an fp32 is monotone, so the host turns `sqrt((double)q) < dist_thr` into the fp32 bound q_lt: no DSQRT per joint)
 __device__ __forceinline__ void spm_joint(const float* __restrict__ disp, long long plane, int pix, int rx, int ry, float conf,
-                                          int k, int apply_act, float zf, double dist_thr, float num, float den, float* o) {
+                                          int k, int apply_act, float zf, float q_lt, float num, float den, float* o) {
     float dx = __ldg(disp + (2 * k) * plane + pix);
     float dy = __ldg(disp + (2 * k + 1) * plane + pix);
     if (apply_act) { dx = tanhf(dx); dy = tanhf(dy); }
@@ -833,7 +835,7 @@ __device__ __forceinline__ void spm_joint(const float* __restrict__ disp, long l
     const float ky = __fadd_rn(__fmul_rn(dy, zf), fy);
     const float ex = __fsub_rn(fx, kx), ey = __fsub_rn(fy, ky);
     const float q = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
-    if (sqrt((double)q) < dist_thr) {
+    if (q < q_lt) {
         o[0] = 0.f; o[1] = 0.f; o[2] = 0.f;
     } else {
         o[0] = __fdiv_rn(__fmul_rn(kx, num), den);
@@ -942,7 +944,7 @@ template <int kSpmDecThreads>
 __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodeParams P) {
     extern __shared__ __align__(16) unsigned int sup_bits[];   // dense fallback only: R*R bits, 1 = suppressed
     __shared__ unsigned int s_cand[kSpmCandCap];               // (y << 16) | x  == row-major order for ties
-    __shared__ float s_val[kSpmCandCap];                       // activated confidence, -inf once struck out
+    __shared__ __align__(8) float s_val[kSpmCandCap];           // activated confidence, -inf once struck out
     __shared__ int s_root_i[kSpmRootCap];
     __shared__ float s_root_c[kSpmRootCap];
     __shared__ float s_v[kSpmDecThreads / 32];
@@ -1032,7 +1034,7 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
                 roots[slot * 3 + 1] = __fdiv_rn(__fmul_rn((float)ry, P.input_size), (float)P.R);
                 roots[slot * 3 + 2] = best;
             } else {
-                spm_joint(base + plane, plane, ry * P.R + rx, rx, ry, best, k, P.apply_act, P.zf, P.dist_thr, P.input_size, (float)P.R,
+                spm_joint(base + plane, plane, ry * P.R + rx, rx, ry, best, k, P.apply_act, P.zf, P.q_lt, P.input_size, (float)P.R,
                           kps + ((long long)slot * P.K + k) * 3);
             }
         }
@@ -1065,45 +1067,62 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
         }
     };
 
-    if (ncand <= 64) {
+    if (ncand <= 64 && P.R <= 32768) {
         // The usual case (a few dozen candidates; config 4: 23 on average, 40 at most): the greedy loop "best remaining, strike its
         // neighbourhood" costs ~1000 cycles per ROOT as a chain of warp reductions (measured with clock64 stamps: 5 700 cycles per
         // image, 11 600 for an 8-person image -- more than the 64 KB stream of the plane at N = 256).  Here one warp does the same
         // selection in closed form, two candidates per lane:
-        //   1. rank of every candidate under (value desc, row-major index asc) by comparison with all others (broadcast LDS);
-        //   2. candidates re-read in rank order; for each, the 64-bit mask of the ranks it would strike (same integer radius test);
+        //   1. rank of every candidate under (value desc, row-major index asc) by comparison with all others -- ONE unsigned 64-bit
+        //      comparison of (ordered value bits, ~index) keys per pair (broadcast LDS.64);
+        //   2. candidates re-read in rank order; for each, the 64-bit mask of the ranks it would strike (the same integer radius
+        //      test, in 32 bits: R <= 32768 keeps dx^2 + dy^2 below 2^31);
         //   3. the greedy walk over a warp-uniform `alive` mask: lowest set bit = next root, alive &= ~its mask -- four shuffles and
         //      three logic operations per root, no reduction.
-        // Same picks in the same order as the loop below.
+        // Same picks in the same order as the loop below.  A single warp runs this, so its time is its instruction count times the
+        // issue latency: the 64-bit keys and 32-bit distances took the two loops from 12 + 30 to 7 + 14 instructions per candidate.
         if (wid == 0) {
             unsigned int* s_skey = reinterpret_cast<unsigned int*>(s_root_i) + kSpmRootCap / 2;      // scratch: upper half of the root record
             float* s_sval = s_root_c + kSpmRootCap / 2;                                             // (a warp-list image records <= 64 roots)
+            unsigned long long* s_k64 = reinterpret_cast<unsigned long long*>(s_val + kSpmCandCap / 2);   // scratch: 64 keys behind the <= 64 listed values
             const int n = ncand;
             const int i0 = lane, i1 = lane + 32;
             const float v0 = i0 < n ? s_val[i0] : -INFINITY, v1 = i1 < n ? s_val[i1] : -INFINITY;
             const unsigned k0 = i0 < n ? s_cand[i0] : 0xffffffffu, k1 = i1 < n ? s_cand[i1] : 0xffffffffu;
+            // larger key = better candidate: value first ((v + 0) folds -0 into +0; struck-out entries are -inf), then the SMALLER (y, x)
+            const unsigned long long key0 = ((unsigned long long)float_key(v0 + 0.0f) << 32) | (unsigned long long)(0xffffffffu - k0);
+            const unsigned long long key1 = ((unsigned long long)float_key(v1 + 0.0f) << 32) | (unsigned long long)(0xffffffffu - k1);
+            if (i0 < n) s_k64[i0] = key0;
+            if (i1 < n) s_k64[i1] = key1;
+            __syncwarp();
             int r0 = 0, r1 = 0;
+#pragma unroll 4
             for (int i = 0; i < n; ++i) {
-                const float vi = s_val[i];
-                const unsigned ki = s_cand[i];
-                r0 += (vi > v0 || (vi == v0 && ki < k0)) ? 1 : 0;
-                r1 += (vi > v1 || (vi == v1 && ki < k1)) ? 1 : 0;
+                const unsigned long long ki = s_k64[i];
+                r0 += ki > key0 ? 1 : 0;
+                r1 += ki > key1 ? 1 : 0;
             }
             if (i0 < n) { s_skey[r0] = k0; s_sval[r0] = v0; }
             if (i1 < n) { s_skey[r1] = k1; s_sval[r1] = v1; }
             __syncwarp();
             const unsigned sk0 = i0 < n ? s_skey[i0] : 0u, sk1 = i1 < n ? s_skey[i1] : 0u;         // lane owns ranks `lane` and `lane + 32`
             const float sv0 = i0 < n ? s_sval[i0] : -INFINITY, sv1 = i1 < n ? s_sval[i1] : -INFINITY;
-            unsigned long long m0 = 0ull, m1 = 0ull;
             const int y0 = (int)(sk0 >> 16), x0 = (int)(sk0 & 0xffffu), y1 = (int)(sk1 >> 16), x1 = (int)(sk1 & 0xffffu);
-            for (int q = 0; q < n; ++q) {
+            const unsigned smin = (unsigned)min(P.s_min, 0xffffffffll);
+            unsigned m0lo = 0u, m0hi = 0u, m1lo = 0u, m1hi = 0u;
+            auto strike = [&](int q, unsigned& ma, unsigned& mb) {
                 const unsigned kq = s_skey[q];
                 const int yq = (int)(kq >> 16), xq = (int)(kq & 0xffffu);
-                const long long a = (long long)(yq - y0) * (yq - y0) + (long long)(xq - x0) * (xq - x0);
-                const long long b = (long long)(yq - y1) * (yq - y1) + (long long)(xq - x1) * (xq - x1);
-                if (a < P.s_min) m0 |= 1ull << q;
-                if (b < P.s_min) m1 |= 1ull << q;
-            }
+                const unsigned a = (unsigned)((yq - y0) * (yq - y0) + (xq - x0) * (xq - x0));
+                const unsigned b = (unsigned)((yq - y1) * (yq - y1) + (xq - x1) * (xq - x1));
+                const unsigned bit = 1u << (q & 31);
+                if (a < smin) ma |= bit;
+                if (b < smin) mb |= bit;
+            };
+            const int nlo = min(n, 32);
+#pragma unroll 4
+            for (int q = 0; q < nlo; ++q) strike(q, m0lo, m1lo);
+#pragma unroll 4
+            for (int q = 32; q < n; ++q) strike(q, m0hi, m1hi);
             __syncwarp();                                                   // the scratch is read; the record may be written
             unsigned long long alive = (unsigned long long)__ballot_sync(FULL_MASK, sv0 > -INFINITY) |
                                        ((unsigned long long)__ballot_sync(FULL_MASK, sv1 > -INFINITY) << 32);
@@ -1112,8 +1131,7 @@ __global__ void __launch_bounds__(kSpmDecThreads) spm_decode_kernel(SpmDecodePar
                 const bool hi = p >= 32;
                 const unsigned key = __shfl_sync(FULL_MASK, hi ? sk1 : sk0, src);
                 const float val = __shfl_sync(FULL_MASK, hi ? sv1 : sv0, src);
-                const unsigned long long mm = hi ? m1 : m0;
-                const unsigned mlo = __shfl_sync(FULL_MASK, (unsigned)mm, src), mhi = __shfl_sync(FULL_MASK, (unsigned)(mm >> 32), src);
+                const unsigned mlo = __shfl_sync(FULL_MASK, hi ? m1lo : m0lo, src), mhi = __shfl_sync(FULL_MASK, hi ? m1hi : m0hi, src);
                 if (lane == 0 && found < P.Pmax) { s_root_i[found] = (int)key; s_root_c[found] = val; }
                 alive &= ~(((unsigned long long)mhi << 32) | (unsigned long long)mlo);
                 alive &= ~(1ull << p);
